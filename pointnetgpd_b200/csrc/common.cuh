@@ -1,0 +1,144 @@
+// common.cuh -- constants, workspace carving, BatchNorm bookkeeping and small reduction kernels
+// shared by the tower and head code.
+#pragma once
+#include "platform.h"
+#include <algorithm>
+#include <cmath>
+#include "../../include/pgpd.h"
+
+namespace pgpd {
+
+constexpr int C1 = 64, C2 = 128, C3 = 1024;   // tower widths (pointnet.py:12-14,127-129)
+constexpr int H1 = 512, H2 = 256;             // head widths  (pointnet.py:16-18,182-184)
+constexpr float BN_EPS = 1e-5f;               // nn.BatchNorm1d defaults (pointnet.py:21-25)
+constexpr float BN_MOM = 0.1f;
+
+// ---- workspace carving: the same code measures (base == nullptr) and assigns ------------------
+struct Carver {
+    char* base;
+    size_t off;
+    explicit Carver(void* b) : base(reinterpret_cast<char*>(b)), off(0) {}
+    template <class T> T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+// per-layer BatchNorm state kept between forward and backward
+struct BnState {
+    float* mean;    // mean of u = W a (bias-free pre-activation); the BN mean is mean + bias
+    float* rstd;    // 1/sqrt(var + eps)
+    float* scale;   // gamma * rstd
+    float* shift;   // train: beta - scale*mean ; eval: beta + scale*(bias - running_mean)
+    void carve(Carver& c, int C) {
+        mean = c.take<float>(C); rstd = c.take<float>(C); scale = c.take<float>(C); shift = c.take<float>(C);
+    }
+};
+
+// ---- ordered 32-bit encoding of floats (unsigned compare == float compare) ---------------------
+__device__ __forceinline__ unsigned ord_encode(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_decode(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
+
+// ---- BatchNorm finalisation ---------------------------------------------------------------------
+// Given the batch mean of the bias-free pre-activation and its biased variance, write the folded
+// affine and update the running statistics exactly as nn.BatchNorm1d does in training mode
+// (momentum 0.1, unbiased running variance).
+__device__ __forceinline__ void bn_finalize_train(int c, double mean_u, double var, double count,
+                                                  const float* bias, pgpd_bn bn, BnState st) {
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
+    float sc = bn.gamma[c] * rstd;
+    st.mean[c] = (float)mean_u;
+    st.rstd[c] = rstd;
+    st.scale[c] = sc;
+    st.shift[c] = bn.beta[c] - sc * (float)mean_u;
+    float mu = (float)mean_u + (bias ? bias[c] : 0.f);
+    float unbiased = (float)(var * (count / (count - 1.0)));
+    bn.running_mean[c] = (1.f - BN_MOM) * bn.running_mean[c] + BN_MOM * mu;
+    bn.running_var[c] = (1.f - BN_MOM) * bn.running_var[c] + BN_MOM * unbiased;
+    if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
+}
+
+// eval mode: y = gamma*(u + b - rm)/sqrt(rv+eps) + beta
+__global__ void k_bn_eval_affine(int C, const float* bias, pgpd_bn bn, BnState st) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C) return;
+    float rstd = 1.0f / sqrtf(bn.running_var[c] + BN_EPS);
+    float sc = bn.gamma[c] * rstd;
+    float b = bias ? bias[c] : 0.f;
+    st.mean[c] = bn.running_mean[c] - b;
+    st.rstd[c] = rstd;
+    st.scale[c] = sc;
+    st.shift[c] = bn.beta[c] + sc * (b - bn.running_mean[c]);
+}
+
+// css partials (float, [nblk][C]) -> variance -> finalize (train)
+__global__ void k_bn_finalize_from_css(const float* part, int nblk, int C, const float* mean_u, double count,
+                                       const float* bias, pgpd_bn bn, BnState st) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += (double)part[(size_t)i * C + c];
+    bn_finalize_train(c, (double)mean_u[c], s / count, count, bias, bn, st);
+}
+
+// out[c] = sum_i part[i][c]  (double partials, fixed order)
+__global__ void k_reduce_d(const double* part, int nblk, int C, double* out) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += part[(size_t)i * C + c];
+    out[c] = s;
+}
+
+// out[c] = (float) sum_i part[i][c]  (float partials, double accumulation, fixed order)
+__global__ void k_reduce_f(const float* part, int nblk, int C, float* out) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += (double)part[(size_t)i * C + c];
+    out[c] = (float)s;
+}
+
+// mean_out[r] = (sum_k W[r][k] * vsum[k]) * inv   in double
+__global__ void k_matvec_mean(const float* W, int rows, int cols, const double* vsum, double inv, float* mean_out) {
+    int r = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (r >= rows) return;
+    double s = 0.0;
+    for (int k = 0; k < cols; ++k) s += (double)W[(size_t)r * cols + k] * vsum[k];
+    mean_out[r] = (float)(s * inv);
+}
+
+__global__ void k_fill(float* p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// BatchNorm backward bookkeeping from [nblk][2][C] float partials of (sum dz, sum dz*yhat):
+//   dgamma = sum dz*yhat ; dbeta = sum dz ; m1 = dbeta/count ; m2 = dgamma/count
+__global__ void k_bn_bwd_finalize(const float* part, int nblk, int C, double count,
+                                  float* dgamma, float* dbeta, float* m1, float* m2) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < nblk; ++i) {
+        s1 += (double)part[((size_t)i * 2 + 0) * C + c];
+        s2 += (double)part[((size_t)i * 2 + 1) * C + c];
+    }
+    dgamma[c] = (float)s2;
+    dbeta[c] = (float)s1;
+    m1[c] = (float)(s1 / count);
+    m2[c] = (float)(s2 / count);
+}
+
+inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
+
+}  // namespace pgpd

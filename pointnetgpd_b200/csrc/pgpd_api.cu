@@ -1,0 +1,254 @@
+// pgpd_api.cu -- extern "C" entry points of libpgpd.so (see include/pgpd.h) and the model-level
+// orchestration: STN3d (tower + regression head), PointNetfeat (+ transform + trunk tower) and
+// PointNetCls (+ classifier head + log_softmax), forward and backward.
+#include "common.cuh"
+#include "tower.cuh"
+#include "head.cuh"
+#ifndef PGPD_EMU
+#include "tc_dispatch.cuh"
+#endif
+
+#include <string>
+
+namespace pgpd {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* msg) {
+    g_err = msg;
+    return code;
+}
+
+static int check_cuda(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_err = std::string(where) + ": " + cudaGetErrorString(e);
+        return PGPD_E_CUDA;
+    }
+    return PGPD_OK;
+}
+
+struct ModelWs {
+    TowerWs stn_t, trunk_t;
+    HeadWs stn_h, cls_h;
+    float* g_stn;    // [B][1024] pooled feature of the T-Net tower
+    float* G;        // [B][1024] global feature (trunk)
+    float* logp;     // [B][k]
+    float* dG;       // [B][1024]
+    float* dg_stn;   // [B][1024]
+    float* dT;       // [B][9]
+    size_t bytes;
+};
+
+static void plan_model(void* base, int what, int B, int N, int k, int flags, ModelWs& w) {
+    Carver c(base);
+    const bool save = (flags & PGPD_F_SAVE) != 0;
+    plan_tower(c, w.stn_t, B, N);
+    if (what >= PGPD_FEAT) {
+        if (save) plan_tower(c, w.trunk_t, B, N);
+        else static_cast<TowerKeep&>(w.trunk_t) = static_cast<TowerKeep&>(w.stn_t);   // inference: reuse
+    }
+    plan_tower_scratch(c, w.stn_t, B, N, save);
+    static_cast<TowerScratch&>(w.trunk_t) = static_cast<TowerScratch&>(w.stn_t);
+    plan_head(c, w.stn_h, B, 9, save);
+    w.g_stn = c.take<float>((size_t)B * C3);
+    w.G = c.take<float>((size_t)B * C3);
+    w.logp = nullptr;
+    if (what == PGPD_CLS) {
+        plan_head(c, w.cls_h, B, k, save);
+        w.logp = c.take<float>((size_t)B * k);
+    }
+    if (save) {
+        w.dG = c.take<float>((size_t)B * C3);
+        w.dg_stn = c.take<float>((size_t)B * C3);
+        w.dT = c.take<float>((size_t)B * 9);
+    }
+    w.bytes = (c.off + 255) & ~(size_t)255;
+}
+
+static int check_common(int what, const void* m, const float* x, int B, int N, int k, const void* ws, size_t ws_bytes, size_t need) {
+    if (what != PGPD_STN && what != PGPD_FEAT && what != PGPD_CLS) return fail(PGPD_E_ARG, "what must be PGPD_STN, PGPD_FEAT or PGPD_CLS");
+    if (!m || !x) return fail(PGPD_E_ARG, "null model or input pointer");
+    if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
+    if (what == PGPD_CLS && (k < 1 || k > 1024)) return fail(PGPD_E_ARG, "k must be in [1,1024]");
+    if ((long long)B * N > 0x7fffffffLL / 128) return fail(PGPD_E_ARG, "B*N too large for this build (B*N*128 must fit in int32)");
+    if (!ws || ((uintptr_t)ws & 255)) return fail(PGPD_E_WORKSPACE, "workspace is null or not 256-byte aligned");
+    if (ws_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small (see pgpd_workspace_bytes)");
+    return PGPD_OK;
+}
+
+__global__ void k_add_opt(const float* a, const float* b, float* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+static void run_tower_fwd(const TowerArgs& a, TowerWs& w, float* pooled, int flags) {
+#ifndef PGPD_EMU
+    if (!(flags & PGPD_F_SIMT) && tc::tower_forward_tc(a, w, pooled)) return;
+#endif
+    (void)flags;
+    tower_forward(a, w, pooled);
+}
+
+static void run_tower_bwd(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad& g, const float* dpooled, float* dtrans, int flags) {
+#ifndef PGPD_EMU
+    if (!(flags & PGPD_F_SIMT) && tc::tower_backward_tc(a, w, g, dpooled, dtrans)) return;
+#endif
+    (void)flags;
+    tower_backward(a, w, g, dpooled, dtrans);
+}
+
+}  // namespace pgpd
+
+using namespace pgpd;
+
+extern "C" {
+
+int pgpd_version(void) { return PGPD_VERSION; }
+
+const char* pgpd_last_error(void) { return g_err.c_str(); }
+
+int pgpd_has_tensor_core_path(void) {
+#ifdef PGPD_EMU
+    return 0;
+#else
+    return tc::available() ? 1 : 0;
+#endif
+}
+
+size_t pgpd_workspace_bytes(int what, int B, int N, int k, int flags) {
+    if (B < 1 || N < 1) return 0;
+    ModelWs w;
+    plan_model(nullptr, what, B, N, k < 1 ? 1 : k, flags, w);
+    return w.bytes;
+}
+
+int pgpd_forward(int what, const pgpd_model* m, const float* x, int B, int N, int k, int flags,
+                 float* out, float* trans, void* workspace, size_t workspace_bytes, void* stream) {
+    ModelWs w;
+    plan_model(nullptr, what, B < 1 ? 1 : B, N < 1 ? 1 : N, k < 1 ? 1 : k, flags, w);
+    int rc = check_common(what, m, x, B, N, k, workspace, workspace_bytes, w.bytes);
+    if (rc) return rc;
+    if (!trans) return fail(PGPD_E_ARG, "trans output pointer is null");
+    if (what != PGPD_STN && !out) return fail(PGPD_E_ARG, "out pointer is null");
+    const bool train = (flags & PGPD_F_TRAIN) != 0;
+    if (train && B == 1)
+        return fail(PGPD_E_BATCH1, "Expected more than 1 value per channel when training (BatchNorm over a batch of 1)");
+    plan_model(workspace, what, B, N, k, flags, w);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool save = (flags & PGPD_F_SAVE) != 0;
+
+    // ---- STN3d (pointnet.py:27-45)
+    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, train, save, s};
+    run_tower_fwd(ta, w.stn_t, w.g_stn, flags);
+    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, train, true, s};
+    head_forward(ha, w.stn_h);
+    cudaMemcpyAsync(trans, w.stn_h.out, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (what >= PGPD_FEAT) {
+        // ---- transform + trunk tower (pointnet.py:140-149)
+        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, train, save, s};
+        run_tower_fwd(tb, w.trunk_t, w.G, flags);
+        if (what == PGPD_FEAT) {
+            cudaMemcpyAsync(out, w.G, (size_t)B * C3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        } else {
+            // ---- classifier head (pointnet.py:191-194)
+            HeadArgs hb{&m->cls_head, w.G, B, k, train, false, s};
+            head_forward(hb, w.cls_h);
+            launch(k_log_softmax, grid1d(B, 128), dim3(128), 0, s, (const float*)w.cls_h.out, B, k, w.logp);
+            cudaMemcpyAsync(out, w.logp, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        }
+    }
+    return check_cuda("pgpd_forward");
+}
+
+int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const float* x,
+                  int B, int N, int k, int flags, const float* dout, const float* dtrans,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    ModelWs w;
+    flags |= PGPD_F_SAVE;
+    plan_model(nullptr, what, B < 1 ? 1 : B, N < 1 ? 1 : N, k < 1 ? 1 : k, flags, w);
+    int rc = check_common(what, m, x, B, N, k, workspace, workspace_bytes, w.bytes);
+    if (rc) return rc;
+    if (!g) return fail(PGPD_E_ARG, "null gradient struct");
+    if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
+    if (what != PGPD_STN && !dout) return fail(PGPD_E_ARG, "dout is null");
+    if (what == PGPD_STN && !dtrans) return fail(PGPD_E_ARG, "dtrans is null");
+    if (B == 1) return fail(PGPD_E_BATCH1, "batch of 1 in training mode");
+    plan_model(workspace, what, B, N, k, flags, w);
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const float* dT_total = dtrans;   // gradient reaching the STN output
+    if (what >= PGPD_FEAT) {
+        const float* dG = dout;
+        if (what == PGPD_CLS) {
+            launch(k_log_softmax_bwd, grid1d(B, 128), dim3(128), 0, s, (const float*)w.logp, dout, B, k, w.cls_h.dO);
+            HeadArgs hb{&m->cls_head, w.G, B, k, true, false, s};
+            head_backward(hb, w.cls_h, g->cls_head, w.dG);
+            dG = w.dG;
+        }
+        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, true, true, s};
+        run_tower_bwd(tb, w.trunk_t, g->trunk, dG, w.dT, flags);
+        launch(k_add_opt, grid1d((size_t)B * 9, 128), dim3(128), 0, s, (const float*)w.dT, dtrans, w.stn_h.dO, (size_t)B * 9);
+    } else {
+        cudaMemcpyAsync(w.stn_h.dO, dT_total, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    }
+    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, true, true, s};
+    head_backward(ha, w.stn_h, g->stn_head, w.dg_stn);
+    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, true, true, s};
+    run_tower_bwd(ta, w.stn_t, g->stn_tower, w.dg_stn, nullptr, flags);
+    return check_cuda("pgpd_backward");
+}
+
+// ---- tower-level entry points -------------------------------------------------------------------------
+static void plan_tower_only(void* base, int B, int N, int flags, TowerWs& w, size_t& bytes) {
+    Carver c(base);
+    plan_tower(c, w, B, N);
+    plan_tower_scratch(c, w, B, N, (flags & PGPD_F_SAVE) != 0);
+    bytes = (c.off + 255) & ~(size_t)255;
+}
+
+size_t pgpd_tower_workspace_bytes(int B, int N, int flags) {
+    if (B < 1 || N < 1) return 0;
+    TowerWs w; size_t bytes;
+    plan_tower_only(nullptr, B, N, flags, w, bytes);
+    return bytes;
+}
+
+int pgpd_tower_forward(const pgpd_tower* t, const float* x, const float* trans, int B, int N,
+                       int relu_last, int flags, float* pooled,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!t || !x || !pooled) return fail(PGPD_E_ARG, "null pointer");
+    if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
+    if ((long long)B * N > 0x7fffffffLL / 128) return fail(PGPD_E_ARG, "B*N too large");
+    const bool train = (flags & PGPD_F_TRAIN) != 0;
+    if (train && (long long)B * N == 1) return fail(PGPD_E_BATCH1, "one value per channel in training mode");
+    TowerWs w; size_t need;
+    plan_tower_only(nullptr, B, N, flags, w, need);
+    if (!workspace || ((uintptr_t)workspace & 255)) return fail(PGPD_E_WORKSPACE, "workspace null or misaligned");
+    if (workspace_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small");
+    plan_tower_only(workspace, B, N, flags, w, need);
+    TowerArgs a{t, x, trans, B, N, relu_last != 0, train, (flags & PGPD_F_SAVE) != 0, (cudaStream_t)stream};
+    run_tower_fwd(a, w, pooled, flags);
+    return check_cuda("pgpd_tower_forward");
+}
+
+int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const float* x,
+                        const float* trans, int B, int N, int relu_last, int flags,
+                        const float* dpooled, float* dtrans_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!t || !g || !x || !dpooled) return fail(PGPD_E_ARG, "null pointer");
+    if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
+    if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
+    if (trans && !dtrans_out) return fail(PGPD_E_ARG, "dtrans_out is null but trans is given");
+    flags |= PGPD_F_SAVE;
+    TowerWs w; size_t need;
+    plan_tower_only(nullptr, B, N, flags, w, need);
+    if (!workspace || ((uintptr_t)workspace & 255)) return fail(PGPD_E_WORKSPACE, "workspace null or misaligned");
+    if (workspace_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small");
+    plan_tower_only(workspace, B, N, flags, w, need);
+    TowerArgs a{t, x, trans, B, N, relu_last != 0, true, true, (cudaStream_t)stream};
+    run_tower_bwd(a, w, *g, dpooled, dtrans_out, flags);
+    return check_cuda("pgpd_tower_backward");
+}
+
+}  // extern "C"

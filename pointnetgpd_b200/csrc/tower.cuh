@@ -1,0 +1,877 @@
+// tower.cuh -- the per-point shared-MLP tower 3->64->128->1024 + global max-pool, forward and
+// backward, CUDA-core (fp32) kernels + host orchestration.
+//
+// Reference semantics: STN3d.forward lines 29-33 (relu_last) and PointNetfeat.forward lines
+// 140-149 (transform, no ReLU before the pool) of PointNetGPD/model/pointnet.py.
+//
+// Design (DESIGN.md has the derivations):
+//  * the 1024-wide activation is NEVER written to memory.  BatchNorm3(+ReLU) is monotone per
+//    channel, so max_n post(u3) = post(max_n sgn*u3): the GEMM epilogue keeps a per-(cloud,
+//    channel) running (max, first arg-max) of the raw pre-activation and BN3 is applied to the
+//    pooled [B,1024] values only;
+//  * train-mode batch statistics are exact two-pass: the mean of every pre-activation is linear in
+//    the mean of its input (mean(W a) = W mean(a)), so it is known BEFORE the GEMM runs and the
+//    epilogue accumulates centred squares;
+//  * the 64- and 128-wide activations (a1, u2) are kept in HBM (768 B/point) for the backward;
+//  * the layer-3 backward never forms the dense 1024-wide gradient: with the Gram matrix of a2 the
+//    dense BatchNorm terms collapse to 128x128 algebra plus a sparse scatter of the <=1024
+//    arg-max rows per cloud ("layer-3 backward collapse").
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace pgpd {
+
+// ================================================================================================
+// workspace
+// ================================================================================================
+struct TowerKeep {
+    // ---- kept from forward to backward -------------------------------------------------------
+    float* A1;        // [M][64]   a1 = relu(bn1(conv1(x')))
+    float* Y2;        // [M][128]  u2 = W2 a1 (bias-free pre-activation of layer 2)
+    float* uext;      // [B][1024] raw u3 at the arg-max (sign restored)
+    int* idx;         // [B][1024] arg-max point index within the cloud
+    BnState bn[3];
+    float* sgn;       // [1024] +1 / -1 : sign of gamma3 (max vs min selection)
+    double* S1;       // [128]  sum over points of a2
+};
+
+struct TowerScratch {
+    double* moments;  // [B][9]
+    double* dpart;    // double partials, max(nb_a1*64, nb_a2*128)
+    double* dsum;     // [128]
+    float* fpart;     // float partials: max over users (see plan_tower_scratch)
+    unsigned long long* keys;  // [B][1024]
+    // backward scratch
+    float* coef;      // [B][1024]
+    float* dvec;      // [1024]
+    float* evec;      // [1024]
+    float* gram;      // [128*128]
+    float* WG;        // [1024*128]
+    float* Q;         // [128*128]
+    float* uvec;      // [128]
+    float* da2s;      // [B*1024][128] compact rows of the sparse part of d a2
+    int* slot;        // [M]  row in da2s or -1
+    float* DZ2;       // [M][128]
+    float* DZ1;       // [M][64]
+    float* m1_2; float* m2_2;   // [128]
+    float* m1_1; float* m2_1;   // [64]
+    // sizes
+    int nb_a1, nb_a2, nb_l2, nb_gram, nb_dw2, tiles_per_cloud;
+    size_t fpart_elems;
+};
+
+struct TowerWs : TowerKeep, TowerScratch {};
+
+constexpr int GRAM_CHUNK = 1024;   // points per split-K block of the Gram GEMM
+constexpr int DW2_CHUNK = 2048;    // points per split-K block of the dW2 GEMM
+
+inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
+    const size_t M = (size_t)B * N;
+    w.A1 = c.take<float>(M * C1);
+    w.Y2 = c.take<float>(M * C2);
+    w.uext = c.take<float>((size_t)B * C3);
+    w.idx = c.take<int>((size_t)B * C3);
+    w.bn[0].carve(c, C1); w.bn[1].carve(c, C2); w.bn[2].carve(c, C3);
+    w.sgn = c.take<float>(C3);
+    w.S1 = c.take<double>(C2);
+}
+
+inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool backward) {
+    const size_t M = (size_t)B * N;
+    w.tiles_per_cloud = idiv_up(N, 128);
+    w.nb_a1 = (int)std::min<size_t>(2048, (M + 63) / 64);
+    w.nb_a2 = (int)std::min<size_t>(2048, (M + 63) / 64);
+    w.nb_l2 = (int)((M + 127) / 128);
+    w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
+    w.nb_dw2 = (int)((M + DW2_CHUNK - 1) / DW2_CHUNK);
+    w.moments = c.take<double>((size_t)B * 9);
+    w.dpart = c.take<double>((size_t)std::max(w.nb_a1 * C1, w.nb_a2 * C2));
+    w.dsum = c.take<double>(C2);
+    size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
+    fp = std::max(fp, (size_t)B * w.tiles_per_cloud * C3);                   // css3 partials
+    if (backward) {
+        fp = std::max(fp, (size_t)w.nb_gram * C2 * C2);                      // Gram partials
+        fp = std::max(fp, (size_t)w.nb_l2 * 2 * C2);                         // BN2 backward partials
+        fp = std::max(fp, (size_t)w.nb_dw2 * C2 * C1);                       // dW2 partials
+        fp = std::max(fp, (size_t)B * (C1 * 3));                             // dW1 partials
+    }
+    w.fpart_elems = fp;
+    w.fpart = c.take<float>(fp);
+    w.keys = c.take<unsigned long long>((size_t)B * C3);
+    if (backward) {
+        w.coef = c.take<float>((size_t)B * C3);
+        w.dvec = c.take<float>(C3);
+        w.evec = c.take<float>(C3);
+        w.gram = c.take<float>(C2 * C2);
+        w.WG = c.take<float>((size_t)C3 * C2);
+        w.Q = c.take<float>(C2 * C2);
+        w.uvec = c.take<float>(C2);
+        w.da2s = c.take<float>((size_t)B * C3 * C2);
+        w.slot = c.take<int>(M);
+        w.DZ2 = c.take<float>(M * C2);
+        w.DZ1 = c.take<float>(M * C1);
+        w.m1_2 = c.take<float>(C2); w.m2_2 = c.take<float>(C2);
+        w.m1_1 = c.take<float>(C1); w.m2_1 = c.take<float>(C1);
+    }
+}
+
+// ================================================================================================
+// forward kernels
+// ================================================================================================
+
+// per-cloud first and second moments of the raw input points, in double.
+// mom[b] = { sum x, sum y, sum z, sum xx, xy, xz, yy, yz, zz }
+__global__ void k_cloud_moments(const float* __restrict__ x, int N, double* __restrict__ mom) {
+    __shared__ double sh[256];
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
+    const float* xb = x + (size_t)b * 3 * N;
+    double acc[9];
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    for (int n = tid; n < N; n += 256) {
+        double p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
+        acc[0] += p0; acc[1] += p1; acc[2] += p2;
+        acc[3] += p0 * p0; acc[4] += p0 * p1; acc[5] += p0 * p2;
+        acc[6] += p1 * p1; acc[7] += p1 * p2; acc[8] += p2 * p2;
+    }
+    for (int q = 0; q < 9; ++q) {
+        sh[tid] = acc[q];
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (tid < s) sh[tid] += sh[tid + s];
+            __syncthreads();
+        }
+        if (tid == 0) mom[(size_t)b * 9 + q] = sh[0];
+        __syncthreads();
+    }
+}
+
+// BatchNorm1 batch statistics, analytically from the cloud moments:
+//   u1 = W1 T^T x  =>  mean = W1 m,  var_c = w_c^T Cov w_c   with m, Cov the moments of x' = T^T x.
+__global__ void k_bn1_finalize(const double* __restrict__ mom, const float* __restrict__ trans, int B, int N,
+                               pgpd_lin conv, pgpd_bn bn, BnState st) {
+    const int c = (int)threadIdx.x;
+    if (c >= C1) return;
+    double m[3] = {0, 0, 0}, S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int b = 0; b < B; ++b) {
+        const double* q = mom + (size_t)b * 9;
+        double s[3] = {q[0], q[1], q[2]};
+        double X[3][3] = {{q[3], q[4], q[5]}, {q[4], q[6], q[7]}, {q[5], q[7], q[8]}};
+        double T[3][3];
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) T[j][i] = trans ? (double)trans[(size_t)b * 9 + j * 3 + i] : (i == j ? 1.0 : 0.0);
+        // x'_i = sum_j T[j][i] x_j
+        for (int i = 0; i < 3; ++i) {
+            double v = 0;
+            for (int j = 0; j < 3; ++j) v += T[j][i] * s[j];
+            m[i] += v;
+        }
+        for (int i = 0; i < 3; ++i)
+            for (int i2 = 0; i2 < 3; ++i2) {
+                double v = 0;
+                for (int j = 0; j < 3; ++j)
+                    for (int j2 = 0; j2 < 3; ++j2) v += T[j][i] * X[j][j2] * T[j2][i2];
+                S[i][i2] += v;
+            }
+    }
+    const double count = (double)B * (double)N;
+    for (int i = 0; i < 3; ++i) m[i] /= count;
+    double w[3] = {conv.w[c * 3 + 0], conv.w[c * 3 + 1], conv.w[c * 3 + 2]};
+    double mean_u = w[0] * m[0] + w[1] * m[1] + w[2] * m[2];
+    double var = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int i2 = 0; i2 < 3; ++i2) var += w[i] * (S[i][i2] / count - m[i] * m[i2]) * w[i2];
+    bn_finalize_train(c, mean_u, var, count, conv.b, bn, st);
+}
+
+// a1 = relu(scale1 * (W1 T^T x) + shift1), stored [M][64]; optional per-block sums of a1 (double).
+// block = 256 threads = 64 channels x 4 point slots.
+__global__ void k_a1(const float* __restrict__ x, const float* __restrict__ trans, int B, int N,
+                     const float* __restrict__ W1, BnState st, float* __restrict__ A1, double* __restrict__ part) {
+    __shared__ double sh[256];
+    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
+    const size_t M = (size_t)B * N;
+    const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
+    const float sc = st.scale[k], sh_ = st.shift[k];
+    float acc = 0.f;
+    for (size_t P = (size_t)blockIdx.x * 4 + q; P < M; P += (size_t)gridDim.x * 4) {
+        const int b = (int)(P / N), n = (int)(P % N);
+        const float* xb = x + (size_t)b * 3 * N;
+        float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
+        float t0 = p0, t1 = p1, t2 = p2;
+        if (trans) {
+            const float* T = trans + (size_t)b * 9;
+            t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+            t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+            t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+        }
+        float u = w0 * t0 + w1 * t1 + w2 * t2;
+        float a = fmaxf(sc * u + sh_, 0.f);
+        A1[P * C1 + k] = a;
+        acc += a;
+    }
+    if (part) {
+        sh[tid] = (double)acc;
+        __syncthreads();
+        if (tid < 64) part[(size_t)blockIdx.x * C1 + tid] = sh[tid] + sh[tid + 64] + sh[tid + 128] + sh[tid + 192];
+    }
+}
+
+// per-block sums over points of a2 = relu(scale2*u2 + shift2); block = 128 channels x 2 slots
+__global__ void k_a2_sum(const float* __restrict__ Y2, size_t M, BnState st, double* __restrict__ part) {
+    __shared__ double sh[256];
+    const int tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
+    const float sc = st.scale[k], sf = st.shift[k];
+    double acc = 0.0;
+    float facc = 0.f;
+    int cnt = 0;
+    for (size_t P = (size_t)blockIdx.x * 2 + q; P < M; P += (size_t)gridDim.x * 2) {
+        facc += fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
+        if (++cnt == 32) { acc += (double)facc; facc = 0.f; cnt = 0; }
+    }
+    acc += (double)facc;
+    sh[tid] = acc;
+    __syncthreads();
+    if (tid < 128) part[(size_t)blockIdx.x * C2 + tid] = sh[tid] + sh[tid + 128];
+}
+
+__global__ void k_sign(const float* __restrict__ gamma, float* __restrict__ sgn, int C) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c < C) sgn[c] = gamma[c] >= 0.f ? 1.f : -1.f;
+}
+
+// ---- layer 2 forward: u2[P][c] = sum_k a1[P][k] W2[c][k] -----------------------------------------
+struct ProbL2Fwd {
+    static constexpr bool A_KFAST = true, B_NFAST = false;
+    static constexpr int SCRATCH = 0;
+    using Cfg = CfgBig;
+    const float* A1; const float* W2; float* Y2; const float* mean_u2; float* css_part; size_t M;
+    struct Blk { int m0, n0, k0, k1; };
+    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.x * Cfg::BM; b.n0 = 0; b.k0 = 0; b.k1 = C1; }
+    __device__ void prologue(const Blk&, float*) const {}
+    __device__ float loadA(const Blk&, const float*, int m, int k) const { return (size_t)m < M ? A1[(size_t)m * C1 + k] : 0.f; }
+    __device__ float loadB(const Blk&, const float*, int k, int n) const { return W2[n * C1 + k]; }
+    __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void* red) const {
+        float v[Cfg::TN];
+#pragma unroll
+        for (int j = 0; j < Cfg::TN; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i) {
+            size_t P = (size_t)b.m0 + Cfg::row_of(ty, i);
+            if (P < M) {
+#pragma unroll
+                for (int c4 = 0; c4 < Cfg::TN / 4; ++c4) {
+                    int col = Cfg::col_of(tx, c4 * 4);
+                    *reinterpret_cast<float4*>(&Y2[P * C2 + col]) =
+                        make_float4(acc[i][c4 * 4 + 0], acc[i][c4 * 4 + 1], acc[i][c4 * 4 + 2], acc[i][c4 * 4 + 3]);
+                }
+                if (mean_u2) {
+#pragma unroll
+                    for (int j = 0; j < Cfg::TN; ++j) {
+                        float d = acc[i][j] - mean_u2[Cfg::col_of(tx, j)];
+                        v[j] = fmaf(d, d, v[j]);
+                    }
+                }
+            }
+        }
+        if (mean_u2) {
+            float s = block_col_sum<Cfg>(v, ty, tx, (float*)red);
+            if ((int)threadIdx.x < Cfg::BN) css_part[(size_t)blockIdx.x * C2 + threadIdx.x] = s;
+        }
+    }
+};
+
+// ---- layer 3 forward + max-pool: u3[c][n] = sum_k W3[c][k] a2[n][k], per cloud ------------------
+struct ProbL3Fwd {
+    static constexpr bool A_KFAST = true, B_NFAST = false;
+    static constexpr int SCRATCH = 2 * C2;
+    using Cfg = CfgBig;
+    const float* W3; const float* Y2; const float* scale2; const float* shift2; const float* sgn;
+    const float* mean_u3; unsigned long long* keys; float* css_part; int N; int tiles;
+    struct Blk { int m0, n0, k0, k1, b; };
+    __device__ void setup(Blk& b) const {
+        b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.b = (int)blockIdx.z; b.k0 = 0; b.k1 = C2;
+    }
+    __device__ void prologue(const Blk&, float* s) const {
+        for (int i = (int)threadIdx.x; i < C2; i += Cfg::NT) { s[i] = scale2[i]; s[C2 + i] = shift2[i]; }
+        __syncthreads();
+    }
+    __device__ float loadA(const Blk&, const float*, int m, int k) const { return W3[(size_t)m * C2 + k]; }
+    __device__ float loadB(const Blk& b, const float* s, int k, int n) const {
+        if (n >= N) return 0.f;
+        return fmaxf(s[k] * Y2[((size_t)b.b * N + n) * C2 + k] + s[C2 + k], 0.f);
+    }
+    __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void* red) const {
+        unsigned long long best[Cfg::TM];
+        float v[Cfg::TM];
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i) {
+            const int c = b.m0 + Cfg::row_of(ty, i);
+            const float sg = sgn[c];
+            const float mu = mean_u3 ? mean_u3[c] : 0.f;
+            unsigned long long bk = 0ull;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < Cfg::TN; ++j) {
+                const int n = b.n0 + Cfg::col_of(tx, j);
+                if (n < N) {
+                    unsigned long long key = ((unsigned long long)ord_encode(sg * acc[i][j]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)n);
+                    bk = key > bk ? key : bk;
+                    float d = acc[i][j] - mu;
+                    s = fmaf(d, d, s);
+                }
+            }
+            best[i] = bk;
+            v[i] = s;
+        }
+        unsigned long long km = block_row_max_u64<Cfg>(best, ty, tx, (unsigned long long*)red);
+        if ((int)threadIdx.x < Cfg::BM) atomicMax(&keys[(size_t)b.b * C3 + b.m0 + threadIdx.x], km);
+        if (mean_u3) {
+            float s = block_row_sum<Cfg>(v, ty, tx, (float*)red);
+            if ((int)threadIdx.x < Cfg::BM)
+                css_part[((size_t)b.b * tiles + blockIdx.x) * C3 + b.m0 + threadIdx.x] = s;
+        }
+    }
+};
+
+// decode the (max, arg-max) keys, apply BN3 (+ReLU) to the pooled values
+__global__ void k_pool_finalize(const unsigned long long* __restrict__ keys, const float* __restrict__ sgn, BnState st,
+                                int relu_last, size_t total, float* __restrict__ pooled, float* __restrict__ uext,
+                                int* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C3);
+    unsigned long long key = keys[i];
+    float u = sgn[c] * ord_decode((unsigned)(key >> 32));
+    int n = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    float g = st.scale[c] * u + st.shift[c];
+    if (relu_last) g = fmaxf(g, 0.f);
+    pooled[i] = g;
+    if (uext) { uext[i] = u; idx[i] = n; }
+}
+
+// ================================================================================================
+// backward kernels
+// ================================================================================================
+
+// BatchNorm3 / max-pool backward on the pooled values.  thread = channel, loop over clouds.
+__global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict__ uext, int B, int relu_last,
+                           double count, const float* __restrict__ gamma, BnState st,
+                           float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                           float* __restrict__ dvec, float* __restrict__ evec) {
+    const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C3) return;
+    const float sc = st.scale[c], sf = st.shift[c], mu = st.mean[c], r = st.rstd[c];
+    double sdz = 0.0, sdzy = 0.0;
+    for (int b = 0; b < B; ++b) {
+        const size_t i = (size_t)b * C3 + c;
+        const float u = uext[i];
+        float dz = dG[i];
+        if (relu_last && !(sc * u + sf > 0.f)) dz = 0.f;
+        const float yhat = (u - mu) * r;
+        sdz += (double)dz;
+        sdzy += (double)dz * (double)yhat;
+        coef[i] = sc * dz;
+    }
+    dgamma[c] = (float)sdzy;
+    dbeta[c] = (float)sdz;
+    const double m1 = sdz / count, m2 = sdzy / count;
+    const double d = (double)sc * m2 * (double)r;
+    dvec[c] = (float)d;
+    evec[c] = (float)((double)sc * m1 - d * (double)mu);
+    (void)gamma;
+}
+
+// Gram = sum_P a2[P] a2[P]^T, split over point chunks
+struct ProbGram {
+    static constexpr bool A_KFAST = false, B_NFAST = true;
+    static constexpr int SCRATCH = 2 * C2;
+    using Cfg = CfgBig;
+    const float* Y2; const float* scale2; const float* shift2; float* part; size_t M;
+    struct Blk { int m0, n0, k0, k1; };
+    __device__ void setup(Blk& b) const {
+        b.m0 = 0; b.n0 = 0;
+        size_t k0 = (size_t)blockIdx.x * GRAM_CHUNK, k1 = k0 + GRAM_CHUNK;
+        b.k0 = (int)k0; b.k1 = (int)(k1 < M ? k1 : M);
+    }
+    __device__ void prologue(const Blk&, float* s) const {
+        for (int i = (int)threadIdx.x; i < C2; i += Cfg::NT) { s[i] = scale2[i]; s[C2 + i] = shift2[i]; }
+        __syncthreads();
+    }
+    __device__ float a2(const float* s, int P, int ch) const { return fmaxf(s[ch] * Y2[(size_t)P * C2 + ch] + s[C2 + ch], 0.f); }
+    __device__ float loadA(const Blk&, const float* s, int m, int k) const { return a2(s, k, m); }
+    __device__ float loadB(const Blk&, const float* s, int k, int n) const { return a2(s, k, n); }
+    __device__ void epilogue(const Blk&, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
+        float* out = part + (size_t)blockIdx.x * C2 * C2;
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i)
+#pragma unroll
+            for (int j = 0; j < Cfg::TN; ++j) out[Cfg::row_of(ty, i) * C2 + Cfg::col_of(tx, j)] = acc[i][j];
+    }
+};
+
+// generic small dense GEMM: C[m][n] = sum_k (rs ? rs[k] : 1) * A[m*sam + k*sak] * B[k*sbk + n*sbn]
+template <bool AK, bool BN_>
+struct ProbDense {
+    static constexpr bool A_KFAST = AK, B_NFAST = BN_;
+    static constexpr int SCRATCH = 0;
+    using Cfg = CfgSmall;
+    const float* A; const float* Bm; float* C; const float* kscale;
+    int Mr, Nc, K; size_t sam, sak, sbk, sbn, ldc;
+    struct Blk { int m0, n0, k0, k1; };
+    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = K; }
+    __device__ void prologue(const Blk&, float*) const {}
+    __device__ float loadA(const Blk&, const float*, int m, int k) const {
+        if (m >= Mr) return 0.f;
+        float a = A[(size_t)m * sam + (size_t)k * sak];
+        return kscale ? a * kscale[k] : a;
+    }
+    __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < Nc ? Bm[(size_t)k * sbk + (size_t)n * sbn] : 0.f; }
+    __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i) {
+            int m = b.m0 + Cfg::row_of(ty, i);
+            if (m >= Mr) continue;
+#pragma unroll
+            for (int j = 0; j < Cfg::TN; ++j) {
+                int n = b.n0 + Cfg::col_of(tx, j);
+                if (n < Nc) C[(size_t)m * ldc + n] = acc[i][j];
+            }
+        }
+    }
+};
+
+// uvec[i] = sum_c W3[c][i] * e[c]
+__global__ void k_uvec(const float* __restrict__ W3, const float* __restrict__ e, float* __restrict__ uvec) {
+    int i = (int)threadIdx.x;
+    if (i >= C2) return;
+    double s = 0.0;
+    for (int c = 0; c < C3; ++c) s += (double)W3[(size_t)c * C2 + i] * (double)e[c];
+    uvec[i] = (float)s;
+}
+
+// dW3[c][k] = sum_b coef[b][c] a2[argmax(b,c)][k]  -  d[c] * (W3 Gram)[c][k]  -  e[c] * S1[k]
+// grid = 1024 channels, block = 128 (k)
+__global__ void k_dw3(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ Y2, BnState st2,
+                      int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec,
+                      const float* __restrict__ WG, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
+    const int c = (int)blockIdx.x, k = (int)threadIdx.x;
+    const float sc = st2.scale[k], sf = st2.shift[k];
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float cf = coef[(size_t)b * C3 + c];
+        if (cf != 0.f) {
+            const size_t P = (size_t)b * N + idx[(size_t)b * C3 + c];
+            acc = fmaf(cf, fmaxf(sc * Y2[P * C2 + k] + sf, 0.f), acc);
+        }
+    }
+    dW3[(size_t)c * C2 + k] = acc - dvec[c] * WG[(size_t)c * C2 + k] - evec[c] * (float)S1[k];
+    if (k == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
+}
+
+// sparse part of d a2: rows  sum_{c : argmax(b,c)=p} coef[b][c] W3[c][:]  for the arg-max points of one cloud.
+// block = 1024 threads (one per channel) = one cloud.
+__global__ void k_da2_sparse(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ W3, int N,
+                             float* __restrict__ da2s, int* __restrict__ slot) {
+    __shared__ unsigned sk[C3];
+    __shared__ int scan[2][C3];
+    __shared__ int rowpos[C3 + 1];
+    __shared__ int nrows_s;
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
+    {
+        const float cf = coef[(size_t)b * C3 + tid];
+        sk[tid] = (cf != 0.f) ? (((unsigned)idx[(size_t)b * C3 + tid] << 10) | (unsigned)tid) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    // bitonic sort of 1024 keys
+    for (int size = 2; size <= C3; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            int partner = tid ^ stride;
+            if (partner > tid) {
+                bool up = ((tid & size) == 0);
+                unsigned a = sk[tid], c = sk[partner];
+                if ((a > c) == up) { sk[tid] = c; sk[partner] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // row starts + inclusive scan
+    const unsigned key = sk[tid];
+    const bool valid = key != 0xFFFFFFFFu;
+    const bool start = valid && (tid == 0 || (sk[tid - 1] >> 10) != (key >> 10));
+    scan[0][tid] = start ? 1 : 0;
+    __syncthreads();
+    int cur = 0;
+    for (int off = 1; off < C3; off <<= 1) {
+        int v = scan[cur][tid];
+        if (tid >= off) v += scan[cur][tid - off];
+        scan[cur ^ 1][tid] = v;
+        cur ^= 1;
+        __syncthreads();
+    }
+    const int rowid = scan[cur][tid] - 1;   // for valid entries
+    if (start) rowpos[rowid] = tid;
+    if (tid == C3 - 1) nrows_s = scan[cur][tid];
+    __syncthreads();
+    const int nrows = nrows_s;
+    if (tid == 0) {
+        // end sentinel: first invalid entry (or 1024)
+        int nvalid = 0;
+        // binary search for the first invalid key (keys are sorted, invalid = max)
+        int lo = 0, hi = C3;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (sk[mid] != 0xFFFFFFFFu) lo = mid + 1; else hi = mid; }
+        nvalid = lo;
+        rowpos[nrows] = nvalid;
+    }
+    __syncthreads();
+    const int grp = tid >> 7, k = tid & 127;
+    for (int r = grp; r < nrows; r += 8) {
+        const int e0 = rowpos[r], e1 = rowpos[r + 1];
+        float acc = 0.f;
+        for (int e = e0; e < e1; ++e) {
+            const int c = (int)(sk[e] & 1023u);
+            acc = fmaf(coef[(size_t)b * C3 + c], W3[(size_t)c * C2 + k], acc);
+        }
+        const size_t row = (size_t)b * C3 + r;
+        da2s[row * C2 + k] = acc;
+        if (k == 0) slot[(size_t)b * N + (sk[e0] >> 10)] = (int)row;
+    }
+}
+
+// ---- layer 2 backward, pass 1: d a2 -> dz2 (stored) + BN2 backward sums ---------------------------
+struct ProbL2BwdA {
+    static constexpr bool A_KFAST = true, B_NFAST = true;
+    static constexpr int SCRATCH = 2 * C2;
+    using Cfg = CfgBig;
+    const float* Y2; BnState st2; const float* Q; const float* uvec; const float* da2s; const int* slot;
+    float* DZ2; float* part; size_t M;
+    struct Blk { int m0, n0, k0, k1; };
+    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.x * Cfg::BM; b.n0 = 0; b.k0 = 0; b.k1 = C2; }
+    __device__ void prologue(const Blk&, float* s) const {
+        for (int i = (int)threadIdx.x; i < C2; i += Cfg::NT) { s[i] = st2.scale[i]; s[C2 + i] = st2.shift[i]; }
+        __syncthreads();
+    }
+    __device__ float loadA(const Blk&, const float* s, int m, int k) const {
+        return (size_t)m < M ? fmaxf(s[k] * Y2[(size_t)m * C2 + k] + s[C2 + k], 0.f) : 0.f;
+    }
+    __device__ float loadB(const Blk&, const float*, int k, int n) const { return Q[k * C2 + n]; }
+    __device__ void epilogue(const Blk& b, const float* s, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void* red) const {
+        float v1[Cfg::TN], v2[Cfg::TN];
+#pragma unroll
+        for (int j = 0; j < Cfg::TN; ++j) { v1[j] = 0.f; v2[j] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i) {
+            const size_t P = (size_t)b.m0 + Cfg::row_of(ty, i);
+            if (P >= M) continue;
+            const int sl = slot[P];
+#pragma unroll
+            for (int j = 0; j < Cfg::TN; ++j) {
+                const int c = Cfg::col_of(tx, j);
+                const float y = Y2[P * C2 + c];
+                const float z = s[c] * y + s[C2 + c];
+                float da2 = -acc[i][j] - uvec[c];
+                if (sl >= 0) da2 += da2s[(size_t)sl * C2 + c];
+                const float dz = z > 0.f ? da2 : 0.f;
+                DZ2[P * C2 + c] = dz;
+                const float yhat = (y - st2.mean[c]) * st2.rstd[c];
+                v1[j] += dz;
+                v2[j] = fmaf(dz, yhat, v2[j]);
+            }
+        }
+        float s1 = block_col_sum<Cfg>(v1, ty, tx, (float*)red);
+        float s2 = block_col_sum<Cfg>(v2, ty, tx, (float*)red);
+        if ((int)threadIdx.x < Cfg::BN) {
+            part[((size_t)blockIdx.x * 2 + 0) * C2 + threadIdx.x] = s1;
+            part[((size_t)blockIdx.x * 2 + 1) * C2 + threadIdx.x] = s2;
+        }
+    }
+};
+
+// dy2[P][c] = s2[c] * (dz2 - m1[c] - yhat2 * m2[c])
+struct Dy2 {
+    const float* DZ2; const float* Y2; BnState st2; const float* m1; const float* m2;
+    __device__ float at(size_t P, int c) const {
+        const float yhat = (Y2[P * C2 + c] - st2.mean[c]) * st2.rstd[c];
+        return st2.scale[c] * (DZ2[P * C2 + c] - m1[c] - yhat * m2[c]);
+    }
+};
+
+// dW2[c][k] = sum_P dy2[P][c] a1[P][k], split over point chunks
+struct ProbDW2 {
+    static constexpr bool A_KFAST = false, B_NFAST = true;
+    static constexpr int SCRATCH = 0;
+    using Cfg = CfgTall;
+    Dy2 dy; const float* A1; float* part; size_t M;
+    struct Blk { int m0, n0, k0, k1; };
+    __device__ void setup(Blk& b) const {
+        b.m0 = 0; b.n0 = 0;
+        size_t k0 = (size_t)blockIdx.x * DW2_CHUNK, k1 = k0 + DW2_CHUNK;
+        b.k0 = (int)k0; b.k1 = (int)(k1 < M ? k1 : M);
+    }
+    __device__ void prologue(const Blk&, float*) const {}
+    __device__ float loadA(const Blk&, const float*, int m, int k) const { return dy.at((size_t)k, m); }
+    __device__ float loadB(const Blk&, const float*, int k, int n) const { return A1[(size_t)k * C1 + n]; }
+    __device__ void epilogue(const Blk&, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
+        float* out = part + (size_t)blockIdx.x * C2 * C1;
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i)
+#pragma unroll
+            for (int j = 0; j < Cfg::TN; ++j) out[Cfg::row_of(ty, i) * C1 + Cfg::col_of(tx, j)] = acc[i][j];
+    }
+};
+
+// d a1[P][k] = sum_c dy2[P][c] W2[c][k] -> dz1 (stored) + BN1 backward sums
+struct ProbDA1 {
+    static constexpr bool A_KFAST = true, B_NFAST = true;
+    static constexpr int SCRATCH = 3 * 128;
+    using Cfg = CfgTall;
+    Dy2 dy; const float* W2; const float* A1; const float* x; const float* trans; const float* W1; BnState st1;
+    float* DZ1; float* part; size_t M; int N;
+    struct Blk { int m0, n0, k0, k1; };
+    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.x * Cfg::BM; b.n0 = 0; b.k0 = 0; b.k1 = C2; }
+    __device__ void prologue(const Blk& b, float* s) const {
+        // transformed coordinates of the tile's points: s[i*128 + r]
+        for (int r = (int)threadIdx.x; r < Cfg::BM; r += Cfg::NT) {
+            size_t P = (size_t)b.m0 + r;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+            if (P < M) {
+                const int bb = (int)(P / N), n = (int)(P % N);
+                const float* xb = x + (size_t)bb * 3 * N;
+                float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
+                t0 = p0; t1 = p1; t2 = p2;
+                if (trans) {
+                    const float* T = trans + (size_t)bb * 9;
+                    t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+                    t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+                    t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+                }
+            }
+            s[r] = t0; s[128 + r] = t1; s[256 + r] = t2;
+        }
+        __syncthreads();
+    }
+    __device__ float loadA(const Blk&, const float*, int m, int k) const { return (size_t)m < M ? dy.at((size_t)m, k) : 0.f; }
+    __device__ float loadB(const Blk&, const float*, int k, int n) const { return W2[k * C1 + n]; }
+    __device__ void epilogue(const Blk& b, const float* s, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void* red) const {
+        float v1[Cfg::TN], v2[Cfg::TN];
+#pragma unroll
+        for (int j = 0; j < Cfg::TN; ++j) { v1[j] = 0.f; v2[j] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < Cfg::TM; ++i) {
+            const int r = Cfg::row_of(ty, i);
+            const size_t P = (size_t)b.m0 + r;
+            if (P >= M) continue;
+            const float t0 = s[r], t1 = s[128 + r], t2 = s[256 + r];
+#pragma unroll
+            for (int j = 0; j < Cfg::TN; ++j) {
+                const int k = Cfg::col_of(tx, j);
+                const float dz = A1[P * C1 + k] > 0.f ? acc[i][j] : 0.f;
+                DZ1[P * C1 + k] = dz;
+                const float u = W1[k * 3 + 0] * t0 + W1[k * 3 + 1] * t1 + W1[k * 3 + 2] * t2;
+                const float yhat = (u - st1.mean[k]) * st1.rstd[k];
+                v1[j] += dz;
+                v2[j] = fmaf(dz, yhat, v2[j]);
+            }
+        }
+        float s1 = block_col_sum<Cfg>(v1, ty, tx, (float*)red);
+        float s2 = block_col_sum<Cfg>(v2, ty, tx, (float*)red);
+        if ((int)threadIdx.x < Cfg::BN) {
+            part[((size_t)blockIdx.x * 2 + 0) * C1 + threadIdx.x] = s1;
+            part[((size_t)blockIdx.x * 2 + 1) * C1 + threadIdx.x] = s2;
+        }
+    }
+};
+
+// layer 1 backward: dW1 partial per cloud and d trans per cloud.  block = 256 = 64 channels x 4 slots.
+__global__ void k_l1_bwd(const float* __restrict__ x, const float* __restrict__ trans, int N,
+                         const float* __restrict__ W1, BnState st1, const float* __restrict__ DZ1,
+                         const float* __restrict__ m1, const float* __restrict__ m2,
+                         float* __restrict__ dW1part, float* __restrict__ dtrans) {
+    __shared__ float shw[256 * 3];
+    __shared__ float sht[8 * 9];
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6, lane = tid & 31;
+    const float* xb = x + (size_t)b * 3 * N;
+    float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (trans)
+        for (int e = 0; e < 9; ++e) T[e] = trans[(size_t)b * 9 + e];
+    const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
+    const float mu = st1.mean[k], r = st1.rstd[k], sc = st1.scale[k], mm1 = m1[k], mm2 = m2[k];
+    float aw0 = 0.f, aw1 = 0.f, aw2 = 0.f;
+    float dT[9];
+    for (int e = 0; e < 9; ++e) dT[e] = 0.f;
+    const int iters = (N + 3) / 4;
+    for (int it = 0; it < iters; ++it) {
+        const int n = it * 4 + q;
+        const bool ok = n < N;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, dy = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        if (ok) {
+            p0 = xb[n]; p1 = xb[N + n]; p2 = xb[2 * N + n];
+            t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+            t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+            t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+            const float u = w0 * t0 + w1 * t1 + w2 * t2;
+            const float yhat = (u - mu) * r;
+            dy = sc * (DZ1[((size_t)b * N + n) * C1 + k] - mm1 - yhat * mm2);
+            aw0 = fmaf(dy, t0, aw0); aw1 = fmaf(dy, t1, aw1); aw2 = fmaf(dy, t2, aw2);
+        }
+        if (dtrans) {
+            // d x'_i = sum_k W1[k][i] dy1[k]  (warp-level partial over 32 channels)
+            float d0 = w0 * dy, d1 = w1 * dy, d2 = w2 * dy;
+            for (int o = 16; o > 0; o >>= 1) {
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (lane == 0 && ok) {
+                // dT[j][i] += x_j * dx'_i
+                dT[0] += p0 * d0; dT[1] += p0 * d1; dT[2] += p0 * d2;
+                dT[3] += p1 * d0; dT[4] += p1 * d1; dT[5] += p1 * d2;
+                dT[6] += p2 * d0; dT[7] += p2 * d1; dT[8] += p2 * d2;
+            }
+        }
+    }
+    shw[tid * 3 + 0] = aw0; shw[tid * 3 + 1] = aw1; shw[tid * 3 + 2] = aw2;
+    if (lane == 0)
+        for (int e = 0; e < 9; ++e) sht[(tid >> 5) * 9 + e] = dT[e];
+    __syncthreads();
+    if (tid < 192) {
+        const int kk = tid / 3, i = tid % 3;
+        float s = 0.f;
+        for (int qq = 0; qq < 4; ++qq) s += shw[(qq * 64 + kk) * 3 + i];
+        dW1part[(size_t)b * (C1 * 3) + tid] = s;
+    }
+    if (dtrans && tid < 9) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += sht[w * 9 + tid];
+        dtrans[(size_t)b * 9 + tid] = s;
+    }
+}
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+struct TowerArgs {
+    const pgpd_tower* t;
+    const float* x;
+    const float* trans;   // or nullptr
+    int B, N;
+    bool relu_last, train, save;
+    cudaStream_t stream;
+};
+
+inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
+    const pgpd_tower& t = *a.t;
+    const size_t M = (size_t)a.B * a.N;
+    cudaStream_t s = a.stream;
+    const double count = (double)M;
+
+    // ---- layer 1 ---------------------------------------------------------------------------------
+    if (a.train) {
+        launch(k_cloud_moments, dim3(a.B), dim3(256), 0, s, a.x, a.N, w.moments);
+        launch(k_bn1_finalize, dim3(1), dim3(64), 0, s, (const double*)w.moments, a.trans, a.B, a.N, t.conv[0], t.bn[0], w.bn[0]);
+    } else {
+        launch(k_bn_eval_affine, grid1d(C1, 128), dim3(128), 0, s, C1, t.conv[0].b, t.bn[0], w.bn[0]);
+        launch(k_bn_eval_affine, grid1d(C2, 128), dim3(128), 0, s, C2, t.conv[1].b, t.bn[1], w.bn[1]);
+        launch(k_bn_eval_affine, grid1d(C3, 128), dim3(128), 0, s, C3, t.conv[2].b, t.bn[2], w.bn[2]);
+    }
+    launch(k_a1, dim3(w.nb_a1), dim3(256), 0, s, a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1,
+           a.train ? w.dpart : (double*)nullptr);
+
+    // ---- layer 2 ---------------------------------------------------------------------------------
+    if (a.train) {
+        launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.dpart, w.nb_a1, C1, w.dsum);
+        launch(k_matvec_mean, dim3(1), dim3(128), 0, s, t.conv[1].w, C2, C1, (const double*)w.dsum, 1.0 / count, w.bn[1].mean);
+    }
+    {
+        ProbL2Fwd p{w.A1, t.conv[1].w, w.Y2, a.train ? w.bn[1].mean : nullptr, w.fpart, M};
+        launch_gemm<ProbL2Fwd::Cfg>(p, dim3(w.nb_l2), s);
+    }
+    if (a.train) {
+        launch(k_bn_finalize_from_css, dim3(1), dim3(128), 0, s, (const float*)w.fpart, w.nb_l2, C2,
+               (const float*)w.bn[1].mean, count, t.conv[1].b, t.bn[1], w.bn[1]);
+        // mean of layer-3 pre-activation: W3 * mean(a2)
+        launch(k_a2_sum, dim3(w.nb_a2), dim3(256), 0, s, (const float*)w.Y2, M, w.bn[1], w.dpart);
+        launch(k_reduce_d, dim3(1), dim3(128), 0, s, (const double*)w.dpart, w.nb_a2, C2, w.S1);
+        launch(k_matvec_mean, grid1d(C3, 128), dim3(128), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.bn[2].mean);
+    }
+
+    // ---- layer 3 + max-pool ------------------------------------------------------------------------
+    launch(k_sign, grid1d(C3, 256), dim3(256), 0, s, t.bn[2].gamma, w.sgn, C3);
+    cudaMemsetAsync(w.keys, 0, (size_t)a.B * C3 * sizeof(unsigned long long), s);
+    {
+        ProbL3Fwd p{t.conv[2].w, w.Y2, w.bn[1].scale, w.bn[1].shift, w.sgn, a.train ? w.bn[2].mean : nullptr,
+                    w.keys, w.fpart, a.N, w.tiles_per_cloud};
+        launch_gemm<ProbL3Fwd::Cfg>(p, dim3(w.tiles_per_cloud, C3 / 128, a.B), s);
+    }
+    if (a.train) {
+        launch(k_bn_finalize_from_css, grid1d(C3, 128), dim3(128), 0, s, (const float*)w.fpart, a.B * w.tiles_per_cloud, C3,
+               (const float*)w.bn[2].mean, count, t.conv[2].b, t.bn[2], w.bn[2]);
+    }
+    launch(k_pool_finalize, grid1d((size_t)a.B * C3, 256), dim3(256), 0, s, (const unsigned long long*)w.keys,
+           (const float*)w.sgn, w.bn[2], a.relu_last ? 1 : 0, (size_t)a.B * C3, pooled, w.uext, w.idx);
+}
+
+// dpooled [B][1024] -> parameter gradients (+ d trans).  Train-mode statistics only.
+inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad& g, const float* dpooled, float* dtrans_out) {
+    const pgpd_tower& t = *a.t;
+    const size_t M = (size_t)a.B * a.N;
+    cudaStream_t s = a.stream;
+    const double count = (double)M;
+
+    // ---- BN3 / max-pool on the pooled values ---------------------------------------------------------
+    launch(k_pool_bwd, grid1d(C3, 128), dim3(128), 0, s, dpooled, (const float*)w.uext, a.B, a.relu_last ? 1 : 0, count,
+           t.bn[2].gamma, w.bn[2], w.coef, g.bn[2].dgamma, g.bn[2].dbeta, w.dvec, w.evec);
+
+    // ---- Gram matrix of a2 -------------------------------------------------------------------------
+    {
+        ProbGram p{w.Y2, w.bn[1].scale, w.bn[1].shift, w.fpart, M};
+        launch_gemm<ProbGram::Cfg>(p, dim3(w.nb_gram), s);
+        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const float*)w.fpart, w.nb_gram, C2 * C2, w.gram);
+    }
+    // WG = W3 * Gram  [1024 x 128]
+    {
+        ProbDense<true, true> p{t.conv[2].w, w.gram, w.WG, nullptr, C3, C2, C2, (size_t)C2, 1, (size_t)C2, 1, (size_t)C2};
+        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C3 / 64), s);
+    }
+    // Q = W3^T diag(d) W3  [128 x 128]
+    {
+        ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.Q, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
+        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64), s);
+    }
+    launch(k_uvec, dim3(1), dim3(128), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
+    launch(k_dw3, dim3(C3), dim3(C2), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
+           (const float*)w.dvec, (const float*)w.evec, (const float*)w.WG, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
+
+    // ---- sparse part of d a2 -----------------------------------------------------------------------
+    cudaMemsetAsync(w.slot, 0xFF, M * sizeof(int), s);
+    launch(k_da2_sparse, dim3(a.B), dim3(C3), 0, s, (const float*)w.coef, (const int*)w.idx, t.conv[2].w, a.N, w.da2s, w.slot);
+
+    // ---- layer 2 backward ---------------------------------------------------------------------------
+    {
+        ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
+        launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
+        launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const float*)w.fpart, w.nb_l2, C2, count,
+               g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
+    }
+    Dy2 dy{w.DZ2, w.Y2, w.bn[1], w.m1_2, w.m2_2};
+    {
+        ProbDW2 p{dy, w.A1, w.fpart, M};
+        launch_gemm<ProbDW2::Cfg>(p, dim3(w.nb_dw2), s);
+        launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const float*)w.fpart, w.nb_dw2, C2 * C1, g.conv[1].dw);
+        launch(k_fill, grid1d(C2, 128), dim3(128), 0, s, g.conv[1].db, (size_t)C2, 0.f);
+    }
+    {
+        ProbDA1 p{dy, t.conv[1].w, w.A1, a.x, a.trans, t.conv[0].w, w.bn[0], w.DZ1, w.fpart, M, a.N};
+        launch_gemm<ProbDA1::Cfg>(p, dim3(w.nb_l2), s);
+        launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const float*)w.fpart, w.nb_l2, C1, count,
+               g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
+    }
+
+    // ---- layer 1 backward ---------------------------------------------------------------------------
+    launch(k_l1_bwd, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, t.conv[0].w, w.bn[0], (const float*)w.DZ1,
+           (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr);
+    launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const float*)w.fpart, a.B, C1 * 3, g.conv[0].dw);
+    launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
+}
+
+}  // namespace pgpd
