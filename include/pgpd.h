@@ -109,6 +109,17 @@ const char* pgpd_last_error(void);
 /* 1 if the library was built with the tcgen05 (sm_100a tensor-core) kernels */
 int pgpd_has_tensor_core_path(void);
 
+/* Kernels launched by this library from the calling thread since it was loaded. */
+unsigned long long pgpd_launch_count(void);
+
+/* Optional timing of the dominant kernel (the layer-3 GEMM + max-pool of a tower forward):
+ * pgpd_profile_enable(1) makes every following launch of that kernel on the calling thread record
+ * a CUDA-event pair on its stream; pgpd_profile_read synchronises those events, returns the number
+ * of launches and their summed duration, and resets the accumulator.  Not for use under CUDA-graph
+ * capture. */
+int pgpd_profile_enable(int on);
+int pgpd_profile_read(int* launches, float* total_ms);
+
 /* Bytes of workspace pgpd_forward/pgpd_backward need for (what,B,N,k,flags).  The same
  * buffer must be handed, untouched, from pgpd_forward(PGPD_F_SAVE) to pgpd_backward. */
 size_t pgpd_workspace_bytes(int what, int B, int N, int k, int flags);

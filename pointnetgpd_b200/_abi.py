@@ -58,7 +58,8 @@ class ModelGrad(C.Structure):
     _fields_ = [("stn_tower", TowerGrad), ("stn_head", HeadGrad), ("trunk", TowerGrad), ("cls_head", HeadGrad)]
 
 
-EXPORTS = ("pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_workspace_bytes",
+EXPORTS = ("pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_launch_count",
+           "pgpd_profile_enable", "pgpd_profile_read", "pgpd_workspace_bytes",
            "pgpd_forward", "pgpd_backward", "pgpd_tower_workspace_bytes", "pgpd_tower_forward",
            "pgpd_tower_backward")
 
@@ -71,6 +72,11 @@ def bind(lib):
     lib.pgpd_version.restype = C.c_int
     lib.pgpd_last_error.restype = C.c_char_p
     lib.pgpd_has_tensor_core_path.restype = C.c_int
+    lib.pgpd_launch_count.restype = C.c_ulonglong
+    lib.pgpd_profile_enable.restype = C.c_int
+    lib.pgpd_profile_enable.argtypes = [C.c_int]
+    lib.pgpd_profile_read.restype = C.c_int
+    lib.pgpd_profile_read.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_float)]
     lib.pgpd_workspace_bytes.restype = C.c_size_t
     lib.pgpd_workspace_bytes.argtypes = [C.c_int] * 5
     lib.pgpd_forward.restype = C.c_int

@@ -139,6 +139,42 @@ __global__ void k_bn_bwd_finalize(const float* part, int nblk, int C, double cou
     m2[c] = (float)(s2 / count);
 }
 
+// ---- optional CUDA-event timing of the dominant kernel ---------------------------------------------
+struct Profiler {
+    bool on = false;
+#ifndef PGPD_EMU
+    static constexpr int MAXP = 8192;
+    cudaEvent_t* ev = nullptr;
+    int n = 0;
+    void begin(cudaStream_t s) {
+        if (!on || n >= MAXP) return;
+        if (!ev) { ev = new cudaEvent_t[2 * MAXP]; for (int i = 0; i < 2 * MAXP; ++i) cudaEventCreate(&ev[i]); }
+        cudaEventRecord(ev[2 * n], s);
+    }
+    void end(cudaStream_t s) {
+        if (!on || n >= MAXP || !ev) return;
+        cudaEventRecord(ev[2 * n + 1], s);
+        ++n;
+    }
+    int read(int* launches, float* total_ms) {
+        float tot = 0.f;
+        for (int i = 0; i < n; ++i) {
+            if (cudaEventSynchronize(ev[2 * i + 1]) != cudaSuccess) return -1;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) != cudaSuccess) return -1;
+            tot += ms;
+        }
+        *launches = n; *total_ms = tot; n = 0;
+        return 0;
+    }
+#else
+    void begin(cudaStream_t) {}
+    void end(cudaStream_t) {}
+    int read(int* launches, float* total_ms) { *launches = 0; *total_ms = 0.f; return 0; }
+#endif
+};
+inline Profiler& profiler() { static thread_local Profiler p; return p; }
+
 inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
 
 }  // namespace pgpd

@@ -116,6 +116,16 @@ int pgpd_has_tensor_core_path(void) {
 #endif
 }
 
+unsigned long long pgpd_launch_count(void) { return launch_counter(); }
+
+int pgpd_profile_enable(int on) { profiler().on = on != 0; return PGPD_OK; }
+
+int pgpd_profile_read(int* launches, float* total_ms) {
+    if (!launches || !total_ms) return fail(PGPD_E_ARG, "null pointer");
+    if (profiler().read(launches, total_ms) != 0) return fail(PGPD_E_CUDA, "event timing failed");
+    return PGPD_OK;
+}
+
 size_t pgpd_workspace_bytes(int what, int B, int N, int k, int flags) {
     if (B < 1 || N < 1) return 0;
     ModelWs w;

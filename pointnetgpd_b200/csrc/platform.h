@@ -18,11 +18,15 @@
 
 namespace pgpd {
 
+// number of kernels this library launched from the calling thread (bench.py reports it)
+inline unsigned long long& launch_counter() { static thread_local unsigned long long n = 0; return n; }
+
 #ifdef PGPD_EMU
 template <class T> __device__ __forceinline__ T* dyn_smem() { return reinterpret_cast<T*>(emu::dyn_smem()); }
 
 template <class... KArgs, class... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args... args) {
+    ++launch_counter();
     emu::run_grid(grid, block, smem, [&]() { kernel(args...); });
 }
 #else
@@ -33,6 +37,7 @@ template <class T> __device__ __forceinline__ T* dyn_smem() {
 
 template <class... KArgs, class... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    ++launch_counter();
     kernel<<<grid, block, smem, stream>>>(args...);
 }
 #endif

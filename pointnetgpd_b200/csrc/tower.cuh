@@ -801,7 +801,9 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     {
         ProbL3Fwd p{t.conv[2].w, w.Y2, w.bn[1].scale, w.bn[1].shift, w.sgn, a.train ? w.bn[2].mean : nullptr,
                     w.keys, w.fpart, a.N, w.tiles_per_cloud};
+        profiler().begin(s);
         launch_gemm<ProbL3Fwd::Cfg>(p, dim3(w.tiles_per_cloud, C3 / 128, a.B), s);
+        profiler().end(s);
     }
     if (a.train) {
         launch(k_bn_finalize_from_css, grid1d(C3, 128), dim3(128), 0, s, (const float*)w.fpart, a.B * w.tiles_per_cloud, C3,

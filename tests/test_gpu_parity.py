@@ -1,0 +1,229 @@
+"""GPU parity tests: the CUDA path (through the nn.Module surface -> ctypes -> C ABI of libpgpd.so)
+against the golden vectors of the unmodified reference, the fp64 oracle, and -- at BASELINE's full
+sizes -- against the oracle's torch port executed in fp32 (TF32 off) plus size-independent
+properties.  Tolerance (north_star): log-probs within 1e-3, arg-max exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASE_NAMES, load_case, grad_errors, is_zero_grad_param
+from oracle import pointnet_torch_port as PT
+from oracle import weights as W
+from pointnetgpd_b200 import _abi as A
+from pointnetgpd_b200.model.pointnet import PointNetCls
+
+pytestmark = pytest.mark.gpu
+LOGP_TOL = 1e-3
+GRAD_FLOOR = 5e-3
+
+
+def _model(state, N, k, train):
+    m = PointNetCls(num_points=N, input_chann=3, k=k)
+    m.load_state_dict({kk: torch.tensor(v) for kk, v in state.items()}, strict=True)
+    m = m.cuda()
+    return m.train() if train else m.eval()
+
+
+def test_library_is_the_cuda_build():
+    lib = A.load()
+    assert lib.pgpd_version() == 100
+    assert os.path.basename(A.LIB_PATH) == "libpgpd.so"
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_eval_forward_golden(name):
+    c = load_case(name)
+    g = c["g"]
+    m = _model(c["state"], c["N"], c["k"], train=False)
+    with torch.no_grad():
+        logp, trans = m(torch.tensor(c["x"]).cuda())
+    logp, trans = logp.cpu().numpy(), trans.cpu().numpy()
+    assert np.abs(logp - g["eval_logp_f64"]).max() < LOGP_TOL
+    assert np.abs(trans - g["eval_trans_f64"]).max() < LOGP_TOL
+    assert (logp.argmax(1) == g["eval_logp_f64"].argmax(1)).all()
+    assert (logp.argmax(1) == g["eval_logp_f32"].argmax(1)).all()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_train_step_golden(name):
+    """forward + nll_loss + backward exactly as main_1v.py:72-75."""
+    c = load_case(name)
+    g = c["g"]
+    m = _model(c["state"], c["N"], c["k"], train=True)
+    x = torch.tensor(c["x"]).cuda()
+    y = torch.tensor(c["y"]).cuda()
+    logp, trans = m(x)
+    loss = torch.nn.functional.nll_loss(logp, y)
+    loss.backward()
+    assert np.abs(logp.detach().cpu().numpy() - g["train_logp_f64"]).max() < LOGP_TOL
+    assert np.abs(trans.detach().cpu().numpy() - g["train_trans_f64"]).max() < LOGP_TOL
+    assert abs(float(loss.detach()) - float(g["train_loss_f64"])) < 1e-4
+    grads = {n: p.grad.cpu().numpy() for n, p in m.named_parameters()}
+    ours = grad_errors(grads, g, "f64")
+    for n, (esub, enorm) in ours.items():
+        if is_zero_grad_param(n):
+            assert np.abs(grads[n]).max() < 1e-3 * max(float(g["gnorm_f64/fc3.weight"]), 1.0), n
+            continue
+        ref64 = g[f"gsub_f64/{n}"].astype(np.float64)
+        ref_err = np.linalg.norm(g[f"gsub_f32/{n}"].astype(np.float64) - ref64) / max(np.linalg.norm(ref64), 1e-30)
+        assert esub < max(GRAD_FLOOR, 10 * ref_err), (n, esub, ref_err)
+        assert enorm < max(GRAD_FLOOR, 10 * ref_err), (n, enorm, ref_err)
+    for n, b in m.named_buffers():
+        ref = np.asarray(g["buf_f64/" + n])
+        if n.endswith("num_batches_tracked"):
+            assert int(b) == 1
+        else:
+            assert np.abs(b.cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), n
+
+
+def test_shipped_checkpoint_known_answer(golden_dir):
+    """Real trained weights (negative BN gammas, extreme running stats): N=500, k=3."""
+    st = dict(np.load(os.path.join(golden_dir, "shipped_3class_state.npz")))
+    out = np.load(os.path.join(golden_dir, "shipped_3class_outputs.npz"))
+    m = _model(st, 500, 3, train=False)
+    for kind, seed in (("box", 123), ("dup", 124)):
+        x = torch.tensor(W.make_clouds(seed, 8, 500, kind)).cuda()
+        with torch.no_grad():
+            logp, trans = m(x)
+        logp = logp.cpu().numpy()
+        assert np.abs(logp - out[f"{kind}_logp_f64"]).max() < LOGP_TOL, kind
+        assert (logp.argmax(1) == out[f"{kind}_logp_f64"].argmax(1)).all()
+        rel = np.abs(trans.cpu().numpy() - out[f"{kind}_trans_f64"]).max() / np.abs(out[f"{kind}_trans_f64"]).max()
+        assert rel < 1e-4
+    # deploy shape B=1 (kinect2grasp.py:479)
+    x1 = torch.tensor(W.make_clouds(125, 1, 500, "box")).cuda()
+    with torch.no_grad():
+        logp1, _ = m(x1)
+    assert np.abs(logp1.cpu().numpy() - out["b1_logp_f64"]).max() < LOGP_TOL
+
+
+def _oracle_on_gpu(state, x, y, train):
+    """the oracle's torch port, executed by eager PyTorch on the GPU in true fp32 (TF32 off)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = {k: v.cuda() for k, v in PT.to_torch_state(state, torch.float32).items()}
+        if not train:
+            with torch.no_grad():
+                return PT.pointnetcls_forward(sd, x, training=False), None
+        for k, v in sd.items():
+            if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+        logp, trans = PT.pointnetcls_forward(sd, x, training=True)
+        torch.nn.functional.nll_loss(logp, y).backward()
+        return (logp.detach(), trans.detach()), {k: v.grad for k, v in sd.items() if v.requires_grad}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,N,k", [(512, 1024, 2), (256, 2048, 2), (512, 1024, 3)])
+def test_full_size_train_step_vs_oracle(B, N, k):
+    """BASELINE configs 2/3 (512x1024) and the per-GPU share of config 4 shape (2048 pts)."""
+    st = W.make_state(900 + k, k=k)
+    x = torch.tensor(W.make_clouds(901, B, N, "box")).cuda()
+    y = torch.tensor(W.make_labels(902, B, k)).cuda()
+    m = _model(st, N, k, train=True)
+    logp, trans = m(x)
+    torch.nn.functional.nll_loss(logp, y).backward()
+    (rl, rt), rg = _oracle_on_gpu(st, x, y, True)
+    assert float((logp - rl).abs().max()) < LOGP_TOL
+    assert float((trans - rt).abs().max()) < LOGP_TOL
+    assert bool((logp.argmax(1) == rl.argmax(1)).all())
+    for n, p in m.named_parameters():
+        if is_zero_grad_param(n):
+            continue
+        r = rg[n].reshape(p.shape)
+        rel = float((p.grad - r).norm() / r.norm())
+        assert rel < 3e-2, (n, rel)      # two fp32 implementations with arg-max routing
+
+
+def test_inference_sweep_vs_oracle():
+    """BASELINE config 5: batched candidate scoring, 750 points, eval mode."""
+    st = W.make_state(910, k=2, style="wild")
+    m = _model(st, 750, 2, train=False)
+    for B in (1, 64, 512, 4096):
+        x = torch.tensor(W.make_clouds(911 + B, B, 750, "dup")).cuda()
+        with torch.no_grad():
+            logp, trans = m(x)
+        (rl, rt), _ = _oracle_on_gpu(st, x, None, False)
+        assert float((logp - rl).abs().max()) < LOGP_TOL, B
+        assert bool((logp.argmax(1) == rl.argmax(1)).all()), B
+
+
+def test_eval_properties_full_size():
+    """Size-independent properties of the path at B=512, N=1024 (eval mode has no cross-cloud
+    coupling): permutation of points, permutation of clouds, batch splitting -- all bit-exact."""
+    st = W.make_state(920, k=2, style="wild")
+    m = _model(st, 1024, 2, train=False)
+    x = torch.tensor(W.make_clouds(921, 512, 1024, "box")).cuda()
+    with torch.no_grad():
+        l0, t0 = m(x)
+        perm = torch.randperm(1024, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+        l1, _ = m(x[:, :, perm].contiguous())
+        assert torch.equal(l0, l1)
+        bperm = torch.randperm(512, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+        l2, _ = m(x[bperm].contiguous())
+        assert torch.equal(l0[bperm], l2)
+        l3, _ = m(x[:100].contiguous())
+        assert torch.equal(l0[:100], l3)
+
+
+def test_train_determinism():
+    st = W.make_state(930, k=2)
+    x = torch.tensor(W.make_clouds(931, 64, 512, "dup")).cuda()
+    y = torch.tensor(W.make_labels(932, 64, 2)).cuda()
+    outs = []
+    for _ in range(2):
+        m = _model(st, 512, 2, train=True)
+        logp, _ = m(x)
+        torch.nn.functional.nll_loss(logp, y).backward()
+        outs.append([logp.detach().clone()] + [p.grad.clone() for p in m.parameters()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_reference_error_behaviour():
+    m = PointNetCls(num_points=64, k=2).cuda().train()
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        m(torch.zeros(1, 3, 64, device="cuda"))
+    with pytest.raises(ValueError, match="num_points"):
+        m(torch.zeros(4, 3, 65, device="cuda"))
+    m.eval()
+    with torch.no_grad():
+        logp, _ = m(torch.zeros(1, 3, 64, device="cuda"))      # B=1 is fine in eval mode
+    assert logp.shape == (1, 2)
+
+
+def test_simt_flag_matches_default_path():
+    """PGPD_F_SIMT (fp32 CUDA-core kernels only) and the default dispatch agree within tolerance."""
+    from pointnetgpd_b200.functional import run_module
+    st = W.make_state(940, k=2, style="wild")
+    m = _model(st, 1000, 2, train=False)
+    x = torch.tensor(W.make_clouds(941, 40, 1000, "box")).cuda()
+    with torch.no_grad():
+        a, _ = run_module(m, A.PGPD_CLS, x, k=2)
+        b, _ = run_module(m, A.PGPD_CLS, x, k=2, flags_extra=A.F_SIMT)
+    assert float((a - b).abs().max()) < LOGP_TOL
+    assert bool((a.argmax(1) == b.argmax(1)).all())
+
+
+def test_optimizer_loop_runs_and_loss_decreases():
+    """main_1v.py:59-84 shape of use: Adam on model.parameters(), several steps."""
+    st = W.make_state(950, k=2)
+    m = _model(st, 256, 2, train=True)
+    x = torch.tensor(W.make_clouds(951, 64, 256, "box")).cuda()
+    y = torch.tensor(W.make_labels(952, 64, 2)).cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=0.005)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad()
+        logp, _ = m(x)
+        loss = torch.nn.functional.nll_loss(logp, y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.5 * losses[0]
+    assert int(m.bn1.num_batches_tracked) == 25
