@@ -80,31 +80,68 @@ __global__ void k_bn_eval_affine(int C, const float* bias, pgpd_bn bn, BnState s
     st.shift[c] = bn.beta[c] + sc * (b - bn.running_mean[c]);
 }
 
-// css partials (float, [nblk][C]) -> variance -> finalize (train)
-__global__ void k_bn_finalize_from_css(const float* part, int nblk, int C, const float* mean_u, double count,
+// ---- deterministic two-stage column reduction ------------------------------------------------------
+// stage 1: tmp[s][c] = sum over the rows of slice s of part[row][c]   (double accumulation, fixed order)
+// grid (ceil(C/32), S), block 256 = 32 columns x 8 row lanes
+constexpr int REDUCE_MAX_SLICES = 32;
+template <class T>
+__global__ void k_colreduce_stage1(const T* __restrict__ part, int nblk, int C, double* __restrict__ tmp) {
+    __shared__ double sh[8][33];
+    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
+    const int c = (int)blockIdx.x * 32 + cx;
+    const int S = (int)gridDim.y, sl = (int)blockIdx.y;
+    const int per = (nblk + S - 1) / S;
+    const int r0 = sl * per, r1 = (r0 + per < nblk) ? r0 + per : nblk;
+    double acc = 0.0;
+    if (c < C)
+        for (int i = r0 + ry; i < r1; i += 8) acc += (double)part[(size_t)i * C + c];
+    sh[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+        tmp[(size_t)sl * C + c] = t;
+    }
+}
+
+inline int reduce_slices(int nblk) {
+    int s = (nblk + 127) / 128;
+    return s < 1 ? 1 : (s > REDUCE_MAX_SLICES ? REDUCE_MAX_SLICES : s);
+}
+
+// runs stage 1 and returns the number of slices S; afterwards tmp holds [S][C] doubles
+template <class T>
+inline int colreduce(const T* part, int nblk, int C, double* tmp, cudaStream_t s) {
+    const int S = reduce_slices(nblk);
+    launch(k_colreduce_stage1<T>, dim3((unsigned)((C + 31) / 32), (unsigned)S), dim3(256), 0, s, part, nblk, C, tmp);
+    return S;
+}
+
+// slices of centred-square sums -> variance -> BatchNorm finalisation (train)
+__global__ void k_bn_finalize_from_css(const double* tmp, int S, int C, const float* mean_u, double count,
                                        const float* bias, pgpd_bn bn, BnState st) {
     int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= C) return;
     double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += (double)part[(size_t)i * C + c];
+    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
     bn_finalize_train(c, (double)mean_u[c], s / count, count, bias, bn, st);
 }
 
-// out[c] = sum_i part[i][c]  (double partials, fixed order)
-__global__ void k_reduce_d(const double* part, int nblk, int C, double* out) {
+// out[c] = sum_i tmp[i][c]
+__global__ void k_reduce_d(const double* tmp, int S, int C, double* out) {
     int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= C) return;
     double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += part[(size_t)i * C + c];
+    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
     out[c] = s;
 }
 
-// out[c] = (float) sum_i part[i][c]  (float partials, double accumulation, fixed order)
-__global__ void k_reduce_f(const float* part, int nblk, int C, float* out) {
+// out[c] = (float) sum_i tmp[i][c]
+__global__ void k_reduce_f(const double* tmp, int S, int C, float* out) {
     int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= C) return;
     double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += (double)part[(size_t)i * C + c];
+    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
     out[c] = (float)s;
 }
 
@@ -122,16 +159,16 @@ __global__ void k_fill(float* p, size_t n, float v) {
     if (i < n) p[i] = v;
 }
 
-// BatchNorm backward bookkeeping from [nblk][2][C] float partials of (sum dz, sum dz*yhat):
+// BatchNorm backward bookkeeping from slices [S][2][C] of (sum dz, sum dz*yhat):
 //   dgamma = sum dz*yhat ; dbeta = sum dz ; m1 = dbeta/count ; m2 = dgamma/count
-__global__ void k_bn_bwd_finalize(const float* part, int nblk, int C, double count,
+__global__ void k_bn_bwd_finalize(const double* tmp, int S, int C, double count,
                                   float* dgamma, float* dbeta, float* m1, float* m2) {
     int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nblk; ++i) {
-        s1 += (double)part[((size_t)i * 2 + 0) * C + c];
-        s2 += (double)part[((size_t)i * 2 + 1) * C + c];
+    for (int i = 0; i < S; ++i) {
+        s1 += tmp[((size_t)i * 2 + 0) * C + c];
+        s2 += tmp[((size_t)i * 2 + 1) * C + c];
     }
     dgamma[c] = (float)s2;
     dbeta[c] = (float)s1;

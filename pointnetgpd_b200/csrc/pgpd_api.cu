@@ -4,9 +4,6 @@
 #include "common.cuh"
 #include "tower.cuh"
 #include "head.cuh"
-#ifndef PGPD_EMU
-#include "tc_dispatch.cuh"
-#endif
 
 #include <string>
 
@@ -82,19 +79,18 @@ __global__ void k_add_opt(const float* a, const float* b, float* out, size_t n) 
     if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
 }
 
-static void run_tower_fwd(const TowerArgs& a, TowerWs& w, float* pooled, int flags) {
-#ifndef PGPD_EMU
-    if (!(flags & PGPD_F_SIMT) && tc::tower_forward_tc(a, w, pooled)) return;
-#endif
+static bool want_tc(int flags) {
+#ifdef PGPD_EMU
     (void)flags;
-    tower_forward(a, w, pooled);
+    return false;
+#else
+    return !(flags & PGPD_F_SIMT) && tc::available();
+#endif
 }
 
-static void run_tower_bwd(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad& g, const float* dpooled, float* dtrans, int flags) {
-#ifndef PGPD_EMU
-    if (!(flags & PGPD_F_SIMT) && tc::tower_backward_tc(a, w, g, dpooled, dtrans)) return;
-#endif
-    (void)flags;
+static void run_tower_fwd(const TowerArgs& a, TowerWs& w, float* pooled, int) { tower_forward(a, w, pooled); }
+
+static void run_tower_bwd(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad& g, const float* dpooled, float* dtrans, int) {
     tower_backward(a, w, g, dpooled, dtrans);
 }
 
@@ -149,14 +145,14 @@ int pgpd_forward(int what, const pgpd_model* m, const float* x, int B, int N, in
     const bool save = (flags & PGPD_F_SAVE) != 0;
 
     // ---- STN3d (pointnet.py:27-45)
-    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, train, save, s};
+    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, train, save, s, want_tc(flags)};
     run_tower_fwd(ta, w.stn_t, w.g_stn, flags);
     HeadArgs ha{&m->stn_head, w.g_stn, B, 9, train, true, s};
     head_forward(ha, w.stn_h);
     cudaMemcpyAsync(trans, w.stn_h.out, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (what >= PGPD_FEAT) {
         // ---- transform + trunk tower (pointnet.py:140-149)
-        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, train, save, s};
+        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, train, save, s, want_tc(flags)};
         run_tower_fwd(tb, w.trunk_t, w.G, flags);
         if (what == PGPD_FEAT) {
             cudaMemcpyAsync(out, w.G, (size_t)B * C3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -196,7 +192,7 @@ int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const
             head_backward(hb, w.cls_h, g->cls_head, w.dG);
             dG = w.dG;
         }
-        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, true, true, s};
+        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, true, true, s, want_tc(flags)};
         run_tower_bwd(tb, w.trunk_t, g->trunk, dG, w.dT, flags);
         launch(k_add_opt, grid1d((size_t)B * 9, 128), dim3(128), 0, s, (const float*)w.dT, dtrans, w.stn_h.dO, (size_t)B * 9);
     } else {
@@ -204,7 +200,7 @@ int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const
     }
     HeadArgs ha{&m->stn_head, w.g_stn, B, 9, true, true, s};
     head_backward(ha, w.stn_h, g->stn_head, w.dg_stn);
-    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, true, true, s};
+    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, true, true, s, want_tc(flags)};
     run_tower_bwd(ta, w.stn_t, g->stn_tower, w.dg_stn, nullptr, flags);
     return check_cuda("pgpd_backward");
 }
@@ -237,7 +233,7 @@ int pgpd_tower_forward(const pgpd_tower* t, const float* x, const float* trans, 
     if (!workspace || ((uintptr_t)workspace & 255)) return fail(PGPD_E_WORKSPACE, "workspace null or misaligned");
     if (workspace_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small");
     plan_tower_only(workspace, B, N, flags, w, need);
-    TowerArgs a{t, x, trans, B, N, relu_last != 0, train, (flags & PGPD_F_SAVE) != 0, (cudaStream_t)stream};
+    TowerArgs a{t, x, trans, B, N, relu_last != 0, train, (flags & PGPD_F_SAVE) != 0, (cudaStream_t)stream, want_tc(flags)};
     run_tower_fwd(a, w, pooled, flags);
     return check_cuda("pgpd_tower_forward");
 }
@@ -256,7 +252,7 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
     if (!workspace || ((uintptr_t)workspace & 255)) return fail(PGPD_E_WORKSPACE, "workspace null or misaligned");
     if (workspace_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small");
     plan_tower_only(workspace, B, N, flags, w, need);
-    TowerArgs a{t, x, trans, B, N, relu_last != 0, true, true, (cudaStream_t)stream};
+    TowerArgs a{t, x, trans, B, N, relu_last != 0, true, true, (cudaStream_t)stream, want_tc(flags)};
     run_tower_bwd(a, w, *g, dpooled, dtrans_out, flags);
     return check_cuda("pgpd_tower_backward");
 }

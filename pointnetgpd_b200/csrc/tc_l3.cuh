@@ -1,0 +1,294 @@
+// tc_l3.cuh -- tcgen05 kernel for the dominant op of the path (94 % of the tower flops):
+//   u3[c][n] = sum_k W3[c][k] * a2[n][k]      (128 -> 1024 channels, every point of every cloud)
+//   fused with: the BatchNorm2+ReLU prologue (a2 = relu(scale2*u2 + shift2) computed while staging),
+//               the global max-pool (+ first arg-max) over the points of each cloud,
+//               the centred sum of squares needed for the train-mode BatchNorm3 statistics.
+// The 1024-wide activation lives only in TMEM.
+//
+// Numerics: fp32-grade.  Both operands are split x = hi + lo into two fp16 values (22 significant
+// bits) and the product is formed as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (3 MMAs
+// at the 16-bit rate).  Operands are pre-scaled by powers of two (exact) so that the lo parts stay
+// in fp16's normal range: every W3 row by 2^e_c with max|w_c|*2^e_c in [2^13,2^14), activations
+// by 2^4.  Max/arg-max are invariant under the positive scaling; sums are rescaled on output.
+//
+// Orientation: channels on the MMA M axis (TMEM lanes), points on N (columns): the max / sum over
+// points is then a per-thread serial reduction over the columns each epilogue thread loads.
+//
+// CTA = 10 warps, persistent over tiles of 256 points:
+//   warp 0    W3 producer: bulk-copies 32 KB stages (one 128-channel x 64-k block, hi+lo) of the
+//             pre-swizzled weight image from L2 into a 3-deep ring;
+//   warp 1    MMA issuer (one thread): per 128-channel block, 2 k-blocks x 3 passes x 4 MMAs of
+//             128 x 256 x 16 into one of two 256-column TMEM accumulators;
+//   warps 2-5 epilogue: tcgen05.ld the accumulator, max / arg-max / centred squares per channel;
+//   warps 6-9 a2 producer: u2 tile -> BN2+ReLU -> hi/lo fp16 -> swizzled shared memory.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace pgpd { namespace tc {
+
+constexpr int L3_NT = 256;                        // points per tile (MMA N)
+constexpr int L3_STAGES = 3;
+constexpr int L3_STAGE_BYTES = 2 * 128 * 128;     // hi + lo, 128 rows x 128 B
+constexpr int L3_A2_PART = L3_NT * 128;           // one (part,kblock) sub-tile: 256 rows x 128 B = 32 KB
+constexpr int L3_A2_BYTES = 4 * L3_A2_PART;       // hi/lo x 2 k-blocks = 128 KB
+constexpr int L3_SMEM_W = L3_A2_BYTES;
+constexpr int L3_SMEM_MISC = L3_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
+constexpr int L3_SMEM_BYTES = L3_SMEM_MISC + 2048 + 1024;   // + slack to align the base to 1024 B
+constexpr int L3_THREADS = 320;
+constexpr float L3_ACT_SCALE = 16.0f;             // 2^4
+constexpr size_t L3_WIMG_BYTES = (size_t)8 * 2 * L3_STAGE_BYTES;   // 512 KB
+
+// ---- weight pre-pack: W3 [1024][128] fp32 -> swizzled hi/lo fp16 image + per-channel inverse scale ----
+// image index: ((mt*2 + kb)*2 + part) * 16 KB + r*128 + ((chunk ^ (r&7)) << 4) + within*2
+// inv[c] = sign(gamma3[c]) * 2^-(e_c + 4): multiplying a TMEM accumulator value by inv[c] gives u3.
+__global__ void k_prepack_w3(const float* __restrict__ W3, const float* __restrict__ gamma3, const float* __restrict__ mean_u3,
+                             __half* __restrict__ img, float* __restrict__ inv, float* __restrict__ mu_s) {
+    __shared__ float red[128];
+    const int c = (int)blockIdx.x, k = (int)threadIdx.x;
+    const float w = W3[(size_t)c * 128 + k];
+    red[k] = fabsf(w);
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if (k < s) red[k] = fmaxf(red[k], red[k + s]);
+        __syncthreads();
+    }
+    const float mx = red[0];
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);             // mx in [2^(ex-1), 2^ex)
+    const int e = (mx > 0.f) ? 14 - ex : 0;    // mx * 2^e in [2^13, 2^14)
+    const float sg = gamma3[c] >= 0.f ? 1.f : -1.f;
+    const float ws = ldexpf(w, e) * sg;
+    const __half hi = __float2half_rn(ws);
+    const __half lo = __float2half_rn(ws - __half2float(hi));
+    const int mt = c >> 7, r = c & 127, kb = k >> 6, j = k & 63, chunk = j >> 3, within = j & 7;
+    const size_t base = ((size_t)(mt * 2 + kb) * 2) * 8192;     // in halves: 16 KB = 8192 halves
+    const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
+    img[base + off] = hi;
+    img[base + 8192 + off] = lo;
+    if (k == 0) {
+        const float iv = sg * ldexpf(1.f, -(e + 4));
+        inv[c] = iv;
+        if (mu_s) mu_s[c] = mean_u3 ? mean_u3[c] / iv : 0.f;
+    }
+}
+
+struct L3Params {
+    const float* Y2;          // [M][128] layer-2 pre-activation
+    const float* scale2;      // [128]
+    const float* shift2;      // [128]
+    const __half* Wimg;       // pre-packed W3 image
+    const float* inv;         // [1024]
+    const float* mu_s;        // [1024] mean of u3 in accumulator units, or nullptr (no statistics)
+    unsigned long long* keys; // [B][1024] (ordered max value, ~arg-max)
+    float* css_part;          // [ntiles][1024]
+    int B, N, tiles_per_cloud, ntiles;
+};
+
+__global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // SWIZZLE_128B operand tiles need a 1024-byte aligned base: align by hand, do not rely on the attribute
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* misc = smem + L3_SMEM_MISC;
+    // barriers (8 bytes each)
+    const uint32_t bar0 = sbase + L3_SMEM_MISC;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // 0..2 w_full, 3..5 w_empty, 6 a2_full, 7 a2_empty, 8..9 tmem_full, 10..11 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+    float* s_scale = reinterpret_cast<float*>(misc + 256);     // [128] (pre-multiplied by 2^4)
+    float* s_shift = s_scale + 128;
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+        mbar_init(BAR(6), 128); mbar_init(BAR(7), 1);
+        mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
+        mbar_init(BAR(10), 128); mbar_init(BAR(11), 128);
+        mbar_fence_init();
+    }
+    if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
+    if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    // contiguous range of tiles for this CTA
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+
+    if (warp == 0) {
+        // ===================== W3 producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t)
+                for (int blk = 0; blk < 16; ++blk) {       // (mt, kb) in issue order
+                    mbar_wait(BAR(3 + stage), phase ^ 1);
+                    mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);
+                    bulk_g2s(sbase + L3_SMEM_W + stage * L3_STAGE_BYTES,
+                             reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES, L3_STAGE_BYTES, BAR(stage));
+                    if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_f16(128, L3_NT);
+            int stage = 0; uint32_t wphase = 0;
+            int acc = 0; uint32_t aphase = 0;
+            uint32_t a2phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                mbar_wait(BAR(6), a2phase);                 // a2 tile staged
+                tc_fence_after_sync();
+                for (int mt = 0; mt < 8; ++mt) {
+                    mbar_wait(BAR(10 + acc), aphase ^ 1);   // accumulator drained by the epilogue
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        mbar_wait(BAR(stage), wphase);      // weights landed
+                        tc_fence_after_sync();
+                        const uint32_t w_hi = sbase + L3_SMEM_W + stage * L3_STAGE_BYTES, w_lo = w_hi + 16384;
+                        const uint32_t b_hi = sbase + (0 * 2 + kb) * L3_A2_PART, b_lo = sbase + (1 * 2 + kb) * L3_A2_PART;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t wa = (pass == 1) ? w_lo : w_hi;
+                            const uint32_t bb = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(bb + k * 32), IDESC,
+                                        (kb | pass | k) ? 1u : 0u);
+                        }
+                        mma_commit(BAR(3 + stage));         // stage free once these MMAs have read it
+                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1; }
+                    }
+                    mma_commit(BAR(8 + acc));               // accumulator complete
+                    if (++acc == 2) { acc = 0; aphase ^= 1; }
+                }
+                mma_commit(BAR(7));                         // a2 tile no longer needed
+                a2phase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                             // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        int acc = 0; uint32_t aphase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
+            const int n0 = tt * L3_NT;
+            const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
+            for (int mt = 0; mt < 8; ++mt) {
+                const int ch = mt * 128 + row;
+                const float mu = p.mu_s ? p.mu_s[ch] : 0.f;
+                mbar_wait(BAR(8 + acc), aphase);
+                tc_fence_after_sync();
+                float best = -INFINITY; int bidx = 0; float css = 0.f;
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
+                for (int c0 = 0; c0 < L3_NT; c0 += 32) {
+                    if (c0 >= nvalid) break;                // warp-uniform
+                    float v[32];
+                    tmem_ld32(tbase + (uint32_t)c0, v);
+                    if (c0 + 32 <= nvalid) {
+                        float m = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                        if (p.mu_s) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
+                        }
+                        if (m > best) {
+                            best = m;
+                            int jj = 31;
+#pragma unroll
+                            for (int j = 30; j >= 0; --j) if (v[j] == m) jj = j;
+                            bidx = n0 + c0 + jj;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j < nvalid) {
+                                if (p.mu_s) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
+                                if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                mbar_arrive(BAR(10 + acc));                 // accumulator may be overwritten
+                if (++acc == 2) { acc = 0; aphase ^= 1; }
+                const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
+                                               (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
+                atomicMax(&p.keys[(size_t)b * C3 + ch], key);
+                if (p.mu_s) {
+                    const float iv = p.inv[ch];
+                    p.css_part[(size_t)t * C3 + ch] = css * iv * iv;
+                }
+            }
+        }
+    } else {
+        // ===================== a2 producer =====================
+        const int wp = warp - 6;                            // 0..3
+        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
+        const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
+        const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
+        uint32_t ephase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
+            const int n0 = tt * L3_NT;
+            const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
+            const float* src = p.Y2 + ((size_t)b * p.N + n0) * C2 + 4 * lane;
+            mbar_wait(BAR(7), ephase ^ 1);                  // previous tile's MMAs are done with a2
+            ephase ^= 1;
+#pragma unroll 4
+            for (int i = 0; i < L3_NT / 4; ++i) {
+                const int r = wp + 4 * i;
+                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool ok = r < nvalid;
+                if (ok) y = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
+                float a0 = ok ? fminf(fmaxf(fmaf(sc0, y.x, sh0), 0.f), 60000.f) : 0.f;
+                float a1 = ok ? fminf(fmaxf(fmaf(sc1, y.y, sh1), 0.f), 60000.f) : 0.f;
+                float a2 = ok ? fminf(fmaxf(fmaf(sc2, y.z, sh2), 0.f), 60000.f) : 0.f;
+                float a3 = ok ? fminf(fmaxf(fmaf(sc3, y.w, sh3), 0.f), 60000.f) : 0.f;
+                __half2 h01, l01, h23, l23;
+                split2(a0, a1, h01, l01);
+                split2(a2, a3, h23, l23);
+                const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(smem + (0 * 2 + kb) * L3_A2_PART + off) = hv;
+                *reinterpret_cast<uint2*>(smem + (1 * 2 + kb) * L3_A2_PART + off) = lv;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(BAR(6));
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// per-device one-time setup: is this an sm_100 part, and can the kernel have its shared memory?
+struct DevInfo { int state = 0; int sms = 148; };   // state: 0 unknown, 1 usable, -1 not usable
+inline DevInfo& dev_info() {
+    static DevInfo info[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevInfo& d = info[dev & 63];
+    if (d.state == 0) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (d.sms <= 0) d.sms = 148;
+        cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
+        d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
+        if (e != cudaSuccess) cudaGetLastError();
+    }
+    return d;
+}
+inline bool available() { return dev_info().state == 1; }
+
+}}  // namespace pgpd::tc

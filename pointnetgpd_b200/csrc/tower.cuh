@@ -19,6 +19,9 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#ifndef PGPD_EMU
+#include "tc_l3.cuh"
+#endif
 
 namespace pgpd {
 
@@ -40,8 +43,11 @@ struct TowerScratch {
     double* moments;  // [B][9]
     double* dpart;    // double partials, max(nb_a1*64, nb_a2*128)
     double* dsum;     // [128]
+    double* rtmp;     // [REDUCE_MAX_SLICES][16384] stage-1 output of the two-stage reductions
     float* fpart;     // float partials: max over users (see plan_tower_scratch)
     unsigned long long* keys;  // [B][1024]
+    void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
+    float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
     // backward scratch
     float* coef;      // [B][1024]
     float* dvec;      // [1024]
@@ -85,7 +91,8 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.nb_l2 = (int)((M + 127) / 128);
     w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
     w.nb_dw2 = (int)((M + DW2_CHUNK - 1) / DW2_CHUNK);
-    w.moments = c.take<double>((size_t)B * 9);
+    w.moments = c.take<double>((size_t)B * 12);
+    w.rtmp = c.take<double>((size_t)REDUCE_MAX_SLICES * C2 * C2);
     w.dpart = c.take<double>((size_t)std::max(w.nb_a1 * C1, w.nb_a2 * C2));
     w.dsum = c.take<double>(C2);
     size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
@@ -99,6 +106,8 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.fpart_elems = fp;
     w.fpart = c.take<float>(fp);
     w.keys = c.take<unsigned long long>((size_t)B * C3);
+    w.wimg = c.take<unsigned char>((size_t)512 * 1024);
+    w.mu_s = c.take<float>(C3);
     if (backward) {
         w.coef = c.take<float>((size_t)B * C3);
         w.dvec = c.take<float>(C3);
@@ -120,10 +129,11 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
 // forward kernels
 // ================================================================================================
 
-// per-cloud first and second moments of the raw input points, in double.
-// mom[b] = { sum x, sum y, sum z, sum xx, xy, xz, yy, yz, zz }
-__global__ void k_cloud_moments(const float* __restrict__ x, int N, double* __restrict__ mom) {
+// per-cloud first and second moments of the TRANSFORMED points x' = T^T x, in double.
+// mom[b] = { sum x'_i (3) , sum x'_i x'_i2 (3x3 row-major) }
+__global__ void k_cloud_moments(const float* __restrict__ x, const float* __restrict__ trans, int N, double* __restrict__ mom) {
     __shared__ double sh[256];
+    __shared__ double raw[9];
     const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
     const float* xb = x + (size_t)b * 3 * N;
     double acc[9];
@@ -141,46 +151,44 @@ __global__ void k_cloud_moments(const float* __restrict__ x, int N, double* __re
             if (tid < s) sh[tid] += sh[tid + s];
             __syncthreads();
         }
-        if (tid == 0) mom[(size_t)b * 9 + q] = sh[0];
+        if (tid == 0) raw[q] = sh[0];
         __syncthreads();
     }
-}
-
-// BatchNorm1 batch statistics, analytically from the cloud moments:
-//   u1 = W1 T^T x  =>  mean = W1 m,  var_c = w_c^T Cov w_c   with m, Cov the moments of x' = T^T x.
-__global__ void k_bn1_finalize(const double* __restrict__ mom, const float* __restrict__ trans, int B, int N,
-                               pgpd_lin conv, pgpd_bn bn, BnState st) {
-    const int c = (int)threadIdx.x;
-    if (c >= C1) return;
-    double m[3] = {0, 0, 0}, S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int b = 0; b < B; ++b) {
-        const double* q = mom + (size_t)b * 9;
-        double s[3] = {q[0], q[1], q[2]};
-        double X[3][3] = {{q[3], q[4], q[5]}, {q[4], q[6], q[7]}, {q[5], q[7], q[8]}};
+    if (tid < 12) {
         double T[3][3];
         for (int j = 0; j < 3; ++j)
             for (int i = 0; i < 3; ++i) T[j][i] = trans ? (double)trans[(size_t)b * 9 + j * 3 + i] : (i == j ? 1.0 : 0.0);
-        // x'_i = sum_j T[j][i] x_j
-        for (int i = 0; i < 3; ++i) {
-            double v = 0;
-            for (int j = 0; j < 3; ++j) v += T[j][i] * s[j];
-            m[i] += v;
+        const double s1[3] = {raw[0], raw[1], raw[2]};
+        const double X[3][3] = {{raw[3], raw[4], raw[5]}, {raw[4], raw[6], raw[7]}, {raw[5], raw[7], raw[8]}};
+        double v = 0.0;
+        if (tid < 3) {
+            for (int j = 0; j < 3; ++j) v += T[j][tid] * s1[j];
+        } else {
+            const int i = (tid - 3) / 3, i2 = (tid - 3) % 3;
+            for (int j = 0; j < 3; ++j)
+                for (int j2 = 0; j2 < 3; ++j2) v += T[j][i] * X[j][j2] * T[j2][i2];
         }
-        for (int i = 0; i < 3; ++i)
-            for (int i2 = 0; i2 < 3; ++i2) {
-                double v = 0;
-                for (int j = 0; j < 3; ++j)
-                    for (int j2 = 0; j2 < 3; ++j2) v += T[j][i] * X[j][j2] * T[j2][i2];
-                S[i][i2] += v;
-            }
+        mom[(size_t)b * 12 + tid] = v;
     }
-    const double count = (double)B * (double)N;
-    for (int i = 0; i < 3; ++i) m[i] /= count;
+}
+
+// BatchNorm1 batch statistics, analytically from the (slice-reduced) cloud moments:
+//   u1 = W1 x'  =>  mean = W1 m,  var_c = w_c^T Cov w_c   with m, Cov the moments of x' over all points.
+__global__ void k_bn1_finalize(const double* __restrict__ tmp, int S, double count,
+                               pgpd_lin conv, pgpd_bn bn, BnState st) {
+    const int c = (int)threadIdx.x;
+    if (c >= C1) return;
+    double q[12];
+    for (int e = 0; e < 12; ++e) {
+        double s = 0.0;
+        for (int i = 0; i < S; ++i) s += tmp[(size_t)i * 12 + e];
+        q[e] = s / count;
+    }
     double w[3] = {conv.w[c * 3 + 0], conv.w[c * 3 + 1], conv.w[c * 3 + 2]};
-    double mean_u = w[0] * m[0] + w[1] * m[1] + w[2] * m[2];
+    double mean_u = w[0] * q[0] + w[1] * q[1] + w[2] * q[2];
     double var = 0;
     for (int i = 0; i < 3; ++i)
-        for (int i2 = 0; i2 < 3; ++i2) var += w[i] * (S[i][i2] / count - m[i] * m[i2]) * w[i2];
+        for (int i2 = 0; i2 < 3; ++i2) var += w[i] * (q[3 + i * 3 + i2] - q[i] * q[i2]) * w[i2];
     bn_finalize_train(c, mean_u, var, count, conv.b, bn, st);
 }
 
@@ -757,6 +765,7 @@ struct TowerArgs {
     int B, N;
     bool relu_last, train, save;
     cudaStream_t stream;
+    bool use_tc;          // tcgen05 kernels where available (never in the emulator build)
 };
 
 inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
@@ -767,8 +776,9 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 
     // ---- layer 1 ---------------------------------------------------------------------------------
     if (a.train) {
-        launch(k_cloud_moments, dim3(a.B), dim3(256), 0, s, a.x, a.N, w.moments);
-        launch(k_bn1_finalize, dim3(1), dim3(64), 0, s, (const double*)w.moments, a.trans, a.B, a.N, t.conv[0], t.bn[0], w.bn[0]);
+        launch(k_cloud_moments, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, w.moments);
+        const int S = colreduce<double>(w.moments, a.B, 12, w.rtmp, s);
+        launch(k_bn1_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, count, t.conv[0], t.bn[0], w.bn[0]);
     } else {
         launch(k_bn_eval_affine, grid1d(C1, 128), dim3(128), 0, s, C1, t.conv[0].b, t.bn[0], w.bn[0]);
         launch(k_bn_eval_affine, grid1d(C2, 128), dim3(128), 0, s, C2, t.conv[1].b, t.bn[1], w.bn[1]);
@@ -779,7 +789,8 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 
     // ---- layer 2 ---------------------------------------------------------------------------------
     if (a.train) {
-        launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.dpart, w.nb_a1, C1, w.dsum);
+        const int S = colreduce<double>(w.dpart, w.nb_a1, C1, w.rtmp, s);
+        launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, w.dsum);
         launch(k_matvec_mean, dim3(1), dim3(128), 0, s, t.conv[1].w, C2, C1, (const double*)w.dsum, 1.0 / count, w.bn[1].mean);
     }
     {
@@ -787,26 +798,45 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         launch_gemm<ProbL2Fwd::Cfg>(p, dim3(w.nb_l2), s);
     }
     if (a.train) {
-        launch(k_bn_finalize_from_css, dim3(1), dim3(128), 0, s, (const float*)w.fpart, w.nb_l2, C2,
+        const int S = colreduce<float>(w.fpart, w.nb_l2, C2, w.rtmp, s);
+        launch(k_bn_finalize_from_css, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2,
                (const float*)w.bn[1].mean, count, t.conv[1].b, t.bn[1], w.bn[1]);
         // mean of layer-3 pre-activation: W3 * mean(a2)
         launch(k_a2_sum, dim3(w.nb_a2), dim3(256), 0, s, (const float*)w.Y2, M, w.bn[1], w.dpart);
-        launch(k_reduce_d, dim3(1), dim3(128), 0, s, (const double*)w.dpart, w.nb_a2, C2, w.S1);
+        const int S2 = colreduce<double>(w.dpart, w.nb_a2, C2, w.rtmp, s);
+        launch(k_reduce_d, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S2, C2, w.S1);
         launch(k_matvec_mean, grid1d(C3, 128), dim3(128), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.bn[2].mean);
     }
 
     // ---- layer 3 + max-pool ------------------------------------------------------------------------
-    launch(k_sign, grid1d(C3, 256), dim3(256), 0, s, t.bn[2].gamma, w.sgn, C3);
     cudaMemsetAsync(w.keys, 0, (size_t)a.B * C3 * sizeof(unsigned long long), s);
+    int n_css = 0;
+#ifndef PGPD_EMU
+    if (a.use_tc) {
+        const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
+        launch(tc::k_prepack_w3, dim3(C3), dim3(128), 0, s, t.conv[2].w, t.bn[2].gamma,
+               a.train ? (const float*)w.bn[2].mean : (const float*)nullptr, (__half*)w.wimg, w.sgn, w.mu_s);
+        tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
+                       w.keys, w.fpart, a.B, a.N, tpc, ntiles};
+        const int grid = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+        profiler().begin(s);
+        launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
+        profiler().end(s);
+        n_css = ntiles;
+    } else
+#endif
     {
+        launch(k_sign, grid1d(C3, 256), dim3(256), 0, s, t.bn[2].gamma, w.sgn, C3);
         ProbL3Fwd p{t.conv[2].w, w.Y2, w.bn[1].scale, w.bn[1].shift, w.sgn, a.train ? w.bn[2].mean : nullptr,
                     w.keys, w.fpart, a.N, w.tiles_per_cloud};
         profiler().begin(s);
         launch_gemm<ProbL3Fwd::Cfg>(p, dim3(w.tiles_per_cloud, C3 / 128, a.B), s);
         profiler().end(s);
+        n_css = a.B * w.tiles_per_cloud;
     }
     if (a.train) {
-        launch(k_bn_finalize_from_css, grid1d(C3, 128), dim3(128), 0, s, (const float*)w.fpart, a.B * w.tiles_per_cloud, C3,
+        const int S = colreduce<float>(w.fpart, n_css, C3, w.rtmp, s);
+        launch(k_bn_finalize_from_css, grid1d(C3, 128), dim3(128), 0, s, (const double*)w.rtmp, S, C3,
                (const float*)w.bn[2].mean, count, t.conv[2].b, t.bn[2], w.bn[2]);
     }
     launch(k_pool_finalize, grid1d((size_t)a.B * C3, 256), dim3(256), 0, s, (const unsigned long long*)w.keys,
@@ -828,7 +858,8 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     {
         ProbGram p{w.Y2, w.bn[1].scale, w.bn[1].shift, w.fpart, M};
         launch_gemm<ProbGram::Cfg>(p, dim3(w.nb_gram), s);
-        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const float*)w.fpart, w.nb_gram, C2 * C2, w.gram);
+        const int S = colreduce<float>(w.fpart, w.nb_gram, C2 * C2, w.rtmp, s);
+        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.gram);
     }
     // WG = W3 * Gram  [1024 x 128]
     {
@@ -852,27 +883,33 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     {
         ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
         launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
-        launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const float*)w.fpart, w.nb_l2, C2, count,
+        const int S = colreduce<float>(w.fpart, w.nb_l2, 2 * C2, w.rtmp, s);
+        launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2, count,
                g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
     }
     Dy2 dy{w.DZ2, w.Y2, w.bn[1], w.m1_2, w.m2_2};
     {
         ProbDW2 p{dy, w.A1, w.fpart, M};
         launch_gemm<ProbDW2::Cfg>(p, dim3(w.nb_dw2), s);
-        launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const float*)w.fpart, w.nb_dw2, C2 * C1, g.conv[1].dw);
+        const int S = colreduce<float>(w.fpart, w.nb_dw2, C2 * C1, w.rtmp, s);
+        launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C1, g.conv[1].dw);
         launch(k_fill, grid1d(C2, 128), dim3(128), 0, s, g.conv[1].db, (size_t)C2, 0.f);
     }
     {
         ProbDA1 p{dy, t.conv[1].w, w.A1, a.x, a.trans, t.conv[0].w, w.bn[0], w.DZ1, w.fpart, M, a.N};
         launch_gemm<ProbDA1::Cfg>(p, dim3(w.nb_l2), s);
-        launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const float*)w.fpart, w.nb_l2, C1, count,
+        const int S = colreduce<float>(w.fpart, w.nb_l2, 2 * C1, w.rtmp, s);
+        launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, count,
                g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
     }
 
     // ---- layer 1 backward ---------------------------------------------------------------------------
     launch(k_l1_bwd, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, t.conv[0].w, w.bn[0], (const float*)w.DZ1,
            (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr);
-    launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const float*)w.fpart, a.B, C1 * 3, g.conv[0].dw);
+    {
+        const int S = colreduce<float>(w.fpart, a.B, C1 * 3, w.rtmp, s);
+        launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const double*)w.rtmp, S, C1 * 3, g.conv[0].dw);
+    }
     launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
 }
 
