@@ -1,0 +1,455 @@
+// tc_stream.cuh -- generic tcgen05 "streaming" GEMM over the points of a batch, points on the MMA N axis:
+//
+//     D[r][P] = sum_k A[r][k] * Bop(P)[k]        r < 128 output features (TMEM lanes), P = point (columns)
+//
+// A (a 128 x KD weight matrix, KD = 64 or 128) is pre-packed once (hi/lo fp16, 128-byte swizzle) and stays
+// resident in shared memory; the B operand of each 128-point tile is produced on the fly from global
+// memory by 4 producer warps (any element-wise transform), double buffered; accumulators ping-pong in
+// TMEM; 4 epilogue warps consume them with a per-kernel functor (stores, masks, per-feature sums).
+// Same 3-pass hi/lo fp16 scheme and warp roles as tc_l3.cuh (which differs by streaming 8 weight blocks).
+//
+// Used for: layer-2 forward (64 -> 128), the layer-2 backward passes (Q a2 and W2^T dy2).
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace pgpd { namespace tc {
+
+constexpr int ST_NT = 128;                 // points per tile
+constexpr int ST_THREADS = 320;
+constexpr float ACT_SCALE = 16.0f;         // 2^4 applied to O(1) activations before the fp16 split
+constexpr int ACT_SHIFT = 4;
+
+// ---- generic weight pre-pack ---------------------------------------------------------------------------
+// A[r][k] = W[r*sr + k*sk] for r < rows_valid (zero rows above), r < 128, k < KD.
+// image: [kb][part(hi,lo)][128 rows][64 halves] with the 128-byte swizzle; inv[r] = 2^-(e_r + extra_shift)
+// where 2^e_r brings the row maximum into [2^13, 2^14).  grid = 128 rows, block = KD threads.
+__global__ void k_prepack_rows(const float* __restrict__ W, int sr, int sk, int rows_valid, int KD, int extra_shift,
+                               __half* __restrict__ img, float* __restrict__ inv) {
+    __shared__ float red[128];
+    const int r = (int)blockIdx.x, k = (int)threadIdx.x;
+    const float w = (r < rows_valid) ? W[(size_t)r * sr + (size_t)k * sk] : 0.f;
+    red[k] = fabsf(w);
+    __syncthreads();
+    for (int s = KD >> 1; s > 0; s >>= 1) {
+        if (k < s) red[k] = fmaxf(red[k], red[k + s]);
+        __syncthreads();
+    }
+    const float mx = red[0];
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int e = (mx > 0.f) ? 14 - ex : 0;
+    const float ws = ldexpf(w, e);
+    const __half hi = __float2half_rn(ws);
+    const __half lo = __float2half_rn(ws - __half2float(hi));
+    const int kb = k >> 6, j = k & 63, chunk = j >> 3, within = j & 7;
+    const size_t base = (size_t)(kb * 2) * 8192;
+    const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
+    img[base + off] = hi;
+    img[base + 8192 + off] = lo;
+    if (k == 0) inv[r] = ldexpf(1.f, -(e + extra_shift));
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------------
+// Traits T provides:
+//   static constexpr int KD;                       // 64 or 128
+//   struct Params { const __half* Aimg; size_t M; int ntiles; ... };
+//   struct Epi { ... };                            // per-thread epilogue state (one output feature)
+//   struct Prod { ... };                           // per-thread producer state (constants of channel group cg)
+//   __device__ static void prod_begin(Prod&, const Params&, int cg);
+//   struct Raw { ... };                            // what one lane loads from global memory for one row
+//   __device__ static void  fetch(Prod&, const Params&, size_t P, bool valid, int cg, Raw&);      // loads only
+//   __device__ static float transform(Prod&, const Params&, size_t P, bool valid, int cg, const Raw&, float (&v)[4]);
+//        values of channels 4*cg .. 4*cg+3 of point P, ALREADY SCALED into fp16 range.  Called by all 32 lanes of
+//        a warp for one row (KD=128) or two rows (KD=64: lanes 0-15 / 16-31).  The return value of lanes cg < 4
+//        is stored as per-point auxiliary value aux[cg][row] for the epilogue (e.g. the factor undoing a
+//        per-point scale).
+//   __device__ static void epi_begin(Epi&, const Params&, int feat);
+//   __device__ static void epi_cols(Epi&, const Params&, int feat, size_t P0, int nvalid, const float (&v)[32], const float* aux);
+//        32 consecutive points P0.. of output feature `feat`; columns >= nvalid are padding; aux[k*128 + j] is the
+//        k-th auxiliary value of column j.
+//   __device__ static void epi_end(Epi&, const Params&, int feat, int cta);
+template <class T>
+struct StreamCfg {
+    static constexpr int KD = T::KD, NKB = KD / 64;
+    static constexpr int A_BYTES = NKB * 2 * 16384;
+    static constexpr int B_BYTES = NKB * 2 * 16384;              // one buffer: [part][kb][128 rows][128 B]
+    static constexpr int OFF_B = A_BYTES;
+    static constexpr int OFF_MISC = A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = OFF_MISC + 256 + 4096 + 1024;
+};
+
+template <class T>
+__global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params p) {
+    using Cfg = StreamCfg<T>;
+    constexpr int NKB = Cfg::NKB;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* misc = smem + Cfg::OFF_MISC;
+    const uint32_t bar0 = sbase + Cfg::OFF_MISC;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // 0 a_full, 1..2 b_full, 3..4 b_empty, 5..6 tmem_full, 7..8 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+    float* s_aux = reinterpret_cast<float*>(misc + 256);           // [2 buffers][4][128] (4 KB)
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(BAR(0), 1);
+        mbar_init(BAR(1), 128); mbar_init(BAR(2), 128);
+        mbar_init(BAR(3), 1); mbar_init(BAR(4), 1);
+        mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
+        mbar_init(BAR(7), 128); mbar_init(BAR(8), 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+
+    if (warp == 0) {
+        // ===================== weight loader (once) =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(BAR(0), Cfg::A_BYTES);
+            bulk_g2s(sbase, p.Aimg, Cfg::A_BYTES, BAR(0));
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_f16(128, ST_NT);
+            mbar_wait(BAR(0), 0);
+            tc_fence_after_sync();
+            uint32_t phase = 0;
+            int buf = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                mbar_wait(BAR(1 + buf), phase);             // operand tile staged
+                mbar_wait(BAR(7 + buf), phase ^ 1);         // accumulator drained
+                tc_fence_after_sync();
+                const uint32_t d = tmem + (uint32_t)(buf * ST_NT);
+                const uint32_t bb = sbase + Cfg::OFF_B + buf * Cfg::B_BYTES;
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                    const uint32_t a_hi = sbase + (kb * 2 + 0) * 16384, a_lo = sbase + (kb * 2 + 1) * 16384;
+                    const uint32_t b_hi = bb + (0 * NKB + kb) * 16384, b_lo = bb + (1 * NKB + kb) * 16384;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
+                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC,
+                                    (kb | pass | k) ? 1u : 0u);
+                    }
+                }
+                mma_commit(BAR(3 + buf));                   // operand buffer free
+                mma_commit(BAR(5 + buf));                   // accumulator complete
+                if (++buf == 2) { buf = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int feat = q * 32 + lane;
+        typename T::Epi st;
+        T::epi_begin(st, p, feat);
+        uint32_t phase = 0;
+        int buf = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const size_t P0 = (size_t)t * ST_NT;
+            const int nvalid = (p.M - P0 < (size_t)ST_NT) ? (int)(p.M - P0) : ST_NT;
+            mbar_wait(BAR(5 + buf), phase);
+            tc_fence_after_sync();
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ST_NT);
+            for (int c0 = 0; c0 < ST_NT; c0 += 32) {
+                if (c0 >= nvalid) break;
+                float v[32];
+                tmem_ld32(tbase + (uint32_t)c0, v);
+                T::epi_cols(st, p, feat, P0 + c0, nvalid - c0, v, s_aux + buf * 512 + c0);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(BAR(7 + buf));
+            if (++buf == 2) { buf = 0; phase ^= 1; }
+        }
+        T::epi_end(st, p, feat, cta);
+    } else {
+        // ===================== operand producer =====================
+        const int wp = warp - 6;
+        constexpr int LPR = Cfg::KD / 4;                    // lanes per row: 32 (KD=128) or 16 (KD=64)
+        constexpr int RPI = 32 / LPR;                       // rows per warp iteration: 1 or 2
+        const int cg = lane % LPR, rsub = lane / LPR;
+        const int kb = cg >> 4, chunk = (cg & 15) >> 1, half8 = cg & 1;
+        typename T::Prod ps;
+        T::prod_begin(ps, p, cg);
+        uint32_t phase = 0;
+        int buf = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const size_t P0 = (size_t)t * ST_NT;
+            const int nvalid = (p.M - P0 < (size_t)ST_NT) ? (int)(p.M - P0) : ST_NT;
+            mbar_wait(BAR(3 + buf), phase ^ 1);             // MMAs of two tiles ago are done with this buffer
+            mbar_wait(BAR(7 + buf), phase ^ 1);             // ... and its epilogue no longer reads aux[buf]
+            unsigned char* bb = smem + Cfg::OFF_B + buf * Cfg::B_BYTES;
+            constexpr int ITERS = ST_NT / (4 * RPI), U = 4;
+            for (int i0 = 0; i0 < ITERS; i0 += U) {
+                typename T::Raw raw[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {               // all global loads of U rows first (memory-level parallelism)
+                    const int r = (wp + 4 * (i0 + u)) * RPI + rsub;
+                    T::fetch(ps, p, P0 + r, r < nvalid, cg, raw[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int r = (wp + 4 * (i0 + u)) * RPI + rsub;
+                    float v[4];
+                    const float aux = T::transform(ps, p, P0 + r, r < nvalid, cg, raw[u], v);
+                    __half2 h01, l01, h23, l23;
+                    split2(v[0], v[1], h01, l01);
+                    split2(v[2], v[3], h23, l23);
+                    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(bb + (0 * NKB + kb) * 16384 + off) = hv;
+                    *reinterpret_cast<uint2*>(bb + (1 * NKB + kb) * 16384 + off) = lv;
+                    if (cg < 4) s_aux[buf * 512 + cg * 128 + r] = aux;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(BAR(1 + buf));
+            if (++buf == 2) { buf = 0; phase ^= 1; }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+template <class T>
+inline bool stream_configure() {
+    static int done[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_stream_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<T>::SMEM_BYTES);
+        done[dev & 63] = (e == cudaSuccess) ? 1 : -1;
+        if (e != cudaSuccess) cudaGetLastError();
+    }
+    return done[dev & 63] == 1;
+}
+
+template <class T>
+inline void launch_stream(const typename T::Params& p, int sms, cudaStream_t s) {
+    stream_configure<T>();
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    launch(k_stream_tc<T>, dim3(grid), dim3(ST_THREADS), (size_t)StreamCfg<T>::SMEM_BYTES, s, p);
+}
+
+// ==================================================================================================================
+// layer 2 forward:  u2[P][c] = sum_k W2[c][k] a1[P][k];   store u2, accumulate sum (u2 - mean)^2 per channel
+// ==================================================================================================================
+struct L2FwdTC {
+    static constexpr int KD = 64;
+    struct Params {
+        const __half* Aimg; size_t M; int ntiles;
+        const float* A1; const float* inv; const float* mean_u2; float* Y2; float* css_part;   // css_part [G][128]
+    };
+    struct Epi { float inv, mu, css; };
+    struct Prod { int dummy; };
+    __device__ static void prod_begin(Prod&, const Params&, int) {}
+    struct Raw { float4 a; };
+    __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
+        r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) r.a = *reinterpret_cast<const float4*>(p.A1 + P * C1 + 4 * cg);
+    }
+    __device__ static float transform(Prod&, const Params&, size_t, bool, int, const Raw& r, float (&v)[4]) {
+        v[0] = fminf(r.a.x * ACT_SCALE, 60000.f); v[1] = fminf(r.a.y * ACT_SCALE, 60000.f);
+        v[2] = fminf(r.a.z * ACT_SCALE, 60000.f); v[3] = fminf(r.a.w * ACT_SCALE, 60000.f);
+        return 1.f;
+    }
+    __device__ static void epi_begin(Epi& e, const Params& p, int c) { e.inv = p.inv[c]; e.mu = p.mean_u2 ? p.mean_u2[c] : 0.f; e.css = 0.f; }
+    __device__ static void epi_cols(Epi& e, const Params& p, int c, size_t P0, int nvalid, const float (&v)[32], const float*) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+                const float u = v[j] * e.inv;
+                p.Y2[(P0 + j) * C2 + c] = u;
+                const float d = u - e.mu;
+                e.css = fmaf(d, d, e.css);
+            }
+        }
+    }
+    __device__ static void epi_end(Epi& e, const Params& p, int c, int cta) { if (p.mean_u2) p.css_part[(size_t)cta * C2 + c] = e.css; }
+};
+
+// ==================================================================================================================
+// layer 2 backward, pass 1:  d a2[P][i] = sparse - u_i - sum_j Q[i][j] a2[P][j];  dz2 = mask * d a2 (stored);
+// per-channel sums of dz2 and dz2*yhat2 (BatchNorm2 backward) and maxima of |dz2|, |yhat2| (operand scaling)
+// ==================================================================================================================
+struct L2BwdATC {
+    static constexpr int KD = 128;
+    struct Params {
+        const __half* Aimg; size_t M; int ntiles;
+        const float* Y2; const float* scale2; const float* shift2; const float* mean2; const float* rstd2;
+        const float* inv; const float* uvec; const float* da2s; const int* slot;
+        float* DZ2; float* part;     // part [G][2][128]: sum dz, sum dz*yhat
+        float* pmax;                 // pmax [G][2][128]: max|dz|, max|yhat|
+    };
+    struct Epi { float inv, u, sc, sh, mu, r, s1, s2, mxdz, mxyh; };
+    struct Prod { float4 sc, sh; };
+    __device__ static void prod_begin(Prod& s, const Params& p, int cg) {
+        s.sc = *reinterpret_cast<const float4*>(p.scale2 + 4 * cg);
+        s.sh = *reinterpret_cast<const float4*>(p.shift2 + 4 * cg);
+        s.sc.x *= ACT_SCALE; s.sc.y *= ACT_SCALE; s.sc.z *= ACT_SCALE; s.sc.w *= ACT_SCALE;
+        s.sh.x *= ACT_SCALE; s.sh.y *= ACT_SCALE; s.sh.z *= ACT_SCALE; s.sh.w *= ACT_SCALE;
+    }
+    struct Raw { float4 y; };
+    __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
+        r.y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
+    }
+    __device__ static float transform(Prod& s, const Params&, size_t, bool valid, int, const Raw& r, float (&v)[4]) {
+        const float4 y = r.y;
+        v[0] = valid ? fminf(fmaxf(fmaf(s.sc.x, y.x, s.sh.x), 0.f), 60000.f) : 0.f;
+        v[1] = valid ? fminf(fmaxf(fmaf(s.sc.y, y.y, s.sh.y), 0.f), 60000.f) : 0.f;
+        v[2] = valid ? fminf(fmaxf(fmaf(s.sc.z, y.z, s.sh.z), 0.f), 60000.f) : 0.f;
+        v[3] = valid ? fminf(fmaxf(fmaf(s.sc.w, y.w, s.sh.w), 0.f), 60000.f) : 0.f;
+        return 1.f;
+    }
+    __device__ static void epi_begin(Epi& e, const Params& p, int c) {
+        e.inv = p.inv[c]; e.u = p.uvec[c]; e.sc = p.scale2[c]; e.sh = p.shift2[c]; e.mu = p.mean2[c]; e.r = p.rstd2[c];
+        e.s1 = 0.f; e.s2 = 0.f; e.mxdz = 0.f; e.mxyh = 0.f;
+    }
+    __device__ static void epi_cols(Epi& e, const Params& p, int c, size_t P0, int nvalid, const float (&v)[32], const float*) {
+        // phase 1: every global load of the 32 columns (kept apart from the stores so they overlap)
+        float y[32], ds[32];
+        int sl[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const bool ok = j < nvalid;
+            y[j] = ok ? __ldg(p.Y2 + (P0 + j) * C2 + c) : 0.f;
+            sl[j] = ok ? __ldg(p.slot + P0 + j) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ds[j] = (sl[j] >= 0) ? __ldg(p.da2s + (size_t)sl[j] * C2 + c) : 0.f;
+        // phase 2: arithmetic + stores
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+                const float da2 = -v[j] * e.inv - e.u + ds[j];
+                const float dz = (e.sc * y[j] + e.sh > 0.f) ? da2 : 0.f;
+                p.DZ2[(P0 + j) * C2 + c] = dz;
+                const float yh = (y[j] - e.mu) * e.r;
+                e.s1 += dz;
+                e.s2 = fmaf(dz, yh, e.s2);
+                e.mxdz = fmaxf(e.mxdz, fabsf(dz));
+                e.mxyh = fmaxf(e.mxyh, fabsf(yh));
+            }
+        }
+    }
+    __device__ static void epi_end(Epi& e, const Params& p, int c, int cta) {
+        float* o = p.part + (size_t)cta * 2 * C2;
+        o[c] = e.s1; o[C2 + c] = e.s2;
+        float* m = p.pmax + (size_t)cta * 2 * C2;
+        m[c] = e.mxdz; m[C2 + c] = e.mxyh;
+    }
+};
+
+// ==================================================================================================================
+// layer 2 backward, pass 2b:  d a1[P][k] = sum_c W2[c][k] dy2[P][c],  dy2 = s2 (dz2 - m1 - yhat2 m2);
+// dz1 = mask * d a1 (stored); per-channel sums of dz1 and dz1*yhat1 (BatchNorm1 backward).
+// dy2 rows are scaled per POINT by a power of two (gradients have no fixed magnitude); aux[0] undoes it,
+// aux[1..3] carry the transformed coordinates x' of the point (for yhat1 = (W1 x' - mean1) * rstd1).
+// ==================================================================================================================
+struct L2BwdBTC {
+    static constexpr int KD = 128;
+    struct Params {
+        const __half* Aimg; size_t M; int ntiles;
+        const float* DZ2; const float* Y2; const float* scale2; const float* mean2; const float* rstd2;
+        const float* m1; const float* m2;
+        const float* x; const float* trans; int N;
+        const float* inv; const float* A1; const float* W1; const float* mean1; const float* rstd1;
+        float* DZ1; float* part;     // part [G][2][64]
+    };
+    struct Prod { float4 s, mu, r, m1, m2; };
+    __device__ static void prod_begin(Prod& q, const Params& p, int cg) {
+        q.s = *reinterpret_cast<const float4*>(p.scale2 + 4 * cg);
+        q.mu = *reinterpret_cast<const float4*>(p.mean2 + 4 * cg);
+        q.r = *reinterpret_cast<const float4*>(p.rstd2 + 4 * cg);
+        q.m1 = *reinterpret_cast<const float4*>(p.m1 + 4 * cg);
+        q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
+    }
+    struct Raw { float4 dz, y; float xa; };
+    __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
+        r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz; r.xa = 0.f;
+        if (valid) {
+            r.dz = *reinterpret_cast<const float4*>(p.DZ2 + P * C2 + 4 * cg);
+            r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
+            if (cg >= 1 && cg < 4) {
+                // transformed coordinate x'_(cg-1) of this point
+                const int b = (int)(P / p.N), n = (int)(P % p.N), i = cg - 1;
+                const float* xb = p.x + (size_t)b * 3 * p.N;
+                const float p0 = xb[n], p1 = xb[p.N + n], p2 = xb[2 * p.N + n];
+                if (p.trans) {
+                    const float* Tm = p.trans + (size_t)b * 9;
+                    r.xa = Tm[i] * p0 + Tm[3 + i] * p1 + Tm[6 + i] * p2;
+                } else {
+                    r.xa = i == 0 ? p0 : (i == 1 ? p1 : p2);
+                }
+            }
+        }
+    }
+    __device__ static float transform(Prod& q, const Params&, size_t, bool valid, int cg, const Raw& r, float (&v)[4]) {
+        const float4 dz = r.dz, y = r.y;
+        float d0 = q.s.x * (dz.x - q.m1.x - (y.x - q.mu.x) * q.r.x * q.m2.x);
+        float d1 = q.s.y * (dz.y - q.m1.y - (y.y - q.mu.y) * q.r.y * q.m2.y);
+        float d2 = q.s.z * (dz.z - q.m1.z - (y.z - q.mu.z) * q.r.z * q.m2.z);
+        float d3 = q.s.w * (dz.w - q.m1.w - (y.w - q.mu.w) * q.r.w * q.m2.w);
+        if (!valid) { d0 = d1 = d2 = d3 = 0.f; }
+        float mx = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        // power of two 2^e bringing the row maximum into [2^13, 2^14): e = 140 - biased_exponent(mx)
+        int e = 140 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+        e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
+        const float sc = __uint_as_float((uint32_t)(127 + e) << 23);
+        v[0] = d0 * sc; v[1] = d1 * sc; v[2] = d2 * sc; v[3] = d3 * sc;
+        return (cg == 0) ? __uint_as_float((uint32_t)(127 - e) << 23) : r.xa;
+    }
+    struct Epi { float inv, w0, w1, w2, mu, r, s1, s2; };
+    __device__ static void epi_begin(Epi& e, const Params& p, int k) {
+        e.s1 = 0.f; e.s2 = 0.f;
+        if (k < C1) {
+            e.inv = p.inv[k]; e.w0 = p.W1[k * 3 + 0]; e.w1 = p.W1[k * 3 + 1]; e.w2 = p.W1[k * 3 + 2];
+            e.mu = p.mean1[k]; e.r = p.rstd1[k];
+        } else { e.inv = e.w0 = e.w1 = e.w2 = e.mu = e.r = 0.f; }
+    }
+    __device__ static void epi_cols(Epi& e, const Params& p, int k, size_t P0, int nvalid, const float (&v)[32], const float* aux) {
+        if (k >= C1) return;
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = (j < nvalid) ? __ldg(p.A1 + (P0 + j) * C1 + k) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+                const float da1 = v[j] * e.inv * aux[j];
+                const float dz = a[j] > 0.f ? da1 : 0.f;
+                p.DZ1[(P0 + j) * C1 + k] = dz;
+                const float u = e.w0 * aux[128 + j] + e.w1 * aux[256 + j] + e.w2 * aux[384 + j];
+                const float yh = (u - e.mu) * e.r;
+                e.s1 += dz;
+                e.s2 = fmaf(dz, yh, e.s2);
+            }
+        }
+    }
+    __device__ static void epi_end(Epi& e, const Params& p, int k, int cta) {
+        if (k >= C1) return;
+        float* o = p.part + (size_t)cta * 2 * C1;
+        o[k] = e.s1; o[C1 + k] = e.s2;
+    }
+};
+
+}}  // namespace pgpd::tc

@@ -21,6 +21,8 @@
 #include "gemm_simt.cuh"
 #ifndef PGPD_EMU
 #include "tc_l3.cuh"
+#include "tc_stream.cuh"
+#include "tc_accum.cuh"
 #endif
 
 namespace pgpd {
@@ -48,6 +50,11 @@ struct TowerScratch {
     unsigned long long* keys;  // [B][1024]
     void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
+    void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
+    float* inv_s;     // [128] its per-row inverse scales
+    float* pmax;      // [256][2][128] per-CTA maxima of |dz2|, |yhat2|
+    float* esc;       // [128] per-channel power-of-two scale of dy2 (tcgen05 dW2)
+    float* einv;      // [128] its inverse
     // backward scratch
     float* coef;      // [B][1024]
     float* dvec;      // [1024]
@@ -108,6 +115,11 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.keys = c.take<unsigned long long>((size_t)B * C3);
     w.wimg = c.take<unsigned char>((size_t)512 * 1024);
     w.mu_s = c.take<float>(C3);
+    w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
+    w.inv_s = c.take<float>(C2);
+    w.pmax = c.take<float>((size_t)256 * 2 * C2);
+    w.esc = c.take<float>(C2);
+    w.einv = c.take<float>(C2);
     if (backward) {
         w.coef = c.take<float>((size_t)B * C3);
         w.dvec = c.take<float>(C3);
@@ -793,12 +805,24 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, w.dsum);
         launch(k_matvec_mean, dim3(1), dim3(128), 0, s, t.conv[1].w, C2, C1, (const double*)w.dsum, 1.0 / count, w.bn[1].mean);
     }
+    int n_css2 = 0;
+#ifndef PGPD_EMU
+    if (a.use_tc) {
+        launch(tc::k_prepack_rows, dim3(128), dim3(C1), 0, s, t.conv[1].w, C1, 1, C2, C1, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
+        const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
+        tc::L2FwdTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.A1, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
+                              w.Y2, w.fpart};
+        tc::launch_stream<tc::L2FwdTC>(p, tc::dev_info().sms, s);
+        n_css2 = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+    } else
+#endif
     {
         ProbL2Fwd p{w.A1, t.conv[1].w, w.Y2, a.train ? w.bn[1].mean : nullptr, w.fpart, M};
         launch_gemm<ProbL2Fwd::Cfg>(p, dim3(w.nb_l2), s);
+        n_css2 = w.nb_l2;
     }
     if (a.train) {
-        const int S = colreduce<float>(w.fpart, w.nb_l2, C2, w.rtmp, s);
+        const int S = colreduce<float>(w.fpart, n_css2, C2, w.rtmp, s);
         launch(k_bn_finalize_from_css, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2,
                (const float*)w.bn[1].mean, count, t.conv[1].b, t.bn[1], w.bn[1]);
         // mean of layer-3 pre-activation: W3 * mean(a2)
@@ -856,9 +880,19 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
 
     // ---- Gram matrix of a2 -------------------------------------------------------------------------
     {
-        ProbGram p{w.Y2, w.bn[1].scale, w.bn[1].shift, w.fpart, M};
-        launch_gemm<ProbGram::Cfg>(p, dim3(w.nb_gram), s);
-        const int S = colreduce<float>(w.fpart, w.nb_gram, C2 * C2, w.rtmp, s);
+        int nrows = 0;
+#ifndef PGPD_EMU
+        if (a.use_tc) {
+            tc::GramTC::Params p{M, (int)((M + tc::AC_NT - 1) / tc::AC_NT), w.fpart, w.Y2, w.bn[1].scale, w.bn[1].shift};
+            nrows = tc::launch_accum<tc::GramTC>(p, tc::dev_info().sms, s);
+        } else
+#endif
+        {
+            ProbGram p{w.Y2, w.bn[1].scale, w.bn[1].shift, w.fpart, M};
+            launch_gemm<ProbGram::Cfg>(p, dim3(w.nb_gram), s);
+            nrows = w.nb_gram;
+        }
+        const int S = colreduce<float>(w.fpart, nrows, C2 * C2, w.rtmp, s);
         launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.gram);
     }
     // WG = W3 * Gram  [1024 x 128]
@@ -880,25 +914,70 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     launch(k_da2_sparse, dim3(a.B), dim3(C3), 0, s, (const float*)w.coef, (const int*)w.idx, t.conv[2].w, a.N, w.da2s, w.slot);
 
     // ---- layer 2 backward ---------------------------------------------------------------------------
+    int g_b4 = 0;   // CTAs of the tcgen05 pass-1 kernel (rows of pmax)
     {
-        ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
-        launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
-        const int S = colreduce<float>(w.fpart, w.nb_l2, 2 * C2, w.rtmp, s);
+        int nrows = 0;
+#ifndef PGPD_EMU
+        if (a.use_tc) {
+            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
+            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
+            tc::L2BwdATC::Params p{(const __half*)w.wimg_s, M, ntiles, w.Y2, w.bn[1].scale, w.bn[1].shift, w.bn[1].mean, w.bn[1].rstd,
+                                   w.inv_s, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, w.pmax};
+            tc::launch_stream<tc::L2BwdATC>(p, tc::dev_info().sms, s);
+            nrows = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+            g_b4 = nrows;
+        } else
+#endif
+        {
+            ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
+            launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
+            nrows = w.nb_l2;
+        }
+        const int S = colreduce<float>(w.fpart, nrows, 2 * C2, w.rtmp, s);
         launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2, count,
                g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
     }
     Dy2 dy{w.DZ2, w.Y2, w.bn[1], w.m1_2, w.m2_2};
     {
-        ProbDW2 p{dy, w.A1, w.fpart, M};
-        launch_gemm<ProbDW2::Cfg>(p, dim3(w.nb_dw2), s);
-        const int S = colreduce<float>(w.fpart, w.nb_dw2, C2 * C1, w.rtmp, s);
+        int nrows = 0;
+#ifndef PGPD_EMU
+        if (a.use_tc) {
+            launch(tc::k_dy2_scale, dim3(1), dim3(128), 0, s, (const float*)w.pmax, g_b4, (const float*)w.bn[1].scale,
+                   (const float*)w.m1_2, (const float*)w.m2_2, w.esc, w.einv);
+            tc::DW2TC::Params p{M, (int)((M + tc::AC_NT - 1) / tc::AC_NT), w.fpart, w.DZ2, w.Y2, w.bn[1].scale, w.bn[1].mean, w.bn[1].rstd,
+                                w.m1_2, w.m2_2, w.esc, w.einv, w.A1};
+            nrows = tc::launch_accum<tc::DW2TC>(p, tc::dev_info().sms, s);
+        } else
+#endif
+        {
+            ProbDW2 p{dy, w.A1, w.fpart, M};
+            launch_gemm<ProbDW2::Cfg>(p, dim3(w.nb_dw2), s);
+            nrows = w.nb_dw2;
+        }
+        const int S = colreduce<float>(w.fpart, nrows, C2 * C1, w.rtmp, s);
         launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C1, g.conv[1].dw);
         launch(k_fill, grid1d(C2, 128), dim3(128), 0, s, g.conv[1].db, (size_t)C2, 0.f);
     }
     {
-        ProbDA1 p{dy, t.conv[1].w, w.A1, a.x, a.trans, t.conv[0].w, w.bn[0], w.DZ1, w.fpart, M, a.N};
-        launch_gemm<ProbDA1::Cfg>(p, dim3(w.nb_l2), s);
-        const int S = colreduce<float>(w.fpart, w.nb_l2, 2 * C1, w.rtmp, s);
+        int nrows = 0;
+#ifndef PGPD_EMU
+        if (a.use_tc) {
+            // A = W2^T padded to 128 rows: A[k][c] = W2[c][k]
+            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, t.conv[1].w, 1, C1, C1, C2, 0, (__half*)w.wimg_s, w.inv_s);
+            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
+            tc::L2BwdBTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.DZ2, w.Y2, w.bn[1].scale, w.bn[1].mean, w.bn[1].rstd,
+                                   w.m1_2, w.m2_2, a.x, a.trans, a.N, w.inv_s, w.A1, t.conv[0].w, w.bn[0].mean, w.bn[0].rstd,
+                                   w.DZ1, w.fpart};
+            tc::launch_stream<tc::L2BwdBTC>(p, tc::dev_info().sms, s);
+            nrows = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+        } else
+#endif
+        {
+            ProbDA1 p{dy, t.conv[1].w, w.A1, a.x, a.trans, t.conv[0].w, w.bn[0], w.DZ1, w.fpart, M, a.N};
+            launch_gemm<ProbDA1::Cfg>(p, dim3(w.nb_l2), s);
+            nrows = w.nb_l2;
+        }
+        const int S = colreduce<float>(w.fpart, nrows, 2 * C1, w.rtmp, s);
         launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, count,
                g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
     }

@@ -16,7 +16,8 @@
 
 struct Variant {
     const char* name;
-    int layout;        // 0 = K-major SWIZZLE_128B (8 x 128 B atoms), 1 = K-major no swizzle (8 x 16 B core matrices)
+    int layout;        // 0 = K-major SWIZZLE_128B (8 x 128 B atoms), 1 = K-major no swizzle (8 x 16 B core matrices),
+                       // 2 = MN-major SWIZZLE_128B: rows indexed by k, 128 B (64 elements of M/N) per row, one 64-wide atom after another
     int kind;          // 0 = f16 (fp16 operands), 1 = tf32 (fp32 operands)
     int split;         // 0 = single pass, 1 = hi/lo 3-pass
     uint32_t lbo, sbo; // bytes; 0xFFFFFFFF = derive from layout
@@ -86,6 +87,20 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
     unsigned char* sB_lo = sB_hi + b_bytes;
 
     // ---- fill operands (generic proxy writes) ----
+    if (v.layout == 2) {
+        // element (mn, k) of an operand with `rows` M/N rows: atom = mn/64 at atom*(K*128) ; row k at k*128 ; chunk = (mn%64)/8 ^ (k&7)
+        for (int idx = tid; idx < (128 + NB) * K; idx += 128) {
+            const bool isA = idx < 128 * K;
+            const int li = isA ? idx : idx - 128 * K;
+            const int mn = li / K, k = li % K;
+            const float f = (isA ? A : B)[(size_t)mn * K + k];
+            const __half h = __float2half_rn(f);
+            const __half l = __float2half_rn(f - __half2float(h));
+            const uint32_t off = (uint32_t)((mn >> 6) * (K * 128) + k * 128 + ((((mn & 63) >> 3) ^ (k & 7)) << 4) + (mn & 7) * 2);
+            *reinterpret_cast<__half*>((isA ? sA_hi : sB_hi) + off) = h;
+            *reinterpret_cast<__half*>((isA ? sA_lo : sB_lo) + off) = l;
+        }
+    } else
     for (int r = tid; r < 128 + NB; r += 128) {
         const bool isA = r < 128;
         const int row = isA ? r : r - 128;
@@ -143,6 +158,7 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
         if (v.kind == 0) idesc |= (0u << 7) | (0u << 10);            // A,B = f16
         else idesc |= (2u << 7) | (2u << 10);                        // A,B = tf32
         idesc |= ((uint32_t)(v.N >> 3) << 17) | ((128u >> 4) << 24);
+        if (v.layout == 2) idesc |= (1u << 15) | (1u << 16);         // A and B are MN-major
         const int kper = v.kind == 0 ? 16 : 8;                       // K per MMA
         const int nk = K / kper;
         const uint32_t lboA = v.lbo != 0xFFFFFFFFu ? v.lbo : (v.layout == 0 ? 0u : 128u);
@@ -158,6 +174,8 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
                     int kb = ks / 4, within = ks % 4;                 // 4 MMAs per 128-byte K block
                     offA = kb * 128 * 128 + within * 32;
                     offB = kb * NB * 128 + within * 32;
+                } else if (v.layout == 2) {
+                    offA = offB = ks * 16 * 128;                      // 16 k-rows of 128 B per MMA
                 } else {
                     offA = offB = ks * 2 * 128;                       // two 16-byte core-matrix columns per MMA
                 }
@@ -213,6 +231,9 @@ int main(int argc, char** argv) {
         {"sw128 f16 plain  N=256", 0, 0, 0, 0, 1024, 2, 1, 1.0f, 256},
         {"sw128 f16 plain  version0", 0, 0, 0, 0, 1024, 2, 0, 1.0f, 128},
         {"nosw  f16 3pass", 1, 0, 1, X, X, 0, 1, 1.0f, 128},
+        {"MN-major sw128 f16 plain lbo=K*128 sbo=1024", 2, 0, 0, 16384, 1024, 2, 1, 1.0f, 128},
+        {"MN-major sw128 f16 plain lbo=1024 sbo=K*128", 2, 0, 0, 1024, 16384, 2, 1, 1.0f, 128},
+        {"MN-major sw128 f16 3pass lbo=K*128 sbo=1024", 2, 0, 1, 16384, 1024, 2, 1, 1.0f, 128},
     };
     const int nv = (int)(sizeof(vs) / sizeof(vs[0]));
     if (argc < 2) { printf("%d\n", nv); return 0; }
