@@ -3,6 +3,7 @@
 #pragma once
 #include "platform.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include "../../include/pgpd.h"
 

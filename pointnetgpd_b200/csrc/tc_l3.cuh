@@ -283,6 +283,7 @@ inline DevInfo& dev_info() {
         cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         if (d.sms <= 0) d.sms = 148;
+        if (d.sms > 256) d.sms = 256;      // per-CTA partial buffers are sized for <= 256 CTAs (plan_tower_scratch)
         cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
         d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
         if (e != cudaSuccess) cudaGetLastError();

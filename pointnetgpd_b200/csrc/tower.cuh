@@ -27,6 +27,17 @@
 
 namespace pgpd {
 
+// which tcgen05 kernels may run (debugging aid): PGPD_TC_MASK bit0 layer-3 fwd, bit1 layer-2 fwd,
+// bit2 Gram, bit3 layer-2 bwd pass 1, bit4 dW2, bit5 layer-2 bwd pass 2b.  Default: all.
+inline unsigned tc_mask() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("PGPD_TC_MASK");
+        m = e ? (int)strtol(e, nullptr, 0) : 0x3F;
+    }
+    return (unsigned)m;
+}
+
 // ================================================================================================
 // workspace
 // ================================================================================================
@@ -102,13 +113,17 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.rtmp = c.take<double>((size_t)REDUCE_MAX_SLICES * C2 * C2);
     w.dpart = c.take<double>((size_t)std::max(w.nb_a1 * C1, w.nb_a2 * C2));
     w.dsum = c.take<double>(C2);
+    // persistent tcgen05 kernels write one partial row per CTA (<= TC_MAX_CTAS rows)
+    constexpr size_t TC_MAX_CTAS = 256;
     size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
+    fp = std::max(fp, TC_MAX_CTAS * C2);
     fp = std::max(fp, (size_t)B * w.tiles_per_cloud * C3);                   // css3 partials
     if (backward) {
         fp = std::max(fp, (size_t)w.nb_gram * C2 * C2);                      // Gram partials
         fp = std::max(fp, (size_t)w.nb_l2 * 2 * C2);                         // BN2 backward partials
         fp = std::max(fp, (size_t)w.nb_dw2 * C2 * C1);                       // dW2 partials
         fp = std::max(fp, (size_t)B * (C1 * 3));                             // dW1 partials
+        fp = std::max(fp, TC_MAX_CTAS * C2 * C2);                            // per-CTA Gram / dW2 / BN-backward partials
     }
     w.fpart_elems = fp;
     w.fpart = c.take<float>(fp);
@@ -807,7 +822,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     }
     int n_css2 = 0;
 #ifndef PGPD_EMU
-    if (a.use_tc) {
+    if (a.use_tc && (tc_mask() & 2)) {
         launch(tc::k_prepack_rows, dim3(128), dim3(C1), 0, s, t.conv[1].w, C1, 1, C2, C1, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
         const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
         tc::L2FwdTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.A1, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
@@ -836,7 +851,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     cudaMemsetAsync(w.keys, 0, (size_t)a.B * C3 * sizeof(unsigned long long), s);
     int n_css = 0;
 #ifndef PGPD_EMU
-    if (a.use_tc) {
+    if (a.use_tc && (tc_mask() & 1)) {
         const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
         launch(tc::k_prepack_w3, dim3(C3), dim3(128), 0, s, t.conv[2].w, t.bn[2].gamma,
                a.train ? (const float*)w.bn[2].mean : (const float*)nullptr, (__half*)w.wimg, w.sgn, w.mu_s);
@@ -882,7 +897,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     {
         int nrows = 0;
 #ifndef PGPD_EMU
-        if (a.use_tc) {
+        if (a.use_tc && (tc_mask() & 4)) {
             tc::GramTC::Params p{M, (int)((M + tc::AC_NT - 1) / tc::AC_NT), w.fpart, w.Y2, w.bn[1].scale, w.bn[1].shift};
             nrows = tc::launch_accum<tc::GramTC>(p, tc::dev_info().sms, s);
         } else
@@ -918,7 +933,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     {
         int nrows = 0;
 #ifndef PGPD_EMU
-        if (a.use_tc) {
+        if (a.use_tc && (tc_mask() & 8)) {
             launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
             const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
             tc::L2BwdATC::Params p{(const __half*)w.wimg_s, M, ntiles, w.Y2, w.bn[1].scale, w.bn[1].shift, w.bn[1].mean, w.bn[1].rstd,
@@ -941,7 +956,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     {
         int nrows = 0;
 #ifndef PGPD_EMU
-        if (a.use_tc) {
+        if (a.use_tc && (tc_mask() & 16) && g_b4 > 0) {
             launch(tc::k_dy2_scale, dim3(1), dim3(128), 0, s, (const float*)w.pmax, g_b4, (const float*)w.bn[1].scale,
                    (const float*)w.m1_2, (const float*)w.m2_2, w.esc, w.einv);
             tc::DW2TC::Params p{M, (int)((M + tc::AC_NT - 1) / tc::AC_NT), w.fpart, w.DZ2, w.Y2, w.bn[1].scale, w.bn[1].mean, w.bn[1].rstd,
@@ -961,7 +976,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     {
         int nrows = 0;
 #ifndef PGPD_EMU
-        if (a.use_tc) {
+        if (a.use_tc && (tc_mask() & 32)) {
             // A = W2^T padded to 128 rows: A[k][c] = W2[c][k]
             launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, t.conv[1].w, 1, C1, C1, C2, 0, (__half*)w.wimg_s, w.inv_s);
             const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
