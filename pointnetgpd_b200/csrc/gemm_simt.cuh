@@ -26,6 +26,7 @@ struct TileCfg {
 using CfgBig = TileCfg<128, 128, 16, 8, 8>;    // 256 threads
 using CfgTall = TileCfg<128, 64, 16, 8, 4>;    // 256 threads
 using CfgSmall = TileCfg<64, 64, 16, 4, 4>;    // 256 threads
+using CfgHead = TileCfg<32, 32, 32, 4, 4>;     // 64 threads: many small blocks for the skinny head GEMMs
 
 // Deterministic block reductions through shared memory ---------------------------------------
 // sum over the rows of the tile (per column): v[j] holds this thread's partial for col_of(tx,j)
@@ -109,18 +110,47 @@ __global__ void __launch_bounds__(Cfg::NT) gemm_kernel(P p) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    for (int kk = blk.k0; kk < blk.k1; kk += BK) {
-        for (int e = tid; e < BM * BK; e += NT) {
+    // software pipeline: the global loads of tile k+1 are issued (into registers) before tile k is multiplied
+    constexpr int EA = (BM * BK) / NT, EB = (BN * BK) / NT;
+    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile elements must divide evenly over the threads");
+    float ra[EA], rb[EB];
+    auto load_regs = [&](int kk) {
+#pragma unroll
+        for (int q = 0; q < EA; ++q) {
+            const int e = tid + q * NT;
             int m, k;
             if (P::A_KFAST) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
-            As[k][m] = (kk + k < blk.k1) ? p.loadA(blk, scratch, blk.m0 + m, kk + k) : 0.f;
+            ra[q] = (kk + k < blk.k1) ? p.loadA(blk, scratch, blk.m0 + m, kk + k) : 0.f;
         }
-        for (int e = tid; e < BN * BK; e += NT) {
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+            const int e = tid + q * NT;
             int n, k;
             if (P::B_NFAST) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
-            Bs[k][n] = (kk + k < blk.k1) ? p.loadB(blk, scratch, kk + k, blk.n0 + n) : 0.f;
+            rb[q] = (kk + k < blk.k1) ? p.loadB(blk, scratch, kk + k, blk.n0 + n) : 0.f;
         }
+    };
+    auto store_regs = [&]() {
+#pragma unroll
+        for (int q = 0; q < EA; ++q) {
+            const int e = tid + q * NT;
+            int m, k;
+            if (P::A_KFAST) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+            As[k][m] = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+            const int e = tid + q * NT;
+            int n, k;
+            if (P::B_NFAST) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
+            Bs[k][n] = rb[q];
+        }
+    };
+    if (blk.k0 < blk.k1) load_regs(blk.k0);
+    for (int kk = blk.k0; kk < blk.k1; kk += BK) {
+        store_regs();
         __syncthreads();
+        if (kk + BK < blk.k1) load_regs(kk + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[TM], b[TN];

@@ -60,7 +60,7 @@ struct GradOut {
 struct ProbLinFwd {
     static constexpr bool A_KFAST = true, B_NFAST = false;
     static constexpr int SCRATCH = 0;
-    using Cfg = CfgSmall;
+    using Cfg = CfgHead;
     ActIn in; const float* W; const float* bias; float* U; int B, J, I; int add_identity;
     struct Blk { int m0, n0, k0, k1; };
     __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = I; }
@@ -85,16 +85,35 @@ struct ProbLinFwd {
     }
 };
 
-// batch statistics of U[:,c] (two-pass, double) -> BatchNorm finalisation.  thread = channel.
+// batch statistics of U[:,c] (two-pass, double) -> BatchNorm finalisation.
+// block = 32 channels x 8 row lanes (fixed-order shared-memory reduction: deterministic)
 __global__ void k_bn_batch_stats(const float* __restrict__ U, int B, int C, const float* bias, pgpd_bn bn, BnState st) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
+    __shared__ double sh[8][33];
+    __shared__ double smean[32];
+    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
+    const int c = (int)blockIdx.x * 32 + cx;
     double s = 0.0;
-    for (int b = 0; b < B; ++b) s += (double)U[(size_t)b * C + c];
-    const double mean = s / B;
+    if (c < C)
+        for (int b = ry; b < B; b += 8) s += (double)U[(size_t)b * C + c];
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+        smean[cx] = t / B;
+    }
+    __syncthreads();
+    const double mean = smean[cx];
     double v = 0.0;
-    for (int b = 0; b < B; ++b) { double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
-    bn_finalize_train(c, mean, v / B, (double)B, bias, bn, st);
+    if (c < C)
+        for (int b = ry; b < B; b += 8) { double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
+    sh[ry][cx] = v;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+        bn_finalize_train(c, mean, t / B, (double)B, bias, bn, st);
+    }
 }
 
 // log_softmax over the last dim (pointnet.py:194); thread = row
@@ -133,7 +152,7 @@ __global__ void k_colsum(const float* __restrict__ G, int B, int J, float* __res
 struct ProbLinBwdW {
     static constexpr bool A_KFAST = false, B_NFAST = true;
     static constexpr int SCRATCH = 0;
-    using Cfg = CfgSmall;
+    using Cfg = CfgHead;
     GradOut dy; ActIn in; float* dW; int B, J, I;
     struct Blk { int m0, n0, k0, k1; };
     __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = B; }
@@ -159,7 +178,7 @@ struct ProbLinBwdW {
 struct ProbLinBwdX {
     static constexpr bool A_KFAST = true, B_NFAST = true;
     static constexpr int SCRATCH = 0;
-    using Cfg = CfgSmall;
+    using Cfg = CfgHead;
     GradOut dy; const float* W; ActIn in; float* dX; int B, J, I;
     struct Blk { int m0, n0, k0, k1; };
     __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = J; }
@@ -186,20 +205,29 @@ struct ProbLinBwdX {
     }
 };
 
-// BatchNorm-over-batch backward sums.  thread = channel.
+// BatchNorm-over-batch backward sums.  block = 32 channels x 8 row lanes.
 __global__ void k_bn_batch_bwd(const float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ m1, float* __restrict__ m2) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    const float mu = st.mean[c], r = st.rstd[c];
+    __shared__ double sh1[8][33], sh2[8][33];
+    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
+    const int c = (int)blockIdx.x * 32 + cx;
     double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < B; ++b) {
-        double dz = (double)DZ[(size_t)b * C + c];
-        double yhat = (double)((U[(size_t)b * C + c] - mu) * r);
-        s1 += dz; s2 += dz * yhat;
+    if (c < C) {
+        const float mu = st.mean[c], r = st.rstd[c];
+        for (int b = ry; b < B; b += 8) {
+            double dz = (double)DZ[(size_t)b * C + c];
+            double yhat = (double)((U[(size_t)b * C + c] - mu) * r);
+            s1 += dz; s2 += dz * yhat;
+        }
     }
-    dgamma[c] = (float)s2; dbeta[c] = (float)s1;
-    m1[c] = (float)(s1 / B); m2[c] = (float)(s2 / B);
+    sh1[ry][cx] = s1; sh2[ry][cx] = s2;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int q = 0; q < 8; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
+        dgamma[c] = (float)t2; dbeta[c] = (float)t1;
+        m1[c] = (float)(t1 / B); m2[c] = (float)(t2 / B);
+    }
 }
 
 struct HeadArgs {
@@ -210,7 +238,7 @@ struct HeadArgs {
     cudaStream_t stream;
 };
 
-inline dim3 lin_grid(int rows, int cols) { return dim3(idiv_up(cols, 64), idiv_up(rows, 64)); }
+inline dim3 lin_grid(int rows, int cols) { return dim3(idiv_up(cols, CfgHead::BN), idiv_up(rows, CfgHead::BM)); }
 
 // X -> w.out  (logits, or t9 + identity)
 inline void head_forward(const HeadArgs& a, HeadWs& w) {
@@ -219,19 +247,19 @@ inline void head_forward(const HeadArgs& a, HeadWs& w) {
     const int B = a.B;
     {
         ProbLinFwd p{ActIn{a.X, nullptr, nullptr, C3}, h.fc[0].w, nullptr, w.U1, B, H1, C3, 0};
-        launch_gemm<CfgSmall>(p, lin_grid(B, H1), s);
+        launch_gemm<CfgHead>(p, lin_grid(B, H1), s);
     }
-    if (a.train) launch(k_bn_batch_stats, grid1d(H1, 128), dim3(128), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0]);
+    if (a.train) launch(k_bn_batch_stats, grid1d(H1, 32), dim3(256), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0]);
     else launch(k_bn_eval_affine, grid1d(H1, 128), dim3(128), 0, s, H1, h.fc[0].b, h.bn[0], w.bn[0]);
     {
         ProbLinFwd p{ActIn{w.U1, w.bn[0].scale, w.bn[0].shift, H1}, h.fc[1].w, nullptr, w.U2, B, H2, H1, 0};
-        launch_gemm<CfgSmall>(p, lin_grid(B, H2), s);
+        launch_gemm<CfgHead>(p, lin_grid(B, H2), s);
     }
-    if (a.train) launch(k_bn_batch_stats, grid1d(H2, 128), dim3(128), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1]);
+    if (a.train) launch(k_bn_batch_stats, grid1d(H2, 32), dim3(256), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1]);
     else launch(k_bn_eval_affine, grid1d(H2, 128), dim3(128), 0, s, H2, h.fc[1].b, h.bn[1], w.bn[1]);
     {
         ProbLinFwd p{ActIn{w.U2, w.bn[1].scale, w.bn[1].shift, H2}, h.fc[2].w, h.fc[2].b, w.out, B, a.out, H2, a.is_stn ? 1 : 0};
-        launch_gemm<CfgSmall>(p, lin_grid(B, a.out), s);
+        launch_gemm<CfgHead>(p, lin_grid(B, a.out), s);
     }
 }
 
@@ -246,23 +274,23 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     ActIn in2{w.U1, w.bn[0].scale, w.bn[0].shift, H1};
     ActIn in1{a.X, nullptr, nullptr, C3};
     // fc3
-    { ProbLinBwdW p{d3, in3, g.fc[2].dw, B, J3, H2}; launch_gemm<CfgSmall>(p, lin_grid(J3, H2), s); }
+    { ProbLinBwdW p{d3, in3, g.fc[2].dw, B, J3, H2}; launch_gemm<CfgHead>(p, lin_grid(J3, H2), s); }
     launch(k_colsum, grid1d(J3, 32), dim3(32), 0, s, (const float*)w.dO, B, J3, g.fc[2].db);
-    { ProbLinBwdX p{d3, h.fc[2].w, in3, w.DZ2, B, J3, H2}; launch_gemm<CfgSmall>(p, lin_grid(B, H2), s); }
-    launch(k_bn_batch_bwd, grid1d(H2, 128), dim3(128), 0, s, (const float*)w.DZ2, (const float*)w.U2, B, H2, w.bn[1],
+    { ProbLinBwdX p{d3, h.fc[2].w, in3, w.DZ2, B, J3, H2}; launch_gemm<CfgHead>(p, lin_grid(B, H2), s); }
+    launch(k_bn_batch_bwd, grid1d(H2, 32), dim3(256), 0, s, (const float*)w.DZ2, (const float*)w.U2, B, H2, w.bn[1],
            g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
     // fc2
     GradOut d2{w.DZ2, w.U2, w.bn[1], w.m1_2, w.m2_2, H2, true};
-    { ProbLinBwdW p{d2, in2, g.fc[1].dw, B, H2, H1}; launch_gemm<CfgSmall>(p, lin_grid(H2, H1), s); }
+    { ProbLinBwdW p{d2, in2, g.fc[1].dw, B, H2, H1}; launch_gemm<CfgHead>(p, lin_grid(H2, H1), s); }
     launch(k_fill, grid1d(H2, 128), dim3(128), 0, s, g.fc[1].db, (size_t)H2, 0.f);
-    { ProbLinBwdX p{d2, h.fc[1].w, in2, w.DZ1, B, H2, H1}; launch_gemm<CfgSmall>(p, lin_grid(B, H1), s); }
-    launch(k_bn_batch_bwd, grid1d(H1, 128), dim3(128), 0, s, (const float*)w.DZ1, (const float*)w.U1, B, H1, w.bn[0],
+    { ProbLinBwdX p{d2, h.fc[1].w, in2, w.DZ1, B, H2, H1}; launch_gemm<CfgHead>(p, lin_grid(B, H1), s); }
+    launch(k_bn_batch_bwd, grid1d(H1, 32), dim3(256), 0, s, (const float*)w.DZ1, (const float*)w.U1, B, H1, w.bn[0],
            g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
     // fc1
     GradOut d1{w.DZ1, w.U1, w.bn[0], w.m1_1, w.m2_1, H1, true};
-    { ProbLinBwdW p{d1, in1, g.fc[0].dw, B, H1, C3}; launch_gemm<CfgSmall>(p, lin_grid(H1, C3), s); }
+    { ProbLinBwdW p{d1, in1, g.fc[0].dw, B, H1, C3}; launch_gemm<CfgHead>(p, lin_grid(H1, C3), s); }
     launch(k_fill, grid1d(H1, 128), dim3(128), 0, s, g.fc[0].db, (size_t)H1, 0.f);
-    { ProbLinBwdX p{d1, h.fc[0].w, in1, dX, B, H1, C3}; launch_gemm<CfgSmall>(p, lin_grid(B, C3), s); }
+    { ProbLinBwdX p{d1, h.fc[0].w, in1, dX, B, H1, C3}; launch_gemm<CfgHead>(p, lin_grid(B, C3), s); }
 }
 
 }  // namespace pgpd

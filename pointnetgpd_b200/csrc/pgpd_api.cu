@@ -122,6 +122,17 @@ int pgpd_profile_read(int* launches, float* total_ms) {
     return PGPD_OK;
 }
 
+/* tuning aid (not part of the documented ABI): copies the [256][8] pipeline cycle counters written by the
+ * layer-3 kernel when PGPD_L3_DEBUG is set */
+int pgpd_debug_l3_counters(long long* host_out) {
+#ifdef PGPD_EMU
+    (void)host_out; return PGPD_E_UNSUPPORTED;
+#else
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, tc::l3_debug_buffer(), 256 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : PGPD_E_CUDA;
+#endif
+}
+
 size_t pgpd_workspace_bytes(int what, int B, int N, int k, int flags) {
     if (B < 1 || N < 1) return 0;
     ModelWs w;

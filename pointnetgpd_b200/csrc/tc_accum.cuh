@@ -137,12 +137,17 @@ __global__ void __launch_bounds__(AC_THREADS, 1) k_accum_tc(typename T::Params p
         for (int t = t_begin; t < t_end; ++t) {
             const size_t P0 = (size_t)t * AC_NT;
             const int nvalid = (p.M - P0 < (size_t)AC_NT) ? (int)(p.M - P0) : AC_NT;
+            if (wp == 0 && lane == 0 && t + 2 < t_end) {
+                const size_t Pn = (size_t)(t + 2) * AC_NT;
+                const int nvn = (p.M - Pn < (size_t)AC_NT) ? (int)(p.M - Pn) : AC_NT;
+                T::prefetch(p, Pn, nvn);
+            }
             mbar_wait(BAR(2 + buf), phase ^ 1);
             unsigned char* ab = smem + buf * Cfg::BUF_BYTES;
             // ---- A rows: 128 channels, one row per warp iteration
             {
                 const int cg = lane, atom = cg >> 4, chunk = (cg & 15) >> 1, half8 = cg & 1;
-                constexpr int U = 4;
+                constexpr int U = 8;
                 for (int i0 = 0; i0 < AC_NT / 4; i0 += U) {
                     typename T::RawA raw[U];
 #pragma unroll
@@ -230,6 +235,7 @@ struct GramTC {
         s.sc.x *= ACT_SCALE; s.sc.y *= ACT_SCALE; s.sc.z *= ACT_SCALE; s.sc.w *= ACT_SCALE;
         s.sh.x *= ACT_SCALE; s.sh.y *= ACT_SCALE; s.sh.z *= ACT_SCALE; s.sh.w *= ACT_SCALE;
     }
+    __device__ static void prefetch(const Params& p, size_t P0, int nrows) { l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u); }
     __device__ static void fetchA(ProdA&, const Params& p, size_t P, bool valid, int cg, RawA& r) {
         r.y = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
@@ -268,6 +274,11 @@ struct DW2TC {
         q.m1 = *reinterpret_cast<const float4*>(p.m1 + 4 * cg);
         q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
         q.e = *reinterpret_cast<const float4*>(p.esc + 4 * cg);
+    }
+    __device__ static void prefetch(const Params& p, size_t P0, int nrows) {
+        l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
+        l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
+        l2_prefetch(p.A1 + P0 * C1, (uint32_t)nrows * C1 * 4u);
     }
     __device__ static void fetchA(ProdA&, const Params& p, size_t P, bool valid, int cg, RawA& r) {
         r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz;

@@ -83,7 +83,14 @@ struct L3Params {
     unsigned long long* keys; // [B][1024] (ordered max value, ~arg-max)
     float* css_part;          // [ntiles][1024]
     int B, N, tiles_per_cloud, ntiles;
+    long long* dbg;           // optional [gridDim.x][8] cycle counters (see PGPD_L3_DEBUG), or nullptr
 };
+
+// cycle accounting of the pipeline roles, for tuning (enabled by a non-null L3Params::dbg):
+//  0 mma: wait a2_full   1 mma: wait tmem_empty   2 mma: wait w_full   3 mma: total loop
+//  4 producer: wait a2_empty   5 producer: stage a tile   6 epilogue: wait tmem_full   7 epilogue: work
+#define L3_T0() const long long _t0 = p.dbg ? clock64() : 0
+#define L3_ACC(slot) do { if (p.dbg) dbg_acc[slot] += clock64() - _t0; } while (0)
 
 __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -119,6 +126,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
 
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (warp == 0) {
         // ===================== W3 producer =====================
         if (lane == 0) {
@@ -139,15 +147,16 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             int stage = 0; uint32_t wphase = 0;
             int acc = 0; uint32_t aphase = 0;
             uint32_t a2phase = 0;
+            const long long tl0 = p.dbg ? clock64() : 0;
             for (int t = t_begin; t < t_end; ++t) {
-                mbar_wait(BAR(6), a2phase);                 // a2 tile staged
+                { L3_T0(); mbar_wait(BAR(6), a2phase); L3_ACC(0); }   // a2 tile staged
                 tc_fence_after_sync();
                 for (int mt = 0; mt < 8; ++mt) {
-                    mbar_wait(BAR(10 + acc), aphase ^ 1);   // accumulator drained by the epilogue
+                    { L3_T0(); mbar_wait(BAR(10 + acc), aphase ^ 1); L3_ACC(1); }   // accumulator drained by the epilogue
                     tc_fence_after_sync();
                     const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
                     for (int kb = 0; kb < 2; ++kb) {
-                        mbar_wait(BAR(stage), wphase);      // weights landed
+                        { L3_T0(); mbar_wait(BAR(stage), wphase); L3_ACC(2); }      // weights landed
                         tc_fence_after_sync();
                         const uint32_t w_hi = sbase + L3_SMEM_W + stage * L3_STAGE_BYTES, w_lo = w_hi + 16384;
                         const uint32_t b_hi = sbase + (0 * 2 + kb) * L3_A2_PART, b_lo = sbase + (1 * 2 + kb) * L3_A2_PART;
@@ -169,6 +178,10 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 mma_commit(BAR(7));                         // a2 tile no longer needed
                 a2phase ^= 1;
             }
+            if (p.dbg) {
+                dbg_acc[3] = clock64() - tl0;
+                for (int i = 0; i < 4; ++i) p.dbg[(size_t)cta * 8 + i] = dbg_acc[i];
+            }
         }
     } else if (warp < 6) {
         // ===================== epilogue =====================
@@ -182,8 +195,9 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             for (int mt = 0; mt < 8; ++mt) {
                 const int ch = mt * 128 + row;
                 const float mu = p.mu_s ? p.mu_s[ch] : 0.f;
-                mbar_wait(BAR(8 + acc), aphase);
+                { L3_T0(); mbar_wait(BAR(8 + acc), aphase); L3_ACC(6); }
                 tc_fence_after_sync();
+                const long long te0 = p.dbg ? clock64() : 0;
                 float best = -INFINITY; int bidx = 0; float css = 0.f;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
                 for (int c0 = 0; c0 < L3_NT; c0 += 32) {
@@ -217,6 +231,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 }
                 tc_fence_before_sync();
                 mbar_arrive(BAR(10 + acc));                 // accumulator may be overwritten
+                if (p.dbg) dbg_acc[7] += clock64() - te0;
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
@@ -227,6 +242,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 }
             }
         }
+        if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
     } else {
         // ===================== a2 producer =====================
         const int wp = warp - 6;                            // 0..3
@@ -239,31 +255,48 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             const float* src = p.Y2 + ((size_t)b * p.N + n0) * C2 + 4 * lane;
-            mbar_wait(BAR(7), ephase ^ 1);                  // previous tile's MMAs are done with a2
+            if (wp == 0 && lane == 0 && t + 1 < t_end) {
+                // pull the NEXT tile's rows into L2 while this tile is being staged / multiplied
+                const int b1 = (t + 1) / p.tiles_per_cloud, tt1 = (t + 1) % p.tiles_per_cloud;
+                const int nv1 = (p.N - tt1 * L3_NT < L3_NT) ? p.N - tt1 * L3_NT : L3_NT;
+                l2_prefetch(p.Y2 + ((size_t)b1 * p.N + (size_t)tt1 * L3_NT) * C2, (uint32_t)nv1 * C2 * 4u);
+            }
+            { L3_T0(); mbar_wait(BAR(7), ephase ^ 1); L3_ACC(4); }   // previous tile's MMAs are done with a2
             ephase ^= 1;
-#pragma unroll 4
-            for (int i = 0; i < L3_NT / 4; ++i) {
-                const int r = wp + 4 * i;
-                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                const bool ok = r < nvalid;
-                if (ok) y = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
-                float a0 = ok ? fminf(fmaxf(fmaf(sc0, y.x, sh0), 0.f), 60000.f) : 0.f;
-                float a1 = ok ? fminf(fmaxf(fmaf(sc1, y.y, sh1), 0.f), 60000.f) : 0.f;
-                float a2 = ok ? fminf(fmaxf(fmaf(sc2, y.z, sh2), 0.f), 60000.f) : 0.f;
-                float a3 = ok ? fminf(fmaxf(fmaf(sc3, y.w, sh3), 0.f), 60000.f) : 0.f;
-                __half2 h01, l01, h23, l23;
-                split2(a0, a1, h01, l01);
-                split2(a2, a3, h23, l23);
-                const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
-                uint2 hv, lv;
-                hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-                lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-                *reinterpret_cast<uint2*>(smem + (0 * 2 + kb) * L3_A2_PART + off) = hv;
-                *reinterpret_cast<uint2*>(smem + (1 * 2 + kb) * L3_A2_PART + off) = lv;
+            const long long tp0 = p.dbg ? clock64() : 0;
+            constexpr int U = 8;
+            for (int i0 = 0; i0 < L3_NT / 4; i0 += U) {
+                float4 y[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {               // all loads of U rows first (memory-level parallelism)
+                    const int r = wp + 4 * (i0 + u);
+                    y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int r = wp + 4 * (i0 + u);
+                    const bool ok = r < nvalid;
+                    float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
+                    float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
+                    float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
+                    float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
+                    __half2 h01, l01, h23, l23;
+                    split2(a0, a1, h01, l01);
+                    split2(a2, a3, h23, l23);
+                    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(smem + (0 * 2 + kb) * L3_A2_PART + off) = hv;
+                    *reinterpret_cast<uint2*>(smem + (1 * 2 + kb) * L3_A2_PART + off) = lv;
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(BAR(6));
+            if (p.dbg) dbg_acc[5] += clock64() - tp0;
         }
+        if (p.dbg && wp == 0 && lane == 0) { p.dbg[(size_t)cta * 8 + 4] = dbg_acc[4]; p.dbg[(size_t)cta * 8 + 5] = dbg_acc[5]; }
     }
 
     tc_fence_before_sync();
@@ -291,5 +324,12 @@ inline DevInfo& dev_info() {
     return d;
 }
 inline bool available() { return dev_info().state == 1; }
+
+// tuning aid only (PGPD_L3_DEBUG=1): a lazily cudaMalloc'ed [256][8] int64 buffer of pipeline cycle counters
+inline long long* l3_debug_buffer() {
+    static long long* buf = nullptr;
+    if (!buf) { cudaMalloc(&buf, 256 * 8 * sizeof(long long)); cudaMemset(buf, 0, 256 * 8 * sizeof(long long)); }
+    return buf;
+}
 
 }}  // namespace pgpd::tc

@@ -47,6 +47,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// pull [src, src+bytes) into L2 ahead of use (bytes multiple of 16, src 16-byte aligned); no completion tracking
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {   // whole warp

@@ -64,6 +64,7 @@ __global__ void k_prepack_rows(const float* __restrict__ W, int sr, int sk, int 
 //        a warp for one row (KD=128) or two rows (KD=64: lanes 0-15 / 16-31).  The return value of lanes cg < 4
 //        is stored as per-point auxiliary value aux[cg][row] for the epilogue (e.g. the factor undoing a
 //        per-point scale).
+//   __device__ static void prefetch(const Params&, size_t P0, int nrows);   // l2_prefetch of what a later tile will read
 //   __device__ static void epi_begin(Epi&, const Params&, int feat);
 //   __device__ static void epi_cols(Epi&, const Params&, int feat, size_t P0, int nvalid, const float (&v)[32], const float* aux);
 //        32 consecutive points P0.. of output feature `feat`; columns >= nvalid are padding; aux[k*128 + j] is the
@@ -192,7 +193,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
             mbar_wait(BAR(3 + buf), phase ^ 1);             // MMAs of two tiles ago are done with this buffer
             mbar_wait(BAR(7 + buf), phase ^ 1);             // ... and its epilogue no longer reads aux[buf]
             unsigned char* bb = smem + Cfg::OFF_B + buf * Cfg::B_BYTES;
-            constexpr int ITERS = ST_NT / (4 * RPI), U = 4;
+            if (wp == 0 && lane == 0 && t + 2 < t_end) {
+                const size_t Pn = (size_t)(t + 2) * ST_NT;
+                const int nvn = (p.M - Pn < (size_t)ST_NT) ? (int)(p.M - Pn) : ST_NT;
+                T::prefetch(p, Pn, nvn);                    // tile t+2 -> L2
+            }
+            constexpr int ITERS = ST_NT / (4 * RPI), U = 8;
             for (int i0 = 0; i0 < ITERS; i0 += U) {
                 typename T::Raw raw[U];
 #pragma unroll
@@ -261,6 +267,7 @@ struct L2FwdTC {
     struct Prod { int dummy; };
     __device__ static void prod_begin(Prod&, const Params&, int) {}
     struct Raw { float4 a; };
+    __device__ static void prefetch(const Params& p, size_t P0, int nrows) { l2_prefetch(p.A1 + P0 * C1, (uint32_t)nrows * C1 * 4u); }
     __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
         r.a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) r.a = *reinterpret_cast<const float4*>(p.A1 + P * C1 + 4 * cg);
@@ -307,6 +314,7 @@ struct L2BwdATC {
         s.sh.x *= ACT_SCALE; s.sh.y *= ACT_SCALE; s.sh.z *= ACT_SCALE; s.sh.w *= ACT_SCALE;
     }
     struct Raw { float4 y; };
+    __device__ static void prefetch(const Params& p, size_t P0, int nrows) { l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u); }
     __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
         r.y = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
@@ -383,14 +391,19 @@ struct L2BwdBTC {
         q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
     }
     struct Raw { float4 dz, y; float xa; };
+    __device__ static void prefetch(const Params& p, size_t P0, int nrows) {
+        l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
+        l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
+        l2_prefetch(p.A1 + P0 * C1, (uint32_t)nrows * C1 * 4u);
+    }
     __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
         r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz; r.xa = 0.f;
         if (valid) {
             r.dz = *reinterpret_cast<const float4*>(p.DZ2 + P * C2 + 4 * cg);
             r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
             if (cg >= 1 && cg < 4) {
-                // transformed coordinate x'_(cg-1) of this point
-                const int b = (int)(P / p.N), n = (int)(P % p.N), i = cg - 1;
+                // transformed coordinate x'_(cg-1) of this point (B*N < 2^24, so 32-bit index math)
+                const int P32 = (int)P, b = P32 / p.N, n = P32 - b * p.N, i = cg - 1;
                 const float* xb = p.x + (size_t)b * 3 * p.N;
                 const float p0 = xb[n], p1 = xb[p.N + n], p2 = xb[2 * p.N + n];
                 if (p.trans) {

@@ -389,16 +389,17 @@ __global__ void k_pool_finalize(const unsigned long long* __restrict__ keys, con
 // backward kernels
 // ================================================================================================
 
-// BatchNorm3 / max-pool backward on the pooled values.  thread = channel, loop over clouds.
+// BatchNorm3 / max-pool backward on the pooled values.  block = 32 channels x 8 cloud lanes.
 __global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict__ uext, int B, int relu_last,
                            double count, const float* __restrict__ gamma, BnState st,
                            float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
                            float* __restrict__ dvec, float* __restrict__ evec) {
-    const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C3) return;
+    __shared__ double sh1[8][33], sh2[8][33];
+    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
+    const int c = (int)blockIdx.x * 32 + cx;
     const float sc = st.scale[c], sf = st.shift[c], mu = st.mean[c], r = st.rstd[c];
     double sdz = 0.0, sdzy = 0.0;
-    for (int b = 0; b < B; ++b) {
+    for (int b = ry; b < B; b += 8) {
         const size_t i = (size_t)b * C3 + c;
         const float u = uext[i];
         float dz = dG[i];
@@ -408,12 +409,18 @@ __global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict
         sdzy += (double)dz * (double)yhat;
         coef[i] = sc * dz;
     }
-    dgamma[c] = (float)sdzy;
-    dbeta[c] = (float)sdz;
-    const double m1 = sdz / count, m2 = sdzy / count;
-    const double d = (double)sc * m2 * (double)r;
-    dvec[c] = (float)d;
-    evec[c] = (float)((double)sc * m1 - d * (double)mu);
+    sh1[ry][cx] = sdz; sh2[ry][cx] = sdzy;
+    __syncthreads();
+    if (ry == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int q = 0; q < 8; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
+        dgamma[c] = (float)t2;
+        dbeta[c] = (float)t1;
+        const double m1 = t1 / count, m2 = t2 / count;
+        const double d = (double)sc * m2 * (double)r;
+        dvec[c] = (float)d;
+        evec[c] = (float)((double)sc * m1 - d * (double)mu);
+    }
     (void)gamma;
 }
 
@@ -453,8 +460,12 @@ struct ProbDense {
     using Cfg = CfgSmall;
     const float* A; const float* Bm; float* C; const float* kscale;
     int Mr, Nc, K; size_t sam, sak, sbk, sbn, ldc;
+    int kslice = 0;     // > 0: blockIdx.z selects a K slice of this size and writes its own Mr x ldc partial
     struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = K; }
+    __device__ void setup(Blk& b) const {
+        b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = K;
+        if (kslice > 0) { b.k0 = (int)blockIdx.z * kslice; b.k1 = b.k0 + kslice < K ? b.k0 + kslice : K; }
+    }
     __device__ void prologue(const Blk&, float*) const {}
     __device__ float loadA(const Blk&, const float*, int m, int k) const {
         if (m >= Mr) return 0.f;
@@ -470,38 +481,51 @@ struct ProbDense {
 #pragma unroll
             for (int j = 0; j < Cfg::TN; ++j) {
                 int n = b.n0 + Cfg::col_of(tx, j);
-                if (n < Nc) C[(size_t)m * ldc + n] = acc[i][j];
+                if (n < Nc) C[(kslice > 0 ? (size_t)blockIdx.z * Mr * ldc : 0) + (size_t)m * ldc + n] = acc[i][j];
             }
         }
     }
 };
 
-// uvec[i] = sum_c W3[c][i] * e[c]
+// uvec[i] = sum_c W3[c][i] * e[c];  grid = 4 blocks of 32 columns x 8 row lanes
 __global__ void k_uvec(const float* __restrict__ W3, const float* __restrict__ e, float* __restrict__ uvec) {
-    int i = (int)threadIdx.x;
-    if (i >= C2) return;
+    __shared__ double sh[8][33];
+    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
+    const int i = (int)blockIdx.x * 32 + cx;
     double s = 0.0;
-    for (int c = 0; c < C3; ++c) s += (double)W3[(size_t)c * C2 + i] * (double)e[c];
-    uvec[i] = (float)s;
+    for (int c = ry; c < C3; c += 8) s += (double)W3[(size_t)c * C2 + i] * (double)e[c];
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+        uvec[i] = (float)t;
+    }
 }
 
 // dW3[c][k] = sum_b coef[b][c] a2[argmax(b,c)][k]  -  d[c] * (W3 Gram)[c][k]  -  e[c] * S1[k]
-// grid = 1024 channels, block = 128 (k)
+// grid = 1024 channels, block = 128 (k) x 4 cloud lanes; the lanes are summed in a fixed order
 __global__ void k_dw3(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ Y2, BnState st2,
                       int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec,
                       const float* __restrict__ WG, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
-    const int c = (int)blockIdx.x, k = (int)threadIdx.x;
+    __shared__ float sh[4][128];
+    const int c = (int)blockIdx.x, k = (int)threadIdx.x & 127, q = (int)threadIdx.x >> 7;
     const float sc = st2.scale[k], sf = st2.shift[k];
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) {
+    for (int b = q; b < B; b += 4) {
         const float cf = coef[(size_t)b * C3 + c];
         if (cf != 0.f) {
             const size_t P = (size_t)b * N + idx[(size_t)b * C3 + c];
             acc = fmaf(cf, fmaxf(sc * Y2[P * C2 + k] + sf, 0.f), acc);
         }
     }
-    dW3[(size_t)c * C2 + k] = acc - dvec[c] * WG[(size_t)c * C2 + k] - evec[c] * (float)S1[k];
-    if (k == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
+    sh[q][k] = acc;
+    __syncthreads();
+    if (q == 0) {
+        const float t = ((sh[0][k] + sh[1][k]) + sh[2][k]) + sh[3][k];
+        dW3[(size_t)c * C2 + k] = t - dvec[c] * WG[(size_t)c * C2 + k] - evec[c] * (float)S1[k];
+        if (k == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
+    }
 }
 
 // sparse part of d a2: rows  sum_{c : argmax(b,c)=p} coef[b][c] W3[c][:]  for the arg-max points of one cloud.
@@ -855,8 +879,10 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
         launch(tc::k_prepack_w3, dim3(C3), dim3(128), 0, s, t.conv[2].w, t.bn[2].gamma,
                a.train ? (const float*)w.bn[2].mean : (const float*)nullptr, (__half*)w.wimg, w.sgn, w.mu_s);
+        // PGPD_L3_DEBUG=1: the kernel writes per-CTA pipeline cycle counters to the start of the rtmp scratch
+        static const bool l3dbg = getenv("PGPD_L3_DEBUG") != nullptr;
         tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
-                       w.keys, w.fpart, a.B, a.N, tpc, ntiles};
+                       w.keys, w.fpart, a.B, a.N, tpc, ntiles, l3dbg ? tc::l3_debug_buffer() : nullptr};
         const int grid = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
         profiler().begin(s);
         launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
@@ -890,7 +916,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     const double count = (double)M;
 
     // ---- BN3 / max-pool on the pooled values ---------------------------------------------------------
-    launch(k_pool_bwd, grid1d(C3, 128), dim3(128), 0, s, dpooled, (const float*)w.uext, a.B, a.relu_last ? 1 : 0, count,
+    launch(k_pool_bwd, dim3(C3 / 32), dim3(256), 0, s, dpooled, (const float*)w.uext, a.B, a.relu_last ? 1 : 0, count,
            t.bn[2].gamma, w.bn[2], w.coef, g.bn[2].dgamma, g.bn[2].dbeta, w.dvec, w.evec);
 
     // ---- Gram matrix of a2 -------------------------------------------------------------------------
@@ -915,13 +941,16 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         ProbDense<true, true> p{t.conv[2].w, w.gram, w.WG, nullptr, C3, C2, C2, (size_t)C2, 1, (size_t)C2, 1, (size_t)C2};
         launch_gemm<CfgSmall>(p, dim3(C2 / 64, C3 / 64), s);
     }
-    // Q = W3^T diag(d) W3  [128 x 128]
+    // Q = W3^T diag(d) W3  [128 x 128], K = 1024 split in 16 slices (blockIdx.z) and reduced deterministically
     {
-        ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.Q, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
-        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64), s);
+        ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.fpart, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
+        p.kslice = C3 / 16;
+        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64, 16), s);
+        const int S = colreduce<float>(w.fpart, 16, C2 * C2, w.rtmp, s);
+        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.Q);
     }
-    launch(k_uvec, dim3(1), dim3(128), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
-    launch(k_dw3, dim3(C3), dim3(C2), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
+    launch(k_uvec, dim3(C2 / 32), dim3(256), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
+    launch(k_dw3, dim3(C3), dim3(4 * C2), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
            (const float*)w.dvec, (const float*)w.evec, (const float*)w.WG, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
 
     // ---- sparse part of d a2 -----------------------------------------------------------------------

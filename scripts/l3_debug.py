@@ -1,0 +1,24 @@
+"""Print the pipeline cycle accounting of the tcgen05 layer-3 kernel (run with PGPD_L3_DEBUG=1)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import weights as W
+from pointnetgpd_b200 import _abi as A
+from pointnetgpd_b200.model.pointnet import PointNetCls
+B, N = 512, 1024
+st = W.make_state(0, k=2)
+m = PointNetCls(N, 3, 2); m.load_state_dict({k: torch.tensor(v) for k, v in st.items()}); m = m.cuda().train()
+x = torch.tensor(W.make_clouds(1, B, N, "box")).cuda()
+for _ in range(3):
+    with torch.no_grad():
+        m(x)
+torch.cuda.synchronize()
+lib = A.load()
+buf = (ctypes.c_longlong * (256 * 8))()
+lib.pgpd_debug_l3_counters.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+lib.pgpd_debug_l3_counters(buf)
+a = np.array(buf[:], dtype=np.int64).reshape(256, 8)[:148]
+names = ["mma wait a2_full", "mma wait tmem_empty", "mma wait w_full", "mma total", "prod wait a2_empty", "prod stage tile", "epi wait tmem_full", "epi work"]
+tiles = 2048 / 148
+for i, n in enumerate(names):
+    print("%-22s mean %10.0f cycles/CTA   %8.0f per tile" % (n, a[:, i].mean(), a[:, i].mean() / tiles))
