@@ -11,83 +11,112 @@ namespace pgpd {
 struct HeadWs {
     float* U1;        // [B][512]  bias-free pre-activation of fc1
     float* U2;        // [B][256]
+    float* Hm1;       // [B][512]  relu(bn(U1)), materialised
+    float* Hm2;       // [B][256]
     float* out;       // [B][out]  fc3 output (+bias, + identity for the STN head) = logits / t9
     BnState bn[2];
+    float* part;      // split-K partials: HEAD_PART_ELEMS floats
     // backward scratch
-    float* DZ1;       // [B][512]
+    float* DZ1;       // [B][512]  dz1, then (in place) dU1
     float* DZ2;       // [B][256]
-    float* m1_1; float* m2_1;   // [512]
-    float* m1_2; float* m2_2;   // [256]
     float* dO;        // [B][out]  gradient w.r.t. fc3 output
 };
+
+constexpr size_t HEAD_PART_ELEMS = (size_t)4 << 20;   // 16 MB of fp32 partials
 
 inline void plan_head(Carver& c, HeadWs& w, int B, int out, bool backward) {
     w.U1 = c.take<float>((size_t)B * H1);
     w.U2 = c.take<float>((size_t)B * H2);
+    w.Hm1 = c.take<float>((size_t)B * H1);
+    w.Hm2 = c.take<float>((size_t)B * H2);
     w.out = c.take<float>((size_t)B * out);
     w.bn[0].carve(c, H1); w.bn[1].carve(c, H2);
+    w.part = c.take<float>(HEAD_PART_ELEMS);
     if (backward) {
         w.DZ1 = c.take<float>((size_t)B * H1);
         w.DZ2 = c.take<float>((size_t)B * H2);
-        w.m1_1 = c.take<float>(H1); w.m2_1 = c.take<float>(H1);
-        w.m1_2 = c.take<float>(H2); w.m2_2 = c.take<float>(H2);
         w.dO = c.take<float>((size_t)B * out);
     }
 }
 
-// input activation of a Linear layer: either a raw feature matrix or relu(scale*U + shift)
-struct ActIn {
-    const float* U; const float* scale; const float* shift; int ld;
-    __device__ float at(int b, int i) const {
-        float v = U[(size_t)b * ld + i];
-        return scale ? fmaxf(scale[i] * v + shift[i], 0.f) : v;
-    }
-};
-
-// gradient w.r.t. a Linear output: either given directly, or through a train-mode BatchNorm:
-//   dU = s*(dz - m1 - yhat*m2)
-struct GradOut {
-    const float* DZ; const float* U; BnState st; const float* m1; const float* m2; int ld; bool bn;
-    __device__ float at(int b, int j) const {
-        float dz = DZ[(size_t)b * ld + j];
-        if (!bn) return dz;
-        float yhat = (U[(size_t)b * ld + j] - st.mean[j]) * st.rstd[j];
-        return st.scale[j] * (dz - m1[j] - yhat * m2[j]);
-    }
-};
-
-// U[b][j] = sum_i act(b,i) W[j][i]  (+ bias[j]) (+ 1 on the diagonal entries of a flattened 3x3)
-struct ProbLinFwd {
-    static constexpr bool A_KFAST = true, B_NFAST = false;
+// ---- plain fp32 GEMM on row-major matrices with optional split-K ---------------------------------------
+//   C[m][n] = sum_k A(m,k) B(k,n);  A(m,k) = A[m*sam + k*sak], B(k,n) = Bm[k*sbk + n*sbn]
+// epilogue (only when the whole K range is handled by one block, ksl == 0):
+//   EPI_BIAS: + bias[n] (+1 on the diagonal of a flattened 3x3 when add_identity);  EPI_MASK: zero where mask[m][n] <= 0
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_MASK = 2 };
+template <bool AK, bool BNF>
+struct ProbPlain {
+    static constexpr bool A_KFAST = AK, B_NFAST = BNF;
     static constexpr int SCRATCH = 0;
-    using Cfg = CfgHead;
-    ActIn in; const float* W; const float* bias; float* U; int B, J, I; int add_identity;
+    using Cfg = CfgSmall;
+    const float* A; const float* Bm; float* C; float* part;
+    int Mr, Nc, K; size_t sam, sak, sbk, sbn;
+    int ksl;            // 0: no split; else K-slice length, blockIdx.z selects the slice, output goes to part[z][Mr][Nc]
+    int epi; const float* bias; int add_identity; const float* mask;
     struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = I; }
+    __device__ void setup(Blk& b) const {
+        b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = K;
+        if (ksl > 0) { b.k0 = (int)blockIdx.z * ksl; b.k1 = b.k0 + ksl < K ? b.k0 + ksl : K; }
+    }
     __device__ void prologue(const Blk&, float*) const {}
-    __device__ float loadA(const Blk&, const float*, int m, int k) const { return m < B ? in.at(m, k) : 0.f; }
-    __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < J ? W[(size_t)n * I + k] : 0.f; }
+    __device__ float loadA(const Blk&, const float*, int m, int k) const { return m < Mr ? A[(size_t)m * sam + (size_t)k * sak] : 0.f; }
+    __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < Nc ? Bm[(size_t)k * sbk + (size_t)n * sbn] : 0.f; }
     __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
+        float* out = ksl > 0 ? part + (size_t)blockIdx.z * Mr * Nc : C;
 #pragma unroll
         for (int i = 0; i < Cfg::TM; ++i) {
-            int m = b.m0 + Cfg::row_of(ty, i);
-            if (m >= B) continue;
+            const int m = b.m0 + Cfg::row_of(ty, i);
+            if (m >= Mr) continue;
 #pragma unroll
             for (int j = 0; j < Cfg::TN; ++j) {
-                int n = b.n0 + Cfg::col_of(tx, j);
-                if (n >= J) continue;
+                const int n = b.n0 + Cfg::col_of(tx, j);
+                if (n >= Nc) continue;
                 float v = acc[i][j];
-                if (bias) v += bias[n];
-                if (add_identity && (n % 4 == 0)) v += 1.f;   // entries 0,4,8 of the flattened 3x3 (pointnet.py:39-43)
-                U[(size_t)m * J + n] = v;
+                if (ksl == 0) v = finish(v, m, n);
+                out[(size_t)m * Nc + n] = v;
             }
         }
     }
+    __device__ float finish(float v, int m, int n) const {
+        if (epi == EPI_BIAS) { v += bias[n]; if (add_identity && (n % 4 == 0)) v += 1.f; }   // entries 0,4,8 (pointnet.py:39-43)
+        else if (epi == EPI_MASK) { if (!(mask[(size_t)m * Nc + n] > 0.f)) v = 0.f; }
+        return v;
+    }
 };
 
-// batch statistics of U[:,c] (two-pass, double) -> BatchNorm finalisation.
+// sums the split-K partials in a fixed order and applies the epilogue
+template <bool AK, bool BNF>
+__global__ void k_splitk_finish(ProbPlain<AK, BNF> p, int nsl) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)p.Mr * p.Nc;
+    if (i >= total) return;
+    float v = 0.f;
+    for (int z = 0; z < nsl; ++z) v += p.part[(size_t)z * total + i];
+    p.C[i] = p.finish(v, (int)(i / p.Nc), (int)(i % p.Nc));
+}
+
+// fixed_nsl > 0: use exactly that many K slices (forward GEMMs: the summation order must not depend on the batch
+// size, so that eval outputs are bit-identical however the clouds are batched); 0: pick by occupancy.
+template <bool AK, bool BNF>
+inline void run_plain(ProbPlain<AK, BNF> p, cudaStream_t s, int fixed_nsl = 0) {
+    const int tm = idiv_up(p.Mr, CfgSmall::BM), tn = idiv_up(p.Nc, CfgSmall::BN);
+    int nsl = 1;
+    if (fixed_nsl > 0) {
+        nsl = fixed_nsl;
+        while (nsl > 1 && (size_t)nsl * p.Mr * p.Nc > HEAD_PART_ELEMS) nsl /= 2;    // huge batches: fewer slices (still batch-size independent below 4M outputs)
+    } else {
+        // enough blocks to occupy the chip (>= ~2 per SM), K slices of at least 64
+        while (tm * tn * nsl < 296 && p.K / (nsl * 2) >= 64 && (size_t)(nsl * 2) * p.Mr * p.Nc <= HEAD_PART_ELEMS) nsl *= 2;
+    }
+    p.ksl = nsl > 1 ? idiv_up(p.K, nsl) : 0;
+    launch_gemm<CfgSmall>(p, dim3(tn, tm, nsl), s);
+    if (nsl > 1) launch(k_splitk_finish<AK, BNF>, grid1d((size_t)p.Mr * p.Nc, 256), dim3(256), 0, s, p, nsl);
+}
+
+// batch statistics of U[:,c] (two-pass, double) -> BatchNorm finalisation -> H = relu(scale*U + shift).
 // block = 32 channels x 8 row lanes (fixed-order shared-memory reduction: deterministic)
-__global__ void k_bn_batch_stats(const float* __restrict__ U, int B, int C, const float* bias, pgpd_bn bn, BnState st) {
+__global__ void k_bn_batch_stats_apply(const float* __restrict__ U, int B, int C, const float* bias, pgpd_bn bn, BnState st,
+                                       float* __restrict__ Hout) {
     __shared__ double sh[8][33];
     __shared__ double smean[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
@@ -114,6 +143,19 @@ __global__ void k_bn_batch_stats(const float* __restrict__ U, int B, int C, cons
         for (int q = 0; q < 8; ++q) t += sh[q][cx];
         bn_finalize_train(c, mean, t / B, (double)B, bias, bn, st);
     }
+    __syncthreads();
+    if (c < C) {
+        const float sc = st.scale[c], sf = st.shift[c];
+        for (int b = ry; b < B; b += 8) Hout[(size_t)b * C + c] = fmaxf(sc * U[(size_t)b * C + c] + sf, 0.f);
+    }
+}
+
+// H = relu(scale*U + shift) (eval mode, after k_bn_eval_affine)
+__global__ void k_bn_apply(const float* __restrict__ U, size_t total, int C, BnState st, float* __restrict__ Hout) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    Hout[i] = fmaxf(st.scale[c] * U[i] + st.shift[c], 0.f);
 }
 
 // log_softmax over the last dim (pointnet.py:194); thread = row
@@ -148,72 +190,17 @@ __global__ void k_colsum(const float* __restrict__ G, int B, int J, float* __res
     out[j] = (float)s;
 }
 
-// dW[j][i] = sum_b dY(b,j) * X(b,i)
-struct ProbLinBwdW {
-    static constexpr bool A_KFAST = false, B_NFAST = true;
-    static constexpr int SCRATCH = 0;
-    using Cfg = CfgHead;
-    GradOut dy; ActIn in; float* dW; int B, J, I;
-    struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = B; }
-    __device__ void prologue(const Blk&, float*) const {}
-    __device__ float loadA(const Blk&, const float*, int m, int k) const { return m < J ? dy.at(k, m) : 0.f; }
-    __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < I ? in.at(k, n) : 0.f; }
-    __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
-#pragma unroll
-        for (int i = 0; i < Cfg::TM; ++i) {
-            int m = b.m0 + Cfg::row_of(ty, i);
-            if (m >= J) continue;
-#pragma unroll
-            for (int j = 0; j < Cfg::TN; ++j) {
-                int n = b.n0 + Cfg::col_of(tx, j);
-                if (n < I) dW[(size_t)m * I + n] = acc[i][j];
-            }
-        }
-    }
-};
-
-// dX[b][i] = sum_j dY(b,j) W[j][i]; if the input was relu(bn(Uin)) the ReLU mask is applied and the
-// result stored as dz of the previous layer, else it is the gradient of the head input.
-struct ProbLinBwdX {
-    static constexpr bool A_KFAST = true, B_NFAST = true;
-    static constexpr int SCRATCH = 0;
-    using Cfg = CfgHead;
-    GradOut dy; const float* W; ActIn in; float* dX; int B, J, I;
-    struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = J; }
-    __device__ void prologue(const Blk&, float*) const {}
-    __device__ float loadA(const Blk&, const float*, int m, int k) const { return m < B ? dy.at(m, k) : 0.f; }
-    __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < I ? W[(size_t)k * I + n] : 0.f; }
-    __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
-#pragma unroll
-        for (int i = 0; i < Cfg::TM; ++i) {
-            int m = b.m0 + Cfg::row_of(ty, i);
-            if (m >= B) continue;
-#pragma unroll
-            for (int j = 0; j < Cfg::TN; ++j) {
-                int n = b.n0 + Cfg::col_of(tx, j);
-                if (n >= I) continue;
-                float v = acc[i][j];
-                if (in.scale) {
-                    float z = in.scale[n] * in.U[(size_t)m * in.ld + n] + in.shift[n];
-                    if (!(z > 0.f)) v = 0.f;
-                }
-                dX[(size_t)m * I + n] = v;
-            }
-        }
-    }
-};
-
-// BatchNorm-over-batch backward sums.  block = 32 channels x 8 row lanes.
-__global__ void k_bn_batch_bwd(const float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
-                               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ m1, float* __restrict__ m2) {
+// BatchNorm-over-batch backward: sums -> dgamma, dbeta; then dU = s*(dz - m1 - yhat*m2) written IN PLACE over dz.
+// block = 32 channels x 8 row lanes.
+__global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ double sh1[8][33], sh2[8][33];
+    __shared__ float sm1[32], sm2[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
+    const float mu = c < C ? st.mean[c] : 0.f, r = c < C ? st.rstd[c] : 0.f, sc = c < C ? st.scale[c] : 0.f;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-        const float mu = st.mean[c], r = st.rstd[c];
         for (int b = ry; b < B; b += 8) {
             double dz = (double)DZ[(size_t)b * C + c];
             double yhat = (double)((U[(size_t)b * C + c] - mu) * r);
@@ -222,11 +209,20 @@ __global__ void k_bn_batch_bwd(const float* __restrict__ DZ, const float* __rest
     }
     sh1[ry][cx] = s1; sh2[ry][cx] = s2;
     __syncthreads();
-    if (ry == 0 && c < C) {
+    if (ry == 0) {
         double t1 = 0.0, t2 = 0.0;
         for (int q = 0; q < 8; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
-        dgamma[c] = (float)t2; dbeta[c] = (float)t1;
-        m1[c] = (float)(t1 / B); m2[c] = (float)(t2 / B);
+        if (c < C) { dgamma[c] = (float)t2; dbeta[c] = (float)t1; }
+        sm1[cx] = (float)(t1 / B); sm2[cx] = (float)(t2 / B);
+    }
+    __syncthreads();
+    if (c < C) {
+        const float m1 = sm1[cx], m2 = sm2[cx];
+        for (int b = ry; b < B; b += 8) {
+            const size_t i = (size_t)b * C + c;
+            const float yhat = (U[i] - mu) * r;
+            DZ[i] = sc * (DZ[i] - m1 - yhat * m2);
+        }
     }
 }
 
@@ -238,29 +234,28 @@ struct HeadArgs {
     cudaStream_t stream;
 };
 
-inline dim3 lin_grid(int rows, int cols) { return dim3(idiv_up(cols, CfgHead::BN), idiv_up(rows, CfgHead::BM)); }
-
 // X -> w.out  (logits, or t9 + identity)
 inline void head_forward(const HeadArgs& a, HeadWs& w) {
     const pgpd_head& h = *a.h;
     cudaStream_t s = a.stream;
     const int B = a.B;
-    {
-        ProbLinFwd p{ActIn{a.X, nullptr, nullptr, C3}, h.fc[0].w, nullptr, w.U1, B, H1, C3, 0};
-        launch_gemm<CfgHead>(p, lin_grid(B, H1), s);
+    // fc1: U1[b][j] = sum_i X[b][i] W1[j][i]
+    run_plain(ProbPlain<true, false>{a.X, h.fc[0].w, w.U1, w.part, B, H1, C3, (size_t)C3, 1, 1, (size_t)C3, 0, EPI_NONE, nullptr, 0, nullptr}, s, 8);
+    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H1, 32), dim3(256), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0], w.Hm1);
+    else {
+        launch(k_bn_eval_affine, grid1d(H1, 128), dim3(128), 0, s, H1, h.fc[0].b, h.bn[0], w.bn[0]);
+        launch(k_bn_apply, grid1d((size_t)B * H1, 256), dim3(256), 0, s, (const float*)w.U1, (size_t)B * H1, H1, w.bn[0], w.Hm1);
     }
-    if (a.train) launch(k_bn_batch_stats, grid1d(H1, 32), dim3(256), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0]);
-    else launch(k_bn_eval_affine, grid1d(H1, 128), dim3(128), 0, s, H1, h.fc[0].b, h.bn[0], w.bn[0]);
-    {
-        ProbLinFwd p{ActIn{w.U1, w.bn[0].scale, w.bn[0].shift, H1}, h.fc[1].w, nullptr, w.U2, B, H2, H1, 0};
-        launch_gemm<CfgHead>(p, lin_grid(B, H2), s);
+    // fc2
+    run_plain(ProbPlain<true, false>{w.Hm1, h.fc[1].w, w.U2, w.part, B, H2, H1, (size_t)H1, 1, 1, (size_t)H1, 0, EPI_NONE, nullptr, 0, nullptr}, s, 4);
+    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H2, 32), dim3(256), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1], w.Hm2);
+    else {
+        launch(k_bn_eval_affine, grid1d(H2, 128), dim3(128), 0, s, H2, h.fc[1].b, h.bn[1], w.bn[1]);
+        launch(k_bn_apply, grid1d((size_t)B * H2, 256), dim3(256), 0, s, (const float*)w.U2, (size_t)B * H2, H2, w.bn[1], w.Hm2);
     }
-    if (a.train) launch(k_bn_batch_stats, grid1d(H2, 32), dim3(256), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1]);
-    else launch(k_bn_eval_affine, grid1d(H2, 128), dim3(128), 0, s, H2, h.fc[1].b, h.bn[1], w.bn[1]);
-    {
-        ProbLinFwd p{ActIn{w.U2, w.bn[1].scale, w.bn[1].shift, H2}, h.fc[2].w, h.fc[2].b, w.out, B, a.out, H2, a.is_stn ? 1 : 0};
-        launch_gemm<CfgHead>(p, lin_grid(B, a.out), s);
-    }
+    // fc3 (+ bias, + identity for the T-Net)
+    run_plain(ProbPlain<true, false>{w.Hm2, h.fc[2].w, w.out, w.part, B, a.out, H2, (size_t)H2, 1, 1, (size_t)H2, 0, EPI_BIAS, h.fc[2].b,
+                                     a.is_stn ? 1 : 0, nullptr}, s, 4);
 }
 
 // w.dO (gradient w.r.t. w.out) -> parameter gradients and dX [B][1024]
@@ -268,29 +263,20 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     const pgpd_head& h = *a.h;
     cudaStream_t s = a.stream;
     const int B = a.B, J3 = a.out;
-    BnState none{};
-    GradOut d3{w.dO, nullptr, none, nullptr, nullptr, J3, false};
-    ActIn in3{w.U2, w.bn[1].scale, w.bn[1].shift, H2};
-    ActIn in2{w.U1, w.bn[0].scale, w.bn[0].shift, H1};
-    ActIn in1{a.X, nullptr, nullptr, C3};
-    // fc3
-    { ProbLinBwdW p{d3, in3, g.fc[2].dw, B, J3, H2}; launch_gemm<CfgHead>(p, lin_grid(J3, H2), s); }
+    // ---- fc3:  dW3[j][i] = sum_b dO[b][j] H2[b][i] ;  db3 = colsum(dO) ;  dz2 = (dO W3) masked by H2 > 0
+    run_plain(ProbPlain<false, true>{w.dO, w.Hm2, g.fc[2].dw, w.part, J3, H2, B, 1, (size_t)J3, (size_t)H2, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
     launch(k_colsum, grid1d(J3, 32), dim3(32), 0, s, (const float*)w.dO, B, J3, g.fc[2].db);
-    { ProbLinBwdX p{d3, h.fc[2].w, in3, w.DZ2, B, J3, H2}; launch_gemm<CfgHead>(p, lin_grid(B, H2), s); }
-    launch(k_bn_batch_bwd, grid1d(H2, 32), dim3(256), 0, s, (const float*)w.DZ2, (const float*)w.U2, B, H2, w.bn[1],
-           g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
-    // fc2
-    GradOut d2{w.DZ2, w.U2, w.bn[1], w.m1_2, w.m2_2, H2, true};
-    { ProbLinBwdW p{d2, in2, g.fc[1].dw, B, H2, H1}; launch_gemm<CfgHead>(p, lin_grid(H2, H1), s); }
+    run_plain(ProbPlain<true, true>{w.dO, h.fc[2].w, w.DZ2, w.part, B, H2, J3, (size_t)J3, 1, (size_t)H2, 1, 0, EPI_MASK, nullptr, 0, w.Hm2}, s);
+    launch(k_bn_batch_bwd_apply, grid1d(H2, 32), dim3(256), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta);
+    // ---- fc2 (w.DZ2 now holds dU2)
+    run_plain(ProbPlain<false, true>{w.DZ2, w.Hm1, g.fc[1].dw, w.part, H2, H1, B, 1, (size_t)H2, (size_t)H1, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
     launch(k_fill, grid1d(H2, 128), dim3(128), 0, s, g.fc[1].db, (size_t)H2, 0.f);
-    { ProbLinBwdX p{d2, h.fc[1].w, in2, w.DZ1, B, H2, H1}; launch_gemm<CfgHead>(p, lin_grid(B, H1), s); }
-    launch(k_bn_batch_bwd, grid1d(H1, 32), dim3(256), 0, s, (const float*)w.DZ1, (const float*)w.U1, B, H1, w.bn[0],
-           g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
-    // fc1
-    GradOut d1{w.DZ1, w.U1, w.bn[0], w.m1_1, w.m2_1, H1, true};
-    { ProbLinBwdW p{d1, in1, g.fc[0].dw, B, H1, C3}; launch_gemm<CfgHead>(p, lin_grid(H1, C3), s); }
+    run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.DZ1, w.part, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0, EPI_MASK, nullptr, 0, w.Hm1}, s);
+    launch(k_bn_batch_bwd_apply, grid1d(H1, 32), dim3(256), 0, s, w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta);
+    // ---- fc1 (w.DZ1 now holds dU1)
+    run_plain(ProbPlain<false, true>{w.DZ1, a.X, g.fc[0].dw, w.part, H1, C3, B, 1, (size_t)H1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
     launch(k_fill, grid1d(H1, 128), dim3(128), 0, s, g.fc[0].db, (size_t)H1, 0.f);
-    { ProbLinBwdX p{d1, h.fc[0].w, in1, dX, B, H1, C3}; launch_gemm<CfgHead>(p, lin_grid(B, C3), s); }
+    run_plain(ProbPlain<true, true>{w.DZ1, h.fc[0].w, dX, w.part, B, C3, H1, (size_t)H1, 1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
 }
 
 }  // namespace pgpd

@@ -509,15 +509,24 @@ __global__ void k_dw3(const float* __restrict__ coef, const int* __restrict__ id
                       int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec,
                       const float* __restrict__ WG, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
     __shared__ float sh[4][128];
-    const int c = (int)blockIdx.x, k = (int)threadIdx.x & 127, q = (int)threadIdx.x >> 7;
+    __shared__ float s_cf[512];
+    __shared__ int s_ix[512];
+    const int c = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
     const float sc = st2.scale[k], sf = st2.shift[k];
     float acc = 0.f;
-    for (int b = q; b < B; b += 4) {
-        const float cf = coef[(size_t)b * C3 + c];
-        if (cf != 0.f) {
-            const size_t P = (size_t)b * N + idx[(size_t)b * C3 + c];
-            acc = fmaf(cf, fmaxf(sc * Y2[P * C2 + k] + sf, 0.f), acc);
+    for (int b0 = 0; b0 < B; b0 += 512) {
+        const int nb = (B - b0 < 512) ? B - b0 : 512;
+        // stage this channel's coefficients / arg-max indices first, so the row loads below are independent
+        if (tid < nb) { s_cf[tid] = coef[(size_t)(b0 + tid) * C3 + c]; s_ix[tid] = idx[(size_t)(b0 + tid) * C3 + c]; }
+        __syncthreads();
+#pragma unroll 4
+        for (int bb = q; bb < nb; bb += 4) {
+            const float cf = s_cf[bb];
+            const size_t P = (size_t)(b0 + bb) * N + s_ix[bb];
+            const float a2v = fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
+            acc = fmaf(cf, a2v, acc);
         }
+        __syncthreads();
     }
     sh[q][k] = acc;
     __syncthreads();
@@ -759,6 +768,7 @@ __global__ void k_l1_bwd(const float* __restrict__ x, const float* __restrict__ 
     float dT[9];
     for (int e = 0; e < 9; ++e) dT[e] = 0.f;
     const int iters = (N + 3) / 4;
+#pragma unroll 4
     for (int it = 0; it < iters; ++it) {
         const int n = it * 4 + q;
         const bool ok = n < N;

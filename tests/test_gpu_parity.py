@@ -99,13 +99,14 @@ def test_shipped_checkpoint_known_answer(golden_dir):
     assert np.abs(logp1.cpu().numpy() - out["b1_logp_f64"]).max() < LOGP_TOL
 
 
-def _oracle_on_gpu(state, x, y, train):
-    """the oracle's torch port, executed by eager PyTorch on the GPU in true fp32 (TF32 off)."""
+def _oracle_on_gpu(state, x, y, train, dtype=torch.float32):
+    """the oracle's torch port, executed by eager PyTorch on the GPU in true fp32 (TF32 off) or fp64."""
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        sd = {k: v.cuda() for k, v in PT.to_torch_state(state, torch.float32).items()}
+        sd = {k: v.cuda() for k, v in PT.to_torch_state(state, dtype).items()}
+        x = x.to(dtype)
         if not train:
             with torch.no_grad():
                 return PT.pointnetcls_forward(sd, x, training=False), None
@@ -121,23 +122,29 @@ def _oracle_on_gpu(state, x, y, train):
 
 @pytest.mark.parametrize("B,N,k", [(512, 1024, 2), (256, 2048, 2), (512, 1024, 3)])
 def test_full_size_train_step_vs_oracle(B, N, k):
-    """BASELINE configs 2/3 (512x1024) and the per-GPU share of config 4 shape (2048 pts)."""
+    """BASELINE configs 2/3 (512x1024) and the per-GPU share of config 4 shape (2048 pts).
+    Ground truth = the oracle in fp64; our error must stay within a small multiple of the error the
+    reference's own fp32 arithmetic (the oracle in fp32) has against the same ground truth
+    (arg-max routing makes fp32 gradients discontinuous)."""
     st = W.make_state(900 + k, k=k)
     x = torch.tensor(W.make_clouds(901, B, N, "box")).cuda()
     y = torch.tensor(W.make_labels(902, B, k)).cuda()
     m = _model(st, N, k, train=True)
     logp, trans = m(x)
     torch.nn.functional.nll_loss(logp, y).backward()
-    (rl, rt), rg = _oracle_on_gpu(st, x, y, True)
-    assert float((logp - rl).abs().max()) < LOGP_TOL
-    assert float((trans - rt).abs().max()) < LOGP_TOL
-    assert bool((logp.argmax(1) == rl.argmax(1)).all())
+    (rl, rt), rg = _oracle_on_gpu(st, x, y, True, torch.float32)
+    (dl, dt), dg = _oracle_on_gpu(st, x, y, True, torch.float64)
+    assert float((logp.detach() - dl).abs().max()) < LOGP_TOL
+    assert float((trans.detach() - dt).abs().max()) < LOGP_TOL
+    assert float((logp.detach() - rl).abs().max()) < LOGP_TOL
+    assert bool((logp.argmax(1) == dl.argmax(1)).all())
     for n, p in m.named_parameters():
         if is_zero_grad_param(n):
             continue
-        r = rg[n].reshape(p.shape)
-        rel = float((p.grad - r).norm() / r.norm())
-        assert rel < 3e-2, (n, rel)      # two fp32 implementations with arg-max routing (SURVEY 7.2 C)
+        d = dg[n].reshape(p.shape)
+        ours = float((p.grad.double() - d).norm() / d.norm())
+        ref = float((rg[n].reshape(p.shape).double() - d).norm() / d.norm())
+        assert ours < max(GRAD_FLOOR, 4 * ref), (n, ours, ref)
 
 
 def test_inference_sweep_vs_oracle():
