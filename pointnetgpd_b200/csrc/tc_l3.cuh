@@ -35,7 +35,7 @@ constexpr int L3_A2_BYTES = 4 * L3_A2_PART;       // hi/lo x 2 k-blocks = 128 KB
 constexpr int L3_SMEM_W = L3_A2_BYTES;
 constexpr int L3_SMEM_MISC = L3_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3_SMEM_BYTES = L3_SMEM_MISC + 2048 + 1024;   // + slack to align the base to 1024 B
-constexpr int L3_THREADS = 320;
+constexpr int L3_THREADS = 448;                  // 14 warps: W producer, MMA issuer, 4 epilogue, 8 a2 producers
 constexpr float L3_ACT_SCALE = 16.0f;             // 2^4
 constexpr size_t L3_WIMG_BYTES = (size_t)8 * 2 * L3_STAGE_BYTES;   // 512 KB
 
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-        mbar_init(BAR(6), 128); mbar_init(BAR(7), 1);
+        mbar_init(BAR(6), 256); mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
         mbar_init(BAR(10), 128); mbar_init(BAR(11), 128);
         mbar_fence_init();
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
         // ===================== epilogue =====================
         const int q = warp & 3;                             // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;
+        const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
         for (int t = t_begin; t < t_end; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt = 0; mt < 8; ++mt) {
                 const int ch = mt * 128 + row;
-                const float mu = p.mu_s ? p.mu_s[ch] : 0.f;
+                const float mu = stats ? p.mu_s[ch] : 0.f;
                 { L3_T0(); mbar_wait(BAR(8 + acc), aphase); L3_ACC(6); }
                 tc_fence_after_sync();
                 const long long te0 = p.dbg ? clock64() : 0;
@@ -205,12 +206,21 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                     float v[32];
                     tmem_ld32(tbase + (uint32_t)c0, v);
                     if (c0 + 32 <= nvalid) {
-                        float m = v[0];
+                        // four independent chains each for the max and the centred squares (ILP)
+                        float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-                        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-                        if (p.mu_s) {
+                        for (int j = 4; j < 32; j += 4) {
+                            m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+                        }
+                        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        if (stats) {
+                            float c0s = 0.f, c1s = 0.f, c2s = 0.f, c3s = 0.f;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
+                            for (int j = 0; j < 32; j += 4) {
+                                const float d0 = v[j] - mu, d1 = v[j + 1] - mu, d2 = v[j + 2] - mu, d3 = v[j + 3] - mu;
+                                c0s = fmaf(d0, d0, c0s); c1s = fmaf(d1, d1, c1s); c2s = fmaf(d2, d2, c2s); c3s = fmaf(d3, d3, c3s);
+                            }
+                            css += (c0s + c1s) + (c2s + c3s);
                         }
                         if (m > best) {
                             best = m;
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (c0 + j < nvalid) {
-                                if (p.mu_s) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
+                                if (stats) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
                                 if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
                             }
                         }
@@ -236,7 +246,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
                 atomicMax(&p.keys[(size_t)b * C3 + ch], key);
-                if (p.mu_s) {
+                if (stats) {
                     const float iv = p.inv[ch];
                     p.css_part[(size_t)t * C3 + ch] = css * iv * iv;
                 }
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
         if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
     } else {
         // ===================== a2 producer =====================
-        const int wp = warp - 6;                            // 0..3
+        const int wp = warp - 6;                            // 0..7
         const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
@@ -265,17 +275,17 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             ephase ^= 1;
             const long long tp0 = p.dbg ? clock64() : 0;
             constexpr int U = 8;
-            for (int i0 = 0; i0 < L3_NT / 4; i0 += U) {
+            for (int i0 = 0; i0 < L3_NT / 8; i0 += U) {
                 float4 y[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {               // all loads of U rows first (memory-level parallelism)
-                    const int r = wp + 4 * (i0 + u);
+                    const int r = wp + 8 * (i0 + u);
                     y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = wp + 4 * (i0 + u);
+                    const int r = wp + 8 * (i0 + u);
                     const bool ok = r < nvalid;
                     float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
                     float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;

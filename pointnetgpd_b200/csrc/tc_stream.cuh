@@ -16,7 +16,8 @@
 namespace pgpd { namespace tc {
 
 constexpr int ST_NT = 128;                 // points per tile
-constexpr int ST_THREADS = 320;
+constexpr int ST_THREADS = 448;            // 14 warps: loader, MMA issuer, 8 epilogue, 4 producer
+constexpr int ST_EPI_ROWS = 2;              // partial rows each CTA writes (two epilogue warps per TMEM quadrant)
 constexpr float ACT_SCALE = 16.0f;         // 2^4 applied to O(1) activations before the fp16 split
 constexpr int ACT_SHIFT = 4;
 
@@ -69,7 +70,7 @@ __global__ void k_prepack_rows(const float* __restrict__ W, int sr, int sk, int 
 //   __device__ static void epi_cols(Epi&, const Params&, int feat, size_t P0, int nvalid, const float (&v)[32], const float* aux);
 //        32 consecutive points P0.. of output feature `feat`; columns >= nvalid are padding; aux[k*128 + j] is the
 //        k-th auxiliary value of column j.
-//   __device__ static void epi_end(Epi&, const Params&, int feat, int cta);
+//   __device__ static void epi_end(Epi&, const Params&, int feat, int row);   // row < ST_EPI_ROWS * gridDim.x: partial row to write
 template <class T>
 struct StreamCfg {
     static constexpr int KD = T::KD, NKB = KD / 64;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
         mbar_init(BAR(1), 128); mbar_init(BAR(2), 128);
         mbar_init(BAR(3), 1); mbar_init(BAR(4), 1);
         mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-        mbar_init(BAR(7), 128); mbar_init(BAR(8), 128);
+        mbar_init(BAR(7), 256); mbar_init(BAR(8), 256);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
@@ -151,9 +152,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
                 if (++buf == 2) { buf = 0; phase ^= 1; }
             }
         }
-    } else if (warp < 6) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;
+    } else if (warp < 10) {
+        // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 64 columns each =====================
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int feat = q * 32 + lane;
         typename T::Epi st;
         T::epi_begin(st, p, feat);
@@ -165,20 +166,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
             mbar_wait(BAR(5 + buf), phase);
             tc_fence_after_sync();
             const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ST_NT);
-            for (int c0 = 0; c0 < ST_NT; c0 += 32) {
-                if (c0 >= nvalid) break;
-                float v[32];
-                tmem_ld32(tbase + (uint32_t)c0, v);
-                T::epi_cols(st, p, feat, P0 + c0, nvalid - c0, v, s_aux + buf * 512 + c0);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = half * 64 + cc * 32;
+                if (c0 < nvalid) {
+                    float v[32];
+                    tmem_ld32(tbase + (uint32_t)c0, v);
+                    T::epi_cols(st, p, feat, P0 + c0, nvalid - c0, v, s_aux + buf * 512 + c0);
+                }
             }
             tc_fence_before_sync();
             mbar_arrive(BAR(7 + buf));
             if (++buf == 2) { buf = 0; phase ^= 1; }
         }
-        T::epi_end(st, p, feat, cta);
+        T::epi_end(st, p, feat, cta * ST_EPI_ROWS + half);
     } else {
         // ===================== operand producer =====================
-        const int wp = warp - 6;
+        const int wp = warp - 10;
         constexpr int LPR = Cfg::KD / 4;                    // lanes per row: 32 (KD=128) or 16 (KD=64)
         constexpr int RPI = 32 / LPR;                       // rows per warp iteration: 1 or 2
         const int cg = lane % LPR, rsub = lane / LPR;
@@ -332,29 +336,31 @@ struct L2BwdATC {
         e.s1 = 0.f; e.s2 = 0.f; e.mxdz = 0.f; e.mxyh = 0.f;
     }
     __device__ static void epi_cols(Epi& e, const Params& p, int c, size_t P0, int nvalid, const float (&v)[32], const float*) {
-        // phase 1: every global load of the 32 columns (kept apart from the stores so they overlap)
-        float y[32], ds[32];
-        int sl[32];
+        // two groups of 16 columns; within a group every global load is issued before any store (they overlap)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const bool ok = j < nvalid;
-            y[j] = ok ? __ldg(p.Y2 + (P0 + j) * C2 + c) : 0.f;
-            sl[j] = ok ? __ldg(p.slot + P0 + j) : -1;
-        }
+        for (int g0 = 0; g0 < 32; g0 += 16) {
+            float y[16], ds[16];
+            int sl[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ds[j] = (sl[j] >= 0) ? __ldg(p.da2s + (size_t)sl[j] * C2 + c) : 0.f;
-        // phase 2: arithmetic + stores
+            for (int j = 0; j < 16; ++j) {
+                const bool ok = g0 + j < nvalid;
+                y[j] = ok ? __ldg(p.Y2 + (P0 + g0 + j) * C2 + c) : 0.f;
+                sl[j] = ok ? __ldg(p.slot + P0 + g0 + j) : -1;
+            }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < nvalid) {
-                const float da2 = -v[j] * e.inv - e.u + ds[j];
-                const float dz = (e.sc * y[j] + e.sh > 0.f) ? da2 : 0.f;
-                p.DZ2[(P0 + j) * C2 + c] = dz;
-                const float yh = (y[j] - e.mu) * e.r;
-                e.s1 += dz;
-                e.s2 = fmaf(dz, yh, e.s2);
-                e.mxdz = fmaxf(e.mxdz, fabsf(dz));
-                e.mxyh = fmaxf(e.mxyh, fabsf(yh));
+            for (int j = 0; j < 16; ++j) ds[j] = (sl[j] >= 0) ? __ldg(p.da2s + (size_t)sl[j] * C2 + c) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (g0 + j < nvalid) {
+                    const float da2 = -v[g0 + j] * e.inv - e.u + ds[j];
+                    const float dz = (e.sc * y[j] + e.sh > 0.f) ? da2 : 0.f;
+                    p.DZ2[(P0 + g0 + j) * C2 + c] = dz;
+                    const float yh = (y[j] - e.mu) * e.r;
+                    e.s1 += dz;
+                    e.s2 = fmaf(dz, yh, e.s2);
+                    e.mxdz = fmaxf(e.mxdz, fabsf(dz));
+                    e.mxyh = fmaxf(e.mxyh, fabsf(yh));
+                }
             }
         }
     }

@@ -63,7 +63,7 @@ struct TowerScratch {
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
-    float* pmax;      // [256][2][128] per-CTA maxima of |dz2|, |yhat2|
+    float* pmax;      // [512][2][128] per-epilogue-row maxima of |dz2|, |yhat2|
     float* esc;       // [128] per-channel power-of-two scale of dy2 (tcgen05 dW2)
     float* einv;      // [128] its inverse
     // backward scratch
@@ -116,7 +116,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     // persistent tcgen05 kernels write one partial row per CTA (<= TC_MAX_CTAS rows)
     constexpr size_t TC_MAX_CTAS = 256;
     size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
-    fp = std::max(fp, TC_MAX_CTAS * C2);
+    fp = std::max(fp, 2 * TC_MAX_CTAS * 2 * C2);
     fp = std::max(fp, (size_t)B * w.tiles_per_cloud * C3);                   // css3 partials
     if (backward) {
         fp = std::max(fp, (size_t)w.nb_gram * C2 * C2);                      // Gram partials
@@ -132,7 +132,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.mu_s = c.take<float>(C3);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
-    w.pmax = c.take<float>((size_t)256 * 2 * C2);
+    w.pmax = c.take<float>((size_t)512 * 2 * C2);
     w.esc = c.take<float>(C2);
     w.einv = c.take<float>(C2);
     if (backward) {
@@ -862,7 +862,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         tc::L2FwdTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.A1, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
                               w.Y2, w.fpart};
         tc::launch_stream<tc::L2FwdTC>(p, tc::dev_info().sms, s);
-        n_css2 = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+        n_css2 = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
     } else
 #endif
     {
@@ -978,7 +978,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
             tc::L2BwdATC::Params p{(const __half*)w.wimg_s, M, ntiles, w.Y2, w.bn[1].scale, w.bn[1].shift, w.bn[1].mean, w.bn[1].rstd,
                                    w.inv_s, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, w.pmax};
             tc::launch_stream<tc::L2BwdATC>(p, tc::dev_info().sms, s);
-            nrows = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+            nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
             g_b4 = nrows;
         } else
 #endif
@@ -1023,7 +1023,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
                                    w.m1_2, w.m2_2, a.x, a.trans, a.N, w.inv_s, w.A1, t.conv[0].w, w.bn[0].mean, w.bn[0].rstd,
                                    w.DZ1, w.fpart};
             tc::launch_stream<tc::L2BwdBTC>(p, tc::dev_info().sms, s);
-            nrows = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+            nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
         } else
 #endif
         {
