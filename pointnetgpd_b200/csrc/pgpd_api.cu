@@ -133,6 +133,18 @@ int pgpd_debug_l3_counters(long long* host_out) {
 #endif
 }
 
+/* tuning aid: route the streaming kernels' cycle counters to the same debug buffer (on != 0) or switch them off */
+int pgpd_debug_stream_counters(int on) {
+#ifdef PGPD_EMU
+    (void)on; return PGPD_E_UNSUPPORTED;
+#else
+    long long* ptr = on ? tc::l3_debug_buffer() : nullptr;
+    cudaDeviceSynchronize();
+    if (on) cudaMemset(ptr, 0, 256 * 8 * sizeof(long long));
+    return cudaMemcpyToSymbol(tc::g_stream_dbg, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : PGPD_E_CUDA;
+#endif
+}
+
 size_t pgpd_workspace_bytes(int what, int B, int N, int k, int flags) {
     if (B < 1 || N < 1) return 0;
     ModelWs w;

@@ -18,7 +18,7 @@
 namespace pgpd { namespace tc {
 
 constexpr int AC_NT = 128;        // points per tile (MMA K extent per tile)
-constexpr int AC_THREADS = 320;
+constexpr int AC_THREADS = 448;      // 14 warps: (idle), MMA issuer, 4 epilogue, 8 producers
 
 // MN-major SWIZZLE_128B descriptor: atoms of 64 M/N-elements (128 B) x 8 K-rows; atom pitch `lbo` bytes
 __device__ __forceinline__ uint64_t desc_sw128_mnmajor(uint32_t saddr, uint32_t lbo) {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(AC_THREADS, 1) k_accum_tc(typename T::Params p
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        mbar_init(BAR(0), 128); mbar_init(BAR(1), 128);
+        mbar_init(BAR(0), 256); mbar_init(BAR(1), 256);
         mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
         mbar_init(BAR(4), 1);
         mbar_fence_init();
@@ -148,13 +148,13 @@ __global__ void __launch_bounds__(AC_THREADS, 1) k_accum_tc(typename T::Params p
             {
                 const int cg = lane, atom = cg >> 4, chunk = (cg & 15) >> 1, half8 = cg & 1;
                 constexpr int U = 8;
-                for (int i0 = 0; i0 < AC_NT / 4; i0 += U) {
+                for (int i0 = 0; i0 < AC_NT / 8; i0 += U) {
                     typename T::RawA raw[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { const int r = wp + 4 * (i0 + u); T::fetchA(pa, p, P0 + r, r < nvalid, cg, raw[u]); }
+                    for (int u = 0; u < U; ++u) { const int r = wp + 8 * (i0 + u); T::fetchA(pa, p, P0 + r, r < nvalid, cg, raw[u]); }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int r = wp + 4 * (i0 + u);
+                        const int r = wp + 8 * (i0 + u);
                         float v[4];
                         T::transformA(pa, p, r < nvalid, raw[u], v);
                         __half2 h01, l01, h23, l23;
@@ -173,14 +173,14 @@ __global__ void __launch_bounds__(AC_THREADS, 1) k_accum_tc(typename T::Params p
             if (!T::SAME) {
                 unsigned char* bb = ab + Cfg::A_BYTES;
                 const int cg = lane & 15, rsub = lane >> 4, chunk = cg >> 1, half8 = cg & 1;
-                constexpr int U = 4;
-                for (int i0 = 0; i0 < AC_NT / 8; i0 += U) {
+                constexpr int U = 8;
+                for (int i0 = 0; i0 < AC_NT / 16; i0 += U) {
                     typename T::RawB raw[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { const int r = (wp + 4 * (i0 + u)) * 2 + rsub; T::fetchB(pb, p, P0 + r, r < nvalid, cg, raw[u]); }
+                    for (int u = 0; u < U; ++u) { const int r = (wp + 8 * (i0 + u)) * 2 + rsub; T::fetchB(pb, p, P0 + r, r < nvalid, cg, raw[u]); }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int r = (wp + 4 * (i0 + u)) * 2 + rsub;
+                        const int r = (wp + 8 * (i0 + u)) * 2 + rsub;
                         float v[4];
                         T::transformB(pb, p, r < nvalid, raw[u], v);
                         __half2 h01, l01, h23, l23;
@@ -274,6 +274,9 @@ struct DW2TC {
         q.m1 = *reinterpret_cast<const float4*>(p.m1 + 4 * cg);
         q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
         q.e = *reinterpret_cast<const float4*>(p.esc + 4 * cg);
+        // fold: e*dy2 = (e*s)*(dz - m1) - (e*s*r*m2)*(y - mu)
+        q.s.x *= q.e.x; q.s.y *= q.e.y; q.s.z *= q.e.z; q.s.w *= q.e.w;
+        q.r.x *= q.s.x * q.m2.x; q.r.y *= q.s.y * q.m2.y; q.r.z *= q.s.z * q.m2.z; q.r.w *= q.s.w * q.m2.w;
     }
     __device__ static void prefetch(const Params& p, size_t P0, int nrows) {
         l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
@@ -289,10 +292,10 @@ struct DW2TC {
     }
     __device__ static float clampf(float x) { return fminf(fmaxf(x, -60000.f), 60000.f); }
     __device__ static void transformA(ProdA& q, const Params&, bool valid, const RawA& r, float (&v)[4]) {
-        v[0] = valid ? clampf(q.e.x * q.s.x * (r.dz.x - q.m1.x - (r.y.x - q.mu.x) * q.r.x * q.m2.x)) : 0.f;
-        v[1] = valid ? clampf(q.e.y * q.s.y * (r.dz.y - q.m1.y - (r.y.y - q.mu.y) * q.r.y * q.m2.y)) : 0.f;
-        v[2] = valid ? clampf(q.e.z * q.s.z * (r.dz.z - q.m1.z - (r.y.z - q.mu.z) * q.r.z * q.m2.z)) : 0.f;
-        v[3] = valid ? clampf(q.e.w * q.s.w * (r.dz.w - q.m1.w - (r.y.w - q.mu.w) * q.r.w * q.m2.w)) : 0.f;
+        v[0] = valid ? clampf(q.s.x * (r.dz.x - q.m1.x) - q.r.x * (r.y.x - q.mu.x)) : 0.f;
+        v[1] = valid ? clampf(q.s.y * (r.dz.y - q.m1.y) - q.r.y * (r.y.y - q.mu.y)) : 0.f;
+        v[2] = valid ? clampf(q.s.z * (r.dz.z - q.m1.z) - q.r.z * (r.y.z - q.mu.z)) : 0.f;
+        v[3] = valid ? clampf(q.s.w * (r.dz.w - q.m1.w) - q.r.w * (r.y.w - q.mu.w)) : 0.f;
     }
     struct ProdB { int d; };
     struct RawB { float4 a; };

@@ -81,6 +81,10 @@ struct StreamCfg {
     static constexpr int SMEM_BYTES = OFF_MISC + 256 + 4096 + 1024;
 };
 
+// tuning aid: when non-null, every CTA writes 8 cycle counters here
+//  0 mma wait b_full  1 mma wait tmem_empty  2 mma total  3 prod wait  4 prod work  5 epi wait  6 epi work
+__device__ long long* g_stream_dbg = nullptr;
+
 template <class T>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params p) {
     using Cfg = StreamCfg<T>;
@@ -112,6 +116,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+    long long* const dbg = g_stream_dbg;
+    long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define ST_WAIT(slot, call) do { const long long _t0 = dbg ? clock64() : 0; call; if (dbg) dacc[slot] += clock64() - _t0; } while (0)
 
     if (warp == 0) {
         // ===================== weight loader (once) =====================
@@ -127,9 +134,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
             tc_fence_after_sync();
             uint32_t phase = 0;
             int buf = 0;
+            const long long tl0 = dbg ? clock64() : 0;
             for (int t = t_begin; t < t_end; ++t) {
-                mbar_wait(BAR(1 + buf), phase);             // operand tile staged
-                mbar_wait(BAR(7 + buf), phase ^ 1);         // accumulator drained
+                ST_WAIT(0, mbar_wait(BAR(1 + buf), phase));             // operand tile staged
+                ST_WAIT(1, mbar_wait(BAR(7 + buf), phase ^ 1));         // accumulator drained
                 tc_fence_after_sync();
                 const uint32_t d = tmem + (uint32_t)(buf * ST_NT);
                 const uint32_t bb = sbase + Cfg::OFF_B + buf * Cfg::B_BYTES;
@@ -151,6 +159,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
                 mma_commit(BAR(5 + buf));                   // accumulator complete
                 if (++buf == 2) { buf = 0; phase ^= 1; }
             }
+            if (dbg) { dbg[cta * 8 + 0] = dacc[0]; dbg[cta * 8 + 1] = dacc[1]; dbg[cta * 8 + 2] = clock64() - tl0; }
         }
     } else if (warp < 10) {
         // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 64 columns each =====================
@@ -163,8 +172,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
         for (int t = t_begin; t < t_end; ++t) {
             const size_t P0 = (size_t)t * ST_NT;
             const int nvalid = (p.M - P0 < (size_t)ST_NT) ? (int)(p.M - P0) : ST_NT;
-            mbar_wait(BAR(5 + buf), phase);
+            ST_WAIT(5, mbar_wait(BAR(5 + buf), phase));
             tc_fence_after_sync();
+            const long long te0 = dbg ? clock64() : 0;
             const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ST_NT);
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -177,9 +187,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
             }
             tc_fence_before_sync();
             mbar_arrive(BAR(7 + buf));
+            if (dbg) dacc[6] += clock64() - te0;
             if (++buf == 2) { buf = 0; phase ^= 1; }
         }
         T::epi_end(st, p, feat, cta * ST_EPI_ROWS + half);
+        if (dbg && warp == 4 && lane == 0) { dbg[cta * 8 + 5] = dacc[5]; dbg[cta * 8 + 6] = dacc[6]; }
     } else {
         // ===================== operand producer =====================
         const int wp = warp - 10;
@@ -194,8 +206,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
         for (int t = t_begin; t < t_end; ++t) {
             const size_t P0 = (size_t)t * ST_NT;
             const int nvalid = (p.M - P0 < (size_t)ST_NT) ? (int)(p.M - P0) : ST_NT;
-            mbar_wait(BAR(3 + buf), phase ^ 1);             // MMAs of two tiles ago are done with this buffer
-            mbar_wait(BAR(7 + buf), phase ^ 1);             // ... and its epilogue no longer reads aux[buf]
+            ST_WAIT(3, mbar_wait(BAR(3 + buf), phase ^ 1));             // MMAs of two tiles ago are done with this buffer
+            ST_WAIT(3, mbar_wait(BAR(7 + buf), phase ^ 1));             // ... and its epilogue no longer reads aux[buf]
+            const long long tp0 = dbg ? clock64() : 0;
             unsigned char* bb = smem + Cfg::OFF_B + buf * Cfg::B_BYTES;
             if (wp == 0 && lane == 0 && t + 2 < t_end) {
                 const size_t Pn = (size_t)(t + 2) * ST_NT;
@@ -229,9 +242,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
             }
             fence_proxy_async_smem();
             mbar_arrive(BAR(1 + buf));
+            if (dbg) dacc[4] += clock64() - tp0;
             if (++buf == 2) { buf = 0; phase ^= 1; }
         }
+        if (dbg && wp == 0 && lane == 0) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
     }
+#undef ST_WAIT
 
     tc_fence_before_sync();
     __syncthreads();
@@ -375,8 +391,9 @@ struct L2BwdATC {
 // ==================================================================================================================
 // layer 2 backward, pass 2b:  d a1[P][k] = sum_c W2[c][k] dy2[P][c],  dy2 = s2 (dz2 - m1 - yhat2 m2);
 // dz1 = mask * d a1 (stored); per-channel sums of dz1 and dz1*yhat1 (BatchNorm1 backward).
-// dy2 rows are scaled per POINT by a power of two (gradients have no fixed magnitude); aux[0] undoes it,
-// aux[1..3] carry the transformed coordinates x' of the point (for yhat1 = (W1 x' - mean1) * rstd1).
+// dy2 rows are scaled per POINT by a power of two (gradients have no fixed magnitude); aux[0] undoes it.
+// yhat1 is only needed where dz1 != 0, i.e. where a1 > 0, and there a1 = gamma1*yhat1 + beta1, so
+// yhat1 = (a1 - beta1) / gamma1 -- no need to recompute the layer-1 pre-activation from the coordinates.
 // ==================================================================================================================
 struct L2BwdBTC {
     static constexpr int KD = 128;
@@ -384,9 +401,8 @@ struct L2BwdBTC {
         const __half* Aimg; size_t M; int ntiles;
         const float* DZ2; const float* Y2; const float* scale2; const float* mean2; const float* rstd2;
         const float* m1; const float* m2;
-        const float* x; const float* trans; int N;
-        const float* inv; const float* A1; const float* W1; const float* mean1; const float* rstd1;
-        float* DZ1; float* part;     // part [G][2][64]
+        const float* inv; const float* A1; const float* gamma1; const float* beta1;
+        float* DZ1; float* part;     // part [rows][2][64]
     };
     struct Prod { float4 s, mu, r, m1, m2; };
     __device__ static void prod_begin(Prod& q, const Params& p, int cg) {
@@ -395,38 +411,28 @@ struct L2BwdBTC {
         q.r = *reinterpret_cast<const float4*>(p.rstd2 + 4 * cg);
         q.m1 = *reinterpret_cast<const float4*>(p.m1 + 4 * cg);
         q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
+        // fold: dy2 = s*(dz - m1) - (s*r*m2)*(y - mu)
+        q.r.x *= q.s.x * q.m2.x; q.r.y *= q.s.y * q.m2.y; q.r.z *= q.s.z * q.m2.z; q.r.w *= q.s.w * q.m2.w;
     }
-    struct Raw { float4 dz, y; float xa; };
+    struct Raw { float4 dz, y; };
     __device__ static void prefetch(const Params& p, size_t P0, int nrows) {
         l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
         l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
         l2_prefetch(p.A1 + P0 * C1, (uint32_t)nrows * C1 * 4u);
     }
     __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
-        r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz; r.xa = 0.f;
+        r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz;
         if (valid) {
             r.dz = *reinterpret_cast<const float4*>(p.DZ2 + P * C2 + 4 * cg);
             r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
-            if (cg >= 1 && cg < 4) {
-                // transformed coordinate x'_(cg-1) of this point (B*N < 2^24, so 32-bit index math)
-                const int P32 = (int)P, b = P32 / p.N, n = P32 - b * p.N, i = cg - 1;
-                const float* xb = p.x + (size_t)b * 3 * p.N;
-                const float p0 = xb[n], p1 = xb[p.N + n], p2 = xb[2 * p.N + n];
-                if (p.trans) {
-                    const float* Tm = p.trans + (size_t)b * 9;
-                    r.xa = Tm[i] * p0 + Tm[3 + i] * p1 + Tm[6 + i] * p2;
-                } else {
-                    r.xa = i == 0 ? p0 : (i == 1 ? p1 : p2);
-                }
-            }
         }
     }
-    __device__ static float transform(Prod& q, const Params&, size_t, bool valid, int cg, const Raw& r, float (&v)[4]) {
+    __device__ static float transform(Prod& q, const Params&, size_t, bool valid, int, const Raw& r, float (&v)[4]) {
         const float4 dz = r.dz, y = r.y;
-        float d0 = q.s.x * (dz.x - q.m1.x - (y.x - q.mu.x) * q.r.x * q.m2.x);
-        float d1 = q.s.y * (dz.y - q.m1.y - (y.y - q.mu.y) * q.r.y * q.m2.y);
-        float d2 = q.s.z * (dz.z - q.m1.z - (y.z - q.mu.z) * q.r.z * q.m2.z);
-        float d3 = q.s.w * (dz.w - q.m1.w - (y.w - q.mu.w) * q.r.w * q.m2.w);
+        float d0 = q.s.x * (dz.x - q.m1.x) - q.r.x * (y.x - q.mu.x);
+        float d1 = q.s.y * (dz.y - q.m1.y) - q.r.y * (y.y - q.mu.y);
+        float d2 = q.s.z * (dz.z - q.m1.z) - q.r.z * (y.z - q.mu.z);
+        float d3 = q.s.w * (dz.w - q.m1.w) - q.r.w * (y.w - q.mu.w);
         if (!valid) { d0 = d1 = d2 = d3 = 0.f; }
         float mx = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3)));
 #pragma unroll
@@ -436,15 +442,16 @@ struct L2BwdBTC {
         e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
         const float sc = __uint_as_float((uint32_t)(127 + e) << 23);
         v[0] = d0 * sc; v[1] = d1 * sc; v[2] = d2 * sc; v[3] = d3 * sc;
-        return (cg == 0) ? __uint_as_float((uint32_t)(127 - e) << 23) : r.xa;
+        return __uint_as_float((uint32_t)(127 - e) << 23);
     }
-    struct Epi { float inv, w0, w1, w2, mu, r, s1, s2; };
+    struct Epi { float inv, be, ginv, s1, s2; };
     __device__ static void epi_begin(Epi& e, const Params& p, int k) {
-        e.s1 = 0.f; e.s2 = 0.f;
+        e.s1 = 0.f; e.s2 = 0.f; e.inv = 0.f; e.be = 0.f; e.ginv = 0.f;
         if (k < C1) {
-            e.inv = p.inv[k]; e.w0 = p.W1[k * 3 + 0]; e.w1 = p.W1[k * 3 + 1]; e.w2 = p.W1[k * 3 + 2];
-            e.mu = p.mean1[k]; e.r = p.rstd1[k];
-        } else { e.inv = e.w0 = e.w1 = e.w2 = e.mu = e.r = 0.f; }
+            e.inv = p.inv[k]; e.be = p.beta1[k];
+            const float g = p.gamma1[k];
+            e.ginv = g != 0.f ? 1.0f / g : 0.f;
+        }
     }
     __device__ static void epi_cols(Epi& e, const Params& p, int k, size_t P0, int nvalid, const float (&v)[32], const float* aux) {
         if (k >= C1) return;
@@ -455,18 +462,18 @@ struct L2BwdBTC {
         for (int j = 0; j < 32; ++j) {
             if (j < nvalid) {
                 const float da1 = v[j] * e.inv * aux[j];
-                const float dz = a[j] > 0.f ? da1 : 0.f;
+                const bool on = a[j] > 0.f;
+                const float dz = on ? da1 : 0.f;
                 p.DZ1[(P0 + j) * C1 + k] = dz;
-                const float u = e.w0 * aux[128 + j] + e.w1 * aux[256 + j] + e.w2 * aux[384 + j];
-                const float yh = (u - e.mu) * e.r;
+                const float yh = (a[j] - e.be) * e.ginv;       // only used where dz != 0
                 e.s1 += dz;
                 e.s2 = fmaf(dz, yh, e.s2);
             }
         }
     }
-    __device__ static void epi_end(Epi& e, const Params& p, int k, int cta) {
+    __device__ static void epi_end(Epi& e, const Params& p, int k, int row) {
         if (k >= C1) return;
-        float* o = p.part + (size_t)cta * 2 * C1;
+        float* o = p.part + (size_t)row * 2 * C1;
         o[k] = e.s1; o[C1 + k] = e.s2;
     }
 };

@@ -1020,8 +1020,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
             launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, t.conv[1].w, 1, C1, C1, C2, 0, (__half*)w.wimg_s, w.inv_s);
             const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
             tc::L2BwdBTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.DZ2, w.Y2, w.bn[1].scale, w.bn[1].mean, w.bn[1].rstd,
-                                   w.m1_2, w.m2_2, a.x, a.trans, a.N, w.inv_s, w.A1, t.conv[0].w, w.bn[0].mean, w.bn[0].rstd,
-                                   w.DZ1, w.fpart};
+                                   w.m1_2, w.m2_2, w.inv_s, w.A1, t.bn[0].gamma, t.bn[0].beta, w.DZ1, w.fpart};
             tc::launch_stream<tc::L2BwdBTC>(p, tc::dev_info().sms, s);
             nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
         } else
