@@ -333,50 +333,50 @@ struct L2BwdATC {
         s.sc.x *= ACT_SCALE; s.sc.y *= ACT_SCALE; s.sc.z *= ACT_SCALE; s.sc.w *= ACT_SCALE;
         s.sh.x *= ACT_SCALE; s.sh.y *= ACT_SCALE; s.sh.z *= ACT_SCALE; s.sh.w *= ACT_SCALE;
     }
-    struct Raw { float4 y; };
+    struct Raw { float4 y; int sl; };
     __device__ static void prefetch(const Params& p, size_t P0, int nrows) { l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u); }
     __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
         r.y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
+        r.sl = -1;
+        if (valid) {
+            r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
+            if (cg == 1) r.sl = __ldg(p.slot + P);      // staged in shared memory (aux[1]) for the epilogue
+        }
     }
-    __device__ static float transform(Prod& s, const Params&, size_t, bool valid, int, const Raw& r, float (&v)[4]) {
+    __device__ static float transform(Prod& s, const Params&, size_t, bool valid, int cg, const Raw& r, float (&v)[4]) {
         const float4 y = r.y;
         v[0] = valid ? fminf(fmaxf(fmaf(s.sc.x, y.x, s.sh.x), 0.f), 60000.f) : 0.f;
         v[1] = valid ? fminf(fmaxf(fmaf(s.sc.y, y.y, s.sh.y), 0.f), 60000.f) : 0.f;
         v[2] = valid ? fminf(fmaxf(fmaf(s.sc.z, y.z, s.sh.z), 0.f), 60000.f) : 0.f;
         v[3] = valid ? fminf(fmaxf(fmaf(s.sc.w, y.w, s.sh.w), 0.f), 60000.f) : 0.f;
-        return 1.f;
+        return cg == 1 ? __int_as_float(r.sl) : 1.f;
     }
     __device__ static void epi_begin(Epi& e, const Params& p, int c) {
         e.inv = p.inv[c]; e.u = p.uvec[c]; e.sc = p.scale2[c]; e.sh = p.shift2[c]; e.mu = p.mean2[c]; e.r = p.rstd2[c];
         e.s1 = 0.f; e.s2 = 0.f; e.mxdz = 0.f; e.mxyh = 0.f;
     }
-    __device__ static void epi_cols(Epi& e, const Params& p, int c, size_t P0, int nvalid, const float (&v)[32], const float*) {
-        // two groups of 16 columns; within a group every global load is issued before any store (they overlap)
+    __device__ static void epi_cols(Epi& e, const Params& p, int c, size_t P0, int nvalid, const float (&v)[32], const float* aux) {
+        // every global load of the 32 columns is issued before any store; the row index of the sparse part comes
+        // from shared memory (aux[1], staged by the producer), so both loads of a column are independent
+        float y[32], ds[32];
 #pragma unroll
-        for (int g0 = 0; g0 < 32; g0 += 16) {
-            float y[16], ds[16];
-            int sl[16];
+        for (int j = 0; j < 32; ++j) {
+            const bool ok = j < nvalid;
+            const int sl = ok ? __float_as_int(aux[128 + j]) : -1;
+            y[j] = ok ? __ldg(p.Y2 + (P0 + j) * C2 + c) : 0.f;
+            ds[j] = (sl >= 0) ? __ldg(p.da2s + (size_t)sl * C2 + c) : 0.f;
+        }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const bool ok = g0 + j < nvalid;
-                y[j] = ok ? __ldg(p.Y2 + (P0 + g0 + j) * C2 + c) : 0.f;
-                sl[j] = ok ? __ldg(p.slot + P0 + g0 + j) : -1;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ds[j] = (sl[j] >= 0) ? __ldg(p.da2s + (size_t)sl[j] * C2 + c) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (g0 + j < nvalid) {
-                    const float da2 = -v[g0 + j] * e.inv - e.u + ds[j];
-                    const float dz = (e.sc * y[j] + e.sh > 0.f) ? da2 : 0.f;
-                    p.DZ2[(P0 + g0 + j) * C2 + c] = dz;
-                    const float yh = (y[j] - e.mu) * e.r;
-                    e.s1 += dz;
-                    e.s2 = fmaf(dz, yh, e.s2);
-                    e.mxdz = fmaxf(e.mxdz, fabsf(dz));
-                    e.mxyh = fmaxf(e.mxyh, fabsf(yh));
-                }
+        for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+                const float da2 = -v[j] * e.inv - e.u + ds[j];
+                const float dz = (e.sc * y[j] + e.sh > 0.f) ? da2 : 0.f;
+                p.DZ2[(P0 + j) * C2 + c] = dz;
+                const float yh = (y[j] - e.mu) * e.r;
+                e.s1 += dz;
+                e.s2 = fmaf(dz, yh, e.s2);
+                e.mxdz = fmaxf(e.mxdz, fabsf(dz));
+                e.mxyh = fmaxf(e.mxyh, fabsf(yh));
             }
         }
     }

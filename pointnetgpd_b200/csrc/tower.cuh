@@ -104,8 +104,8 @@ inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
 inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool backward) {
     const size_t M = (size_t)B * N;
     w.tiles_per_cloud = idiv_up(N, 128);
-    w.nb_a1 = (int)std::min<size_t>(2048, (M + 63) / 64);
-    w.nb_a2 = (int)std::min<size_t>(2048, (M + 63) / 64);
+    w.nb_a1 = (int)std::min<size_t>(8192, (M + 15) / 16);
+    w.nb_a2 = (int)std::min<size_t>(8192, (M + 15) / 16);
     w.nb_l2 = (int)((M + 127) / 128);
     w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
     w.nb_dw2 = (int)((M + DW2_CHUNK - 1) / DW2_CHUNK);
@@ -229,6 +229,7 @@ __global__ void k_a1(const float* __restrict__ x, const float* __restrict__ tran
     const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
     const float sc = st.scale[k], sh_ = st.shift[k];
     float acc = 0.f;
+#pragma unroll 4
     for (size_t P = (size_t)blockIdx.x * 4 + q; P < M; P += (size_t)gridDim.x * 4) {
         const int b = (int)(P / N), n = (int)(P % N);
         const float* xb = x + (size_t)b * 3 * N;
@@ -257,14 +258,16 @@ __global__ void k_a2_sum(const float* __restrict__ Y2, size_t M, BnState st, dou
     __shared__ double sh[256];
     const int tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
     const float sc = st.scale[k], sf = st.shift[k];
-    double acc = 0.0;
-    float facc = 0.f;
-    int cnt = 0;
-    for (size_t P = (size_t)blockIdx.x * 2 + q; P < M; P += (size_t)gridDim.x * 2) {
-        facc += fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
-        if (++cnt == 32) { acc += (double)facc; facc = 0.f; cnt = 0; }
+    // four independent partial sums so that the loads of consecutive iterations overlap
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+    const size_t stride = (size_t)gridDim.x * 2;
+    size_t P = (size_t)blockIdx.x * 2 + q;
+    for (; P + 3 * stride < M; P += 4 * stride) {
+        const float y0 = Y2[P * C2 + k], y1 = Y2[(P + stride) * C2 + k], y2 = Y2[(P + 2 * stride) * C2 + k], y3 = Y2[(P + 3 * stride) * C2 + k];
+        f0 += fmaxf(sc * y0 + sf, 0.f); f1 += fmaxf(sc * y1 + sf, 0.f); f2 += fmaxf(sc * y2 + sf, 0.f); f3 += fmaxf(sc * y3 + sf, 0.f);
     }
-    acc += (double)facc;
+    for (; P < M; P += stride) f0 += fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
+    const double acc = ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
     sh[tid] = acc;
     __syncthreads();
     if (tid < 128) part[(size_t)blockIdx.x * C2 + tid] = sh[tid] + sh[tid + 128];
@@ -750,68 +753,54 @@ struct ProbDA1 {
     }
 };
 
-// layer 1 backward: dW1 partial per cloud and d trans per cloud.  block = 256 = 64 channels x 4 slots.
+// layer 1 backward: dW1 partial per cloud and d trans per cloud.  block = 256 = 64 channels x 4 point slots.
+// Everything reduces to the per-cloud 64 x 3 matrix  G[k][j] = sum_n dy1[k][n] x_j[n]  (raw coordinates):
+//   dW1_b[k][i] = sum_n dy1 x'_i = sum_j T[j][i] G[k][j]        (x' = T^T x)
+//   dT_b[j][i]  = sum_n x_j dx'_i = sum_k W1[k][i] G[k][j]      (dx' = W1^T dy1)
+// and the pre-activation needed for yhat1 is u1 = sum_j (W1 T^T)[k][j] x_j.  No per-point cross-thread traffic.
 __global__ void k_l1_bwd(const float* __restrict__ x, const float* __restrict__ trans, int N,
                          const float* __restrict__ W1, BnState st1, const float* __restrict__ DZ1,
                          const float* __restrict__ m1, const float* __restrict__ m2,
                          float* __restrict__ dW1part, float* __restrict__ dtrans) {
-    __shared__ float shw[256 * 3];
-    __shared__ float sht[8 * 9];
-    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6, lane = tid & 31;
+    __shared__ float shg[256 * 3];
+    __shared__ float G[64 * 3];
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
     const float* xb = x + (size_t)b * 3 * N;
     float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (trans)
         for (int e = 0; e < 9; ++e) T[e] = trans[(size_t)b * 9 + e];
     const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
+    // (W1 T^T)[k][j] = sum_i W1[k][i] T[j][i]
+    const float v0 = w0 * T[0] + w1 * T[1] + w2 * T[2];
+    const float v1 = w0 * T[3] + w1 * T[4] + w2 * T[5];
+    const float v2 = w0 * T[6] + w1 * T[7] + w2 * T[8];
     const float mu = st1.mean[k], r = st1.rstd[k], sc = st1.scale[k], mm1 = m1[k], mm2 = m2[k];
-    float aw0 = 0.f, aw1 = 0.f, aw2 = 0.f;
-    float dT[9];
-    for (int e = 0; e < 9; ++e) dT[e] = 0.f;
-    const int iters = (N + 3) / 4;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    const float* dz = DZ1 + (size_t)b * N * C1 + k;
 #pragma unroll 4
-    for (int it = 0; it < iters; ++it) {
-        const int n = it * 4 + q;
-        const bool ok = n < N;
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, dy = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
-        if (ok) {
-            p0 = xb[n]; p1 = xb[N + n]; p2 = xb[2 * N + n];
-            t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
-            t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
-            t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
-            const float u = w0 * t0 + w1 * t1 + w2 * t2;
-            const float yhat = (u - mu) * r;
-            dy = sc * (DZ1[((size_t)b * N + n) * C1 + k] - mm1 - yhat * mm2);
-            aw0 = fmaf(dy, t0, aw0); aw1 = fmaf(dy, t1, aw1); aw2 = fmaf(dy, t2, aw2);
-        }
-        if (dtrans) {
-            // d x'_i = sum_k W1[k][i] dy1[k]  (warp-level partial over 32 channels)
-            float d0 = w0 * dy, d1 = w1 * dy, d2 = w2 * dy;
-            for (int o = 16; o > 0; o >>= 1) {
-                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-            }
-            if (lane == 0 && ok) {
-                // dT[j][i] += x_j * dx'_i
-                dT[0] += p0 * d0; dT[1] += p0 * d1; dT[2] += p0 * d2;
-                dT[3] += p1 * d0; dT[4] += p1 * d1; dT[5] += p1 * d2;
-                dT[6] += p2 * d0; dT[7] += p2 * d1; dT[8] += p2 * d2;
-            }
-        }
+    for (int n = q; n < N; n += 4) {
+        const float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
+        const float u = v0 * p0 + v1 * p1 + v2 * p2;
+        const float yhat = (u - mu) * r;
+        const float dy = sc * (dz[(size_t)n * C1] - mm1 - yhat * mm2);
+        g0 = fmaf(dy, p0, g0); g1 = fmaf(dy, p1, g1); g2 = fmaf(dy, p2, g2);
     }
-    shw[tid * 3 + 0] = aw0; shw[tid * 3 + 1] = aw1; shw[tid * 3 + 2] = aw2;
-    if (lane == 0)
-        for (int e = 0; e < 9; ++e) sht[(tid >> 5) * 9 + e] = dT[e];
+    shg[tid * 3 + 0] = g0; shg[tid * 3 + 1] = g1; shg[tid * 3 + 2] = g2;
+    __syncthreads();
+    if (tid < 192) {
+        const int kk = tid / 3, j = tid % 3;
+        G[tid] = ((shg[(0 * 64 + kk) * 3 + j] + shg[(1 * 64 + kk) * 3 + j]) + shg[(2 * 64 + kk) * 3 + j]) + shg[(3 * 64 + kk) * 3 + j];
+    }
     __syncthreads();
     if (tid < 192) {
         const int kk = tid / 3, i = tid % 3;
-        float s = 0.f;
-        for (int qq = 0; qq < 4; ++qq) s += shw[(qq * 64 + kk) * 3 + i];
-        dW1part[(size_t)b * (C1 * 3) + tid] = s;
+        // dW1_b[kk][i] = sum_j T[j][i] G[kk][j]
+        dW1part[(size_t)b * (C1 * 3) + tid] = T[i] * G[kk * 3 + 0] + T[3 + i] * G[kk * 3 + 1] + T[6 + i] * G[kk * 3 + 2];
     }
     if (dtrans && tid < 9) {
+        const int j = tid / 3, i = tid % 3;
         float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += sht[w * 9 + tid];
+        for (int kk = 0; kk < C1; ++kk) s = fmaf(W1[kk * 3 + i], G[kk * 3 + j], s);
         dtrans[(size_t)b * 9 + tid] = s;
     }
 }
