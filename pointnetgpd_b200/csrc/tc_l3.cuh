@@ -314,6 +314,260 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ====================================================================================================================
+// Version 2: CTA PAIRS (thread-block cluster of 2) share the W3 stream.
+//   * every 32 KB weight stage is fetched from L2 only ONCE per pair: each CTA bulk-copies one 16 KB half with
+//     .multicast::cluster into both CTAs' shared memory -> half the L2 traffic per SM, which is what allows
+//   * 128-point tiles with a DOUBLE-BUFFERED a2 operand (2 x 64 KB): staging the next tile overlaps the MMAs of the
+//     current one (in version 1 the 256-point tile is single-buffered and the tensor pipe idles while it is staged),
+//   * four 128-column TMEM accumulators (512 columns) decouple the MMA issuer from the epilogue.
+// The two CTAs of a pair walk disjoint tiles but consume the weight ring in lock step (a stage is refilled only when
+// BOTH have released it: the MMA issuer's tcgen05.commit is multicast to both CTAs' "empty" barriers).
+// ====================================================================================================================
+constexpr int L3B_NT = 128;
+constexpr int L3B_A2_PART = L3B_NT * 128;          // 16 KB: one (part, k-block) sub-tile
+constexpr int L3B_A2_BUF = 4 * L3B_A2_PART;        // 64 KB: hi/lo x 2 k-blocks
+constexpr int L3B_SMEM_W = 2 * L3B_A2_BUF;         // 128 KB
+constexpr int L3B_SMEM_MISC = L3B_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
+constexpr int L3B_SMEM_BYTES = L3B_SMEM_MISC + 2048 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc2(L3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* misc = smem + L3B_SMEM_MISC;
+    const uint32_t bar0 = sbase + L3B_SMEM_MISC;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // 0..2 w_full, 3..5 w_empty, 6..7 a2_full, 8..9 a2_empty, 10..13 tmem_full, 14..17 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 192);
+    float* s_scale = reinterpret_cast<float*>(misc + 256);
+    float* s_shift = s_scale + 128;
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 2); }
+        mbar_init(BAR(6), 256); mbar_init(BAR(7), 256);
+        mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(BAR(10 + i), 1); mbar_init(BAR(14 + i), 128); }
+        mbar_fence_init();
+    }
+    if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
+    if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's barriers exist before anything is multicast to them
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    // tiles of this PAIR, interleaved between its two CTAs; both run the same number of iterations
+    const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    const int T0 = (int)(((long long)p.ntiles * pair) / npairs), T1 = (int)(((long long)p.ntiles * (pair + 1)) / npairs);
+    const int niter = (T1 - T0 + 1) >> 1;
+    const int cta = (int)blockIdx.x;
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    if (warp == 0) {
+        // ===================== W3 producer: my 16 KB half of every stage, multicast to both CTAs =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it)
+                for (int blk = 0; blk < 16; ++blk) {
+                    mbar_wait(BAR(3 + stage), phase ^ 1);                       // released by BOTH CTAs
+                    mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);          // 16 KB from me + 16 KB from the peer
+                    bulk_g2s_multicast(sbase + L3B_SMEM_W + stage * L3_STAGE_BYTES + rank * 16384,
+                                       reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES + rank * 16384,
+                                       16384, BAR(stage), (uint16_t)0x3);
+                    if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_f16(128, L3B_NT);
+            int stage = 0; uint32_t wphase = 0;
+            int acc = 0; uint32_t aphase = 0;
+            int buf = 0; uint32_t bphase = 0;
+            const long long tl0 = p.dbg ? clock64() : 0;
+            for (int it = 0; it < niter; ++it) {
+                { L3_T0(); mbar_wait(BAR(6 + buf), bphase); L3_ACC(0); }
+                tc_fence_after_sync();
+                const uint32_t a2b = sbase + buf * L3B_A2_BUF;
+                for (int mt = 0; mt < 8; ++mt) {
+                    { L3_T0(); mbar_wait(BAR(14 + acc), aphase ^ 1); L3_ACC(1); }
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem + (uint32_t)(acc * L3B_NT);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        { L3_T0(); mbar_wait(BAR(stage), wphase); L3_ACC(2); }
+                        tc_fence_after_sync();
+                        const uint32_t w_hi = sbase + L3B_SMEM_W + stage * L3_STAGE_BYTES, w_lo = w_hi + 16384;
+                        const uint32_t b_hi = a2b + (0 * 2 + kb) * L3B_A2_PART, b_lo = a2b + (1 * 2 + kb) * L3B_A2_PART;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t wa = (pass == 1) ? w_lo : w_hi;
+                            const uint32_t bb = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(bb + k * 32), IDESC,
+                                        (kb | pass | k) ? 1u : 0u);
+                        }
+                        mma_commit_multicast(BAR(3 + stage), (uint16_t)0x3);    // stage released in BOTH CTAs' books
+                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1; }
+                    }
+                    mma_commit(BAR(10 + acc));
+                    if (++acc == 4) { acc = 0; aphase ^= 1; }
+                }
+                mma_commit(BAR(8 + buf));                                        // a2 buffer free
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+            if (p.dbg) {
+                dbg_acc[3] = clock64() - tl0;
+                for (int i = 0; i < 4; ++i) p.dbg[(size_t)cta * 8 + i] = dbg_acc[i];
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool stats = p.mu_s != nullptr;
+        int acc = 0; uint32_t aphase = 0;
+        for (int it = 0; it < niter; ++it) {
+            const int t = T0 + 2 * it + (int)rank;
+            const bool live = t < T1;
+            const int b = live ? t / p.tiles_per_cloud : 0, tt = live ? t % p.tiles_per_cloud : 0;
+            const int n0 = tt * L3B_NT;
+            const int nvalid = live ? ((p.N - n0 < L3B_NT) ? p.N - n0 : L3B_NT) : 0;
+            for (int mt = 0; mt < 8; ++mt) {
+                const int ch = mt * 128 + row;
+                const float mu = stats ? p.mu_s[ch] : 0.f;
+                { L3_T0(); mbar_wait(BAR(10 + acc), aphase); L3_ACC(6); }
+                tc_fence_after_sync();
+                const long long te0 = p.dbg ? clock64() : 0;
+                float best = -INFINITY; int bidx = 0; float css = 0.f;
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3B_NT);
+                for (int c0 = 0; c0 < L3B_NT; c0 += 32) {
+                    if (c0 >= nvalid) break;
+                    float v[32];
+                    tmem_ld32(tbase + (uint32_t)c0, v);
+                    if (c0 + 32 <= nvalid) {
+                        float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+                        for (int j = 4; j < 32; j += 4) {
+                            m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+                        }
+                        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        if (stats) {
+                            float c0s = 0.f, c1s = 0.f, c2s = 0.f, c3s = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float d0 = v[j] - mu, d1 = v[j + 1] - mu, d2 = v[j + 2] - mu, d3 = v[j + 3] - mu;
+                                c0s = fmaf(d0, d0, c0s); c1s = fmaf(d1, d1, c1s); c2s = fmaf(d2, d2, c2s); c3s = fmaf(d3, d3, c3s);
+                            }
+                            css += (c0s + c1s) + (c2s + c3s);
+                        }
+                        if (m > best) {
+                            best = m;
+                            int jj = 31;
+#pragma unroll
+                            for (int j = 30; j >= 0; --j) if (v[j] == m) jj = j;
+                            bidx = n0 + c0 + jj;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j < nvalid) {
+                                if (stats) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
+                                if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                mbar_arrive(BAR(14 + acc));
+                if (p.dbg) dbg_acc[7] += clock64() - te0;
+                if (++acc == 4) { acc = 0; aphase ^= 1; }
+                if (live) {
+                    const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
+                                                   (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
+                    atomicMax(&p.keys[(size_t)b * C3 + ch], key);
+                    if (stats) {
+                        const float iv = p.inv[ch];
+                        p.css_part[(size_t)t * C3 + ch] = css * iv * iv;
+                    }
+                }
+            }
+        }
+        if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
+    } else {
+        // ===================== a2 producer (8 warps, double-buffered 128-point tiles) =====================
+        const int wp = warp - 6;
+        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
+        const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
+        const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
+        int buf = 0; uint32_t bphase = 0;
+        for (int it = 0; it < niter; ++it) {
+            const int t = T0 + 2 * it + (int)rank;
+            const bool live = t < T1;
+            const int b = live ? t / p.tiles_per_cloud : 0, tt = live ? t % p.tiles_per_cloud : 0;
+            const int n0 = tt * L3B_NT;
+            const int nvalid = live ? ((p.N - n0 < L3B_NT) ? p.N - n0 : L3B_NT) : 0;
+            const float* src = p.Y2 + ((size_t)b * p.N + n0) * C2 + 4 * lane;
+            if (wp == 0 && lane == 0) {
+                const int t2 = t + 4;                           // two iterations ahead
+                if (t2 < T1) {
+                    const int b2 = t2 / p.tiles_per_cloud, tt2 = t2 % p.tiles_per_cloud;
+                    const int nv2 = (p.N - tt2 * L3B_NT < L3B_NT) ? p.N - tt2 * L3B_NT : L3B_NT;
+                    l2_prefetch(p.Y2 + ((size_t)b2 * p.N + (size_t)tt2 * L3B_NT) * C2, (uint32_t)nv2 * C2 * 4u);
+                }
+            }
+            { L3_T0(); mbar_wait(BAR(8 + buf), bphase ^ 1); L3_ACC(4); }
+            const long long tp0 = p.dbg ? clock64() : 0;
+            unsigned char* a2b = smem + buf * L3B_A2_BUF;
+            if (live) {
+                constexpr int U = 8;
+                for (int i0 = 0; i0 < L3B_NT / 8; i0 += U) {
+                    float4 y[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = wp + 8 * (i0 + u);
+                        y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = wp + 8 * (i0 + u);
+                        const bool ok = r < nvalid;
+                        float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
+                        float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
+                        float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
+                        float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
+                        __half2 h01, l01, h23, l23;
+                        split2(a0, a1, h01, l01);
+                        split2(a2, a3, h23, l23);
+                        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                        *reinterpret_cast<uint2*>(a2b + (0 * 2 + kb) * L3B_A2_PART + off) = hv;
+                        *reinterpret_cast<uint2*>(a2b + (1 * 2 + kb) * L3B_A2_PART + off) = lv;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(BAR(6 + buf));
+            if (p.dbg) dbg_acc[5] += clock64() - tp0;
+            if (++buf == 2) { buf = 0; bphase ^= 1; }
+        }
+        if (p.dbg && wp == 0 && lane == 0) { p.dbg[(size_t)cta * 8 + 4] = dbg_acc[4]; p.dbg[(size_t)cta * 8 + 5] = dbg_acc[5]; }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                 // nobody exits while the peer may still multicast into / arrive on this CTA
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 // per-device one-time setup: is this an sm_100 part, and can the kernel have its shared memory?
 struct DevInfo { int state = 0; int sms = 148; };   // state: 0 unknown, 1 usable, -1 not usable
 inline DevInfo& dev_info() {
@@ -328,6 +582,7 @@ inline DevInfo& dev_info() {
         if (d.sms <= 0) d.sms = 148;
         if (d.sms > 256) d.sms = 256;      // per-CTA partial buffers are sized for <= 256 CTAs (plan_tower_scratch)
         cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, L3B_SMEM_BYTES);
         d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
         if (e != cudaSuccess) cudaGetLastError();
     }

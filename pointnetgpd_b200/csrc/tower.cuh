@@ -875,16 +875,26 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     int n_css = 0;
 #ifndef PGPD_EMU
     if (a.use_tc && (tc_mask() & 1)) {
-        const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
+        // layer-3 kernel version: 1 (default) = single-CTA 256-point tiles; 2 = CTA pairs sharing the weight stream
+        // (PGPD_L3_VERSION=2; correct but currently slower: its 768-cycle stages out-run the 3-deep weight ring)
+        static const int l3ver = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 1;
+        const int tile_pts = l3ver == 2 ? tc::L3B_NT : tc::L3_NT;
+        const int tpc = idiv_up(a.N, tile_pts), ntiles = a.B * tpc;
         launch(tc::k_prepack_w3, dim3(C3), dim3(128), 0, s, t.conv[2].w, t.bn[2].gamma,
                a.train ? (const float*)w.bn[2].mean : (const float*)nullptr, (__half*)w.wimg, w.sgn, w.mu_s);
-        // PGPD_L3_DEBUG=1: the kernel writes per-CTA pipeline cycle counters to the start of the rtmp scratch
+        // PGPD_L3_DEBUG=1: the kernel writes per-CTA pipeline cycle counters to a debug buffer
         static const bool l3dbg = getenv("PGPD_L3_DEBUG") != nullptr;
         tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
                        w.keys, w.fpart, a.B, a.N, tpc, ntiles, l3dbg ? tc::l3_debug_buffer() : nullptr};
-        const int grid = ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms;
+        const int sms = tc::dev_info().sms;
         profiler().begin(s);
-        launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
+        if (l3ver == 2) {
+            const int pairs = (ntiles + 1) / 2 < sms / 2 ? (ntiles + 1) / 2 : sms / 2;
+            launch(tc::k_l3_fwd_tc2, dim3(2 * pairs), dim3(tc::L3_THREADS), (size_t)tc::L3B_SMEM_BYTES, s, p);
+        } else {
+            const int grid = ntiles < sms ? ntiles : sms;
+            launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
+        }
         profiler().end(s);
         n_css = ntiles;
     } else
