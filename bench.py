@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--points", type=int, default=1024)
     ap.add_argument("--classes", type=int, default=2)
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core kernels")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=128)
     args = ap.parse_args()
@@ -152,7 +153,7 @@ def main():
     B, N, k = args.batch, args.points, args.classes
     workload = "PointNetCls k=%d train step (fwd+nll+bwd+allreduce+Adam), B=%d clouds/GPU x N=%d pts" % (k, B, N)
     config = {"workload": workload, "global_batch": B * world, "points": N, "classes": k,
-              "parallelism": "dp%d" % world, "l2": "per-step working set ~1.2 GB of saved activations >> 126 MB L2; 8 rotating input batches"}
+              "parallelism": "dp%d" % world, "cuda_graph": None, "l2": "per-step working set ~1.2 GB of saved activations >> 126 MB L2; 8 rotating input batches"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -193,7 +194,7 @@ def main():
     model = PointNetCls(num_points=N, input_chann=3, k=k)
     model.load_state_dict({kk: torch.tensor(v) for kk, v in st.items()})
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True, capturable=True)
     sync = FlatGradAllReduce(list(model.parameters()), world)
     flags_extra = A.F_SIMT if args.simt else 0
     if flags_extra:
@@ -208,19 +209,35 @@ def main():
     xs_dev = [t.to(dev) for t in xs_host]
     ys_dev = [t.to(dev) for t in ys_host]
 
-    def step(x, y):
+    def eager_step(x, y):
         opt.zero_grad(set_to_none=True)
         logp, _ = fwd(x)
         loss = F.nll_loss(logp, y)
         loss.backward()
         sync.all_reduce()
         opt.step()
-        return loss
+        return loss.detach()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    # The step is captured once into a CUDA graph and replayed (pointnetgpd_b200.graph.GraphedTrainStep); the dominant
+    # kernel's event pair is recorded INSIDE the graph (external event nodes), so its duration is still measured live.
+    use_graph = not args.no_graph and not args.simt
+    graphed = None
+    lib.pgpd_profile_enable(0)
+    if use_graph:
+        try:
+            from pointnetgpd_b200.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(model, opt, xs_dev[0], ys_dev[0], grad_sync=sync if world > 1 else None, warmup=3,
+                                       before_capture=lambda: lib.pgpd_profile_enable(2))
+        except Exception as e:           # e.g. a collective that cannot be captured: fall back to eager launches
+            sys.stderr.write("CUDA-graph capture failed (%s: %s); running eagerly\n" % (type(e).__name__, e))
+            graphed = None
+            lib.pgpd_profile_enable(0)
+    step = graphed.step if graphed is not None else eager_step
 
     for i in range(args.warmup):
         step(xs_dev[i % NBUF], ys_dev[i % NBUF])
@@ -231,7 +248,8 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    lib.pgpd_profile_enable(1)
+    if graphed is None:
+        lib.pgpd_profile_enable(1)
     n0 = lib.pgpd_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -244,17 +262,26 @@ def main():
     launches = int(lib.pgpd_launch_count() - n0)
     import ctypes
     nl, tot = ctypes.c_int(0), ctypes.c_float(0.0)
-    lib.pgpd_profile_read(ctypes.byref(nl), ctypes.byref(tot))
+    lib.pgpd_profile_read(ctypes.byref(nl), ctypes.byref(tot))      # graph mode: the event nodes of the LAST replayed step
     lib.pgpd_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
+    if graphed is not None:
+        # replays launch the captured kernels without passing through the library's host code: count them from one eager step
+        n1 = lib.pgpd_launch_count()
+        eager_step(xs_dev[0], ys_dev[0])
+        torch.cuda.synchronize(dev)
+        launches = int(lib.pgpd_launch_count() - n1) * args.steps
 
     # ---- end-to-end region: pinned host inputs -> H2D -> step -> D2H of the loss ------------------
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        x = xs_host[i % NBUF].to(dev, non_blocking=True)
-        y = ys_host[i % NBUF].to(dev, non_blocking=True)
-        loss = step(x, y)
+        if graphed is not None:
+            loss = graphed.step(xs_host[i % NBUF], ys_host[i % NBUF])      # pinned host -> static device buffers -> replay
+        else:
+            x = xs_host[i % NBUF].to(dev, non_blocking=True)
+            y = ys_host[i % NBUF].to(dev, non_blocking=True)
+            loss = eager_step(x, y)
         _ = loss.item()                     # D2H read of the step's result
     barrier()
     e2e_ms_total = (time.perf_counter() - t0) * 1e3
@@ -267,6 +294,7 @@ def main():
     value = B * world / (ms_per_step / 1e3)
     e2e_value = B * world / (e2e_ms_total / args.steps / 1e3)
 
+    config["cuda_graph"] = graphed is not None
     if rank == 0:
         peaks, peak_src = load_peaks()
         M = B * N
@@ -279,7 +307,9 @@ def main():
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "kernel_ms": k3_ms, "launches_timed": nl.value, "traffic": None,
                     "impl": "tcgen05" if (lib.pgpd_has_tensor_core_path() and not args.simt) else "cuda-core fp32",
-                    "step_algorithmic_tflops": 3.0 * fwd_flops_per_grasp(N, k) * B / (ms_per_step * 1e-3) / 1e12}
+                    "step_algorithmic_tflops": 3.0 * fwd_flops_per_grasp(N, k) * B / (ms_per_step * 1e-3) / 1e12,
+                    "timing": ("event pairs recorded as nodes of the replayed CUDA graph (last timed step)" if graphed is not None
+                               else "event pairs around every launch in the timed region")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,

@@ -115,8 +115,10 @@ unsigned long long pgpd_launch_count(void);
 /* Optional timing of the dominant kernel (the layer-3 GEMM + max-pool of a tower forward):
  * pgpd_profile_enable(1) makes every following launch of that kernel on the calling thread record
  * a CUDA-event pair on its stream; pgpd_profile_read synchronises those events, returns the number
- * of launches and their summed duration, and resets the accumulator.  Not for use under CUDA-graph
- * capture. */
+ * of launches and their summed duration, and resets the accumulator.
+ * pgpd_profile_enable(2): "sticky" mode for CUDA graphs -- launches made while the stream is being captured record
+ * external event nodes into the graph, every replay re-records them, and pgpd_profile_read (which then does not
+ * reset) returns the durations of the most recent replay. */
 int pgpd_profile_enable(int on);
 int pgpd_profile_read(int* launches, float* total_ms);
 

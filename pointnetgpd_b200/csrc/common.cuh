@@ -180,18 +180,25 @@ __global__ void k_bn_bwd_finalize(const double* tmp, int S, int C, double count,
 // ---- optional CUDA-event timing of the dominant kernel ---------------------------------------------
 struct Profiler {
     bool on = false;
+    bool sticky = false;     // keep the recorded pairs across reads (pairs captured into a CUDA graph are re-recorded by every replay)
 #ifndef PGPD_EMU
     static constexpr int MAXP = 8192;
     cudaEvent_t* ev = nullptr;
     int n = 0;
+    static void record(cudaEvent_t e, cudaStream_t s) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &st);
+        if (st == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);   // becomes a graph node
+        else cudaEventRecord(e, s);
+    }
     void begin(cudaStream_t s) {
         if (!on || n >= MAXP) return;
         if (!ev) { ev = new cudaEvent_t[2 * MAXP]; for (int i = 0; i < 2 * MAXP; ++i) cudaEventCreate(&ev[i]); }
-        cudaEventRecord(ev[2 * n], s);
+        record(ev[2 * n], s);
     }
     void end(cudaStream_t s) {
         if (!on || n >= MAXP || !ev) return;
-        cudaEventRecord(ev[2 * n + 1], s);
+        record(ev[2 * n + 1], s);
         ++n;
     }
     int read(int* launches, float* total_ms) {
@@ -202,13 +209,16 @@ struct Profiler {
             if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) != cudaSuccess) return -1;
             tot += ms;
         }
-        *launches = n; *total_ms = tot; n = 0;
+        *launches = n; *total_ms = tot;
+        if (!sticky) n = 0;
         return 0;
     }
+    void reset() { n = 0; }
 #else
     void begin(cudaStream_t) {}
     void end(cudaStream_t) {}
     int read(int* launches, float* total_ms) { *launches = 0; *total_ms = 0.f; return 0; }
+    void reset() {}
 #endif
 };
 inline Profiler& profiler() { static thread_local Profiler p; return p; }

@@ -114,7 +114,13 @@ int pgpd_has_tensor_core_path(void) {
 
 unsigned long long pgpd_launch_count(void) { return launch_counter(); }
 
-int pgpd_profile_enable(int on) { profiler().on = on != 0; return PGPD_OK; }
+int pgpd_profile_enable(int on) {
+    Profiler& pr = profiler();
+    pr.reset();
+    pr.on = on != 0;
+    pr.sticky = on == 2;
+    return PGPD_OK;
+}
 
 int pgpd_profile_read(int* launches, float* total_ms) {
     if (!launches || !total_ms) return fail(PGPD_E_ARG, "null pointer");
