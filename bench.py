@@ -321,9 +321,18 @@ def main():
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": "oracle torch port on the host CPU: %d timed fwd+nll+bwd+Adam steps on a %d-cloud x %d-point "
                                               "batch (1 warm-up)" % (r["steps_done"], args.cpu_sample_batch, N)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the line is out; never let communicator teardown hang the job
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        try:
+            del graphed
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            sys.stdout.flush()
+            os._exit(0)
     return 0
 
 

@@ -10,8 +10,9 @@ import torch.distributed as dist
 
 
 class FlatGradAllReduce:
-    """Keeps one persistent flat fp32 buffer; after backward, packs all gradients into it, all-reduces
-    it once, and leaves every `p.grad` as a view into the averaged buffer."""
+    """Keeps one persistent flat fp32 buffer; after backward, packs all gradients into it, all-reduces it once and
+    writes the averages back IN PLACE into the existing `p.grad` tensors (their addresses stay fixed, which is what a
+    CUDA-graph captured optimizer step needs)."""
 
     def __init__(self, params, world_size=None, group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -40,8 +41,10 @@ class FlatGradAllReduce:
         torch._foreach_copy_(self.views, grads)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.mul_(1.0 / self.world)
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+        for p, g in zip(self.params, grads):
+            if p.grad is None:
+                p.grad = g
+        torch._foreach_copy_(grads, self.views)
 
     @property
     def bytes_per_step(self):

@@ -11,40 +11,58 @@ import torch.nn.functional as F
 
 
 class GraphedTrainStep:
+    """Single GPU: one graph (zero_grad, forward, loss, backward, optimizer).
+    With a gradient all-reduce (`grad_sync`): two graphs -- (forward, loss, backward) and (optimizer) -- with the NCCL
+    all-reduce launched eagerly in between, so no collective is ever captured."""
+
     def __init__(self, model, optimizer, x_example, y_example, grad_sync=None, warmup=3, loss_fn=F.nll_loss,
                  before_capture=None):
         self.model, self.opt, self.sync, self.loss_fn = model, optimizer, grad_sync, loss_fn
-        self.sx = torch.empty_like(x_example, device=x_example.device if x_example.is_cuda else next(model.parameters()).device)
-        self.sy = torch.empty_like(y_example, device=self.sx.device)
+        dev = x_example.device if x_example.is_cuda else next(model.parameters()).device
+        self.sx = torch.empty_like(x_example, device=dev)
+        self.sy = torch.empty_like(y_example, device=dev)
         self.sx.copy_(x_example)
         self.sy.copy_(y_example)
-        side = torch.cuda.Stream(device=self.sx.device)
-        side.wait_stream(torch.cuda.current_stream(self.sx.device))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._eager()
-        torch.cuda.current_stream(self.sx.device).wait_stream(side)
-        torch.cuda.synchronize(self.sx.device)
+                self._fwd_bwd()
+                if self.sync is not None:
+                    self.sync.all_reduce()
+                self.opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
         if before_capture is not None:
             before_capture()
-        self.graph = torch.cuda.CUDAGraph()
+        self.g_main = torch.cuda.CUDAGraph()
+        self.g_opt = None
+        # gradients keep the tensors of the last warm-up step: capture re-creates them inside the graph's pool
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.loss = self._eager()
+        if self.sync is None:
+            with torch.cuda.graph(self.g_main):
+                self.loss = self._fwd_bwd()
+                self.opt.step()
+        else:
+            with torch.cuda.graph(self.g_main):
+                self.loss = self._fwd_bwd()
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_main.pool()):
+                self.opt.step()
 
-    def _eager(self):
+    def _fwd_bwd(self):
         self.opt.zero_grad(set_to_none=True)
         logp, _ = self.model(self.sx)
         loss = self.loss_fn(logp, self.sy)
         loss.backward()
-        if self.sync is not None:
-            self.sync.all_reduce()
-        self.opt.step()
         return loss.detach()
 
     def step(self, x, y):
         """x, y: device tensors or pinned host tensors of the captured shapes.  Returns the (static) loss tensor."""
         self.sx.copy_(x, non_blocking=True)
         self.sy.copy_(y, non_blocking=True)
-        self.graph.replay()
+        self.g_main.replay()
+        if self.g_opt is not None:
+            self.sync.all_reduce()          # eager NCCL all-reduce, in place on the graph's static gradient tensors
+            self.g_opt.replay()
         return self.loss

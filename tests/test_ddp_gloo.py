@@ -35,6 +35,7 @@ def _worker(rank, world, port, q):
         x = torch.randn(6, 7)          # different data per rank (seeded by rank)
         net(x).square().sum().backward()
         local = [p.grad.clone() for p in net.parameters()]
+        l_ptrs = {id(p): p.grad.data_ptr() for p in net.parameters()}
         sync.all_reduce()
         # expected: mean over ranks of the local gradients
         ok = True
@@ -43,7 +44,7 @@ def _worker(rank, world, port, q):
             dist.all_gather(buf, l)
             exp = sum(buf) / world
             ok = ok and torch.allclose(p.grad, exp, atol=1e-6)
-            ok = ok and p.grad.data_ptr() >= sync.flat.data_ptr()      # grads are views of the flat buffer
+            ok = ok and p.grad.data_ptr() == l_ptrs[id(p)]              # averaged in place: gradient tensors keep their storage
         # a second step must work with p.grad reset to None (zero_grad(set_to_none=True))
         for p in net.parameters():
             p.grad = None
