@@ -160,6 +160,27 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
                         const float* dpooled, float* dtrans_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- data preparation in front of the model ------------------------------------
+ * Gripper-box crop of one cloud for G grasps (BaseGraspDataset.collect_pc, PointNetGPD/model/dataset.py:51-76;
+ * kinect2grasp.py:178-235).
+ *   pc      : [P][3] fp32 cloud points (row-major, as the reference's numpy arrays)
+ *   frames  : [G][15] fp64 per grasp: center[3], rotation rows (approach, binormal, minor_normal)[9], half extents
+ *             (x,y,z)[3] -- the quantities dataset.py:16-59 derives from the 12-float grasp row on the host
+ *   counts  : [G] number of points inside each box, or NULL
+ *   offsets : [G] start of each grasp's output segment (exclusive prefix sum of counts); needed with out_*
+ *   out_pts : [sum][3] fp32 local coordinates of the inside points, ascending cloud index; out_idx: their indices
+ * Call once with counts only, prefix-sum on the host, call again with offsets + outputs.  Arithmetic is fp64 like
+ * numpy in the reference, so the selected index sets are identical. */
+int pgpd_crop_box(const float* pc, int P, const double* frames, int G, const int* offsets, int* counts,
+                  float* out_pts, int* out_idx, void* stream);
+
+/* Resample C point sets (concatenated in pts [total][3], delimited by offsets [C+1]) to exactly N points each,
+ * `repeat` independent draws (dataset.py:438-444; kinect2grasp.py:473-478): a uniformly random subset of N distinct
+ * points when the set has >= N points, N uniform draws with replacement otherwise.  Deterministic in `seed`.
+ *   out_x   : [C*repeat][3][N] fp32, channel-major = the model's input layout;  out_idx: [C*repeat][N] or NULL */
+int pgpd_resample(const float* pts, const int* offsets, int C, int N, int repeat, unsigned long long seed,
+                  float* out_x, int* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,43 @@ def run_shipped(PointNetCls):
     print("wrote shipped checkpoint fixtures; box logp[0] =", out["box_logp_f32"][0])
 
 
+def run_collect_pc():
+    """Golden vectors for the gripper-box crop: executes the reference's own BaseGraspDataset.collect_pc
+    (PointNetGPD/model/dataset.py:15-76).  dataset.py cannot be imported here (it needs open3d), so the method's
+    source is pulled out of the file with `ast` and executed as is against a stub `self` -- nothing is copied."""
+    import ast
+    path = os.path.join(REF, "model", "dataset.py")
+    src = open(path).read()
+    fn = None
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == "collect_pc":
+            fn = ast.get_source_segment(src, node)
+            break
+    ns = {"np": np}
+    import textwrap
+    exec(textwrap.dedent(fn), ns)
+    stub = types.SimpleNamespace(min_point_limit=1, projection=False, in_ind=None)
+    P, G, seed = 4000, 9, 77
+    pc = W.uniform(seed, (P, 3), -0.12, 0.12).astype(np.float32)
+    centers = W.uniform(seed + 1, (G, 3), -0.05, 0.05)
+    axes = W.normal(seed + 2, (G, 3))
+    axes[0] = [0, 0, 1.0]
+    width = W.uniform(seed + 3, (G,), 0.05, 0.085)
+    angle = W.uniform(seed + 4, (G,), -1.5, 1.5)
+    grasps = np.concatenate([centers, axes, width[:, None], angle[:, None], np.zeros((G, 4))], axis=1)
+    th = 0.3
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]
+    T[:3, 3] = [0.01, -0.02, 0.005]
+    out = {"pc": pc, "grasps": grasps, "transform": T}
+    for g in range(G):
+        res = ns["collect_pc"](stub, grasps[g], pc, T)
+        out[f"in_ind_{g}"] = np.asarray(stub.in_ind, dtype=np.int64)
+        out[f"pc_t_{g}"] = np.zeros((0, 3)) if res is None else np.asarray(res, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "collect_pc.npz"), **out)
+    print("wrote collect_pc golden:", [len(out[f"in_ind_{g}"]) for g in range(G)])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -158,6 +195,7 @@ def main():
     for case in CASES:
         run_case(PointNetCls, *case)
     run_shipped(PointNetCls)
+    run_collect_pc()
 
 
 if __name__ == "__main__":

@@ -61,7 +61,7 @@ class ModelGrad(C.Structure):
 EXPORTS = ("pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_launch_count",
            "pgpd_profile_enable", "pgpd_profile_read", "pgpd_workspace_bytes",
            "pgpd_forward", "pgpd_backward", "pgpd_tower_workspace_bytes", "pgpd_tower_forward",
-           "pgpd_tower_backward")
+           "pgpd_tower_backward", "pgpd_crop_box", "pgpd_resample")
 
 
 def bind(lib):
@@ -93,6 +93,10 @@ def bind(lib):
     lib.pgpd_tower_backward.restype = C.c_int
     lib.pgpd_tower_backward.argtypes = [C.POINTER(Tower), C.POINTER(TowerGrad), _fp, _fp, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]
+    lib.pgpd_crop_box.restype = C.c_int
+    lib.pgpd_crop_box.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp]
+    lib.pgpd_resample.restype = C.c_int
+    lib.pgpd_resample.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_ulonglong, _fp, _fp, _fp]
     return lib
 
 

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "tower.cuh"
 #include "head.cuh"
+#include "prep.cuh"
 
 #include <string>
 
@@ -284,6 +285,23 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
     TowerArgs a{t, x, trans, B, N, relu_last != 0, true, true, (cudaStream_t)stream, want_tc(flags)};
     run_tower_bwd(a, w, *g, dpooled, dtrans_out, flags);
     return check_cuda("pgpd_tower_backward");
+}
+
+// ---- data preparation in front of the model ---------------------------------------
+int pgpd_crop_box(const float* pc, int P, const double* frames, int G, const int* offsets, int* counts,
+                  float* out_pts, int* out_idx, void* stream) {
+    if (!pc || !frames || P < 0 || G < 1) return fail(PGPD_E_ARG, "bad argument");
+    if (!counts && !(out_pts && out_idx && offsets)) return fail(PGPD_E_ARG, "need counts, or offsets + out_pts + out_idx");
+    if ((out_pts == nullptr) != (out_idx == nullptr)) return fail(PGPD_E_ARG, "out_pts and out_idx go together");
+    launch(k_crop_box, dim3(G), dim3(256), 0, (cudaStream_t)stream, pc, P, frames, offsets, counts, out_pts, out_idx);
+    return check_cuda("pgpd_crop_box");
+}
+
+int pgpd_resample(const float* pts, const int* offsets, int C, int N, int repeat, unsigned long long seed,
+                  float* out_x, int* out_idx, void* stream) {
+    if (!pts || !offsets || !out_x || C < 1 || N < 1 || repeat < 1) return fail(PGPD_E_ARG, "bad argument");
+    launch(k_resample, dim3(C, repeat), dim3(256), 0, (cudaStream_t)stream, pts, offsets, N, seed, out_x, out_idx);
+    return check_cuda("pgpd_resample");
 }
 
 }  // extern "C"

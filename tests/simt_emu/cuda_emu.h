@@ -217,6 +217,19 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int
     return emu::shfl_from(v, src);
 }
 
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned bit = pred ? 1u : 0u;
+    unsigned out = 0;
+    int members = emu::warp_members(emu::S().cur / 32);
+    for (int l = 0; l < members; ++l) {
+        unsigned b = emu::shfl_from(bit, l);
+        out |= (b & 1u) << l;
+    }
+    return out;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }

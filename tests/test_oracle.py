@@ -94,3 +94,16 @@ def test_shipped_checkpoint_known_answer(golden_dir):
     x = W.make_clouds(123, 8, 500, "box").astype(np.float64)
     logp, trans, _, _ = PN.forward(sd64, x, training=False)
     assert np.abs(logp - out["box_logp_f64"]).max() < 1e-8
+
+
+def test_crop_oracle_matches_reference_collect_pc(golden_dir):
+    """oracle/grasp_crop_np.py vs golden vectors produced by executing the reference's own collect_pc."""
+    import os
+    from oracle import grasp_crop_np as OC
+    g = np.load(os.path.join(golden_dir, "collect_pc.npz"))
+    pc, grasps, T = g["pc"], g["grasps"], g["transform"]
+    for i in range(len(grasps)):
+        idx, pts = OC.crop(pc, grasps[i], T)
+        assert np.array_equal(idx, g[f"in_ind_{i}"]), i
+        if len(idx):
+            assert np.abs(pts - g[f"pc_t_{i}"]).max() < 1e-15
