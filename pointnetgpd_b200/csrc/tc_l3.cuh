@@ -35,7 +35,8 @@ constexpr int L3_A2_BYTES = 4 * L3_A2_PART;       // hi/lo x 2 k-blocks = 128 KB
 constexpr int L3_SMEM_W = L3_A2_BYTES;
 constexpr int L3_SMEM_MISC = L3_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3_SMEM_BYTES = L3_SMEM_MISC + 2048 + 1024;   // + slack to align the base to 1024 B
-constexpr int L3_THREADS = 448;                  // 14 warps: W producer, MMA issuer, 4 epilogue, 8 a2 producers
+constexpr int L3_THREADS = 448;                  // v2 kernel: 14 warps: W producer, MMA issuer, 4 epilogue, 8 a2 producers
+constexpr int L3A_THREADS = 576;                 // v1 kernel: 18 warps: W producer, MMA issuer, 8 epilogue, 8 a2 producers
 constexpr float L3_ACT_SCALE = 16.0f;             // 2^4
 constexpr size_t L3_WIMG_BYTES = (size_t)8 * 2 * L3_STAGE_BYTES;   // 512 KB
 
@@ -92,7 +93,7 @@ struct L3Params {
 #define L3_T0() const long long _t0 = p.dbg ? clock64() : 0
 #define L3_ACC(slot) do { if (p.dbg) dbg_acc[slot] += clock64() - _t0; } while (0)
 
-__global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
+__global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles need a 1024-byte aligned base: align by hand, do not rely on the attribute
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
         for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
         mbar_init(BAR(6), 256); mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
-        mbar_init(BAR(10), 128); mbar_init(BAR(11), 128);
+        mbar_init(BAR(10), 256); mbar_init(BAR(11), 256);
         mbar_fence_init();
     }
     if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
@@ -183,9 +184,10 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 for (int i = 0; i < 4; ++i) p.dbg[(size_t)cta * 8 + i] = dbg_acc[i];
             }
         }
-    } else if (warp < 6) {
-        // ===================== epilogue =====================
+    } else if (warp < 10) {
+        // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 128 columns each =====================
         const int q = warp & 3;                             // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                   // which half of the 256 columns
         const int row = q * 32 + lane;
         const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 const long long te0 = p.dbg ? clock64() : 0;
                 float best = -INFINITY; int bidx = 0; float css = 0.f;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
-                for (int c0 = 0; c0 < L3_NT; c0 += 32) {
+                for (int c0 = half * (L3_NT / 2); c0 < (half + 1) * (L3_NT / 2); c0 += 32) {
                     if (c0 >= nvalid) break;                // warp-uniform
                     float v[32];
                     tmem_ld32(tbase + (uint32_t)c0, v);
@@ -248,14 +250,14 @@ __global__ void __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                 atomicMax(&p.keys[(size_t)b * C3 + ch], key);
                 if (stats) {
                     const float iv = p.inv[ch];
-                    p.css_part[(size_t)t * C3 + ch] = css * iv * iv;
+                    p.css_part[((size_t)t * 2 + half) * C3 + ch] = css * iv * iv;     // two partial rows per tile
                 }
             }
         }
         if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
     } else {
         // ===================== a2 producer =====================
-        const int wp = warp - 6;                            // 0..7
+        const int wp = warp - 10;                           // 0..7
         const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];

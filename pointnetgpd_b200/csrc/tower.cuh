@@ -87,6 +87,7 @@ struct TowerScratch {
 
 struct TowerWs : TowerKeep, TowerScratch {};
 
+constexpr int A1_CHUNK = 64;       // points per block of k_a1
 constexpr int GRAM_CHUNK = 1024;   // points per split-K block of the Gram GEMM
 constexpr int DW2_CHUNK = 2048;    // points per split-K block of the dW2 GEMM
 
@@ -104,7 +105,7 @@ inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
 inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool backward) {
     const size_t M = (size_t)B * N;
     w.tiles_per_cloud = idiv_up(N, 128);
-    w.nb_a1 = (int)std::min<size_t>(8192, (M + 15) / 16);
+    w.nb_a1 = B * idiv_up(N, A1_CHUNK);                                       // one partial row per k_a1 block
     w.nb_a2 = (int)std::min<size_t>(8192, (M + 15) / 16);
     w.nb_l2 = (int)((M + 127) / 128);
     w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
@@ -117,7 +118,8 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     constexpr size_t TC_MAX_CTAS = 256;
     size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
     fp = std::max(fp, 2 * TC_MAX_CTAS * 2 * C2);
-    fp = std::max(fp, (size_t)B * w.tiles_per_cloud * C3);                   // css3 partials
+    fp = std::max(fp, (size_t)B * w.tiles_per_cloud * C3);                   // css3 partials (CUDA-core kernel, 128-point tiles)
+    fp = std::max(fp, (size_t)B * 2 * idiv_up(N, 256) * C3);                  // css3 partials (tcgen05 kernel: 2 rows per 256-point tile)
     if (backward) {
         fp = std::max(fp, (size_t)w.nb_gram * C2 * C2);                      // Gram partials
         fp = std::max(fp, (size_t)w.nb_l2 * 2 * C2);                         // BN2 backward partials
@@ -220,36 +222,46 @@ __global__ void k_bn1_finalize(const double* __restrict__ tmp, int S, double cou
 }
 
 // a1 = relu(scale1 * (W1 T^T x) + shift1), stored [M][64]; optional per-block sums of a1 (double).
-// block = 256 threads = 64 channels x 4 point slots.
+// grid = (chunks of 64 points, clouds), block = 256 threads = 64 channels x 4 point slots.  The chunk's transformed
+// coordinates are staged once in shared memory; no integer division, 256-byte coalesced stores.
 __global__ void k_a1(const float* __restrict__ x, const float* __restrict__ trans, int B, int N,
                      const float* __restrict__ W1, BnState st, float* __restrict__ A1, double* __restrict__ part) {
+    __shared__ float xs[3][A1_CHUNK];
     __shared__ double sh[256];
     const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
-    const size_t M = (size_t)B * N;
+    const int b = (int)blockIdx.y, n0 = (int)blockIdx.x * A1_CHUNK;
+    const int nv = (N - n0 < A1_CHUNK) ? N - n0 : A1_CHUNK;
+    if (tid < A1_CHUNK) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        if (tid < nv) {
+            const float* xb = x + (size_t)b * 3 * N + n0 + tid;
+            const float p0 = xb[0], p1 = xb[N], p2 = xb[2 * N];
+            t0 = p0; t1 = p1; t2 = p2;
+            if (trans) {
+                const float* T = trans + (size_t)b * 9;
+                t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+                t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+                t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+            }
+        }
+        xs[0][tid] = t0; xs[1][tid] = t1; xs[2][tid] = t2;
+    }
+    __syncthreads();
     const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
     const float sc = st.scale[k], sh_ = st.shift[k];
+    float* out = A1 + ((size_t)b * N + n0) * C1 + k;
     float acc = 0.f;
 #pragma unroll 4
-    for (size_t P = (size_t)blockIdx.x * 4 + q; P < M; P += (size_t)gridDim.x * 4) {
-        const int b = (int)(P / N), n = (int)(P % N);
-        const float* xb = x + (size_t)b * 3 * N;
-        float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
-        float t0 = p0, t1 = p1, t2 = p2;
-        if (trans) {
-            const float* T = trans + (size_t)b * 9;
-            t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
-            t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
-            t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
-        }
-        float u = w0 * t0 + w1 * t1 + w2 * t2;
-        float a = fmaxf(sc * u + sh_, 0.f);
-        A1[P * C1 + k] = a;
+    for (int p = q; p < nv; p += 4) {
+        const float u = w0 * xs[0][p] + w1 * xs[1][p] + w2 * xs[2][p];
+        const float a = fmaxf(sc * u + sh_, 0.f);
+        out[(size_t)p * C1] = a;
         acc += a;
     }
     if (part) {
         sh[tid] = (double)acc;
         __syncthreads();
-        if (tid < 64) part[(size_t)blockIdx.x * C1 + tid] = sh[tid] + sh[tid + 64] + sh[tid + 128] + sh[tid + 192];
+        if (tid < 64) part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C1 + tid] = sh[tid] + sh[tid + 64] + sh[tid + 128] + sh[tid + 192];
     }
 }
 
@@ -834,7 +846,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         launch(k_bn_eval_affine, grid1d(C2, 128), dim3(128), 0, s, C2, t.conv[1].b, t.bn[1], w.bn[1]);
         launch(k_bn_eval_affine, grid1d(C3, 128), dim3(128), 0, s, C3, t.conv[2].b, t.bn[2], w.bn[2]);
     }
-    launch(k_a1, dim3(w.nb_a1), dim3(256), 0, s, a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1,
+    launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK), a.B), dim3(256), 0, s, a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1,
            a.train ? w.dpart : (double*)nullptr);
 
     // ---- layer 2 ---------------------------------------------------------------------------------
@@ -872,7 +884,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 
     // ---- layer 3 + max-pool ------------------------------------------------------------------------
     cudaMemsetAsync(w.keys, 0, (size_t)a.B * C3 * sizeof(unsigned long long), s);
-    int n_css = 0;
+    int n_css = 0, n_css_mult = 1;
 #ifndef PGPD_EMU
     if (a.use_tc && (tc_mask() & 1)) {
         // layer-3 kernel version: 1 (default) = single-CTA 256-point tiles; 2 = CTA pairs sharing the weight stream
@@ -893,10 +905,11 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
             launch(tc::k_l3_fwd_tc2, dim3(2 * pairs), dim3(tc::L3_THREADS), (size_t)tc::L3B_SMEM_BYTES, s, p);
         } else {
             const int grid = ntiles < sms ? ntiles : sms;
-            launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
+            launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3A_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
         }
         profiler().end(s);
-        n_css = ntiles;
+        n_css_mult = l3ver == 2 ? 1 : 2;
+        n_css = ntiles * n_css_mult;
     } else
 #endif
     {
