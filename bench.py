@@ -301,11 +301,16 @@ def main():
         k3_flops = 2.0 * 128 * 1024 * M                       # layer-3 GEMM of one tower forward, algorithmic
         k3_ms = (tot.value / nl.value) if nl.value else None
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        traffic = None          # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        tpath = os.path.join(ROOT, "profiles", "r1_l3_traffic.json")
+        if os.path.exists(tpath) and (B, N) == (512, 1024) and not args.simt:
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "tower layer-3 GEMM (128->1024) + max-pool epilogue, one launch per tower forward",
                     "achieved": (k3_flops / (k3_ms * 1e-3) / 1e12) if k3_ms else None, "peak": peak, "unit": "TFLOP/s",
                     "frac": ((k3_flops / (k3_ms * 1e-3) / 1e12) / peak) if k3_ms else None,
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
-                    "kernel_ms": k3_ms, "launches_timed": nl.value, "traffic": None,
+                    "kernel_ms": k3_ms, "launches_timed": nl.value, "traffic": traffic,
                     "impl": "tcgen05" if (lib.pgpd_has_tensor_core_path() and not args.simt) else "cuda-core fp32",
                     "step_algorithmic_tflops": 3.0 * fwd_flops_per_grasp(N, k) * B / (ms_per_step * 1e-3) / 1e12,
                     "timing": ("event pairs recorded as nodes of the replayed CUDA graph (last timed step)" if graphed is not None
