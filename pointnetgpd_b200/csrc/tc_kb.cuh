@@ -1,0 +1,409 @@
+// tc_kb.cuh -- tcgen05 version of the fused layer-2 / layer-1 backward pass (math and outputs: l2bwd.cuh).
+//
+// One persistent CTA per SM walks 64-point tiles (never straddling a cloud).  Per tile:
+//   loader     two bulk async copies (UBLKCP) bring the raw fp32 rows of dz2 [64][128] and a1 [64][64] straight
+//              into the operand buffers (48 KB; nothing passes through registers on the way in, so the bytes in
+//              flight per SM are bounded by shared memory, not by the register file);
+//   converters 8 warps read the raw rows, synchronise among themselves, and overwrite them IN PLACE with the
+//              hi/lo fp16 operand tiles (128-byte swizzle), dz2 scaled per channel by a power of two;
+//   MMA        D1[k][P]  = sum_c A1op[k][c] dz[P][c] + sum_k' A2op[k][k'] a1[P][k']      (d a1 without the constant)
+//              D2[c][k] += sum_P dz[P][c] a1[P][k]                                       (C, for dW2; MN-major operands)
+//              D3[m][k] += sum_P [a1_hi ; a1_lo][P][m] a1[P][k]                           (Gram of a1 in two passes)
+//   epilogue   8 warps: d a1 -> ReLU mask (a1 read back from the operand tile) -> BatchNorm1-backward sums and the
+//              per-cloud sums H = sum dz1 x_j; nothing is written per point.
+// Accumulators: D1 double-buffered (2 x 64 TMEM columns), D2 and D3 persistent (64 columns each).
+// Same fp32-grade 3-pass hi/lo scheme as the other tensor-core kernels.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_accum.cuh"
+
+namespace pgpd { namespace tc {
+
+constexpr int KB_NT = 64;                                   // points per tile
+constexpr int KB_THREADS = 576;                             // 18 warps: 8 epilogue + 8 converter (interleaved), loader, MMA issuer
+constexpr int KB_A1_BYTES = 65536;                          // W2^T image  [kb][part][128 rows][128 B]
+constexpr int KB_A2_BYTES = 32768;                          // -K image        [part][128 rows][128 B]
+constexpr int KB_DZ_BYTES = 32768;                          // dz2 tile    [part][kb][64 rows][128 B]  (raw: [64][128] fp32)
+constexpr int KB_A1T_BYTES = 16384;                         // a1 tile         [part][64 rows][128 B]  (raw: [64][64] fp32)
+constexpr int KB_BUF_BYTES = KB_DZ_BYTES + KB_A1T_BYTES;
+constexpr int KB_OFF_A2 = KB_A1_BYTES;
+constexpr int KB_OFF_BUF = KB_A1_BYTES + KB_A2_BYTES;
+constexpr int KB_OFF_X = KB_OFF_BUF + 2 * KB_BUF_BYTES;     // [2][3][64] floats
+constexpr int KB_OFF_MISC = KB_OFF_X + 2 * 3 * KB_NT * 4;
+constexpr int KB_SMEM_BYTES = KB_OFF_MISC + 256 + 1024;
+constexpr int KB_EPI_GROUPS = 4;                            // column groups of 16 points: partial rows per tile / per CTA
+
+// esc[c] = 2^e with max|dz2[.,c]| 2^e in [2^12, 2^13), from the per-row maxima written by the layer-2 backward pass 1.
+// block = 1024 = 128 channels x 8 row lanes
+__global__ void k_kb_scale(const float* __restrict__ pmax, int G, float* __restrict__ esc, float* __restrict__ einv) {
+    __shared__ float sh[8][C2];
+    const int c = (int)threadIdx.x & 127, ry = (int)threadIdx.x >> 7;
+    float mx = 0.f;
+    for (int g = ry; g < G; g += 8) mx = fmaxf(mx, pmax[(size_t)g * 2 * C2 + c]);
+    sh[ry][c] = mx;
+    __syncthreads();
+    if (ry == 0) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sh[q][c]);
+        int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+        e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
+        esc[c] = __uint_as_float((uint32_t)(127 + e) << 23);
+        einv[c] = __uint_as_float((uint32_t)(127 - e) << 23);
+    }
+}
+
+// A-operand images of the pass.  Row k < 64:  A1op[k][c] = W2[c][k] s_c einv_c 2^g_k,  A2op[k][k'] = -K[k][k'] 2^g_k / 16,
+// with 2^g_k bringing the larger of the two row maxima into [2^13, 2^14); rows 64..127 are zero (the MMA M extent is 128).
+// ginv[k] = 2^-g_k.  grid = 128 rows, block = 128.
+__global__ void k_kb_prepack(const float* __restrict__ W2, const float* __restrict__ scale2, const float* __restrict__ einv,
+                             const float* __restrict__ Kmat, __half* __restrict__ img1, __half* __restrict__ img2,
+                             float* __restrict__ ginv) {
+    __shared__ float red[128];
+    const int r = (int)blockIdx.x, c = (int)threadIdx.x;
+    const float w = (r < C1) ? W2[c * C1 + r] * scale2[c] * einv[c] : 0.f;
+    const float kk = (r < C1 && c < C1) ? -Kmat[r * C1 + c] * (1.0f / ACT_SCALE) : 0.f;
+    red[c] = fmaxf(fabsf(w), fabsf(kk));
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if (c < s) red[c] = fmaxf(red[c], red[c + s]);
+        __syncthreads();
+    }
+    const float mx = red[0];
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int e = (mx > 0.f) ? 14 - ex : 0;
+    {
+        const float ws = ldexpf(w, e);
+        const __half hi = __float2half_rn(ws);
+        const __half lo = __float2half_rn(ws - __half2float(hi));
+        const int kb = c >> 6, j = c & 63, chunk = j >> 3, within = j & 7;
+        const size_t base = (size_t)(kb * 2) * 8192;
+        const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
+        img1[base + off] = hi;
+        img1[base + 8192 + off] = lo;
+    }
+    if (c < C1) {
+        const float ks = ldexpf(kk, e);
+        const __half hi = __float2half_rn(ks);
+        const __half lo = __float2half_rn(ks - __half2float(hi));
+        const int chunk = c >> 3, within = c & 7;
+        const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
+        img2[off] = hi;
+        img2[8192 + off] = lo;
+    }
+    if (c == 0) ginv[r] = ldexpf(1.f, -e);
+}
+
+struct KbParams {
+    const __half* A1img; const __half* A2img; const float* ginv;
+    const float* cvec; const float* gamma1; const float* beta1;
+    const float* esc; const float* einv;
+    const float* DZ2; const float* A1; const float* x;
+    int B, N, tiles_per_cloud, ntiles;
+    float* Cpart;     // [gridDim.x][128*64]
+    float* G1part;    // [gridDim.x][64*64]
+    float* bnpart;    // [gridDim.x * 4][2][64]
+    float* Hpart;     // [ntiles * 4][64*3]
+};
+
+__global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* misc = smem + KB_OFF_MISC;
+    const uint32_t bar0 = sbase + KB_OFF_MISC;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // 0 a_full | 1,2 full (bulk copies landed) | 3,4 op_ready (converted) | 5,6 acc_full (D1 complete)
+    // 7,8 buf_empty (all MMAs reading the buffer complete + epilogue done with it) | 9 final (every MMA complete)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+    float* sx = reinterpret_cast<float*>(smem + KB_OFF_X);           // [2][3][64]
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(BAR(0), 1);
+        mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
+        mbar_init(BAR(3), 256); mbar_init(BAR(4), 256);
+        mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
+        mbar_init(BAR(7), 257); mbar_init(BAR(8), 257);
+        mbar_init(BAR(9), 1);
+        mbar_fence_init();
+    }
+    if (warp == 17) tmem_alloc<256>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+
+    if (warp == 16) {
+        // ===================== loader =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(BAR(0), KB_A1_BYTES + KB_A2_BYTES);
+            bulk_g2s(sbase, p.A1img, KB_A1_BYTES, BAR(0));
+            bulk_g2s(sbase + KB_OFF_A2, p.A2img, KB_A2_BYTES, BAR(0));
+            int i = 0;
+            for (int t = t_begin; t < t_end; ++t, ++i) {
+                const int b = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                {   // tile t+3 -> L2
+                    const int tp = t + 3;
+                    if (tp < t_end) {
+                        const int cb = tp / p.tiles_per_cloud, tt = tp % p.tiles_per_cloud, n0 = tt * KB_NT;
+                        const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
+                        const size_t P0 = (size_t)cb * p.N + n0;
+                        l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nv * C2 * 4u);
+                        l2_prefetch(p.A1 + P0 * C1, (uint32_t)nv * C1 * 4u);
+                    }
+                }
+                const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
+                const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
+                const size_t P0 = (size_t)cb * p.N + n0;
+                mbar_wait(BAR(7 + b), ph ^ 1);
+                mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)nv * (C2 + C1) * 4u);
+                const uint32_t dst = sbase + KB_OFF_BUF + b * KB_BUF_BYTES;
+                bulk_g2s(dst, p.DZ2 + P0 * C2, (uint32_t)nv * C2 * 4u, BAR(1 + b));
+                bulk_g2s(dst + KB_DZ_BYTES, p.A1 + P0 * C1, (uint32_t)nv * C1 * 4u, BAR(1 + b));
+            }
+        }
+    } else if (warp == 17) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC_K = idesc_f16(128, KB_NT);
+            constexpr uint32_t IDESC_MN = idesc_f16_mn(128, KB_NT);
+            mbar_wait(BAR(0), 0);
+            tc_fence_after_sync();
+            uint32_t first = 1;
+            int i = 0;
+            for (int t = t_begin; t < t_end; ++t, ++i) {
+                const int b = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(BAR(3 + b), ph);
+                tc_fence_after_sync();
+                const uint32_t dz = sbase + KB_OFF_BUF + b * KB_BUF_BYTES, a1 = dz + KB_DZ_BYTES;
+                const uint32_t d1 = tmem + (uint32_t)(b * KB_NT);
+                // ---- D1 = A1op x dz (K = 128 channels)
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint32_t a_hi = sbase + (kb * 2 + 0) * 16384, a_lo = sbase + (kb * 2 + 1) * 16384;
+                    const uint32_t b_hi = dz + (0 * 2 + kb) * 8192, b_lo = dz + (1 * 2 + kb) * 8192;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
+                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16(d1, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC_K,
+                                    (kb | pass | k) ? 1u : 0u);
+                    }
+                }
+                // ---- D1 += A2op x a1 (K = 64 channels)
+                {
+                    const uint32_t a_hi = sbase + KB_OFF_A2, a_lo = a_hi + 16384;
+                    const uint32_t b_hi = a1, b_lo = a1 + 8192;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
+                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16(d1, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC_K, 1u);
+                    }
+                }
+                mma_commit(BAR(5 + b));                     // d a1 of this tile complete -> epilogue
+                // ---- D2 += dz^T a1 (K = 64 points, MN-major operands; A atoms = the two 64-channel blocks, 8 KB apart)
+                {
+                    const uint32_t d2 = tmem + 128u;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = (pass == 1) ? dz + 16384 : dz;
+                        const uint32_t wb = (pass == 2) ? a1 + 8192 : a1;
+#pragma unroll
+                        for (int k = 0; k < KB_NT / 16; ++k)
+                            mma_f16(d2, desc_sw128_mnmajor(wa + k * 2048, 8192), desc_sw128_mnmajor(wb + k * 2048, 8192), IDESC_MN,
+                                    (first && pass == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+                // ---- D3 += [a1_hi ; a1_lo]^T a1_hi, then ... a1_lo  (rows 0-63: hi.hi + hi.lo, rows 64-127: lo.hi + lo.lo)
+                {
+                    const uint32_t d3 = tmem + 192u;
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const uint32_t wb = pass ? a1 + 8192 : a1;
+#pragma unroll
+                        for (int k = 0; k < KB_NT / 16; ++k)
+                            mma_f16(d3, desc_sw128_mnmajor(a1 + k * 2048, 8192), desc_sw128_mnmajor(wb + k * 2048, 8192), IDESC_MN,
+                                    (first && pass == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+                first = 0;
+                mma_commit(BAR(7 + b));                     // the tensor core is done reading this buffer
+            }
+            mma_commit(BAR(9));
+        }
+    } else if ((warp & 3) < 2) {
+        // ===================== epilogue: feature k = TMEM lane, 16 of the tile's 64 points per warp =====================
+        const int q = warp & 3, cgp = warp >> 2;
+        const int k = q * 32 + lane;
+        const float ginv = p.ginv[k], cv = p.cvec[k], be = p.beta1[k];
+        const float gm = p.gamma1[k], g1inv = gm != 0.f ? 1.0f / gm : 0.f;
+        const uint32_t koff = (uint32_t)((k & 7) * 2), kchunk = (uint32_t)(k >> 3);
+        float s1 = 0.f, s2 = 0.f;
+        int i = 0;
+        for (int t = t_begin; t < t_end; ++t, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
+            const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
+            mbar_wait(BAR(5 + b), ph);
+            tc_fence_after_sync();
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KB_NT + cgp * 16), v);
+            const unsigned char* a1b = smem + KB_OFF_BUF + b * KB_BUF_BYTES + KB_DZ_BYTES;
+            const float* xb = sx + b * (3 * KB_NT);
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int pp = cgp * 16 + j;
+                if (pp < nv) {
+                    const uint32_t off = (uint32_t)pp * 128u + ((kchunk ^ (uint32_t)(pp & 7)) << 4) + koff;
+                    const float a = (__half2float(*reinterpret_cast<const __half*>(a1b + off)) +
+                                     __half2float(*reinterpret_cast<const __half*>(a1b + 8192 + off))) * (1.0f / ACT_SCALE);
+                    const float da1 = fmaf(v[j], ginv, cv);
+                    const float dz1 = a > 0.f ? da1 : 0.f;
+                    const float yh = (a - be) * g1inv;      // only used where dz1 != 0
+                    s1 += dz1;
+                    s2 = fmaf(dz1, yh, s2);
+                    h0 = fmaf(dz1, xb[pp], h0); h1 = fmaf(dz1, xb[KB_NT + pp], h1); h2 = fmaf(dz1, xb[2 * KB_NT + pp], h2);
+                }
+            }
+            float* h = p.Hpart + ((size_t)t * KB_EPI_GROUPS + cgp) * (C1 * 3) + k * 3;
+            h[0] = h0; h[1] = h1; h[2] = h2;
+            tc_fence_before_sync();
+            mbar_arrive(BAR(7 + b));
+        }
+        float* o = p.bnpart + ((size_t)cta * KB_EPI_GROUPS + cgp) * 2 * C1;
+        o[k] = s1; o[C1 + k] = s2;
+    } else {
+        // ===================== converters: raw fp32 rows -> hi/lo fp16 operand tiles, in place =====================
+        const int cw = (warp >> 2) * 2 + (warp & 1);        // 0..7
+        const int ctid = cw * 32 + lane;
+        const float4 e4 = *reinterpret_cast<const float4*>(p.esc + 4 * lane);
+        int i = 0;
+        for (int t = t_begin; t < t_end; ++t, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
+            const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
+            float xv = 0.f;
+            if (ctid < 3 * KB_NT) {
+                const int j = ctid >> 6, pp = ctid & 63;
+                if (pp < nv) xv = __ldg(p.x + (size_t)cb * 3 * p.N + (size_t)j * p.N + n0 + pp);
+            }
+            mbar_wait(BAR(1 + b), ph);
+            unsigned char* dzb = smem + KB_OFF_BUF + b * KB_BUF_BYTES;
+            unsigned char* a1b = dzb + KB_DZ_BYTES;
+            float4 rdz[8], ra[4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rdz[u] = *reinterpret_cast<const float4*>(dzb + (cw * 8 + u) * 512 + lane * 16);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ra[u] = *reinterpret_cast<const float4*>(a1b + (cw * 8 + u * 2 + (lane >> 4)) * 256 + (lane & 15) * 16);
+            named_bar_sync(1, 256);                         // every converter thread has read its raw rows
+            if (ctid < 3 * KB_NT) sx[b * (3 * KB_NT) + ctid] = xv;
+            {
+                const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = cw * 8 + u;
+                    const bool ok = r < nv;
+                    const float d0 = ok ? fminf(fmaxf(rdz[u].x * e4.x, -60000.f), 60000.f) : 0.f;
+                    const float d1 = ok ? fminf(fmaxf(rdz[u].y * e4.y, -60000.f), 60000.f) : 0.f;
+                    const float d2 = ok ? fminf(fmaxf(rdz[u].z * e4.z, -60000.f), 60000.f) : 0.f;
+                    const float d3 = ok ? fminf(fmaxf(rdz[u].w * e4.w, -60000.f), 60000.f) : 0.f;
+                    __half2 h01, l01, h23, l23;
+                    split2(d0, d1, h01, l01);
+                    split2(d2, d3, h23, l23);
+                    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(dzb + (0 * 2 + kb) * 8192 + off) = hv;
+                    *reinterpret_cast<uint2*>(dzb + (1 * 2 + kb) * 8192 + off) = lv;
+                }
+            }
+            {
+                const int cg = lane & 15, chunk = cg >> 1, half8 = cg & 1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = cw * 8 + u * 2 + (lane >> 4);
+                    const bool ok = r < nv;
+                    const float a0 = ok ? fminf(ra[u].x * ACT_SCALE, 60000.f) : 0.f;
+                    const float a1v = ok ? fminf(ra[u].y * ACT_SCALE, 60000.f) : 0.f;
+                    const float a2 = ok ? fminf(ra[u].z * ACT_SCALE, 60000.f) : 0.f;
+                    const float a3 = ok ? fminf(ra[u].w * ACT_SCALE, 60000.f) : 0.f;
+                    __half2 h01, l01, h23, l23;
+                    split2(a0, a1v, h01, l01);
+                    split2(a2, a3, h23, l23);
+                    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(a1b + off) = hv;
+                    *reinterpret_cast<uint2*>(a1b + 8192 + off) = lv;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(BAR(3 + b));
+        }
+    }
+
+    // ===================== read-out of the persistent accumulators (warps 0..15: all four TMEM lane quadrants) ==========
+    if (warp < 16) {
+        const int q = warp & 3, cg = warp >> 2, row = q * 32 + lane;
+        mbar_wait(BAR(9), 0);
+        tc_fence_after_sync();
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(cg * 16), v);
+        {
+            const float sc = p.einv[row] * (1.0f / ACT_SCALE);
+            float* out = p.Cpart + (size_t)cta * (C2 * C1) + (size_t)row * C1 + cg * 16;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(out + j) = make_float4(v[j] * sc, v[j + 1] * sc, v[j + 2] * sc, v[j + 3] * sc);
+        }
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 192u + (uint32_t)(cg * 16), v);
+        float* scr = reinterpret_cast<float*>(smem + KB_OFF_BUF);      // the operand buffers are dead: [64][64] scratch
+        if (q >= 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) scr[(row - 64) * C1 + cg * 16 + j] = v[j];
+        }
+        named_bar_sync(2, 512);
+        if (q < 2) {
+            float* out = p.G1part + (size_t)cta * (C1 * C1) + (size_t)row * C1 + cg * 16;
+            constexpr float sc = 1.0f / (ACT_SCALE * ACT_SCALE);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out[j] = (v[j] + scr[row * C1 + cg * 16 + j]) * sc;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc<256>(tmem);
+}
+
+inline int launch_kb(const KbParams& p, int sms, cudaStream_t s) {
+    static int done[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 63]) {
+        cudaFuncSetAttribute(k_kb_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES);
+        done[dev & 63] = 1;
+    }
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    launch(k_kb_tc, dim3(grid), dim3(KB_THREADS), (size_t)KB_SMEM_BYTES, s, p);
+    return grid;
+}
+
+}}  // namespace pgpd::tc

@@ -16,8 +16,16 @@
 namespace pgpd { namespace tc {
 
 constexpr int ST_NT = 128;                 // points per tile
-constexpr int ST_THREADS = 448;            // 14 warps: loader, MMA issuer, 8 epilogue, 4 producer
+#ifndef PGPD_ST_NP
+#define PGPD_ST_NP 4
+#endif
+constexpr int ST_NP = PGPD_ST_NP;           // operand producer warps (4 or 8)
+constexpr int ST_THREADS = 320 + 32 * ST_NP;   // warps: loader, MMA issuer, 8 epilogue, ST_NP producer
 constexpr int ST_EPI_ROWS = 2;              // partial rows each CTA writes (two epilogue warps per TMEM quadrant)
+#ifndef PGPD_EPI_BATCH
+#define PGPD_EPI_BATCH 32
+#endif
+constexpr int EPI_BATCH = PGPD_EPI_BATCH;   // columns whose global operands an epilogue thread loads before it computes (32 or 16)
 constexpr float ACT_SCALE = 16.0f;         // 2^4 applied to O(1) activations before the fp16 split
 constexpr int ACT_SHIFT = 4;
 
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(BAR(0), 1);
-        mbar_init(BAR(1), 128); mbar_init(BAR(2), 128);
+        mbar_init(BAR(1), 32 * ST_NP); mbar_init(BAR(2), 32 * ST_NP);
         mbar_init(BAR(3), 1); mbar_init(BAR(4), 1);
         mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
         mbar_init(BAR(7), 256); mbar_init(BAR(8), 256);
@@ -215,17 +223,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stream_tc(typename T::Params 
                 const int nvn = (p.M - Pn < (size_t)ST_NT) ? (int)(p.M - Pn) : ST_NT;
                 T::prefetch(p, Pn, nvn);                    // tile t+2 -> L2
             }
-            constexpr int ITERS = ST_NT / (4 * RPI), U = 8;
+            constexpr int ITERS = ST_NT / (ST_NP * RPI), U = (ITERS < 8) ? ITERS : 8;
             for (int i0 = 0; i0 < ITERS; i0 += U) {
                 typename T::Raw raw[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {               // all global loads of U rows first (memory-level parallelism)
-                    const int r = (wp + 4 * (i0 + u)) * RPI + rsub;
+                    const int r = (wp + ST_NP * (i0 + u)) * RPI + rsub;
                     T::fetch(ps, p, P0 + r, r < nvalid, cg, raw[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = (wp + 4 * (i0 + u)) * RPI + rsub;
+                    const int r = (wp + ST_NP * (i0 + u)) * RPI + rsub;
                     float v[4];
                     const float aux = T::transform(ps, p, P0 + r, r < nvalid, cg, raw[u], v);
                     __half2 h01, l01, h23, l23;
@@ -358,25 +366,30 @@ struct L2BwdATC {
     __device__ static void epi_cols(Epi& e, const Params& p, int c, size_t P0, int nvalid, const float (&v)[32], const float* aux) {
         // every global load of the 32 columns is issued before any store; the row index of the sparse part comes
         // from shared memory (aux[1], staged by the producer), so both loads of a column are independent
-        float y[32], ds[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const bool ok = j < nvalid;
-            const int sl = ok ? __float_as_int(aux[128 + j]) : -1;
-            y[j] = ok ? __ldg(p.Y2 + (P0 + j) * C2 + c) : 0.f;
-            ds[j] = (sl >= 0) ? __ldg(p.da2s + (size_t)sl * C2 + c) : 0.f;
-        }
+        for (int h0 = 0; h0 < 32; h0 += EPI_BATCH) {
+            float y[EPI_BATCH], ds[EPI_BATCH];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < nvalid) {
-                const float da2 = -v[j] * e.inv - e.u + ds[j];
-                const float dz = (e.sc * y[j] + e.sh > 0.f) ? da2 : 0.f;
-                p.DZ2[(P0 + j) * C2 + c] = dz;
-                const float yh = (y[j] - e.mu) * e.r;
-                e.s1 += dz;
-                e.s2 = fmaf(dz, yh, e.s2);
-                e.mxdz = fmaxf(e.mxdz, fabsf(dz));
-                e.mxyh = fmaxf(e.mxyh, fabsf(yh));
+            for (int jj = 0; jj < EPI_BATCH; ++jj) {
+                const int j = h0 + jj;
+                const bool ok = j < nvalid;
+                const int sl = ok ? __float_as_int(aux[128 + j]) : -1;
+                y[jj] = ok ? __ldg(p.Y2 + (P0 + j) * C2 + c) : 0.f;
+                ds[jj] = (sl >= 0) ? __ldg(p.da2s + (size_t)sl * C2 + c) : 0.f;
+            }
+#pragma unroll
+            for (int jj = 0; jj < EPI_BATCH; ++jj) {
+                const int j = h0 + jj;
+                if (j < nvalid) {
+                    const float da2 = -v[j] * e.inv - e.u + ds[jj];
+                    const float dz = (e.sc * y[jj] + e.sh > 0.f) ? da2 : 0.f;
+                    p.DZ2[(P0 + j) * C2 + c] = dz;
+                    const float yh = (y[jj] - e.mu) * e.r;
+                    e.s1 += dz;
+                    e.s2 = fmaf(dz, yh, e.s2);
+                    e.mxdz = fmaxf(e.mxdz, fabsf(dz));
+                    e.mxyh = fmaxf(e.mxyh, fabsf(yh));
+                }
             }
         }
     }
@@ -455,19 +468,23 @@ struct L2BwdBTC {
     }
     __device__ static void epi_cols(Epi& e, const Params& p, int k, size_t P0, int nvalid, const float (&v)[32], const float* aux) {
         if (k >= C1) return;
-        float a[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = (j < nvalid) ? __ldg(p.A1 + (P0 + j) * C1 + k) : 0.f;
+        for (int h0 = 0; h0 < 32; h0 += EPI_BATCH) {
+            float a[EPI_BATCH];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < nvalid) {
-                const float da1 = v[j] * e.inv * aux[j];
-                const bool on = a[j] > 0.f;
-                const float dz = on ? da1 : 0.f;
-                p.DZ1[(P0 + j) * C1 + k] = dz;
-                const float yh = (a[j] - e.be) * e.ginv;       // only used where dz != 0
-                e.s1 += dz;
-                e.s2 = fmaf(dz, yh, e.s2);
+            for (int jj = 0; jj < EPI_BATCH; ++jj) a[jj] = (h0 + jj < nvalid) ? __ldg(p.A1 + (P0 + h0 + jj) * C1 + k) : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < EPI_BATCH; ++jj) {
+                const int j = h0 + jj;
+                if (j < nvalid) {
+                    const float da1 = v[j] * e.inv * aux[j];
+                    const bool on = a[jj] > 0.f;
+                    const float dz = on ? da1 : 0.f;
+                    p.DZ1[(P0 + j) * C1 + k] = dz;
+                    const float yh = (a[jj] - e.be) * e.ginv;       // only used where dz != 0
+                    e.s1 += dz;
+                    e.s2 = fmaf(dz, yh, e.s2);
+                }
             }
         }
     }

@@ -19,10 +19,12 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "l2bwd.cuh"
 #ifndef PGPD_EMU
 #include "tc_l3.cuh"
 #include "tc_stream.cuh"
 #include "tc_accum.cuh"
+#include "tc_kb.cuh"
 #endif
 
 namespace pgpd {
@@ -50,6 +52,8 @@ struct TowerKeep {
     BnState bn[3];
     float* sgn;       // [1024] +1 / -1 : sign of gamma3 (max vs min selection)
     double* S1;       // [128]  sum over points of a2
+    double* S1a;      // [64]   sum over points of a1
+    double* xmom;     // [B][12] per-cloud raw-coordinate moments: sum x (3), sum x x^T (3x3)
 };
 
 struct TowerScratch {
@@ -61,6 +65,7 @@ struct TowerScratch {
     unsigned long long* keys;  // [B][1024]
     void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
+    void* wimg_kb;    // 96 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
     float* pmax;      // [512][2][128] per-epilogue-row maxima of |dz2|, |yhat2|
@@ -80,6 +85,16 @@ struct TowerScratch {
     float* DZ1;       // [M][64]
     float* m1_2; float* m2_2;   // [128]
     float* m1_1; float* m2_1;   // [64]
+    // fused layer-2/1 backward (l2bwd.cuh, tc_kb.cuh)
+    float* Kmat;      // [64*64]
+    float* cvec;      // [64]
+    float* kbC;       // [128*64]  C = sum dz2 a1^T
+    float* kbG1;      // [64*64]   Gram of a1
+    float* kb_Cpart;  // [KB_MAX_PART][128*64]
+    float* kb_G1part; // [KB_MAX_PART][64*64]
+    float* kb_bn;     // [kb_rows][2][64]
+    float* kb_H;      // [kb_rows][64*3]
+    int kb_rows;
     // sizes
     int nb_a1, nb_a2, nb_l2, nb_gram, nb_dw2, tiles_per_cloud;
     size_t fpart_elems;
@@ -90,6 +105,7 @@ struct TowerWs : TowerKeep, TowerScratch {};
 constexpr int A1_CHUNK = 64;       // points per block of k_a1
 constexpr int GRAM_CHUNK = 1024;   // points per split-K block of the Gram GEMM
 constexpr int DW2_CHUNK = 2048;    // points per split-K block of the dW2 GEMM
+constexpr int KB_MAX_PART = KB_REF_MAX_BLOCKS;   // per-block partial slots of the fused layer-2/1 backward pass
 
 inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
     const size_t M = (size_t)B * N;
@@ -100,6 +116,8 @@ inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
     w.bn[0].carve(c, C1); w.bn[1].carve(c, C2); w.bn[2].carve(c, C3);
     w.sgn = c.take<float>(C3);
     w.S1 = c.take<double>(C2);
+    w.S1a = c.take<double>(C1);
+    w.xmom = c.take<double>((size_t)B * 12);
 }
 
 inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool backward) {
@@ -132,6 +150,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.keys = c.take<unsigned long long>((size_t)B * C3);
     w.wimg = c.take<unsigned char>((size_t)512 * 1024);
     w.mu_s = c.take<float>(C3);
+    w.wimg_kb = c.take<unsigned char>((size_t)96 * 1024);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
     w.pmax = c.take<float>((size_t)512 * 2 * C2);
@@ -151,6 +170,15 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         w.DZ1 = c.take<float>(M * C1);
         w.m1_2 = c.take<float>(C2); w.m2_2 = c.take<float>(C2);
         w.m1_1 = c.take<float>(C1); w.m2_1 = c.take<float>(C1);
+        w.Kmat = c.take<float>(C1 * C1);
+        w.cvec = c.take<float>(C1);
+        w.kbC = c.take<float>(C2 * C1);
+        w.kbG1 = c.take<float>(C1 * C1);
+        w.kb_Cpart = c.take<float>((size_t)KB_MAX_PART * C2 * C1);
+        w.kb_G1part = c.take<float>((size_t)KB_MAX_PART * C1 * C1);
+        w.kb_rows = B * idiv_up(N, 64) * 4;             // >= the rows either version of the pass writes
+        w.kb_bn = c.take<float>((size_t)w.kb_rows * 2 * C1);
+        w.kb_H = c.take<float>((size_t)w.kb_rows * C1 * 3);
     }
 }
 
@@ -160,7 +188,8 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
 
 // per-cloud first and second moments of the TRANSFORMED points x' = T^T x, in double.
 // mom[b] = { sum x'_i (3) , sum x'_i x'_i2 (3x3 row-major) }
-__global__ void k_cloud_moments(const float* __restrict__ x, const float* __restrict__ trans, int N, double* __restrict__ mom) {
+__global__ void k_cloud_moments(const float* __restrict__ x, const float* __restrict__ trans, int N, double* __restrict__ mom,
+                                double* __restrict__ rawmom) {
     __shared__ double sh[256];
     __shared__ double raw[9];
     const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
@@ -198,6 +227,10 @@ __global__ void k_cloud_moments(const float* __restrict__ x, const float* __rest
                 for (int j2 = 0; j2 < 3; ++j2) v += T[j][i] * X[j][j2] * T[j2][i2];
         }
         mom[(size_t)b * 12 + tid] = v;
+        if (rawmom) {
+            // raw-coordinate moments, kept for the layer-1 backward: X1 (3), X2 (3x3 row-major)
+            rawmom[(size_t)b * 12 + tid] = tid < 3 ? s1[tid] : X[(tid - 3) / 3][(tid - 3) % 3];
+        }
     }
 }
 
@@ -607,17 +640,30 @@ __global__ void k_da2_sparse(const float* __restrict__ coef, const int* __restri
         rowpos[nrows] = nvalid;
     }
     __syncthreads();
-    const int grp = tid >> 7, k = tid & 127;
-    for (int r = grp; r < nrows; r += 8) {
+    // one WARP per output row (lane = 4 consecutive channels, float4): 32 independent rows in flight per block.
+    // The entries of a row are summed in ascending channel order (the sort order), so the result is reproducible.
+    const int wrp = tid >> 5, lane = tid & 31;
+    const float4* W3v = reinterpret_cast<const float4*>(W3);
+    for (int r = wrp; r < nrows; r += 32) {
         const int e0 = rowpos[r], e1 = rowpos[r + 1];
-        float acc = 0.f;
-        for (int e = e0; e < e1; ++e) {
-            const int c = (int)(sk[e] & 1023u);
-            acc = fmaf(coef[(size_t)b * C3 + c], W3[(size_t)c * C2 + k], acc);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = e0;
+        for (; e + 1 < e1; e += 2) {            // two entries per iteration: their loads are independent
+            const int c0 = (int)(sk[e] & 1023u), c1 = (int)(sk[e + 1] & 1023u);
+            const float f0 = coef[(size_t)b * C3 + c0], f1 = coef[(size_t)b * C3 + c1];
+            const float4 w0 = W3v[(size_t)c0 * (C2 / 4) + lane], w1 = W3v[(size_t)c1 * (C2 / 4) + lane];
+            acc.x = fmaf(f0, w0.x, acc.x); acc.y = fmaf(f0, w0.y, acc.y); acc.z = fmaf(f0, w0.z, acc.z); acc.w = fmaf(f0, w0.w, acc.w);
+            acc.x = fmaf(f1, w1.x, acc.x); acc.y = fmaf(f1, w1.y, acc.y); acc.z = fmaf(f1, w1.z, acc.z); acc.w = fmaf(f1, w1.w, acc.w);
+        }
+        if (e < e1) {
+            const int c0 = (int)(sk[e] & 1023u);
+            const float f0 = coef[(size_t)b * C3 + c0];
+            const float4 w0 = W3v[(size_t)c0 * (C2 / 4) + lane];
+            acc.x = fmaf(f0, w0.x, acc.x); acc.y = fmaf(f0, w0.y, acc.y); acc.z = fmaf(f0, w0.z, acc.z); acc.w = fmaf(f0, w0.w, acc.w);
         }
         const size_t row = (size_t)b * C3 + r;
-        da2s[row * C2 + k] = acc;
-        if (k == 0) slot[(size_t)b * N + (sk[e0] >> 10)] = (int)row;
+        reinterpret_cast<float4*>(da2s)[row * (C2 / 4) + lane] = acc;
+        if (lane == 0) slot[(size_t)b * N + (sk[e0] >> 10)] = (int)row;
     }
 }
 
@@ -774,34 +820,52 @@ __global__ void k_l1_bwd(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ W1, BnState st1, const float* __restrict__ DZ1,
                          const float* __restrict__ m1, const float* __restrict__ m2,
                          float* __restrict__ dW1part, float* __restrict__ dtrans) {
-    __shared__ float shg[256 * 3];
-    __shared__ float G[64 * 3];
-    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
+    // thread = 4 consecutive channels (one float4 of a DZ1 row) x one of 16 point slots: 16-byte loads, and with
+    // the 4-fold unrolled point loop 64 B per thread in flight.  The 16 slots are summed in a fixed order.
+    __shared__ float shg[16][C1 * 3 + 1];
+    __shared__ float G[C1 * 3];
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, kq = tid & 15, q = tid >> 4;
     const float* xb = x + (size_t)b * 3 * N;
     float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (trans)
         for (int e = 0; e < 9; ++e) T[e] = trans[(size_t)b * 9 + e];
-    const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
-    // (W1 T^T)[k][j] = sum_i W1[k][i] T[j][i]
-    const float v0 = w0 * T[0] + w1 * T[1] + w2 * T[2];
-    const float v1 = w0 * T[3] + w1 * T[4] + w2 * T[5];
-    const float v2 = w0 * T[6] + w1 * T[7] + w2 * T[8];
-    const float mu = st1.mean[k], r = st1.rstd[k], sc = st1.scale[k], mm1 = m1[k], mm2 = m2[k];
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    const float* dz = DZ1 + (size_t)b * N * C1 + k;
-#pragma unroll 4
-    for (int n = q; n < N; n += 4) {
-        const float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
-        const float u = v0 * p0 + v1 * p1 + v2 * p2;
-        const float yhat = (u - mu) * r;
-        const float dy = sc * (dz[(size_t)n * C1] - mm1 - yhat * mm2);
-        g0 = fmaf(dy, p0, g0); g1 = fmaf(dy, p1, g1); g2 = fmaf(dy, p2, g2);
+    float v0[4], v1[4], v2[4], mu[4], rr[4], sc[4], mm1[4], mm2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = 4 * kq + i;
+        const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
+        // (W1 T^T)[k][j] = sum_i W1[k][i] T[j][i]
+        v0[i] = w0 * T[0] + w1 * T[1] + w2 * T[2];
+        v1[i] = w0 * T[3] + w1 * T[4] + w2 * T[5];
+        v2[i] = w0 * T[6] + w1 * T[7] + w2 * T[8];
+        mu[i] = st1.mean[k]; rr[i] = st1.rstd[k]; sc[i] = st1.scale[k]; mm1[i] = m1[k]; mm2[i] = m2[k];
     }
-    shg[tid * 3 + 0] = g0; shg[tid * 3 + 1] = g1; shg[tid * 3 + 2] = g2;
+    float g0[4] = {0.f, 0.f, 0.f, 0.f}, g1[4] = {0.f, 0.f, 0.f, 0.f}, g2[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* dz = reinterpret_cast<const float4*>(DZ1 + (size_t)b * N * C1) + kq;
+#pragma unroll 4
+    for (int n = q; n < N; n += 16) {
+        const float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
+        const float4 d4 = dz[(size_t)n * (C1 / 4)];
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float u = v0[i] * p0 + v1[i] * p1 + v2[i] * p2;
+            const float yhat = (u - mu[i]) * rr[i];
+            const float dy = sc[i] * (d[i] - mm1[i] - yhat * mm2[i]);
+            g0[i] = fmaf(dy, p0, g0[i]); g1[i] = fmaf(dy, p1, g1[i]); g2[i] = fmaf(dy, p2, g2[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = 4 * kq + i;
+        shg[q][k * 3 + 0] = g0[i]; shg[q][k * 3 + 1] = g1[i]; shg[q][k * 3 + 2] = g2[i];
+    }
     __syncthreads();
     if (tid < 192) {
-        const int kk = tid / 3, j = tid % 3;
-        G[tid] = ((shg[(0 * 64 + kk) * 3 + j] + shg[(1 * 64 + kk) * 3 + j]) + shg[(2 * 64 + kk) * 3 + j]) + shg[(3 * 64 + kk) * 3 + j];
+        float t = 0.f;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) t += shg[s][tid];
+        G[tid] = t;
     }
     __syncthreads();
     if (tid < 192) {
@@ -838,7 +902,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 
     // ---- layer 1 ---------------------------------------------------------------------------------
     if (a.train) {
-        launch(k_cloud_moments, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, w.moments);
+        launch(k_cloud_moments, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, w.moments, a.save ? w.xmom : (double*)nullptr);
         const int S = colreduce<double>(w.moments, a.B, 12, w.rtmp, s);
         launch(k_bn1_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, count, t.conv[0], t.bn[0], w.bn[0]);
     } else {
@@ -852,8 +916,8 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     // ---- layer 2 ---------------------------------------------------------------------------------
     if (a.train) {
         const int S = colreduce<double>(w.dpart, w.nb_a1, C1, w.rtmp, s);
-        launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, w.dsum);
-        launch(k_matvec_mean, dim3(1), dim3(128), 0, s, t.conv[1].w, C2, C1, (const double*)w.dsum, 1.0 / count, w.bn[1].mean);
+        launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, w.S1a);
+        launch(k_matvec_mean, dim3(1), dim3(128), 0, s, t.conv[1].w, C2, C1, (const double*)w.S1a, 1.0 / count, w.bn[1].mean);
     }
     int n_css2 = 0;
 #ifndef PGPD_EMU
@@ -1002,6 +1066,57 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         const int S = colreduce<float>(w.fpart, nrows, 2 * C2, w.rtmp, s);
         launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2, count,
                g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
+    }
+    // ---- layers 2 and 1, fused pass over (dz2, a1) (l2bwd.cuh); PGPD_KB=0 selects the older three-kernel form ----
+    static const bool use_kb = !(getenv("PGPD_KB") && atoi(getenv("PGPD_KB")) == 0);
+    if (use_kb) {
+        launch(k_kb_prep, dim3(C1), dim3(C1), 0, s, t.conv[1].w, w.bn[1], (const float*)w.m1_2, (const float*)w.m2_2, w.Kmat, w.cvec);
+        int nparts = 0, nrows = 0, rpc = 0;
+#ifndef PGPD_EMU
+        if (a.use_tc && (tc_mask() & 16) && g_b4 > 0) {
+            launch(tc::k_kb_scale, dim3(1), dim3(1024), 0, s, (const float*)w.pmax, g_b4, w.esc, w.einv);
+            __half* img1 = (__half*)w.wimg_kb;
+            __half* img2 = img1 + tc::KB_A1_BYTES / 2;
+            launch(tc::k_kb_prepack, dim3(128), dim3(128), 0, s, t.conv[1].w, (const float*)w.bn[1].scale, (const float*)w.einv,
+                   (const float*)w.Kmat, img1, img2, w.inv_s);
+            const int tpc = idiv_up(a.N, tc::KB_NT), ntiles = a.B * tpc;
+            tc::KbParams p{img1, img2, w.inv_s, w.cvec, t.bn[0].gamma, t.bn[0].beta, w.esc, w.einv, w.DZ2, w.A1, a.x,
+                           a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
+            nparts = tc::launch_kb(p, tc::dev_info().sms, s);
+            nrows = nparts * tc::KB_EPI_GROUPS; rpc = tpc * tc::KB_EPI_GROUPS;
+        } else
+#endif
+        {
+            const int tpc = idiv_up(a.N, KB_REF_NT), ntiles = a.B * tpc;
+            const int grid = ntiles < KB_REF_MAX_BLOCKS ? ntiles : KB_REF_MAX_BLOCKS;
+            KbRefParams p{w.DZ2, w.A1, a.x, t.conv[1].w, w.bn[1].scale, w.Kmat, w.cvec, t.bn[0].gamma, t.bn[0].beta,
+                          a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
+            launch(k_kb_ref, dim3(grid), dim3(256), 0, s, p);
+            nparts = grid; nrows = ntiles; rpc = tpc;
+        }
+        {
+            const int S = colreduce<float>(w.kb_bn, nrows, 2 * C1, w.rtmp, s);
+            launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, count,
+                   g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
+        }
+        {
+            const int S = colreduce<float>(w.kb_Cpart, nparts, C2 * C1, w.rtmp, s);
+            launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C1, w.kbC);
+        }
+        {
+            const int S = colreduce<float>(w.kb_G1part, nparts, C1 * C1, w.rtmp, s);
+            launch(k_reduce_f, grid1d(C1 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C1 * C1, w.kbG1);
+        }
+        launch(k_kb_dw2, dim3(C2), dim3(C1), 0, s, (const float*)w.kbC, (const float*)w.kbG1, (const double*)w.S1a, t.conv[1].w, w.bn[1],
+               (const float*)w.m1_2, (const float*)w.m2_2, g.conv[1].dw, g.conv[1].db);
+        launch(k_kb_l1, dim3(a.B), dim3(192), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
+               (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr);
+        {
+            const int S = colreduce<float>(w.fpart, a.B, C1 * 3, w.rtmp, s);
+            launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const double*)w.rtmp, S, C1 * 3, g.conv[0].dw);
+        }
+        launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
+        return;
     }
     Dy2 dy{w.DZ2, w.Y2, w.bn[1], w.m1_2, w.m2_2};
     {

@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oracle import weights as W
 from pointnetgpd_b200 import _abi as A
+if os.environ.get("PGPD_LIB"):
+    A.LIB_PATH = os.path.abspath(os.environ["PGPD_LIB"])
 from pointnetgpd_b200.model.pointnet import PointNetCls
 B, N = 512, 1024
 st = W.make_state(0, k=2)
