@@ -94,8 +94,10 @@ __global__ void k_colreduce_stage1(const T* __restrict__ part, int nblk, int C, 
     const int per = (nblk + S - 1) / S;
     const int r0 = sl * per, r1 = (r0 + per < nblk) ? r0 + per : nblk;
     double acc = 0.0;
-    if (c < C)
+    if (c < C) {
+#pragma unroll 4
         for (int i = r0 + ry; i < r1; i += 8) acc += (double)part[(size_t)i * C + c];
+    }
     sh[ry][cx] = acc;
     __syncthreads();
     if (ry == 0 && c < C) {
@@ -146,13 +148,17 @@ __global__ void k_reduce_f(const double* tmp, int S, int C, float* out) {
     out[c] = (float)s;
 }
 
-// mean_out[r] = (sum_k W[r][k] * vsum[k]) * inv   in double
-__global__ void k_matvec_mean(const float* W, int rows, int cols, const double* vsum, double inv, float* mean_out) {
-    int r = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (r >= rows) return;
+// mean_out[r] = (sum_k W[r][k] * vsum[k]) * inv   in double.  One warp per row (coalesced row reads, fixed shuffle tree);
+// block = 256 threads = 8 rows, grid = ceil(rows / 8).
+__global__ void k_matvec_mean(const float* __restrict__ W, int rows, int cols, const double* __restrict__ vsum, double inv,
+                              float* __restrict__ mean_out) {
+    const int r = (int)blockIdx.x * 8 + ((int)threadIdx.x >> 5), lane = (int)threadIdx.x & 31;
     double s = 0.0;
-    for (int k = 0; k < cols; ++k) s += (double)W[(size_t)r * cols + k] * vsum[k];
-    mean_out[r] = (float)(s * inv);
+    if (r < rows)
+        for (int k = lane; k < cols; k += 32) s += (double)W[(size_t)r * cols + k] * vsum[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (r < rows && lane == 0) mean_out[r] = (float)(s * inv);
 }
 
 __global__ void k_fill(float* p, size_t n, float v) {

@@ -114,39 +114,41 @@ inline void run_plain(ProbPlain<AK, BNF> p, cudaStream_t s, int fixed_nsl = 0) {
 }
 
 // batch statistics of U[:,c] (two-pass, double) -> BatchNorm finalisation -> H = relu(scale*U + shift).
-// block = 32 channels x 8 row lanes (fixed-order shared-memory reduction: deterministic)
+// block = 32 channels x 32 row lanes (fixed-order shared-memory reduction: deterministic)
 __global__ void k_bn_batch_stats_apply(const float* __restrict__ U, int B, int C, const float* bias, pgpd_bn bn, BnState st,
                                        float* __restrict__ Hout) {
-    __shared__ double sh[8][33];
+    __shared__ double sh[32][33];
     __shared__ double smean[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
     double s = 0.0;
-    if (c < C)
-        for (int b = ry; b < B; b += 8) s += (double)U[(size_t)b * C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int b = ry; b < B; b += 32) s += (double)U[(size_t)b * C + c];
+    }
     sh[ry][cx] = s;
     __syncthreads();
     if (ry == 0) {
         double t = 0.0;
-        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+        for (int q = 0; q < 32; ++q) t += sh[q][cx];
         smean[cx] = t / B;
     }
     __syncthreads();
     const double mean = smean[cx];
     double v = 0.0;
     if (c < C)
-        for (int b = ry; b < B; b += 8) { double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
+        for (int b = ry; b < B; b += 32) { double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
     sh[ry][cx] = v;
     __syncthreads();
     if (ry == 0 && c < C) {
         double t = 0.0;
-        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+        for (int q = 0; q < 32; ++q) t += sh[q][cx];
         bn_finalize_train(c, mean, t / B, (double)B, bias, bn, st);
     }
     __syncthreads();
     if (c < C) {
         const float sc = st.scale[c], sf = st.shift[c];
-        for (int b = ry; b < B; b += 8) Hout[(size_t)b * C + c] = fmaxf(sc * U[(size_t)b * C + c] + sf, 0.f);
+        for (int b = ry; b < B; b += 32) Hout[(size_t)b * C + c] = fmaxf(sc * U[(size_t)b * C + c] + sf, 0.f);
     }
 }
 
@@ -181,27 +183,33 @@ __global__ void k_log_softmax_bwd(const float* __restrict__ logp, const float* _
     for (int j = 0; j < K; ++j) dlogits[(size_t)b * K + j] = dlogp[(size_t)b * K + j] - expf(logp[(size_t)b * K + j]) * s;
 }
 
-// out[j] = sum_b G[b][j]   (bias gradient of fc3); thread = column
+// out[j] = sum_b G[b][j]   (bias gradient of fc3); block = column, 256 row lanes summed in a fixed order
 __global__ void k_colsum(const float* __restrict__ G, int B, int J, float* __restrict__ out) {
-    int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (j >= J) return;
+    __shared__ double sh[256];
+    const int j = (int)blockIdx.x, tid = (int)threadIdx.x;
     double s = 0.0;
-    for (int b = 0; b < B; ++b) s += (double)G[(size_t)b * J + j];
-    out[j] = (float)s;
+    for (int b = tid; b < B; b += 256) s += (double)G[(size_t)b * J + j];
+    sh[tid] = s;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (tid < st) sh[tid] += sh[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0) out[j] = (float)sh[0];
 }
 
 // BatchNorm-over-batch backward: sums -> dgamma, dbeta; then dU = s*(dz - m1 - yhat*m2) written IN PLACE over dz.
-// block = 32 channels x 8 row lanes.
+// block = 32 channels x 32 row lanes.
 __global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ double sh1[8][33], sh2[8][33];
+    __shared__ double sh1[32][33], sh2[32][33];
     __shared__ float sm1[32], sm2[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
     const float mu = c < C ? st.mean[c] : 0.f, r = c < C ? st.rstd[c] : 0.f, sc = c < C ? st.scale[c] : 0.f;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-        for (int b = ry; b < B; b += 8) {
+        for (int b = ry; b < B; b += 32) {
             double dz = (double)DZ[(size_t)b * C + c];
             double yhat = (double)((U[(size_t)b * C + c] - mu) * r);
             s1 += dz; s2 += dz * yhat;
@@ -211,14 +219,14 @@ __global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __rest
     __syncthreads();
     if (ry == 0) {
         double t1 = 0.0, t2 = 0.0;
-        for (int q = 0; q < 8; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
+        for (int q = 0; q < 32; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
         if (c < C) { dgamma[c] = (float)t2; dbeta[c] = (float)t1; }
         sm1[cx] = (float)(t1 / B); sm2[cx] = (float)(t2 / B);
     }
     __syncthreads();
     if (c < C) {
         const float m1 = sm1[cx], m2 = sm2[cx];
-        for (int b = ry; b < B; b += 8) {
+        for (int b = ry; b < B; b += 32) {
             const size_t i = (size_t)b * C + c;
             const float yhat = (U[i] - mu) * r;
             DZ[i] = sc * (DZ[i] - m1 - yhat * m2);
@@ -241,14 +249,14 @@ inline void head_forward(const HeadArgs& a, HeadWs& w) {
     const int B = a.B;
     // fc1: U1[b][j] = sum_i X[b][i] W1[j][i]
     run_plain(ProbPlain<true, false>{a.X, h.fc[0].w, w.U1, w.part, B, H1, C3, (size_t)C3, 1, 1, (size_t)C3, 0, EPI_NONE, nullptr, 0, nullptr}, s, 8);
-    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H1, 32), dim3(256), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0], w.Hm1);
+    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H1, 32), dim3(1024), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0], w.Hm1);
     else {
         launch(k_bn_eval_affine, grid1d(H1, 128), dim3(128), 0, s, H1, h.fc[0].b, h.bn[0], w.bn[0]);
         launch(k_bn_apply, grid1d((size_t)B * H1, 256), dim3(256), 0, s, (const float*)w.U1, (size_t)B * H1, H1, w.bn[0], w.Hm1);
     }
     // fc2
     run_plain(ProbPlain<true, false>{w.Hm1, h.fc[1].w, w.U2, w.part, B, H2, H1, (size_t)H1, 1, 1, (size_t)H1, 0, EPI_NONE, nullptr, 0, nullptr}, s, 4);
-    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H2, 32), dim3(256), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1], w.Hm2);
+    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H2, 32), dim3(1024), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1], w.Hm2);
     else {
         launch(k_bn_eval_affine, grid1d(H2, 128), dim3(128), 0, s, H2, h.fc[1].b, h.bn[1], w.bn[1]);
         launch(k_bn_apply, grid1d((size_t)B * H2, 256), dim3(256), 0, s, (const float*)w.U2, (size_t)B * H2, H2, w.bn[1], w.Hm2);
@@ -265,14 +273,14 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     const int B = a.B, J3 = a.out;
     // ---- fc3:  dW3[j][i] = sum_b dO[b][j] H2[b][i] ;  db3 = colsum(dO) ;  dz2 = (dO W3) masked by H2 > 0
     run_plain(ProbPlain<false, true>{w.dO, w.Hm2, g.fc[2].dw, w.part, J3, H2, B, 1, (size_t)J3, (size_t)H2, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
-    launch(k_colsum, grid1d(J3, 32), dim3(32), 0, s, (const float*)w.dO, B, J3, g.fc[2].db);
+    launch(k_colsum, dim3(J3), dim3(256), 0, s, (const float*)w.dO, B, J3, g.fc[2].db);
     run_plain(ProbPlain<true, true>{w.dO, h.fc[2].w, w.DZ2, w.part, B, H2, J3, (size_t)J3, 1, (size_t)H2, 1, 0, EPI_MASK, nullptr, 0, w.Hm2}, s);
-    launch(k_bn_batch_bwd_apply, grid1d(H2, 32), dim3(256), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta);
+    launch(k_bn_batch_bwd_apply, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta);
     // ---- fc2 (w.DZ2 now holds dU2)
     run_plain(ProbPlain<false, true>{w.DZ2, w.Hm1, g.fc[1].dw, w.part, H2, H1, B, 1, (size_t)H2, (size_t)H1, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
     launch(k_fill, grid1d(H2, 128), dim3(128), 0, s, g.fc[1].db, (size_t)H2, 0.f);
     run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.DZ1, w.part, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0, EPI_MASK, nullptr, 0, w.Hm1}, s);
-    launch(k_bn_batch_bwd_apply, grid1d(H1, 32), dim3(256), 0, s, w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta);
+    launch(k_bn_batch_bwd_apply, grid1d(H1, 32), dim3(1024), 0, s, w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta);
     // ---- fc1 (w.DZ1 now holds dU1)
     run_plain(ProbPlain<false, true>{w.DZ1, a.X, g.fc[0].dw, w.part, H1, C3, B, 1, (size_t)H1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
     launch(k_fill, grid1d(H1, 128), dim3(128), 0, s, g.fc[0].db, (size_t)H1, 0.f);

@@ -31,20 +31,32 @@ namespace pgpd {
 constexpr int KB_REF_NT = 32;          // points per tile of the CUDA-core pass
 constexpr int KB_REF_MAX_BLOCKS = 592;
 
-// K[k][k'] = sum_c W2[c][k] s_c r_c m2_c W2[c][k'],  cvec[k] = sum_c W2[c][k] s_c (r_c m2_c mu_c - m1_c).  grid 64 x block 64
+// K[k][k'] = sum_c W2[c][k] s_c r_c m2_c W2[c][k'],  cvec[k] = sum_c W2[c][k] s_c (r_c m2_c mu_c - m1_c).
+// grid 64 (k) x block 256 = 64 (k') x 4 lanes over c; the lanes are summed in a fixed order.
 __global__ void k_kb_prep(const float* __restrict__ W2, BnState st2, const float* __restrict__ m1, const float* __restrict__ m2,
                           float* __restrict__ Kmat, float* __restrict__ cvec) {
-    const int k = (int)blockIdx.x, kp = (int)threadIdx.x;
-    double acc = 0.0, cv = 0.0;
-#pragma unroll 8
-    for (int c = 0; c < C2; ++c) {
-        const double w = (double)W2[c * C1 + k];
-        const double s = (double)st2.scale[c], rm2 = (double)st2.rstd[c] * (double)m2[c];
-        acc += w * (s * rm2) * (double)W2[c * C1 + kp];
-        if (kp == 0) cv += w * s * (rm2 * (double)st2.mean[c] - (double)m1[c]);
+    __shared__ double sd[C2], se[C2], swk[C2];
+    __shared__ double part[4][C1 + 1];
+    const int k = (int)blockIdx.x, tid = (int)threadIdx.x, kp = tid & 63, ln = tid >> 6;
+    if (tid < C2) {
+        const double s = (double)st2.scale[tid], rm2 = (double)st2.rstd[tid] * (double)m2[tid];
+        const double w = (double)W2[tid * C1 + k];
+        swk[tid] = w;
+        sd[tid] = w * s * rm2;
+        se[tid] = w * s * (rm2 * (double)st2.mean[tid] - (double)m1[tid]);
     }
-    Kmat[k * C1 + kp] = (float)acc;
-    if (kp == 0) cvec[k] = (float)cv;
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll 8
+    for (int c = ln * 32; c < ln * 32 + 32; ++c) acc += sd[c] * (double)W2[c * C1 + kp];
+    part[ln][kp] = acc;
+    __syncthreads();
+    if (ln == 0) Kmat[k * C1 + kp] = (float)(((part[0][kp] + part[1][kp]) + part[2][kp]) + part[3][kp]);
+    if (tid == 0) {
+        double cv = 0.0;
+        for (int c = 0; c < C2; ++c) cv += se[c];
+        cvec[k] = (float)cv;
+    }
 }
 
 struct KbRefParams {

@@ -1,0 +1,301 @@
+// tc_ka.cuh -- tcgen05 layer-2 backward pass 1 fused with the Gram matrix of a2 ("K_A").
+//
+//   d a2[P][c] = sparse[P][c] - u_c - sum_j Q[c][j] a2[P][j]        (layer-3 backward collapse, tower.cuh / DESIGN.md)
+//   dz2 = d a2 . [a2 > 0]  (stored, fp32)      BatchNorm2-backward sums  sum dz2, sum dz2 yhat2,  max |dz2|
+//   Gram = sum_P a2 a2^T   as  hi.hi  and  hi.lo  accumulators (Gram = hh + hl + hl^T: the third pass is the transpose
+//   of the second)
+//
+// Same structure as tc_kb.cuh: one persistent CTA per SM, 64-point tiles that never straddle a cloud; per tile the
+// loader warp bulk-copies the raw u2 rows (32 KB) into the operand buffer and the <= 64 sparse rows of d a2 that the
+// tile's points own into a staging buffer (it reads the tile's slot indices itself, one tile ahead); 8 converter
+// warps turn u2 into the a2 = relu(bn2(u2)) hi/lo fp16 operand tile IN PLACE; the epilogue (8 warps, channel = TMEM
+// lane) reads a2 back from the operand tile (mask, and yhat2 = (a2 - beta2)/gamma2 where a2 > 0) and the sparse
+// rows from shared memory, so it issues no global loads at all; its only global traffic are the dz2 stores.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_accum.cuh"
+
+namespace pgpd { namespace tc {
+
+constexpr int KA_NT = 64;
+constexpr int KA_THREADS = 576;                             // 8 epilogue + 8 converter warps, loader warp, MMA issuer
+constexpr int KA_Q_BYTES = 65536;                           // Q image [kb][part][128 rows][128 B]
+constexpr int KA_OP_BYTES = 32768;                          // a2 tile [part][kb][64 rows][128 B]   (raw: [64][128] fp32)
+constexpr int KA_SP_BYTES = 32768;                          // sparse rows of the tile [64][128] fp32 (only owned rows are filled)
+constexpr int KA_BUF_BYTES = KA_OP_BYTES + KA_SP_BYTES;
+constexpr int KA_OFF_BUF = KA_Q_BYTES;
+constexpr int KA_OFF_SLOT = KA_OFF_BUF + 2 * KA_BUF_BYTES;  // [2][64] int
+constexpr int KA_OFF_MISC = KA_OFF_SLOT + 2 * KA_NT * 4;
+constexpr int KA_SMEM_BYTES = KA_OFF_MISC + 256 + 1024;
+constexpr int KA_EPI_ROWS = 2;                              // partial rows per CTA (two 32-column halves)
+
+struct KaParams {
+    const __half* Qimg; const float* inv;                   // pre-packed Q (k_prepack_rows, extra shift ACT_SHIFT) and its row scales
+    const float* uvec; const float* scale2; const float* shift2; const float* gamma2; const float* beta2;
+    const float* Y2; const float* da2s; const int* slot;
+    int B, N, tiles_per_cloud, ntiles;
+    float* DZ2;
+    float* part;      // [gridDim.x * 2][2][128]   sum dz2, sum dz2*yhat2
+    float* pmax;      // [gridDim.x * 2][2][128]   max |dz2|, (unused, 0)
+    float* gpart;     // [gridDim.x][2][128*128]   Gram partials: hi.hi, hi.lo   (accumulator units: x 256)
+};
+
+__global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* misc = smem + KA_OFF_MISC;
+    const uint32_t bar0 = sbase + KA_OFF_MISC;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // 0 q_full | 1,2 full | 3,4 op_ready | 5,6 acc_full | 7,8 buf_empty | 9 final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+    int* s_slot = reinterpret_cast<int*>(smem + KA_OFF_SLOT);        // [2][64]
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(BAR(0), 1);
+        mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
+        mbar_init(BAR(3), 256); mbar_init(BAR(4), 256);
+        mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
+        mbar_init(BAR(7), 257); mbar_init(BAR(8), 257);
+        mbar_init(BAR(9), 1);
+        mbar_fence_init();
+    }
+    if (warp == 17) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+
+    if (warp == 16) {
+        // ===================== loader (whole warp: lane l owns points 2l, 2l+1 of the tile) =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(BAR(0), KA_Q_BYTES);
+            bulk_g2s(sbase, p.Qimg, KA_Q_BYTES, BAR(0));
+        }
+        auto tile_slots = [&](int t, int& s0, int& s1) {
+            s0 = -1; s1 = -1;
+            if (t < t_end) {
+                const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
+                const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
+                const size_t P0 = (size_t)cb * p.N + n0;
+                if (2 * lane < nv) s0 = __ldg(p.slot + P0 + 2 * lane);
+                if (2 * lane + 1 < nv) s1 = __ldg(p.slot + P0 + 2 * lane + 1);
+            }
+        };
+        int s0, s1;
+        tile_slots(t_begin, s0, s1);
+        int i = 0;
+        for (int t = t_begin; t < t_end; ++t, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            int n0s, n1s;
+            tile_slots(t + 1, n0s, n1s);                    // next tile's slot indices: in flight while this tile is issued
+            if (lane == 0) {
+                const int tp = t + 3;                       // tile t+3 -> L2
+                if (tp < t_end) {
+                    const int cb = tp / p.tiles_per_cloud, tt = tp % p.tiles_per_cloud, n0 = tt * KA_NT;
+                    const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
+                    l2_prefetch(p.Y2 + ((size_t)cb * p.N + n0) * C2, (uint32_t)nv * C2 * 4u);
+                }
+            }
+            const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
+            const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
+            const size_t P0 = (size_t)cb * p.N + n0;
+            mbar_wait(BAR(7 + b), ph ^ 1);
+            s_slot[b * KA_NT + 2 * lane] = s0;
+            s_slot[b * KA_NT + 2 * lane + 1] = s1;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, s0 >= 0)) + __popc(__ballot_sync(0xffffffffu, s1 >= 0));
+            __syncwarp();
+            const uint32_t dst = sbase + KA_OFF_BUF + b * KA_BUF_BYTES;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)(nv + cnt) * C2 * 4u);
+                bulk_g2s(dst, p.Y2 + P0 * C2, (uint32_t)nv * C2 * 4u, BAR(1 + b));
+            }
+            __syncwarp();
+            if (s0 >= 0) bulk_g2s(dst + KA_OP_BYTES + (uint32_t)(2 * lane) * 512u, p.da2s + (size_t)s0 * C2, 512u, BAR(1 + b));
+            if (s1 >= 0) bulk_g2s(dst + KA_OP_BYTES + (uint32_t)(2 * lane + 1) * 512u, p.da2s + (size_t)s1 * C2, 512u, BAR(1 + b));
+            s0 = n0s; s1 = n1s;
+        }
+    } else if (warp == 17) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC_K = idesc_f16(128, KA_NT);
+            constexpr uint32_t IDESC_MN = idesc_f16_mn(128, 128);
+            mbar_wait(BAR(0), 0);
+            tc_fence_after_sync();
+            uint32_t first = 1;
+            int i = 0;
+            for (int t = t_begin; t < t_end; ++t, ++i) {
+                const int b = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(BAR(3 + b), ph);
+                tc_fence_after_sync();
+                const uint32_t op = sbase + KA_OFF_BUF + b * KA_BUF_BYTES;
+                const uint32_t d1 = tmem + (uint32_t)(b * KA_NT);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint32_t a_hi = sbase + (kb * 2 + 0) * 16384, a_lo = sbase + (kb * 2 + 1) * 16384;
+                    const uint32_t b_hi = op + (0 * 2 + kb) * 8192, b_lo = op + (1 * 2 + kb) * 8192;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
+                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16(d1, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC_K,
+                                    (kb | pass | k) ? 1u : 0u);
+                    }
+                }
+                mma_commit(BAR(5 + b));
+                // Gram: hh += a2_hi^T a2_hi,  hl += a2_hi^T a2_lo   (K = the tile's 64 points; both operands MN-major,
+                // the two 64-channel atoms of a part are 8 KB apart)
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint32_t dg = tmem + 128u + (uint32_t)(pass * 128);
+                    const uint32_t wb = pass ? op + 16384 : op;
+#pragma unroll
+                    for (int k = 0; k < KA_NT / 16; ++k)
+                        mma_f16(dg, desc_sw128_mnmajor(op + k * 2048, 8192), desc_sw128_mnmajor(wb + k * 2048, 8192), IDESC_MN,
+                                (first && k == 0) ? 0u : 1u);
+                }
+                first = 0;
+                mma_commit(BAR(7 + b));
+            }
+            mma_commit(BAR(9));
+        }
+    } else if (warp < 8) {
+        // ===================== epilogue: channel c = TMEM lane, 32 of the tile's 64 points per warp =====================
+        const int q = warp & 3, half = warp >> 2;
+        const int c = q * 32 + lane;
+        const float inv = p.inv[c], u = p.uvec[c], be = p.beta2[c];
+        const float gm = p.gamma2[c], g2inv = gm != 0.f ? 1.0f / gm : 0.f;
+        const uint32_t coff = (uint32_t)((c & 7) * 2), cchunk = (uint32_t)((c & 63) >> 3), ckb = (uint32_t)(c >> 6);
+        float s1 = 0.f, s2 = 0.f, mxdz = 0.f;
+        int i = 0;
+        for (int t = t_begin; t < t_end; ++t, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
+            const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
+            const size_t P0 = (size_t)cb * p.N + n0;
+            mbar_wait(BAR(5 + b), ph);
+            tc_fence_after_sync();
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KA_NT + half * 32), v);
+            const unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES + ckb * 8192;
+            const float* sp = reinterpret_cast<const float*>(smem + KA_OFF_BUF + b * KA_BUF_BYTES + KA_OP_BYTES);
+            const int* sl = s_slot + b * KA_NT;
+            float* dzo = p.DZ2 + P0 * C2 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int pp = half * 32 + j;
+                if (pp < nv) {
+                    const uint32_t off = (uint32_t)pp * 128u + ((cchunk ^ (uint32_t)(pp & 7)) << 4) + coff;
+                    const float a = (__half2float(*reinterpret_cast<const __half*>(opb + off)) +
+                                     __half2float(*reinterpret_cast<const __half*>(opb + 16384 + off))) * (1.0f / ACT_SCALE);
+                    float da2 = -v[j] * inv - u;
+                    if (sl[pp] >= 0) da2 += sp[pp * C2 + c];
+                    const float dz = a > 0.f ? da2 : 0.f;
+                    dzo[(size_t)pp * C2] = dz;
+                    const float yh = (a - be) * g2inv;      // only used where dz != 0
+                    s1 += dz;
+                    s2 = fmaf(dz, yh, s2);
+                    mxdz = fmaxf(mxdz, fabsf(dz));
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(BAR(7 + b));
+        }
+        const size_t row = (size_t)cta * KA_EPI_ROWS + half;
+        p.part[row * 2 * C2 + c] = s1; p.part[row * 2 * C2 + C2 + c] = s2;
+        p.pmax[row * 2 * C2 + c] = mxdz; p.pmax[row * 2 * C2 + C2 + c] = 0.f;
+    } else {
+        // ===================== converters: u2 rows -> a2 = relu(bn2(u2)) hi/lo operand tile, in place =====================
+        const int cw = warp - 8;                            // 0..7
+        float4 sc = *reinterpret_cast<const float4*>(p.scale2 + 4 * lane);
+        float4 sh = *reinterpret_cast<const float4*>(p.shift2 + 4 * lane);
+        sc.x *= ACT_SCALE; sc.y *= ACT_SCALE; sc.z *= ACT_SCALE; sc.w *= ACT_SCALE;
+        sh.x *= ACT_SCALE; sh.y *= ACT_SCALE; sh.z *= ACT_SCALE; sh.w *= ACT_SCALE;
+        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
+        int i = 0;
+        for (int t = t_begin; t < t_end; ++t, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
+            const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
+            mbar_wait(BAR(1 + b), ph);
+            unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES;
+            float4 ry[8];
+#pragma unroll
+            for (int uu = 0; uu < 8; ++uu) ry[uu] = *reinterpret_cast<const float4*>(opb + (cw * 8 + uu) * 512 + lane * 16);
+            named_bar_sync(1, 256);                         // every converter thread has read its raw rows
+#pragma unroll
+            for (int uu = 0; uu < 8; ++uu) {
+                const int r = cw * 8 + uu;
+                const bool ok = r < nv;
+                const float a0 = ok ? fminf(fmaxf(fmaf(sc.x, ry[uu].x, sh.x), 0.f), 60000.f) : 0.f;
+                const float a1 = ok ? fminf(fmaxf(fmaf(sc.y, ry[uu].y, sh.y), 0.f), 60000.f) : 0.f;
+                const float a2 = ok ? fminf(fmaxf(fmaf(sc.z, ry[uu].z, sh.z), 0.f), 60000.f) : 0.f;
+                const float a3 = ok ? fminf(fmaxf(fmaf(sc.w, ry[uu].w, sh.w), 0.f), 60000.f) : 0.f;
+                __half2 h01, l01, h23, l23;
+                split2(a0, a1, h01, l01);
+                split2(a2, a3, h23, l23);
+                const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(opb + (0 * 2 + kb) * 8192 + off) = hv;
+                *reinterpret_cast<uint2*>(opb + (1 * 2 + kb) * 8192 + off) = lv;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(BAR(3 + b));
+        }
+    }
+
+    // ===================== read-out of the Gram accumulators (warps 0..15) =====================
+    if (warp < 16) {
+        const int q = warp & 3, cg = warp >> 2, row = q * 32 + lane;
+        mbar_wait(BAR(9), 0);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            float* out = p.gpart + ((size_t)cta * 2 + part) * (C2 * C2) + (size_t)row * C2 + cg * 32;
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(part * 128 + cg * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc<512>(tmem);
+}
+
+// gram[m][n] = (hh[m][n] + hl[m][n] + hl[n][m]) / 256  from the reduced partial sums [2][128*128]
+__global__ void k_gram_sym(const float* __restrict__ hh_hl, float* __restrict__ gram) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= C2 * C2) return;
+    const int m = i >> 7, n = i & 127;
+    gram[i] = (hh_hl[i] + hh_hl[C2 * C2 + i] + hh_hl[C2 * C2 + n * C2 + m]) * (1.0f / (ACT_SCALE * ACT_SCALE));
+}
+
+inline int launch_ka(const KaParams& p, int sms, cudaStream_t s) {
+    static int done[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 63]) {
+        cudaFuncSetAttribute(k_ka_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KA_SMEM_BYTES);
+        done[dev & 63] = 1;
+    }
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    launch(k_ka_tc, dim3(grid), dim3(KA_THREADS), (size_t)KA_SMEM_BYTES, s, p);
+    return grid;
+}
+
+}}  // namespace pgpd::tc

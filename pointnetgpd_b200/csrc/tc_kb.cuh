@@ -137,6 +137,13 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+    // tuning aid (pgpd_debug_stream_counters): 0 loader wait buf_empty | 1 load latency (issue -> landed, seen by a converter)
+    // 2 converter work | 3 mma wait op_ready | 4 mma issue | 5 epilogue wait acc_full | 6 epilogue work | 7 total
+    long long* const dbg = g_stream_dbg;
+    long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    volatile long long* s_clk = reinterpret_cast<volatile long long*>(misc + 160);      // [2] issue time of the buffer's loads
+    const long long tk0 = dbg ? clock64() : 0;
+#define KB_T(slot, call) do { const long long _t0 = dbg ? clock64() : 0; call; if (dbg) dacc[slot] += clock64() - _t0; } while (0)
 
     if (warp == 16) {
         // ===================== loader =====================
@@ -161,12 +168,14 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
                 const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
                 const size_t P0 = (size_t)cb * p.N + n0;
-                mbar_wait(BAR(7 + b), ph ^ 1);
+                KB_T(0, mbar_wait(BAR(7 + b), ph ^ 1));
+                if (dbg) s_clk[b] = clock64();
                 mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)nv * (C2 + C1) * 4u);
                 const uint32_t dst = sbase + KB_OFF_BUF + b * KB_BUF_BYTES;
                 bulk_g2s(dst, p.DZ2 + P0 * C2, (uint32_t)nv * C2 * 4u, BAR(1 + b));
                 bulk_g2s(dst + KB_DZ_BYTES, p.A1 + P0 * C1, (uint32_t)nv * C1 * 4u, BAR(1 + b));
             }
+            if (dbg) dbg[cta * 8 + 0] = dacc[0];
         }
     } else if (warp == 17) {
         // ===================== MMA issuer =====================
@@ -180,8 +189,9 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             for (int t = t_begin; t < t_end; ++t, ++i) {
                 const int b = i & 1;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                mbar_wait(BAR(3 + b), ph);
+                KB_T(3, mbar_wait(BAR(3 + b), ph));
                 tc_fence_after_sync();
+                const long long ti0 = dbg ? clock64() : 0;
                 const uint32_t dz = sbase + KB_OFF_BUF + b * KB_BUF_BYTES, a1 = dz + KB_DZ_BYTES;
                 const uint32_t d1 = tmem + (uint32_t)(b * KB_NT);
                 // ---- D1 = A1op x dz (K = 128 channels)
@@ -240,8 +250,10 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 }
                 first = 0;
                 mma_commit(BAR(7 + b));                     // the tensor core is done reading this buffer
+                if (dbg) dacc[4] += clock64() - ti0;
             }
             mma_commit(BAR(9));
+            if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
     } else if ((warp & 3) < 2) {
         // ===================== epilogue: feature k = TMEM lane, 16 of the tile's 64 points per warp =====================
@@ -257,8 +269,9 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
             const int tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
             const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
-            mbar_wait(BAR(5 + b), ph);
+            KB_T(5, mbar_wait(BAR(5 + b), ph));
             tc_fence_after_sync();
+            const long long te0 = dbg ? clock64() : 0;
             float v[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KB_NT + cgp * 16), v);
             const unsigned char* a1b = smem + KB_OFF_BUF + b * KB_BUF_BYTES + KB_DZ_BYTES;
@@ -283,7 +296,9 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             h[0] = h0; h[1] = h1; h[2] = h2;
             tc_fence_before_sync();
             mbar_arrive(BAR(7 + b));
+            if (dbg) dacc[6] += clock64() - te0;
         }
+        if (dbg && warp == 0 && lane == 0) { dbg[cta * 8 + 5] = dacc[5]; dbg[cta * 8 + 6] = dacc[6]; dbg[cta * 8 + 7] = clock64() - tk0; }
         float* o = p.bnpart + ((size_t)cta * KB_EPI_GROUPS + cgp) * 2 * C1;
         o[k] = s1; o[C1 + k] = s2;
     } else {
@@ -303,6 +318,8 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 if (pp < nv) xv = __ldg(p.x + (size_t)cb * 3 * p.N + (size_t)j * p.N + n0 + pp);
             }
             mbar_wait(BAR(1 + b), ph);
+            const long long tc0 = dbg ? clock64() : 0;
+            if (dbg) dacc[1] += tc0 - s_clk[b];
             unsigned char* dzb = smem + KB_OFF_BUF + b * KB_BUF_BYTES;
             unsigned char* a1b = dzb + KB_DZ_BYTES;
             float4 rdz[8], ra[4];
@@ -356,8 +373,11 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             }
             fence_proxy_async_smem();
             mbar_arrive(BAR(3 + b));
+            if (dbg) dacc[2] += clock64() - tc0;
         }
+        if (dbg && cw == 0 && lane == 0) { dbg[cta * 8 + 1] = dacc[1]; dbg[cta * 8 + 2] = dacc[2]; }
     }
+#undef KB_T
 
     // ===================== read-out of the persistent accumulators (warps 0..15: all four TMEM lane quadrants) ==========
     if (warp < 16) {

@@ -25,6 +25,8 @@
 #include "tc_stream.cuh"
 #include "tc_accum.cuh"
 #include "tc_kb.cuh"
+#include "tc_ka.cuh"
+#include "tc_kf.cuh"
 #endif
 
 namespace pgpd {
@@ -76,6 +78,8 @@ struct TowerScratch {
     float* dvec;      // [1024]
     float* evec;      // [1024]
     float* gram;      // [128*128]
+    float* gram2;     // [2][128*128] reduced hi.hi / hi.lo Gram accumulators of the fused pass-1 kernel
+    float* ka_part;   // [512][2][128] BatchNorm2-backward partial sums of the tcgen05 pass-1 kernels
     float* WG;        // [1024*128]
     float* Q;         // [128*128]
     float* uvec;      // [128]
@@ -143,7 +147,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         fp = std::max(fp, (size_t)w.nb_l2 * 2 * C2);                         // BN2 backward partials
         fp = std::max(fp, (size_t)w.nb_dw2 * C2 * C1);                       // dW2 partials
         fp = std::max(fp, (size_t)B * (C1 * 3));                             // dW1 partials
-        fp = std::max(fp, TC_MAX_CTAS * C2 * C2);                            // per-CTA Gram / dW2 / BN-backward partials
+        fp = std::max(fp, 2 * TC_MAX_CTAS * C2 * C2);                        // per-CTA Gram (hi.hi, hi.lo) / BN-backward partials
     }
     w.fpart_elems = fp;
     w.fpart = c.take<float>(fp);
@@ -161,6 +165,8 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         w.dvec = c.take<float>(C3);
         w.evec = c.take<float>(C3);
         w.gram = c.take<float>(C2 * C2);
+        w.gram2 = c.take<float>(2 * C2 * C2);
+        w.ka_part = c.take<float>((size_t)512 * 2 * C2);
         w.WG = c.take<float>((size_t)C3 * C2);
         w.Q = c.take<float>(C2 * C2);
         w.uvec = c.take<float>(C2);
@@ -437,17 +443,18 @@ __global__ void k_pool_finalize(const unsigned long long* __restrict__ keys, con
 // backward kernels
 // ================================================================================================
 
-// BatchNorm3 / max-pool backward on the pooled values.  block = 32 channels x 8 cloud lanes.
+// BatchNorm3 / max-pool backward on the pooled values.  block = 32 channels x 32 cloud lanes.
 __global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict__ uext, int B, int relu_last,
                            double count, const float* __restrict__ gamma, BnState st,
                            float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
                            float* __restrict__ dvec, float* __restrict__ evec) {
-    __shared__ double sh1[8][33], sh2[8][33];
+    __shared__ double sh1[32][33], sh2[32][33];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
     const float sc = st.scale[c], sf = st.shift[c], mu = st.mean[c], r = st.rstd[c];
     double sdz = 0.0, sdzy = 0.0;
-    for (int b = ry; b < B; b += 8) {
+#pragma unroll 4
+    for (int b = ry; b < B; b += 32) {
         const size_t i = (size_t)b * C3 + c;
         const float u = uext[i];
         float dz = dG[i];
@@ -461,7 +468,8 @@ __global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict
     __syncthreads();
     if (ry == 0) {
         double t1 = 0.0, t2 = 0.0;
-        for (int q = 0; q < 8; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
         dgamma[c] = (float)t2;
         dbeta[c] = (float)t1;
         const double m1 = t1 / count, m2 = t2 / count;
@@ -535,18 +543,20 @@ struct ProbDense {
     }
 };
 
-// uvec[i] = sum_c W3[c][i] * e[c];  grid = 4 blocks of 32 columns x 8 row lanes
+// uvec[i] = sum_c W3[c][i] * e[c];  grid = 4 blocks of 32 columns x 32 row lanes (fixed-order reduction)
 __global__ void k_uvec(const float* __restrict__ W3, const float* __restrict__ e, float* __restrict__ uvec) {
-    __shared__ double sh[8][33];
+    __shared__ double sh[32][33];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int i = (int)blockIdx.x * 32 + cx;
     double s = 0.0;
-    for (int c = ry; c < C3; c += 8) s += (double)W3[(size_t)c * C2 + i] * (double)e[c];
+#pragma unroll 8
+    for (int c = ry; c < C3; c += 32) s += (double)W3[(size_t)c * C2 + i] * (double)e[c];
     sh[ry][cx] = s;
     __syncthreads();
     if (ry == 0) {
         double t = 0.0;
-        for (int q = 0; q < 8; ++q) t += sh[q][cx];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) t += sh[q][cx];
         uvec[i] = (float)t;
     }
 }
@@ -917,17 +927,25 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     if (a.train) {
         const int S = colreduce<double>(w.dpart, w.nb_a1, C1, w.rtmp, s);
         launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, w.S1a);
-        launch(k_matvec_mean, dim3(1), dim3(128), 0, s, t.conv[1].w, C2, C1, (const double*)w.S1a, 1.0 / count, w.bn[1].mean);
+        launch(k_matvec_mean, dim3(C2 / 8), dim3(256), 0, s, t.conv[1].w, C2, C1, (const double*)w.S1a, 1.0 / count, w.bn[1].mean);
     }
     int n_css2 = 0;
 #ifndef PGPD_EMU
     if (a.use_tc && (tc_mask() & 2)) {
         launch(tc::k_prepack_rows, dim3(128), dim3(C1), 0, s, t.conv[1].w, C1, 1, C2, C1, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
-        const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
-        tc::L2FwdTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.A1, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
-                              w.Y2, w.fpart};
-        tc::launch_stream<tc::L2FwdTC>(p, tc::dev_info().sms, s);
-        n_css2 = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
+        static const bool use_kf = !(getenv("PGPD_KF") && atoi(getenv("PGPD_KF")) == 0);
+        if (use_kf) {
+            const int tpc = idiv_up(a.N, tc::KF_NT), ntiles = a.B * tpc;
+            tc::KfParams p{(const __half*)w.wimg_s, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
+                           w.A1, w.Y2, w.fpart, a.B, a.N, tpc, ntiles};
+            n_css2 = tc::KF_EPI_ROWS * tc::launch_kf(p, tc::dev_info().sms, s);
+        } else {
+            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
+            tc::L2FwdTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.A1, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
+                                  w.Y2, w.fpart};
+            tc::launch_stream<tc::L2FwdTC>(p, tc::dev_info().sms, s);
+            n_css2 = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
+        }
     } else
 #endif
     {
@@ -943,7 +961,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         launch(k_a2_sum, dim3(w.nb_a2), dim3(256), 0, s, (const float*)w.Y2, M, w.bn[1], w.dpart);
         const int S2 = colreduce<double>(w.dpart, w.nb_a2, C2, w.rtmp, s);
         launch(k_reduce_d, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S2, C2, w.S1);
-        launch(k_matvec_mean, grid1d(C3, 128), dim3(128), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.bn[2].mean);
+        launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.bn[2].mean);
     }
 
     // ---- layer 3 + max-pool ------------------------------------------------------------------------
@@ -1002,11 +1020,69 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     const double count = (double)M;
 
     // ---- BN3 / max-pool on the pooled values ---------------------------------------------------------
-    launch(k_pool_bwd, dim3(C3 / 32), dim3(256), 0, s, dpooled, (const float*)w.uext, a.B, a.relu_last ? 1 : 0, count,
+    launch(k_pool_bwd, dim3(C3 / 32), dim3(1024), 0, s, dpooled, (const float*)w.uext, a.B, a.relu_last ? 1 : 0, count,
            t.bn[2].gamma, w.bn[2], w.coef, g.bn[2].dgamma, g.bn[2].dbeta, w.dvec, w.evec);
 
-    // ---- Gram matrix of a2 -------------------------------------------------------------------------
+    // Q = W3^T diag(d) W3  [128 x 128], K = 1024 split in 16 slices (blockIdx.z) and reduced deterministically
     {
+        ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.fpart, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
+        p.kslice = C3 / 16;
+        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64, 16), s);
+        const int S = colreduce<float>(w.fpart, 16, C2 * C2, w.rtmp, s);
+        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.Q);
+    }
+    launch(k_uvec, dim3(C2 / 32), dim3(1024), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
+
+    // ---- sparse part of d a2 -----------------------------------------------------------------------
+    cudaMemsetAsync(w.slot, 0xFF, M * sizeof(int), s);
+    launch(k_da2_sparse, dim3(a.B), dim3(C3), 0, s, (const float*)w.coef, (const int*)w.idx, t.conv[2].w, a.N, w.da2s, w.slot);
+
+    // ---- layer 2 backward pass 1 (d a2 -> dz2, BatchNorm2 backward sums) and the Gram matrix of a2 -----------------------
+    // tcgen05: ONE kernel (tc_ka.cuh) unless PGPD_KA=0 selects the older pair (streaming GEMM + separate Gram kernel)
+    int g_b4 = 0;   // rows of pmax written by the tcgen05 pass-1 kernel
+    bool gram_done = false;
+    {
+        int nrows = 0;
+        const float* bnpart = w.fpart;
+#ifndef PGPD_EMU
+        static const bool use_ka = !(getenv("PGPD_KA") && atoi(getenv("PGPD_KA")) == 0);
+        if (a.use_tc && (tc_mask() & 8) && use_ka) {
+            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
+            const int tpc = idiv_up(a.N, tc::KA_NT), ntiles = a.B * tpc;
+            tc::KaParams p{(const __half*)w.wimg_s, w.inv_s, w.uvec, w.bn[1].scale, w.bn[1].shift, t.bn[1].gamma, t.bn[1].beta,
+                           w.Y2, w.da2s, w.slot, a.B, a.N, tpc, ntiles, w.DZ2, w.ka_part, w.pmax, w.fpart};
+            const int grid = tc::launch_ka(p, tc::dev_info().sms, s);
+            nrows = grid * tc::KA_EPI_ROWS;
+            g_b4 = nrows;
+            bnpart = w.ka_part;
+            // Gram = hh + hl + hl^T from the per-CTA accumulators
+            const int S = colreduce<float>(w.fpart, grid, 2 * C2 * C2, w.rtmp, s);
+            launch(k_reduce_f, grid1d(2 * C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, 2 * C2 * C2, w.gram2);
+            launch(tc::k_gram_sym, grid1d(C2 * C2, 256), dim3(256), 0, s, (const float*)w.gram2, w.gram);
+            gram_done = true;
+        } else if (a.use_tc && (tc_mask() & 8)) {
+            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
+            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
+            tc::L2BwdATC::Params p{(const __half*)w.wimg_s, M, ntiles, w.Y2, w.bn[1].scale, w.bn[1].shift, w.bn[1].mean, w.bn[1].rstd,
+                                   w.inv_s, w.uvec, w.da2s, w.slot, w.DZ2, w.ka_part, w.pmax};
+            tc::launch_stream<tc::L2BwdATC>(p, tc::dev_info().sms, s);
+            nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
+            g_b4 = nrows;
+            bnpart = w.ka_part;
+        } else
+#endif
+        {
+            ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
+            launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
+            nrows = w.nb_l2;
+        }
+        const int S = colreduce<float>(bnpart, nrows, 2 * C2, w.rtmp, s);
+        launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2, count,
+               g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
+    }
+
+    // ---- Gram matrix of a2 (if the pass above did not produce it), W3 Gram, dW3 -----------------------------------------
+    if (!gram_done) {
         int nrows = 0;
 #ifndef PGPD_EMU
         if (a.use_tc && (tc_mask() & 4)) {
@@ -1027,50 +1103,13 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         ProbDense<true, true> p{t.conv[2].w, w.gram, w.WG, nullptr, C3, C2, C2, (size_t)C2, 1, (size_t)C2, 1, (size_t)C2};
         launch_gemm<CfgSmall>(p, dim3(C2 / 64, C3 / 64), s);
     }
-    // Q = W3^T diag(d) W3  [128 x 128], K = 1024 split in 16 slices (blockIdx.z) and reduced deterministically
-    {
-        ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.fpart, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
-        p.kslice = C3 / 16;
-        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64, 16), s);
-        const int S = colreduce<float>(w.fpart, 16, C2 * C2, w.rtmp, s);
-        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.Q);
-    }
-    launch(k_uvec, dim3(C2 / 32), dim3(256), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
     launch(k_dw3, dim3(C3), dim3(4 * C2), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
            (const float*)w.dvec, (const float*)w.evec, (const float*)w.WG, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
 
-    // ---- sparse part of d a2 -----------------------------------------------------------------------
-    cudaMemsetAsync(w.slot, 0xFF, M * sizeof(int), s);
-    launch(k_da2_sparse, dim3(a.B), dim3(C3), 0, s, (const float*)w.coef, (const int*)w.idx, t.conv[2].w, a.N, w.da2s, w.slot);
-
-    // ---- layer 2 backward ---------------------------------------------------------------------------
-    int g_b4 = 0;   // CTAs of the tcgen05 pass-1 kernel (rows of pmax)
-    {
-        int nrows = 0;
-#ifndef PGPD_EMU
-        if (a.use_tc && (tc_mask() & 8)) {
-            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
-            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
-            tc::L2BwdATC::Params p{(const __half*)w.wimg_s, M, ntiles, w.Y2, w.bn[1].scale, w.bn[1].shift, w.bn[1].mean, w.bn[1].rstd,
-                                   w.inv_s, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, w.pmax};
-            tc::launch_stream<tc::L2BwdATC>(p, tc::dev_info().sms, s);
-            nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
-            g_b4 = nrows;
-        } else
-#endif
-        {
-            ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
-            launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
-            nrows = w.nb_l2;
-        }
-        const int S = colreduce<float>(w.fpart, nrows, 2 * C2, w.rtmp, s);
-        launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2, count,
-               g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
-    }
     // ---- layers 2 and 1, fused pass over (dz2, a1) (l2bwd.cuh); PGPD_KB=0 selects the older three-kernel form ----
     static const bool use_kb = !(getenv("PGPD_KB") && atoi(getenv("PGPD_KB")) == 0);
     if (use_kb) {
-        launch(k_kb_prep, dim3(C1), dim3(C1), 0, s, t.conv[1].w, w.bn[1], (const float*)w.m1_2, (const float*)w.m2_2, w.Kmat, w.cvec);
+        launch(k_kb_prep, dim3(C1), dim3(256), 0, s, t.conv[1].w, w.bn[1], (const float*)w.m1_2, (const float*)w.m2_2, w.Kmat, w.cvec);
         int nparts = 0, nrows = 0, rpc = 0;
 #ifndef PGPD_EMU
         if (a.use_tc && (tc_mask() & 16) && g_b4 > 0) {

@@ -1,0 +1,32 @@
+"""Pipeline cycle accounting of the fused layer-2/1 backward kernel (k_kb_tc): last launch of a train step = STN tower."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import weights as W
+from pointnetgpd_b200 import _abi as A
+from pointnetgpd_b200.model.pointnet import PointNetCls
+B, N = 512, 1024
+st = W.make_state(0, k=2)
+m = PointNetCls(N, 3, 2); m.load_state_dict({k: torch.tensor(v) for k, v in st.items()}); m = m.cuda().train()
+x = torch.tensor(W.make_clouds(1, B, N, "box")).cuda()
+y = torch.tensor(W.make_labels(2, B, 2)).cuda()
+lib = A.load()
+def step():
+    m.zero_grad()
+    logp, _ = m(x)
+    torch.nn.functional.nll_loss(logp, y).backward()
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+lib.pgpd_debug_stream_counters(1)
+step()
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (256 * 8))()
+lib.pgpd_debug_l3_counters.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+lib.pgpd_debug_l3_counters(buf)
+lib.pgpd_debug_stream_counters(0)
+a = np.array(buf[:], dtype=np.int64).reshape(256, 8)[:148]
+names = ["loader wait buf_empty", "load latency (issue->landed)", "converter work", "mma wait op_ready", "mma issue", "epi wait acc_full", "epi work", "total"]
+tiles = (B * (N // 64)) / 148
+for i, n in enumerate(names):
+    print("%-30s mean %10.0f cycles/CTA   %8.0f per tile" % (n, a[:, i].mean(), a[:, i].mean() / tiles))
