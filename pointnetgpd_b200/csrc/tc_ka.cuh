@@ -8,7 +8,7 @@
 // Same structure as tc_kb.cuh: one persistent CTA per SM, 64-point tiles that never straddle a cloud; per tile the
 // loader warp bulk-copies the raw u2 rows (32 KB) into the operand buffer and the <= 64 sparse rows of d a2 that the
 // tile's points own into a staging buffer (it reads the tile's slot indices itself, one tile ahead); 8 converter
-// warps turn u2 into the a2 = relu(bn2(u2)) hi/lo fp16 operand tile IN PLACE; the epilogue (8 warps, channel = TMEM
+// warps turn u2 into the a2 = relu(bn2(u2)) hi/lo fp16 operand tile IN PLACE; the epilogue (16 warps, channel = TMEM
 // lane) reads a2 back from the operand tile (mask, and yhat2 = (a2 - beta2)/gamma2 where a2 > 0) and the sparse
 // rows from shared memory, so it issues no global loads at all; its only global traffic are the dz2 stores.
 #pragma once
@@ -19,7 +19,7 @@
 namespace pgpd { namespace tc {
 
 constexpr int KA_NT = 64;
-constexpr int KA_THREADS = 576;                             // 8 epilogue + 8 converter warps, loader warp, MMA issuer
+constexpr int KA_THREADS = 832;                             // 16 epilogue + 8 converter warps, loader warp, MMA issuer
 constexpr int KA_Q_BYTES = 65536;                           // Q image [kb][part][128 rows][128 B]
 constexpr int KA_OP_BYTES = 32768;                          // a2 tile [part][kb][64 rows][128 B]   (raw: [64][128] fp32)
 constexpr int KA_SP_BYTES = 32768;                          // sparse rows of the tile [64][128] fp32 (only owned rows are filled)
@@ -28,7 +28,7 @@ constexpr int KA_OFF_BUF = KA_Q_BYTES;
 constexpr int KA_OFF_SLOT = KA_OFF_BUF + 2 * KA_BUF_BYTES;  // [2][64] int
 constexpr int KA_OFF_MISC = KA_OFF_SLOT + 2 * KA_NT * 4;
 constexpr int KA_SMEM_BYTES = KA_OFF_MISC + 256 + 1024;
-constexpr int KA_EPI_ROWS = 2;                              // partial rows per CTA (two 32-column halves)
+constexpr int KA_EPI_ROWS = 4;                              // partial rows per CTA (four 16-column groups)
 
 struct KaParams {
     const __half* Qimg; const float* inv;                   // pre-packed Q (k_prepack_rows, extra shift ACT_SHIFT) and its row scales
@@ -36,8 +36,8 @@ struct KaParams {
     const float* Y2; const float* da2s; const int* slot;
     int B, N, tiles_per_cloud, ntiles;
     float* DZ2;
-    float* part;      // [gridDim.x * 2][2][128]   sum dz2, sum dz2*yhat2
-    float* pmax;      // [gridDim.x * 2][2][128]   max |dz2|, (unused, 0)
+    float* part;      // [gridDim.x * 4][2][128]   sum dz2, sum dz2*yhat2
+    float* pmax;      // [gridDim.x * 4][2][128]   max |dz2|, (unused, 0)
     float* gpart;     // [gridDim.x][2][128*128]   Gram partials: hi.hi, hi.lo   (accumulator units: x 256)
 };
 
@@ -58,11 +58,11 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
         mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
         mbar_init(BAR(3), 256); mbar_init(BAR(4), 256);
         mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-        mbar_init(BAR(7), 257); mbar_init(BAR(8), 257);
+        mbar_init(BAR(7), 513); mbar_init(BAR(8), 513);
         mbar_init(BAR(9), 1);
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc<512>(smem_u32(tmem_slot));
+    if (warp == 25) tmem_alloc<512>(smem_u32(tmem_slot));
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
 
-    if (warp == 16) {
+    if (warp == 24) {
         // ===================== loader (whole warp: lane l owns points 2l, 2l+1 of the tile) =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(BAR(0), KA_Q_BYTES);
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             if (s1 >= 0) bulk_g2s(dst + KA_OP_BYTES + (uint32_t)(2 * lane + 1) * 512u, p.da2s + (size_t)s1 * C2, 512u, BAR(1 + b));
             s0 = n0s; s1 = n1s;
         }
-    } else if (warp == 17) {
+    } else if (warp == 25) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t IDESC_K = idesc_f16(128, KA_NT);
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             mbar_wait(BAR(0), 0);
             tc_fence_after_sync();
             uint32_t first = 1;
+            const uint64_t dQ = desc_sw128_kmajor(sbase);
             int i = 0;
             for (int t = t_begin; t < t_end; ++t, ++i) {
                 const int b = i & 1;
@@ -137,18 +138,16 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
                 tc_fence_after_sync();
                 const uint32_t op = sbase + KA_OFF_BUF + b * KA_BUF_BYTES;
                 const uint32_t d1 = tmem + (uint32_t)(b * KA_NT);
+                const uint64_t kop = desc_sw128_kmajor(op), mop = desc_sw128_mnmajor(op, 8192);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
-                    const uint32_t a_hi = sbase + (kb * 2 + 0) * 16384, a_lo = sbase + (kb * 2 + 1) * 16384;
-                    const uint32_t b_hi = op + (0 * 2 + kb) * 8192, b_lo = op + (1 * 2 + kb) * 8192;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
-                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+                        const uint32_t oa = (uint32_t)((kb * 2 + (pass == 1 ? 1 : 0)) * 16384);
+                        const uint32_t ob = (uint32_t)(((pass == 2 ? 1 : 0) * 2 + kb) * 8192);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_f16(d1, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC_K,
-                                    (kb | pass | k) ? 1u : 0u);
+                            mma_f16(d1, dQ + ((oa + k * 32) >> 4), kop + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
                     }
                 }
                 mma_commit(BAR(5 + b));
@@ -157,20 +156,19 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     const uint32_t dg = tmem + 128u + (uint32_t)(pass * 128);
-                    const uint32_t wb = pass ? op + 16384 : op;
+                    const uint32_t ob = pass ? 16384u : 0u;
 #pragma unroll
                     for (int k = 0; k < KA_NT / 16; ++k)
-                        mma_f16(dg, desc_sw128_mnmajor(op + k * 2048, 8192), desc_sw128_mnmajor(wb + k * 2048, 8192), IDESC_MN,
-                                (first && k == 0) ? 0u : 1u);
+                        mma_f16(dg, mop + ((k * 2048) >> 4), mop + ((ob + k * 2048) >> 4), IDESC_MN, (first && k == 0) ? 0u : 1u);
                 }
                 first = 0;
                 mma_commit(BAR(7 + b));
             }
             mma_commit(BAR(9));
         }
-    } else if (warp < 8) {
-        // ===================== epilogue: channel c = TMEM lane, 32 of the tile's 64 points per warp =====================
-        const int q = warp & 3, half = warp >> 2;
+    } else if (warp < 16) {
+        // ===================== epilogue: channel c = TMEM lane, 16 of the tile's 64 points per warp =====================
+        const int q = warp & 3, cgp = warp >> 2;
         const int c = q * 32 + lane;
         const float inv = p.inv[c], u = p.uvec[c], be = p.beta2[c];
         const float gm = p.gamma2[c], g2inv = gm != 0.f ? 1.0f / gm : 0.f;
@@ -185,21 +183,27 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             const size_t P0 = (size_t)cb * p.N + n0;
             mbar_wait(BAR(5 + b), ph);
             tc_fence_after_sync();
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KA_NT + half * 32), v);
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KA_NT + cgp * 16), v);
             const unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES + ckb * 8192;
             const float* sp = reinterpret_cast<const float*>(smem + KA_OFF_BUF + b * KA_BUF_BYTES + KA_OP_BYTES);
             const int* sl = s_slot + b * KA_NT;
             float* dzo = p.DZ2 + P0 * C2 + c;
+            float av[16], sv[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int pp = half * 32 + j;
+            for (int j = 0; j < 16; ++j) {                  // a2 read back from the operand tile, sparse rows from the staging buffer
+                const int pp = cgp * 16 + j;
+                const uint32_t off = (uint32_t)pp * 128u + ((cchunk ^ (uint32_t)(pp & 7)) << 4) + coff;
+                av[j] = (__half2float(*reinterpret_cast<const __half*>(opb + off)) +
+                         __half2float(*reinterpret_cast<const __half*>(opb + 16384 + off))) * (1.0f / ACT_SCALE);
+                sv[j] = (sl[pp] >= 0) ? sp[pp * C2 + c] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int pp = cgp * 16 + j;
                 if (pp < nv) {
-                    const uint32_t off = (uint32_t)pp * 128u + ((cchunk ^ (uint32_t)(pp & 7)) << 4) + coff;
-                    const float a = (__half2float(*reinterpret_cast<const __half*>(opb + off)) +
-                                     __half2float(*reinterpret_cast<const __half*>(opb + 16384 + off))) * (1.0f / ACT_SCALE);
-                    float da2 = -v[j] * inv - u;
-                    if (sl[pp] >= 0) da2 += sp[pp * C2 + c];
+                    const float a = av[j];
+                    const float da2 = -v[j] * inv - u + sv[j];
                     const float dz = a > 0.f ? da2 : 0.f;
                     dzo[(size_t)pp * C2] = dz;
                     const float yh = (a - be) * g2inv;      // only used where dz != 0
@@ -211,12 +215,12 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             tc_fence_before_sync();
             mbar_arrive(BAR(7 + b));
         }
-        const size_t row = (size_t)cta * KA_EPI_ROWS + half;
+        const size_t row = (size_t)cta * KA_EPI_ROWS + cgp;
         p.part[row * 2 * C2 + c] = s1; p.part[row * 2 * C2 + C2 + c] = s2;
         p.pmax[row * 2 * C2 + c] = mxdz; p.pmax[row * 2 * C2 + C2 + c] = 0.f;
     } else {
         // ===================== converters: u2 rows -> a2 = relu(bn2(u2)) hi/lo operand tile, in place =====================
-        const int cw = warp - 8;                            // 0..7
+        const int cw = warp - 16;                           // 0..7
         float4 sc = *reinterpret_cast<const float4*>(p.scale2 + 4 * lane);
         float4 sh = *reinterpret_cast<const float4*>(p.shift2 + 4 * lane);
         sc.x *= ACT_SCALE; sc.y *= ACT_SCALE; sc.z *= ACT_SCALE; sc.w *= ACT_SCALE;
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 17) tmem_dealloc<512>(tmem);
+    if (warp == 25) tmem_dealloc<512>(tmem);
 }
 
 // gram[m][n] = (hh[m][n] + hl[m][n] + hl[n][m]) / 256  from the reduced partial sums [2][128*128]

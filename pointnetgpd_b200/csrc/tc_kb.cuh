@@ -21,7 +21,8 @@
 namespace pgpd { namespace tc {
 
 constexpr int KB_NT = 64;                                   // points per tile
-constexpr int KB_THREADS = 576;                             // 18 warps: 8 epilogue + 8 converter (interleaved), loader, MMA issuer
+constexpr int KB_THREADS = 832;                             // 26 warps: 8 epilogue + 16 converter, loader, MMA issuer
+constexpr int KB_CONV_THREADS = 512;
 constexpr int KB_A1_BYTES = 65536;                          // W2^T image  [kb][part][128 rows][128 B]
 constexpr int KB_A2_BYTES = 32768;                          // -K image        [part][128 rows][128 B]
 constexpr int KB_DZ_BYTES = 32768;                          // dz2 tile    [part][kb][64 rows][128 B]  (raw: [64][128] fp32)
@@ -123,13 +124,13 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     if (tid == 0) {
         mbar_init(BAR(0), 1);
         mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-        mbar_init(BAR(3), 256); mbar_init(BAR(4), 256);
+        mbar_init(BAR(3), KB_CONV_THREADS); mbar_init(BAR(4), KB_CONV_THREADS);
         mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
         mbar_init(BAR(7), 257); mbar_init(BAR(8), 257);
         mbar_init(BAR(9), 1);
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc<256>(smem_u32(tmem_slot));
+    if (warp == 25) tmem_alloc<256>(smem_u32(tmem_slot));
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     const long long tk0 = dbg ? clock64() : 0;
 #define KB_T(slot, call) do { const long long _t0 = dbg ? clock64() : 0; call; if (dbg) dacc[slot] += clock64() - _t0; } while (0)
 
-    if (warp == 16) {
+    if (warp == 24) {
         // ===================== loader =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(BAR(0), KB_A1_BYTES + KB_A2_BYTES);
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             }
             if (dbg) dbg[cta * 8 + 0] = dacc[0];
         }
-    } else if (warp == 17) {
+    } else if (warp == 25) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t IDESC_K = idesc_f16(128, KB_NT);
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             mbar_wait(BAR(0), 0);
             tc_fence_after_sync();
             uint32_t first = 1;
+            const uint64_t dA1 = desc_sw128_kmajor(sbase), dA2 = desc_sw128_kmajor(sbase + KB_OFF_A2);
             int i = 0;
             for (int t = t_begin; t < t_end; ++t, ++i) {
                 const int b = i & 1;
@@ -194,33 +196,29 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 const long long ti0 = dbg ? clock64() : 0;
                 const uint32_t dz = sbase + KB_OFF_BUF + b * KB_BUF_BYTES, a1 = dz + KB_DZ_BYTES;
                 const uint32_t d1 = tmem + (uint32_t)(b * KB_NT);
+                // descriptors: one base per operand, every other one is base + (byte offset >> 4) in the address field
+                const uint64_t kA1 = dA1, kA2 = dA2;
+                const uint64_t kdz = desc_sw128_kmajor(dz), ka1 = desc_sw128_kmajor(a1);
+                const uint64_t mdz = desc_sw128_mnmajor(dz, 8192), ma1 = desc_sw128_mnmajor(a1, 8192);
                 // ---- D1 = A1op x dz (K = 128 channels)
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
-                    const uint32_t a_hi = sbase + (kb * 2 + 0) * 16384, a_lo = sbase + (kb * 2 + 1) * 16384;
-                    const uint32_t b_hi = dz + (0 * 2 + kb) * 8192, b_lo = dz + (1 * 2 + kb) * 8192;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
-                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+                        const uint32_t oa = (uint32_t)((kb * 2 + (pass == 1 ? 1 : 0)) * 16384);
+                        const uint32_t ob = (uint32_t)(((pass == 2 ? 1 : 0) * 2 + kb) * 8192);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_f16(d1, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC_K,
-                                    (kb | pass | k) ? 1u : 0u);
+                            mma_f16(d1, kA1 + ((oa + k * 32) >> 4), kdz + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
                     }
                 }
                 // ---- D1 += A2op x a1 (K = 64 channels)
-                {
-                    const uint32_t a_hi = sbase + KB_OFF_A2, a_lo = a_hi + 16384;
-                    const uint32_t b_hi = a1, b_lo = a1 + 8192;
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = (pass == 1) ? a_lo : a_hi;
-                        const uint32_t wb = (pass == 2) ? b_lo : b_hi;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t oa = (pass == 1) ? 16384u : 0u, ob = (pass == 2) ? 8192u : 0u;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_f16(d1, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC_K, 1u);
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        mma_f16(d1, kA2 + ((oa + k * 32) >> 4), ka1 + ((ob + k * 32) >> 4), IDESC_K, 1u);
                 }
                 mma_commit(BAR(5 + b));                     // d a1 of this tile complete -> epilogue
                 // ---- D2 += dz^T a1 (K = 64 points, MN-major operands; A atoms = the two 64-channel blocks, 8 KB apart)
@@ -228,11 +226,10 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                     const uint32_t d2 = tmem + 128u;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t wa = (pass == 1) ? dz + 16384 : dz;
-                        const uint32_t wb = (pass == 2) ? a1 + 8192 : a1;
+                        const uint32_t oa = (pass == 1) ? 16384u : 0u, ob = (pass == 2) ? 8192u : 0u;
 #pragma unroll
                         for (int k = 0; k < KB_NT / 16; ++k)
-                            mma_f16(d2, desc_sw128_mnmajor(wa + k * 2048, 8192), desc_sw128_mnmajor(wb + k * 2048, 8192), IDESC_MN,
+                            mma_f16(d2, mdz + ((oa + k * 2048) >> 4), ma1 + ((ob + k * 2048) >> 4), IDESC_MN,
                                     (first && pass == 0 && k == 0) ? 0u : 1u);
                     }
                 }
@@ -241,10 +238,10 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                     const uint32_t d3 = tmem + 192u;
 #pragma unroll
                     for (int pass = 0; pass < 2; ++pass) {
-                        const uint32_t wb = pass ? a1 + 8192 : a1;
+                        const uint32_t ob = pass ? 8192u : 0u;
 #pragma unroll
                         for (int k = 0; k < KB_NT / 16; ++k)
-                            mma_f16(d3, desc_sw128_mnmajor(a1 + k * 2048, 8192), desc_sw128_mnmajor(wb + k * 2048, 8192), IDESC_MN,
+                            mma_f16(d3, ma1 + ((k * 2048) >> 4), ma1 + ((ob + k * 2048) >> 4), IDESC_MN,
                                     (first && pass == 0 && k == 0) ? 0u : 1u);
                     }
                 }
@@ -255,7 +252,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             mma_commit(BAR(9));
             if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
-    } else if ((warp & 3) < 2) {
+    } else if (warp < 16 && (warp & 3) < 2) {
         // ===================== epilogue: feature k = TMEM lane, 16 of the tile's 64 points per warp =====================
         const int q = warp & 3, cgp = warp >> 2;
         const int k = q * 32 + lane;
@@ -277,21 +274,26 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             const unsigned char* a1b = smem + KB_OFF_BUF + b * KB_BUF_BYTES + KB_DZ_BYTES;
             const float* xb = sx + b * (3 * KB_NT);
             float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+            float av[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {                  // a1 of the 16 points, read back from the operand tile
+                const int pp = cgp * 16 + j;
+                const uint32_t off = (uint32_t)pp * 128u + ((kchunk ^ (uint32_t)(pp & 7)) << 4) + koff;
+                av[j] = (__half2float(*reinterpret_cast<const __half*>(a1b + off)) +
+                         __half2float(*reinterpret_cast<const __half*>(a1b + 8192 + off))) * (1.0f / ACT_SCALE);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int pp = cgp * 16 + j;
-                if (pp < nv) {
-                    const uint32_t off = (uint32_t)pp * 128u + ((kchunk ^ (uint32_t)(pp & 7)) << 4) + koff;
-                    const float a = (__half2float(*reinterpret_cast<const __half*>(a1b + off)) +
-                                     __half2float(*reinterpret_cast<const __half*>(a1b + 8192 + off))) * (1.0f / ACT_SCALE);
-                    const float da1 = fmaf(v[j], ginv, cv);
-                    const float dz1 = a > 0.f ? da1 : 0.f;
-                    const float yh = (a - be) * g1inv;      // only used where dz1 != 0
-                    s1 += dz1;
-                    s2 = fmaf(dz1, yh, s2);
-                    h0 = fmaf(dz1, xb[pp], h0); h1 = fmaf(dz1, xb[KB_NT + pp], h1); h2 = fmaf(dz1, xb[2 * KB_NT + pp], h2);
-                }
+                const float a = av[j];                      // rows >= nv of the operand tile are zero -> dz1 = 0
+                const float da1 = fmaf(v[j], ginv, cv);
+                const float dz1 = a > 0.f ? da1 : 0.f;
+                const float yh = (a - be) * g1inv;          // only used where dz1 != 0
+                s1 += dz1;
+                s2 = fmaf(dz1, yh, s2);
+                h0 = fmaf(dz1, xb[pp], h0); h1 = fmaf(dz1, xb[KB_NT + pp], h1); h2 = fmaf(dz1, xb[2 * KB_NT + pp], h2);
             }
+            (void)nv;
             float* h = p.Hpart + ((size_t)t * KB_EPI_GROUPS + cgp) * (C1 * 3) + k * 3;
             h[0] = h0; h[1] = h1; h[2] = h2;
             tc_fence_before_sync();
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
         o[k] = s1; o[C1 + k] = s2;
     } else {
         // ===================== converters: raw fp32 rows -> hi/lo fp16 operand tiles, in place =====================
-        const int cw = (warp >> 2) * 2 + (warp & 1);        // 0..7
+        const int cw = warp < 16 ? (warp >> 2) * 2 + (warp & 1) : warp - 8;        // 0..15
         const int ctid = cw * 32 + lane;
         const float4 e4 = *reinterpret_cast<const float4*>(p.esc + 4 * lane);
         int i = 0;
@@ -322,18 +324,18 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             if (dbg) dacc[1] += tc0 - s_clk[b];
             unsigned char* dzb = smem + KB_OFF_BUF + b * KB_BUF_BYTES;
             unsigned char* a1b = dzb + KB_DZ_BYTES;
-            float4 rdz[8], ra[4];
+            float4 rdz[4], ra[2];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) rdz[u] = *reinterpret_cast<const float4*>(dzb + (cw * 8 + u) * 512 + lane * 16);
+            for (int u = 0; u < 4; ++u) rdz[u] = *reinterpret_cast<const float4*>(dzb + (cw * 4 + u) * 512 + lane * 16);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) ra[u] = *reinterpret_cast<const float4*>(a1b + (cw * 8 + u * 2 + (lane >> 4)) * 256 + (lane & 15) * 16);
-            named_bar_sync(1, 256);                         // every converter thread has read its raw rows
+            for (int u = 0; u < 2; ++u) ra[u] = *reinterpret_cast<const float4*>(a1b + (cw * 4 + u * 2 + (lane >> 4)) * 256 + (lane & 15) * 16);
+            named_bar_sync(1, KB_CONV_THREADS);             // every converter thread has read its raw rows
             if (ctid < 3 * KB_NT) sx[b * (3 * KB_NT) + ctid] = xv;
             {
                 const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int r = cw * 8 + u;
+                for (int u = 0; u < 4; ++u) {
+                    const int r = cw * 4 + u;
                     const bool ok = r < nv;
                     const float d0 = ok ? fminf(fmaxf(rdz[u].x * e4.x, -60000.f), 60000.f) : 0.f;
                     const float d1 = ok ? fminf(fmaxf(rdz[u].y * e4.y, -60000.f), 60000.f) : 0.f;
@@ -353,8 +355,8 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             {
                 const int cg = lane & 15, chunk = cg >> 1, half8 = cg & 1;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int r = cw * 8 + u * 2 + (lane >> 4);
+                for (int u = 0; u < 2; ++u) {
+                    const int r = cw * 4 + u * 2 + (lane >> 4);
                     const bool ok = r < nv;
                     const float a0 = ok ? fminf(ra[u].x * ACT_SCALE, 60000.f) : 0.f;
                     const float a1v = ok ? fminf(ra[u].y * ACT_SCALE, 60000.f) : 0.f;
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 17) tmem_dealloc<256>(tmem);
+    if (warp == 25) tmem_dealloc<256>(tmem);
 }
 
 inline int launch_kb(const KbParams& p, int sms, cudaStream_t s) {

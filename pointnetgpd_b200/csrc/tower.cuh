@@ -70,7 +70,7 @@ struct TowerScratch {
     void* wimg_kb;    // 96 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
-    float* pmax;      // [512][2][128] per-epilogue-row maxima of |dz2|, |yhat2|
+    float* pmax;      // [1024][2][128] per-epilogue-row maxima of |dz2|, |yhat2|
     float* esc;       // [128] per-channel power-of-two scale of dy2 (tcgen05 dW2)
     float* einv;      // [128] its inverse
     // backward scratch
@@ -79,7 +79,7 @@ struct TowerScratch {
     float* evec;      // [1024]
     float* gram;      // [128*128]
     float* gram2;     // [2][128*128] reduced hi.hi / hi.lo Gram accumulators of the fused pass-1 kernel
-    float* ka_part;   // [512][2][128] BatchNorm2-backward partial sums of the tcgen05 pass-1 kernels
+    float* ka_part;   // [1024][2][128] BatchNorm2-backward partial sums of the tcgen05 pass-1 kernels
     float* WG;        // [1024*128]
     float* Q;         // [128*128]
     float* uvec;      // [128]
@@ -157,7 +157,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.wimg_kb = c.take<unsigned char>((size_t)96 * 1024);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
-    w.pmax = c.take<float>((size_t)512 * 2 * C2);
+    w.pmax = c.take<float>((size_t)1024 * 2 * C2);
     w.esc = c.take<float>(C2);
     w.einv = c.take<float>(C2);
     if (backward) {
@@ -166,7 +166,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         w.evec = c.take<float>(C3);
         w.gram = c.take<float>(C2 * C2);
         w.gram2 = c.take<float>(2 * C2 * C2);
-        w.ka_part = c.take<float>((size_t)512 * 2 * C2);
+        w.ka_part = c.take<float>((size_t)1024 * 2 * C2);
         w.WG = c.take<float>((size_t)C3 * C2);
         w.Q = c.take<float>(C2 * C2);
         w.uvec = c.take<float>(C2);
