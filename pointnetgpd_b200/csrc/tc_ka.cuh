@@ -70,6 +70,13 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
+    // tuning aid (pgpd_debug_stream_counters): 0 loader wait buf_empty | 1 load latency (issue -> landed, seen by a converter)
+    // 2 converter work | 3 mma wait op_ready | 4 mma issue | 5 epilogue wait acc_full | 6 epilogue work | 7 total
+    long long* const dbg = g_stream_dbg;
+    long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    volatile long long* s_clk = reinterpret_cast<volatile long long*>(misc + 160);
+    const long long tk0 = dbg ? clock64() : 0;
+#define KA_T(slot, call) do { const long long _t0 = dbg ? clock64() : 0; call; if (dbg) dacc[slot] += clock64() - _t0; } while (0)
 
     if (warp == 24) {
         // ===================== loader (whole warp: lane l owns points 2l, 2l+1 of the tile) =====================
@@ -106,7 +113,8 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
             const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
             const size_t P0 = (size_t)cb * p.N + n0;
-            mbar_wait(BAR(7 + b), ph ^ 1);
+            KA_T(0, mbar_wait(BAR(7 + b), ph ^ 1));
+            if (dbg && lane == 0) s_clk[b] = clock64();
             s_slot[b * KA_NT + 2 * lane] = s0;
             s_slot[b * KA_NT + 2 * lane + 1] = s1;
             const int cnt = __popc(__ballot_sync(0xffffffffu, s0 >= 0)) + __popc(__ballot_sync(0xffffffffu, s1 >= 0));
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             if (s1 >= 0) bulk_g2s(dst + KA_OP_BYTES + (uint32_t)(2 * lane + 1) * 512u, p.da2s + (size_t)s1 * C2, 512u, BAR(1 + b));
             s0 = n0s; s1 = n1s;
         }
+        if (dbg && lane == 0) dbg[cta * 8 + 0] = dacc[0];
     } else if (warp == 25) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -134,8 +143,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             for (int t = t_begin; t < t_end; ++t, ++i) {
                 const int b = i & 1;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                mbar_wait(BAR(3 + b), ph);
+                KA_T(3, mbar_wait(BAR(3 + b), ph));
                 tc_fence_after_sync();
+                const long long ti0 = dbg ? clock64() : 0;
                 const uint32_t op = sbase + KA_OFF_BUF + b * KA_BUF_BYTES;
                 const uint32_t d1 = tmem + (uint32_t)(b * KA_NT);
                 const uint64_t kop = desc_sw128_kmajor(op), mop = desc_sw128_mnmajor(op, 8192);
@@ -163,8 +173,10 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
                 }
                 first = 0;
                 mma_commit(BAR(7 + b));
+                if (dbg) dacc[4] += clock64() - ti0;
             }
             mma_commit(BAR(9));
+            if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
     } else if (warp < 16) {
         // ===================== epilogue: channel c = TMEM lane, 16 of the tile's 64 points per warp =====================
@@ -181,8 +193,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
             const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
             const size_t P0 = (size_t)cb * p.N + n0;
-            mbar_wait(BAR(5 + b), ph);
+            KA_T(5, mbar_wait(BAR(5 + b), ph));
             tc_fence_after_sync();
+            const long long te0 = dbg ? clock64() : 0;
             float v[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KA_NT + cgp * 16), v);
             const unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES + ckb * 8192;
@@ -214,7 +227,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             }
             tc_fence_before_sync();
             mbar_arrive(BAR(7 + b));
+            if (dbg) dacc[6] += clock64() - te0;
         }
+        if (dbg && warp == 0 && lane == 0) { dbg[cta * 8 + 5] = dacc[5]; dbg[cta * 8 + 6] = dacc[6]; dbg[cta * 8 + 7] = clock64() - tk0; }
         const size_t row = (size_t)cta * KA_EPI_ROWS + cgp;
         p.part[row * 2 * C2 + c] = s1; p.part[row * 2 * C2 + C2 + c] = s2;
         p.pmax[row * 2 * C2 + c] = mxdz; p.pmax[row * 2 * C2 + C2 + c] = 0.f;
@@ -233,6 +248,8 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             const int tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
             const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
             mbar_wait(BAR(1 + b), ph);
+            const long long tc0 = dbg ? clock64() : 0;
+            if (dbg) dacc[1] += tc0 - s_clk[b];
             unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES;
             float4 ry[8];
 #pragma unroll
@@ -258,8 +275,11 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             }
             fence_proxy_async_smem();
             mbar_arrive(BAR(3 + b));
+            if (dbg) dacc[2] += clock64() - tc0;
         }
+        if (dbg && cw == 0 && lane == 0) { dbg[cta * 8 + 1] = dacc[1]; dbg[cta * 8 + 2] = dacc[2]; }
     }
+#undef KA_T
 
     // ===================== read-out of the Gram accumulators (warps 0..15) =====================
     if (warp < 16) {

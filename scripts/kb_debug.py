@@ -28,5 +28,6 @@ lib.pgpd_debug_stream_counters(0)
 a = np.array(buf[:], dtype=np.int64).reshape(256, 8)[:148]
 names = ["loader wait buf_empty", "load latency (issue->landed)", "converter work", "mma wait op_ready", "mma issue", "epi wait acc_full", "epi work", "total"]
 tiles = (B * (N // 64)) / 148
+print("kernel:", os.environ.get("WHICH", "kb"), "(ka: run with PGPD_TC_MASK=0x2F so that k_kb_tc does not overwrite the counters)")
 for i, n in enumerate(names):
     print("%-30s mean %10.0f cycles/CTA   %8.0f per tile" % (n, a[:, i].mean(), a[:, i].mean() / tiles))
