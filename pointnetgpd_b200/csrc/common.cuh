@@ -121,13 +121,17 @@ inline int colreduce(const T* part, int nblk, int C, double* tmp, cudaStream_t s
 }
 
 // slices of centred-square sums -> variance -> BatchNorm finalisation (train)
+// The squares were centred on `centre` (nullptr: on mean_u itself): sum (u-c)^2 = sum (u-mu)^2 + count (mu-c)^2.
 __global__ void k_bn_finalize_from_css(const double* tmp, int S, int C, const float* mean_u, double count,
-                                       const float* bias, pgpd_bn bn, BnState st) {
+                                       const float* bias, pgpd_bn bn, BnState st, const float* centre) {
     int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= C) return;
     double s = 0.0;
     for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
-    bn_finalize_train(c, (double)mean_u[c], s / count, count, bias, bn, st);
+    const double mu = (double)mean_u[c];
+    double var = s / count;
+    if (centre) { const double d = mu - (double)centre[c]; var -= d * d; }
+    bn_finalize_train(c, mu, var, count, bias, bn, st);
 }
 
 // out[c] = sum_i tmp[i][c]
@@ -137,6 +141,15 @@ __global__ void k_reduce_d(const double* tmp, int S, int C, double* out) {
     double s = 0.0;
     for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
     out[c] = s;
+}
+
+// out[c] = scale * sum_i tmp[i][c]
+__global__ void k_reduce_ds(const double* tmp, int S, int C, double scale, double* out) {
+    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
+    out[c] = s * scale;
 }
 
 // out[c] = (float) sum_i tmp[i][c]

@@ -5,6 +5,9 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#ifndef PGPD_EMU
+#include "tc_gemm.cuh"
+#endif
 
 namespace pgpd {
 
@@ -20,6 +23,7 @@ struct HeadWs {
     float* DZ1;       // [B][512]  dz1, then (in place) dU1
     float* DZ2;       // [B][256]
     float* dO;        // [B][out]  gradient w.r.t. fc3 output
+    unsigned* amax;   // [4] bit patterns of max |x|: fc1.weight, fc2.weight, dU1, dU2 (operand scales of the tcgen05 GEMMs)
 };
 
 constexpr size_t HEAD_PART_ELEMS = (size_t)4 << 20;   // 16 MB of fp32 partials
@@ -32,6 +36,7 @@ inline void plan_head(Carver& c, HeadWs& w, int B, int out, bool backward) {
     w.out = c.take<float>((size_t)B * out);
     w.bn[0].carve(c, H1); w.bn[1].carve(c, H2);
     w.part = c.take<float>(HEAD_PART_ELEMS);
+    w.amax = c.take<unsigned>(4);
     if (backward) {
         w.DZ1 = c.take<float>((size_t)B * H1);
         w.DZ2 = c.take<float>((size_t)B * H2);
@@ -201,7 +206,7 @@ __global__ void k_colsum(const float* __restrict__ G, int B, int J, float* __res
 // BatchNorm-over-batch backward: sums -> dgamma, dbeta; then dU = s*(dz - m1 - yhat*m2) written IN PLACE over dz.
 // block = 32 channels x 32 row lanes.
 __global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, unsigned* __restrict__ amax) {
     __shared__ double sh1[32][33], sh2[32][33];
     __shared__ float sm1[32], sm2[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
@@ -224,13 +229,21 @@ __global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __rest
         sm1[cx] = (float)(t1 / B); sm2[cx] = (float)(t2 / B);
     }
     __syncthreads();
+    float mx = 0.f;
     if (c < C) {
         const float m1 = sm1[cx], m2 = sm2[cx];
         for (int b = ry; b < B; b += 32) {
             const size_t i = (size_t)b * C + c;
             const float yhat = (U[i] - mu) * r;
-            DZ[i] = sc * (DZ[i] - m1 - yhat * m2);
+            const float du = sc * (DZ[i] - m1 - yhat * m2);
+            DZ[i] = du;
+            mx = fmaxf(mx, fabsf(du));
         }
+    }
+    if (amax) {     // max |dU|: operand scale of the tcgen05 GEMMs that consume dU (max is order-independent: deterministic)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (cx == 0) atomicMax(amax, __float_as_uint(mx));
     }
 }
 
@@ -240,7 +253,29 @@ struct HeadArgs {
     int B, out;
     bool train, is_stn;
     cudaStream_t stream;
+    bool use_tc;         // tcgen05 GEMMs for fc1 / fc2 (never in the emulator build)
 };
+
+#ifndef PGPD_EMU
+// C[M][N] = sum_k A(m,k) B(n,k) on the tensor cores; split-K partials go through `part` and are summed in a fixed order.
+// nsl_fixed > 0: exactly that many K slices (forward: the summation order must not depend on the batch size).
+inline void run_gemm_tc(tc::GemmOp A, tc::GemmOp Bo, int M, int N, int K, float* C, float* part, const float* mask,
+                        int nsl_fixed, cudaStream_t s) {
+    const int tiles = idiv_up(M, tc::GM_T) * idiv_up(N, tc::GM_T);
+    int nsl = nsl_fixed > 0 ? nsl_fixed : 1;
+    if (nsl_fixed <= 0)
+        while (tiles * nsl < 120 && K / (nsl * 2) >= tc::GM_KC && (size_t)(nsl * 2) * M * N <= HEAD_PART_ELEMS) nsl *= 2;
+    while (nsl > 1 && (size_t)nsl * M * N > HEAD_PART_ELEMS) nsl /= 2;
+    int kslice = idiv_up(idiv_up(K, nsl), tc::GM_KC) * tc::GM_KC;
+    nsl = idiv_up(K, kslice);                       // no empty slices
+    tc::GemmParams p{A, Bo, M, N, K, kslice, nsl > 1 ? part : C, mask};
+    tc::launch_gemm_tc(p, nsl, s);
+    if (nsl > 1) {
+        ProbPlain<true, true> f{nullptr, nullptr, C, part, M, N, K, 0, 0, 0, 0, kslice, mask ? EPI_MASK : EPI_NONE, nullptr, 0, mask};
+        launch(k_splitk_finish<true, true>, grid1d((size_t)M * N, 256), dim3(256), 0, s, f, nsl);
+    }
+}
+#endif
 
 // X -> w.out  (logits, or t9 + identity)
 inline void head_forward(const HeadArgs& a, HeadWs& w) {
@@ -248,6 +283,14 @@ inline void head_forward(const HeadArgs& a, HeadWs& w) {
     cudaStream_t s = a.stream;
     const int B = a.B;
     // fc1: U1[b][j] = sum_i X[b][i] W1[j][i]
+#ifndef PGPD_EMU
+    if (a.use_tc) {
+        cudaMemsetAsync(w.amax, 0, 4 * sizeof(unsigned), s);
+        launch(tc::k_absmax2, dim3(64), dim3(256), 0, s, h.fc[0].w, (size_t)H1 * C3, h.fc[1].w, (size_t)H2 * H1, w.amax);
+        run_gemm_tc(tc::GemmOp{a.X, C3, 0, nullptr, tc::ACT_SCALE}, tc::GemmOp{h.fc[0].w, C3, 0, w.amax + 0, 1.f}, B, H1, C3,
+                    w.U1, w.part, nullptr, 8, s);
+    } else
+#endif
     run_plain(ProbPlain<true, false>{a.X, h.fc[0].w, w.U1, w.part, B, H1, C3, (size_t)C3, 1, 1, (size_t)C3, 0, EPI_NONE, nullptr, 0, nullptr}, s, 8);
     if (a.train) launch(k_bn_batch_stats_apply, grid1d(H1, 32), dim3(1024), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0], w.Hm1);
     else {
@@ -255,6 +298,12 @@ inline void head_forward(const HeadArgs& a, HeadWs& w) {
         launch(k_bn_apply, grid1d((size_t)B * H1, 256), dim3(256), 0, s, (const float*)w.U1, (size_t)B * H1, H1, w.bn[0], w.Hm1);
     }
     // fc2
+#ifndef PGPD_EMU
+    if (a.use_tc)
+        run_gemm_tc(tc::GemmOp{w.Hm1, H1, 0, nullptr, tc::ACT_SCALE}, tc::GemmOp{h.fc[1].w, H1, 0, w.amax + 1, 1.f}, B, H2, H1,
+                    w.U2, w.part, nullptr, 4, s);
+    else
+#endif
     run_plain(ProbPlain<true, false>{w.Hm1, h.fc[1].w, w.U2, w.part, B, H2, H1, (size_t)H1, 1, 1, (size_t)H1, 0, EPI_NONE, nullptr, 0, nullptr}, s, 4);
     if (a.train) launch(k_bn_batch_stats_apply, grid1d(H2, 32), dim3(1024), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1], w.Hm2);
     else {
@@ -275,16 +324,42 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     run_plain(ProbPlain<false, true>{w.dO, w.Hm2, g.fc[2].dw, w.part, J3, H2, B, 1, (size_t)J3, (size_t)H2, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
     launch(k_colsum, dim3(J3), dim3(256), 0, s, (const float*)w.dO, B, J3, g.fc[2].db);
     run_plain(ProbPlain<true, true>{w.dO, h.fc[2].w, w.DZ2, w.part, B, H2, J3, (size_t)J3, 1, (size_t)H2, 1, 0, EPI_MASK, nullptr, 0, w.Hm2}, s);
-    launch(k_bn_batch_bwd_apply, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta);
-    // ---- fc2 (w.DZ2 now holds dU2)
-    run_plain(ProbPlain<false, true>{w.DZ2, w.Hm1, g.fc[1].dw, w.part, H2, H1, B, 1, (size_t)H2, (size_t)H1, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+    bool tcg = false;
+#ifndef PGPD_EMU
+    tcg = a.use_tc;
+#endif
+    launch(k_bn_batch_bwd_apply, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta,
+           tcg ? w.amax + 3 : (unsigned*)nullptr);
+    // ---- fc2 (w.DZ2 now holds dU2):  dW2 = dU2^T Hm1,  dz1 = (dU2 W2) masked by Hm1 > 0
     launch(k_fill, grid1d(H2, 128), dim3(128), 0, s, g.fc[1].db, (size_t)H2, 0.f);
-    run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.DZ1, w.part, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0, EPI_MASK, nullptr, 0, w.Hm1}, s);
-    launch(k_bn_batch_bwd_apply, grid1d(H1, 32), dim3(1024), 0, s, w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta);
-    // ---- fc1 (w.DZ1 now holds dU1)
-    run_plain(ProbPlain<false, true>{w.DZ1, a.X, g.fc[0].dw, w.part, H1, C3, B, 1, (size_t)H1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+#ifndef PGPD_EMU
+    if (tcg) {
+        run_gemm_tc(tc::GemmOp{w.DZ2, H2, 1, w.amax + 3, 1.f}, tc::GemmOp{w.Hm1, H1, 1, nullptr, tc::ACT_SCALE}, H2, H1, B,
+                    g.fc[1].dw, w.part, nullptr, 0, s);
+        run_gemm_tc(tc::GemmOp{w.DZ2, H2, 0, w.amax + 3, 1.f}, tc::GemmOp{h.fc[1].w, H1, 1, w.amax + 1, 1.f}, B, H1, H2,
+                    w.DZ1, w.part, w.Hm1, 0, s);
+    } else
+#endif
+    {
+        run_plain(ProbPlain<false, true>{w.DZ2, w.Hm1, g.fc[1].dw, w.part, H2, H1, B, 1, (size_t)H2, (size_t)H1, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+        run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.DZ1, w.part, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0, EPI_MASK, nullptr, 0, w.Hm1}, s);
+    }
+    launch(k_bn_batch_bwd_apply, grid1d(H1, 32), dim3(1024), 0, s, w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta,
+           tcg ? w.amax + 2 : (unsigned*)nullptr);
+    // ---- fc1 (w.DZ1 now holds dU1):  dW1 = dU1^T X,  dX = dU1 W1
     launch(k_fill, grid1d(H1, 128), dim3(128), 0, s, g.fc[0].db, (size_t)H1, 0.f);
-    run_plain(ProbPlain<true, true>{w.DZ1, h.fc[0].w, dX, w.part, B, C3, H1, (size_t)H1, 1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+#ifndef PGPD_EMU
+    if (tcg) {
+        run_gemm_tc(tc::GemmOp{w.DZ1, H1, 1, w.amax + 2, 1.f}, tc::GemmOp{a.X, C3, 1, nullptr, tc::ACT_SCALE}, H1, C3, B,
+                    g.fc[0].dw, w.part, nullptr, 0, s);
+        run_gemm_tc(tc::GemmOp{w.DZ1, H1, 0, w.amax + 2, 1.f}, tc::GemmOp{h.fc[0].w, C3, 1, w.amax + 0, 1.f}, B, C3, H1,
+                    dX, w.part, nullptr, 0, s);
+    } else
+#endif
+    {
+        run_plain(ProbPlain<false, true>{w.DZ1, a.X, g.fc[0].dw, w.part, H1, C3, B, 1, (size_t)H1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+        run_plain(ProbPlain<true, true>{w.DZ1, h.fc[0].w, dX, w.part, B, C3, H1, (size_t)H1, 1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+    }
 }
 
 }  // namespace pgpd

@@ -89,6 +89,9 @@ static bool want_tc(int flags) {
 #endif
 }
 
+// tcgen05 GEMMs in the FC heads: PGPD_TC_MASK bit 6 (default on)
+static bool head_tc(int flags) { return want_tc(flags) && (tc_mask() & 64); }
+
 static void run_tower_fwd(const TowerArgs& a, TowerWs& w, float* pooled, int) { tower_forward(a, w, pooled); }
 
 static void run_tower_bwd(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad& g, const float* dpooled, float* dtrans, int) {
@@ -177,7 +180,7 @@ int pgpd_forward(int what, const pgpd_model* m, const float* x, int B, int N, in
     // ---- STN3d (pointnet.py:27-45)
     TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, train, save, s, want_tc(flags)};
     run_tower_fwd(ta, w.stn_t, w.g_stn, flags);
-    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, train, true, s};
+    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, train, true, s, head_tc(flags)};
     head_forward(ha, w.stn_h);
     cudaMemcpyAsync(trans, w.stn_h.out, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (what >= PGPD_FEAT) {
@@ -188,7 +191,7 @@ int pgpd_forward(int what, const pgpd_model* m, const float* x, int B, int N, in
             cudaMemcpyAsync(out, w.G, (size_t)B * C3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
         } else {
             // ---- classifier head (pointnet.py:191-194)
-            HeadArgs hb{&m->cls_head, w.G, B, k, train, false, s};
+            HeadArgs hb{&m->cls_head, w.G, B, k, train, false, s, head_tc(flags)};
             head_forward(hb, w.cls_h);
             launch(k_log_softmax, grid1d(B, 128), dim3(128), 0, s, (const float*)w.cls_h.out, B, k, w.logp);
             cudaMemcpyAsync(out, w.logp, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -218,7 +221,7 @@ int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const
         const float* dG = dout;
         if (what == PGPD_CLS) {
             launch(k_log_softmax_bwd, grid1d(B, 128), dim3(128), 0, s, (const float*)w.logp, dout, B, k, w.cls_h.dO);
-            HeadArgs hb{&m->cls_head, w.G, B, k, true, false, s};
+            HeadArgs hb{&m->cls_head, w.G, B, k, true, false, s, head_tc(flags)};
             head_backward(hb, w.cls_h, g->cls_head, w.dG);
             dG = w.dG;
         }
@@ -228,7 +231,7 @@ int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const
     } else {
         cudaMemcpyAsync(w.stn_h.dO, dT_total, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     }
-    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, true, true, s};
+    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, true, true, s, head_tc(flags)};
     head_backward(ha, w.stn_h, g->stn_head, w.dg_stn);
     TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, true, true, s, want_tc(flags)};
     run_tower_bwd(ta, w.stn_t, g->stn_tower, w.dg_stn, nullptr, flags);

@@ -85,6 +85,7 @@ struct L3Params {
     float* css_part;          // [ntiles][1024]
     int B, N, tiles_per_cloud, ntiles;
     long long* dbg;           // optional [gridDim.x][8] cycle counters (see PGPD_L3_DEBUG), or nullptr
+    float* s1_part;           // optional [gridDim.x][128]: per-CTA sums over its points of a2 * 2^4 (v1 kernel), or nullptr
 };
 
 // cycle accounting of the pipeline roles, for tuning (enabled by a non-null L3Params::dbg):
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
         uint32_t ephase = 0;
+        float sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f;   // sums of this thread's a2 values (x 2^4)
         for (int t = t_begin; t < t_end; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT;
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                     float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
                     float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
                     float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
+                    sa0 += a0; sa1 += a1; sa2 += a2; sa3 += a3;
                     __half2 h01, l01, h23, l23;
                     split2(a0, a1, h01, l01);
                     split2(a2, a3, h23, l23);
@@ -309,6 +312,25 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             if (p.dbg) dbg_acc[5] += clock64() - tp0;
         }
         if (p.dbg && wp == 0 && lane == 0) { p.dbg[(size_t)cta * 8 + 4] = dbg_acc[4]; p.dbg[(size_t)cta * 8 + 5] = dbg_acc[5]; }
+        if (p.s1_part) {
+            // per-CTA sum of a2 (for the exact mean of u3 = W3 mean(a2) and for dW3): the 8 producer warps' partial
+            // sums are added in a fixed order through the (now idle) operand tile
+            mbar_wait(BAR(7), ephase ^ 1);                  // the last tile's MMAs are done with the buffer
+            float* red = reinterpret_cast<float*>(smem);    // [8][128]
+            red[wp * C2 + 4 * lane + 0] = sa0; red[wp * C2 + 4 * lane + 1] = sa1;
+            red[wp * C2 + 4 * lane + 2] = sa2; red[wp * C2 + 4 * lane + 3] = sa3;
+            named_bar_sync(1, 256);
+            if (wp == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ch = 4 * lane + e;
+                    float t = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) t += red[w8 * C2 + ch];
+                    p.s1_part[(size_t)cta * C2 + ch] = t;
+                }
+            }
+        }
     }
 
     tc_fence_before_sync();

@@ -32,12 +32,13 @@
 namespace pgpd {
 
 // which tcgen05 kernels may run (debugging aid): PGPD_TC_MASK bit0 layer-3 fwd, bit1 layer-2 fwd,
-// bit2 Gram, bit3 layer-2 bwd pass 1, bit4 dW2, bit5 layer-2 bwd pass 2b.  Default: all.
+// bit2 Gram, bit3 layer-2 bwd pass 1, bit4 fused layer-2/1 backward pass, bit5 (older layer-2 bwd pass 2b), bit6 FC-head GEMMs.
+// Default: all.
 inline unsigned tc_mask() {
     static int m = -1;
     if (m < 0) {
         const char* e = getenv("PGPD_TC_MASK");
-        m = e ? (int)strtol(e, nullptr, 0) : 0x3F;
+        m = e ? (int)strtol(e, nullptr, 0) : 0x7F;
     }
     return (unsigned)m;
 }
@@ -67,6 +68,8 @@ struct TowerScratch {
     unsigned long long* keys;  // [B][1024]
     void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
+    float* mu_x;      // [1024] exact mean of u3 when the kernel centred its squares on a pilot estimate
+    float* s1part;    // [256][128] per-CTA sums of a2 * 2^4 written by the tcgen05 layer-3 kernel
     void* wimg_kb;    // 96 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
@@ -154,6 +157,8 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.keys = c.take<unsigned long long>((size_t)B * C3);
     w.wimg = c.take<unsigned char>((size_t)512 * 1024);
     w.mu_s = c.take<float>(C3);
+    w.mu_x = c.take<float>(C3);
+    w.s1part = c.take<float>((size_t)256 * C2);
     w.wimg_kb = c.take<unsigned char>((size_t)96 * 1024);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
@@ -304,20 +309,22 @@ __global__ void k_a1(const float* __restrict__ x, const float* __restrict__ tran
     }
 }
 
-// per-block sums over points of a2 = relu(scale2*u2 + shift2); block = 128 channels x 2 slots
-__global__ void k_a2_sum(const float* __restrict__ Y2, size_t M, BnState st, double* __restrict__ part) {
+// per-block sums over points of a2 = relu(scale2*u2 + shift2); block = 128 channels x 2 slots.
+// pstride > 1: only every pstride-th point (Ms = ceil(M / pstride) samples) -- the pilot estimate of mean(a2).
+__global__ void k_a2_sum(const float* __restrict__ Y2, size_t Ms, size_t pstride, BnState st, double* __restrict__ part) {
     __shared__ double sh[256];
     const int tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
     const float sc = st.scale[k], sf = st.shift[k];
     // four independent partial sums so that the loads of consecutive iterations overlap
     float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
     const size_t stride = (size_t)gridDim.x * 2;
+    const size_t rs = pstride * C2;                 // floats between consecutive samples
     size_t P = (size_t)blockIdx.x * 2 + q;
-    for (; P + 3 * stride < M; P += 4 * stride) {
-        const float y0 = Y2[P * C2 + k], y1 = Y2[(P + stride) * C2 + k], y2 = Y2[(P + 2 * stride) * C2 + k], y3 = Y2[(P + 3 * stride) * C2 + k];
+    for (; P + 3 * stride < Ms; P += 4 * stride) {
+        const float y0 = Y2[P * rs + k], y1 = Y2[(P + stride) * rs + k], y2 = Y2[(P + 2 * stride) * rs + k], y3 = Y2[(P + 3 * stride) * rs + k];
         f0 += fmaxf(sc * y0 + sf, 0.f); f1 += fmaxf(sc * y1 + sf, 0.f); f2 += fmaxf(sc * y2 + sf, 0.f); f3 += fmaxf(sc * y3 + sf, 0.f);
     }
-    for (; P < M; P += stride) f0 += fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
+    for (; P < Ms; P += stride) f0 += fmaxf(sc * Y2[P * rs + k] + sf, 0.f);
     const double acc = ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
     sh[tid] = acc;
     __syncthreads();
@@ -930,6 +937,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         launch(k_matvec_mean, dim3(C2 / 8), dim3(256), 0, s, t.conv[1].w, C2, C1, (const double*)w.S1a, 1.0 / count, w.bn[1].mean);
     }
     int n_css2 = 0;
+    bool l3_pilot = false;      // BatchNorm3 statistics centred on a pilot mean (tcgen05 layer-3 kernel), corrected below
 #ifndef PGPD_EMU
     if (a.use_tc && (tc_mask() & 2)) {
         launch(tc::k_prepack_rows, dim3(128), dim3(C1), 0, s, t.conv[1].w, C1, 1, C2, C1, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
@@ -956,17 +964,30 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     if (a.train) {
         const int S = colreduce<float>(w.fpart, n_css2, C2, w.rtmp, s);
         launch(k_bn_finalize_from_css, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2,
-               (const float*)w.bn[1].mean, count, t.conv[1].b, t.bn[1], w.bn[1]);
-        // mean of layer-3 pre-activation: W3 * mean(a2)
-        launch(k_a2_sum, dim3(w.nb_a2), dim3(256), 0, s, (const float*)w.Y2, M, w.bn[1], w.dpart);
-        const int S2 = colreduce<double>(w.dpart, w.nb_a2, C2, w.rtmp, s);
+               (const float*)w.bn[1].mean, count, t.conv[1].b, t.bn[1], w.bn[1], (const float*)nullptr);
+        // mean of layer-3 pre-activation: W3 * mean(a2).  tcgen05 layer-3 kernel (version 1): only a PILOT estimate from
+        // every pstride-th point is computed here (the centre of the kernel's sum of squares); the kernel's operand
+        // producers accumulate the exact sum of a2 on the way and the statistics are corrected afterwards.
+        size_t pstride = 1;
+#ifndef PGPD_EMU
+        {
+            static const bool pilot_ok = !(getenv("PGPD_L3_PILOT") && atoi(getenv("PGPD_L3_PILOT")) == 0);
+            static const int l3v = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 1;
+            if (a.use_tc && (tc_mask() & 1) && pilot_ok && l3v != 2 && M >= 65536) pstride = M / 32768;
+        }
+#endif
+        l3_pilot = pstride > 1;
+        const size_t Ms = (M + pstride - 1) / pstride;
+        const int nb = (int)std::min<size_t>((size_t)w.nb_a2, (Ms + 15) / 16);
+        launch(k_a2_sum, dim3(nb), dim3(256), 0, s, (const float*)w.Y2, Ms, pstride, w.bn[1], w.dpart);
+        const int S2 = colreduce<double>(w.dpart, nb, C2, w.rtmp, s);
         launch(k_reduce_d, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S2, C2, w.S1);
-        launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.bn[2].mean);
+        launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / (double)Ms, w.bn[2].mean);
     }
 
     // ---- layer 3 + max-pool ------------------------------------------------------------------------
     cudaMemsetAsync(w.keys, 0, (size_t)a.B * C3 * sizeof(unsigned long long), s);
-    int n_css = 0, n_css_mult = 1;
+    int n_css = 0, n_css_mult = 1, l3_grid = 0;
 #ifndef PGPD_EMU
     if (a.use_tc && (tc_mask() & 1)) {
         // layer-3 kernel version: 1 (default) = single-CTA 256-point tiles; 2 = CTA pairs sharing the weight stream
@@ -979,7 +1000,9 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         // PGPD_L3_DEBUG=1: the kernel writes per-CTA pipeline cycle counters to a debug buffer
         static const bool l3dbg = getenv("PGPD_L3_DEBUG") != nullptr;
         tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
-                       w.keys, w.fpart, a.B, a.N, tpc, ntiles, l3dbg ? tc::l3_debug_buffer() : nullptr};
+                       w.keys, w.fpart, a.B, a.N, tpc, ntiles, l3dbg ? tc::l3_debug_buffer() : nullptr,
+                       l3_pilot ? w.s1part : (float*)nullptr};
+        l3_grid = l3ver == 2 ? 0 : (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
         const int sms = tc::dev_info().sms;
         profiler().begin(s);
         if (l3ver == 2) {
@@ -1004,9 +1027,18 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         n_css = a.B * w.tiles_per_cloud;
     }
     if (a.train) {
+        const float* mean3 = w.bn[2].mean;
+        const float* centre = nullptr;
+        if (l3_pilot) {
+            // exact sum of a2 from the kernel's per-CTA partials -> exact mean of u3; bn[2].mean still holds the pilot centre
+            const int S1s = colreduce<float>(w.s1part, l3_grid, C2, w.rtmp, s);
+            launch(k_reduce_ds, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S1s, C2, 1.0 / 16.0 /* the kernel sums a2 * 2^4 (L3_ACT_SCALE) */, w.S1);
+            launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.mu_x);
+            mean3 = w.mu_x; centre = w.bn[2].mean;
+        }
         const int S = colreduce<float>(w.fpart, n_css, C3, w.rtmp, s);
         launch(k_bn_finalize_from_css, grid1d(C3, 128), dim3(128), 0, s, (const double*)w.rtmp, S, C3,
-               (const float*)w.bn[2].mean, count, t.conv[2].b, t.bn[2], w.bn[2]);
+               mean3, count, t.conv[2].b, t.bn[2], w.bn[2], centre);
     }
     launch(k_pool_finalize, grid1d((size_t)a.B * C3, 256), dim3(256), 0, s, (const unsigned long long*)w.keys,
            (const float*)w.sgn, w.bn[2], a.relu_last ? 1 : 0, (size_t)a.B * C3, pooled, w.uext, w.idx);
