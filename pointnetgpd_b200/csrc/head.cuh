@@ -286,7 +286,7 @@ inline void head_forward(const HeadArgs& a, HeadWs& w) {
 #ifndef PGPD_EMU
     if (a.use_tc) {
         cudaMemsetAsync(w.amax, 0, 4 * sizeof(unsigned), s);
-        launch(tc::k_absmax2, dim3(64), dim3(256), 0, s, h.fc[0].w, (size_t)H1 * C3, h.fc[1].w, (size_t)H2 * H1, w.amax);
+        launch(tc::k_absmax2, dim3(64, 2), dim3(256), 0, s, h.fc[0].w, (size_t)H1 * C3, h.fc[1].w, (size_t)H2 * H1, w.amax);
         run_gemm_tc(tc::GemmOp{a.X, C3, 0, nullptr, tc::ACT_SCALE}, tc::GemmOp{h.fc[0].w, C3, 0, w.amax + 0, 1.f}, B, H1, C3,
                     w.U1, w.part, nullptr, 8, s);
     } else

@@ -41,25 +41,31 @@ struct GemmParams {
     const float* mask;     // optional [M][N]: output zeroed where mask <= 0 (only without split-K)
 };
 
-// max |x| over up to two arrays -> out[0], out[1] (bit patterns; the caller zeroes them first).  grid = any, block = 256
+// max |x| over up to two arrays -> out[0], out[1] (bit patterns; the caller zeroes them first; max is order-independent).
+// grid = (blocks, 2), block = 256; array lengths must be multiples of 4 and the pointers 16-byte aligned.
 __global__ void k_absmax2(const float* __restrict__ a, size_t na, const float* __restrict__ b, size_t nb, unsigned* __restrict__ out) {
     __shared__ float sh[8];
-    const int tid = (int)threadIdx.x;
-    for (int which = 0; which < 2; ++which) {
-        const float* p = which ? b : a;
-        const size_t n = which ? nb : na;
-        if (!p) continue;
-        float mx = 0.f;
-        for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n; i += (size_t)gridDim.x * 256) mx = fmaxf(mx, fabsf(p[i]));
+    const int tid = (int)threadIdx.x, which = (int)blockIdx.y;
+    const float4* p = reinterpret_cast<const float4*>(which ? b : a);
+    const size_t n4 = (which ? nb : na) >> 2;
+    if (!p) return;
+    float m0 = 0.f, m1 = 0.f;
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + tid;
+    for (; i + stride < n4; i += 2 * stride) {
+        const float4 u = p[i], v = p[i + stride];
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w))));
+        m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (i < n4) { const float4 u = p[i]; m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w)))); }
+    float mx = fmaxf(m0, m1);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((tid & 31) == 0) sh[tid >> 5] = mx;
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
-            atomicMax(out + which, __float_as_uint(mx));
-        }
-        __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) sh[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
+        atomicMax(out + which, __float_as_uint(mx));
     }
 }
 

@@ -36,7 +36,11 @@ constexpr int L3_SMEM_W = L3_A2_BYTES;
 constexpr int L3_SMEM_MISC = L3_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3_SMEM_BYTES = L3_SMEM_MISC + 2048 + 1024;   // + slack to align the base to 1024 B
 constexpr int L3_THREADS = 448;                  // v2 kernel: 14 warps: W producer, MMA issuer, 4 epilogue, 8 a2 producers
-constexpr int L3A_THREADS = 576;                 // v1 kernel: 18 warps: W producer, MMA issuer, 8 epilogue, 8 a2 producers
+#ifndef PGPD_L3_NP
+#define PGPD_L3_NP 16
+#endif
+constexpr int L3A_NP = PGPD_L3_NP;               // a2 producer warps of the v1 kernel (8 or 16)
+constexpr int L3A_THREADS = 320 + 32 * L3A_NP;   // v1 kernel: W producer, MMA issuer, 8 epilogue, L3A_NP a2 producer warps
 constexpr float L3_ACT_SCALE = 16.0f;             // 2^4
 constexpr size_t L3_WIMG_BYTES = (size_t)8 * 2 * L3_STAGE_BYTES;   // 512 KB
 
@@ -85,7 +89,7 @@ struct L3Params {
     float* css_part;          // [ntiles][1024]
     int B, N, tiles_per_cloud, ntiles;
     long long* dbg;           // optional [gridDim.x][8] cycle counters (see PGPD_L3_DEBUG), or nullptr
-    float* s1_part;           // optional [gridDim.x][128]: per-CTA sums over its points of a2 * 2^4 (v1 kernel), or nullptr
+    float* s1_part;           // optional partial sums over the points of a2 * 2^4: v1 [gridDim.x][128], v3 [gridDim.x * 8][128]
 };
 
 // cycle accounting of the pipeline roles, for tuning (enabled by a non-null L3Params::dbg):
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-        mbar_init(BAR(6), 256); mbar_init(BAR(7), 1);
+        mbar_init(BAR(6), 32 * L3A_NP); mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
         mbar_init(BAR(10), 256); mbar_init(BAR(11), 256);
         mbar_fence_init();
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             for (int mt = 0; mt < 8; ++mt) {
                 const int ch = mt * 128 + row;
                 const float mu = stats ? p.mu_s[ch] : 0.f;
+                const uint64_t nmu2 = f2_pack(-mu, -mu);
                 { L3_T0(); mbar_wait(BAR(8 + acc), aphase); L3_ACC(6); }
                 tc_fence_after_sync();
                 const long long te0 = p.dbg ? clock64() : 0;
@@ -217,12 +222,15 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
                         }
                         const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                         if (stats) {
-                            float c0s = 0.f, c1s = 0.f, c2s = 0.f, c3s = 0.f;
+                            // centred squares with packed fp32 pairs (FADD2 / FFMA2): one issue slot per element instead of two
+                            uint64_t q0 = 0ull, q1 = 0ull;              // (+0.f, +0.f)
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const float d0 = v[j] - mu, d1 = v[j + 1] - mu, d2 = v[j + 2] - mu, d3 = v[j + 3] - mu;
-                                c0s = fmaf(d0, d0, c0s); c1s = fmaf(d1, d1, c1s); c2s = fmaf(d2, d2, c2s); c3s = fmaf(d3, d3, c3s);
+                                const uint64_t d0 = f2_add(f2_pack(v[j], v[j + 1]), nmu2), d1 = f2_add(f2_pack(v[j + 2], v[j + 3]), nmu2);
+                                q0 = f2_fma(d0, d0, q0); q1 = f2_fma(d1, d1, q1);
                             }
+                            float c0s, c1s, c2s, c3s;
+                            f2_unpack(q0, c0s, c1s); f2_unpack(q1, c2s, c3s);
                             css += (c0s + c1s) + (c2s + c3s);
                         }
                         if (m > best) {
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
         if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
     } else {
         // ===================== a2 producer =====================
-        const int wp = warp - 10;                           // 0..7
+        const int wp = warp - 10;                           // 0..L3A_NP-1
         const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
@@ -279,17 +287,17 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             ephase ^= 1;
             const long long tp0 = p.dbg ? clock64() : 0;
             constexpr int U = 8;
-            for (int i0 = 0; i0 < L3_NT / 8; i0 += U) {
+            for (int i0 = 0; i0 < L3_NT / L3A_NP; i0 += U) {
                 float4 y[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {               // all loads of U rows first (memory-level parallelism)
-                    const int r = wp + 8 * (i0 + u);
+                    const int r = wp + L3A_NP * (i0 + u);
                     y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = wp + 8 * (i0 + u);
+                    const int r = wp + L3A_NP * (i0 + u);
                     const bool ok = r < nvalid;
                     float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
                     float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
@@ -316,17 +324,17 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             // per-CTA sum of a2 (for the exact mean of u3 = W3 mean(a2) and for dW3): the 8 producer warps' partial
             // sums are added in a fixed order through the (now idle) operand tile
             mbar_wait(BAR(7), ephase ^ 1);                  // the last tile's MMAs are done with the buffer
-            float* red = reinterpret_cast<float*>(smem);    // [8][128]
+            float* red = reinterpret_cast<float*>(smem);    // [L3A_NP][128]
             red[wp * C2 + 4 * lane + 0] = sa0; red[wp * C2 + 4 * lane + 1] = sa1;
             red[wp * C2 + 4 * lane + 2] = sa2; red[wp * C2 + 4 * lane + 3] = sa3;
-            named_bar_sync(1, 256);
+            named_bar_sync(1, 32 * L3A_NP);
             if (wp == 0) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int ch = 4 * lane + e;
                     float t = 0.f;
 #pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) t += red[w8 * C2 + ch];
+                    for (int w8 = 0; w8 < L3A_NP; ++w8) t += red[w8 * C2 + ch];
                     p.s1_part[(size_t)cta * C2 + ch] = t;
                 }
             }
@@ -592,6 +600,275 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3_THREADS, 1) k_l3_
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ====================================================================================================================
+// Version 3: CTA PAIRS with cta_group::2 MMAs (M = 256 channels x N = 256 points per instruction).
+//   * each CTA of a pair holds HALF of the W3 block of a stage (its 128 of the 256 channels: 32 KB) and HALF of the a2
+//     operand tile (its 128 of the pair's 256 points: 64 KB): the W3 stream per SM is halved (the layer's L2->SM traffic
+//     per point drops from 2.5 KB to 1.25 KB) and the a2 operand fits twice, so staging the next tile overlaps the MMAs of
+//     the current one (version 1 is single-buffered: ~9 k of its ~38 k cycles per tile are exposed staging);
+//   * the leader CTA (cluster rank 0) issues every MMA; tcgen05.commit arrives on BOTH CTAs' barriers (multicast);
+//     barriers the leader waits on that depend on the peer (operand tile staged, weight stage landed, accumulator
+//     drained) receive the peer's arrivals through DSMEM (mapa + mbarrier.arrive.release.cluster);
+//   * each CTA's epilogue drains its own 128 channels x 256 points from its own TMEM; everything else as in version 1.
+// ====================================================================================================================
+constexpr int L3C_NH = 128;                        // points staged per CTA (half of the pair's tile)
+constexpr int L3C_A2_PART = L3C_NH * 128;          // 16 KB: one (part, k-block) sub-tile
+constexpr int L3C_A2_BUF = 4 * L3C_A2_PART;        // 64 KB
+constexpr int L3C_SMEM_W = 2 * L3C_A2_BUF;         // 128 KB
+constexpr int L3C_SMEM_MISC = L3C_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
+constexpr int L3C_SMEM_BYTES = L3C_SMEM_MISC + 2048 + 1024;
+constexpr int L3C_THREADS = 576;                   // W producer, MMA issuer / relay, 8 epilogue, 8 a2 producer warps
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* misc = smem + L3C_SMEM_MISC;
+    const uint32_t bar0 = sbase + L3C_SMEM_MISC;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // 0..2 w_full (local bulk copies) | 3..5 w_fullp (leader: the peer's stage landed) | 6..8 w_empty (commit, both CTAs)
+    // 9,10 a2_full (leader: 16 producer warps of both CTAs) | 11,12 a2_empty (commit, both) | 13,14 tmem_full (commit, both)
+    // 15,16 tmem_empty (leader: 16 epilogue warps of both CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 192);
+    float* s_scale = reinterpret_cast<float*>(misc + 256);
+    float* s_shift = s_scale + 128;
+
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); mbar_init(BAR(6 + i), 1); }
+        mbar_init(BAR(9), 16); mbar_init(BAR(10), 16);
+        mbar_init(BAR(11), 1); mbar_init(BAR(12), 1);
+        mbar_init(BAR(13), 1); mbar_init(BAR(14), 1);
+        mbar_init(BAR(15), 16); mbar_init(BAR(16), 16);
+        mbar_fence_init();
+    }
+    if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
+    if (warp == 1) tmem_alloc_pair<512>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs' barriers exist before anything is signalled across
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    // tiles of this PAIR (256 points each); both CTAs walk the same tiles
+    const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    const int T0 = (int)(((long long)p.ntiles * pair) / npairs), T1 = (int)(((long long)p.ntiles * (pair + 1)) / npairs);
+
+    if (warp == 0) {
+        // ===================== W3 producer: this CTA's 128 of the 256 channels of every stage =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = T0; t < T1; ++t)
+                for (int mt4 = 0; mt4 < 4; ++mt4)
+                    for (int kb = 0; kb < 2; ++kb) {
+                        mbar_wait(BAR(6 + stage), phase ^ 1);
+                        mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);
+                        const int blk = (mt4 * 2 + (int)rank) * 2 + kb;
+                        bulk_g2s(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES,
+                                 reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES, L3_STAGE_BYTES, BAR(stage));
+                        if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            if (!leader) {
+                // ===================== peer: relay "my weight stage has landed" to the leader =====================
+                int stage = 0; uint32_t phase = 0;
+                for (int t = T0; t < T1; ++t)
+                    for (int blk = 0; blk < 8; ++blk) {
+                        mbar_wait(BAR(stage), phase);
+                        mbar_arrive_cluster(BAR(3 + stage), 0u);
+                        if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
+                    }
+            } else {
+                // ===================== leader: MMA issuer for the pair =====================
+                constexpr uint32_t IDESC = idesc_f16(256, L3_NT);
+                int stage = 0; uint32_t wphase = 0;
+                int acc = 0; uint32_t aphase = 0;
+                int buf = 0; uint32_t bphase = 0;
+                for (int t = T0; t < T1; ++t) {
+                    mbar_wait_cluster(BAR(9 + buf), bphase);                    // both halves of the operand tile staged
+                    tc_fence_after_sync();
+                    const uint32_t a2b = sbase + buf * L3C_A2_BUF;
+                    for (int mt4 = 0; mt4 < 4; ++mt4) {
+                        mbar_wait_cluster(BAR(15 + acc), aphase ^ 1);           // both epilogues drained the accumulator
+                        tc_fence_after_sync();
+                        const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
+                        for (int kb = 0; kb < 2; ++kb) {
+                            mbar_wait(BAR(stage), wphase);                      // my half of the weight stage
+                            mbar_wait_cluster(BAR(3 + stage), wphase);          // the peer's half
+                            tc_fence_after_sync();
+                            const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES);
+                            const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
+#pragma unroll
+                            for (int pass = 0; pass < 3; ++pass) {
+                                const uint32_t oa = (pass == 1) ? 16384u : 0u;
+                                const uint32_t ob = (pass == 2) ? (uint32_t)(2 * L3C_A2_PART) : 0u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC, (kb | pass | k) ? 1u : 0u);
+                            }
+                            mma_commit_pair(BAR(6 + stage), (uint16_t)0x3);     // stage free in both CTAs
+                            if (++stage == L3_STAGES) { stage = 0; wphase ^= 1; }
+                        }
+                        mma_commit_pair(BAR(13 + acc), (uint16_t)0x3);          // accumulator complete in both CTAs
+                        if (++acc == 2) { acc = 0; aphase ^= 1; }
+                    }
+                    mma_commit_pair(BAR(11 + buf), (uint16_t)0x3);              // operand buffer free in both CTAs
+                    if (++buf == 2) { buf = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== epilogue: my 128 channels of every 256-channel block, all 256 points of the tile =====================
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const bool stats = p.mu_s != nullptr;
+        int acc = 0; uint32_t aphase = 0;
+        for (int t = T0; t < T1; ++t) {
+            const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
+            const int n0 = tt * L3_NT;
+            const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
+            for (int mt4 = 0; mt4 < 4; ++mt4) {
+                const int ch = (mt4 * 2 + (int)rank) * 128 + row;
+                const float mu = stats ? p.mu_s[ch] : 0.f;
+                const uint64_t nmu2 = f2_pack(-mu, -mu);
+                mbar_wait(BAR(13 + acc), aphase);
+                tc_fence_after_sync();
+                float best = -INFINITY; int bidx = 0; float css = 0.f;
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
+                for (int c0 = half * (L3_NT / 2); c0 < (half + 1) * (L3_NT / 2); c0 += 32) {
+                    if (c0 >= nvalid) break;                // warp-uniform
+                    float v[32];
+                    tmem_ld32(tbase + (uint32_t)c0, v);
+                    if (c0 + 32 <= nvalid) {
+                        float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+                        for (int j = 4; j < 32; j += 4) {
+                            m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+                        }
+                        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        if (stats) {
+                            uint64_t q0 = 0ull, q1 = 0ull;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const uint64_t d0 = f2_add(f2_pack(v[j], v[j + 1]), nmu2), d1 = f2_add(f2_pack(v[j + 2], v[j + 3]), nmu2);
+                                q0 = f2_fma(d0, d0, q0); q1 = f2_fma(d1, d1, q1);
+                            }
+                            float c0s, c1s, c2s, c3s;
+                            f2_unpack(q0, c0s, c1s); f2_unpack(q1, c2s, c3s);
+                            css += (c0s + c1s) + (c2s + c3s);
+                        }
+                        if (m > best) {
+                            best = m;
+                            int jj = 31;
+#pragma unroll
+                            for (int j = 30; j >= 0; --j) if (v[j] == m) jj = j;
+                            bidx = n0 + c0 + jj;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j < nvalid) {
+                                if (stats) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
+                                if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {                            // one arrival per warp on the LEADER's barrier
+                    if (leader) mbar_arrive(BAR(15 + acc)); else mbar_arrive_cluster(BAR(15 + acc), 0u);
+                }
+                if (++acc == 2) { acc = 0; aphase ^= 1; }
+                const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
+                                               (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
+                atomicMax(&p.keys[(size_t)b * C3 + ch], key);
+                if (stats) {
+                    const float iv = p.inv[ch];
+                    p.css_part[((size_t)t * 2 + half) * C3 + ch] = css * iv * iv;     // two partial rows per tile
+                }
+            }
+        }
+    } else {
+        // ===================== a2 producer: my 128 of the tile's 256 points, double-buffered =====================
+        const int wp = warp - 10;                           // 0..7
+        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
+        const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
+        const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
+        float sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f;
+        int buf = 0; uint32_t bphase = 0;
+        for (int t = T0; t < T1; ++t) {
+            const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
+            const int n0 = tt * L3_NT + (int)rank * L3C_NH;
+            int nvalid = p.N - n0;                          // valid rows of MY half (<= 0: none)
+            nvalid = nvalid < 0 ? 0 : (nvalid > L3C_NH ? L3C_NH : nvalid);
+            const float* src = p.Y2 + ((size_t)b * p.N + n0) * C2 + 4 * lane;
+            if (wp == 0 && lane == 0 && t + 2 < T1) {
+                const int t2 = t + 2;                       // two tiles ahead -> L2
+                const int b2 = t2 / p.tiles_per_cloud, tt2 = t2 % p.tiles_per_cloud;
+                const int m0 = tt2 * L3_NT + (int)rank * L3C_NH;
+                int nv2 = p.N - m0;
+                nv2 = nv2 < 0 ? 0 : (nv2 > L3C_NH ? L3C_NH : nv2);
+                if (nv2 > 0) l2_prefetch(p.Y2 + ((size_t)b2 * p.N + m0) * C2, (uint32_t)nv2 * C2 * 4u);
+            }
+            mbar_wait(BAR(11 + buf), bphase ^ 1);           // the MMAs that read this buffer two tiles ago are done
+            unsigned char* a2b = smem + buf * L3C_A2_BUF;
+            constexpr int U = 8;
+            for (int i0 = 0; i0 < L3C_NH / 8; i0 += U) {
+                float4 y[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int r = wp + 8 * (i0 + u);
+                    y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int r = wp + 8 * (i0 + u);
+                    const bool ok = r < nvalid;
+                    float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
+                    float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
+                    float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
+                    float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
+                    sa0 += a0; sa1 += a1; sa2 += a2; sa3 += a3;
+                    __half2 h01, l01, h23, l23;
+                    split2(a0, a1, h01, l01);
+                    split2(a2, a3, h23, l23);
+                    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(a2b + (0 * 2 + kb) * L3C_A2_PART + off) = hv;
+                    *reinterpret_cast<uint2*>(a2b + (1 * 2 + kb) * L3C_A2_PART + off) = lv;
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {                                // one arrival per warp on the LEADER's barrier
+                if (leader) mbar_arrive(BAR(9 + buf)); else mbar_arrive_cluster(BAR(9 + buf), 0u);
+            }
+            if (++buf == 2) { buf = 0; bphase ^= 1; }
+        }
+        if (p.s1_part) {
+            // sums of a2 (x 2^4): one partial row per producer warp, [gridDim.x * 8][128]; the caller's fixed-order column
+            // reduction adds them up
+            float* o = p.s1_part + ((size_t)blockIdx.x * 8 + wp) * C2 + 4 * lane;
+            o[0] = sa0; o[1] = sa1; o[2] = sa2; o[3] = sa3;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                 // nobody exits while the peer may still signal this CTA
+    if (warp == 1) tmem_dealloc_pair<512>(tmem);
+}
+
 // per-device one-time setup: is this an sm_100 part, and can the kernel have its shared memory?
 struct DevInfo { int state = 0; int sms = 148; };   // state: 0 unknown, 1 usable, -1 not usable
 inline DevInfo& dev_info() {
@@ -607,6 +884,7 @@ inline DevInfo& dev_info() {
         if (d.sms > 256) d.sms = 256;      // per-CTA partial buffers are sized for <= 256 CTAs (plan_tower_scratch)
         cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, L3B_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
         d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
         if (e != cudaSuccess) cudaGetLastError();
     }

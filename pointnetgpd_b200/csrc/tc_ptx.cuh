@@ -65,6 +65,44 @@ __device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_
                  :: "r"(bar), "h"(cta_mask) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one MMA spans the tensor cores / shared memories / TMEMs of the two CTAs of a cluster ------
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem) {   // one whole warp in EACH CTA of the pair, same smem offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(COLS) : "memory");
+}
+// D[256 x N] += A[256 x 16] B[N x 16]^T: issued by ONE thread of the leader CTA; each CTA supplies its 128 rows of A and
+// its N/2 rows of B at the same shared-memory offsets, and receives its 128 rows of D in its own TMEM
+__device__ __forceinline__ void mma_f16_pair(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once every MMA issued so far has completed) on the mbarrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(cta_mask) : "memory");
+}
+// arrive on the mbarrier at local offset `bar` of CTA `rank` of this cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" :: "r"(bar), "r"(rank) : "memory");
+}
+// wait on a LOCAL mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
 // pull [src, src+bytes) into L2 ahead of use (bytes multiple of 16, src 16-byte aligned); no completion tracking
 __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
@@ -158,6 +196,24 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                    "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
+}
+
+// ---- packed fp32 pairs (sm_100 FADD2 / FFMA2): two lanes of fp32 arithmetic per issued instruction -----------------
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 // fp32 -> (hi, lo) fp16 pair with hi + lo == x to ~22 bits (x must be pre-scaled into fp16's normal range)

@@ -69,7 +69,7 @@ struct TowerScratch {
     void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
     float* mu_x;      // [1024] exact mean of u3 when the kernel centred its squares on a pilot estimate
-    float* s1part;    // [256][128] per-CTA sums of a2 * 2^4 written by the tcgen05 layer-3 kernel
+    float* s1part;    // [256 * 8][128] partial sums of a2 * 2^4 written by the tcgen05 layer-3 kernel
     void* wimg_kb;    // 96 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
@@ -158,7 +158,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.wimg = c.take<unsigned char>((size_t)512 * 1024);
     w.mu_s = c.take<float>(C3);
     w.mu_x = c.take<float>(C3);
-    w.s1part = c.take<float>((size_t)256 * C2);
+    w.s1part = c.take<float>((size_t)256 * 8 * C2);
     w.wimg_kb = c.take<unsigned char>((size_t)96 * 1024);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
@@ -1008,6 +1008,10 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         if (l3ver == 2) {
             const int pairs = (ntiles + 1) / 2 < sms / 2 ? (ntiles + 1) / 2 : sms / 2;
             launch(tc::k_l3_fwd_tc2, dim3(2 * pairs), dim3(tc::L3_THREADS), (size_t)tc::L3B_SMEM_BYTES, s, p);
+        } else if (l3ver == 3) {
+            const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
+            launch(tc::k_l3_fwd_tc3, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
+            l3_grid = 2 * pairs * 8;                    // partial rows of the sum of a2: one per producer warp
         } else {
             const int grid = ntiles < sms ? ntiles : sms;
             launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3A_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
