@@ -15,11 +15,13 @@
 #endif
 
 #include <cstddef>
+#include <atomic>
 
 namespace pgpd {
 
-// number of kernels this library launched from the calling thread (bench.py reports it)
-inline unsigned long long& launch_counter() { static thread_local unsigned long long n = 0; return n; }
+// number of kernels this library launched, process-wide (bench.py reports it; the backward runs on autograd's
+// worker thread, so a per-thread counter would miss it)
+inline std::atomic<unsigned long long>& launch_counter() { static std::atomic<unsigned long long> n{0}; return n; }
 
 #ifdef PGPD_EMU
 template <class T> __device__ __forceinline__ T* dyn_smem() { return reinterpret_cast<T*>(emu::dyn_smem()); }

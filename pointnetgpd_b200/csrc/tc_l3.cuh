@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
     float* s_shift = s_scale + 128;
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long gt0 = 0, ck0 = 0;
+    if (p.dbg && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
@@ -137,12 +139,18 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
         // ===================== W3 producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            // every CTA walks the eight 128-channel blocks in a different rotation, so that the 148 SMs do not all pull
+            // the same lines of the (L2-resident) weight image at the same moment
+            const int rot = cta & 7;
             for (int t = t_begin; t < t_end; ++t)
                 for (int blk = 0; blk < 16; ++blk) {       // (mt, kb) in issue order
+                    const int sblk = ((((blk >> 1) + rot) & 7) << 1) | (blk & 1);
                     mbar_wait(BAR(3 + stage), phase ^ 1);
                     mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);
-                    bulk_g2s(sbase + L3_SMEM_W + stage * L3_STAGE_BYTES,
-                             reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES, L3_STAGE_BYTES, BAR(stage));
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)sblk * L3_STAGE_BYTES;
+                    const uint32_t dst = sbase + L3_SMEM_W + stage * L3_STAGE_BYTES;
+                    bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(stage));                                   // hi part
+                    bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(stage));   // lo part
                     if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
                 }
         }
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt = 0; mt < 8; ++mt) {
-                const int ch = mt * 128 + row;
+                const int ch = ((mt + (cta & 7)) & 7) * 128 + row;      // same rotation as the weight producer
                 const float mu = stats ? p.mu_s[ch] : 0.f;
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
                 { L3_T0(); mbar_wait(BAR(8 + acc), aphase); L3_ACC(6); }
@@ -343,6 +351,11 @@ __global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
 
     tc_fence_before_sync();
     __syncthreads();
+    if (p.dbg && tid == 0) {            // wall time (ns) and SM cycles of this CTA: effective clock under this load
+        long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        p.dbg[(size_t)(200 + (blockIdx.x & 31)) * 8 + 0] = gt1 - gt0;
+        p.dbg[(size_t)(200 + (blockIdx.x & 31)) * 8 + 1] = clock64() - ck0;
+    }
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
@@ -617,7 +630,8 @@ constexpr int L3C_A2_BUF = 4 * L3C_A2_PART;        // 64 KB
 constexpr int L3C_SMEM_W = 2 * L3C_A2_BUF;         // 128 KB
 constexpr int L3C_SMEM_MISC = L3C_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3C_SMEM_BYTES = L3C_SMEM_MISC + 2048 + 1024;
-constexpr int L3C_THREADS = 576;                   // W producer, MMA issuer / relay, 8 epilogue, 8 a2 producer warps
+constexpr int L3C_THREADS = 832;                   // W producer, MMA issuer / relay, 16 epilogue, 8 a2 producer warps
+constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred squares per tile (one per 64-column quarter)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -628,7 +642,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     // 0..2 w_full (local bulk copies) | 3..5 w_fullp (leader: the peer's stage landed) | 6..8 w_empty (commit, both CTAs)
     // 9,10 a2_full (leader: 16 producer warps of both CTAs) | 11,12 a2_empty (commit, both) | 13,14 tmem_full (commit, both)
-    // 15,16 tmem_empty (leader: 16 epilogue warps of both CTAs)
+    // 15,16 tmem_empty (leader: 2 x 16 epilogue warps of both CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 192);
     float* s_scale = reinterpret_cast<float*>(misc + 256);
     float* s_shift = s_scale + 128;
@@ -636,13 +650,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    long long gt0 = 0, ck0 = 0;
+    if (p.dbg && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); mbar_init(BAR(6 + i), 1); }
         mbar_init(BAR(9), 16); mbar_init(BAR(10), 16);
         mbar_init(BAR(11), 1); mbar_init(BAR(12), 1);
         mbar_init(BAR(13), 1); mbar_init(BAR(14), 1);
-        mbar_init(BAR(15), 16); mbar_init(BAR(16), 16);
+        mbar_init(BAR(15), 32); mbar_init(BAR(16), 32);
         mbar_fence_init();
     }
     if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
@@ -666,9 +682,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                     for (int kb = 0; kb < 2; ++kb) {
                         mbar_wait(BAR(6 + stage), phase ^ 1);
                         mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);
-                        const int blk = (mt4 * 2 + (int)rank) * 2 + kb;
-                        bulk_g2s(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES,
-                                 reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES, L3_STAGE_BYTES, BAR(stage));
+                        const int blk = ((((mt4 + pair) & 3) * 2 + (int)rank) * 2 + kb);      // pairs walk the channel blocks in different rotations
+                        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES;
+                        const uint32_t dst = sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES;
+                        bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(stage));
+                        bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(stage));
                         if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
                     }
         }
@@ -689,17 +707,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 int stage = 0; uint32_t wphase = 0;
                 int acc = 0; uint32_t aphase = 0;
                 int buf = 0; uint32_t bphase = 0;
+                long long w_a2 = 0, w_acc = 0, w_w = 0;
+                const long long tl0 = p.dbg ? clock64() : 0;
                 for (int t = T0; t < T1; ++t) {
-                    mbar_wait_cluster(BAR(9 + buf), bphase);                    // both halves of the operand tile staged
+                    { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(9 + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
                     tc_fence_after_sync();
                     const uint32_t a2b = sbase + buf * L3C_A2_BUF;
                     for (int mt4 = 0; mt4 < 4; ++mt4) {
-                        mbar_wait_cluster(BAR(15 + acc), aphase ^ 1);           // both epilogues drained the accumulator
+                        { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(15 + acc), aphase ^ 1); if (p.dbg) w_acc += clock64() - _t; }   // drained
                         tc_fence_after_sync();
                         const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
                         for (int kb = 0; kb < 2; ++kb) {
-                            mbar_wait(BAR(stage), wphase);                      // my half of the weight stage
-                            mbar_wait_cluster(BAR(3 + stage), wphase);          // the peer's half
+                            { const long long _t = p.dbg ? clock64() : 0;
+                              mbar_wait(BAR(stage), wphase);                    // my half of the weight stage
+                              mbar_wait_cluster(BAR(3 + stage), wphase);        // the peer's half
+                              if (p.dbg) w_w += clock64() - _t; }
                             tc_fence_after_sync();
                             const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES);
                             const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
@@ -720,12 +742,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                     mma_commit_pair(BAR(11 + buf), (uint16_t)0x3);              // operand buffer free in both CTAs
                     if (++buf == 2) { buf = 0; bphase ^= 1; }
                 }
+                if (p.dbg) {
+                    long long* o = p.dbg + (size_t)blockIdx.x * 8;
+                    o[0] = w_a2; o[1] = w_acc; o[2] = w_w; o[3] = clock64() - tl0;
+                }
             }
         }
-    } else if (warp < 10) {
-        // ===================== epilogue: my 128 channels of every 256-channel block, all 256 points of the tile =====================
+    } else if (warp < 18) {
+        // ===================== epilogue (16 warps: TMEM lane quadrant x 64-column quarter): my 128 channels of every
+        // 256-channel block, all 256 points of the tile =====================
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;                   // 0..3: which quarter of the 256 columns
         const int row = q * 32 + lane;
         const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
@@ -734,14 +761,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int ch = (mt4 * 2 + (int)rank) * 128 + row;
+                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
                 const float mu = stats ? p.mu_s[ch] : 0.f;
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
                 mbar_wait(BAR(13 + acc), aphase);
                 tc_fence_after_sync();
                 float best = -INFINITY; int bidx = 0; float css = 0.f;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
-                for (int c0 = half * (L3_NT / 2); c0 < (half + 1) * (L3_NT / 2); c0 += 32) {
+                for (int c0 = half * (L3_NT / 4); c0 < (half + 1) * (L3_NT / 4); c0 += 32) {
                     if (c0 >= nvalid) break;                // warp-uniform
                     float v[32];
                     tmem_ld32(tbase + (uint32_t)c0, v);
@@ -791,13 +818,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 atomicMax(&p.keys[(size_t)b * C3 + ch], key);
                 if (stats) {
                     const float iv = p.inv[ch];
-                    p.css_part[((size_t)t * 2 + half) * C3 + ch] = css * iv * iv;     // two partial rows per tile
+                    p.css_part[((size_t)t * L3C_EPI_ROWS + half) * C3 + ch] = css * iv * iv;     // four partial rows per tile
                 }
             }
         }
     } else {
         // ===================== a2 producer: my 128 of the tile's 256 points, double-buffered =====================
-        const int wp = warp - 10;                           // 0..7
+        const int wp = warp - 18;                           // 0..7
         const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
@@ -866,6 +893,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();                 // nobody exits while the peer may still signal this CTA
+    if (p.dbg && tid == 0) {
+        long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        p.dbg[(size_t)(200 + (blockIdx.x & 31)) * 8 + 0] = gt1 - gt0;
+        p.dbg[(size_t)(200 + (blockIdx.x & 31)) * 8 + 1] = clock64() - ck0;
+    }
     if (warp == 1) tmem_dealloc_pair<512>(tmem);
 }
 

@@ -144,7 +144,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
     fp = std::max(fp, 2 * TC_MAX_CTAS * 2 * C2);
     fp = std::max(fp, (size_t)B * w.tiles_per_cloud * C3);                   // css3 partials (CUDA-core kernel, 128-point tiles)
-    fp = std::max(fp, (size_t)B * 2 * idiv_up(N, 256) * C3);                  // css3 partials (tcgen05 kernel: 2 rows per 256-point tile)
+    fp = std::max(fp, (size_t)B * 4 * idiv_up(N, 256) * C3);                  // css3 partials (tcgen05 kernels: up to 4 rows per 256-point tile)
     if (backward) {
         fp = std::max(fp, (size_t)w.nb_gram * C2 * C2);                      // Gram partials
         fp = std::max(fp, (size_t)w.nb_l2 * 2 * C2);                         // BN2 backward partials
@@ -972,7 +972,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 #ifndef PGPD_EMU
         {
             static const bool pilot_ok = !(getenv("PGPD_L3_PILOT") && atoi(getenv("PGPD_L3_PILOT")) == 0);
-            static const int l3v = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 1;
+            static const int l3v = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 3;
             if (a.use_tc && (tc_mask() & 1) && pilot_ok && l3v != 2 && M >= 65536) pstride = M / 32768;
         }
 #endif
@@ -990,9 +990,9 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     int n_css = 0, n_css_mult = 1, l3_grid = 0;
 #ifndef PGPD_EMU
     if (a.use_tc && (tc_mask() & 1)) {
-        // layer-3 kernel version: 1 (default) = single-CTA 256-point tiles; 2 = CTA pairs sharing the weight stream
-        // (PGPD_L3_VERSION=2; correct but currently slower: its 768-cycle stages out-run the 3-deep weight ring)
-        static const int l3ver = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 1;
+        // layer-3 kernel version (PGPD_L3_VERSION): 3 (default) = CTA pairs with cta_group::2 MMAs; 1 = single-CTA 256-point
+        // tiles; 2 = CTA pairs that only share the weight stream by multicast (correct but slower)
+        static const int l3ver = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 3;
         const int tile_pts = l3ver == 2 ? tc::L3B_NT : tc::L3_NT;
         const int tpc = idiv_up(a.N, tile_pts), ntiles = a.B * tpc;
         launch(tc::k_prepack_w3, dim3(C3), dim3(128), 0, s, t.conv[2].w, t.bn[2].gamma,
@@ -1017,7 +1017,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
             launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3A_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
         }
         profiler().end(s);
-        n_css_mult = l3ver == 2 ? 1 : 2;
+        n_css_mult = l3ver == 2 ? 1 : (l3ver == 3 ? tc::L3C_EPI_ROWS : 2);
         n_css = ntiles * n_css_mult;
     } else
 #endif

@@ -17,8 +17,15 @@ lib = A.load()
 buf = (ctypes.c_longlong * (256 * 8))()
 lib.pgpd_debug_l3_counters.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
 lib.pgpd_debug_l3_counters(buf)
-a = np.array(buf[:], dtype=np.int64).reshape(256, 8)[:148]
+full = np.array(buf[:], dtype=np.int64).reshape(256, 8)
+a = full[:148]
+ver = os.environ.get("PGPD_L3_VERSION", "1")
+if ver == "3":
+    a = a[0::2]          # leader CTAs hold the MMA-loop counters
+g = full[200:232]
+g = g[g[:, 0] > 0]
+print("version", ver, ": CTA wall time %.1f us, %.0f SM cycles -> effective SM clock %.3f GHz" % (g[:, 0].mean() / 1e3, g[:, 1].mean(), (g[:, 1] / g[:, 0]).mean()))
 names = ["mma wait a2_full", "mma wait tmem_empty", "mma wait w_full", "mma total", "prod wait a2_empty", "prod stage tile", "epi wait tmem_full", "epi work"]
-tiles = 2048 / 148
+tiles = 2048 / (74 if ver == "3" else 148)
 for i, n in enumerate(names):
     print("%-22s mean %10.0f cycles/CTA   %8.0f per tile" % (n, a[:, i].mean(), a[:, i].mean() / tiles))
