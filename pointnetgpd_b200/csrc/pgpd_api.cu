@@ -72,6 +72,17 @@ static int check_common(int what, const void* m, const float* x, int B, int N, i
     if ((long long)B * N > 0x7fffffffLL / 128) return fail(PGPD_E_ARG, "B*N too large for this build (B*N*128 must fit in int32)");
     if (!ws || ((uintptr_t)ws & 255)) return fail(PGPD_E_WORKSPACE, "workspace is null or not 256-byte aligned");
     if (ws_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small (see pgpd_workspace_bytes)");
+    {
+        // weights are read with 16-byte vector loads
+        const pgpd_model* mm = static_cast<const pgpd_model*>(m);
+        bool ok = true;
+        auto chk_t = [&](const pgpd_tower& t) { for (int i = 0; i < 3; ++i) ok = ok && !((uintptr_t)t.conv[i].w & 15); };
+        auto chk_h = [&](const pgpd_head& h) { for (int i = 0; i < 3; ++i) ok = ok && !((uintptr_t)h.fc[i].w & 15); };
+        chk_t(mm->stn_tower); chk_h(mm->stn_head);
+        if (what >= PGPD_FEAT) chk_t(mm->trunk);
+        if (what == PGPD_CLS) chk_h(mm->cls_head);
+        if (!ok || ((uintptr_t)x & 3)) return fail(PGPD_E_ARG, "conv / fc weight pointers must be 16-byte aligned");
+    }
     return PGPD_OK;
 }
 
@@ -257,6 +268,7 @@ int pgpd_tower_forward(const pgpd_tower* t, const float* x, const float* trans, 
                        int relu_last, int flags, float* pooled,
                        void* workspace, size_t workspace_bytes, void* stream) {
     if (!t || !x || !pooled) return fail(PGPD_E_ARG, "null pointer");
+    for (int i = 0; i < 3; ++i) if ((uintptr_t)t->conv[i].w & 15) return fail(PGPD_E_ARG, "conv weight pointers must be 16-byte aligned");
     if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
     if ((long long)B * N > 0x7fffffffLL / 128) return fail(PGPD_E_ARG, "B*N too large");
     const bool train = (flags & PGPD_F_TRAIN) != 0;
@@ -276,6 +288,7 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
                         const float* dpooled, float* dtrans_out,
                         void* workspace, size_t workspace_bytes, void* stream) {
     if (!t || !g || !x || !dpooled) return fail(PGPD_E_ARG, "null pointer");
+    for (int i = 0; i < 3; ++i) if ((uintptr_t)t->conv[i].w & 15) return fail(PGPD_E_ARG, "conv weight pointers must be 16-byte aligned");
     if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
     if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
     if (trans && !dtrans_out) return fail(PGPD_E_ARG, "dtrans_out is null but trans is given");

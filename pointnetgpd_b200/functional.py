@@ -65,7 +65,13 @@ def _check_tensor(t, name, device):
         raise RuntimeError("pgpd: %s is on %s but the input is on %s" % (name, t.device, device))
     if t.dtype not in (torch.float32, torch.int64):
         raise TypeError("pgpd: %s must be float32 (got %s); the fused path computes in fp32" % (name, t.dtype))
-    return t if t.is_contiguous() else t.contiguous()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        # the ABI wants 16-byte aligned weights (vector loads).  nn.DataParallel replicas are views into a coalesced
+        # broadcast buffer at arbitrary 4-byte offsets (torch.nn.parallel.replicate): take an aligned copy.
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
 
 
 class _Fused(torch.autograd.Function):

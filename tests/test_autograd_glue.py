@@ -59,6 +59,37 @@ def test_module_train_step_through_autograd(emu):
             assert np.allclose(b.numpy(), g["buf_f64/" + name], atol=1e-4), name
 
 
+def test_misaligned_parameter_views_like_dataparallel_replicas(emu):
+    """nn.DataParallel replicas are views into a coalesced broadcast buffer at arbitrary 4-byte offsets
+    (torch.nn.parallel.replicate); the C ABI wants 16-byte aligned weights, so the glue must pass aligned copies and the
+    gradients must still reach the (misaligned) parameters."""
+    c = load_case("fresh_b8_n96_k2")
+    m = PointNetCls(num_points=c["N"], input_chann=3, k=c["k"])
+    _load_state(m, c["state"])
+    ref = PointNetCls(num_points=c["N"], input_chann=3, k=c["k"])
+    _load_state(ref, c["state"])
+    for name, p in list(m.named_parameters()):
+        flat = torch.zeros(p.numel() + 1)
+        flat[1:] = p.detach().reshape(-1)
+        view = flat[1:].view_as(p)                       # 4 bytes past a 64-byte aligned allocation
+        assert view.data_ptr() % 16 != 0
+        mod = m
+        parts = name.split(".")
+        for q in parts[:-1]:
+            mod = getattr(mod, q)
+        mod._parameters[parts[-1]] = torch.nn.Parameter(view)
+    m.train(); ref.train()
+    x = torch.tensor(c["x"]); y = torch.tensor(c["y"])
+    out = []
+    for mm in (m, ref):
+        logp, _ = _apply(mm, A.PGPD_CLS, x, k=c["k"])
+        torch.nn.functional.nll_loss(logp, y).backward()
+        out.append(logp.detach())
+    assert torch.equal(out[0], out[1])
+    for (n, p), (_, r) in zip(m.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and torch.equal(p.grad, r.grad), n
+
+
 def test_eval_no_grad_and_eval_backward_raises(emu):
     c = load_case("wild_b6_n80_k3")
     m = PointNetCls(num_points=c["N"], k=c["k"])
