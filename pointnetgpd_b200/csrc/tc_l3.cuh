@@ -633,17 +633,24 @@ constexpr int L3C_SMEM_BYTES = L3C_SMEM_MISC + 2048 + 1024;
 constexpr int L3C_THREADS = 832;                   // W producer, MMA issuer / relay, 16 epilogue, 8 a2 producer warps
 constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred squares per tile (one per 64-column quarter)
 
+// SPLIT: the weight ring is managed in 16 KB sub-stages (the hi and the lo half of a stage separately) and the passes
+// run in the order hi.hi, hi.lo, lo.hi, so that the hi half is released after 8 of a stage's 12 MMAs and its refill
+// starts ~0.5 k cycles earlier -- the 3-stage ring otherwise runs dry (profiles/README.md).
+template <bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p) {
+    constexpr int NSUB = SPLIT ? 6 : 3;                    // ring slots
+    constexpr int SUB_BYTES = SPLIT ? L3_STAGE_BYTES / 2 : L3_STAGE_BYTES;
+    constexpr int W_FULL = 0, W_FULLP = 6, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 24;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     unsigned char* misc = smem + L3C_SMEM_MISC;
     const uint32_t bar0 = sbase + L3C_SMEM_MISC;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // 0..2 w_full (local bulk copies) | 3..5 w_fullp (leader: the peer's stage landed) | 6..8 w_empty (commit, both CTAs)
-    // 9,10 a2_full (leader: 16 producer warps of both CTAs) | 11,12 a2_empty (commit, both) | 13,14 tmem_full (commit, both)
-    // 15,16 tmem_empty (leader: 2 x 16 epilogue warps of both CTAs)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 192);
+    // W_FULL.. w_full (local bulk copies) | W_FULLP.. (leader: the peer's slot landed) | W_EMPTY.. (commit, both CTAs)
+    // A2_FULL (leader: 16 producer warps of both CTAs) | A2_EMPTY (commit, both) | TM_FULL (commit, both)
+    // TM_EMPTY (leader: 2 x 16 epilogue warps of both CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 240);
     float* s_scale = reinterpret_cast<float*>(misc + 256);
     float* s_shift = s_scale + 128;
 
@@ -654,11 +661,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     if (p.dbg && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); mbar_init(BAR(6 + i), 1); }
-        mbar_init(BAR(9), 16); mbar_init(BAR(10), 16);
-        mbar_init(BAR(11), 1); mbar_init(BAR(12), 1);
-        mbar_init(BAR(13), 1); mbar_init(BAR(14), 1);
-        mbar_init(BAR(15), 32); mbar_init(BAR(16), 32);
+        for (int i = 0; i < NSUB; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_FULLP + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
+        mbar_init(BAR(A2_FULL), 16); mbar_init(BAR(A2_FULL + 1), 16);
+        mbar_init(BAR(A2_EMPTY), 1); mbar_init(BAR(A2_EMPTY + 1), 1);
+        mbar_init(BAR(TM_FULL), 1); mbar_init(BAR(TM_FULL + 1), 1);
+        mbar_init(BAR(TM_EMPTY), 32); mbar_init(BAR(TM_EMPTY + 1), 32);
         mbar_fence_init();
     }
     if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
@@ -680,14 +687,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             for (int t = T0; t < T1; ++t)
                 for (int mt4 = 0; mt4 < 4; ++mt4)
                     for (int kb = 0; kb < 2; ++kb) {
-                        mbar_wait(BAR(6 + stage), phase ^ 1);
-                        mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);
                         const int blk = ((((mt4 + pair) & 3) * 2 + (int)rank) * 2 + kb);      // pairs walk the channel blocks in different rotations
                         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES;
-                        const uint32_t dst = sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES;
-                        bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(stage));
-                        bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(stage));
-                        if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
+                        for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                            mbar_wait(BAR(W_EMPTY + stage), phase ^ 1);
+                            mbar_arrive_expect_tx(BAR(W_FULL + stage), SUB_BYTES);
+                            const uint32_t dst = sbase + L3C_SMEM_W + stage * SUB_BYTES;
+                            if (SPLIT) {
+                                bulk_g2s(dst, src + part * SUB_BYTES, SUB_BYTES, BAR(W_FULL + stage));
+                            } else {
+                                bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(W_FULL + stage));
+                                bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(W_FULL + stage));
+                            }
+                            if (++stage == NSUB) { stage = 0; phase ^= 1; }
+                        }
                     }
         }
     } else if (warp == 1) {
@@ -696,10 +709,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 // ===================== peer: relay "my weight stage has landed" to the leader =====================
                 int stage = 0; uint32_t phase = 0;
                 for (int t = T0; t < T1; ++t)
-                    for (int blk = 0; blk < 8; ++blk) {
-                        mbar_wait(BAR(stage), phase);
-                        mbar_arrive_cluster(BAR(3 + stage), 0u);
-                        if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
+                    for (int blk = 0; blk < (SPLIT ? 16 : 8); ++blk) {
+                        mbar_wait(BAR(W_FULL + stage), phase);
+                        mbar_arrive_cluster(BAR(W_FULLP + stage), 0u);
+                        if (++stage == NSUB) { stage = 0; phase ^= 1; }
                     }
             } else {
                 // ===================== leader: MMA issuer for the pair =====================
@@ -710,36 +723,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 long long w_a2 = 0, w_acc = 0, w_w = 0;
                 const long long tl0 = p.dbg ? clock64() : 0;
                 for (int t = T0; t < T1; ++t) {
-                    { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(9 + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
+                    { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(A2_FULL + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
                     tc_fence_after_sync();
                     const uint32_t a2b = sbase + buf * L3C_A2_BUF;
                     for (int mt4 = 0; mt4 < 4; ++mt4) {
-                        { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(15 + acc), aphase ^ 1); if (p.dbg) w_acc += clock64() - _t; }   // drained
+                        { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(TM_EMPTY + acc), aphase ^ 1); if (p.dbg) w_acc += clock64() - _t; }   // drained
                         tc_fence_after_sync();
                         const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
                         for (int kb = 0; kb < 2; ++kb) {
-                            { const long long _t = p.dbg ? clock64() : 0;
-                              mbar_wait(BAR(stage), wphase);                    // my half of the weight stage
-                              mbar_wait_cluster(BAR(3 + stage), wphase);        // the peer's half
-                              if (p.dbg) w_w += clock64() - _t; }
-                            tc_fence_after_sync();
-                            const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES);
                             const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
+                            constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);      // the a2 lo part
+                            auto wait_w = [&]() {
+                                const long long _t = p.dbg ? clock64() : 0;
+                                mbar_wait(BAR(W_FULL + stage), wphase);                 // my half of the weight slot
+                                mbar_wait_cluster(BAR(W_FULLP + stage), wphase);        // the peer's half
+                                if (p.dbg) w_w += clock64() - _t;
+                                tc_fence_after_sync();
+                            };
+                            auto release_w = [&]() {
+                                mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);   // slot free in both CTAs
+                                if (++stage == NSUB) { stage = 0; wphase ^= 1; }
+                            };
+                            if (SPLIT) {
+                                wait_w();                                               // W hi
+                                const uint64_t dwh = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * SUB_BYTES);
 #pragma unroll
-                            for (int pass = 0; pass < 3; ++pass) {
-                                const uint32_t oa = (pass == 1) ? 16384u : 0u;
-                                const uint32_t ob = (pass == 2) ? (uint32_t)(2 * L3C_A2_PART) : 0u;
+                                for (int k = 0; k < 4; ++k) mma_f16_pair(d, dwh + ((k * 32) >> 4), db + ((k * 32) >> 4), IDESC, (kb | k) ? 1u : 0u);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC, (kb | pass | k) ? 1u : 0u);
+                                for (int k = 0; k < 4; ++k) mma_f16_pair(d, dwh + ((k * 32) >> 4), db + ((OB_LO + k * 32) >> 4), IDESC, 1u);
+                                release_w();
+                                wait_w();                                               // W lo
+                                const uint64_t dwl = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * SUB_BYTES);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) mma_f16_pair(d, dwl + ((k * 32) >> 4), db + ((k * 32) >> 4), IDESC, 1u);
+                                release_w();
+                            } else {
+                                wait_w();
+                                const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * SUB_BYTES);
+#pragma unroll
+                                for (int pass = 0; pass < 3; ++pass) {
+                                    const uint32_t oa = (pass == 1) ? 16384u : 0u;
+                                    const uint32_t ob = (pass == 2) ? OB_LO : 0u;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC, (kb | pass | k) ? 1u : 0u);
+                                }
+                                release_w();
                             }
-                            mma_commit_pair(BAR(6 + stage), (uint16_t)0x3);     // stage free in both CTAs
-                            if (++stage == L3_STAGES) { stage = 0; wphase ^= 1; }
                         }
-                        mma_commit_pair(BAR(13 + acc), (uint16_t)0x3);          // accumulator complete in both CTAs
+                        mma_commit_pair(BAR(TM_FULL + acc), (uint16_t)0x3);        // accumulator complete in both CTAs
                         if (++acc == 2) { acc = 0; aphase ^= 1; }
                     }
-                    mma_commit_pair(BAR(11 + buf), (uint16_t)0x3);              // operand buffer free in both CTAs
+                    mma_commit_pair(BAR(A2_EMPTY + buf), (uint16_t)0x3);        // operand buffer free in both CTAs
                     if (++buf == 2) { buf = 0; bphase ^= 1; }
                 }
                 if (p.dbg) {
@@ -764,7 +799,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
                 const float mu = stats ? p.mu_s[ch] : 0.f;
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
-                mbar_wait(BAR(13 + acc), aphase);
+                mbar_wait(BAR(TM_FULL + acc), aphase);
                 tc_fence_after_sync();
                 float best = -INFINITY; int bidx = 0; float css = 0.f;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
@@ -810,7 +845,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) {                            // one arrival per warp on the LEADER's barrier
-                    if (leader) mbar_arrive(BAR(15 + acc)); else mbar_arrive_cluster(BAR(15 + acc), 0u);
+                    if (leader) mbar_arrive(BAR(TM_EMPTY + acc)); else mbar_arrive_cluster(BAR(TM_EMPTY + acc), 0u);
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
@@ -844,7 +879,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 nv2 = nv2 < 0 ? 0 : (nv2 > L3C_NH ? L3C_NH : nv2);
                 if (nv2 > 0) l2_prefetch(p.Y2 + ((size_t)b2 * p.N + m0) * C2, (uint32_t)nv2 * C2 * 4u);
             }
-            mbar_wait(BAR(11 + buf), bphase ^ 1);           // the MMAs that read this buffer two tiles ago are done
+            mbar_wait(BAR(A2_EMPTY + buf), bphase ^ 1);     // the MMAs that read this buffer two tiles ago are done
             unsigned char* a2b = smem + buf * L3C_A2_BUF;
             constexpr int U = 8;
             for (int i0 = 0; i0 < L3C_NH / 8; i0 += U) {
@@ -878,7 +913,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {                                // one arrival per warp on the LEADER's barrier
-                if (leader) mbar_arrive(BAR(9 + buf)); else mbar_arrive_cluster(BAR(9 + buf), 0u);
+                if (leader) mbar_arrive(BAR(A2_FULL + buf)); else mbar_arrive_cluster(BAR(A2_FULL + buf), 0u);
             }
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
@@ -916,7 +951,8 @@ inline DevInfo& dev_info() {
         if (d.sms > 256) d.sms = 256;      // per-CTA partial buffers are sized for <= 256 CTAs (plan_tower_scratch)
         cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, L3B_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
         d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
         if (e != cudaSuccess) cudaGetLastError();
     }

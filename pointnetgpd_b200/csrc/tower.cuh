@@ -1010,7 +1010,10 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
             launch(tc::k_l3_fwd_tc2, dim3(2 * pairs), dim3(tc::L3_THREADS), (size_t)tc::L3B_SMEM_BYTES, s, p);
         } else if (l3ver == 3) {
             const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
-            launch(tc::k_l3_fwd_tc3, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
+            // PGPD_L3_SPLIT=1: 16 KB sub-stages of the weight ring (see the kernel)
+            static const bool l3split = getenv("PGPD_L3_SPLIT") ? atoi(getenv("PGPD_L3_SPLIT")) != 0 : false;
+            if (l3split) launch(tc::k_l3_fwd_tc3<true>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
+            else launch(tc::k_l3_fwd_tc3<false>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
             l3_grid = 2 * pairs * 8;                    // partial rows of the sum of a2: one per producer warp
         } else {
             const int grid = ntiles < sms ? ntiles : sms;
