@@ -254,80 +254,4 @@ struct GramTC {
     __device__ static float out_scale(const Params&, int) { return 1.0f / (ACT_SCALE * ACT_SCALE); }
 };
 
-// ==================================================================================================================
-// dW2[c][k] = sum_P dy2[P][c] a1[P][k];  dy2 columns are scaled per CHANNEL by 2^e_c (esc), undone per output row
-// ==================================================================================================================
-struct DW2TC {
-    static constexpr int NB = 64;
-    static constexpr bool SAME = false;
-    struct Params {
-        size_t M; int ntiles; float* part;
-        const float* DZ2; const float* Y2; const float* scale2; const float* mean2; const float* rstd2;
-        const float* m1; const float* m2; const float* esc; const float* einv; const float* A1;
-    };
-    struct ProdA { float4 s, mu, r, m1, m2, e; };
-    struct RawA { float4 dz, y; };
-    __device__ static void prodA_begin(ProdA& q, const Params& p, int cg) {
-        q.s = *reinterpret_cast<const float4*>(p.scale2 + 4 * cg);
-        q.mu = *reinterpret_cast<const float4*>(p.mean2 + 4 * cg);
-        q.r = *reinterpret_cast<const float4*>(p.rstd2 + 4 * cg);
-        q.m1 = *reinterpret_cast<const float4*>(p.m1 + 4 * cg);
-        q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
-        q.e = *reinterpret_cast<const float4*>(p.esc + 4 * cg);
-        // fold: e*dy2 = (e*s)*(dz - m1) - (e*s*r*m2)*(y - mu)
-        q.s.x *= q.e.x; q.s.y *= q.e.y; q.s.z *= q.e.z; q.s.w *= q.e.w;
-        q.r.x *= q.s.x * q.m2.x; q.r.y *= q.s.y * q.m2.y; q.r.z *= q.s.z * q.m2.z; q.r.w *= q.s.w * q.m2.w;
-    }
-    __device__ static void prefetch(const Params& p, size_t P0, int nrows) {
-        l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
-        l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
-        l2_prefetch(p.A1 + P0 * C1, (uint32_t)nrows * C1 * 4u);
-    }
-    __device__ static void fetchA(ProdA&, const Params& p, size_t P, bool valid, int cg, RawA& r) {
-        r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz;
-        if (valid) {
-            r.dz = *reinterpret_cast<const float4*>(p.DZ2 + P * C2 + 4 * cg);
-            r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
-        }
-    }
-    __device__ static float clampf(float x) { return fminf(fmaxf(x, -60000.f), 60000.f); }
-    __device__ static void transformA(ProdA& q, const Params&, bool valid, const RawA& r, float (&v)[4]) {
-        v[0] = valid ? clampf(q.s.x * (r.dz.x - q.m1.x) - q.r.x * (r.y.x - q.mu.x)) : 0.f;
-        v[1] = valid ? clampf(q.s.y * (r.dz.y - q.m1.y) - q.r.y * (r.y.y - q.mu.y)) : 0.f;
-        v[2] = valid ? clampf(q.s.z * (r.dz.z - q.m1.z) - q.r.z * (r.y.z - q.mu.z)) : 0.f;
-        v[3] = valid ? clampf(q.s.w * (r.dz.w - q.m1.w) - q.r.w * (r.y.w - q.mu.w)) : 0.f;
-    }
-    struct ProdB { int d; };
-    struct RawB { float4 a; };
-    __device__ static void prodB_begin(ProdB&, const Params&, int) {}
-    __device__ static void fetchB(ProdB&, const Params& p, size_t P, bool valid, int cg, RawB& r) {
-        r.a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) r.a = *reinterpret_cast<const float4*>(p.A1 + P * C1 + 4 * cg);
-    }
-    __device__ static void transformB(ProdB&, const Params&, bool, const RawB& r, float (&v)[4]) {
-        v[0] = fminf(r.a.x * ACT_SCALE, 60000.f); v[1] = fminf(r.a.y * ACT_SCALE, 60000.f);
-        v[2] = fminf(r.a.z * ACT_SCALE, 60000.f); v[3] = fminf(r.a.w * ACT_SCALE, 60000.f);
-    }
-    __device__ static float out_scale(const Params& p, int m) { return p.einv[m] * (1.0f / ACT_SCALE); }
-};
-
-// per-channel power-of-two scale for the dy2 operand of DW2TC from the maxima gathered by L2BwdATC:
-//   |dy2[.,c]| <= |s2_c| (max|dz2| + |m1_c| + max|yhat2| |m2_c|)  =: bnd_c ;  esc_c = 2^e with bnd_c 2^e in [2^12, 2^13)
-__global__ void k_dy2_scale(const float* __restrict__ pmax, int G, const float* __restrict__ scale2,
-                            const float* __restrict__ m1, const float* __restrict__ m2,
-                            float* __restrict__ esc, float* __restrict__ einv) {
-    const int c = (int)threadIdx.x;
-    if (c >= C2) return;
-    float mxdz = 0.f, mxyh = 0.f;
-    for (int g = 0; g < G; ++g) {
-        mxdz = fmaxf(mxdz, pmax[(size_t)g * 2 * C2 + c]);
-        mxyh = fmaxf(mxyh, pmax[(size_t)g * 2 * C2 + C2 + c]);
-    }
-    const float bnd = fabsf(scale2[c]) * (mxdz + fabsf(m1[c]) + mxyh * fabsf(m2[c]));
-    int e = 139 - (int)((__float_as_uint(bnd) >> 23) & 0xFFu);
-    e = (bnd > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
-    esc[c] = __uint_as_float((uint32_t)(127 + e) << 23);
-    einv[c] = __uint_as_float((uint32_t)(127 - e) << 23);
-}
-
 }}  // namespace pgpd::tc

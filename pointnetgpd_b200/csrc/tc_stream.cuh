@@ -401,98 +401,4 @@ struct L2BwdATC {
     }
 };
 
-// ==================================================================================================================
-// layer 2 backward, pass 2b:  d a1[P][k] = sum_c W2[c][k] dy2[P][c],  dy2 = s2 (dz2 - m1 - yhat2 m2);
-// dz1 = mask * d a1 (stored); per-channel sums of dz1 and dz1*yhat1 (BatchNorm1 backward).
-// dy2 rows are scaled per POINT by a power of two (gradients have no fixed magnitude); aux[0] undoes it.
-// yhat1 is only needed where dz1 != 0, i.e. where a1 > 0, and there a1 = gamma1*yhat1 + beta1, so
-// yhat1 = (a1 - beta1) / gamma1 -- no need to recompute the layer-1 pre-activation from the coordinates.
-// ==================================================================================================================
-struct L2BwdBTC {
-    static constexpr int KD = 128;
-    struct Params {
-        const __half* Aimg; size_t M; int ntiles;
-        const float* DZ2; const float* Y2; const float* scale2; const float* mean2; const float* rstd2;
-        const float* m1; const float* m2;
-        const float* inv; const float* A1; const float* gamma1; const float* beta1;
-        float* DZ1; float* part;     // part [rows][2][64]
-    };
-    struct Prod { float4 s, mu, r, m1, m2; };
-    __device__ static void prod_begin(Prod& q, const Params& p, int cg) {
-        q.s = *reinterpret_cast<const float4*>(p.scale2 + 4 * cg);
-        q.mu = *reinterpret_cast<const float4*>(p.mean2 + 4 * cg);
-        q.r = *reinterpret_cast<const float4*>(p.rstd2 + 4 * cg);
-        q.m1 = *reinterpret_cast<const float4*>(p.m1 + 4 * cg);
-        q.m2 = *reinterpret_cast<const float4*>(p.m2 + 4 * cg);
-        // fold: dy2 = s*(dz - m1) - (s*r*m2)*(y - mu)
-        q.r.x *= q.s.x * q.m2.x; q.r.y *= q.s.y * q.m2.y; q.r.z *= q.s.z * q.m2.z; q.r.w *= q.s.w * q.m2.w;
-    }
-    struct Raw { float4 dz, y; };
-    __device__ static void prefetch(const Params& p, size_t P0, int nrows) {
-        l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
-        l2_prefetch(p.Y2 + P0 * C2, (uint32_t)nrows * C2 * 4u);
-        l2_prefetch(p.A1 + P0 * C1, (uint32_t)nrows * C1 * 4u);
-    }
-    __device__ static void fetch(Prod&, const Params& p, size_t P, bool valid, int cg, Raw& r) {
-        r.dz = make_float4(0.f, 0.f, 0.f, 0.f); r.y = r.dz;
-        if (valid) {
-            r.dz = *reinterpret_cast<const float4*>(p.DZ2 + P * C2 + 4 * cg);
-            r.y = *reinterpret_cast<const float4*>(p.Y2 + P * C2 + 4 * cg);
-        }
-    }
-    __device__ static float transform(Prod& q, const Params&, size_t, bool valid, int, const Raw& r, float (&v)[4]) {
-        const float4 dz = r.dz, y = r.y;
-        float d0 = q.s.x * (dz.x - q.m1.x) - q.r.x * (y.x - q.mu.x);
-        float d1 = q.s.y * (dz.y - q.m1.y) - q.r.y * (y.y - q.mu.y);
-        float d2 = q.s.z * (dz.z - q.m1.z) - q.r.z * (y.z - q.mu.z);
-        float d3 = q.s.w * (dz.w - q.m1.w) - q.r.w * (y.w - q.mu.w);
-        if (!valid) { d0 = d1 = d2 = d3 = 0.f; }
-        float mx = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3)));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        // power of two 2^e bringing the row maximum into [2^13, 2^14): e = 140 - biased_exponent(mx)
-        int e = 140 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-        e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
-        const float sc = __uint_as_float((uint32_t)(127 + e) << 23);
-        v[0] = d0 * sc; v[1] = d1 * sc; v[2] = d2 * sc; v[3] = d3 * sc;
-        return __uint_as_float((uint32_t)(127 - e) << 23);
-    }
-    struct Epi { float inv, be, ginv, s1, s2; };
-    __device__ static void epi_begin(Epi& e, const Params& p, int k) {
-        e.s1 = 0.f; e.s2 = 0.f; e.inv = 0.f; e.be = 0.f; e.ginv = 0.f;
-        if (k < C1) {
-            e.inv = p.inv[k]; e.be = p.beta1[k];
-            const float g = p.gamma1[k];
-            e.ginv = g != 0.f ? 1.0f / g : 0.f;
-        }
-    }
-    __device__ static void epi_cols(Epi& e, const Params& p, int k, size_t P0, int nvalid, const float (&v)[32], const float* aux) {
-        if (k >= C1) return;
-#pragma unroll
-        for (int h0 = 0; h0 < 32; h0 += EPI_BATCH) {
-            float a[EPI_BATCH];
-#pragma unroll
-            for (int jj = 0; jj < EPI_BATCH; ++jj) a[jj] = (h0 + jj < nvalid) ? __ldg(p.A1 + (P0 + h0 + jj) * C1 + k) : 0.f;
-#pragma unroll
-            for (int jj = 0; jj < EPI_BATCH; ++jj) {
-                const int j = h0 + jj;
-                if (j < nvalid) {
-                    const float da1 = v[j] * e.inv * aux[j];
-                    const bool on = a[jj] > 0.f;
-                    const float dz = on ? da1 : 0.f;
-                    p.DZ1[(P0 + j) * C1 + k] = dz;
-                    const float yh = (a[jj] - e.be) * e.ginv;       // only used where dz != 0
-                    e.s1 += dz;
-                    e.s2 = fmaf(dz, yh, e.s2);
-                }
-            }
-        }
-    }
-    __device__ static void epi_end(Epi& e, const Params& p, int k, int row) {
-        if (k >= C1) return;
-        float* o = p.part + (size_t)row * 2 * C1;
-        o[k] = e.s1; o[C1 + k] = e.s2;
-    }
-};
-
 }}  // namespace pgpd::tc

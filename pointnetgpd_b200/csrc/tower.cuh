@@ -32,7 +32,7 @@
 namespace pgpd {
 
 // which tcgen05 kernels may run (debugging aid): PGPD_TC_MASK bit0 layer-3 fwd, bit1 layer-2 fwd,
-// bit2 Gram, bit3 layer-2 bwd pass 1, bit4 fused layer-2/1 backward pass, bit5 (older layer-2 bwd pass 2b), bit6 FC-head GEMMs.
+// bit2 Gram (only with PGPD_KA=0), bit3 layer-2 bwd pass 1, bit4 fused layer-2/1 backward pass, bit5 unused, bit6 FC-head GEMMs.
 // Default: all.
 inline unsigned tc_mask() {
     static int m = -1;
@@ -89,7 +89,6 @@ struct TowerScratch {
     float* da2s;      // [B*1024][128] compact rows of the sparse part of d a2
     int* slot;        // [M]  row in da2s or -1
     float* DZ2;       // [M][128]
-    float* DZ1;       // [M][64]
     float* m1_2; float* m2_2;   // [128]
     float* m1_1; float* m2_1;   // [64]
     // fused layer-2/1 backward (l2bwd.cuh, tc_kb.cuh)
@@ -103,7 +102,7 @@ struct TowerScratch {
     float* kb_H;      // [kb_rows][64*3]
     int kb_rows;
     // sizes
-    int nb_a1, nb_a2, nb_l2, nb_gram, nb_dw2, tiles_per_cloud;
+    int nb_a1, nb_a2, nb_l2, nb_gram, tiles_per_cloud;
     size_t fpart_elems;
 };
 
@@ -111,7 +110,6 @@ struct TowerWs : TowerKeep, TowerScratch {};
 
 constexpr int A1_CHUNK = 64;       // points per block of k_a1
 constexpr int GRAM_CHUNK = 1024;   // points per split-K block of the Gram GEMM
-constexpr int DW2_CHUNK = 2048;    // points per split-K block of the dW2 GEMM
 constexpr int KB_MAX_PART = KB_REF_MAX_BLOCKS;   // per-block partial slots of the fused layer-2/1 backward pass
 
 inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
@@ -134,7 +132,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.nb_a2 = (int)std::min<size_t>(8192, (M + 15) / 16);
     w.nb_l2 = (int)((M + 127) / 128);
     w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
-    w.nb_dw2 = (int)((M + DW2_CHUNK - 1) / DW2_CHUNK);
     w.moments = c.take<double>((size_t)B * 12);
     w.rtmp = c.take<double>((size_t)REDUCE_MAX_SLICES * C2 * C2);
     w.dpart = c.take<double>((size_t)std::max(w.nb_a1 * C1, w.nb_a2 * C2));
@@ -148,7 +145,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     if (backward) {
         fp = std::max(fp, (size_t)w.nb_gram * C2 * C2);                      // Gram partials
         fp = std::max(fp, (size_t)w.nb_l2 * 2 * C2);                         // BN2 backward partials
-        fp = std::max(fp, (size_t)w.nb_dw2 * C2 * C1);                       // dW2 partials
         fp = std::max(fp, (size_t)B * (C1 * 3));                             // dW1 partials
         fp = std::max(fp, 2 * TC_MAX_CTAS * C2 * C2);                        // per-CTA Gram (hi.hi, hi.lo) / BN-backward partials
     }
@@ -178,7 +174,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         w.da2s = c.take<float>((size_t)B * C3 * C2);
         w.slot = c.take<int>(M);
         w.DZ2 = c.take<float>(M * C2);
-        w.DZ1 = c.take<float>(M * C1);
         w.m1_2 = c.take<float>(C2); w.m2_2 = c.take<float>(C2);
         w.m1_1 = c.take<float>(C1); w.m2_1 = c.take<float>(C1);
         w.Kmat = c.take<float>(C1 * C1);
@@ -733,171 +728,6 @@ struct ProbL2BwdA {
     }
 };
 
-// dy2[P][c] = s2[c] * (dz2 - m1[c] - yhat2 * m2[c])
-struct Dy2 {
-    const float* DZ2; const float* Y2; BnState st2; const float* m1; const float* m2;
-    __device__ float at(size_t P, int c) const {
-        const float yhat = (Y2[P * C2 + c] - st2.mean[c]) * st2.rstd[c];
-        return st2.scale[c] * (DZ2[P * C2 + c] - m1[c] - yhat * m2[c]);
-    }
-};
-
-// dW2[c][k] = sum_P dy2[P][c] a1[P][k], split over point chunks
-struct ProbDW2 {
-    static constexpr bool A_KFAST = false, B_NFAST = true;
-    static constexpr int SCRATCH = 0;
-    using Cfg = CfgTall;
-    Dy2 dy; const float* A1; float* part; size_t M;
-    struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const {
-        b.m0 = 0; b.n0 = 0;
-        size_t k0 = (size_t)blockIdx.x * DW2_CHUNK, k1 = k0 + DW2_CHUNK;
-        b.k0 = (int)k0; b.k1 = (int)(k1 < M ? k1 : M);
-    }
-    __device__ void prologue(const Blk&, float*) const {}
-    __device__ float loadA(const Blk&, const float*, int m, int k) const { return dy.at((size_t)k, m); }
-    __device__ float loadB(const Blk&, const float*, int k, int n) const { return A1[(size_t)k * C1 + n]; }
-    __device__ void epilogue(const Blk&, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
-        float* out = part + (size_t)blockIdx.x * C2 * C1;
-#pragma unroll
-        for (int i = 0; i < Cfg::TM; ++i)
-#pragma unroll
-            for (int j = 0; j < Cfg::TN; ++j) out[Cfg::row_of(ty, i) * C1 + Cfg::col_of(tx, j)] = acc[i][j];
-    }
-};
-
-// d a1[P][k] = sum_c dy2[P][c] W2[c][k] -> dz1 (stored) + BN1 backward sums
-struct ProbDA1 {
-    static constexpr bool A_KFAST = true, B_NFAST = true;
-    static constexpr int SCRATCH = 3 * 128;
-    using Cfg = CfgTall;
-    Dy2 dy; const float* W2; const float* A1; const float* x; const float* trans; const float* W1; BnState st1;
-    float* DZ1; float* part; size_t M; int N;
-    struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const { b.m0 = (int)blockIdx.x * Cfg::BM; b.n0 = 0; b.k0 = 0; b.k1 = C2; }
-    __device__ void prologue(const Blk& b, float* s) const {
-        // transformed coordinates of the tile's points: s[i*128 + r]
-        for (int r = (int)threadIdx.x; r < Cfg::BM; r += Cfg::NT) {
-            size_t P = (size_t)b.m0 + r;
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-            if (P < M) {
-                const int bb = (int)(P / N), n = (int)(P % N);
-                const float* xb = x + (size_t)bb * 3 * N;
-                float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
-                t0 = p0; t1 = p1; t2 = p2;
-                if (trans) {
-                    const float* T = trans + (size_t)bb * 9;
-                    t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
-                    t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
-                    t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
-                }
-            }
-            s[r] = t0; s[128 + r] = t1; s[256 + r] = t2;
-        }
-        __syncthreads();
-    }
-    __device__ float loadA(const Blk&, const float*, int m, int k) const { return (size_t)m < M ? dy.at((size_t)m, k) : 0.f; }
-    __device__ float loadB(const Blk&, const float*, int k, int n) const { return W2[k * C1 + n]; }
-    __device__ void epilogue(const Blk& b, const float* s, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void* red) const {
-        float v1[Cfg::TN], v2[Cfg::TN];
-#pragma unroll
-        for (int j = 0; j < Cfg::TN; ++j) { v1[j] = 0.f; v2[j] = 0.f; }
-#pragma unroll
-        for (int i = 0; i < Cfg::TM; ++i) {
-            const int r = Cfg::row_of(ty, i);
-            const size_t P = (size_t)b.m0 + r;
-            if (P >= M) continue;
-            const float t0 = s[r], t1 = s[128 + r], t2 = s[256 + r];
-#pragma unroll
-            for (int j = 0; j < Cfg::TN; ++j) {
-                const int k = Cfg::col_of(tx, j);
-                const float dz = A1[P * C1 + k] > 0.f ? acc[i][j] : 0.f;
-                DZ1[P * C1 + k] = dz;
-                const float u = W1[k * 3 + 0] * t0 + W1[k * 3 + 1] * t1 + W1[k * 3 + 2] * t2;
-                const float yhat = (u - st1.mean[k]) * st1.rstd[k];
-                v1[j] += dz;
-                v2[j] = fmaf(dz, yhat, v2[j]);
-            }
-        }
-        float s1 = block_col_sum<Cfg>(v1, ty, tx, (float*)red);
-        float s2 = block_col_sum<Cfg>(v2, ty, tx, (float*)red);
-        if ((int)threadIdx.x < Cfg::BN) {
-            part[((size_t)blockIdx.x * 2 + 0) * C1 + threadIdx.x] = s1;
-            part[((size_t)blockIdx.x * 2 + 1) * C1 + threadIdx.x] = s2;
-        }
-    }
-};
-
-// layer 1 backward: dW1 partial per cloud and d trans per cloud.  block = 256 = 64 channels x 4 point slots.
-// Everything reduces to the per-cloud 64 x 3 matrix  G[k][j] = sum_n dy1[k][n] x_j[n]  (raw coordinates):
-//   dW1_b[k][i] = sum_n dy1 x'_i = sum_j T[j][i] G[k][j]        (x' = T^T x)
-//   dT_b[j][i]  = sum_n x_j dx'_i = sum_k W1[k][i] G[k][j]      (dx' = W1^T dy1)
-// and the pre-activation needed for yhat1 is u1 = sum_j (W1 T^T)[k][j] x_j.  No per-point cross-thread traffic.
-__global__ void k_l1_bwd(const float* __restrict__ x, const float* __restrict__ trans, int N,
-                         const float* __restrict__ W1, BnState st1, const float* __restrict__ DZ1,
-                         const float* __restrict__ m1, const float* __restrict__ m2,
-                         float* __restrict__ dW1part, float* __restrict__ dtrans) {
-    // thread = 4 consecutive channels (one float4 of a DZ1 row) x one of 16 point slots: 16-byte loads, and with
-    // the 4-fold unrolled point loop 64 B per thread in flight.  The 16 slots are summed in a fixed order.
-    __shared__ float shg[16][C1 * 3 + 1];
-    __shared__ float G[C1 * 3];
-    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, kq = tid & 15, q = tid >> 4;
-    const float* xb = x + (size_t)b * 3 * N;
-    float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    if (trans)
-        for (int e = 0; e < 9; ++e) T[e] = trans[(size_t)b * 9 + e];
-    float v0[4], v1[4], v2[4], mu[4], rr[4], sc[4], mm1[4], mm2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = 4 * kq + i;
-        const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
-        // (W1 T^T)[k][j] = sum_i W1[k][i] T[j][i]
-        v0[i] = w0 * T[0] + w1 * T[1] + w2 * T[2];
-        v1[i] = w0 * T[3] + w1 * T[4] + w2 * T[5];
-        v2[i] = w0 * T[6] + w1 * T[7] + w2 * T[8];
-        mu[i] = st1.mean[k]; rr[i] = st1.rstd[k]; sc[i] = st1.scale[k]; mm1[i] = m1[k]; mm2[i] = m2[k];
-    }
-    float g0[4] = {0.f, 0.f, 0.f, 0.f}, g1[4] = {0.f, 0.f, 0.f, 0.f}, g2[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4* dz = reinterpret_cast<const float4*>(DZ1 + (size_t)b * N * C1) + kq;
-#pragma unroll 4
-    for (int n = q; n < N; n += 16) {
-        const float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
-        const float4 d4 = dz[(size_t)n * (C1 / 4)];
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float u = v0[i] * p0 + v1[i] * p1 + v2[i] * p2;
-            const float yhat = (u - mu[i]) * rr[i];
-            const float dy = sc[i] * (d[i] - mm1[i] - yhat * mm2[i]);
-            g0[i] = fmaf(dy, p0, g0[i]); g1[i] = fmaf(dy, p1, g1[i]); g2[i] = fmaf(dy, p2, g2[i]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = 4 * kq + i;
-        shg[q][k * 3 + 0] = g0[i]; shg[q][k * 3 + 1] = g1[i]; shg[q][k * 3 + 2] = g2[i];
-    }
-    __syncthreads();
-    if (tid < 192) {
-        float t = 0.f;
-#pragma unroll
-        for (int s = 0; s < 16; ++s) t += shg[s][tid];
-        G[tid] = t;
-    }
-    __syncthreads();
-    if (tid < 192) {
-        const int kk = tid / 3, i = tid % 3;
-        // dW1_b[kk][i] = sum_j T[j][i] G[kk][j]
-        dW1part[(size_t)b * (C1 * 3) + tid] = T[i] * G[kk * 3 + 0] + T[3 + i] * G[kk * 3 + 1] + T[6 + i] * G[kk * 3 + 2];
-    }
-    if (dtrans && tid < 9) {
-        const int j = tid / 3, i = tid % 3;
-        float s = 0.f;
-        for (int kk = 0; kk < C1; ++kk) s = fmaf(W1[kk * 3 + i], G[kk * 3 + j], s);
-        dtrans[(size_t)b * 9 + tid] = s;
-    }
-}
-
 // ================================================================================================
 // host orchestration
 // ================================================================================================
@@ -1145,9 +975,8 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     launch(k_dw3, dim3(C3), dim3(4 * C2), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
            (const float*)w.dvec, (const float*)w.evec, (const float*)w.WG, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
 
-    // ---- layers 2 and 1, fused pass over (dz2, a1) (l2bwd.cuh); PGPD_KB=0 selects the older three-kernel form ----
-    static const bool use_kb = !(getenv("PGPD_KB") && atoi(getenv("PGPD_KB")) == 0);
-    if (use_kb) {
+    // ---- layers 2 and 1: one fused pass over (dz2, a1) (l2bwd.cuh / tc_kb.cuh) ----
+    {
         launch(k_kb_prep, dim3(C1), dim3(256), 0, s, t.conv[1].w, w.bn[1], (const float*)w.m1_2, (const float*)w.m2_2, w.Kmat, w.cvec);
         int nparts = 0, nrows = 0, rpc = 0;
 #ifndef PGPD_EMU
@@ -1194,60 +1023,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
             launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const double*)w.rtmp, S, C1 * 3, g.conv[0].dw);
         }
         launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
-        return;
     }
-    Dy2 dy{w.DZ2, w.Y2, w.bn[1], w.m1_2, w.m2_2};
-    {
-        int nrows = 0;
-#ifndef PGPD_EMU
-        if (a.use_tc && (tc_mask() & 16) && g_b4 > 0) {
-            launch(tc::k_dy2_scale, dim3(1), dim3(128), 0, s, (const float*)w.pmax, g_b4, (const float*)w.bn[1].scale,
-                   (const float*)w.m1_2, (const float*)w.m2_2, w.esc, w.einv);
-            tc::DW2TC::Params p{M, (int)((M + tc::AC_NT - 1) / tc::AC_NT), w.fpart, w.DZ2, w.Y2, w.bn[1].scale, w.bn[1].mean, w.bn[1].rstd,
-                                w.m1_2, w.m2_2, w.esc, w.einv, w.A1};
-            nrows = tc::launch_accum<tc::DW2TC>(p, tc::dev_info().sms, s);
-        } else
-#endif
-        {
-            ProbDW2 p{dy, w.A1, w.fpart, M};
-            launch_gemm<ProbDW2::Cfg>(p, dim3(w.nb_dw2), s);
-            nrows = w.nb_dw2;
-        }
-        const int S = colreduce<float>(w.fpart, nrows, C2 * C1, w.rtmp, s);
-        launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C1, g.conv[1].dw);
-        launch(k_fill, grid1d(C2, 128), dim3(128), 0, s, g.conv[1].db, (size_t)C2, 0.f);
-    }
-    {
-        int nrows = 0;
-#ifndef PGPD_EMU
-        if (a.use_tc && (tc_mask() & 32)) {
-            // A = W2^T padded to 128 rows: A[k][c] = W2[c][k]
-            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, t.conv[1].w, 1, C1, C1, C2, 0, (__half*)w.wimg_s, w.inv_s);
-            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
-            tc::L2BwdBTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.DZ2, w.Y2, w.bn[1].scale, w.bn[1].mean, w.bn[1].rstd,
-                                   w.m1_2, w.m2_2, w.inv_s, w.A1, t.bn[0].gamma, t.bn[0].beta, w.DZ1, w.fpart};
-            tc::launch_stream<tc::L2BwdBTC>(p, tc::dev_info().sms, s);
-            nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
-        } else
-#endif
-        {
-            ProbDA1 p{dy, t.conv[1].w, w.A1, a.x, a.trans, t.conv[0].w, w.bn[0], w.DZ1, w.fpart, M, a.N};
-            launch_gemm<ProbDA1::Cfg>(p, dim3(w.nb_l2), s);
-            nrows = w.nb_l2;
-        }
-        const int S = colreduce<float>(w.fpart, nrows, 2 * C1, w.rtmp, s);
-        launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, count,
-               g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
-    }
-
-    // ---- layer 1 backward ---------------------------------------------------------------------------
-    launch(k_l1_bwd, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, t.conv[0].w, w.bn[0], (const float*)w.DZ1,
-           (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr);
-    {
-        const int S = colreduce<float>(w.fpart, a.B, C1 * 3, w.rtmp, s);
-        launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const double*)w.rtmp, S, C1 * 3, g.conv[0].dw);
-    }
-    launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
 }
 
 }  // namespace pgpd
