@@ -120,6 +120,28 @@ inline int colreduce(const T* part, int nblk, int C, double* tmp, cudaStream_t s
     return S;
 }
 
+// one-kernel variant for at most 1024 partial rows: out[c] = (float) sum_rows part[row][c]; block = 32 columns x 32 row lanes
+// (each lane sums its rows in order, the 32 lane sums are added in lane order: deterministic)
+template <class T>
+__global__ void k_colreduce_direct(const T* __restrict__ part, int nblk, int C, float* __restrict__ out) {
+    __shared__ double sh[32][33];
+    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
+    const int c = (int)blockIdx.x * 32 + cx;
+    double acc = 0.0;
+    if (c < C) {
+#pragma unroll 4
+        for (int i = ry; i < nblk; i += 32) acc += (double)part[(size_t)i * C + c];
+    }
+    sh[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) t += sh[q][cx];
+        out[c] = (float)t;
+    }
+}
+
 // slices of centred-square sums -> variance -> BatchNorm finalisation (train)
 // The squares were centred on `centre` (nullptr: on mean_u itself): sum (u-c)^2 = sum (u-mu)^2 + count (mu-c)^2.
 __global__ void k_bn_finalize_from_css(const double* tmp, int S, int C, const float* mean_u, double count,
@@ -134,24 +156,6 @@ __global__ void k_bn_finalize_from_css(const double* tmp, int S, int C, const fl
     bn_finalize_train(c, mu, var, count, bias, bn, st);
 }
 
-// out[c] = sum_i tmp[i][c]
-__global__ void k_reduce_d(const double* tmp, int S, int C, double* out) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    double s = 0.0;
-    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
-    out[c] = s;
-}
-
-// out[c] = scale * sum_i tmp[i][c]
-__global__ void k_reduce_ds(const double* tmp, int S, int C, double scale, double* out) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    double s = 0.0;
-    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
-    out[c] = s * scale;
-}
-
 // out[c] = (float) sum_i tmp[i][c]
 __global__ void k_reduce_f(const double* tmp, int S, int C, float* out) {
     int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -161,17 +165,39 @@ __global__ void k_reduce_f(const double* tmp, int S, int C, float* out) {
     out[c] = (float)s;
 }
 
+// vsum[k] = scale * sum_s tmp[s][k]  (the slices of a two-stage column reduction), then
 // mean_out[r] = (sum_k W[r][k] * vsum[k]) * inv   in double.  One warp per row (coalesced row reads, fixed shuffle tree);
-// block = 256 threads = 8 rows, grid = ceil(rows / 8).
-__global__ void k_matvec_mean(const float* __restrict__ W, int rows, int cols, const double* __restrict__ vsum, double inv,
-                              float* __restrict__ mean_out) {
-    const int r = (int)blockIdx.x * 8 + ((int)threadIdx.x >> 5), lane = (int)threadIdx.x & 31;
+// block = 256 threads = 8 rows, grid = ceil(rows / 8); cols <= 128.  Block 0 also stores vsum (kept for the backward).
+__global__ void k_matvec_mean(const float* __restrict__ W, int rows, int cols, const double* __restrict__ tmp, int S, double scale,
+                              double inv, float* __restrict__ mean_out, double* __restrict__ vsum_out) {
+    __shared__ double vs[128];
+    const int tid = (int)threadIdx.x;
+    if (tid < cols) {
+        double t = 0.0;
+        for (int i = 0; i < S; ++i) t += tmp[(size_t)i * cols + tid];
+        t *= scale;
+        vs[tid] = t;
+        if (blockIdx.x == 0 && vsum_out) vsum_out[tid] = t;
+    }
+    __syncthreads();
+    const int r = (int)blockIdx.x * 8 + (tid >> 5), lane = tid & 31;
     double s = 0.0;
     if (r < rows)
-        for (int k = lane; k < cols; k += 32) s += (double)W[(size_t)r * cols + k] * vsum[k];
+        for (int k = lane; k < cols; k += 32) s += (double)W[(size_t)r * cols + k] * vs[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (r < rows && lane == 0) mean_out[r] = (float)(s * inv);
+}
+
+// out[c] = (float) sum over the nblk partial rows; one kernel for up to 1024 rows, the two-stage reduction otherwise
+template <class T>
+inline void colreduce_to_float(const T* part, int nblk, int C, float* out, double* tmp, cudaStream_t s) {
+    if (nblk <= 1024) {
+        launch(k_colreduce_direct<T>, dim3((unsigned)((C + 31) / 32)), dim3(1024), 0, s, part, nblk, C, out);
+    } else {
+        const int S = colreduce<T>(part, nblk, C, tmp, s);
+        launch(k_reduce_f, dim3((unsigned)((C + 255) / 256)), dim3(256), 0, s, (const double*)tmp, S, C, out);
+    }
 }
 
 __global__ void k_fill(float* p, size_t n, float v) {

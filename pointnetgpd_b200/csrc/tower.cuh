@@ -763,8 +763,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     // ---- layer 2 ---------------------------------------------------------------------------------
     if (a.train) {
         const int S = colreduce<double>(w.dpart, w.nb_a1, C1, w.rtmp, s);
-        launch(k_reduce_d, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, w.S1a);
-        launch(k_matvec_mean, dim3(C2 / 8), dim3(256), 0, s, t.conv[1].w, C2, C1, (const double*)w.S1a, 1.0 / count, w.bn[1].mean);
+        launch(k_matvec_mean, dim3(C2 / 8), dim3(256), 0, s, t.conv[1].w, C2, C1, (const double*)w.rtmp, S, 1.0, 1.0 / count, w.bn[1].mean, w.S1a);
     }
     int n_css2 = 0;
     bool l3_pilot = false;      // BatchNorm3 statistics centred on a pilot mean (tcgen05 layer-3 kernel), corrected below
@@ -811,8 +810,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         const int nb = (int)std::min<size_t>((size_t)w.nb_a2, (Ms + 15) / 16);
         launch(k_a2_sum, dim3(nb), dim3(256), 0, s, (const float*)w.Y2, Ms, pstride, w.bn[1], w.dpart);
         const int S2 = colreduce<double>(w.dpart, nb, C2, w.rtmp, s);
-        launch(k_reduce_d, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S2, C2, w.S1);
-        launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / (double)Ms, w.bn[2].mean);
+        launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.rtmp, S2, 1.0, 1.0 / (double)Ms, w.bn[2].mean, w.S1);
     }
 
     // ---- layer 3 + max-pool ------------------------------------------------------------------------
@@ -869,8 +867,8 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         if (l3_pilot) {
             // exact sum of a2 from the kernel's per-CTA partials -> exact mean of u3; bn[2].mean still holds the pilot centre
             const int S1s = colreduce<float>(w.s1part, l3_grid, C2, w.rtmp, s);
-            launch(k_reduce_ds, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S1s, C2, 1.0 / 16.0 /* the kernel sums a2 * 2^4 (L3_ACT_SCALE) */, w.S1);
-            launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.S1, 1.0 / count, w.mu_x);
+            launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.rtmp, S1s,
+                   1.0 / 16.0 /* the kernel sums a2 * 2^4 (L3_ACT_SCALE) */, 1.0 / count, w.mu_x, w.S1);
             mean3 = w.mu_x; centre = w.bn[2].mean;
         }
         const int S = colreduce<float>(w.fpart, n_css, C3, w.rtmp, s);
@@ -897,8 +895,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.fpart, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
         p.kslice = C3 / 16;
         launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64, 16), s);
-        const int S = colreduce<float>(w.fpart, 16, C2 * C2, w.rtmp, s);
-        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.Q);
+        colreduce_to_float<float>(w.fpart, 16, C2 * C2, w.Q, w.rtmp, s);
     }
     launch(k_uvec, dim3(C2 / 32), dim3(1024), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
 
@@ -925,8 +922,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
             g_b4 = nrows;
             bnpart = w.ka_part;
             // Gram = hh + hl + hl^T from the per-CTA accumulators
-            const int S = colreduce<float>(w.fpart, grid, 2 * C2 * C2, w.rtmp, s);
-            launch(k_reduce_f, grid1d(2 * C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, 2 * C2 * C2, w.gram2);
+            colreduce_to_float<float>(w.fpart, grid, 2 * C2 * C2, w.gram2, w.rtmp, s);
             launch(tc::k_gram_sym, grid1d(C2 * C2, 256), dim3(256), 0, s, (const float*)w.gram2, w.gram);
             gram_done = true;
         } else if (a.use_tc && (tc_mask() & 8)) {
@@ -964,8 +960,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
             launch_gemm<ProbGram::Cfg>(p, dim3(w.nb_gram), s);
             nrows = w.nb_gram;
         }
-        const int S = colreduce<float>(w.fpart, nrows, C2 * C2, w.rtmp, s);
-        launch(k_reduce_f, grid1d(C2 * C2, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C2, w.gram);
+        colreduce_to_float<float>(w.fpart, nrows, C2 * C2, w.gram, w.rtmp, s);
     }
     // WG = W3 * Gram  [1024 x 128]
     {
@@ -1007,20 +1002,17 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
                    g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
         }
         {
-            const int S = colreduce<float>(w.kb_Cpart, nparts, C2 * C1, w.rtmp, s);
-            launch(k_reduce_f, grid1d(C2 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C2 * C1, w.kbC);
+            colreduce_to_float<float>(w.kb_Cpart, nparts, C2 * C1, w.kbC, w.rtmp, s);
         }
         {
-            const int S = colreduce<float>(w.kb_G1part, nparts, C1 * C1, w.rtmp, s);
-            launch(k_reduce_f, grid1d(C1 * C1, 256), dim3(256), 0, s, (const double*)w.rtmp, S, C1 * C1, w.kbG1);
+            colreduce_to_float<float>(w.kb_G1part, nparts, C1 * C1, w.kbG1, w.rtmp, s);
         }
         launch(k_kb_dw2, dim3(C2), dim3(C1), 0, s, (const float*)w.kbC, (const float*)w.kbG1, (const double*)w.S1a, t.conv[1].w, w.bn[1],
                (const float*)w.m1_2, (const float*)w.m2_2, g.conv[1].dw, g.conv[1].db);
         launch(k_kb_l1, dim3(a.B), dim3(192), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
                (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr);
         {
-            const int S = colreduce<float>(w.fpart, a.B, C1 * 3, w.rtmp, s);
-            launch(k_reduce_f, dim3(1), dim3(192), 0, s, (const double*)w.rtmp, S, C1 * 3, g.conv[0].dw);
+            colreduce_to_float<float>(w.fpart, a.B, C1 * 3, g.conv[0].dw, w.rtmp, s);
         }
         launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
     }
