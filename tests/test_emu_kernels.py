@@ -178,6 +178,17 @@ def test_abi_argument_checks():
     # bad module id
     rc = lib.pgpd_forward(7, C.byref(m), x.ctypes.data, 2, 8, 2, 0, out.ctypes.data, tr.ctypes.data, ws.addr, need, None)
     assert rc == A.E_ARG
+    # a conv weight that is only 4-byte aligned (the kernels read weights with 16-byte vector loads)
+    big = np.zeros(stc["feat.conv3.weight"].size + 4, np.float32)
+    off = 1 if big[1:].ctypes.data % 16 else 2
+    mis = big[off:off + stc["feat.conv3.weight"].size]
+    mis[:] = stc["feat.conv3.weight"].reshape(-1)
+    assert mis.ctypes.data % 16 != 0
+    table = dict(stc)
+    table["feat.conv3.weight"] = mis
+    m2 = A.build_model(lambda key: table[key].ctypes.data)
+    rc = lib.pgpd_forward(A.PGPD_CLS, C.byref(m2), x.ctypes.data, 2, 8, 2, 0, out.ctypes.data, tr.ctypes.data, ws.addr, need, None)
+    assert rc == A.E_ARG and b"aligned" in lib.pgpd_last_error()
     ws.check()
 
 
