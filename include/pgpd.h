@@ -20,8 +20,8 @@
  *   - x is [B,3,N] channel-major exactly as the reference model receives it
  *     (main_1v.py:69-73: data.float() of shape [B,3,N]);
  *   - weights use the reference parameter layout: Conv1d(k=1) weight [out,in,1] and
- *     Linear weight [out,in], both row-major [out][in]; conv / fc weight pointers and the
- *     conv3 weight-gradient pointers must be 16-byte aligned (PGPD_E_ARG otherwise).
+ *     Linear weight [out,in], both row-major [out][in]; conv / fc weight pointers must be
+ *     16-byte aligned (PGPD_E_ARG otherwise).
  */
 #ifndef PGPD_H_
 #define PGPD_H_

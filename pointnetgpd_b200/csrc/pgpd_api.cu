@@ -220,8 +220,6 @@ int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const
     int rc = check_common(what, m, x, B, N, k, workspace, workspace_bytes, w.bytes);
     if (rc) return rc;
     if (!g) return fail(PGPD_E_ARG, "null gradient struct");
-    if (((uintptr_t)g->stn_tower.conv[2].dw & 15) || (what >= PGPD_FEAT && ((uintptr_t)g->trunk.conv[2].dw & 15)))
-        return fail(PGPD_E_ARG, "conv3 weight-gradient pointers must be 16-byte aligned");
     if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
     if (what != PGPD_STN && !dout) return fail(PGPD_E_ARG, "dout is null");
     if (what == PGPD_STN && !dtrans) return fail(PGPD_E_ARG, "dtrans is null");
@@ -290,7 +288,6 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
                         const float* dpooled, float* dtrans_out,
                         void* workspace, size_t workspace_bytes, void* stream) {
     if (!t || !g || !x || !dpooled) return fail(PGPD_E_ARG, "null pointer");
-    if ((uintptr_t)g->conv[2].dw & 15) return fail(PGPD_E_ARG, "conv3 weight-gradient pointer must be 16-byte aligned");
     for (int i = 0; i < 3; ++i) if ((uintptr_t)t->conv[i].w & 15) return fail(PGPD_E_ARG, "conv weight pointers must be 16-byte aligned");
     if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
     if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");

@@ -564,50 +564,36 @@ __global__ void k_uvec(const float* __restrict__ W3, const float* __restrict__ e
 }
 
 // dW3[c][k] = sum_b coef[b][c] a2[argmax(b,c)][k]  -  d[c] * (W3 Gram)[c][k]  -  e[c] * S1[k]
-// grid = 1024 channels, block = 512 = 16 cloud lanes (warps) x 32 lanes of 4 consecutive k (one 16-byte load per lane and
-// arg-max row, four rows in flight per warp); the 16 cloud lanes are summed in a fixed order
+// grid = 1024 channels, block = 128 (k) x 4 cloud lanes; the lanes are summed in a fixed order
 __global__ void k_dw3(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ Y2, BnState st2,
                       int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec,
                       const float* __restrict__ WG, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
-    __shared__ float4 sh[16][32];
+    __shared__ float sh[4][128];
     __shared__ float s_cf[512];
     __shared__ int s_ix[512];
-    const int c = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, q = tid >> 5;
-    const float4 sc = *reinterpret_cast<const float4*>(st2.scale + 4 * lane);
-    const float4 sf = *reinterpret_cast<const float4*>(st2.shift + 4 * lane);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
+    const float sc = st2.scale[k], sf = st2.shift[k];
+    float acc = 0.f;
     for (int b0 = 0; b0 < B; b0 += 512) {
         const int nb = (B - b0 < 512) ? B - b0 : 512;
         // stage this channel's coefficients / arg-max indices first, so the row loads below are independent
         if (tid < nb) { s_cf[tid] = coef[(size_t)(b0 + tid) * C3 + c]; s_ix[tid] = idx[(size_t)(b0 + tid) * C3 + c]; }
         __syncthreads();
 #pragma unroll 4
-        for (int bb = q; bb < nb; bb += 16) {
+        for (int bb = q; bb < nb; bb += 4) {
             const float cf = s_cf[bb];
             const size_t P = (size_t)(b0 + bb) * N + s_ix[bb];
-            const float4 y = *reinterpret_cast<const float4*>(Y2 + P * C2 + 4 * lane);
-            acc.x = fmaf(cf, fmaxf(fmaf(sc.x, y.x, sf.x), 0.f), acc.x);
-            acc.y = fmaf(cf, fmaxf(fmaf(sc.y, y.y, sf.y), 0.f), acc.y);
-            acc.z = fmaf(cf, fmaxf(fmaf(sc.z, y.z, sf.z), 0.f), acc.z);
-            acc.w = fmaf(cf, fmaxf(fmaf(sc.w, y.w, sf.w), 0.f), acc.w);
+            const float a2v = fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
+            acc = fmaf(cf, a2v, acc);
         }
         __syncthreads();
     }
-    sh[q][lane] = acc;
+    sh[q][k] = acc;
     __syncthreads();
     if (q == 0) {
-        float4 t = sh[0][lane];
-#pragma unroll
-        for (int w = 1; w < 16; ++w) { const float4 u = sh[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
-        const float d = dvec[c], e = evec[c];
-        const float4 wg = *reinterpret_cast<const float4*>(WG + (size_t)c * C2 + 4 * lane);
-        float4 o;
-        o.x = t.x - d * wg.x - e * (float)S1[4 * lane + 0];
-        o.y = t.y - d * wg.y - e * (float)S1[4 * lane + 1];
-        o.z = t.z - d * wg.z - e * (float)S1[4 * lane + 2];
-        o.w = t.w - d * wg.w - e * (float)S1[4 * lane + 3];
-        *reinterpret_cast<float4*>(dW3 + (size_t)c * C2 + 4 * lane) = o;
-        if (lane == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
+        const float t = ((sh[0][k] + sh[1][k]) + sh[2][k]) + sh[3][k];
+        dW3[(size_t)c * C2 + k] = t - dvec[c] * WG[(size_t)c * C2 + k] - evec[c] * (float)S1[k];
+        if (k == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
     }
 }
 
