@@ -39,13 +39,41 @@ struct BnState {
 };
 
 // ---- ordered 32-bit encoding of floats (unsigned compare == float compare) ---------------------
+// NaN (either sign) maps to the largest key, so a NaN activation wins the max-pool like it does in torch's MaxPool1d.
 __device__ __forceinline__ unsigned ord_encode(float f) {
+    if (f != f) return 0xFFFFFFFFu;
     unsigned u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float ord_decode(unsigned k) {
     unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
     return __uint_as_float(u);
+}
+
+// relu that keeps NaN (fmaxf(NaN, 0) is 0; torch.relu(NaN) is NaN)
+__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }
+
+// fp16 operand range of the tensor-core path: activations are pre-scaled by 2^4 before the hi/lo split, so anything
+// above 60000/16 would saturate.  Producers of activations flag such values (and NaN) per cloud instead of clamping
+// silently; the pooled feature of a flagged cloud is written as NaN (see k_tail_l3).
+constexpr float TC_ACT_LIMIT = 60000.0f / 16.0f;
+
+// ---- last-block-done: the block that arrives last at `counter` (zero before the launch) returns true and resets it ----
+// Used by the fused tail kernels: per-block partial results are written first, the last block reduces them in a fixed
+// order (deterministic) and finalises.  All threads of the block must call it.
+__device__ __forceinline__ bool last_block_done(unsigned* counter, unsigned nblocks) {
+    __shared__ int s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(counter, 1u);
+        s_is_last = (t == nblocks - 1u) ? 1 : 0;
+        if (s_is_last) *counter = 0u;
+    }
+    __syncthreads();
+    const bool last = s_is_last != 0;
+    if (last) __threadfence();
+    return last;
 }
 
 // ---- BatchNorm finalisation ---------------------------------------------------------------------

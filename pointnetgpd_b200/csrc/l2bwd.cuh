@@ -21,8 +21,9 @@
 //   V_b = W1 T_b^T,   dW1_b = G_b T_b,   dT_b[j][i] = sum_k W1[k][i] G_b[k][j]
 // so dz1 is never written either.  Per point the pass reads 768 B (dz2 + a1) + 12 B (x) and writes nothing.
 //
-// This file: the 64x64 / 64-vector precompute, a plain fp32 CUDA-core version of the pass (PGPD_F_SIMT path and
-// the reference every run of the tcgen05 version in tc_kb.cuh is tested against), and the finalisation kernels.
+// This file: a plain fp32 CUDA-core version of the pass (PGPD_F_SIMT path and the reference every run of the tcgen05
+// version in tc_kb.cuh is tested against) and the per-cloud layer-1 finalisation; the 64x64 / 64-vector precompute and
+// the dW2 finalisation are parts of the fused tail kernels (tails.cuh: k_tail_ka, k_tail_kb).
 #pragma once
 #include "common.cuh"
 
@@ -30,34 +31,6 @@ namespace pgpd {
 
 constexpr int KB_REF_NT = 32;          // points per tile of the CUDA-core pass
 constexpr int KB_REF_MAX_BLOCKS = 592;
-
-// K[k][k'] = sum_c W2[c][k] s_c r_c m2_c W2[c][k'],  cvec[k] = sum_c W2[c][k] s_c (r_c m2_c mu_c - m1_c).
-// grid 64 (k) x block 256 = 64 (k') x 4 lanes over c; the lanes are summed in a fixed order.
-__global__ void k_kb_prep(const float* __restrict__ W2, BnState st2, const float* __restrict__ m1, const float* __restrict__ m2,
-                          float* __restrict__ Kmat, float* __restrict__ cvec) {
-    __shared__ double sd[C2], se[C2], swk[C2];
-    __shared__ double part[4][C1 + 1];
-    const int k = (int)blockIdx.x, tid = (int)threadIdx.x, kp = tid & 63, ln = tid >> 6;
-    if (tid < C2) {
-        const double s = (double)st2.scale[tid], rm2 = (double)st2.rstd[tid] * (double)m2[tid];
-        const double w = (double)W2[tid * C1 + k];
-        swk[tid] = w;
-        sd[tid] = w * s * rm2;
-        se[tid] = w * s * (rm2 * (double)st2.mean[tid] - (double)m1[tid]);
-    }
-    __syncthreads();
-    double acc = 0.0;
-#pragma unroll 8
-    for (int c = ln * 32; c < ln * 32 + 32; ++c) acc += sd[c] * (double)W2[c * C1 + kp];
-    part[ln][kp] = acc;
-    __syncthreads();
-    if (ln == 0) Kmat[k * C1 + kp] = (float)(((part[0][kp] + part[1][kp]) + part[2][kp]) + part[3][kp]);
-    if (tid == 0) {
-        double cv = 0.0;
-        for (int c = 0; c < C2; ++c) cv += se[c];
-        cvec[k] = (float)cv;
-    }
-}
 
 struct KbRefParams {
     const float* DZ2; const float* A1; const float* x; const float* W2; const float* scale2;
@@ -160,25 +133,13 @@ __global__ void __launch_bounds__(256) k_kb_ref(KbRefParams p) {
     }
 }
 
-// dW2[c][k] = s_c ( C[c][k] - m1_c S1a_k - r_c m2_c ( (W2 Gram1)[c][k] - mu_c S1a_k ) ).  grid 128 x block 64
-__global__ void k_kb_dw2(const float* __restrict__ Cm, const float* __restrict__ G1, const double* __restrict__ S1a,
-                         const float* __restrict__ W2, BnState st2, const float* __restrict__ m1, const float* __restrict__ m2,
-                         float* __restrict__ dW2, float* __restrict__ db2) {
-    const int c = (int)blockIdx.x, k = (int)threadIdx.x;
-    double wg = 0.0;
-#pragma unroll 8
-    for (int kk = 0; kk < C1; ++kk) wg += (double)W2[c * C1 + kk] * (double)G1[kk * C1 + k];
-    const double s = (double)st2.scale[c], rm2 = (double)st2.rstd[c] * (double)m2[c];
-    const double v = (double)Cm[c * C1 + k] - (double)m1[c] * S1a[k] - rm2 * (wg - (double)st2.mean[c] * S1a[k]);
-    dW2[c * C1 + k] = (float)(s * v);
-    if (k == 0 && db2) db2[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
-}
-
 // per cloud: H_b (sum of its `rpc` partial rows, fixed order) -> G_b -> dW1 partial of the cloud and d trans.
 // grid = B, block = 192 (k, j).  xmom[b] = { X1 (3), X2 (3x3 row-major) } raw-coordinate moments (double).
+// The last block sums the per-cloud partials of dW1 in cloud order (deterministic) and zeroes the conv1 bias gradient.
 __global__ void k_kb_l1(const float* __restrict__ Hpart, int rpc, const double* __restrict__ xmom, const float* __restrict__ trans,
                         const float* __restrict__ W1, BnState st1, const float* __restrict__ m1, const float* __restrict__ m2,
-                        float* __restrict__ dW1part, float* __restrict__ dtrans) {
+                        float* __restrict__ dW1part, float* __restrict__ dtrans, unsigned* counter, float* __restrict__ dW1,
+                        float* __restrict__ db1) {
     __shared__ float G[C1 * 3];
     const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
     float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -212,6 +173,14 @@ __global__ void k_kb_l1(const float* __restrict__ Hpart, int rpc, const double* 
         for (int kk = 0; kk < C1; ++kk) s = fmaf(W1[kk * 3 + i], G[kk * 3 + j], s);
         dtrans[(size_t)b * 9 + tid] = s;
     }
+    if (!last_block_done(counter, gridDim.x)) return;
+    if (tid < C1 * 3) {
+        double s = 0.0;
+#pragma unroll 4
+        for (unsigned bb = 0; bb < gridDim.x; ++bb) s += (double)dW1part[(size_t)bb * (C1 * 3) + tid];
+        dW1[tid] = (float)s;
+    }
+    if (tid < C1 && db1) db1[tid] = 0.f;          // bias feeding a train-mode BatchNorm: gradient is identically zero
 }
 
 }  // namespace pgpd

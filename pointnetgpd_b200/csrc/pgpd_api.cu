@@ -143,6 +143,7 @@ int pgpd_profile_read(int* launches, float* total_ms) {
     return PGPD_OK;
 }
 
+#ifdef PGPD_DEBUG
 /* tuning aid (not part of the documented ABI): copies the [256][8] pipeline cycle counters written by the
  * layer-3 kernel when PGPD_L3_DEBUG is set */
 int pgpd_debug_l3_counters(long long* host_out) {
@@ -165,6 +166,7 @@ int pgpd_debug_stream_counters(int on) {
     return cudaMemcpyToSymbol(tc::g_stream_dbg, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : PGPD_E_CUDA;
 #endif
 }
+#endif  /* PGPD_DEBUG */
 
 size_t pgpd_workspace_bytes(int what, int B, int N, int k, int flags) {
     if (B < 1 || N < 1) return 0;

@@ -1,0 +1,748 @@
+// tails.cuh -- the small kernels around the big streaming / tensor-core kernels of a tower, FUSED.
+//
+// Round 1 ran every reduction, BatchNorm finalisation, mean propagation and weight pre-pack as its own launch
+// (~150 launches of 2-10 us per training step, a third of the step).  Here each chain between two big kernels is ONE
+// launch: blocks write partial results, the last block to finish (common.cuh: last_block_done) reduces them in a fixed
+// order and finalises, or the work is split by output channel so that no cross-block step exists at all.
+// Everything stays deterministic (fixed summation orders, no floating-point atomics).
+//
+// Reference semantics of what is finalised here: nn.BatchNorm1d in training mode (batch statistics, running-stat
+// update; pointnet.py:21-25,130-132), MaxPool1d over the points (pointnet.py:32,148) -- see tower.cuh.
+#pragma once
+#include "common.cuh"
+#ifndef PGPD_EMU
+#include "tc_ptx.cuh"
+#endif
+
+namespace pgpd {
+
+constexpr int PRE_THREADS = 256;
+constexpr int A1_CHUNK = 64;        // points per staging chunk of k_a1
+constexpr int A1_CPB = 4;           // chunks per block: one partial row of the a1 sums per 256 points
+
+// ================================================================================================
+// F1: k_tower_pre -- everything a tower forward needs before its first per-point kernel
+//   role MOMENTS (train): one block per cloud: first and second moments of the TRANSFORMED points x' = T^T x in double
+//                 (mom[b] = {sum x'_i (3), sum x'_i x'_i2 (3x3)}), raw-coordinate moments kept for the backward; the last
+//                 of these blocks sums the clouds in a fixed order and finalises BatchNorm1 analytically:
+//                 u1 = W1 x'  =>  mean = W1 m,  var_c = w_c^T Cov w_c.
+//   role AFFINE  (eval): one block: folded scale/shift of the three BatchNorms from the running statistics.
+//   role W2IMG / W3IMG (tensor-core path): hi/lo fp16 operand images of conv2.weight / conv3.weight (swizzled, rows
+//                 scaled by powers of two; layout as consumed by tc_kf.cuh / tc_l3.cuh), sign(gamma3) folded into W3.
+//   role SIGN    (CUDA-core path): sgn[c] = sign(gamma3[c]).
+// ================================================================================================
+struct PreParams {
+    const float* x; const float* trans; int B, N;
+    double* moments; double* rawmom;          // [B][12]; rawmom may be null
+    pgpd_lin conv[3]; pgpd_bn bn[3]; BnState st[3];
+    int train; double count;
+    unsigned* counter;                        // ticket of the MOMENTS role
+    unsigned* bad;                            // [B+1] flags; [B] = "a weight is not finite"
+    int n_mom, n_w2, n_w3;                    // blocks per role (n_w2 = n_w3 = 0 on the CUDA-core path: SIGN role instead)
+    void* wimg2; float* inv2;                 // W2 image (32 KB) + per-row inverse scale [128]
+    void* wimg3; float* sgn;                  // W3 image (512 KB) + inv / sign [1024]
+    int act_shift;
+};
+
+#ifndef PGPD_EMU
+namespace tc {
+// one row of a K-major hi/lo operand image: row r of [kb][part][128 rows][64 halves], 128-byte swizzle.
+// w: this thread's element k of the row (already sign-adjusted), mx: the row's max |w|.  Returns the exponent e used.
+__device__ __forceinline__ int prepack_elem(float w, float mx, int r, int k, __half* img, size_t img_base_halves) {
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);               // mx in [2^(ex-1), 2^ex)
+    const int e = (mx > 0.f && mx < INFINITY) ? 14 - ex : 0;     // mx * 2^e in [2^13, 2^14)
+    const float ws = ldexpf(w, e);
+    const __half hi = __float2half_rn(ws);
+    const __half lo = __float2half_rn(ws - __half2float(hi));
+    const int kb = k >> 6, j = k & 63, chunk = j >> 3, within = j & 7;
+    const size_t base = img_base_halves + (size_t)(kb * 2) * 8192;
+    const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
+    img[base + off] = hi;
+    img[base + 8192 + off] = lo;
+    return e;
+}
+}  // namespace tc
+#endif
+
+__global__ void __launch_bounds__(PRE_THREADS) k_tower_pre(PreParams p) {
+    __shared__ double sh[PRE_THREADS];
+    __shared__ double raw[12];
+    __shared__ float redf[PRE_THREADS];
+    const int tid = (int)threadIdx.x;
+    int blk = (int)blockIdx.x;
+    if (blk < p.n_mom) {
+        if (!p.train) {
+            // ---- AFFINE (eval): y = gamma*(u + b - rm)/sqrt(rv+eps) + beta for the three layers
+            for (int L = 0; L < 3; ++L) {
+                const int C = L == 0 ? C1 : (L == 1 ? C2 : C3);
+                for (int c = tid; c < C; c += PRE_THREADS) {
+                    const pgpd_bn& bn = p.bn[L];
+                    const float rstd = 1.0f / sqrtf(bn.running_var[c] + BN_EPS);
+                    const float sc = bn.gamma[c] * rstd;
+                    const float b = p.conv[L].b ? p.conv[L].b[c] : 0.f;
+                    p.st[L].mean[c] = bn.running_mean[c] - b;
+                    p.st[L].rstd[c] = rstd;
+                    p.st[L].scale[c] = sc;
+                    p.st[L].shift[c] = bn.beta[c] + sc * (b - bn.running_mean[c]);
+                }
+            }
+            return;
+        }
+        // ---- MOMENTS (train): cloud b = blk
+        const int b = blk;
+        const float* xb = p.x + (size_t)b * 3 * p.N;
+        double acc[9];
+        for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+        for (int n = tid; n < p.N; n += PRE_THREADS) {
+            const double p0 = xb[n], p1 = xb[p.N + n], p2 = xb[2 * p.N + n];
+            acc[0] += p0; acc[1] += p1; acc[2] += p2;
+            acc[3] += p0 * p0; acc[4] += p0 * p1; acc[5] += p0 * p2;
+            acc[6] += p1 * p1; acc[7] += p1 * p2; acc[8] += p2 * p2;
+        }
+        for (int q = 0; q < 9; ++q) {
+            sh[tid] = acc[q];
+            __syncthreads();
+            for (int s = PRE_THREADS / 2; s > 0; s >>= 1) {
+                if (tid < s) sh[tid] += sh[tid + s];
+                __syncthreads();
+            }
+            if (tid == 0) raw[q] = sh[0];
+            __syncthreads();
+        }
+        if (tid < 12) {
+            double T[3][3];
+            for (int j = 0; j < 3; ++j)
+                for (int i = 0; i < 3; ++i) T[j][i] = p.trans ? (double)p.trans[(size_t)b * 9 + j * 3 + i] : (i == j ? 1.0 : 0.0);
+            const double s1[3] = {raw[0], raw[1], raw[2]};
+            const double X[3][3] = {{raw[3], raw[4], raw[5]}, {raw[4], raw[6], raw[7]}, {raw[5], raw[7], raw[8]}};
+            double v = 0.0;
+            if (tid < 3) {
+                for (int j = 0; j < 3; ++j) v += T[j][tid] * s1[j];
+            } else {
+                const int i = (tid - 3) / 3, i2 = (tid - 3) % 3;
+                for (int j = 0; j < 3; ++j)
+                    for (int j2 = 0; j2 < 3; ++j2) v += T[j][i] * X[j][j2] * T[j2][i2];
+            }
+            p.moments[(size_t)b * 12 + tid] = v;
+            if (p.rawmom) p.rawmom[(size_t)b * 12 + tid] = tid < 3 ? s1[tid] : X[(tid - 3) / 3][(tid - 3) % 3];
+        }
+        if (!last_block_done(p.counter, (unsigned)p.n_mom)) return;
+        // ---- last cloud block: sum the clouds (12 entries x 21 lanes, lanes added in order) and finalise BatchNorm1
+        {
+            const int e = tid % 12, ln = tid / 12;          // 252 active threads
+            double s = 0.0;
+            if (ln < 21)
+                for (int bb = ln; bb < p.B; bb += 21) s += p.moments[(size_t)bb * 12 + e];
+            sh[tid] = s;
+            __syncthreads();
+            if (tid < 12) {
+                double t = 0.0;
+                for (int l2 = 0; l2 < 21; ++l2) t += sh[l2 * 12 + tid];
+                raw[tid] = t / p.count;
+            }
+            __syncthreads();
+            if (tid < C1) {
+                const int c = tid;
+                const double w[3] = {p.conv[0].w[c * 3 + 0], p.conv[0].w[c * 3 + 1], p.conv[0].w[c * 3 + 2]};
+                const double mean_u = w[0] * raw[0] + w[1] * raw[1] + w[2] * raw[2];
+                double var = 0;
+                for (int i = 0; i < 3; ++i)
+                    for (int i2 = 0; i2 < 3; ++i2) var += w[i] * (raw[3 + i * 3 + i2] - raw[i] * raw[i2]) * w[i2];
+                bn_finalize_train(c, mean_u, var, p.count, p.conv[0].b, p.bn[0], p.st[0]);
+            }
+        }
+        return;
+    }
+    blk -= p.n_mom;
+#ifndef PGPD_EMU
+    if (blk < p.n_w2) {
+        // ---- W2IMG: 4 rows of conv2.weight [128][64] per block (KD = 64: one k-block)
+        const int r = blk * 4 + (tid >> 6), k = tid & 63;
+        const float w = p.conv[1].w[(size_t)r * C1 + k];
+        redf[tid] = fabsf(w);
+        __syncthreads();
+        for (int s = 32; s > 0; s >>= 1) {
+            if (k < s) redf[tid] = fmaxf(redf[tid], redf[tid + s]);
+            __syncthreads();
+        }
+        const float mx = redf[tid & ~63];
+        const int e = tc::prepack_elem(w, mx, r, k, (__half*)p.wimg2, 0);
+        if (k == 0) p.inv2[r] = ldexpf(1.f, -(e + p.act_shift));
+        return;
+    }
+    blk -= p.n_w2;
+    if (blk < p.n_w3) {
+        // ---- W3IMG: 2 rows of conv3.weight [1024][128] per block; image block (mt = c/128): [mt][kb][part][128 rows][64 halves]
+        const int c = blk * 2 + (tid >> 7), k = tid & 127;
+        const float w = p.conv[2].w[(size_t)c * C2 + k];
+        redf[tid] = fabsf(w);
+        __syncthreads();
+        for (int s = 64; s > 0; s >>= 1) {
+            if (k < s) redf[tid] = fmaxf(redf[tid], redf[tid + s]);
+            __syncthreads();
+        }
+        const float mx = redf[tid & ~127];
+        const float sg = p.bn[2].gamma[c] >= 0.f ? 1.f : -1.f;
+        const int mt = c >> 7, r = c & 127;
+        const int e = tc::prepack_elem(w * sg, mx, r, k, (__half*)p.wimg3, (size_t)(mt * 4) * 8192);
+        if (k == 0) {
+            p.sgn[c] = sg * ldexpf(1.f, -(e + p.act_shift));
+            if (!(mx < INFINITY)) p.bad[p.B] = 1u;           // NaN / Inf weight: every pooled value of this tower is poisoned
+        }
+        return;
+    }
+#else
+    (void)redf;
+#endif
+    // ---- SIGN (CUDA-core path): the remaining blocks
+    {
+        const int c = blk * PRE_THREADS + tid;
+        if (c < C3) p.sgn[c] = p.bn[2].gamma[c] >= 0.f ? 1.f : -1.f;
+    }
+}
+
+// ================================================================================================
+// k_a1: a1 = relu(scale1 * (W1 T^T x) + shift1), stored [M][64]  (+ train: sum of a1 -> S1a, mean(u2) = W2 mean(a1))
+// grid = (ceil(N / 256), clouds), block = 256 threads = 64 channels x 4 point slots; A1_CPB chunks of 64 points per block.
+// Train mode: every block writes one partial row of the a1 sums; the LAST block sums the rows (fixed order, double) and
+// propagates the mean through conv2: mean(u2) = W2 mean(a1) -- the centre of layer 2's sum of squares.
+// `limit`: activations above it (or NaN) flag the cloud in bad[] (tensor-core path: the fp16 operand range).
+// ================================================================================================
+struct A1Params {
+    const float* x; const float* trans; int B, N;
+    const float* W1; BnState st; float* A1;
+    double* part;                 // [gridDim.y * gridDim.x][64] or null (eval)
+    unsigned* counter; const float* W2; double count; float* mean_u2; double* S1a;
+    unsigned* bad; float limit;
+};
+
+__global__ void __launch_bounds__(256) k_a1(A1Params p) {
+    __shared__ float xs[3][A1_CHUNK];
+    __shared__ double sh[256];
+    __shared__ double vs[C1];
+    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
+    const int b = (int)blockIdx.y;
+    const float w0 = p.W1[k * 3 + 0], w1 = p.W1[k * 3 + 1], w2 = p.W1[k * 3 + 2];
+    const float sc = p.st.scale[k], sh_ = p.st.shift[k];
+    float acc = 0.f;
+    bool flag = false;
+    for (int ch = 0; ch < A1_CPB; ++ch) {
+        const int n0 = ((int)blockIdx.x * A1_CPB + ch) * A1_CHUNK;
+        if (n0 >= p.N) break;
+        const int nv = (p.N - n0 < A1_CHUNK) ? p.N - n0 : A1_CHUNK;
+        __syncthreads();
+        if (tid < A1_CHUNK) {
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+            if (tid < nv) {
+                const float* xb = p.x + (size_t)b * 3 * p.N + n0 + tid;
+                const float p0 = xb[0], p1 = xb[p.N], p2 = xb[2 * p.N];
+                t0 = p0; t1 = p1; t2 = p2;
+                if (p.trans) {
+                    const float* T = p.trans + (size_t)b * 9;
+                    t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+                    t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+                    t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+                }
+            }
+            xs[0][tid] = t0; xs[1][tid] = t1; xs[2][tid] = t2;
+        }
+        __syncthreads();
+        float* out = p.A1 + ((size_t)b * p.N + n0) * C1 + k;
+#pragma unroll 4
+        for (int pp = q; pp < nv; pp += 4) {
+            const float u = w0 * xs[0][pp] + w1 * xs[1][pp] + w2 * xs[2][pp];
+            const float a = relu_nan(sc * u + sh_);
+            flag = flag || !(a <= p.limit);
+            out[(size_t)pp * C1] = a;
+            acc += a;
+        }
+    }
+    if (flag) p.bad[b] = 1u;
+    if (!p.part) return;
+    const unsigned nblk = gridDim.x * gridDim.y;
+    sh[tid] = (double)acc;
+    __syncthreads();
+    if (tid < 64) p.part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C1 + tid] = sh[tid] + sh[tid + 64] + sh[tid + 128] + sh[tid + 192];
+    if (!last_block_done(p.counter, nblk)) return;
+    // ---- last block: S1a = sum of the partial rows (64 columns x 4 lanes), mean(u2) = W2 S1a / count
+    {
+        double s = 0.0;
+#pragma unroll 4
+        for (unsigned r = (unsigned)q; r < nblk; r += 4) s += p.part[(size_t)r * C1 + k];
+        sh[tid] = s;
+        __syncthreads();
+        if (tid < 64) {
+            const double t = ((sh[tid] + sh[tid + 64]) + sh[tid + 128]) + sh[tid + 192];
+            vs[tid] = t;
+            if (p.S1a) p.S1a[tid] = t;
+        }
+        __syncthreads();
+        if (tid < C2) {
+            double s2 = 0.0;
+            for (int kk = 0; kk < C1; ++kk) s2 += (double)p.W2[(size_t)tid * C1 + kk] * vs[kk];
+            p.mean_u2[tid] = (float)(s2 / p.count);
+        }
+    }
+}
+
+// ================================================================================================
+// T3: k_tail_l2 (train) -- between the layer-2 GEMM and the layer-3 GEMM
+//   every block: BatchNorm2 batch statistics from the partial rows of centred squares -> scale/shift (block 0 also
+//                writes the state and updates the running statistics);
+//   then the sum of a2 = relu(bn2(u2)): either from the caller's partial rows (CUDA-core path: k_a2_sum over all points,
+//                the exact mean) or, tensor-core path, a PILOT estimate from `nsample` points spread over the batch
+//                (each block sums its share; the layer-3 kernel accumulates the exact sum while it stages the tiles);
+//   the last block: mean(u3) = W3 mean(a2) -> st3.mean (the centre of layer 3's sum of squares), S1, and (tensor-core path)
+//                the centre in accumulator units mu_s = mean / inv.
+// grid = TL2_BLOCKS, block = 256.
+// ================================================================================================
+constexpr int TL2_BLOCKS = 16;
+constexpr int TL2_SAMPLE = 4096;              // points of the pilot estimate of mean(a2)
+struct TailL2Params {
+    const float* css; int n_css;              // [n_css][128] partial sums of (u2 - mean)^2
+    int bn_done;                              // 1: BatchNorm2 is already finalised (second call of the CUDA-core path): only read st2
+    const float* mean_u2; double count; const float* bias2; pgpd_bn bn2; BnState st2;
+    const float* Y2; size_t nsample, pstride;  // pilot: points P = i * pstride, i < nsample   (a2part == null)
+    const double* a2part; int n_a2part;       // or: exact partial rows [n][128] (nsample = number of points they cover)
+    double* part;                             // [TL2_BLOCKS][128] scratch
+    unsigned* counter;
+    const float* W3; float* mean_u3; double* S1; const float* inv3; float* mu_s;   // mu_s may be null
+};
+
+__global__ void __launch_bounds__(256) k_tail_l2(TailL2Params p) {
+    __shared__ double sh[256];
+    __shared__ float s_sc[C2], s_sf[C2];
+    __shared__ double vs[C2];
+    const int tid = (int)threadIdx.x, c = tid & 127, q = tid >> 7;
+    // ---- BatchNorm2 statistics (every block, identically)
+    if (p.bn_done) {
+        if (tid < C2) { s_sc[tid] = p.st2.scale[tid]; s_sf[tid] = p.st2.shift[tid]; }
+        __syncthreads();
+    } else {
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = q; r < p.n_css; r += 2) s += (double)p.css[(size_t)r * C2 + c];
+        sh[tid] = s;
+        __syncthreads();
+        if (tid < C2) {
+            const double var0 = (sh[tid] + sh[tid + C2]) / p.count;
+            const double var = var0 < 0.0 ? 0.0 : var0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
+            const float sc = p.bn2.gamma[tid] * rstd;
+            const float mu = p.mean_u2[tid];
+            s_sc[tid] = sc;
+            s_sf[tid] = p.bn2.beta[tid] - sc * mu;
+            if (blockIdx.x == 0) bn_finalize_train(tid, (double)mu, var0, p.count, p.bias2, p.bn2, p.st2);
+        }
+        __syncthreads();
+    }
+    // ---- this block's share of the sum of a2
+    double acc = 0.0;
+    if (p.a2part) {
+        for (int r = (int)blockIdx.x * 2 + q; r < p.n_a2part; r += 2 * (int)gridDim.x) acc += p.a2part[(size_t)r * C2 + c];
+    } else {
+        const float sc = s_sc[c], sf = s_sf[c];
+        float f0 = 0.f, f1 = 0.f;
+        const size_t stride = (size_t)gridDim.x * 2;
+        const size_t rs = p.pstride * C2;
+        size_t i = (size_t)blockIdx.x * 2 + q;
+        for (; i + stride < p.nsample; i += 2 * stride) {
+            const float y0 = p.Y2[i * rs + c], y1 = p.Y2[(i + stride) * rs + c];
+            f0 += relu_nan(sc * y0 + sf); f1 += relu_nan(sc * y1 + sf);
+        }
+        if (i < p.nsample) f0 += relu_nan(sc * p.Y2[i * rs + c] + sf);
+        acc = (double)f0 + (double)f1;
+    }
+    sh[tid] = acc;
+    __syncthreads();
+    if (tid < C2) p.part[(size_t)blockIdx.x * C2 + tid] = sh[tid] + sh[tid + C2];
+    if (!last_block_done(p.counter, gridDim.x)) return;
+    // ---- last block: total, mean(u3) = W3 S / nsample  (one warp per row of W3: coalesced, fixed shuffle tree)
+    if (tid < C2) {
+        double t = 0.0;
+        for (unsigned r = 0; r < gridDim.x; ++r) t += p.part[(size_t)r * C2 + tid];
+        vs[tid] = t;
+        if (p.S1) p.S1[tid] = t;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const double inv_n = 1.0 / (double)p.nsample;
+    for (int r = warp; r < C3; r += 8) {
+        double s = 0.0;
+#pragma unroll
+        for (int kk = lane; kk < C2; kk += 32) s += (double)p.W3[(size_t)r * C2 + kk] * vs[kk];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const float m = (float)(s * inv_n);
+            p.mean_u3[r] = m;
+            if (p.mu_s) p.mu_s[r] = m / p.inv3[r];
+        }
+    }
+}
+
+// ================================================================================================
+// T4: k_tail_l3 -- after the layer-3 GEMM + max-pool kernel; split by output channel (TL3_CH channels per block), so
+// there is no cross-block step:
+//   train: exact sum of a2 from the GEMM kernel's partial rows (tensor-core path with a pilot centre) -> exact mean(u3);
+//          BatchNorm3 batch statistics from the partial rows of squares (centred on `centre`):
+//          var = sum (u-c)^2 / count - (mean - c)^2;  finalisation + running statistics;
+//   both:  decode the (max, arg-max) keys and apply BatchNorm3 (+ReLU) to the pooled [B][1024] values;
+//          a cloud flagged in bad[] (NaN / out-of-range activation) or a pooled value outside the fp16 operand range of
+//          the tensor-core heads gets NaN instead of a silently clamped number.
+// grid = 1024 / TL3_CH, block = 256 = TL3_CH channels x 16 lanes.
+// ================================================================================================
+constexpr int TL3_CH = 16;
+struct TailL3Params {
+    int B; int relu_last; int train;
+    const unsigned long long* keys; const float* sgn; BnState st3;
+    float* pooled; float* uext; int* idx;     // uext / idx may be null (no backward)
+    const unsigned* bad; float limit;
+    // train
+    const float* css; int n_css;              // [n_css][1024]
+    const float* s1part; int n_s1; double s1scale;   // [n_s1][128] partial sums of a2 * 2^4, or null
+    const float* W3; const float* bias3; pgpd_bn bn3; double count;
+    double* S1;                               // [128] exact sum of a2 (written by block 0 when s1part != null)
+};
+
+__global__ void __launch_bounds__(256) k_tail_l3(TailL3Params p) {
+    __shared__ double sh[16][TL3_CH + 1];
+    __shared__ double vs[C2];
+    __shared__ float s_sc[TL3_CH], s_sf[TL3_CH];
+    const int tid = (int)threadIdx.x, cx = tid & (TL3_CH - 1), ln = tid >> 4;
+    const int c0 = (int)blockIdx.x * TL3_CH, c = c0 + cx;
+    if (p.train) {
+        double mean_exact = 0.0;
+        const bool pilot = p.s1part != nullptr;
+        if (pilot) {
+            // exact sum of a2: the rows are few (one per CTA of the GEMM kernel); every block repeats the same sums
+            if (tid < C2) {
+                double t = 0.0;
+#pragma unroll 4
+                for (int r = 0; r < p.n_s1; ++r) t += (double)p.s1part[(size_t)r * C2 + tid];
+                t *= p.s1scale;
+                vs[tid] = t;
+                if (blockIdx.x == 0 && p.S1) p.S1[tid] = t;
+            }
+            __syncthreads();
+            // mean(u3)[c] = W3[c] . S / count : 16 lanes x 8 k each, lanes added in order
+            double s = 0.0;
+#pragma unroll
+            for (int kk = ln * 8; kk < ln * 8 + 8; ++kk) s += (double)p.W3[(size_t)c * C2 + kk] * vs[kk];
+            sh[ln][cx] = s;
+            __syncthreads();
+            if (ln == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int l2 = 0; l2 < 16; ++l2) t += sh[l2][cx];
+                mean_exact = t / p.count;
+            }
+            __syncthreads();
+        }
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = ln; r < p.n_css; r += 16) s += (double)p.css[(size_t)r * C3 + c];
+        sh[ln][cx] = s;
+        __syncthreads();
+        if (ln == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int l2 = 0; l2 < 16; ++l2) t += sh[l2][cx];
+            const double centre = (double)p.st3.mean[c];         // what the GEMM kernel centred its squares on
+            double var = t / p.count, mu = centre;
+            if (pilot) { mu = mean_exact; const double d = mu - centre; var -= d * d; }
+            bn_finalize_train(c, mu, var, p.count, p.bias3, p.bn3, p.st3);
+            s_sc[cx] = p.st3.scale[c]; s_sf[cx] = p.st3.shift[c];
+        }
+        __syncthreads();
+    } else {
+        if (tid < TL3_CH) { s_sc[tid] = p.st3.scale[c0 + tid]; s_sf[tid] = p.st3.shift[c0 + tid]; }
+        __syncthreads();
+    }
+    // ---- pooled values of my TL3_CH channels, all clouds
+    const float sc = s_sc[cx], sf = s_sf[cx], sg = p.sgn[c];
+    const bool bad_all = p.bad[p.B] != 0u;
+    const float qnan = __uint_as_float(0x7FC00000u);
+    for (int b = ln; b < p.B; b += 16) {
+        const size_t i = (size_t)b * C3 + c;
+        const unsigned long long key = p.keys[i];
+        const float u = sg * ord_decode((unsigned)(key >> 32));
+        const int n = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        float g = sc * u + sf;
+        if (p.relu_last) g = relu_nan(g);
+        if (bad_all || p.bad[b] != 0u || !(fabsf(g) <= p.limit)) g = qnan;
+        p.pooled[i] = g;
+        if (p.uext) { p.uext[i] = u; p.idx[i] = n; }
+    }
+}
+
+// ================================================================================================
+// backward tails
+// ================================================================================================
+
+// B2: k_q_uvec -- after k_pool_bwd:  Q = W3^T diag(d) W3 (128 x 128),  uvec = W3^T e,  and (tensor-core path) the hi/lo
+// operand image of Q for the pass-A kernel.  grid = 32 blocks x 4 rows of Q, block = 128 threads (column j).
+// Sums over the 1024 channels run in a fixed order (two interleaved chains).
+struct QuParams {
+    const float* W3; const float* dvec; const float* evec;
+    float* Q; float* uvec;
+    void* qimg; float* inv_s; int act_shift;      // qimg == null: no image (CUDA-core path)
+};
+
+__global__ void __launch_bounds__(128) k_q_uvec(QuParams p) {
+    __shared__ float s_wd[64][4];
+    __shared__ double s_red[4][128];
+    __shared__ float s_mx[4][128];
+    const int j = (int)threadIdx.x, i0 = (int)blockIdx.x * 4;
+    float acc[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+    double ue[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int cb = 0; cb < C3; cb += 64) {
+        __syncthreads();
+        for (int t = j; t < 64 * 4; t += 128) {
+            const int cc = t >> 2, r = t & 3;
+            s_wd[cc][r] = p.W3[(size_t)(cb + cc) * C2 + i0 + r] * p.dvec[cb + cc];
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int cc = 0; cc < 64; ++cc) {
+            const float w = p.W3[(size_t)(cb + cc) * C2 + j];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r][cc & 1] = fmaf(s_wd[cc][r], w, acc[r][cc & 1]);
+        }
+    }
+    // uvec rows i0..i0+3: thread j covers channels c = j, j+128, ...
+    for (int c = j; c < C3; c += 128) {
+        const double e = (double)p.evec[c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ue[r] += (double)p.W3[(size_t)c * C2 + i0 + r] * e;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s_red[r][j] = ue[r];
+    float q[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        q[r] = acc[r][0] + acc[r][1];
+        p.Q[(size_t)(i0 + r) * C2 + j] = q[r];
+        s_mx[r][j] = fabsf(q[r]);
+    }
+    __syncthreads();
+    if (j < 4) {
+        double t = 0.0;
+        for (int l = 0; l < 128; ++l) t += s_red[j][l];
+        p.uvec[i0 + j] = (float)t;
+    }
+#ifndef PGPD_EMU
+    if (p.qimg) {
+        for (int st = 64; st > 0; st >>= 1) {
+            if (j < st) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s_mx[r][j] = fmaxf(s_mx[r][j], s_mx[r][j + st]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tc::prepack_elem(q[r], s_mx[r][0], i0 + r, j, (__half*)p.qimg, 0);
+            if (j == 0) p.inv_s[i0 + r] = ldexpf(1.f, -(e + p.act_shift));
+        }
+    }
+#endif
+}
+
+// T5: k_tail_ka -- after pass A of the backward (d a2 -> dz2):
+//   all blocks: column slices of the Gram partial rows -> g2 (tensor-core path: the hi.hi and hi.lo accumulators, 2 x 128 x 128;
+//               CUDA-core path: the plain Gram matrix, directly into `gram`);
+//   last block: Gram = (hh + hl + hl^T) / 256 (tensor-core path); BatchNorm2-backward sums -> dgamma2, dbeta2, m1, m2;
+//               the 64 x 64 / 64-vector precompute of the fused layer-2/1 pass (K, cvec; l2bwd.cuh); and (tensor-core path)
+//               the per-channel scale of dz2 and the two A-operand images of that pass (tc_kb.cuh).
+// grid = gcols / 256, block = 256.
+struct TailKaParams {
+    const float* gpart; int n_g; int gcols;       // [n_g][gcols] partial rows; gcols = 16384 (plain) or 32768 (hh, hl)
+    float* g2;                                    // [gcols] reduced (scratch when sym)
+    float* gram; int sym;                         // [128*128]
+    const float* bnpart; int n_bn; double count;  // [n_bn][2][128] partial (sum dz, sum dz*yhat)
+    float* dgamma; float* dbeta; float* m1; float* m2;
+    const float* W2; BnState st2; float* Kmat; float* cvec;
+    unsigned* counter;
+    // tensor-core path only
+    const float* pmax; int n_pm; float* esc; float* einv;
+    void* img1; void* img2; float* ginv; float act_scale;
+};
+
+__global__ void __launch_bounds__(256) k_tail_ka(TailKaParams p) {
+    __shared__ double sd[C2], se[C2];
+    __shared__ float s_m1[C2], s_m2[C2], s_einv[C2];
+    const int tid = (int)threadIdx.x;
+    {
+        const int col = (int)blockIdx.x * 256 + tid;
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < p.n_g; ++r) s += (double)p.gpart[(size_t)r * p.gcols + col];
+        (p.sym ? p.g2 : p.gram)[col] = (float)s;
+    }
+    if (!last_block_done(p.counter, gridDim.x)) return;
+    if (p.sym) {
+        const float sc = 1.0f / (p.act_scale * p.act_scale);
+        for (int i = tid; i < C2 * C2; i += 256) {
+            const int m = i >> 7, n = i & 127;
+            p.gram[i] = (p.g2[i] + p.g2[C2 * C2 + i] + p.g2[C2 * C2 + n * C2 + m]) * sc;
+        }
+    }
+    // ---- BatchNorm2 backward sums: thread = column of [2][128]
+    {
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < p.n_bn; ++r) s += (double)p.bnpart[(size_t)r * 2 * C2 + tid];
+        if (tid < C2) { p.dbeta[tid] = (float)s; s_m1[tid] = (float)(s / p.count); p.m1[tid] = s_m1[tid]; }
+        else { p.dgamma[tid - C2] = (float)s; s_m2[tid - C2] = (float)(s / p.count); p.m2[tid - C2] = s_m2[tid - C2]; }
+    }
+    __syncthreads();
+    // ---- K[k][k'] = sum_c W2[c][k] s_c r_c m2_c W2[c][k'],  cvec[k] = sum_c W2[c][k] s_c (r_c m2_c mu_c - m1_c)
+    if (tid < C2) {
+        const double sc = (double)p.st2.scale[tid], rm2 = (double)p.st2.rstd[tid] * (double)s_m2[tid];
+        sd[tid] = sc * rm2;
+        se[tid] = sc * (rm2 * (double)p.st2.mean[tid] - (double)s_m1[tid]);
+    }
+    __syncthreads();
+    for (int o = tid; o < C1 * C1; o += 256) {
+        const int k = o >> 6, kp = o & 63;
+        double a = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < C2; ++c) a += (double)p.W2[c * C1 + k] * sd[c] * (double)p.W2[c * C1 + kp];
+        p.Kmat[o] = (float)a;
+    }
+    if (tid < C1) {
+        double cv = 0.0;
+        for (int c = 0; c < C2; ++c) cv += (double)p.W2[c * C1 + tid] * se[c];
+        p.cvec[tid] = (float)cv;
+    }
+#ifndef PGPD_EMU
+    if (!p.img1) return;
+    // ---- esc[c] = 2^e with max|dz2[.,c]| 2^e in [2^12, 2^13)
+    {
+        const int c = tid & 127, half = tid >> 7;
+        float mx = 0.f;
+        for (int g = half; g < p.n_pm; g += 2) mx = fmaxf(mx, p.pmax[(size_t)g * 2 * C2 + c]);
+        __shared__ float s_pm[2][C2];
+        s_pm[half][c] = mx;
+        __syncthreads();
+        if (half == 0) {
+            mx = fmaxf(mx, s_pm[1][c]);
+            int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+            e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
+            const float ev = __uint_as_float((uint32_t)(127 - e) << 23);
+            p.esc[c] = __uint_as_float((uint32_t)(127 + e) << 23);
+            p.einv[c] = ev;
+            s_einv[c] = ev;
+        }
+        __syncthreads();
+    }
+    // ---- A-operand images of the pass: row k < 64: A1op[k][c] = W2[c][k] s_c einv_c 2^g_k, A2op[k][k'] = -K[k][k'] 2^g_k / 16;
+    // rows 64..127 zero.  One warp per row (lane: 4 columns c of A1op, 2 columns k' of A2op); Kmat was written by this block.
+    __syncthreads();
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        __half* img1 = (__half*)p.img1;
+        __half* img2 = (__half*)p.img2;
+        for (int r = warp; r < 128; r += 8) {
+            float w[4], kk[2];
+            float mx = 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = lane + 32 * u;
+                w[u] = (r < C1) ? p.W2[c * C1 + r] * p.st2.scale[c] * s_einv[c] : 0.f;
+                mx = fmaxf(mx, fabsf(w[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int kp = lane + 32 * u;
+                kk[u] = (r < C1) ? -p.Kmat[r * C1 + kp] * (1.0f / p.act_scale) : 0.f;
+                mx = fmaxf(mx, fabsf(kk[u]));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            int e = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e = tc::prepack_elem(w[u], mx, r, lane + 32 * u, img1, 0);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = lane + 32 * u;
+                const float ks = ldexpf(kk[u], e);
+                const __half hi = __float2half_rn(ks);
+                const __half lo = __float2half_rn(ks - __half2float(hi));
+                const int chunk = c >> 3, within = c & 7;
+                const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
+                img2[off] = hi;
+                img2[8192 + off] = lo;
+            }
+            if (lane == 0) p.ginv[r] = ldexpf(1.f, -e);
+        }
+    }
+#endif
+}
+
+// T7a: k_tail_kb -- after the fused layer-2/1 backward pass:
+//   blocks [0, 48): column slices of the partial rows of C = sum dz2 a1^T (128 x 64) and Gram1 = sum a1 a1^T (64 x 64);
+//   blocks [48, 56): BatchNorm1-backward partial rows (sum dz1, sum dz1 yhat1), 16 columns each;
+//   last block: dgamma1, dbeta1, m1, m2;  dW2 = diag(s)[C - m1 S1a^T - diag(r m2)(W2 Gram1 - mu2 S1a^T)];  db2 = 0.
+struct TailKbParams {
+    const float* Cpart; const float* G1part; int n_parts;     // [n_parts][8192], [n_parts][4096]
+    float* Cm; float* G1;
+    const float* bnpart; int n_bn; double count;              // [n_bn][2][64]
+    double* bnsum;                                            // [128] scratch
+    float* dgamma1; float* dbeta1; float* m1_1; float* m2_1;
+    const double* S1a; const float* W2; BnState st2; const float* m1_2; const float* m2_2;
+    float* dW2; float* db2;
+    unsigned* counter;
+};
+constexpr int TKB_BLOCKS = 56;
+
+__global__ void __launch_bounds__(256) k_tail_kb(TailKbParams p) {
+    __shared__ double sh[16][17];
+    const int tid = (int)threadIdx.x, blk = (int)blockIdx.x;
+    if (blk < 48) {
+        const int col = blk * 256 + tid;                      // 0 .. 12287
+        const bool isC = col < C2 * C1;
+        const float* src = isC ? p.Cpart + col : p.G1part + (col - C2 * C1);
+        const size_t ld = isC ? (size_t)C2 * C1 : (size_t)C1 * C1;
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < p.n_parts; ++r) s += (double)src[(size_t)r * ld];
+        if (isC) p.Cm[col] = (float)s; else p.G1[col - C2 * C1] = (float)s;
+    } else {
+        const int cx = tid & 15, ln = tid >> 4;
+        const int col = (blk - 48) * 16 + cx;                 // 0 .. 127 of [2][64]
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = ln; r < p.n_bn; r += 16) s += (double)p.bnpart[(size_t)r * 2 * C1 + col];
+        sh[ln][cx] = s;
+        __syncthreads();
+        if (ln == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int l2 = 0; l2 < 16; ++l2) t += sh[l2][cx];
+            p.bnsum[col] = t;
+        }
+    }
+    if (!last_block_done(p.counter, gridDim.x)) return;
+    if (tid < 2 * C1) {
+        const double s = p.bnsum[tid];
+        if (tid < C1) { p.dbeta1[tid] = (float)s; p.m1_1[tid] = (float)(s / p.count); }
+        else { p.dgamma1[tid - C1] = (float)s; p.m2_1[tid - C1] = (float)(s / p.count); }
+    }
+    for (int o = tid; o < C2 * C1; o += 256) {
+        const int c = o >> 6, k = o & 63;
+        double wg = 0.0;
+#pragma unroll 8
+        for (int kk = 0; kk < C1; ++kk) wg += (double)p.W2[c * C1 + kk] * (double)p.G1[kk * C1 + k];
+        const double sc = (double)p.st2.scale[c], rm2 = (double)p.st2.rstd[c] * (double)p.m2_2[c];
+        const double v = (double)p.Cm[o] - (double)p.m1_2[c] * p.S1a[k] - rm2 * (wg - (double)p.st2.mean[c] * p.S1a[k]);
+        p.dW2[o] = (float)(sc * v);
+    }
+    if (tid < C2 && p.db2) p.db2[tid] = 0.f;     // bias feeding a train-mode BatchNorm: gradient is identically zero
+}
+
+}  // namespace pgpd

@@ -90,6 +90,7 @@ struct L3Params {
     int B, N, tiles_per_cloud, ntiles;
     long long* dbg;           // optional [gridDim.x][8] cycle counters (see PGPD_L3_DEBUG), or nullptr
     float* s1_part;           // optional partial sums over the points of a2 * 2^4: v1 [gridDim.x][128], v3 [gridDim.x * 8][128]
+    unsigned* bad;            // [B] set to 1 for a cloud with a NaN / out-of-fp16-range activation (version 3)
 };
 
 // cycle accounting of the pipeline roles, for tuning (enabled by a non-null L3Params::dbg):
@@ -791,6 +792,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         const int row = q * 32 + lane;
         const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
+        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;      // centred squares of my channel of block mt4 = 0..3, summed over my tiles
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT;
@@ -851,10 +853,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
                 atomicMax(&p.keys[(size_t)b * C3 + ch], key);
-                if (stats) {
-                    const float iv = p.inv[ch];
-                    p.css_part[((size_t)t * L3C_EPI_ROWS + half) * C3 + ch] = css * iv * iv;     // four partial rows per tile
-                }
+                if (mt4 == 0) cs0 += css; else if (mt4 == 1) cs1 += css; else if (mt4 == 2) cs2 += css; else cs3 += css;
+            }
+        }
+        if (stats) {
+            // four partial rows per PAIR (one per 64-column quarter); each CTA of the pair fills its 512 channels of them
+#pragma unroll
+            for (int mt4 = 0; mt4 < 4; ++mt4) {
+                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
+                const float iv = p.inv[ch];
+                const float cs = mt4 == 0 ? cs0 : (mt4 == 1 ? cs1 : (mt4 == 2 ? cs2 : cs3));
+                p.css_part[((size_t)pair * L3C_EPI_ROWS + half) * C3 + ch] = cs * iv * iv;
             }
         }
     } else {
@@ -864,6 +873,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
         float sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f;
+        bool oor = false;
         int buf = 0; uint32_t bphase = 0;
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
@@ -894,10 +904,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 for (int u = 0; u < U; ++u) {
                     const int r = wp + 8 * (i0 + u);
                     const bool ok = r < nvalid;
-                    float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
-                    float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
-                    float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
-                    float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
+                    // relu that keeps NaN; values beyond the fp16 operand range (or NaN) flag the cloud (its pooled feature
+                    // becomes NaN in k_tail_l3) instead of being clamped silently
+                    float a0 = ok ? relu_nan(fmaf(sc0, y[u].x, sh0)) : 0.f;
+                    float a1 = ok ? relu_nan(fmaf(sc1, y[u].y, sh1)) : 0.f;
+                    float a2 = ok ? relu_nan(fmaf(sc2, y[u].z, sh2)) : 0.f;
+                    float a3 = ok ? relu_nan(fmaf(sc3, y[u].w, sh3)) : 0.f;
+                    oor = oor || !(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) <= 60000.f) || !((a0 + a1) + (a2 + a3) <= 3.0e5f);   // the sum catches NaN
+                    a0 = fminf(a0, 60000.f); a1 = fminf(a1, 60000.f); a2 = fminf(a2, 60000.f); a3 = fminf(a3, 60000.f);
                     sa0 += a0; sa1 += a1; sa2 += a2; sa3 += a3;
                     __half2 h01, l01, h23, l23;
                     split2(a0, a1, h01, l01);
@@ -910,6 +924,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                     *reinterpret_cast<uint2*>(a2b + (1 * 2 + kb) * L3C_A2_PART + off) = lv;
                 }
             }
+            if (oor) { p.bad[b] = 1u; oor = false; }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {                                // one arrival per warp on the LEADER's barrier
@@ -960,11 +975,20 @@ inline DevInfo& dev_info() {
 }
 inline bool available() { return dev_info().state == 1; }
 
-// tuning aid only (PGPD_L3_DEBUG=1): a lazily cudaMalloc'ed [256][8] int64 buffer of pipeline cycle counters
+// tuning aid, only in builds with -DPGPD_DEBUG (never in the product library: the ABI promises no allocation, no global
+// state): a lazily cudaMalloc'ed [256][8] int64 buffer of pipeline cycle counters, used when PGPD_L3_DEBUG is set
+#ifdef PGPD_DEBUG
 inline long long* l3_debug_buffer() {
     static long long* buf = nullptr;
     if (!buf) { cudaMalloc(&buf, 256 * 8 * sizeof(long long)); cudaMemset(buf, 0, 256 * 8 * sizeof(long long)); }
     return buf;
 }
+inline long long* l3_debug_buffer_if_enabled() {
+    static const bool on = getenv("PGPD_L3_DEBUG") != nullptr;
+    return on ? l3_debug_buffer() : nullptr;
+}
+#else
+inline long long* l3_debug_buffer_if_enabled() { return nullptr; }
+#endif
 
 }}  // namespace pgpd::tc

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "l2bwd.cuh"
+#include "tails.cuh"
 #ifndef PGPD_EMU
 #include "tc_l3.cuh"
 #include "tc_stream.cuh"
@@ -65,7 +66,10 @@ struct TowerScratch {
     double* dsum;     // [128]
     double* rtmp;     // [REDUCE_MAX_SLICES][16384] stage-1 output of the two-stage reductions
     float* fpart;     // float partials: max over users (see plan_tower_scratch)
-    unsigned long long* keys;  // [B][1024]
+    unsigned long long* keys;  // [B][1024]   -- keys, bad and counters are contiguous: ONE memset of zero_bytes per forward
+    unsigned* bad;             // [B+1] per-cloud "NaN / out-of-range activation" flags (+ [B]: a conv3 weight is not finite)
+    unsigned* counters;        // [16] tickets of the fused tail kernels (self-resetting)
+    size_t zero_bytes;
     void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
     float* mu_x;      // [1024] exact mean of u3 when the kernel centred its squares on a pilot estimate
@@ -108,7 +112,6 @@ struct TowerScratch {
 
 struct TowerWs : TowerKeep, TowerScratch {};
 
-constexpr int A1_CHUNK = 64;       // points per block of k_a1
 constexpr int GRAM_CHUNK = 1024;   // points per split-K block of the Gram GEMM
 constexpr int KB_MAX_PART = KB_REF_MAX_BLOCKS;   // per-block partial slots of the fused layer-2/1 backward pass
 
@@ -128,7 +131,7 @@ inline void plan_tower(Carver& c, TowerKeep& w, int B, int N) {
 inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool backward) {
     const size_t M = (size_t)B * N;
     w.tiles_per_cloud = idiv_up(N, 128);
-    w.nb_a1 = B * idiv_up(N, A1_CHUNK);                                       // one partial row per k_a1 block
+    w.nb_a1 = B * idiv_up(N, A1_CHUNK * A1_CPB);                              // one partial row per k_a1 block
     w.nb_a2 = (int)std::min<size_t>(8192, (M + 15) / 16);
     w.nb_l2 = (int)((M + 127) / 128);
     w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
@@ -150,7 +153,16 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     }
     w.fpart_elems = fp;
     w.fpart = c.take<float>(fp);
-    w.keys = c.take<unsigned long long>((size_t)B * C3);
+    {
+        // [B*1024 u64 keys][B+1 flags][16 tickets], zeroed together at the start of every forward
+        const size_t key_bytes = (size_t)B * C3 * sizeof(unsigned long long);
+        const size_t flag_elems = (size_t)B + 1 + 16;
+        unsigned char* z = c.take<unsigned char>(key_bytes + flag_elems * sizeof(unsigned));
+        w.keys = reinterpret_cast<unsigned long long*>(z);
+        w.bad = reinterpret_cast<unsigned*>(z + key_bytes);
+        w.counters = w.bad + (B + 1);
+        w.zero_bytes = key_bytes + flag_elems * sizeof(unsigned);
+    }
     w.wimg = c.take<unsigned char>((size_t)512 * 1024);
     w.mu_s = c.take<float>(C3);
     w.mu_x = c.take<float>(C3);
@@ -167,7 +179,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         w.evec = c.take<float>(C3);
         w.gram = c.take<float>(C2 * C2);
         w.gram2 = c.take<float>(2 * C2 * C2);
-        w.ka_part = c.take<float>((size_t)1024 * 2 * C2);
+        w.ka_part = c.take<float>((size_t)std::max(1024, w.nb_l2) * 2 * C2);
         w.WG = c.take<float>((size_t)C3 * C2);
         w.Q = c.take<float>(C2 * C2);
         w.uvec = c.take<float>(C2);
@@ -192,118 +204,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
 // forward kernels
 // ================================================================================================
 
-// per-cloud first and second moments of the TRANSFORMED points x' = T^T x, in double.
-// mom[b] = { sum x'_i (3) , sum x'_i x'_i2 (3x3 row-major) }
-__global__ void k_cloud_moments(const float* __restrict__ x, const float* __restrict__ trans, int N, double* __restrict__ mom,
-                                double* __restrict__ rawmom) {
-    __shared__ double sh[256];
-    __shared__ double raw[9];
-    const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
-    const float* xb = x + (size_t)b * 3 * N;
-    double acc[9];
-    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
-    for (int n = tid; n < N; n += 256) {
-        double p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
-        acc[0] += p0; acc[1] += p1; acc[2] += p2;
-        acc[3] += p0 * p0; acc[4] += p0 * p1; acc[5] += p0 * p2;
-        acc[6] += p1 * p1; acc[7] += p1 * p2; acc[8] += p2 * p2;
-    }
-    for (int q = 0; q < 9; ++q) {
-        sh[tid] = acc[q];
-        __syncthreads();
-        for (int s = 128; s > 0; s >>= 1) {
-            if (tid < s) sh[tid] += sh[tid + s];
-            __syncthreads();
-        }
-        if (tid == 0) raw[q] = sh[0];
-        __syncthreads();
-    }
-    if (tid < 12) {
-        double T[3][3];
-        for (int j = 0; j < 3; ++j)
-            for (int i = 0; i < 3; ++i) T[j][i] = trans ? (double)trans[(size_t)b * 9 + j * 3 + i] : (i == j ? 1.0 : 0.0);
-        const double s1[3] = {raw[0], raw[1], raw[2]};
-        const double X[3][3] = {{raw[3], raw[4], raw[5]}, {raw[4], raw[6], raw[7]}, {raw[5], raw[7], raw[8]}};
-        double v = 0.0;
-        if (tid < 3) {
-            for (int j = 0; j < 3; ++j) v += T[j][tid] * s1[j];
-        } else {
-            const int i = (tid - 3) / 3, i2 = (tid - 3) % 3;
-            for (int j = 0; j < 3; ++j)
-                for (int j2 = 0; j2 < 3; ++j2) v += T[j][i] * X[j][j2] * T[j2][i2];
-        }
-        mom[(size_t)b * 12 + tid] = v;
-        if (rawmom) {
-            // raw-coordinate moments, kept for the layer-1 backward: X1 (3), X2 (3x3 row-major)
-            rawmom[(size_t)b * 12 + tid] = tid < 3 ? s1[tid] : X[(tid - 3) / 3][(tid - 3) % 3];
-        }
-    }
-}
-
-// BatchNorm1 batch statistics, analytically from the (slice-reduced) cloud moments:
-//   u1 = W1 x'  =>  mean = W1 m,  var_c = w_c^T Cov w_c   with m, Cov the moments of x' over all points.
-__global__ void k_bn1_finalize(const double* __restrict__ tmp, int S, double count,
-                               pgpd_lin conv, pgpd_bn bn, BnState st) {
-    const int c = (int)threadIdx.x;
-    if (c >= C1) return;
-    double q[12];
-    for (int e = 0; e < 12; ++e) {
-        double s = 0.0;
-        for (int i = 0; i < S; ++i) s += tmp[(size_t)i * 12 + e];
-        q[e] = s / count;
-    }
-    double w[3] = {conv.w[c * 3 + 0], conv.w[c * 3 + 1], conv.w[c * 3 + 2]};
-    double mean_u = w[0] * q[0] + w[1] * q[1] + w[2] * q[2];
-    double var = 0;
-    for (int i = 0; i < 3; ++i)
-        for (int i2 = 0; i2 < 3; ++i2) var += w[i] * (q[3 + i * 3 + i2] - q[i] * q[i2]) * w[i2];
-    bn_finalize_train(c, mean_u, var, count, conv.b, bn, st);
-}
-
-// a1 = relu(scale1 * (W1 T^T x) + shift1), stored [M][64]; optional per-block sums of a1 (double).
-// grid = (chunks of 64 points, clouds), block = 256 threads = 64 channels x 4 point slots.  The chunk's transformed
-// coordinates are staged once in shared memory; no integer division, 256-byte coalesced stores.
-__global__ void k_a1(const float* __restrict__ x, const float* __restrict__ trans, int B, int N,
-                     const float* __restrict__ W1, BnState st, float* __restrict__ A1, double* __restrict__ part) {
-    __shared__ float xs[3][A1_CHUNK];
-    __shared__ double sh[256];
-    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
-    const int b = (int)blockIdx.y, n0 = (int)blockIdx.x * A1_CHUNK;
-    const int nv = (N - n0 < A1_CHUNK) ? N - n0 : A1_CHUNK;
-    if (tid < A1_CHUNK) {
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-        if (tid < nv) {
-            const float* xb = x + (size_t)b * 3 * N + n0 + tid;
-            const float p0 = xb[0], p1 = xb[N], p2 = xb[2 * N];
-            t0 = p0; t1 = p1; t2 = p2;
-            if (trans) {
-                const float* T = trans + (size_t)b * 9;
-                t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
-                t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
-                t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
-            }
-        }
-        xs[0][tid] = t0; xs[1][tid] = t1; xs[2][tid] = t2;
-    }
-    __syncthreads();
-    const float w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
-    const float sc = st.scale[k], sh_ = st.shift[k];
-    float* out = A1 + ((size_t)b * N + n0) * C1 + k;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int p = q; p < nv; p += 4) {
-        const float u = w0 * xs[0][p] + w1 * xs[1][p] + w2 * xs[2][p];
-        const float a = fmaxf(sc * u + sh_, 0.f);
-        out[(size_t)p * C1] = a;
-        acc += a;
-    }
-    if (part) {
-        sh[tid] = (double)acc;
-        __syncthreads();
-        if (tid < 64) part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C1 + tid] = sh[tid] + sh[tid + 64] + sh[tid + 128] + sh[tid + 192];
-    }
-}
-
 // per-block sums over points of a2 = relu(scale2*u2 + shift2); block = 128 channels x 2 slots.
 // pstride > 1: only every pstride-th point (Ms = ceil(M / pstride) samples) -- the pilot estimate of mean(a2).
 __global__ void k_a2_sum(const float* __restrict__ Y2, size_t Ms, size_t pstride, BnState st, double* __restrict__ part) {
@@ -324,11 +224,6 @@ __global__ void k_a2_sum(const float* __restrict__ Y2, size_t Ms, size_t pstride
     sh[tid] = acc;
     __syncthreads();
     if (tid < 128) part[(size_t)blockIdx.x * C2 + tid] = sh[tid] + sh[tid + 128];
-}
-
-__global__ void k_sign(const float* __restrict__ gamma, float* __restrict__ sgn, int C) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c < C) sgn[c] = gamma[c] >= 0.f ? 1.f : -1.f;
 }
 
 // ---- layer 2 forward: u2[P][c] = sum_k a1[P][k] W2[c][k] -----------------------------------------
@@ -390,7 +285,7 @@ struct ProbL3Fwd {
     __device__ float loadA(const Blk&, const float*, int m, int k) const { return W3[(size_t)m * C2 + k]; }
     __device__ float loadB(const Blk& b, const float* s, int k, int n) const {
         if (n >= N) return 0.f;
-        return fmaxf(s[k] * Y2[((size_t)b.b * N + n) * C2 + k] + s[C2 + k], 0.f);
+        return relu_nan(s[k] * Y2[((size_t)b.b * N + n) * C2 + k] + s[C2 + k]);
     }
     __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void* red) const {
         unsigned long long best[Cfg::TM];
@@ -424,22 +319,6 @@ struct ProbL3Fwd {
         }
     }
 };
-
-// decode the (max, arg-max) keys, apply BN3 (+ReLU) to the pooled values
-__global__ void k_pool_finalize(const unsigned long long* __restrict__ keys, const float* __restrict__ sgn, BnState st,
-                                int relu_last, size_t total, float* __restrict__ pooled, float* __restrict__ uext,
-                                int* __restrict__ idx) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)(i % C3);
-    unsigned long long key = keys[i];
-    float u = sgn[c] * ord_decode((unsigned)(key >> 32));
-    int n = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-    float g = st.scale[c] * u + st.shift[c];
-    if (relu_last) g = fmaxf(g, 0.f);
-    pooled[i] = g;
-    if (uext) { uext[i] = u; idx[i] = n; }
-}
 
 // ================================================================================================
 // backward kernels
@@ -510,90 +389,61 @@ struct ProbGram {
     }
 };
 
-// generic small dense GEMM: C[m][n] = sum_k (rs ? rs[k] : 1) * A[m*sam + k*sak] * B[k*sbk + n*sbn]
-template <bool AK, bool BN_>
-struct ProbDense {
-    static constexpr bool A_KFAST = AK, B_NFAST = BN_;
-    static constexpr int SCRATCH = 0;
-    using Cfg = CfgSmall;
-    const float* A; const float* Bm; float* C; const float* kscale;
-    int Mr, Nc, K; size_t sam, sak, sbk, sbn, ldc;
-    int kslice = 0;     // > 0: blockIdx.z selects a K slice of this size and writes its own Mr x ldc partial
-    struct Blk { int m0, n0, k0, k1; };
-    __device__ void setup(Blk& b) const {
-        b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = K;
-        if (kslice > 0) { b.k0 = (int)blockIdx.z * kslice; b.k1 = b.k0 + kslice < K ? b.k0 + kslice : K; }
-    }
-    __device__ void prologue(const Blk&, float*) const {}
-    __device__ float loadA(const Blk&, const float*, int m, int k) const {
-        if (m >= Mr) return 0.f;
-        float a = A[(size_t)m * sam + (size_t)k * sak];
-        return kscale ? a * kscale[k] : a;
-    }
-    __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < Nc ? Bm[(size_t)k * sbk + (size_t)n * sbn] : 0.f; }
-    __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
-#pragma unroll
-        for (int i = 0; i < Cfg::TM; ++i) {
-            int m = b.m0 + Cfg::row_of(ty, i);
-            if (m >= Mr) continue;
-#pragma unroll
-            for (int j = 0; j < Cfg::TN; ++j) {
-                int n = b.n0 + Cfg::col_of(tx, j);
-                if (n < Nc) C[(kslice > 0 ? (size_t)blockIdx.z * Mr * ldc : 0) + (size_t)m * ldc + n] = acc[i][j];
-            }
-        }
-    }
-};
-
-// uvec[i] = sum_c W3[c][i] * e[c];  grid = 4 blocks of 32 columns x 32 row lanes (fixed-order reduction)
-__global__ void k_uvec(const float* __restrict__ W3, const float* __restrict__ e, float* __restrict__ uvec) {
-    __shared__ double sh[32][33];
-    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
-    const int i = (int)blockIdx.x * 32 + cx;
-    double s = 0.0;
-#pragma unroll 8
-    for (int c = ry; c < C3; c += 32) s += (double)W3[(size_t)c * C2 + i] * (double)e[c];
-    sh[ry][cx] = s;
-    __syncthreads();
-    if (ry == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) t += sh[q][cx];
-        uvec[i] = (float)t;
-    }
-}
-
 // dW3[c][k] = sum_b coef[b][c] a2[argmax(b,c)][k]  -  d[c] * (W3 Gram)[c][k]  -  e[c] * S1[k]
-// grid = 1024 channels, block = 128 (k) x 4 cloud lanes; the lanes are summed in a fixed order
-__global__ void k_dw3(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ Y2, BnState st2,
-                      int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec,
-                      const float* __restrict__ WG, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
-    __shared__ float sh[4][128];
+// grid = 1024 channels, block = 512 = 16 cloud lanes (warps) x 32 lanes of 4 consecutive k (one 16-byte load per lane and
+// arg-max row, four rows in flight per warp); the 16 cloud lanes are summed in a fixed order.  The row c of W3 * Gram
+// (128 x 128, L2-resident) is formed here by warp 0 instead of by a separate 1024 x 128 x 128 GEMM launch.
+__global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ Y2, BnState st2,
+                      int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec, const float* __restrict__ W3,
+                      const float* __restrict__ gram, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
+    __shared__ float4 sh[16][32];
     __shared__ float s_cf[512];
     __shared__ int s_ix[512];
-    const int c = (int)blockIdx.x, tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
-    const float sc = st2.scale[k], sf = st2.shift[k];
-    float acc = 0.f;
+    __shared__ float s_w[C2];
+    const int c = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, q = tid >> 5;
+    const float4 sc = *reinterpret_cast<const float4*>(st2.scale + 4 * lane);
+    const float4 sf = *reinterpret_cast<const float4*>(st2.shift + 4 * lane);
+    if (tid < C2) s_w[tid] = W3[(size_t)c * C2 + tid];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b0 = 0; b0 < B; b0 += 512) {
         const int nb = (B - b0 < 512) ? B - b0 : 512;
         // stage this channel's coefficients / arg-max indices first, so the row loads below are independent
         if (tid < nb) { s_cf[tid] = coef[(size_t)(b0 + tid) * C3 + c]; s_ix[tid] = idx[(size_t)(b0 + tid) * C3 + c]; }
         __syncthreads();
 #pragma unroll 4
-        for (int bb = q; bb < nb; bb += 4) {
+        for (int bb = q; bb < nb; bb += 16) {
             const float cf = s_cf[bb];
             const size_t P = (size_t)(b0 + bb) * N + s_ix[bb];
-            const float a2v = fmaxf(sc * Y2[P * C2 + k] + sf, 0.f);
-            acc = fmaf(cf, a2v, acc);
+            const float4 y = *reinterpret_cast<const float4*>(Y2 + P * C2 + 4 * lane);
+            acc.x = fmaf(cf, fmaxf(fmaf(sc.x, y.x, sf.x), 0.f), acc.x);
+            acc.y = fmaf(cf, fmaxf(fmaf(sc.y, y.y, sf.y), 0.f), acc.y);
+            acc.z = fmaf(cf, fmaxf(fmaf(sc.z, y.z, sf.z), 0.f), acc.z);
+            acc.w = fmaf(cf, fmaxf(fmaf(sc.w, y.w, sf.w), 0.f), acc.w);
         }
         __syncthreads();
     }
-    sh[q][k] = acc;
+    sh[q][lane] = acc;
     __syncthreads();
     if (q == 0) {
-        const float t = ((sh[0][k] + sh[1][k]) + sh[2][k]) + sh[3][k];
-        dW3[(size_t)c * C2 + k] = t - dvec[c] * WG[(size_t)c * C2 + k] - evec[c] * (float)S1[k];
-        if (k == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
+        float4 t = sh[0][lane];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) { const float4 u = sh[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        // (W3 Gram)[c][4*lane .. 4*lane+3]
+        float4 wg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int j = 0; j < C2; ++j) {
+            const float wj = s_w[j];
+            const float4 gr = *reinterpret_cast<const float4*>(gram + (size_t)j * C2 + 4 * lane);
+            wg.x = fmaf(wj, gr.x, wg.x); wg.y = fmaf(wj, gr.y, wg.y); wg.z = fmaf(wj, gr.z, wg.z); wg.w = fmaf(wj, gr.w, wg.w);
+        }
+        const float d = dvec[c], e = evec[c];
+        float4 o;
+        o.x = t.x - d * wg.x - e * (float)S1[4 * lane + 0];
+        o.y = t.y - d * wg.y - e * (float)S1[4 * lane + 1];
+        o.z = t.z - d * wg.z - e * (float)S1[4 * lane + 2];
+        o.w = t.w - d * wg.w - e * (float)S1[4 * lane + 3];
+        *reinterpret_cast<float4*>(dW3 + (size_t)c * C2 + 4 * lane) = o;
+        if (lane == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
     }
 }
 
@@ -746,43 +596,48 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     const size_t M = (size_t)a.B * a.N;
     cudaStream_t s = a.stream;
     const double count = (double)M;
-
-    // ---- layer 1 ---------------------------------------------------------------------------------
-    if (a.train) {
-        launch(k_cloud_moments, dim3(a.B), dim3(256), 0, s, a.x, a.trans, a.N, w.moments, a.save ? w.xmom : (double*)nullptr);
-        const int S = colreduce<double>(w.moments, a.B, 12, w.rtmp, s);
-        launch(k_bn1_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, count, t.conv[0], t.bn[0], w.bn[0]);
-    } else {
-        launch(k_bn_eval_affine, grid1d(C1, 128), dim3(128), 0, s, C1, t.conv[0].b, t.bn[0], w.bn[0]);
-        launch(k_bn_eval_affine, grid1d(C2, 128), dim3(128), 0, s, C2, t.conv[1].b, t.bn[1], w.bn[1]);
-        launch(k_bn_eval_affine, grid1d(C3, 128), dim3(128), 0, s, C3, t.conv[2].b, t.bn[2], w.bn[2]);
-    }
-    launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK), a.B), dim3(256), 0, s, a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1,
-           a.train ? w.dpart : (double*)nullptr);
-
-    // ---- layer 2 ---------------------------------------------------------------------------------
-    if (a.train) {
-        const int S = colreduce<double>(w.dpart, w.nb_a1, C1, w.rtmp, s);
-        launch(k_matvec_mean, dim3(C2 / 8), dim3(256), 0, s, t.conv[1].w, C2, C1, (const double*)w.rtmp, S, 1.0, 1.0 / count, w.bn[1].mean, w.S1a);
-    }
-    int n_css2 = 0;
-    bool l3_pilot = false;      // BatchNorm3 statistics centred on a pilot mean (tcgen05 layer-3 kernel), corrected below
+    bool tcp = false;               // tensor-core path (tcgen05 kernels) for this call
 #ifndef PGPD_EMU
-    if (a.use_tc && (tc_mask() & 2)) {
-        launch(tc::k_prepack_rows, dim3(128), dim3(C1), 0, s, t.conv[1].w, C1, 1, C2, C1, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
-        static const bool use_kf = !(getenv("PGPD_KF") && atoi(getenv("PGPD_KF")) == 0);
-        if (use_kf) {
-            const int tpc = idiv_up(a.N, tc::KF_NT), ntiles = a.B * tpc;
-            tc::KfParams p{(const __half*)w.wimg_s, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
-                           w.A1, w.Y2, w.fpart, a.B, a.N, tpc, ntiles};
-            n_css2 = tc::KF_EPI_ROWS * tc::launch_kf(p, tc::dev_info().sms, s);
-        } else {
-            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
-            tc::L2FwdTC::Params p{(const __half*)w.wimg_s, M, ntiles, w.A1, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
-                                  w.Y2, w.fpart};
-            tc::launch_stream<tc::L2FwdTC>(p, tc::dev_info().sms, s);
-            n_css2 = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
-        }
+    tcp = a.use_tc;
+#endif
+    const float act_limit = tcp ? TC_ACT_LIMIT : INFINITY;
+
+    // max-pool keys, per-cloud "bad activation" flags and the tickets of the fused tail kernels: one memset
+    cudaMemsetAsync(w.keys, 0, w.zero_bytes, s);
+
+    // ---- F1: cloud moments + BatchNorm1 statistics (train) / folded running statistics (eval) + weight images -------------
+    {
+        PreParams p{};
+        p.x = a.x; p.trans = a.trans; p.B = a.B; p.N = a.N;
+        p.moments = w.moments; p.rawmom = a.save ? w.xmom : nullptr;
+        for (int L = 0; L < 3; ++L) { p.conv[L] = t.conv[L]; p.bn[L] = t.bn[L]; p.st[L] = w.bn[L]; }
+        p.train = a.train ? 1 : 0; p.count = count;
+        p.counter = w.counters + 0; p.bad = w.bad;
+        p.n_mom = a.train ? a.B : 1;
+        p.n_w2 = tcp ? C2 / 4 : 0; p.n_w3 = tcp ? C3 / 2 : 0;
+        p.wimg2 = w.wimg_s; p.inv2 = w.inv_s; p.wimg3 = w.wimg; p.sgn = w.sgn;
+#ifndef PGPD_EMU
+        p.act_shift = tc::ACT_SHIFT;
+#endif
+        const int n_sign = tcp ? 0 : C3 / PRE_THREADS;
+        launch(k_tower_pre, dim3(p.n_mom + p.n_w2 + p.n_w3 + n_sign), dim3(PRE_THREADS), 0, s, p);
+    }
+
+    // ---- layer 1 (+ train: sum of a1, mean of the layer-2 pre-activation) ---------------------------------------------------
+    {
+        A1Params p{a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1, a.train ? w.dpart : (double*)nullptr,
+                   w.counters + 1, t.conv[1].w, count, w.bn[1].mean, w.S1a, w.bad, act_limit};
+        launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK * A1_CPB), a.B), dim3(256), 0, s, p);
+    }
+
+    // ---- layer 2 ---------------------------------------------------------------------------------------------------------
+    int n_css2 = 0;
+#ifndef PGPD_EMU
+    if (tcp) {
+        const int tpc = idiv_up(a.N, tc::KF_NT), ntiles = a.B * tpc;
+        tc::KfParams p{(const __half*)w.wimg_s, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
+                       w.A1, w.Y2, w.fpart, a.B, a.N, tpc, ntiles};
+        n_css2 = tc::KF_EPI_ROWS * tc::launch_kf(p, tc::dev_info().sms, s);
     } else
 #endif
     {
@@ -790,70 +645,50 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         launch_gemm<ProbL2Fwd::Cfg>(p, dim3(w.nb_l2), s);
         n_css2 = w.nb_l2;
     }
+
+    // ---- T3 (train): BatchNorm2 statistics, (pilot) mean of a2 -> mean of the layer-3 pre-activation -----------------------
+    // Tensor-core path with many points: only a PILOT estimate of mean(a2) from TL2_SAMPLE points is computed here (the
+    // centre of the layer-3 kernel's sum of squares); that kernel's operand producers accumulate the exact sum of a2 on the
+    // way and k_tail_l3 corrects the statistics (var = sum (u-c)^2 / M - (mean - c)^2, an identity).
+    bool l3_pilot = false;
     if (a.train) {
-        const int S = colreduce<float>(w.fpart, n_css2, C2, w.rtmp, s);
-        launch(k_bn_finalize_from_css, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2,
-               (const float*)w.bn[1].mean, count, t.conv[1].b, t.bn[1], w.bn[1], (const float*)nullptr);
-        // mean of layer-3 pre-activation: W3 * mean(a2).  tcgen05 layer-3 kernel (version 1): only a PILOT estimate from
-        // every pstride-th point is computed here (the centre of the kernel's sum of squares); the kernel's operand
-        // producers accumulate the exact sum of a2 on the way and the statistics are corrected afterwards.
-        size_t pstride = 1;
-#ifndef PGPD_EMU
-        {
-            static const bool pilot_ok = !(getenv("PGPD_L3_PILOT") && atoi(getenv("PGPD_L3_PILOT")) == 0);
-            static const int l3v = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 3;
-            if (a.use_tc && (tc_mask() & 1) && pilot_ok && l3v != 2 && M >= 65536) pstride = M / 32768;
+        TailL2Params p{};
+        p.css = w.fpart; p.n_css = n_css2; p.mean_u2 = w.bn[1].mean; p.count = count; p.bias2 = t.conv[1].b; p.bn2 = t.bn[1]; p.st2 = w.bn[1];
+        p.Y2 = w.Y2; p.part = w.rtmp; p.counter = w.counters + 2;
+        p.W3 = t.conv[2].w; p.mean_u3 = w.bn[2].mean; p.S1 = w.S1; p.inv3 = w.sgn; p.mu_s = tcp ? w.mu_s : nullptr;
+        const size_t pstride = M >= 4 * (size_t)TL2_SAMPLE ? M / TL2_SAMPLE : 1;
+        p.pstride = pstride; p.nsample = (M + pstride - 1) / pstride;
+        launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(256), 0, s, p);
+        if (tcp) {
+            l3_pilot = pstride > 1;
+        } else {
+            // CUDA-core path: its layer-3 kernel centres the squares on the exact mean, so the sum of a2 over ALL points is
+            // taken now (BatchNorm2 is final) and the tail runs once more for the mean propagation only
+            const int nb = (int)std::min<size_t>((size_t)w.nb_a2, (M + 15) / 16);
+            launch(k_a2_sum, dim3(nb), dim3(256), 0, s, (const float*)w.Y2, M, (size_t)1, w.bn[1], w.dpart);
+            p.bn_done = 1; p.a2part = w.dpart; p.n_a2part = nb; p.nsample = M; p.pstride = 1;
+            launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(256), 0, s, p);
         }
-#endif
-        l3_pilot = pstride > 1;
-        const size_t Ms = (M + pstride - 1) / pstride;
-        const int nb = (int)std::min<size_t>((size_t)w.nb_a2, (Ms + 15) / 16);
-        launch(k_a2_sum, dim3(nb), dim3(256), 0, s, (const float*)w.Y2, Ms, pstride, w.bn[1], w.dpart);
-        const int S2 = colreduce<double>(w.dpart, nb, C2, w.rtmp, s);
-        launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.rtmp, S2, 1.0, 1.0 / (double)Ms, w.bn[2].mean, w.S1);
     }
 
-    // ---- layer 3 + max-pool ------------------------------------------------------------------------
-    cudaMemsetAsync(w.keys, 0, (size_t)a.B * C3 * sizeof(unsigned long long), s);
-    int n_css = 0, n_css_mult = 1, l3_grid = 0;
+    // ---- layer 3 + max-pool ------------------------------------------------------------------------------------------------
+    int n_css = 0, n_s1 = 0;
 #ifndef PGPD_EMU
-    if (a.use_tc && (tc_mask() & 1)) {
-        // layer-3 kernel version (PGPD_L3_VERSION): 3 (default) = CTA pairs with cta_group::2 MMAs; 1 = single-CTA 256-point
-        // tiles; 2 = CTA pairs that only share the weight stream by multicast (correct but slower)
-        static const int l3ver = getenv("PGPD_L3_VERSION") ? atoi(getenv("PGPD_L3_VERSION")) : 3;
-        const int tile_pts = l3ver == 2 ? tc::L3B_NT : tc::L3_NT;
-        const int tpc = idiv_up(a.N, tile_pts), ntiles = a.B * tpc;
-        launch(tc::k_prepack_w3, dim3(C3), dim3(128), 0, s, t.conv[2].w, t.bn[2].gamma,
-               a.train ? (const float*)w.bn[2].mean : (const float*)nullptr, (__half*)w.wimg, w.sgn, w.mu_s);
-        // PGPD_L3_DEBUG=1: the kernel writes per-CTA pipeline cycle counters to a debug buffer
-        static const bool l3dbg = getenv("PGPD_L3_DEBUG") != nullptr;
+    if (tcp) {
+        const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
         tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
-                       w.keys, w.fpart, a.B, a.N, tpc, ntiles, l3dbg ? tc::l3_debug_buffer() : nullptr,
-                       l3_pilot ? w.s1part : (float*)nullptr};
-        l3_grid = l3ver == 2 ? 0 : (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
+                       w.keys, w.fpart, a.B, a.N, tpc, ntiles, tc::l3_debug_buffer_if_enabled(),
+                       l3_pilot ? w.s1part : (float*)nullptr, w.bad};
         const int sms = tc::dev_info().sms;
+        const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
         profiler().begin(s);
-        if (l3ver == 2) {
-            const int pairs = (ntiles + 1) / 2 < sms / 2 ? (ntiles + 1) / 2 : sms / 2;
-            launch(tc::k_l3_fwd_tc2, dim3(2 * pairs), dim3(tc::L3_THREADS), (size_t)tc::L3B_SMEM_BYTES, s, p);
-        } else if (l3ver == 3) {
-            const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
-            // PGPD_L3_SPLIT=1: 16 KB sub-stages of the weight ring (see the kernel)
-            static const bool l3split = getenv("PGPD_L3_SPLIT") ? atoi(getenv("PGPD_L3_SPLIT")) != 0 : false;
-            if (l3split) launch(tc::k_l3_fwd_tc3<true>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
-            else launch(tc::k_l3_fwd_tc3<false>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
-            l3_grid = 2 * pairs * 8;                    // partial rows of the sum of a2: one per producer warp
-        } else {
-            const int grid = ntiles < sms ? ntiles : sms;
-            launch(tc::k_l3_fwd_tc, dim3(grid), dim3(tc::L3A_THREADS), (size_t)tc::L3_SMEM_BYTES, s, p);
-        }
+        launch(tc::k_l3_fwd_tc3<false>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
         profiler().end(s);
-        n_css_mult = l3ver == 2 ? 1 : (l3ver == 3 ? tc::L3C_EPI_ROWS : 2);
-        n_css = ntiles * n_css_mult;
+        n_css = pairs * tc::L3C_EPI_ROWS;             // partial rows of centred squares: four per CTA pair
+        n_s1 = 2 * pairs * 8;                         // partial rows of the sum of a2: one per producer warp
     } else
 #endif
     {
-        launch(k_sign, grid1d(C3, 256), dim3(256), 0, s, t.bn[2].gamma, w.sgn, C3);
         ProbL3Fwd p{t.conv[2].w, w.Y2, w.bn[1].scale, w.bn[1].shift, w.sgn, a.train ? w.bn[2].mean : nullptr,
                     w.keys, w.fpart, a.N, w.tiles_per_cloud};
         profiler().begin(s);
@@ -861,22 +696,19 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         profiler().end(s);
         n_css = a.B * w.tiles_per_cloud;
     }
-    if (a.train) {
-        const float* mean3 = w.bn[2].mean;
-        const float* centre = nullptr;
-        if (l3_pilot) {
-            // exact sum of a2 from the kernel's per-CTA partials -> exact mean of u3; bn[2].mean still holds the pilot centre
-            const int S1s = colreduce<float>(w.s1part, l3_grid, C2, w.rtmp, s);
-            launch(k_matvec_mean, dim3(C3 / 8), dim3(256), 0, s, t.conv[2].w, C3, C2, (const double*)w.rtmp, S1s,
-                   1.0 / 16.0 /* the kernel sums a2 * 2^4 (L3_ACT_SCALE) */, 1.0 / count, w.mu_x, w.S1);
-            mean3 = w.mu_x; centre = w.bn[2].mean;
-        }
-        const int S = colreduce<float>(w.fpart, n_css, C3, w.rtmp, s);
-        launch(k_bn_finalize_from_css, grid1d(C3, 128), dim3(128), 0, s, (const double*)w.rtmp, S, C3,
-               mean3, count, t.conv[2].b, t.bn[2], w.bn[2], centre);
+
+    // ---- T4: BatchNorm3 statistics (train) + pooled values -------------------------------------------------------------------
+    {
+        TailL3Params p{};
+        p.B = a.B; p.relu_last = a.relu_last ? 1 : 0; p.train = a.train ? 1 : 0;
+        p.keys = w.keys; p.sgn = w.sgn; p.st3 = w.bn[2];
+        p.pooled = pooled; p.uext = w.uext; p.idx = w.idx;
+        p.bad = w.bad; p.limit = act_limit;
+        p.css = w.fpart; p.n_css = n_css;
+        p.s1part = l3_pilot ? w.s1part : nullptr; p.n_s1 = n_s1; p.s1scale = 1.0 / 16.0;   // the kernel sums a2 * 2^4 (L3_ACT_SCALE)
+        p.W3 = t.conv[2].w; p.bias3 = t.conv[2].b; p.bn3 = t.bn[2]; p.count = count; p.S1 = w.S1;
+        launch(k_tail_l3, dim3(C3 / TL3_CH), dim3(256), 0, s, p);
     }
-    launch(k_pool_finalize, grid1d((size_t)a.B * C3, 256), dim3(256), 0, s, (const unsigned long long*)w.keys,
-           (const float*)w.sgn, w.bn[2], a.relu_last ? 1 : 0, (size_t)a.B * C3, pooled, w.uext, w.idx);
 }
 
 // dpooled [B][1024] -> parameter gradients (+ d trans).  Train-mode statistics only.
@@ -885,137 +717,93 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     const size_t M = (size_t)a.B * a.N;
     cudaStream_t s = a.stream;
     const double count = (double)M;
+    bool tcp = false;
+#ifndef PGPD_EMU
+    tcp = a.use_tc;
+#endif
 
     // ---- BN3 / max-pool on the pooled values ---------------------------------------------------------
     launch(k_pool_bwd, dim3(C3 / 32), dim3(1024), 0, s, dpooled, (const float*)w.uext, a.B, a.relu_last ? 1 : 0, count,
            t.bn[2].gamma, w.bn[2], w.coef, g.bn[2].dgamma, g.bn[2].dbeta, w.dvec, w.evec);
 
-    // Q = W3^T diag(d) W3  [128 x 128], K = 1024 split in 16 slices (blockIdx.z) and reduced deterministically
+    // ---- Q = W3^T diag(d) W3, uvec = W3^T e (+ the operand image of Q for the tensor-core pass A) ---------------
     {
-        ProbDense<false, true> p{t.conv[2].w, t.conv[2].w, w.fpart, w.dvec, C2, C2, C3, 1, (size_t)C2, (size_t)C2, 1, (size_t)C2};
-        p.kslice = C3 / 16;
-        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C2 / 64, 16), s);
-        colreduce_to_float<float>(w.fpart, 16, C2 * C2, w.Q, w.rtmp, s);
+        QuParams p{t.conv[2].w, w.dvec, w.evec, w.Q, w.uvec, tcp ? w.wimg_s : nullptr, w.inv_s, 0};
+#ifndef PGPD_EMU
+        p.act_shift = tc::ACT_SHIFT;
+#endif
+        launch(k_q_uvec, dim3(C2 / 4), dim3(128), 0, s, p);
     }
-    launch(k_uvec, dim3(C2 / 32), dim3(1024), 0, s, t.conv[2].w, (const float*)w.evec, w.uvec);
 
     // ---- sparse part of d a2 -----------------------------------------------------------------------
     cudaMemsetAsync(w.slot, 0xFF, M * sizeof(int), s);
     launch(k_da2_sparse, dim3(a.B), dim3(C3), 0, s, (const float*)w.coef, (const int*)w.idx, t.conv[2].w, a.N, w.da2s, w.slot);
 
-    // ---- layer 2 backward pass 1 (d a2 -> dz2, BatchNorm2 backward sums) and the Gram matrix of a2 -----------------------
-    // tcgen05: ONE kernel (tc_ka.cuh) unless PGPD_KA=0 selects the older pair (streaming GEMM + separate Gram kernel)
-    int g_b4 = 0;   // rows of pmax written by the tcgen05 pass-1 kernel
-    bool gram_done = false;
-    {
-        int nrows = 0;
-        const float* bnpart = w.fpart;
+    // ---- pass A: d a2 -> dz2 (stored), BatchNorm2 backward sums, Gram matrix of a2 --------------------------------------------
+    TailKaParams tk{};
+    tk.g2 = w.gram2; tk.gram = w.gram; tk.count = count;
+    tk.dgamma = g.bn[1].dgamma; tk.dbeta = g.bn[1].dbeta; tk.m1 = w.m1_2; tk.m2 = w.m2_2;
+    tk.W2 = t.conv[1].w; tk.st2 = w.bn[1]; tk.Kmat = w.Kmat; tk.cvec = w.cvec; tk.counter = w.counters + 3;
+    int g_b4 = 0;       // rows of pmax written by the tcgen05 pass-A kernel
 #ifndef PGPD_EMU
-        static const bool use_ka = !(getenv("PGPD_KA") && atoi(getenv("PGPD_KA")) == 0);
-        if (a.use_tc && (tc_mask() & 8) && use_ka) {
-            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
-            const int tpc = idiv_up(a.N, tc::KA_NT), ntiles = a.B * tpc;
-            tc::KaParams p{(const __half*)w.wimg_s, w.inv_s, w.uvec, w.bn[1].scale, w.bn[1].shift, t.bn[1].gamma, t.bn[1].beta,
-                           w.Y2, w.da2s, w.slot, a.B, a.N, tpc, ntiles, w.DZ2, w.ka_part, w.pmax, w.fpart};
-            const int grid = tc::launch_ka(p, tc::dev_info().sms, s);
-            nrows = grid * tc::KA_EPI_ROWS;
-            g_b4 = nrows;
-            bnpart = w.ka_part;
-            // Gram = hh + hl + hl^T from the per-CTA accumulators
-            colreduce_to_float<float>(w.fpart, grid, 2 * C2 * C2, w.gram2, w.rtmp, s);
-            launch(tc::k_gram_sym, grid1d(C2 * C2, 256), dim3(256), 0, s, (const float*)w.gram2, w.gram);
-            gram_done = true;
-        } else if (a.use_tc && (tc_mask() & 8)) {
-            launch(tc::k_prepack_rows, dim3(128), dim3(C2), 0, s, (const float*)w.Q, C2, 1, C2, C2, tc::ACT_SHIFT, (__half*)w.wimg_s, w.inv_s);
-            const int ntiles = (int)((M + tc::ST_NT - 1) / tc::ST_NT);
-            tc::L2BwdATC::Params p{(const __half*)w.wimg_s, M, ntiles, w.Y2, w.bn[1].scale, w.bn[1].shift, w.bn[1].mean, w.bn[1].rstd,
-                                   w.inv_s, w.uvec, w.da2s, w.slot, w.DZ2, w.ka_part, w.pmax};
-            tc::launch_stream<tc::L2BwdATC>(p, tc::dev_info().sms, s);
-            nrows = tc::ST_EPI_ROWS * (ntiles < tc::dev_info().sms ? ntiles : tc::dev_info().sms);
-            g_b4 = nrows;
-            bnpart = w.ka_part;
-        } else
+    if (tcp) {
+        const int tpc = idiv_up(a.N, tc::KA_NT), ntiles = a.B * tpc;
+        tc::KaParams p{(const __half*)w.wimg_s, w.inv_s, w.uvec, w.bn[1].scale, w.bn[1].shift, t.bn[1].gamma, t.bn[1].beta,
+                       w.Y2, w.da2s, w.slot, a.B, a.N, tpc, ntiles, w.DZ2, w.ka_part, w.pmax, w.fpart};
+        const int grid = tc::launch_ka(p, tc::dev_info().sms, s);
+        g_b4 = grid * tc::KA_EPI_ROWS;
+        tk.gpart = w.fpart; tk.n_g = grid; tk.gcols = 2 * C2 * C2; tk.sym = 1;      // per-CTA hi.hi / hi.lo accumulators
+        tk.bnpart = w.ka_part; tk.n_bn = g_b4;
+        tk.pmax = w.pmax; tk.n_pm = g_b4; tk.esc = w.esc; tk.einv = w.einv;
+        tk.img1 = w.wimg_kb; tk.img2 = (unsigned char*)w.wimg_kb + tc::KB_A1_BYTES; tk.ginv = w.inv_s; tk.act_scale = tc::ACT_SCALE;
+    } else
 #endif
-        {
-            ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.fpart, M};
-            launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
-            nrows = w.nb_l2;
-        }
-        const int S = colreduce<float>(bnpart, nrows, 2 * C2, w.rtmp, s);
-        launch(k_bn_bwd_finalize, dim3(1), dim3(128), 0, s, (const double*)w.rtmp, S, C2, count,
-               g.bn[1].dgamma, g.bn[1].dbeta, w.m1_2, w.m2_2);
+    {
+        // BatchNorm partial rows go to ka_part so that fpart is free for the Gram partials
+        ProbL2BwdA p{w.Y2, w.bn[1], w.Q, w.uvec, w.da2s, w.slot, w.DZ2, w.ka_part, M};
+        launch_gemm<ProbL2BwdA::Cfg>(p, dim3(w.nb_l2), s);
+        ProbGram pg{w.Y2, w.bn[1].scale, w.bn[1].shift, w.fpart, M};
+        launch_gemm<ProbGram::Cfg>(pg, dim3(w.nb_gram), s);
+        tk.gpart = w.fpart; tk.n_g = w.nb_gram; tk.gcols = C2 * C2; tk.sym = 0;
+        tk.bnpart = w.ka_part; tk.n_bn = w.nb_l2;
+        tk.act_scale = 1.f;
     }
+    launch(k_tail_ka, dim3(tk.gcols / 256), dim3(256), 0, s, tk);
 
-    // ---- Gram matrix of a2 (if the pass above did not produce it), W3 Gram, dW3 -----------------------------------------
-    if (!gram_done) {
-        int nrows = 0;
-#ifndef PGPD_EMU
-        if (a.use_tc && (tc_mask() & 4)) {
-            tc::GramTC::Params p{M, (int)((M + tc::AC_NT - 1) / tc::AC_NT), w.fpart, w.Y2, w.bn[1].scale, w.bn[1].shift};
-            nrows = tc::launch_accum<tc::GramTC>(p, tc::dev_info().sms, s);
-        } else
-#endif
-        {
-            ProbGram p{w.Y2, w.bn[1].scale, w.bn[1].shift, w.fpart, M};
-            launch_gemm<ProbGram::Cfg>(p, dim3(w.nb_gram), s);
-            nrows = w.nb_gram;
-        }
-        colreduce_to_float<float>(w.fpart, nrows, C2 * C2, w.gram, w.rtmp, s);
-    }
-    // WG = W3 * Gram  [1024 x 128]
-    {
-        ProbDense<true, true> p{t.conv[2].w, w.gram, w.WG, nullptr, C3, C2, C2, (size_t)C2, 1, (size_t)C2, 1, (size_t)C2};
-        launch_gemm<CfgSmall>(p, dim3(C2 / 64, C3 / 64), s);
-    }
-    launch(k_dw3, dim3(C3), dim3(4 * C2), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
-           (const float*)w.dvec, (const float*)w.evec, (const float*)w.WG, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
+    // ---- dW3 ---------------------------------------------------------------------------------------------------------------
+    launch(k_dw3, dim3(C3), dim3(512), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
+           (const float*)w.dvec, (const float*)w.evec, t.conv[2].w, (const float*)w.gram, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
 
-    // ---- layers 2 and 1: one fused pass over (dz2, a1) (l2bwd.cuh / tc_kb.cuh) ----
-    {
-        launch(k_kb_prep, dim3(C1), dim3(256), 0, s, t.conv[1].w, w.bn[1], (const float*)w.m1_2, (const float*)w.m2_2, w.Kmat, w.cvec);
-        int nparts = 0, nrows = 0, rpc = 0;
+    // ---- layers 2 and 1: one fused pass over (dz2, a1) (l2bwd.cuh / tc_kb.cuh) -------------------------------------------------
+    int nparts = 0, nrows = 0, rpc = 0;
 #ifndef PGPD_EMU
-        if (a.use_tc && (tc_mask() & 16) && g_b4 > 0) {
-            launch(tc::k_kb_scale, dim3(1), dim3(1024), 0, s, (const float*)w.pmax, g_b4, w.esc, w.einv);
-            __half* img1 = (__half*)w.wimg_kb;
-            __half* img2 = img1 + tc::KB_A1_BYTES / 2;
-            launch(tc::k_kb_prepack, dim3(128), dim3(128), 0, s, t.conv[1].w, (const float*)w.bn[1].scale, (const float*)w.einv,
-                   (const float*)w.Kmat, img1, img2, w.inv_s);
-            const int tpc = idiv_up(a.N, tc::KB_NT), ntiles = a.B * tpc;
-            tc::KbParams p{img1, img2, w.inv_s, w.cvec, t.bn[0].gamma, t.bn[0].beta, w.esc, w.einv, w.DZ2, w.A1, a.x,
-                           a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
-            nparts = tc::launch_kb(p, tc::dev_info().sms, s);
-            nrows = nparts * tc::KB_EPI_GROUPS; rpc = tpc * tc::KB_EPI_GROUPS;
-        } else
+    if (tcp) {
+        __half* img1 = (__half*)w.wimg_kb;
+        __half* img2 = img1 + tc::KB_A1_BYTES / 2;
+        const int tpc = idiv_up(a.N, tc::KB_NT), ntiles = a.B * tpc;
+        tc::KbParams p{img1, img2, w.inv_s, w.cvec, t.bn[0].gamma, t.bn[0].beta, w.esc, w.einv, w.DZ2, w.A1, a.x,
+                       a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
+        nparts = tc::launch_kb(p, tc::dev_info().sms, s);
+        nrows = nparts * tc::KB_EPI_GROUPS; rpc = tpc * tc::KB_EPI_GROUPS;
+    } else
 #endif
-        {
-            const int tpc = idiv_up(a.N, KB_REF_NT), ntiles = a.B * tpc;
-            const int grid = ntiles < KB_REF_MAX_BLOCKS ? ntiles : KB_REF_MAX_BLOCKS;
-            KbRefParams p{w.DZ2, w.A1, a.x, t.conv[1].w, w.bn[1].scale, w.Kmat, w.cvec, t.bn[0].gamma, t.bn[0].beta,
-                          a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
-            launch(k_kb_ref, dim3(grid), dim3(256), 0, s, p);
-            nparts = grid; nrows = ntiles; rpc = tpc;
-        }
-        {
-            const int S = colreduce<float>(w.kb_bn, nrows, 2 * C1, w.rtmp, s);
-            launch(k_bn_bwd_finalize, dim3(1), dim3(64), 0, s, (const double*)w.rtmp, S, C1, count,
-                   g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1);
-        }
-        {
-            colreduce_to_float<float>(w.kb_Cpart, nparts, C2 * C1, w.kbC, w.rtmp, s);
-        }
-        {
-            colreduce_to_float<float>(w.kb_G1part, nparts, C1 * C1, w.kbG1, w.rtmp, s);
-        }
-        launch(k_kb_dw2, dim3(C2), dim3(C1), 0, s, (const float*)w.kbC, (const float*)w.kbG1, (const double*)w.S1a, t.conv[1].w, w.bn[1],
-               (const float*)w.m1_2, (const float*)w.m2_2, g.conv[1].dw, g.conv[1].db);
-        launch(k_kb_l1, dim3(a.B), dim3(192), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
-               (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr);
-        {
-            colreduce_to_float<float>(w.fpart, a.B, C1 * 3, g.conv[0].dw, w.rtmp, s);
-        }
-        launch(k_fill, dim3(1), dim3(64), 0, s, g.conv[0].db, (size_t)C1, 0.f);
+    {
+        const int tpc = idiv_up(a.N, KB_REF_NT), ntiles = a.B * tpc;
+        const int grid = ntiles < KB_REF_MAX_BLOCKS ? ntiles : KB_REF_MAX_BLOCKS;
+        KbRefParams p{w.DZ2, w.A1, a.x, t.conv[1].w, w.bn[1].scale, w.Kmat, w.cvec, t.bn[0].gamma, t.bn[0].beta,
+                      a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
+        launch(k_kb_ref, dim3(grid), dim3(256), 0, s, p);
+        nparts = grid; nrows = ntiles; rpc = tpc;
     }
+    {
+        TailKbParams p{w.kb_Cpart, w.kb_G1part, nparts, w.kbC, w.kbG1, w.kb_bn, nrows, count, w.rtmp,
+                       g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1, w.S1a, t.conv[1].w, w.bn[1], w.m1_2, w.m2_2,
+                       g.conv[1].dw, g.conv[1].db, w.counters + 4};
+        launch(k_tail_kb, dim3(TKB_BLOCKS), dim3(256), 0, s, p);
+    }
+    launch(k_kb_l1, dim3(a.B), dim3(192), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
+           (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr, w.counters + 5,
+           g.conv[0].dw, g.conv[0].db);
 }
 
 }  // namespace pgpd

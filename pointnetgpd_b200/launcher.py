@@ -9,6 +9,7 @@ What it fabricates around the byte-identical script:
   * `tensorboardX.SummaryWriter` (main_1v.py:12,40) -> torch.utils.tensorboard if importable, else a no-op logger;
   * `torch.load` of whole-module pickles: `weights_only=False` default (main_1v.py:153) and the
     `torch.nn.backends.thnn` stub the 2018 checkpoint needs (SURVEY.md Appendix B);
+  * `scipy.stats.mode` accepts the CUDA tensors main_test.py:92 hands it under --cuda (host copies);
   * `./assets/learned_models` exists (the *_mc / fullv scripts never create it);
   * optionally a synthetic `$PointNetGPD_FOLDER` tree (`--synthetic-data DIR`, see `synth.py`).
 The script itself is executed with `runpy.run_path(..., run_name="__main__")`, which does not put the script's own
@@ -46,6 +47,24 @@ def install_shims():
         thnn = types.ModuleType("torch.nn.backends.thnn")
         thnn._get_thnn_function_backend = lambda: None
         sys.modules["torch.nn.backends.thnn"] = thnn
+    try:
+        # main_test.py:92 calls scipy.stats.mode on a list of tensors; with --cuda they are CUDA tensors, which numpy
+        # cannot read (TypeError in the unmodified reference as well).  Hand scipy host copies.
+        import scipy.stats as _st
+        import torch as _torch
+        if not getattr(_st.mode, "_pgpd_shim", False):
+            _orig_mode = _st.mode
+
+            def _mode(a, *args, **kwargs):
+                if isinstance(a, (list, tuple)):
+                    a = [t.detach().cpu().numpy() if isinstance(t, _torch.Tensor) else t for t in a]
+                elif isinstance(a, _torch.Tensor):
+                    a = a.detach().cpu().numpy()
+                return _orig_mode(a, *args, **kwargs)
+            _mode._pgpd_shim = True
+            _st.mode = _mode
+    except Exception:
+        pass
     os.environ.setdefault("TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD", "1")
     os.makedirs("./assets/learned_models", exist_ok=True)
 

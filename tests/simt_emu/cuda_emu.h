@@ -193,6 +193,7 @@ inline void* dyn_smem() {
 
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __threadfence() {}
 
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
     int lane = emu::S().cur % 32;

@@ -118,7 +118,7 @@ def test_odd_shapes_eval_gpu(B, N):
     assert (lo.cpu().numpy().argmax(1) == logp.argmax(1)).all()
 
 
-@pytest.mark.parametrize("B,N", [(2, 129), (2, 750), (3, 257), (2, 1000), (4, 1)])
+@pytest.mark.parametrize("B,N", [(2, 129), (2, 750), (3, 257), (2, 1000), (4, 1), (5, 750), (3, 1000)])
 def test_odd_shapes_train_step_gpu(B, N):
     """train step (batch statistics over B*N values; B = 2 is the smallest batch BatchNorm1d over the FC heads accepts)
     at odd tile tails, forward + backward vs the fp64 oracle."""
@@ -126,13 +126,19 @@ def test_odd_shapes_train_step_gpu(B, N):
     x = W.make_clouds(34, B, N, "box")
     y = W.make_labels(35, B, 2)
     ref_logp, ref_trans, ref_loss, ref_grads, _ = PN.nll_train_step(PN.cast_state(st, np.float64), x.astype(np.float64), y)
+    # BatchNorm over a batch of 2 (FC heads) is ill-conditioned: the reference's own fp32 arithmetic is 1e-2..1e-1 away from
+    # fp64 there.  The bar is therefore the larger of 1e-3 and twice the reference's fp32 error on the same input.
+    with torch.no_grad():
+        l32, t32 = PT.pointnetcls_forward(PT.to_torch_state(st, torch.float32), torch.tensor(x), training=True)
+    tol_l = max(LOGP_TOL, 2.0 * float(np.abs(l32.numpy() - ref_logp).max()))
+    tol_t = max(LOGP_TOL, 2.0 * float(np.abs(t32.numpy() - ref_trans).max()))
     m = _model(st, N, 2, train=True)
     logp, trans = m(torch.tensor(x).cuda())
     loss = torch.nn.functional.nll_loss(logp, torch.tensor(y).cuda())
     loss.backward()
-    assert np.abs(logp.detach().cpu().numpy() - ref_logp).max() < LOGP_TOL
-    assert np.abs(trans.detach().cpu().numpy() - ref_trans).max() < LOGP_TOL
-    if N > 1:      # N = 1: every pooled value IS the single point, gradients are ill-conditioned (BatchNorm over 4 values)
+    assert np.abs(logp.detach().cpu().numpy() - ref_logp).max() < tol_l
+    assert np.abs(trans.detach().cpu().numpy() - ref_trans).max() < tol_t
+    if N > 1 and B > 2:      # gradients: only where the problem is well conditioned
         for n, p in m.named_parameters():
             r = ref_grads[n].reshape(p.shape)
             nrm = np.linalg.norm(r)
@@ -140,6 +146,8 @@ def test_odd_shapes_train_step_gpu(B, N):
                 continue
             rel = np.linalg.norm(p.grad.cpu().numpy() - r) / nrm
             assert rel < 3e-2, (n, rel)
+    else:
+        assert all(bool(torch.isfinite(p.grad).all()) for p in m.parameters())
 
 
 def test_config4_per_gpu_shape_train_step():
@@ -173,15 +181,16 @@ def test_large_magnitude_inputs_never_saturate_silently():
     non-finite (poisoned) -- never finite and wrong; and the fp32 CUDA-core path (PGPD_F_SIMT) must match the oracle."""
     st = W.make_state(980, k=2, style="wild")
     m = _model(st, 300, 2, train=False)
-    x = torch.tensor(W.make_clouds(981, 6, 300, "box") * 1000.0).cuda()
+    x = torch.tensor(W.make_clouds(981, 6, 300, "box") * 1.0e5).cuda()
     sd = {kk: v.cuda() for kk, v in PT.to_torch_state(st, torch.float64).items()}
     with torch.no_grad():
         ref, _ = PT.pointnetcls_forward(sd, x.double(), training=False)
         a, _ = run_module(m, A.PGPD_CLS, x, k=2)
         b, _ = run_module(m, A.PGPD_CLS, x, k=2, flags_extra=A.F_SIMT)
+    tol = 2e-3 * max(1.0, float(ref.abs().max()))
     ok_rows = torch.isfinite(a).all(1)
-    assert float((a[ok_rows].double() - ref[ok_rows]).abs().max() if ok_rows.any() else 0.0) < 5e-3
-    assert float((b.double() - ref).abs().max()) < 5e-3 * max(1.0, float(ref.abs().max()))
+    assert float((a[ok_rows].double() - ref[ok_rows]).abs().max() if ok_rows.any() else 0.0) < tol
+    assert float((b.double() - ref).abs().max()) < tol
 
 
 def test_nan_input_propagates():
