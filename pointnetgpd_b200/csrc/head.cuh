@@ -1,7 +1,11 @@
 // head.cuh -- the small dense heads 1024->512->256->out with BatchNorm over the batch:
 //   STN3d regression head     pointnet.py:35-44  (out = 9, + identity)
 //   PointNetCls classifier    pointnet.py:191-194 (out = k, log_softmax)
-// CUDA-core fp32 kernels (2.6 MFLOP per grasp: launch count, not flops, is what matters here).
+// 2.6 MFLOP per grasp: launch count, not flops, is what matters here.  fc1 / fc2 (forward, dW, dX) are split-K GEMMs
+// (tcgen05: tc_gemm.cuh; CUDA-core: gemm_simt.cuh) that write their K-slice partials; the kernel that CONSUMES a GEMM's
+// output (BatchNorm forward / backward, gradient finish) sums the slices in a fixed order on the way in, so no separate
+// "split-K finish" launch exists.  fc3 (9 / k outputs) is a CUDA-core kernel fused with its bias, the identity of the
+// T-Net and log_softmax.
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -11,6 +15,10 @@
 
 namespace pgpd {
 
+constexpr size_t HEAD_PART_ELEMS = (size_t)4 << 20;   // 16 MB of fp32 split-K partials per buffer (two buffers)
+constexpr int HEAD_AMAX_BLOCKS = 64;                  // partial maxima per weight matrix (forward operand scales)
+constexpr int HEAD_AMAX_ELEMS = 2 * HEAD_AMAX_BLOCKS + 2 * 16;   // [fc1.weight | fc2.weight] x 64, [dU1 | dU2] x 16
+
 struct HeadWs {
     float* U1;        // [B][512]  bias-free pre-activation of fc1
     float* U2;        // [B][256]
@@ -18,15 +26,14 @@ struct HeadWs {
     float* Hm2;       // [B][256]
     float* out;       // [B][out]  fc3 output (+bias, + identity for the STN head) = logits / t9
     BnState bn[2];
-    float* part;      // split-K partials: HEAD_PART_ELEMS floats
+    float* partA;     // split-K partials of the first GEMM of a pair
+    float* partB;     // ... of the second
     // backward scratch
-    float* DZ1;       // [B][512]  dz1, then (in place) dU1
-    float* DZ2;       // [B][256]
+    float* DZ1;       // [B][512]  dU1
+    float* DZ2;       // [B][256]  dz2, then (in place) dU2
     float* dO;        // [B][out]  gradient w.r.t. fc3 output
-    unsigned* amax;   // [4] bit patterns of max |x|: fc1.weight, fc2.weight, dU1, dU2 (operand scales of the tcgen05 GEMMs)
+    unsigned* amax;   // [HEAD_AMAX_ELEMS] bit patterns of partial max |x| (operand scales of the tcgen05 GEMMs)
 };
-
-constexpr size_t HEAD_PART_ELEMS = (size_t)4 << 20;   // 16 MB of fp32 partials
 
 inline void plan_head(Carver& c, HeadWs& w, int B, int out, bool backward) {
     w.U1 = c.take<float>((size_t)B * H1);
@@ -35,8 +42,9 @@ inline void plan_head(Carver& c, HeadWs& w, int B, int out, bool backward) {
     w.Hm2 = c.take<float>((size_t)B * H2);
     w.out = c.take<float>((size_t)B * out);
     w.bn[0].carve(c, H1); w.bn[1].carve(c, H2);
-    w.part = c.take<float>(HEAD_PART_ELEMS);
-    w.amax = c.take<unsigned>(4);
+    w.partA = c.take<float>(HEAD_PART_ELEMS);
+    w.partB = c.take<float>(HEAD_PART_ELEMS);
+    w.amax = c.take<unsigned>(HEAD_AMAX_ELEMS);
     if (backward) {
         w.DZ1 = c.take<float>((size_t)B * H1);
         w.DZ2 = c.take<float>((size_t)B * H2);
@@ -44,30 +52,26 @@ inline void plan_head(Carver& c, HeadWs& w, int B, int out, bool backward) {
     }
 }
 
-// ---- plain fp32 GEMM on row-major matrices with optional split-K ---------------------------------------
-//   C[m][n] = sum_k A(m,k) B(k,n);  A(m,k) = A[m*sam + k*sak], B(k,n) = Bm[k*sbk + n*sbn]
-// epilogue (only when the whole K range is handled by one block, ksl == 0):
-//   EPI_BIAS: + bias[n] (+1 on the diagonal of a flattened 3x3 when add_identity);  EPI_MASK: zero where mask[m][n] <= 0
-enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_MASK = 2 };
+// ---- plain fp32 GEMM on row-major matrices, split-K partials -------------------------------------------------------
+//   part[z][m][n] = sum_{k in slice z} A(m,k) B(k,n);  A(m,k) = A[m*sam + k*sak], B(k,n) = Bm[k*sbk + n*sbn]
 template <bool AK, bool BNF>
 struct ProbPlain {
     static constexpr bool A_KFAST = AK, B_NFAST = BNF;
     static constexpr int SCRATCH = 0;
     using Cfg = CfgSmall;
-    const float* A; const float* Bm; float* C; float* part;
+    const float* A; const float* Bm; float* part;
     int Mr, Nc, K; size_t sam, sak, sbk, sbn;
-    int ksl;            // 0: no split; else K-slice length, blockIdx.z selects the slice, output goes to part[z][Mr][Nc]
-    int epi; const float* bias; int add_identity; const float* mask;
+    int ksl;            // K-slice length; blockIdx.z selects the slice
     struct Blk { int m0, n0, k0, k1; };
     __device__ void setup(Blk& b) const {
-        b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN; b.k0 = 0; b.k1 = K;
-        if (ksl > 0) { b.k0 = (int)blockIdx.z * ksl; b.k1 = b.k0 + ksl < K ? b.k0 + ksl : K; }
+        b.m0 = (int)blockIdx.y * Cfg::BM; b.n0 = (int)blockIdx.x * Cfg::BN;
+        b.k0 = (int)blockIdx.z * ksl; b.k1 = b.k0 + ksl < K ? b.k0 + ksl : K;
     }
     __device__ void prologue(const Blk&, float*) const {}
     __device__ float loadA(const Blk&, const float*, int m, int k) const { return m < Mr ? A[(size_t)m * sam + (size_t)k * sak] : 0.f; }
     __device__ float loadB(const Blk&, const float*, int k, int n) const { return n < Nc ? Bm[(size_t)k * sbk + (size_t)n * sbn] : 0.f; }
     __device__ void epilogue(const Blk& b, const float*, float (&acc)[Cfg::TM][Cfg::TN], int ty, int tx, void*) const {
-        float* out = ksl > 0 ? part + (size_t)blockIdx.z * Mr * Nc : C;
+        float* out = part + (size_t)blockIdx.z * Mr * Nc;
 #pragma unroll
         for (int i = 0; i < Cfg::TM; ++i) {
             const int m = b.m0 + Cfg::row_of(ty, i);
@@ -75,107 +79,146 @@ struct ProbPlain {
 #pragma unroll
             for (int j = 0; j < Cfg::TN; ++j) {
                 const int n = b.n0 + Cfg::col_of(tx, j);
-                if (n >= Nc) continue;
-                float v = acc[i][j];
-                if (ksl == 0) v = finish(v, m, n);
-                out[(size_t)m * Nc + n] = v;
+                if (n < Nc) out[(size_t)m * Nc + n] = acc[i][j];
             }
         }
     }
-    __device__ float finish(float v, int m, int n) const {
-        if (epi == EPI_BIAS) { v += bias[n]; if (add_identity && (n % 4 == 0)) v += 1.f; }   // entries 0,4,8 (pointnet.py:39-43)
-        else if (epi == EPI_MASK) { if (!(mask[(size_t)m * Nc + n] > 0.f)) v = 0.f; }
-        return v;
-    }
 };
 
-// sums the split-K partials in a fixed order and applies the epilogue
-template <bool AK, bool BNF>
-__global__ void k_splitk_finish(ProbPlain<AK, BNF> p, int nsl) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)p.Mr * p.Nc;
-    if (i >= total) return;
-    float v = 0.f;
-    for (int z = 0; z < nsl; ++z) v += p.part[(size_t)z * total + i];
-    p.C[i] = p.finish(v, (int)(i / p.Nc), (int)(i % p.Nc));
-}
-
-// fixed_nsl > 0: use exactly that many K slices (forward GEMMs: the summation order must not depend on the batch
-// size, so that eval outputs are bit-identical however the clouds are batched); 0: pick by occupancy.
-template <bool AK, bool BNF>
-inline void run_plain(ProbPlain<AK, BNF> p, cudaStream_t s, int fixed_nsl = 0) {
-    const int tm = idiv_up(p.Mr, CfgSmall::BM), tn = idiv_up(p.Nc, CfgSmall::BN);
+// number of K slices.  fixed_nsl > 0: exactly that many (forward GEMMs: the summation order must not depend on the batch
+// size, so that eval outputs are bit-identical however the clouds are batched); 0: by occupancy.
+inline int pick_slices(int tiles, int Mr, int Nc, int K, int min_slice, int fixed_nsl) {
     int nsl = 1;
-    if (fixed_nsl > 0) {
-        nsl = fixed_nsl;
-        while (nsl > 1 && (size_t)nsl * p.Mr * p.Nc > HEAD_PART_ELEMS) nsl /= 2;    // huge batches: fewer slices (still batch-size independent below 4M outputs)
-    } else {
-        // enough blocks to occupy the chip (>= ~2 per SM), K slices of at least 64
-        while (tm * tn * nsl < 296 && p.K / (nsl * 2) >= 64 && (size_t)(nsl * 2) * p.Mr * p.Nc <= HEAD_PART_ELEMS) nsl *= 2;
-    }
-    p.ksl = nsl > 1 ? idiv_up(p.K, nsl) : 0;
-    launch_gemm<CfgSmall>(p, dim3(tn, tm, nsl), s);
-    if (nsl > 1) launch(k_splitk_finish<AK, BNF>, grid1d((size_t)p.Mr * p.Nc, 256), dim3(256), 0, s, p, nsl);
+    if (fixed_nsl > 0) nsl = fixed_nsl;
+    else
+        while (tiles * nsl < 148 && K / (nsl * 2) >= min_slice && (size_t)(nsl * 2) * Mr * Nc <= HEAD_PART_ELEMS) nsl *= 2;
+    while (nsl > 1 && (size_t)nsl * Mr * Nc > HEAD_PART_ELEMS) nsl /= 2;
+    return nsl;
 }
 
-// batch statistics of U[:,c] (two-pass, double) -> BatchNorm finalisation -> H = relu(scale*U + shift).
-// block = 32 channels x 32 row lanes (fixed-order shared-memory reduction: deterministic)
-__global__ void k_bn_batch_stats_apply(const float* __restrict__ U, int B, int C, const float* bias, pgpd_bn bn, BnState st,
-                                       float* __restrict__ Hout) {
+// returns the number of slices written to `part`
+template <bool AK, bool BNF>
+inline int run_plain(ProbPlain<AK, BNF> p, cudaStream_t s, int fixed_nsl) {
+    const int tm = idiv_up(p.Mr, CfgSmall::BM), tn = idiv_up(p.Nc, CfgSmall::BN);
+    int nsl = pick_slices(tm * tn, p.Mr, p.Nc, p.K, 64, fixed_nsl);
+    p.ksl = idiv_up(p.K, nsl);
+    nsl = idiv_up(p.K, p.ksl);
+    launch_gemm<CfgSmall>(p, dim3(tn, tm, nsl), s);
+    return nsl;
+}
+
+#ifndef PGPD_EMU
+// C[M][N] = sum_k A(m,k) B(n,k) on the tensor cores; returns the number of K slices written to `part`
+inline int run_gemm_tc(tc::GemmOp A, tc::GemmOp Bo, int M, int N, int K, float* part, int nsl_fixed, cudaStream_t s) {
+    const int tiles = idiv_up(M, tc::GM_T) * idiv_up(N, tc::GM_T);
+    int nsl = pick_slices(tiles, M, N, K, tc::GM_KC, nsl_fixed);
+    const int kslice = idiv_up(idiv_up(K, nsl), tc::GM_KC) * tc::GM_KC;
+    nsl = idiv_up(K, kslice);                       // no empty slices
+    tc::GemmParams p{A, Bo, M, N, K, kslice, part, nullptr};
+    tc::launch_gemm_tc(p, nsl, s);
+    return nsl;
+}
+#endif
+
+// ---- BatchNorm over the batch, forward -----------------------------------------------------------------------------------
+// U[b][c] = sum_z part[z][b][c] (fixed order; written out, the backward needs it); train: batch statistics of U[:,c]
+// (two-pass, double) -> finalisation + running statistics; eval: folded running statistics; H = relu(scale*U + shift).
+// limit: an activation beyond it (the fp16 operand range of the tensor-core GEMM that consumes H) is replaced by NaN
+// instead of being clamped silently.  block = 32 channels x 32 row lanes (fixed-order reduction: deterministic).
+__global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ part, int nsl, int B, int C, int train,
+                                                      const float* bias, pgpd_bn bn, BnState st, float limit,
+                                                      float* __restrict__ U, float* __restrict__ Hout) {
     __shared__ double sh[32][33];
     __shared__ double smean[32];
+    __shared__ float s_sc[32], s_sf[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
+    const size_t slice = (size_t)B * C;
     double s = 0.0;
     if (c < C) {
-#pragma unroll 4
-        for (int b = ry; b < B; b += 32) s += (double)U[(size_t)b * C + c];
+        for (int b = ry; b < B; b += 32) {
+            const size_t i = (size_t)b * C + c;
+            float u = part[i];
+            for (int z = 1; z < nsl; ++z) u += part[(size_t)z * slice + i];
+            U[i] = u;
+            s += (double)u;
+        }
     }
-    sh[ry][cx] = s;
-    __syncthreads();
-    if (ry == 0) {
-        double t = 0.0;
-        for (int q = 0; q < 32; ++q) t += sh[q][cx];
-        smean[cx] = t / B;
-    }
-    __syncthreads();
-    const double mean = smean[cx];
-    double v = 0.0;
-    if (c < C)
-        for (int b = ry; b < B; b += 32) { double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
-    sh[ry][cx] = v;
-    __syncthreads();
-    if (ry == 0 && c < C) {
-        double t = 0.0;
-        for (int q = 0; q < 32; ++q) t += sh[q][cx];
-        bn_finalize_train(c, mean, t / B, (double)B, bias, bn, st);
+    if (train) {
+        sh[ry][cx] = s;
+        __syncthreads();
+        if (ry == 0) {
+            double t = 0.0;
+            for (int q = 0; q < 32; ++q) t += sh[q][cx];
+            smean[cx] = t / B;
+        }
+        __syncthreads();
+        const double mean = smean[cx];
+        double v = 0.0;
+        if (c < C)
+            for (int b = ry; b < B; b += 32) { const double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
+        sh[ry][cx] = v;
+        __syncthreads();
+        if (ry == 0 && c < C) {
+            double t = 0.0;
+            for (int q = 0; q < 32; ++q) t += sh[q][cx];
+            bn_finalize_train(c, mean, t / B, (double)B, bias, bn, st);
+            s_sc[cx] = st.scale[c]; s_sf[cx] = st.shift[c];
+        }
+    } else if (ry == 0 && c < C) {
+        const float rstd = 1.0f / sqrtf(bn.running_var[c] + BN_EPS);
+        const float sc = bn.gamma[c] * rstd;
+        const float bb = bias ? bias[c] : 0.f;
+        s_sc[cx] = sc; s_sf[cx] = bn.beta[c] + sc * (bb - bn.running_mean[c]);
     }
     __syncthreads();
     if (c < C) {
-        const float sc = st.scale[c], sf = st.shift[c];
-        for (int b = ry; b < B; b += 32) Hout[(size_t)b * C + c] = fmaxf(sc * U[(size_t)b * C + c] + sf, 0.f);
+        const float sc = s_sc[cx], sf = s_sf[cx];
+        const float qnan = __uint_as_float(0x7FC00000u);
+        for (int b = ry; b < B; b += 32) {
+            float h = relu_nan(sc * U[(size_t)b * C + c] + sf);
+            if (!(h <= limit)) h = qnan;
+            Hout[(size_t)b * C + c] = h;
+        }
     }
 }
 
-// H = relu(scale*U + shift) (eval mode, after k_bn_eval_affine)
-__global__ void k_bn_apply(const float* __restrict__ U, size_t total, int C, BnState st, float* __restrict__ Hout) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)(i % C);
-    Hout[i] = fmaxf(st.scale[c] * U[i] + st.shift[c], 0.f);
-}
-
-// log_softmax over the last dim (pointnet.py:194); thread = row
-__global__ void k_log_softmax(const float* __restrict__ logits, int B, int K, float* __restrict__ logp) {
-    int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+// ---- fc3 + bias (+ identity of the T-Net, pointnet.py:39-43) (+ log_softmax, pointnet.py:194) ------------------------------
+// one warp per cloud, fixed shuffle tree (the result of a cloud does not depend on the batch it is in).
+//   out [B][J]: fc3 output incl. bias / identity (kept: logits / t9);  user1: copy of out (STN: trans) or null;
+//   logp / user2: log_softmax(out) (classifier) or null.
+__global__ void __launch_bounds__(256) k_fc3_out(const float* __restrict__ Hm2, const float* __restrict__ W, const float* __restrict__ bias,
+                                                 int B, int J, int add_identity, float* __restrict__ out, float* __restrict__ user1,
+                                                 float* __restrict__ logp, float* __restrict__ user2) {
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    const int b = (int)blockIdx.x * 8 + warp;
     if (b >= B) return;
-    const float* l = logits + (size_t)b * K;
-    float m = l[0];
-    for (int j = 1; j < K; ++j) m = fmaxf(m, l[j]);
-    float s = 0.f;
-    for (int j = 0; j < K; ++j) s += expf(l[j] - m);
-    float lse = m + logf(s);
-    for (int j = 0; j < K; ++j) logp[(size_t)b * K + j] = l[j] - lse;
+    float h[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) h[u] = Hm2[(size_t)b * H2 + lane + 32 * u];
+    float mx = -INFINITY;
+    for (int j = 0; j < J; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = fmaf(h[u], W[(size_t)j * H2 + lane + 32 * u], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s += bias[j];
+        if (add_identity && (j % 4 == 0)) s += 1.f;          // entries 0, 4, 8 of the flattened 3x3
+        if (lane == 0) { out[(size_t)b * J + j] = s; if (user1) user1[(size_t)b * J + j] = s; }
+        mx = s > mx || s != s ? s : mx;                       // NaN wins (log_softmax of a row with NaN is NaN)
+    }
+    if (!logp) return;
+    __syncwarp();
+    // log_softmax over J values written by lane 0 of this warp: every lane re-reads them (J is small: k classes)
+    float sum = 0.f;
+    for (int j = 0; j < J; ++j) sum += expf(out[(size_t)b * J + j] - mx);
+    const float lse = mx + logf(sum);
+    for (int j = lane; j < J; j += 32) {
+        const float v = out[(size_t)b * J + j] - lse;
+        logp[(size_t)b * J + j] = v;
+        if (user2) user2[(size_t)b * J + j] = v;
+    }
 }
 
 // dlogits = dlogp - softmax * sum_j dlogp
@@ -188,35 +231,65 @@ __global__ void k_log_softmax_bwd(const float* __restrict__ logp, const float* _
     for (int j = 0; j < K; ++j) dlogits[(size_t)b * K + j] = dlogp[(size_t)b * K + j] - expf(logp[(size_t)b * K + j]) * s;
 }
 
-// out[j] = sum_b G[b][j]   (bias gradient of fc3); block = column, 256 row lanes summed in a fixed order
-__global__ void k_colsum(const float* __restrict__ G, int B, int J, float* __restrict__ out) {
-    __shared__ double sh[256];
-    const int j = (int)blockIdx.x, tid = (int)threadIdx.x;
-    double s = 0.0;
-    for (int b = tid; b < B; b += 256) s += (double)G[(size_t)b * J + j];
-    sh[tid] = s;
-    __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
-        if (tid < st) sh[tid] += sh[tid + st];
-        __syncthreads();
+// ---- fc3 backward: dW3[j][i] = sum_b dO[b][j] H2[b][i];  db3[j] = sum_b dO[b][j];  dz2[b][i] = (sum_j dO[b][j] W3[j][i]) [H2 > 0]
+// blocks [0, J): one output row j of dW3 (thread i; clouds summed in order) + db3[j];  blocks [J, J + ceil(B/8)): dz2 of 8 clouds.
+__global__ void __launch_bounds__(256) k_fc3_bwd(const float* __restrict__ dO, const float* __restrict__ Hm2, const float* __restrict__ W3,
+                                                 int B, int J, float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ DZ2) {
+    const int i = (int)threadIdx.x;
+    if ((int)blockIdx.x < J) {
+        const int j = (int)blockIdx.x;
+        float a0 = 0.f, a1 = 0.f;
+        double bsum = 0.0;
+        int b = 0;
+        for (; b + 1 < B; b += 2) {
+            const float d0 = dO[(size_t)b * J + j], d1 = dO[(size_t)(b + 1) * J + j];
+            a0 = fmaf(d0, Hm2[(size_t)b * H2 + i], a0);
+            a1 = fmaf(d1, Hm2[(size_t)(b + 1) * H2 + i], a1);
+            bsum += (double)d0 + (double)d1;
+        }
+        if (b < B) { const float d0 = dO[(size_t)b * J + j]; a0 = fmaf(d0, Hm2[(size_t)b * H2 + i], a0); bsum += (double)d0; }
+        dW3[(size_t)j * H2 + i] = a0 + a1;
+        if (i == 0) db3[j] = (float)bsum;
+        return;
     }
-    if (tid == 0) out[j] = (float)sh[0];
+    const int b0 = ((int)blockIdx.x - J) * 8;
+    for (int bb = 0; bb < 8 && b0 + bb < B; ++bb) {
+        const int b = b0 + bb;
+        float s = 0.f;
+        for (int j = 0; j < J; ++j) s = fmaf(dO[(size_t)b * J + j], W3[(size_t)j * H2 + i], s);
+        DZ2[(size_t)b * H2 + i] = Hm2[(size_t)b * H2 + i] > 0.f ? s : 0.f;
+    }
 }
 
-// BatchNorm-over-batch backward: sums -> dgamma, dbeta; then dU = s*(dz - m1 - yhat*m2) written IN PLACE over dz.
+// ---- BatchNorm-over-batch backward -------------------------------------------------------------------------------------------
+// dz[b][c] = sum_z part[z][b][c] masked by H[b][c] > 0 (part != null: the dZ GEMM's split-K partials) or DZ as given;
+// sums -> dgamma, dbeta; dU = s*(dz - m1 - yhat*m2) written to DZ; db (the Linear bias feeding this BatchNorm) = 0;
+// amax_part[block] = max |dU| of the block (operand scale of the tcgen05 GEMMs that consume dU).
 // block = 32 channels x 32 row lanes.
-__global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, unsigned* __restrict__ amax) {
+__device__ __forceinline__ void bn_head_bwd_block(int blk, const float* __restrict__ part, int nsl, const float* __restrict__ Hmask,
+                                                  float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
+                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db,
+                                                  unsigned* __restrict__ amax_part) {
     __shared__ double sh1[32][33], sh2[32][33];
     __shared__ float sm1[32], sm2[32];
+    __shared__ float smx[32];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
-    const int c = (int)blockIdx.x * 32 + cx;
+    const int c = blk * 32 + cx;
     const float mu = c < C ? st.mean[c] : 0.f, r = c < C ? st.rstd[c] : 0.f, sc = c < C ? st.scale[c] : 0.f;
+    const size_t slice = (size_t)B * C;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
         for (int b = ry; b < B; b += 32) {
-            double dz = (double)DZ[(size_t)b * C + c];
-            double yhat = (double)((U[(size_t)b * C + c] - mu) * r);
+            const size_t i = (size_t)b * C + c;
+            float dzf;
+            if (part) {
+                dzf = part[i];
+                for (int z = 1; z < nsl; ++z) dzf += part[(size_t)z * slice + i];
+                if (!(Hmask[i] > 0.f)) dzf = 0.f;
+                DZ[i] = dzf;
+            } else dzf = DZ[i];
+            const double dz = (double)dzf;
+            const double yhat = (double)((U[i] - mu) * r);
             s1 += dz; s2 += dz * yhat;
         }
     }
@@ -225,7 +298,7 @@ __global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __rest
     if (ry == 0) {
         double t1 = 0.0, t2 = 0.0;
         for (int q = 0; q < 32; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
-        if (c < C) { dgamma[c] = (float)t2; dbeta[c] = (float)t1; }
+        if (c < C) { dgamma[c] = (float)t2; dbeta[c] = (float)t1; if (db) db[c] = 0.f; }
         sm1[cx] = (float)(t1 / B); sm2[cx] = (float)(t2 / B);
     }
     __syncthreads();
@@ -240,10 +313,61 @@ __global__ void k_bn_batch_bwd_apply(float* __restrict__ DZ, const float* __rest
             mx = fmaxf(mx, fabsf(du));
         }
     }
-    if (amax) {     // max |dU|: operand scale of the tcgen05 GEMMs that consume dU (max is order-independent: deterministic)
+    if (amax_part) {     // max |dU| of this block (max is order-independent: deterministic)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (cx == 0) atomicMax(amax, __float_as_uint(mx));
+        if (cx == 0) smx[ry] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            float m = smx[0];
+            for (int q = 1; q < 32; ++q) m = fmaxf(m, smx[q]);
+            amax_part[blk] = __float_as_uint(m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_bn_head_bwd(float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
+                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db,
+                                                      unsigned* __restrict__ amax_part) {
+    bn_head_bwd_block((int)blockIdx.x, nullptr, 0, nullptr, DZ, U, B, C, st, dgamma, dbeta, db, amax_part);
+}
+
+// blocks [0, nbn): BatchNorm backward of the layer below, reading the dZ GEMM's partials (sum + ReLU mask);
+// remaining blocks: dW[i] = sum_z partW[z][i] (the dW GEMM's partials)
+__global__ void __launch_bounds__(1024) k_head_mid(int nbn, const float* __restrict__ partZ, int nslZ, const float* __restrict__ Hmask,
+                                                   float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
+                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db,
+                                                   unsigned* __restrict__ amax_part,
+                                                   const float* __restrict__ partW, int nslW, size_t nW, float* __restrict__ dW) {
+    if ((int)blockIdx.x < nbn) {
+        bn_head_bwd_block((int)blockIdx.x, partZ, nslZ, Hmask, DZ, U, B, C, st, dgamma, dbeta, db, amax_part);
+        return;
+    }
+    const size_t i = (size_t)((int)blockIdx.x - nbn) * 1024 + threadIdx.x;
+    if (i >= nW) return;
+    float v = partW[i];
+    for (int z = 1; z < nslW; ++z) v += partW[(size_t)z * nW + i];
+    dW[i] = v;
+}
+
+// out1[i] = sum_z part1[z][i] (i < n1);  out2[i] = sum_z part2[z][i] (i < n2)
+__global__ void __launch_bounds__(1024) k_finish2(const float* __restrict__ part1, int nsl1, size_t n1, float* __restrict__ out1,
+                                                  const float* __restrict__ part2, int nsl2, size_t n2, float* __restrict__ out2) {
+    size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    const size_t n1r = ((n1 + 1023) / 1024) * 1024;
+    if (i < n1r) {
+        if (i < n1) {
+            float v = part1[i];
+            for (int z = 1; z < nsl1; ++z) v += part1[(size_t)z * n1 + i];
+            out1[i] = v;
+        }
+        return;
+    }
+    i -= n1r;
+    if (i < n2) {
+        float v = part2[i];
+        for (int z = 1; z < nsl2; ++z) v += part2[(size_t)z * n2 + i];
+        out2[i] = v;
     }
 }
 
@@ -256,63 +380,42 @@ struct HeadArgs {
     bool use_tc;         // tcgen05 GEMMs for fc1 / fc2 (never in the emulator build)
 };
 
-#ifndef PGPD_EMU
-// C[M][N] = sum_k A(m,k) B(n,k) on the tensor cores; split-K partials go through `part` and are summed in a fixed order.
-// nsl_fixed > 0: exactly that many K slices (forward: the summation order must not depend on the batch size).
-inline void run_gemm_tc(tc::GemmOp A, tc::GemmOp Bo, int M, int N, int K, float* C, float* part, const float* mask,
-                        int nsl_fixed, cudaStream_t s) {
-    const int tiles = idiv_up(M, tc::GM_T) * idiv_up(N, tc::GM_T);
-    int nsl = nsl_fixed > 0 ? nsl_fixed : 1;
-    if (nsl_fixed <= 0)
-        while (tiles * nsl < 120 && K / (nsl * 2) >= tc::GM_KC && (size_t)(nsl * 2) * M * N <= HEAD_PART_ELEMS) nsl *= 2;
-    while (nsl > 1 && (size_t)nsl * M * N > HEAD_PART_ELEMS) nsl /= 2;
-    int kslice = idiv_up(idiv_up(K, nsl), tc::GM_KC) * tc::GM_KC;
-    nsl = idiv_up(K, kslice);                       // no empty slices
-    tc::GemmParams p{A, Bo, M, N, K, kslice, nsl > 1 ? part : C, mask};
-    tc::launch_gemm_tc(p, nsl, s);
-    if (nsl > 1) {
-        ProbPlain<true, true> f{nullptr, nullptr, C, part, M, N, K, 0, 0, 0, 0, kslice, mask ? EPI_MASK : EPI_NONE, nullptr, 0, mask};
-        launch(k_splitk_finish<true, true>, grid1d((size_t)M * N, 256), dim3(256), 0, s, f, nsl);
-    }
-}
-#endif
-
-// X -> w.out  (logits, or t9 + identity)
-inline void head_forward(const HeadArgs& a, HeadWs& w) {
+// X -> w.out (logits, or t9 + identity); user_out: STN: trans [B][9]; classifier: log-probs [B][k].  logp_keep: [B][k] kept for the
+// backward (classifier) or null.
+inline void head_forward(const HeadArgs& a, HeadWs& w, float* user_out, float* logp_keep) {
     const pgpd_head& h = *a.h;
     cudaStream_t s = a.stream;
     const int B = a.B;
-    // fc1: U1[b][j] = sum_i X[b][i] W1[j][i]
+    bool tcg = false;
 #ifndef PGPD_EMU
-    if (a.use_tc) {
-        cudaMemsetAsync(w.amax, 0, 4 * sizeof(unsigned), s);
-        launch(tc::k_absmax2, dim3(64, 2), dim3(256), 0, s, h.fc[0].w, (size_t)H1 * C3, h.fc[1].w, (size_t)H2 * H1, w.amax);
-        run_gemm_tc(tc::GemmOp{a.X, C3, 0, nullptr, tc::ACT_SCALE}, tc::GemmOp{h.fc[0].w, C3, 0, w.amax + 0, 1.f}, B, H1, C3,
-                    w.U1, w.part, nullptr, 8, s);
+    tcg = a.use_tc;
+#endif
+    const float limit = tcg ? TC_ACT_LIMIT : INFINITY;
+    int nsl = 0;
+    // fc1: U1[b][j] = sum_i X[b][i] W1[j][i]   (8 K-slices, whatever the batch)
+#ifndef PGPD_EMU
+    if (tcg) {
+        launch(tc::k_absmax2, dim3(HEAD_AMAX_BLOCKS, 2), dim3(256), 0, s, h.fc[0].w, (size_t)H1 * C3, h.fc[1].w, (size_t)H2 * H1, w.amax);
+        nsl = run_gemm_tc(tc::GemmOp{a.X, C3, 0, nullptr, 0, tc::ACT_SCALE}, tc::GemmOp{h.fc[0].w, C3, 0, w.amax, HEAD_AMAX_BLOCKS, 1.f},
+                          B, H1, C3, w.partA, 8, s);
     } else
 #endif
-    run_plain(ProbPlain<true, false>{a.X, h.fc[0].w, w.U1, w.part, B, H1, C3, (size_t)C3, 1, 1, (size_t)C3, 0, EPI_NONE, nullptr, 0, nullptr}, s, 8);
-    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H1, 32), dim3(1024), 0, s, (const float*)w.U1, B, H1, h.fc[0].b, h.bn[0], w.bn[0], w.Hm1);
-    else {
-        launch(k_bn_eval_affine, grid1d(H1, 128), dim3(128), 0, s, H1, h.fc[0].b, h.bn[0], w.bn[0]);
-        launch(k_bn_apply, grid1d((size_t)B * H1, 256), dim3(256), 0, s, (const float*)w.U1, (size_t)B * H1, H1, w.bn[0], w.Hm1);
-    }
+    nsl = run_plain(ProbPlain<true, false>{a.X, h.fc[0].w, w.partA, B, H1, C3, (size_t)C3, 1, 1, (size_t)C3, 0}, s, 8);
+    launch(k_bn_head_fwd, grid1d(H1, 32), dim3(1024), 0, s, (const float*)w.partA, nsl, B, H1, a.train ? 1 : 0, h.fc[0].b, h.bn[0], w.bn[0],
+           limit, w.U1, w.Hm1);
     // fc2
 #ifndef PGPD_EMU
-    if (a.use_tc)
-        run_gemm_tc(tc::GemmOp{w.Hm1, H1, 0, nullptr, tc::ACT_SCALE}, tc::GemmOp{h.fc[1].w, H1, 0, w.amax + 1, 1.f}, B, H2, H1,
-                    w.U2, w.part, nullptr, 4, s);
+    if (tcg)
+        nsl = run_gemm_tc(tc::GemmOp{w.Hm1, H1, 0, nullptr, 0, tc::ACT_SCALE},
+                          tc::GemmOp{h.fc[1].w, H1, 0, w.amax + HEAD_AMAX_BLOCKS, HEAD_AMAX_BLOCKS, 1.f}, B, H2, H1, w.partB, 4, s);
     else
 #endif
-    run_plain(ProbPlain<true, false>{w.Hm1, h.fc[1].w, w.U2, w.part, B, H2, H1, (size_t)H1, 1, 1, (size_t)H1, 0, EPI_NONE, nullptr, 0, nullptr}, s, 4);
-    if (a.train) launch(k_bn_batch_stats_apply, grid1d(H2, 32), dim3(1024), 0, s, (const float*)w.U2, B, H2, h.fc[1].b, h.bn[1], w.bn[1], w.Hm2);
-    else {
-        launch(k_bn_eval_affine, grid1d(H2, 128), dim3(128), 0, s, H2, h.fc[1].b, h.bn[1], w.bn[1]);
-        launch(k_bn_apply, grid1d((size_t)B * H2, 256), dim3(256), 0, s, (const float*)w.U2, (size_t)B * H2, H2, w.bn[1], w.Hm2);
-    }
-    // fc3 (+ bias, + identity for the T-Net)
-    run_plain(ProbPlain<true, false>{w.Hm2, h.fc[2].w, w.out, w.part, B, a.out, H2, (size_t)H2, 1, 1, (size_t)H2, 0, EPI_BIAS, h.fc[2].b,
-                                     a.is_stn ? 1 : 0, nullptr}, s, 4);
+    nsl = run_plain(ProbPlain<true, false>{w.Hm1, h.fc[1].w, w.partB, B, H2, H1, (size_t)H1, 1, 1, (size_t)H1, 0}, s, 4);
+    launch(k_bn_head_fwd, grid1d(H2, 32), dim3(1024), 0, s, (const float*)w.partB, nsl, B, H2, a.train ? 1 : 0, h.fc[1].b, h.bn[1], w.bn[1],
+           INFINITY, w.U2, w.Hm2);
+    // fc3 (+ bias, + identity for the T-Net, + log_softmax for the classifier)
+    launch(k_fc3_out, grid1d(B, 8), dim3(256), 0, s, (const float*)w.Hm2, h.fc[2].w, h.fc[2].b, B, a.out, a.is_stn ? 1 : 0, w.out,
+           a.is_stn ? user_out : (float*)nullptr, a.is_stn ? (float*)nullptr : logp_keep, a.is_stn ? (float*)nullptr : user_out);
 }
 
 // w.dO (gradient w.r.t. w.out) -> parameter gradients and dX [B][1024]
@@ -320,45 +423,56 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     const pgpd_head& h = *a.h;
     cudaStream_t s = a.stream;
     const int B = a.B, J3 = a.out;
-    // ---- fc3:  dW3[j][i] = sum_b dO[b][j] H2[b][i] ;  db3 = colsum(dO) ;  dz2 = (dO W3) masked by H2 > 0
-    run_plain(ProbPlain<false, true>{w.dO, w.Hm2, g.fc[2].dw, w.part, J3, H2, B, 1, (size_t)J3, (size_t)H2, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
-    launch(k_colsum, dim3(J3), dim3(256), 0, s, (const float*)w.dO, B, J3, g.fc[2].db);
-    run_plain(ProbPlain<true, true>{w.dO, h.fc[2].w, w.DZ2, w.part, B, H2, J3, (size_t)J3, 1, (size_t)H2, 1, 0, EPI_MASK, nullptr, 0, w.Hm2}, s);
     bool tcg = false;
 #ifndef PGPD_EMU
     tcg = a.use_tc;
 #endif
-    launch(k_bn_batch_bwd_apply, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta,
-           tcg ? w.amax + 3 : (unsigned*)nullptr);
+    unsigned* amax_du1 = w.amax + 2 * HEAD_AMAX_BLOCKS;        // [16] partial max |dU1| (512 channels / 32)
+    unsigned* amax_du2 = amax_du1 + 16;                        // [8 of 16]
+    // ---- fc3: dW3, db3, dz2
+    launch(k_fc3_bwd, dim3(J3 + idiv_up(B, 8)), dim3(256), 0, s, (const float*)w.dO, (const float*)w.Hm2, h.fc[2].w, B, J3,
+           g.fc[2].dw, g.fc[2].db, w.DZ2);
+    launch(k_bn_head_bwd, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta,
+           g.fc[1].db, tcg ? amax_du2 : (unsigned*)nullptr);
     // ---- fc2 (w.DZ2 now holds dU2):  dW2 = dU2^T Hm1,  dz1 = (dU2 W2) masked by Hm1 > 0
-    launch(k_fill, grid1d(H2, 128), dim3(128), 0, s, g.fc[1].db, (size_t)H2, 0.f);
+    int nslW = 0, nslZ = 0;
 #ifndef PGPD_EMU
     if (tcg) {
-        run_gemm_tc(tc::GemmOp{w.DZ2, H2, 1, w.amax + 3, 1.f}, tc::GemmOp{w.Hm1, H1, 1, nullptr, tc::ACT_SCALE}, H2, H1, B,
-                    g.fc[1].dw, w.part, nullptr, 0, s);
-        run_gemm_tc(tc::GemmOp{w.DZ2, H2, 0, w.amax + 3, 1.f}, tc::GemmOp{h.fc[1].w, H1, 1, w.amax + 1, 1.f}, B, H1, H2,
-                    w.DZ1, w.part, w.Hm1, 0, s);
+        nslW = run_gemm_tc(tc::GemmOp{w.DZ2, H2, 1, amax_du2, H2 / 32, 1.f}, tc::GemmOp{w.Hm1, H1, 1, nullptr, 0, tc::ACT_SCALE}, H2, H1, B,
+                           w.partA, 0, s);
+        nslZ = run_gemm_tc(tc::GemmOp{w.DZ2, H2, 0, amax_du2, H2 / 32, 1.f},
+                           tc::GemmOp{h.fc[1].w, H1, 1, w.amax + HEAD_AMAX_BLOCKS, HEAD_AMAX_BLOCKS, 1.f}, B, H1, H2, w.partB, 0, s);
     } else
 #endif
     {
-        run_plain(ProbPlain<false, true>{w.DZ2, w.Hm1, g.fc[1].dw, w.part, H2, H1, B, 1, (size_t)H2, (size_t)H1, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
-        run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.DZ1, w.part, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0, EPI_MASK, nullptr, 0, w.Hm1}, s);
+        nslW = run_plain(ProbPlain<false, true>{w.DZ2, w.Hm1, w.partA, H2, H1, B, 1, (size_t)H2, (size_t)H1, 1, 0}, s, 0);
+        nslZ = run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.partB, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0}, s, 0);
     }
-    launch(k_bn_batch_bwd_apply, grid1d(H1, 32), dim3(1024), 0, s, w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta,
-           tcg ? w.amax + 2 : (unsigned*)nullptr);
+    {
+        const int nbn = idiv_up(H1, 32);
+        const size_t nW = (size_t)H2 * H1;
+        launch(k_head_mid, dim3(nbn + (unsigned)((nW + 1023) / 1024)), dim3(1024), 0, s, nbn, (const float*)w.partB, nslZ, (const float*)w.Hm1,
+               w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta, g.fc[0].db, tcg ? amax_du1 : (unsigned*)nullptr,
+               (const float*)w.partA, nslW, nW, g.fc[1].dw);
+    }
     // ---- fc1 (w.DZ1 now holds dU1):  dW1 = dU1^T X,  dX = dU1 W1
-    launch(k_fill, grid1d(H1, 128), dim3(128), 0, s, g.fc[0].db, (size_t)H1, 0.f);
+    int nsl1 = 0, nslX = 0;
 #ifndef PGPD_EMU
     if (tcg) {
-        run_gemm_tc(tc::GemmOp{w.DZ1, H1, 1, w.amax + 2, 1.f}, tc::GemmOp{a.X, C3, 1, nullptr, tc::ACT_SCALE}, H1, C3, B,
-                    g.fc[0].dw, w.part, nullptr, 0, s);
-        run_gemm_tc(tc::GemmOp{w.DZ1, H1, 0, w.amax + 2, 1.f}, tc::GemmOp{h.fc[0].w, C3, 1, w.amax + 0, 1.f}, B, C3, H1,
-                    dX, w.part, nullptr, 0, s);
+        nsl1 = run_gemm_tc(tc::GemmOp{w.DZ1, H1, 1, amax_du1, H1 / 32, 1.f}, tc::GemmOp{a.X, C3, 1, nullptr, 0, tc::ACT_SCALE}, H1, C3, B,
+                           w.partA, 0, s);
+        nslX = run_gemm_tc(tc::GemmOp{w.DZ1, H1, 0, amax_du1, H1 / 32, 1.f}, tc::GemmOp{h.fc[0].w, C3, 1, w.amax, HEAD_AMAX_BLOCKS, 1.f}, B, C3, H1,
+                           w.partB, 0, s);
     } else
 #endif
     {
-        run_plain(ProbPlain<false, true>{w.DZ1, a.X, g.fc[0].dw, w.part, H1, C3, B, 1, (size_t)H1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
-        run_plain(ProbPlain<true, true>{w.DZ1, h.fc[0].w, dX, w.part, B, C3, H1, (size_t)H1, 1, (size_t)C3, 1, 0, EPI_NONE, nullptr, 0, nullptr}, s);
+        nsl1 = run_plain(ProbPlain<false, true>{w.DZ1, a.X, w.partA, H1, C3, B, 1, (size_t)H1, (size_t)C3, 1, 0}, s, 0);
+        nslX = run_plain(ProbPlain<true, true>{w.DZ1, h.fc[0].w, w.partB, B, C3, H1, (size_t)H1, 1, (size_t)C3, 1, 0}, s, 0);
+    }
+    {
+        const size_t n1 = (size_t)H1 * C3, n2 = (size_t)B * C3;
+        launch(k_finish2, dim3((unsigned)((n1 + 1023) / 1024 + (n2 + 1023) / 1024)), dim3(1024), 0, s, (const float*)w.partA, nsl1, n1,
+               g.fc[0].dw, (const float*)w.partB, nslX, n2, dX);
     }
 }
 

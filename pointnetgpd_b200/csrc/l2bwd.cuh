@@ -134,22 +134,31 @@ __global__ void __launch_bounds__(256) k_kb_ref(KbRefParams p) {
 }
 
 // per cloud: H_b (sum of its `rpc` partial rows, fixed order) -> G_b -> dW1 partial of the cloud and d trans.
-// grid = B, block = 192 (k, j).  xmom[b] = { X1 (3), X2 (3x3 row-major) } raw-coordinate moments (double).
-// The last block sums the per-cloud partials of dW1 in cloud order (deterministic) and zeroes the conv1 bias gradient.
-__global__ void k_kb_l1(const float* __restrict__ Hpart, int rpc, const double* __restrict__ xmom, const float* __restrict__ trans,
-                        const float* __restrict__ W1, BnState st1, const float* __restrict__ m1, const float* __restrict__ m2,
-                        float* __restrict__ dW1part, float* __restrict__ dtrans, unsigned* counter, float* __restrict__ dW1,
-                        float* __restrict__ db1) {
+// grid = B, block = 768 = 192 (k, j) x 4 lanes.  xmom[b] = { X1 (3), X2 (3x3 row-major) } raw-coordinate moments (double).
+// The last block sums the per-cloud partials of dW1 (4 lanes, clouds in order within a lane, lanes added in order:
+// deterministic) and zeroes the conv1 bias gradient.
+__global__ void __launch_bounds__(768) k_kb_l1(const float* __restrict__ Hpart, int rpc, const double* __restrict__ xmom,
+                        const float* __restrict__ trans, const float* __restrict__ W1, BnState st1, const float* __restrict__ m1,
+                        const float* __restrict__ m2, float* __restrict__ dW1part, float* __restrict__ dtrans, unsigned* counter,
+                        float* __restrict__ dW1, float* __restrict__ db1) {
     __shared__ float G[C1 * 3];
-    const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
+    __shared__ float hs[4][C1 * 3];
+    __shared__ double ds[4][C1 * 3];
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x, e = tid % 192, ln = tid / 192;
     float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (trans)
-        for (int e = 0; e < 9; ++e) T[e] = trans[(size_t)b * 9 + e];
+        for (int q = 0; q < 9; ++q) T[q] = trans[(size_t)b * 9 + q];
+    {
+        float h = 0.f;
+        const float* hp = Hpart + (size_t)b * rpc * (C1 * 3) + e;
+#pragma unroll 8
+        for (int r = ln; r < rpc; r += 4) h += hp[(size_t)r * (C1 * 3)];
+        hs[ln][e] = h;
+    }
+    __syncthreads();
     if (tid < C1 * 3) {
         const int k = tid / 3, j = tid % 3;
-        float h = 0.f;
-        const float* hp = Hpart + (size_t)b * rpc * (C1 * 3) + tid;
-        for (int r = 0; r < rpc; ++r) h += hp[(size_t)r * (C1 * 3)];
+        const float h = ((hs[0][tid] + hs[1][tid]) + hs[2][tid]) + hs[3][tid];
         const double* mo = xmom + (size_t)b * 12;
         const double w0 = W1[k * 3 + 0], w1 = W1[k * 3 + 1], w2 = W1[k * 3 + 2];
         // V[k][j'] = sum_i W1[k][i] T[j'][i]
@@ -174,12 +183,14 @@ __global__ void k_kb_l1(const float* __restrict__ Hpart, int rpc, const double* 
         dtrans[(size_t)b * 9 + tid] = s;
     }
     if (!last_block_done(counter, gridDim.x)) return;
-    if (tid < C1 * 3) {
+    {
         double s = 0.0;
-#pragma unroll 4
-        for (unsigned bb = 0; bb < gridDim.x; ++bb) s += (double)dW1part[(size_t)bb * (C1 * 3) + tid];
-        dW1[tid] = (float)s;
+#pragma unroll 8
+        for (unsigned bb = (unsigned)ln; bb < gridDim.x; bb += 4) s += (double)dW1part[(size_t)bb * (C1 * 3) + e];
+        ds[ln][e] = s;
     }
+    __syncthreads();
+    if (tid < C1 * 3) dW1[tid] = (float)(((ds[0][tid] + ds[1][tid]) + ds[2][tid]) + ds[3][tid]);
     if (tid < C1 && db1) db1[tid] = 0.f;          // bias feeding a train-mode BatchNorm: gradient is identically zero
 }
 

@@ -100,8 +100,7 @@ static bool want_tc(int flags) {
 #endif
 }
 
-// tcgen05 GEMMs in the FC heads: PGPD_TC_MASK bit 6 (default on)
-static bool head_tc(int flags) { return want_tc(flags) && (tc_mask() & 64); }
+static bool head_tc(int flags) { return want_tc(flags); }
 
 static void run_tower_fwd(const TowerArgs& a, TowerWs& w, float* pooled, int) { tower_forward(a, w, pooled); }
 
@@ -194,20 +193,15 @@ int pgpd_forward(int what, const pgpd_model* m, const float* x, int B, int N, in
     TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, train, save, s, want_tc(flags)};
     run_tower_fwd(ta, w.stn_t, w.g_stn, flags);
     HeadArgs ha{&m->stn_head, w.g_stn, B, 9, train, true, s, head_tc(flags)};
-    head_forward(ha, w.stn_h);
-    cudaMemcpyAsync(trans, w.stn_h.out, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    head_forward(ha, w.stn_h, trans, nullptr);
     if (what >= PGPD_FEAT) {
-        // ---- transform + trunk tower (pointnet.py:140-149)
+        // ---- transform + trunk tower (pointnet.py:140-149); the pooled feature goes straight to the caller for PGPD_FEAT
         TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, train, save, s, want_tc(flags)};
-        run_tower_fwd(tb, w.trunk_t, w.G, flags);
-        if (what == PGPD_FEAT) {
-            cudaMemcpyAsync(out, w.G, (size_t)B * C3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-        } else {
+        run_tower_fwd(tb, w.trunk_t, what == PGPD_FEAT ? out : w.G, flags);
+        if (what == PGPD_CLS) {
             // ---- classifier head (pointnet.py:191-194)
             HeadArgs hb{&m->cls_head, w.G, B, k, train, false, s, head_tc(flags)};
-            head_forward(hb, w.cls_h);
-            launch(k_log_softmax, grid1d(B, 128), dim3(128), 0, s, (const float*)w.cls_h.out, B, k, w.logp);
-            cudaMemcpyAsync(out, w.logp, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToDevice, s);
+            head_forward(hb, w.cls_h, out, w.logp);
         }
     }
     return check_cuda("pgpd_forward");
@@ -292,6 +286,7 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
     if (!t || !g || !x || !dpooled) return fail(PGPD_E_ARG, "null pointer");
     for (int i = 0; i < 3; ++i) if ((uintptr_t)t->conv[i].w & 15) return fail(PGPD_E_ARG, "conv weight pointers must be 16-byte aligned");
     if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
+    if ((long long)B * N > 0x7fffffffLL / 128) return fail(PGPD_E_ARG, "B*N too large for this build (B*N*128 must fit in int32)");
     if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
     if (trans && !dtrans_out) return fail(PGPD_E_ARG, "dtrans_out is null but trans is given");
     flags |= PGPD_F_SAVE;

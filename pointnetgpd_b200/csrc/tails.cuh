@@ -18,7 +18,7 @@ namespace pgpd {
 
 constexpr int PRE_THREADS = 256;
 constexpr int A1_CHUNK = 64;        // points per staging chunk of k_a1
-constexpr int A1_CPB = 4;           // chunks per block: one partial row of the a1 sums per 256 points
+constexpr int A1_CPB = 16;          // chunks per block: one partial row of the a1 sums per 1024 points
 
 // ================================================================================================
 // F1: k_tower_pre -- everything a tower forward needs before its first per-point kernel
@@ -204,11 +204,15 @@ __global__ void __launch_bounds__(PRE_THREADS) k_tower_pre(PreParams p) {
 
 // ================================================================================================
 // k_a1: a1 = relu(scale1 * (W1 T^T x) + shift1), stored [M][64]  (+ train: sum of a1 -> S1a, mean(u2) = W2 mean(a1))
-// grid = (ceil(N / 256), clouds), block = 256 threads = 64 channels x 4 point slots; A1_CPB chunks of 64 points per block.
-// Train mode: every block writes one partial row of the a1 sums; the LAST block sums the rows (fixed order, double) and
-// propagates the mean through conv2: mean(u2) = W2 mean(a1) -- the centre of layer 2's sum of squares.
+// grid = (ceil(N / 1024), clouds), block = 1024 threads = 64 channels x 16 point slots; chunks of 64 points are staged
+// (transformed) in shared memory.  Train mode: every block writes one partial row of the a1 sums; the LAST block sums the
+// rows (64 columns x 16 lanes, fixed order, double) and propagates the mean through conv2: mean(u2) = W2 mean(a1) -- the
+// centre of layer 2's sum of squares.
 // `limit`: activations above it (or NaN) flag the cloud in bad[] (tensor-core path: the fp16 operand range).
+// Rule for every tail in this file: a serial loop over partial rows is a chain of L2 round trips (~0.4 us each), so rows are
+// spread over many lanes and the loops are unrolled 8-fold (8 loads in flight per thread).
 // ================================================================================================
+constexpr int A1_THREADS = 1024;
 struct A1Params {
     const float* x; const float* trans; int B, N;
     const float* W1; BnState st; float* A1;
@@ -217,11 +221,11 @@ struct A1Params {
     unsigned* bad; float limit;
 };
 
-__global__ void __launch_bounds__(256) k_a1(A1Params p) {
+__global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
     __shared__ float xs[3][A1_CHUNK];
-    __shared__ double sh[256];
+    __shared__ double sh[A1_THREADS];
     __shared__ double vs[C1];
-    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;
+    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;      // q = 0..15
     const int b = (int)blockIdx.y;
     const float w0 = p.W1[k * 3 + 0], w1 = p.W1[k * 3 + 1], w2 = p.W1[k * 3 + 2];
     const float sc = p.st.scale[k], sh_ = p.st.shift[k];
@@ -249,13 +253,15 @@ __global__ void __launch_bounds__(256) k_a1(A1Params p) {
         }
         __syncthreads();
         float* out = p.A1 + ((size_t)b * p.N + n0) * C1 + k;
-#pragma unroll 4
-        for (int pp = q; pp < nv; pp += 4) {
-            const float u = w0 * xs[0][pp] + w1 * xs[1][pp] + w2 * xs[2][pp];
-            const float a = relu_nan(sc * u + sh_);
-            flag = flag || !(a <= p.limit);
-            out[(size_t)pp * C1] = a;
-            acc += a;
+#pragma unroll
+        for (int pp = q; pp < A1_CHUNK; pp += 16) {
+            if (pp < nv) {
+                const float u = w0 * xs[0][pp] + w1 * xs[1][pp] + w2 * xs[2][pp];
+                const float a = relu_nan(sc * u + sh_);
+                flag = flag || !(a <= p.limit);
+                out[(size_t)pp * C1] = a;
+                acc += a;
+            }
         }
     }
     if (flag) p.bad[b] = 1u;
@@ -263,23 +269,31 @@ __global__ void __launch_bounds__(256) k_a1(A1Params p) {
     const unsigned nblk = gridDim.x * gridDim.y;
     sh[tid] = (double)acc;
     __syncthreads();
-    if (tid < 64) p.part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C1 + tid] = sh[tid] + sh[tid + 64] + sh[tid + 128] + sh[tid + 192];
+    if (tid < 64) {
+        double t = 0.0;
+#pragma unroll
+        for (int l = 0; l < 16; ++l) t += sh[l * 64 + tid];
+        p.part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C1 + tid] = t;
+    }
     if (!last_block_done(p.counter, nblk)) return;
-    // ---- last block: S1a = sum of the partial rows (64 columns x 4 lanes), mean(u2) = W2 S1a / count
+    // ---- last block: S1a = sum of the partial rows (64 columns x 16 lanes), mean(u2) = W2 S1a / count
     {
         double s = 0.0;
-#pragma unroll 4
-        for (unsigned r = (unsigned)q; r < nblk; r += 4) s += p.part[(size_t)r * C1 + k];
+#pragma unroll 8
+        for (unsigned r = (unsigned)q; r < nblk; r += 16) s += p.part[(size_t)r * C1 + k];
         sh[tid] = s;
         __syncthreads();
         if (tid < 64) {
-            const double t = ((sh[tid] + sh[tid + 64]) + sh[tid + 128]) + sh[tid + 192];
+            double t = 0.0;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) t += sh[l * 64 + tid];
             vs[tid] = t;
             if (p.S1a) p.S1a[tid] = t;
         }
         __syncthreads();
         if (tid < C2) {
             double s2 = 0.0;
+#pragma unroll 8
             for (int kk = 0; kk < C1; ++kk) s2 += (double)p.W2[(size_t)tid * C1 + kk] * vs[kk];
             p.mean_u2[tid] = (float)(s2 / p.count);
         }
@@ -293,11 +307,11 @@ __global__ void __launch_bounds__(256) k_a1(A1Params p) {
 //   then the sum of a2 = relu(bn2(u2)): either from the caller's partial rows (CUDA-core path: k_a2_sum over all points,
 //                the exact mean) or, tensor-core path, a PILOT estimate from `nsample` points spread over the batch
 //                (each block sums its share; the layer-3 kernel accumulates the exact sum while it stages the tiles);
-//   the last block: mean(u3) = W3 mean(a2) -> st3.mean (the centre of layer 3's sum of squares), S1, and (tensor-core path)
-//                the centre in accumulator units mu_s = mean / inv.
-// grid = TL2_BLOCKS, block = 256.
+//   the last block: S1 = the (pilot) sum of a2; CUDA-core path only (mean_u3 != null): mean(u3) = W3 S1 / nsample, the centre
+//                of layer 3's sum of squares (the tensor-core layer-3 kernel forms its centres itself from S1).
+// grid = TL2_BLOCKS, block = 1024 = 128 channels x 8 lanes.
 // ================================================================================================
-constexpr int TL2_BLOCKS = 16;
+constexpr int TL2_BLOCKS = 32;
 constexpr int TL2_SAMPLE = 4096;              // points of the pilot estimate of mean(a2)
 struct TailL2Params {
     const float* css; int n_css;              // [n_css][128] partial sums of (u2 - mean)^2
@@ -307,26 +321,30 @@ struct TailL2Params {
     const double* a2part; int n_a2part;       // or: exact partial rows [n][128] (nsample = number of points they cover)
     double* part;                             // [TL2_BLOCKS][128] scratch
     unsigned* counter;
-    const float* W3; float* mean_u3; double* S1; const float* inv3; float* mu_s;   // mu_s may be null
+    double* S1;                               // [128] sum of a2 over the nsample points
+    const float* W3; float* mean_u3;          // CUDA-core path: [1024] mean of u3; null on the tensor-core path
 };
 
-__global__ void __launch_bounds__(256) k_tail_l2(TailL2Params p) {
-    __shared__ double sh[256];
+__global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
+    __shared__ double sh[1024];
     __shared__ float s_sc[C2], s_sf[C2];
     __shared__ double vs[C2];
-    const int tid = (int)threadIdx.x, c = tid & 127, q = tid >> 7;
+    const int tid = (int)threadIdx.x, c = tid & 127, q = tid >> 7;      // q = 0..7
     // ---- BatchNorm2 statistics (every block, identically)
     if (p.bn_done) {
         if (tid < C2) { s_sc[tid] = p.st2.scale[tid]; s_sf[tid] = p.st2.shift[tid]; }
         __syncthreads();
     } else {
         double s = 0.0;
-#pragma unroll 4
-        for (int r = q; r < p.n_css; r += 2) s += (double)p.css[(size_t)r * C2 + c];
+#pragma unroll 8
+        for (int r = q; r < p.n_css; r += 8) s += (double)p.css[(size_t)r * C2 + c];
         sh[tid] = s;
         __syncthreads();
         if (tid < C2) {
-            const double var0 = (sh[tid] + sh[tid + C2]) / p.count;
+            double t = 0.0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) t += sh[l * C2 + tid];
+            const double var0 = t / p.count;
             const double var = var0 < 0.0 ? 0.0 : var0;
             const float rstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
             const float sc = p.bn2.gamma[tid] * rstd;
@@ -340,45 +358,52 @@ __global__ void __launch_bounds__(256) k_tail_l2(TailL2Params p) {
     // ---- this block's share of the sum of a2
     double acc = 0.0;
     if (p.a2part) {
-        for (int r = (int)blockIdx.x * 2 + q; r < p.n_a2part; r += 2 * (int)gridDim.x) acc += p.a2part[(size_t)r * C2 + c];
+#pragma unroll 4
+        for (int r = (int)blockIdx.x * 8 + q; r < p.n_a2part; r += 8 * (int)gridDim.x) acc += p.a2part[(size_t)r * C2 + c];
     } else {
         const float sc = s_sc[c], sf = s_sf[c];
-        float f0 = 0.f, f1 = 0.f;
-        const size_t stride = (size_t)gridDim.x * 2;
+        float f = 0.f;
+        const size_t stride = (size_t)gridDim.x * 8;
         const size_t rs = p.pstride * C2;
-        size_t i = (size_t)blockIdx.x * 2 + q;
-        for (; i + stride < p.nsample; i += 2 * stride) {
-            const float y0 = p.Y2[i * rs + c], y1 = p.Y2[(i + stride) * rs + c];
-            f0 += relu_nan(sc * y0 + sf); f1 += relu_nan(sc * y1 + sf);
-        }
-        if (i < p.nsample) f0 += relu_nan(sc * p.Y2[i * rs + c] + sf);
-        acc = (double)f0 + (double)f1;
+#pragma unroll 8
+        for (size_t i = (size_t)blockIdx.x * 8 + q; i < p.nsample; i += stride) f += relu_nan(sc * p.Y2[i * rs + c] + sf);
+        acc = (double)f;
     }
     sh[tid] = acc;
     __syncthreads();
-    if (tid < C2) p.part[(size_t)blockIdx.x * C2 + tid] = sh[tid] + sh[tid + C2];
-    if (!last_block_done(p.counter, gridDim.x)) return;
-    // ---- last block: total, mean(u3) = W3 S / nsample  (one warp per row of W3: coalesced, fixed shuffle tree)
     if (tid < C2) {
         double t = 0.0;
-        for (unsigned r = 0; r < gridDim.x; ++r) t += p.part[(size_t)r * C2 + tid];
-        vs[tid] = t;
-        if (p.S1) p.S1[tid] = t;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t += sh[l * C2 + tid];
+        p.part[(size_t)blockIdx.x * C2 + tid] = t;
     }
-    __syncthreads();
+    if (!last_block_done(p.counter, gridDim.x)) return;
+    // ---- last block: total
+    {
+        double s = 0.0;
+        for (unsigned r = (unsigned)q; r < gridDim.x; r += 8) s += p.part[(size_t)r * C2 + c];
+        sh[tid] = s;
+        __syncthreads();
+        if (tid < C2) {
+            double t = 0.0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) t += sh[l * C2 + tid];
+            vs[tid] = t;
+            if (p.S1) p.S1[tid] = t;
+        }
+        __syncthreads();
+    }
+    if (!p.mean_u3) return;
+    // CUDA-core path: mean(u3) = W3 S / nsample  (one warp per row of W3: coalesced, fixed shuffle tree)
     const int warp = tid >> 5, lane = tid & 31;
     const double inv_n = 1.0 / (double)p.nsample;
-    for (int r = warp; r < C3; r += 8) {
+    for (int r = warp; r < C3; r += 32) {
         double s = 0.0;
 #pragma unroll
         for (int kk = lane; kk < C2; kk += 32) s += (double)p.W3[(size_t)r * C2 + kk] * vs[kk];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            const float m = (float)(s * inv_n);
-            p.mean_u3[r] = m;
-            if (p.mu_s) p.mu_s[r] = m / p.inv3[r];
-        }
+        if (lane == 0) p.mean_u3[r] = (float)(s * inv_n);
     }
 }
 
@@ -391,9 +416,10 @@ __global__ void __launch_bounds__(256) k_tail_l2(TailL2Params p) {
 //   both:  decode the (max, arg-max) keys and apply BatchNorm3 (+ReLU) to the pooled [B][1024] values;
 //          a cloud flagged in bad[] (NaN / out-of-range activation) or a pooled value outside the fp16 operand range of
 //          the tensor-core heads gets NaN instead of a silently clamped number.
-// grid = 1024 / TL3_CH, block = 256 = TL3_CH channels x 16 lanes.
+// grid = 1024 / TL3_CH, block = 1024 = TL3_CH channels x 64 lanes.
 // ================================================================================================
 constexpr int TL3_CH = 16;
+constexpr int TL3_LANES = 64;
 struct TailL3Params {
     int B; int relu_last; int train;
     const unsigned long long* keys; const float* sgn; BnState st3;
@@ -406,49 +432,60 @@ struct TailL3Params {
     double* S1;                               // [128] exact sum of a2 (written by block 0 when s1part != null)
 };
 
-__global__ void __launch_bounds__(256) k_tail_l3(TailL3Params p) {
-    __shared__ double sh[16][TL3_CH + 1];
+__global__ void __launch_bounds__(1024) k_tail_l3(TailL3Params p) {
+    __shared__ double sh[TL3_LANES][TL3_CH + 1];
     __shared__ double vs[C2];
     __shared__ float s_sc[TL3_CH], s_sf[TL3_CH];
-    const int tid = (int)threadIdx.x, cx = tid & (TL3_CH - 1), ln = tid >> 4;
+    const int tid = (int)threadIdx.x, cx = tid & (TL3_CH - 1), ln = tid >> 4;      // ln = 0..63
     const int c0 = (int)blockIdx.x * TL3_CH, c = c0 + cx;
     if (p.train) {
         double mean_exact = 0.0;
         const bool pilot = p.s1part != nullptr;
         if (pilot) {
-            // exact sum of a2: the rows are few (one per CTA of the GEMM kernel); every block repeats the same sums
-            if (tid < C2) {
+            // exact sum of a2: one partial row per CTA of the GEMM kernel; every block repeats the same sums
+            // (128 columns x 8 lanes, lanes added in order)
+            {
+                const int k = tid & 127, l8 = tid >> 7;
                 double t = 0.0;
-#pragma unroll 4
-                for (int r = 0; r < p.n_s1; ++r) t += (double)p.s1part[(size_t)r * C2 + tid];
+#pragma unroll 8
+                for (int r = l8; r < p.n_s1; r += 8) t += (double)p.s1part[(size_t)r * C2 + k];
+                double* shf = &sh[0][0];
+                shf[l8 * C2 + k] = t;              // 1024 doubles fit: sh is 64 x 17
+            }
+            __syncthreads();
+            if (tid < C2) {
+                const double* shf = &sh[0][0];
+                double t = 0.0;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) t += shf[l * C2 + tid];
                 t *= p.s1scale;
                 vs[tid] = t;
                 if (blockIdx.x == 0 && p.S1) p.S1[tid] = t;
             }
             __syncthreads();
-            // mean(u3)[c] = W3[c] . S / count : 16 lanes x 8 k each, lanes added in order
+            // mean(u3)[c] = W3[c] . S / count : 64 lanes x 2 k each, lanes added in order
             double s = 0.0;
 #pragma unroll
-            for (int kk = ln * 8; kk < ln * 8 + 8; ++kk) s += (double)p.W3[(size_t)c * C2 + kk] * vs[kk];
+            for (int kk = ln * 2; kk < ln * 2 + 2; ++kk) s += (double)p.W3[(size_t)c * C2 + kk] * vs[kk];
             sh[ln][cx] = s;
             __syncthreads();
             if (ln == 0) {
                 double t = 0.0;
-#pragma unroll
-                for (int l2 = 0; l2 < 16; ++l2) t += sh[l2][cx];
+#pragma unroll 8
+                for (int l2 = 0; l2 < TL3_LANES; ++l2) t += sh[l2][cx];
                 mean_exact = t / p.count;
             }
             __syncthreads();
         }
         double s = 0.0;
-#pragma unroll 4
-        for (int r = ln; r < p.n_css; r += 16) s += (double)p.css[(size_t)r * C3 + c];
+#pragma unroll 8
+        for (int r = ln; r < p.n_css; r += TL3_LANES) s += (double)p.css[(size_t)r * C3 + c];
         sh[ln][cx] = s;
         __syncthreads();
         if (ln == 0) {
             double t = 0.0;
-#pragma unroll
-            for (int l2 = 0; l2 < 16; ++l2) t += sh[l2][cx];
+#pragma unroll 8
+            for (int l2 = 0; l2 < TL3_LANES; ++l2) t += sh[l2][cx];
             const double centre = (double)p.st3.mean[c];         // what the GEMM kernel centred its squares on
             double var = t / p.count, mu = centre;
             if (pilot) { mu = mean_exact; const double d = mu - centre; var -= d * d; }
@@ -464,7 +501,8 @@ __global__ void __launch_bounds__(256) k_tail_l3(TailL3Params p) {
     const float sc = s_sc[cx], sf = s_sf[cx], sg = p.sgn[c];
     const bool bad_all = p.bad[p.B] != 0u;
     const float qnan = __uint_as_float(0x7FC00000u);
-    for (int b = ln; b < p.B; b += 16) {
+#pragma unroll 4
+    for (int b = ln; b < p.B; b += TL3_LANES) {
         const size_t i = (size_t)b * C3 + c;
         const unsigned long long key = p.keys[i];
         const float u = sg * ord_decode((unsigned)(key >> 32));
@@ -482,120 +520,170 @@ __global__ void __launch_bounds__(256) k_tail_l3(TailL3Params p) {
 // ================================================================================================
 
 // B2: k_q_uvec -- after k_pool_bwd:  Q = W3^T diag(d) W3 (128 x 128),  uvec = W3^T e,  and (tensor-core path) the hi/lo
-// operand image of Q for the pass-A kernel.  grid = 32 blocks x 4 rows of Q, block = 128 threads (column j).
-// Sums over the 1024 channels run in a fixed order (two interleaved chains).
+// operand image of Q for the pass-A kernel.  grid = 32 blocks x 4 rows of Q, block = 1024 = 128 columns j x 8 lanes over the
+// 1024 channels (128 channels per lane, summed in order; the 8 lanes are added in lane order).
 struct QuParams {
     const float* W3; const float* dvec; const float* evec;
     float* Q; float* uvec;
     void* qimg; float* inv_s; int act_shift;      // qimg == null: no image (CUDA-core path)
 };
 
-__global__ void __launch_bounds__(128) k_q_uvec(QuParams p) {
-    __shared__ float s_wd[64][4];
-    __shared__ double s_red[4][128];
+__global__ void __launch_bounds__(1024) k_q_uvec(QuParams p) {
+    __shared__ float s_q[8][4][128];
+    __shared__ double s_u[4][32];              // [row][warp]: per-warp sums of the uvec products (fixed shuffle tree)
     __shared__ float s_mx[4][128];
-    const int j = (int)threadIdx.x, i0 = (int)blockIdx.x * 4;
-    float acc[4][2];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+    const int tid = (int)threadIdx.x, j = tid & 127, ln = tid >> 7, i0 = (int)blockIdx.x * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     double ue[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int cb = 0; cb < C3; cb += 64) {
-        __syncthreads();
-        for (int t = j; t < 64 * 4; t += 128) {
-            const int cc = t >> 2, r = t & 3;
-            s_wd[cc][r] = p.W3[(size_t)(cb + cc) * C2 + i0 + r] * p.dvec[cb + cc];
-        }
-        __syncthreads();
+    const int cbeg = ln * 128;
 #pragma unroll 8
-        for (int cc = 0; cc < 64; ++cc) {
-            const float w = p.W3[(size_t)(cb + cc) * C2 + j];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r][cc & 1] = fmaf(s_wd[cc][r], w, acc[r][cc & 1]);
-        }
+    for (int c = cbeg; c < cbeg + 128; ++c) {
+        const float w = p.W3[(size_t)c * C2 + j];
+        const float4 wi = *reinterpret_cast<const float4*>(p.W3 + (size_t)c * C2 + i0);    // same address for the whole block: broadcast
+        const float d = p.dvec[c];
+        acc[0] = fmaf(wi.x * d, w, acc[0]); acc[1] = fmaf(wi.y * d, w, acc[1]);
+        acc[2] = fmaf(wi.z * d, w, acc[2]); acc[3] = fmaf(wi.w * d, w, acc[3]);
     }
-    // uvec rows i0..i0+3: thread j covers channels c = j, j+128, ...
-    for (int c = j; c < C3; c += 128) {
+    // uvec rows i0..i0+3: the same 128 channels, split over the 128 "columns": thread (ln, j) covers channel c = ln*128 + j
+    {
+        const int c = cbeg + j;
         const double e = (double)p.evec[c];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) ue[r] += (double)p.W3[(size_t)c * C2 + i0 + r] * e;
+        const float4 wi = *reinterpret_cast<const float4*>(p.W3 + (size_t)c * C2 + i0);
+        ue[0] = (double)wi.x * e; ue[1] = (double)wi.y * e; ue[2] = (double)wi.z * e; ue[3] = (double)wi.w * e;
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) s_red[r][j] = ue[r];
-    float q[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        q[r] = acc[r][0] + acc[r][1];
-        p.Q[(size_t)(i0 + r) * C2 + j] = q[r];
-        s_mx[r][j] = fabsf(q[r]);
+        s_q[ln][r][j] = acc[r];
+        double u = ue[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+        if ((tid & 31) == 0) s_u[r][tid >> 5] = u;
     }
     __syncthreads();
-    if (j < 4) {
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ln == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float t = s_q[0][r][j];
+#pragma unroll
+            for (int l = 1; l < 8; ++l) t += s_q[l][r][j];
+            q[r] = t;
+            p.Q[(size_t)(i0 + r) * C2 + j] = t;
+            s_mx[r][j] = fabsf(t);
+        }
+    } else if (ln == 1 && j < 4) {
+        // uvec[i0 + j] = sum of the 32 warp sums, fixed order
         double t = 0.0;
-        for (int l = 0; l < 128; ++l) t += s_red[j][l];
+        for (int wv = 0; wv < 32; ++wv) t += s_u[j][wv];
         p.uvec[i0 + j] = (float)t;
     }
 #ifndef PGPD_EMU
     if (p.qimg) {
+        __syncthreads();
         for (int st = 64; st > 0; st >>= 1) {
-            if (j < st) {
+            if (ln == 0 && j < st) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) s_mx[r][j] = fmaxf(s_mx[r][j], s_mx[r][j + st]);
             }
             __syncthreads();
         }
+        if (ln == 0) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int e = tc::prepack_elem(q[r], s_mx[r][0], i0 + r, j, (__half*)p.qimg, 0);
-            if (j == 0) p.inv_s[i0 + r] = ldexpf(1.f, -(e + p.act_shift));
+            for (int r = 0; r < 4; ++r) {
+                const int e = tc::prepack_elem(q[r], s_mx[r][0], i0 + r, j, (__half*)p.qimg, 0);
+                if (j == 0) p.inv_s[i0 + r] = ldexpf(1.f, -(e + p.act_shift));
+            }
         }
     }
 #endif
 }
 
-// T5: k_tail_ka -- after pass A of the backward (d a2 -> dz2):
-//   all blocks: column slices of the Gram partial rows -> g2 (tensor-core path: the hi.hi and hi.lo accumulators, 2 x 128 x 128;
-//               CUDA-core path: the plain Gram matrix, directly into `gram`);
-//   last block: Gram = (hh + hl + hl^T) / 256 (tensor-core path); BatchNorm2-backward sums -> dgamma2, dbeta2, m1, m2;
-//               the 64 x 64 / 64-vector precompute of the fused layer-2/1 pass (K, cvec; l2bwd.cuh); and (tensor-core path)
-//               the per-channel scale of dz2 and the two A-operand images of that pass (tc_kb.cuh).
-// grid = gcols / 256, block = 256.
+// T5: k_tail_ka -- after pass A of the backward (d a2 -> dz2).  Roles by block (block = 1024 threads):
+//   [0, n_gram): column slices (256 columns x 4 lanes) of the Gram partial rows -> g2 (tensor-core path: the hi.hi and hi.lo
+//               accumulators, 2 x 128 x 128; CUDA-core path: the plain Gram matrix, directly into `gram`);
+//   [n_gram, +8): BatchNorm2-backward partial rows (sum dz, sum dz*yhat): 32 columns x 32 lanes each -> bnsum[256];
+//   [.., +4) (tensor-core path): per-channel max |dz2| from the kernel's partial maxima: 32 columns x 32 lanes -> pmx[128];
+//   last block: Gram = (hh + hl + hl^T) / 256 (tensor-core path); dgamma2, dbeta2, m1, m2; the 64 x 64 / 64-vector
+//               precompute of the fused layer-2/1 pass (K, cvec; l2bwd.cuh); and (tensor-core path) the per-channel scale of
+//               dz2 and the two A-operand images of that pass (tc_kb.cuh).
 struct TailKaParams {
     const float* gpart; int n_g; int gcols;       // [n_g][gcols] partial rows; gcols = 16384 (plain) or 32768 (hh, hl)
     float* g2;                                    // [gcols] reduced (scratch when sym)
     float* gram; int sym;                         // [128*128]
     const float* bnpart; int n_bn; double count;  // [n_bn][2][128] partial (sum dz, sum dz*yhat)
+    double* bnsum;                                // [256] scratch
     float* dgamma; float* dbeta; float* m1; float* m2;
     const float* W2; BnState st2; float* Kmat; float* cvec;
     unsigned* counter;
     // tensor-core path only
-    const float* pmax; int n_pm; float* esc; float* einv;
+    const float* pmax; int n_pm; float* pmx;      // [n_pm][2][128] partial maxima; pmx [128] scratch
+    float* esc; float* einv;
     void* img1; void* img2; float* ginv; float act_scale;
 };
 
-__global__ void __launch_bounds__(256) k_tail_ka(TailKaParams p) {
+__global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
+    __shared__ double sh[32][33];
+    __shared__ float s_w2[C2 * C1];               // 32 KB: conv2.weight staged for the last block
     __shared__ double sd[C2], se[C2];
     __shared__ float s_m1[C2], s_m2[C2], s_einv[C2];
     const int tid = (int)threadIdx.x;
-    {
-        const int col = (int)blockIdx.x * 256 + tid;
+    const int n_gram = p.gcols / 256;
+    int blk = (int)blockIdx.x;
+    if (blk < n_gram) {
+        const int cl = tid & 255, ln = tid >> 8;          // 4 lanes
+        const int col = blk * 256 + cl;
         double s = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < p.n_g; ++r) s += (double)p.gpart[(size_t)r * p.gcols + col];
-        (p.sym ? p.g2 : p.gram)[col] = (float)s;
+#pragma unroll 8
+        for (int r = ln; r < p.n_g; r += 4) s += (double)p.gpart[(size_t)r * p.gcols + col];
+        double* shf = &sh[0][0];                          // 1024 doubles
+        shf[ln * 256 + cl] = s;
+        __syncthreads();
+        if (ln == 0) {
+            const double t = ((shf[cl] + shf[256 + cl]) + shf[512 + cl]) + shf[768 + cl];
+            (p.sym ? p.g2 : p.gram)[col] = (float)t;
+        }
+    } else if (blk < n_gram + 8) {
+        const int cx = tid & 31, ry = tid >> 5;
+        const int col = (blk - n_gram) * 32 + cx;         // 0..255 of [2][128]
+        double s = 0.0;
+#pragma unroll 8
+        for (int r = ry; r < p.n_bn; r += 32) s += (double)p.bnpart[(size_t)r * 2 * C2 + col];
+        sh[ry][cx] = s;
+        __syncthreads();
+        if (ry == 0) {
+            double t = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) t += sh[q][cx];
+            p.bnsum[col] = t;
+        }
+    } else {
+        const int cx = tid & 31, ry = tid >> 5;
+        const int col = (blk - n_gram - 8) * 32 + cx;     // 0..127
+        float mx = 0.f;
+#pragma unroll 8
+        for (int r = ry; r < p.n_pm; r += 32) mx = fmaxf(mx, p.pmax[(size_t)r * 2 * C2 + col]);
+        float* shf = reinterpret_cast<float*>(&sh[0][0]);
+        shf[ry * 32 + cx] = mx;
+        __syncthreads();
+        if (ry == 0) {
+#pragma unroll 8
+            for (int q = 1; q < 32; ++q) mx = fmaxf(mx, shf[q * 32 + cx]);
+            p.pmx[col] = mx;
+        }
     }
     if (!last_block_done(p.counter, gridDim.x)) return;
+    // ================================ last block ================================
+    for (int i = tid; i < C2 * C1; i += 1024) s_w2[i] = p.W2[i];
     if (p.sym) {
         const float sc = 1.0f / (p.act_scale * p.act_scale);
-        for (int i = tid; i < C2 * C2; i += 256) {
+#pragma unroll 4
+        for (int i = tid; i < C2 * C2; i += 1024) {
             const int m = i >> 7, n = i & 127;
             p.gram[i] = (p.g2[i] + p.g2[C2 * C2 + i] + p.g2[C2 * C2 + n * C2 + m]) * sc;
         }
     }
-    // ---- BatchNorm2 backward sums: thread = column of [2][128]
-    {
-        double s = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < p.n_bn; ++r) s += (double)p.bnpart[(size_t)r * 2 * C2 + tid];
+    if (tid < 2 * C2) {
+        const double s = p.bnsum[tid];
         if (tid < C2) { p.dbeta[tid] = (float)s; s_m1[tid] = (float)(s / p.count); p.m1[tid] = s_m1[tid]; }
         else { p.dgamma[tid - C2] = (float)s; s_m2[tid - C2] = (float)(s / p.count); p.m2[tid - C2] = s_m2[tid - C2]; }
     }
@@ -607,53 +695,45 @@ __global__ void __launch_bounds__(256) k_tail_ka(TailKaParams p) {
         se[tid] = sc * (rm2 * (double)p.st2.mean[tid] - (double)s_m1[tid]);
     }
     __syncthreads();
-    for (int o = tid; o < C1 * C1; o += 256) {
+    for (int o = tid; o < C1 * C1; o += 1024) {
         const int k = o >> 6, kp = o & 63;
         double a = 0.0;
 #pragma unroll 8
-        for (int c = 0; c < C2; ++c) a += (double)p.W2[c * C1 + k] * sd[c] * (double)p.W2[c * C1 + kp];
+        for (int c = 0; c < C2; ++c) a += (double)s_w2[c * C1 + k] * sd[c] * (double)s_w2[c * C1 + kp];
         p.Kmat[o] = (float)a;
     }
     if (tid < C1) {
         double cv = 0.0;
-        for (int c = 0; c < C2; ++c) cv += (double)p.W2[c * C1 + tid] * se[c];
+#pragma unroll 8
+        for (int c = 0; c < C2; ++c) cv += (double)s_w2[c * C1 + tid] * se[c];
         p.cvec[tid] = (float)cv;
     }
 #ifndef PGPD_EMU
     if (!p.img1) return;
     // ---- esc[c] = 2^e with max|dz2[.,c]| 2^e in [2^12, 2^13)
-    {
-        const int c = tid & 127, half = tid >> 7;
-        float mx = 0.f;
-        for (int g = half; g < p.n_pm; g += 2) mx = fmaxf(mx, p.pmax[(size_t)g * 2 * C2 + c]);
-        __shared__ float s_pm[2][C2];
-        s_pm[half][c] = mx;
-        __syncthreads();
-        if (half == 0) {
-            mx = fmaxf(mx, s_pm[1][c]);
-            int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-            e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
-            const float ev = __uint_as_float((uint32_t)(127 - e) << 23);
-            p.esc[c] = __uint_as_float((uint32_t)(127 + e) << 23);
-            p.einv[c] = ev;
-            s_einv[c] = ev;
-        }
-        __syncthreads();
+    if (tid < C2) {
+        const float mx = p.pmx[tid];
+        int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+        e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
+        const float ev = __uint_as_float((uint32_t)(127 - e) << 23);
+        p.esc[tid] = __uint_as_float((uint32_t)(127 + e) << 23);
+        p.einv[tid] = ev;
+        s_einv[tid] = ev;
     }
+    __syncthreads();        // also: Kmat (global, written by this block) is visible to this block
     // ---- A-operand images of the pass: row k < 64: A1op[k][c] = W2[c][k] s_c einv_c 2^g_k, A2op[k][k'] = -K[k][k'] 2^g_k / 16;
-    // rows 64..127 zero.  One warp per row (lane: 4 columns c of A1op, 2 columns k' of A2op); Kmat was written by this block.
-    __syncthreads();
+    // rows 64..127 zero.  One warp per row (lane: 4 columns c of A1op, 2 columns k' of A2op).
     {
         const int warp = tid >> 5, lane = tid & 31;
         __half* img1 = (__half*)p.img1;
         __half* img2 = (__half*)p.img2;
-        for (int r = warp; r < 128; r += 8) {
+        for (int r = warp; r < 128; r += 32) {
             float w[4], kk[2];
             float mx = 0.f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = lane + 32 * u;
-                w[u] = (r < C1) ? p.W2[c * C1 + r] * p.st2.scale[c] * s_einv[c] : 0.f;
+                w[u] = (r < C1) ? s_w2[c * C1 + r] * p.st2.scale[c] * s_einv[c] : 0.f;
                 mx = fmaxf(mx, fabsf(w[u]));
             }
 #pragma unroll
@@ -681,12 +761,15 @@ __global__ void __launch_bounds__(256) k_tail_ka(TailKaParams p) {
             if (lane == 0) p.ginv[r] = ldexpf(1.f, -e);
         }
     }
+#else
+    (void)s_einv;
 #endif
 }
 
-// T7a: k_tail_kb -- after the fused layer-2/1 backward pass:
-//   blocks [0, 48): column slices of the partial rows of C = sum dz2 a1^T (128 x 64) and Gram1 = sum a1 a1^T (64 x 64);
-//   blocks [48, 56): BatchNorm1-backward partial rows (sum dz1, sum dz1 yhat1), 16 columns each;
+// T7a: k_tail_kb -- after the fused layer-2/1 backward pass (block = 1024 threads):
+//   blocks [0, 48): column slices (256 columns x 4 lanes) of the partial rows of C = sum dz2 a1^T (128 x 64) and
+//                   Gram1 = sum a1 a1^T (64 x 64);
+//   blocks [48, 52): BatchNorm1-backward partial rows (sum dz1, sum dz1 yhat1), 32 columns x 32 lanes each;
 //   last block: dgamma1, dbeta1, m1, m2;  dW2 = diag(s)[C - m1 S1a^T - diag(r m2)(W2 Gram1 - mu2 S1a^T)];  db2 = 0.
 struct TailKbParams {
     const float* Cpart; const float* G1part; int n_parts;     // [n_parts][8192], [n_parts][4096]
@@ -698,46 +781,57 @@ struct TailKbParams {
     float* dW2; float* db2;
     unsigned* counter;
 };
-constexpr int TKB_BLOCKS = 56;
+constexpr int TKB_BLOCKS = 52;
 
-__global__ void __launch_bounds__(256) k_tail_kb(TailKbParams p) {
-    __shared__ double sh[16][17];
+__global__ void __launch_bounds__(1024) k_tail_kb(TailKbParams p) {
+    __shared__ double sh[32][33];
+    __shared__ float s_g1[C1 * C1];               // 16 KB
     const int tid = (int)threadIdx.x, blk = (int)blockIdx.x;
     if (blk < 48) {
-        const int col = blk * 256 + tid;                      // 0 .. 12287
+        const int cl = tid & 255, ln = tid >> 8;
+        const int col = blk * 256 + cl;                       // 0 .. 12287
         const bool isC = col < C2 * C1;
         const float* src = isC ? p.Cpart + col : p.G1part + (col - C2 * C1);
         const size_t ld = isC ? (size_t)C2 * C1 : (size_t)C1 * C1;
         double s = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < p.n_parts; ++r) s += (double)src[(size_t)r * ld];
-        if (isC) p.Cm[col] = (float)s; else p.G1[col - C2 * C1] = (float)s;
-    } else {
-        const int cx = tid & 15, ln = tid >> 4;
-        const int col = (blk - 48) * 16 + cx;                 // 0 .. 127 of [2][64]
-        double s = 0.0;
-#pragma unroll 4
-        for (int r = ln; r < p.n_bn; r += 16) s += (double)p.bnpart[(size_t)r * 2 * C1 + col];
-        sh[ln][cx] = s;
+#pragma unroll 8
+        for (int r = ln; r < p.n_parts; r += 4) s += (double)src[(size_t)r * ld];
+        double* shf = &sh[0][0];
+        shf[ln * 256 + cl] = s;
         __syncthreads();
         if (ln == 0) {
+            const double t = ((shf[cl] + shf[256 + cl]) + shf[512 + cl]) + shf[768 + cl];
+            if (isC) p.Cm[col] = (float)t; else p.G1[col - C2 * C1] = (float)t;
+        }
+    } else {
+        const int cx = tid & 31, ry = tid >> 5;
+        const int col = (blk - 48) * 32 + cx;                 // 0 .. 127 of [2][64]
+        double s = 0.0;
+#pragma unroll 8
+        for (int r = ry; r < p.n_bn; r += 32) s += (double)p.bnpart[(size_t)r * 2 * C1 + col];
+        sh[ry][cx] = s;
+        __syncthreads();
+        if (ry == 0) {
             double t = 0.0;
-#pragma unroll
-            for (int l2 = 0; l2 < 16; ++l2) t += sh[l2][cx];
+#pragma unroll 8
+            for (int l2 = 0; l2 < 32; ++l2) t += sh[l2][cx];
             p.bnsum[col] = t;
         }
     }
     if (!last_block_done(p.counter, gridDim.x)) return;
+    for (int i = tid; i < C1 * C1; i += 1024) s_g1[i] = p.G1[i];
     if (tid < 2 * C1) {
         const double s = p.bnsum[tid];
         if (tid < C1) { p.dbeta1[tid] = (float)s; p.m1_1[tid] = (float)(s / p.count); }
         else { p.dgamma1[tid - C1] = (float)s; p.m2_1[tid - C1] = (float)(s / p.count); }
     }
-    for (int o = tid; o < C2 * C1; o += 256) {
+    __syncthreads();
+#pragma unroll 2
+    for (int o = tid; o < C2 * C1; o += 1024) {
         const int c = o >> 6, k = o & 63;
         double wg = 0.0;
 #pragma unroll 8
-        for (int kk = 0; kk < C1; ++kk) wg += (double)p.W2[c * C1 + kk] * (double)p.G1[kk * C1 + k];
+        for (int kk = 0; kk < C1; ++kk) wg += (double)p.W2[c * C1 + kk] * (double)s_g1[kk * C1 + k];
         const double sc = (double)p.st2.scale[c], rm2 = (double)p.st2.rstd[c] * (double)p.m2_2[c];
         const double v = (double)p.Cm[o] - (double)p.m1_2[c] * p.S1a[k] - rm2 * (wg - (double)p.st2.mean[c] * p.S1a[k]);
         p.dW2[o] = (float)(sc * v);

@@ -30,7 +30,8 @@ struct GemmOp {
     const float* p;        // row-major matrix
     int ld;                // its row length (floats)
     int mode;              // 0: rows indexed by m (or n), contraction along the row; 1: rows indexed by k
-    const unsigned* absmax_bits;   // device scalar: bit pattern of max |x| (non-negative float), or nullptr
+    const unsigned* absmax_bits;   // device array of n_absmax bit patterns of partial max |x| (non-negative floats), or nullptr
+    int n_absmax;
     float fixed_scale;     // used when absmax_bits == nullptr
 };
 
@@ -41,23 +42,23 @@ struct GemmParams {
     const float* mask;     // optional [M][N]: output zeroed where mask <= 0 (only without split-K)
 };
 
-// max |x| over up to two arrays -> out[0], out[1] (bit patterns; the caller zeroes them first; max is order-independent).
+// partial max |x| over up to two arrays: out[which * gridDim.x + block] (bit patterns; no atomics, nothing to zero first: the
+// consumer takes the max over the gridDim.x values, see gemm_op_scale).
 // grid = (blocks, 2), block = 256; array lengths must be multiples of 4 and the pointers 16-byte aligned.
 __global__ void k_absmax2(const float* __restrict__ a, size_t na, const float* __restrict__ b, size_t nb, unsigned* __restrict__ out) {
     __shared__ float sh[8];
     const int tid = (int)threadIdx.x, which = (int)blockIdx.y;
     const float4* p = reinterpret_cast<const float4*>(which ? b : a);
     const size_t n4 = (which ? nb : na) >> 2;
-    if (!p) return;
     float m0 = 0.f, m1 = 0.f;
     const size_t stride = (size_t)gridDim.x * 256;
     size_t i = (size_t)blockIdx.x * 256 + tid;
-    for (; i + stride < n4; i += 2 * stride) {
+    for (; p && i + stride < n4; i += 2 * stride) {
         const float4 u = p[i], v = p[i + stride];
         m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w))));
         m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    if (i < n4) { const float4 u = p[i]; m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w)))); }
+    if (p && i < n4) { const float4 u = p[i]; m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w)))); }
     float mx = fmaxf(m0, m1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -65,13 +66,18 @@ __global__ void k_absmax2(const float* __restrict__ a, size_t na, const float* _
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
-        atomicMax(out + which, __float_as_uint(mx));
+        out[(size_t)which * gridDim.x + blockIdx.x] = __float_as_uint(mx);
     }
 }
 
+// saturate to the fp16 operand range but keep NaN (fminf / fmaxf would turn NaN into a finite bound): gradients are scaled
+// from their measured maxima and never reach the bound; activations beyond it were replaced by NaN where they were produced
+__device__ __forceinline__ float clamp_keepnan(float t) { return t > 60000.f ? 60000.f : (t < -60000.f ? -60000.f : t); }
+
 __device__ __forceinline__ float gemm_op_scale(const GemmOp& o) {
     if (!o.absmax_bits) return o.fixed_scale;
-    const unsigned bits = *o.absmax_bits;
+    unsigned bits = 0u;
+    for (int i = 0; i < o.n_absmax; ++i) { const unsigned b = o.absmax_bits[i]; bits = b > bits ? b : bits; }   // non-negative floats order like their bits
     if (bits == 0u) return 1.f;
     int e = 139 - (int)((bits >> 23) & 0xFFu);          // max |x| * 2^e in [2^12, 2^13)
     e = e > 100 ? 100 : (e < -100 ? -100 : e);
@@ -102,8 +108,8 @@ __device__ __forceinline__ void gemm_stage(const GemmOp& o, float scale, int mn0
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int r = (warp + 4 * (i0 + u)) * 2 + rsub;
-                const float a0 = fminf(fmaxf(v[u].x * scale, -60000.f), 60000.f), a1 = fminf(fmaxf(v[u].y * scale, -60000.f), 60000.f);
-                const float a2 = fminf(fmaxf(v[u].z * scale, -60000.f), 60000.f), a3 = fminf(fmaxf(v[u].w * scale, -60000.f), 60000.f);
+                const float a0 = clamp_keepnan(v[u].x * scale), a1 = clamp_keepnan(v[u].y * scale);
+                const float a2 = clamp_keepnan(v[u].z * scale), a3 = clamp_keepnan(v[u].w * scale);
                 __half2 h01, l01, h23, l23;
                 split2(a0, a1, h01, l01);
                 split2(a2, a3, h23, l23);
@@ -135,8 +141,8 @@ __device__ __forceinline__ void gemm_stage(const GemmOp& o, float scale, int mn0
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int r = warp + 4 * (i0 + u);
-                const float a0 = fminf(fmaxf(v[u].x * scale, -60000.f), 60000.f), a1 = fminf(fmaxf(v[u].y * scale, -60000.f), 60000.f);
-                const float a2 = fminf(fmaxf(v[u].z * scale, -60000.f), 60000.f), a3 = fminf(fmaxf(v[u].w * scale, -60000.f), 60000.f);
+                const float a0 = clamp_keepnan(v[u].x * scale), a1 = clamp_keepnan(v[u].y * scale);
+                const float a2 = clamp_keepnan(v[u].z * scale), a3 = clamp_keepnan(v[u].w * scale);
                 __half2 h01, l01, h23, l23;
                 split2(a0, a1, h01, l01);
                 split2(a2, a3, h23, l23);

@@ -84,13 +84,16 @@ struct L3Params {
     const float* shift2;      // [128]
     const __half* Wimg;       // pre-packed W3 image
     const float* inv;         // [1024]
-    const float* mu_s;        // [1024] mean of u3 in accumulator units, or nullptr (no statistics)
+    const float* mu_s;        // versions 1/2: [1024] mean of u3 in accumulator units, or nullptr (no statistics)
     unsigned long long* keys; // [B][1024] (ordered max value, ~arg-max)
     float* css_part;          // [ntiles][1024]
     int B, N, tiles_per_cloud, ntiles;
     long long* dbg;           // optional [gridDim.x][8] cycle counters (see PGPD_L3_DEBUG), or nullptr
     float* s1_part;           // optional partial sums over the points of a2 * 2^4: v1 [gridDim.x][128], v3 [gridDim.x * 8][128]
     unsigned* bad;            // [B] set to 1 for a cloud with a NaN / out-of-fp16-range activation (version 3)
+    // version 3, train mode: the kernel forms the centres of its sums of squares itself: centre[c] = W3[c] . (s1_pilot * inv_n)
+    // (a pilot estimate of mean(u3), tails.cuh: k_tail_l2) and publishes them in centre_out; null: no statistics
+    const double* s1_pilot; double inv_n; const float* W3f; float* centre_out;
 };
 
 // cycle accounting of the pipeline roles, for tuning (enabled by a non-null L3Params::dbg):
@@ -654,6 +657,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 240);
     float* s_scale = reinterpret_cast<float*>(misc + 256);
     float* s_shift = s_scale + 128;
+    float* s_ma2 = s_shift + 128;                          // pilot mean of a2 (train mode)
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -669,7 +673,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         mbar_init(BAR(TM_EMPTY), 32); mbar_init(BAR(TM_EMPTY + 1), 32);
         mbar_fence_init();
     }
-    if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
+    if (tid < 128) {
+        s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE;
+        s_ma2[tid] = p.s1_pilot ? (float)(p.s1_pilot[tid] * p.inv_n) : 0.f;
+    }
     if (warp == 1) tmem_alloc_pair<512>(smem_u32(tmem_slot));
     tc_fence_before_sync();
     __syncthreads();
@@ -790,16 +797,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;                   // 0..3: which quarter of the 256 columns
         const int row = q * 32 + lane;
-        const bool stats = p.mu_s != nullptr;
+        const bool stats = p.centre_out != nullptr;
         int acc = 0; uint32_t aphase = 0;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;      // centred squares of my channel of block mt4 = 0..3, summed over my tiles
+        float mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, mu3 = 0.f;      // their centres, in accumulator units
+        if (stats) {
+            // centre[c] = W3[c] . mean(a2) (pilot): 4 channels per thread, 128 FMAs each, while the pipeline fills
+#pragma unroll
+            for (int mt4 = 0; mt4 < 4; ++mt4) {
+                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
+                const float4* wr = reinterpret_cast<const float4*>(p.W3f + (size_t)ch * C2);
+                float sacc = 0.f;
+#pragma unroll 8
+                for (int k4 = 0; k4 < C2 / 4; ++k4) {
+                    const float4 wv = wr[k4];
+                    sacc = fmaf(wv.x, s_ma2[4 * k4 + 0], sacc); sacc = fmaf(wv.y, s_ma2[4 * k4 + 1], sacc);
+                    sacc = fmaf(wv.z, s_ma2[4 * k4 + 2], sacc); sacc = fmaf(wv.w, s_ma2[4 * k4 + 3], sacc);
+                }
+                if (half == 0) p.centre_out[ch] = sacc;          // every pair writes the same value
+                const float m = sacc / p.inv[ch];
+                if (mt4 == 0) mu0 = m; else if (mt4 == 1) mu1 = m; else if (mt4 == 2) mu2 = m; else mu3 = m;
+            }
+        }
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt4 = 0; mt4 < 4; ++mt4) {
                 const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
-                const float mu = stats ? p.mu_s[ch] : 0.f;
+                const float mu = mt4 == 0 ? mu0 : (mt4 == 1 ? mu1 : (mt4 == 2 ? mu2 : mu3));
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
                 mbar_wait(BAR(TM_FULL + acc), aphase);
                 tc_fence_after_sync();
@@ -933,10 +959,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
         if (p.s1_part) {
-            // sums of a2 (x 2^4): one partial row per producer warp, [gridDim.x * 8][128]; the caller's fixed-order column
-            // reduction adds them up
-            float* o = p.s1_part + ((size_t)blockIdx.x * 8 + wp) * C2 + 4 * lane;
+            // sums of a2 (x 2^4): ONE partial row per CTA, [gridDim.x][128].  The 8 producer warps add their rows in warp order
+            // through the first operand buffer, which is free once the MMAs of the last two tiles have released both buffers.
+            for (int e = 0; e < 2; ++e) {
+                mbar_wait(BAR(A2_EMPTY + buf), bphase ^ 1);
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+            float* red = reinterpret_cast<float*>(smem);
+            float* o = red + wp * C2 + 4 * lane;
             o[0] = sa0; o[1] = sa1; o[2] = sa2; o[3] = sa3;
+            named_bar_sync(3, 256);
+            if (wp == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float t = red[4 * lane + i];
+#pragma unroll
+                    for (int w2 = 1; w2 < 8; ++w2) t += red[w2 * C2 + 4 * lane + i];
+                    p.s1_part[(size_t)blockIdx.x * C2 + 4 * lane + i] = t;
+                }
+            }
         }
     }
 

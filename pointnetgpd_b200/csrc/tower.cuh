@@ -627,7 +627,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     {
         A1Params p{a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1, a.train ? w.dpart : (double*)nullptr,
                    w.counters + 1, t.conv[1].w, count, w.bn[1].mean, w.S1a, w.bad, act_limit};
-        launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK * A1_CPB), a.B), dim3(256), 0, s, p);
+        launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK * A1_CPB), a.B), dim3(A1_THREADS), 0, s, p);
     }
 
     // ---- layer 2 ---------------------------------------------------------------------------------------------------------
@@ -651,14 +651,16 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     // centre of the layer-3 kernel's sum of squares); that kernel's operand producers accumulate the exact sum of a2 on the
     // way and k_tail_l3 corrects the statistics (var = sum (u-c)^2 / M - (mean - c)^2, an identity).
     bool l3_pilot = false;
+    size_t tl2_nsample = 1;
     if (a.train) {
         TailL2Params p{};
         p.css = w.fpart; p.n_css = n_css2; p.mean_u2 = w.bn[1].mean; p.count = count; p.bias2 = t.conv[1].b; p.bn2 = t.bn[1]; p.st2 = w.bn[1];
         p.Y2 = w.Y2; p.part = w.rtmp; p.counter = w.counters + 2;
-        p.W3 = t.conv[2].w; p.mean_u3 = w.bn[2].mean; p.S1 = w.S1; p.inv3 = w.sgn; p.mu_s = tcp ? w.mu_s : nullptr;
+        p.W3 = t.conv[2].w; p.mean_u3 = tcp ? (float*)nullptr : w.bn[2].mean; p.S1 = w.S1;
         const size_t pstride = M >= 4 * (size_t)TL2_SAMPLE ? M / TL2_SAMPLE : 1;
         p.pstride = pstride; p.nsample = (M + pstride - 1) / pstride;
-        launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(256), 0, s, p);
+        tl2_nsample = p.nsample;
+        launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(1024), 0, s, p);
         if (tcp) {
             l3_pilot = pstride > 1;
         } else {
@@ -667,7 +669,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
             const int nb = (int)std::min<size_t>((size_t)w.nb_a2, (M + 15) / 16);
             launch(k_a2_sum, dim3(nb), dim3(256), 0, s, (const float*)w.Y2, M, (size_t)1, w.bn[1], w.dpart);
             p.bn_done = 1; p.a2part = w.dpart; p.n_a2part = nb; p.nsample = M; p.pstride = 1;
-            launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(256), 0, s, p);
+            launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(1024), 0, s, p);
         }
     }
 
@@ -676,16 +678,17 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 #ifndef PGPD_EMU
     if (tcp) {
         const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
-        tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
+        tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, nullptr,
                        w.keys, w.fpart, a.B, a.N, tpc, ntiles, tc::l3_debug_buffer_if_enabled(),
-                       l3_pilot ? w.s1part : (float*)nullptr, w.bad};
+                       l3_pilot ? w.s1part : (float*)nullptr, w.bad,
+                       a.train ? w.S1 : (const double*)nullptr, 1.0 / (double)tl2_nsample, t.conv[2].w, a.train ? w.bn[2].mean : (float*)nullptr};
         const int sms = tc::dev_info().sms;
         const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
         profiler().begin(s);
         launch(tc::k_l3_fwd_tc3<false>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
         profiler().end(s);
         n_css = pairs * tc::L3C_EPI_ROWS;             // partial rows of centred squares: four per CTA pair
-        n_s1 = 2 * pairs * 8;                         // partial rows of the sum of a2: one per producer warp
+        n_s1 = 2 * pairs;                             // partial rows of the sum of a2: one per CTA
     } else
 #endif
     {
@@ -707,7 +710,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         p.css = w.fpart; p.n_css = n_css;
         p.s1part = l3_pilot ? w.s1part : nullptr; p.n_s1 = n_s1; p.s1scale = 1.0 / 16.0;   // the kernel sums a2 * 2^4 (L3_ACT_SCALE)
         p.W3 = t.conv[2].w; p.bias3 = t.conv[2].b; p.bn3 = t.bn[2]; p.count = count; p.S1 = w.S1;
-        launch(k_tail_l3, dim3(C3 / TL3_CH), dim3(256), 0, s, p);
+        launch(k_tail_l3, dim3(C3 / TL3_CH), dim3(1024), 0, s, p);
     }
 }
 
@@ -732,7 +735,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
 #ifndef PGPD_EMU
         p.act_shift = tc::ACT_SHIFT;
 #endif
-        launch(k_q_uvec, dim3(C2 / 4), dim3(128), 0, s, p);
+        launch(k_q_uvec, dim3(C2 / 4), dim3(1024), 0, s, p);
     }
 
     // ---- sparse part of d a2 -----------------------------------------------------------------------
@@ -741,7 +744,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
 
     // ---- pass A: d a2 -> dz2 (stored), BatchNorm2 backward sums, Gram matrix of a2 --------------------------------------------
     TailKaParams tk{};
-    tk.g2 = w.gram2; tk.gram = w.gram; tk.count = count;
+    tk.g2 = w.gram2; tk.gram = w.gram; tk.count = count; tk.bnsum = w.rtmp; tk.pmx = w.esc;   // esc doubles as the scratch of the maxima
     tk.dgamma = g.bn[1].dgamma; tk.dbeta = g.bn[1].dbeta; tk.m1 = w.m1_2; tk.m2 = w.m2_2;
     tk.W2 = t.conv[1].w; tk.st2 = w.bn[1]; tk.Kmat = w.Kmat; tk.cvec = w.cvec; tk.counter = w.counters + 3;
     int g_b4 = 0;       // rows of pmax written by the tcgen05 pass-A kernel
@@ -768,7 +771,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         tk.bnpart = w.ka_part; tk.n_bn = w.nb_l2;
         tk.act_scale = 1.f;
     }
-    launch(k_tail_ka, dim3(tk.gcols / 256), dim3(256), 0, s, tk);
+    launch(k_tail_ka, dim3(tk.gcols / 256 + 8 + (tcp ? 4 : 0)), dim3(1024), 0, s, tk);
 
     // ---- dW3 ---------------------------------------------------------------------------------------------------------------
     launch(k_dw3, dim3(C3), dim3(512), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
@@ -799,9 +802,9 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         TailKbParams p{w.kb_Cpart, w.kb_G1part, nparts, w.kbC, w.kbG1, w.kb_bn, nrows, count, w.rtmp,
                        g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1, w.S1a, t.conv[1].w, w.bn[1], w.m1_2, w.m2_2,
                        g.conv[1].dw, g.conv[1].db, w.counters + 4};
-        launch(k_tail_kb, dim3(TKB_BLOCKS), dim3(256), 0, s, p);
+        launch(k_tail_kb, dim3(TKB_BLOCKS), dim3(1024), 0, s, p);
     }
-    launch(k_kb_l1, dim3(a.B), dim3(192), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
+    launch(k_kb_l1, dim3(a.B), dim3(768), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
            (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr, w.counters + 5,
            g.conv[0].dw, g.conv[0].db);
 }

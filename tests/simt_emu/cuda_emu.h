@@ -192,7 +192,11 @@ inline void* dyn_smem() {
 #define gridDim (emu::S().gridDim_)
 
 static inline void __syncthreads() { emu::syncthreads(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __syncwarp(unsigned = 0xffffffffu) {      // a real barrier: fibers of a warp do not run in lockstep
+    emu::State& s = emu::S();
+    const int warp = s.cur / 32;
+    emu::warp_barrier(s.warps[warp], emu::warp_members(warp));
+}
 static inline void __threadfence() {}
 
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
