@@ -87,11 +87,11 @@ struct ProbPlain {
 
 // number of K slices.  fixed_nsl > 0: exactly that many (forward GEMMs: the summation order must not depend on the batch
 // size, so that eval outputs are bit-identical however the clouds are batched); 0: by occupancy.
-inline int pick_slices(int tiles, int Mr, int Nc, int K, int min_slice, int fixed_nsl) {
+inline int pick_slices(int tiles, int Mr, int Nc, int K, int min_slice, int fixed_nsl, int target) {
     int nsl = 1;
     if (fixed_nsl > 0) nsl = fixed_nsl;
     else
-        while (tiles * nsl < 148 && K / (nsl * 2) >= min_slice && (size_t)(nsl * 2) * Mr * Nc <= HEAD_PART_ELEMS) nsl *= 2;
+        while (tiles * nsl < target && K / (nsl * 2) >= min_slice && (size_t)(nsl * 2) * Mr * Nc <= HEAD_PART_ELEMS) nsl *= 2;
     while (nsl > 1 && (size_t)nsl * Mr * Nc > HEAD_PART_ELEMS) nsl /= 2;
     return nsl;
 }
@@ -100,7 +100,7 @@ inline int pick_slices(int tiles, int Mr, int Nc, int K, int min_slice, int fixe
 template <bool AK, bool BNF>
 inline int run_plain(ProbPlain<AK, BNF> p, cudaStream_t s, int fixed_nsl) {
     const int tm = idiv_up(p.Mr, CfgSmall::BM), tn = idiv_up(p.Nc, CfgSmall::BN);
-    int nsl = pick_slices(tm * tn, p.Mr, p.Nc, p.K, 64, fixed_nsl);
+    int nsl = pick_slices(tm * tn, p.Mr, p.Nc, p.K, 64, fixed_nsl, 296);
     p.ksl = idiv_up(p.K, nsl);
     nsl = idiv_up(p.K, p.ksl);
     launch_gemm<CfgSmall>(p, dim3(tn, tm, nsl), s);
@@ -111,7 +111,7 @@ inline int run_plain(ProbPlain<AK, BNF> p, cudaStream_t s, int fixed_nsl) {
 // C[M][N] = sum_k A(m,k) B(n,k) on the tensor cores; returns the number of K slices written to `part`
 inline int run_gemm_tc(tc::GemmOp A, tc::GemmOp Bo, int M, int N, int K, float* part, int nsl_fixed, cudaStream_t s) {
     const int tiles = idiv_up(M, tc::GM_T) * idiv_up(N, tc::GM_T);
-    int nsl = pick_slices(tiles, M, N, K, tc::GM_KC, nsl_fixed);
+    int nsl = pick_slices(tiles, M, N, K, tc::GM_KC, nsl_fixed, 120);
     const int kslice = idiv_up(idiv_up(K, nsl), tc::GM_KC) * tc::GM_KC;
     nsl = idiv_up(K, kslice);                       // no empty slices
     tc::GemmParams p{A, Bo, M, N, K, kslice, part, nullptr};
@@ -136,10 +136,12 @@ __global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ 
     const size_t slice = (size_t)B * C;
     double s = 0.0;
     if (c < C) {
+#pragma unroll 2
         for (int b = ry; b < B; b += 32) {
             const size_t i = (size_t)b * C + c;
             float u = part[i];
-            for (int z = 1; z < nsl; ++z) u += part[(size_t)z * slice + i];
+#pragma unroll 8
+            for (int z = 1; z < nsl; ++z) u += part[(size_t)z * slice + i];      // loads are independent of the running sum
             U[i] = u;
             s += (double)u;
         }
@@ -232,27 +234,33 @@ __global__ void k_log_softmax_bwd(const float* __restrict__ logp, const float* _
 }
 
 // ---- fc3 backward: dW3[j][i] = sum_b dO[b][j] H2[b][i];  db3[j] = sum_b dO[b][j];  dz2[b][i] = (sum_j dO[b][j] W3[j][i]) [H2 > 0]
-// blocks [0, J): one output row j of dW3 (thread i; clouds summed in order) + db3[j];  blocks [J, J + ceil(B/8)): dz2 of 8 clouds.
-__global__ void __launch_bounds__(256) k_fc3_bwd(const float* __restrict__ dO, const float* __restrict__ Hm2, const float* __restrict__ W3,
-                                                 int B, int J, float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ DZ2) {
-    const int i = (int)threadIdx.x;
+// block = 1024 = 256 columns i x 4 cloud lanes.  blocks [0, J): one output row j of dW3 (each lane sums its clouds in order, the 4
+// lanes are added in order) + db3[j];  blocks [J, J + ceil(B/32)): dz2 of 32 clouds (8 per lane).
+__global__ void __launch_bounds__(1024) k_fc3_bwd(const float* __restrict__ dO, const float* __restrict__ Hm2, const float* __restrict__ W3,
+                                                  int B, int J, float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ DZ2) {
+    __shared__ float s_a[4][H2];
+    __shared__ double s_b[4];
+    const int i = (int)threadIdx.x & 255, ln = (int)threadIdx.x >> 8;
     if ((int)blockIdx.x < J) {
         const int j = (int)blockIdx.x;
-        float a0 = 0.f, a1 = 0.f;
+        float a = 0.f;
         double bsum = 0.0;
-        int b = 0;
-        for (; b + 1 < B; b += 2) {
-            const float d0 = dO[(size_t)b * J + j], d1 = dO[(size_t)(b + 1) * J + j];
-            a0 = fmaf(d0, Hm2[(size_t)b * H2 + i], a0);
-            a1 = fmaf(d1, Hm2[(size_t)(b + 1) * H2 + i], a1);
-            bsum += (double)d0 + (double)d1;
+#pragma unroll 8
+        for (int b = ln; b < B; b += 4) {
+            const float d = dO[(size_t)b * J + j];
+            a = fmaf(d, Hm2[(size_t)b * H2 + i], a);
+            bsum += (double)d;
         }
-        if (b < B) { const float d0 = dO[(size_t)b * J + j]; a0 = fmaf(d0, Hm2[(size_t)b * H2 + i], a0); bsum += (double)d0; }
-        dW3[(size_t)j * H2 + i] = a0 + a1;
-        if (i == 0) db3[j] = (float)bsum;
+        s_a[ln][i] = a;
+        if (i == 0) s_b[ln] = bsum;
+        __syncthreads();
+        if (ln == 0) {
+            dW3[(size_t)j * H2 + i] = ((s_a[0][i] + s_a[1][i]) + s_a[2][i]) + s_a[3][i];
+            if (i == 0) db3[j] = (float)(((s_b[0] + s_b[1]) + s_b[2]) + s_b[3]);
+        }
         return;
     }
-    const int b0 = ((int)blockIdx.x - J) * 8;
+    const int b0 = ((int)blockIdx.x - J) * 32 + ln * 8;
     for (int bb = 0; bb < 8 && b0 + bb < B; ++bb) {
         const int b = b0 + bb;
         float s = 0.f;
@@ -284,6 +292,7 @@ __device__ __forceinline__ void bn_head_bwd_block(int blk, const float* __restri
             float dzf;
             if (part) {
                 dzf = part[i];
+#pragma unroll 8
                 for (int z = 1; z < nsl; ++z) dzf += part[(size_t)z * slice + i];
                 if (!(Hmask[i] > 0.f)) dzf = 0.f;
                 DZ[i] = dzf;
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(1024) k_head_mid(int nbn, const float* __restr
     const size_t i = (size_t)((int)blockIdx.x - nbn) * 1024 + threadIdx.x;
     if (i >= nW) return;
     float v = partW[i];
+#pragma unroll 8
     for (int z = 1; z < nslW; ++z) v += partW[(size_t)z * nW + i];
     dW[i] = v;
 }
@@ -358,6 +368,7 @@ __global__ void __launch_bounds__(1024) k_finish2(const float* __restrict__ part
     if (i < n1r) {
         if (i < n1) {
             float v = part1[i];
+#pragma unroll 8
             for (int z = 1; z < nsl1; ++z) v += part1[(size_t)z * n1 + i];
             out1[i] = v;
         }
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(1024) k_finish2(const float* __restrict__ part
     i -= n1r;
     if (i < n2) {
         float v = part2[i];
+#pragma unroll 8
         for (int z = 1; z < nsl2; ++z) v += part2[(size_t)z * n2 + i];
         out2[i] = v;
     }
@@ -430,7 +442,7 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     unsigned* amax_du1 = w.amax + 2 * HEAD_AMAX_BLOCKS;        // [16] partial max |dU1| (512 channels / 32)
     unsigned* amax_du2 = amax_du1 + 16;                        // [8 of 16]
     // ---- fc3: dW3, db3, dz2
-    launch(k_fc3_bwd, dim3(J3 + idiv_up(B, 8)), dim3(256), 0, s, (const float*)w.dO, (const float*)w.Hm2, h.fc[2].w, B, J3,
+    launch(k_fc3_bwd, dim3(J3 + idiv_up(B, 32)), dim3(1024), 0, s, (const float*)w.dO, (const float*)w.Hm2, h.fc[2].w, B, J3,
            g.fc[2].dw, g.fc[2].db, w.DZ2);
     launch(k_bn_head_bwd, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta,
            g.fc[1].db, tcg ? amax_du2 : (unsigned*)nullptr);

@@ -137,13 +137,15 @@ __global__ void __launch_bounds__(256) k_kb_ref(KbRefParams p) {
 // grid = B, block = 768 = 192 (k, j) x 4 lanes.  xmom[b] = { X1 (3), X2 (3x3 row-major) } raw-coordinate moments (double).
 // The last block sums the per-cloud partials of dW1 (4 lanes, clouds in order within a lane, lanes added in order:
 // deterministic) and zeroes the conv1 bias gradient.
-__global__ void __launch_bounds__(768) k_kb_l1(const float* __restrict__ Hpart, int rpc, const double* __restrict__ xmom,
+// Blocks [B, gridDim.x) are a different job that shares the launch: rows of dW2 (tails.cuh: dw2_row).
+__global__ void __launch_bounds__(768) k_kb_l1(int B, const float* __restrict__ Hpart, int rpc, const double* __restrict__ xmom,
                         const float* __restrict__ trans, const float* __restrict__ W1, BnState st1, const float* __restrict__ m1,
                         const float* __restrict__ m2, float* __restrict__ dW1part, float* __restrict__ dtrans, unsigned* counter,
-                        float* __restrict__ dW1, float* __restrict__ db1) {
+                        float* __restrict__ dW1, float* __restrict__ db1, Dw2Params d2) {
+    if ((int)blockIdx.x >= B) { dw2_row(d2, (int)blockIdx.x - B); return; }
     __shared__ float G[C1 * 3];
     __shared__ float hs[4][C1 * 3];
-    __shared__ double ds[4][C1 * 3];
+    __shared__ double ds[24][C1 * 3];
     const int b = (int)blockIdx.x, tid = (int)threadIdx.x, e = tid % 192, ln = tid / 192;
     float T[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (trans)
@@ -182,15 +184,28 @@ __global__ void __launch_bounds__(768) k_kb_l1(const float* __restrict__ Hpart, 
         for (int kk = 0; kk < C1; ++kk) s = fmaf(W1[kk * 3 + i], G[kk * 3 + j], s);
         dtrans[(size_t)b * 9 + tid] = s;
     }
-    if (!last_block_done(counter, gridDim.x)) return;
+    if (!last_block_done(counter, (unsigned)B)) return;
+    // dW1 = sum over the clouds: warp w takes clouds w, w+24, ... (each lane 6 of the 192 columns, rows 4-fold unrolled: 24 loads
+    // in flight per lane), then the 24 warp rows are added in order
     {
-        double s = 0.0;
-#pragma unroll 8
-        for (unsigned bb = (unsigned)ln; bb < gridDim.x; bb += 4) s += (double)dW1part[(size_t)bb * (C1 * 3) + e];
-        ds[ln][e] = s;
+        const int warp = tid >> 5, lane = tid & 31;
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (int bb = warp; bb < B; bb += 24) {
+            const float* row = dW1part + (size_t)bb * (C1 * 3);
+#pragma unroll
+            for (int u = 0; u < 6; ++u) acc[u] += (double)row[lane + 32 * u];
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) ds[warp][lane + 32 * u] = acc[u];
     }
     __syncthreads();
-    if (tid < C1 * 3) dW1[tid] = (float)(((ds[0][tid] + ds[1][tid]) + ds[2][tid]) + ds[3][tid]);
+    if (tid < C1 * 3) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int w2 = 0; w2 < 24; ++w2) t += ds[w2][tid];
+        dW1[tid] = (float)t;
+    }
     if (tid < C1 && db1) db1[tid] = 0.f;          // bias feeding a train-mode BatchNorm: gradient is identically zero
 }
 

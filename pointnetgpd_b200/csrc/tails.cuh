@@ -222,47 +222,43 @@ struct A1Params {
 };
 
 __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
-    __shared__ float xs[3][A1_CHUNK];
+    __shared__ float xs[3][A1_CHUNK * A1_CPB];
     __shared__ double sh[A1_THREADS];
     __shared__ double vs[C1];
     const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;      // q = 0..15
     const int b = (int)blockIdx.y;
     const float w0 = p.W1[k * 3 + 0], w1 = p.W1[k * 3 + 1], w2 = p.W1[k * 3 + 2];
     const float sc = p.st.scale[k], sh_ = p.st.shift[k];
+    const int n0 = (int)blockIdx.x * (A1_CHUNK * A1_CPB);
+    const int nv = (p.N - n0 < A1_CHUNK * A1_CPB) ? p.N - n0 : A1_CHUNK * A1_CPB;
+    {
+        // the block's (up to) 1024 points, transformed, staged once
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        if (tid < nv) {
+            const float* xb = p.x + (size_t)b * 3 * p.N + n0 + tid;
+            const float p0 = xb[0], p1 = xb[p.N], p2 = xb[2 * p.N];
+            t0 = p0; t1 = p1; t2 = p2;
+            if (p.trans) {
+                const float* T = p.trans + (size_t)b * 9;
+                t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+                t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+                t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+            }
+        }
+        xs[0][tid] = t0; xs[1][tid] = t1; xs[2][tid] = t2;
+    }
+    __syncthreads();
     float acc = 0.f;
     bool flag = false;
-    for (int ch = 0; ch < A1_CPB; ++ch) {
-        const int n0 = ((int)blockIdx.x * A1_CPB + ch) * A1_CHUNK;
-        if (n0 >= p.N) break;
-        const int nv = (p.N - n0 < A1_CHUNK) ? p.N - n0 : A1_CHUNK;
-        __syncthreads();
-        if (tid < A1_CHUNK) {
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-            if (tid < nv) {
-                const float* xb = p.x + (size_t)b * 3 * p.N + n0 + tid;
-                const float p0 = xb[0], p1 = xb[p.N], p2 = xb[2 * p.N];
-                t0 = p0; t1 = p1; t2 = p2;
-                if (p.trans) {
-                    const float* T = p.trans + (size_t)b * 9;
-                    t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
-                    t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
-                    t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
-                }
-            }
-            xs[0][tid] = t0; xs[1][tid] = t1; xs[2][tid] = t2;
-        }
-        __syncthreads();
-        float* out = p.A1 + ((size_t)b * p.N + n0) * C1 + k;
-#pragma unroll
-        for (int pp = q; pp < A1_CHUNK; pp += 16) {
-            if (pp < nv) {
-                const float u = w0 * xs[0][pp] + w1 * xs[1][pp] + w2 * xs[2][pp];
-                const float a = relu_nan(sc * u + sh_);
-                flag = flag || !(a <= p.limit);
-                out[(size_t)pp * C1] = a;
-                acc += a;
-            }
-        }
+    float* out = p.A1 + ((size_t)b * p.N + n0) * C1 + k;
+    // thread (k, q): points q, q+16, ... : a half warp writes one 128-byte segment per point
+#pragma unroll 8
+    for (int pp = q; pp < nv; pp += 16) {
+        const float u = w0 * xs[0][pp] + w1 * xs[1][pp] + w2 * xs[2][pp];
+        const float a = relu_nan(sc * u + sh_);
+        flag = flag || !(a <= p.limit);
+        out[(size_t)pp * C1] = a;
+        acc += a;
     }
     if (flag) p.bad[b] = 1u;
     if (!p.part) return;
@@ -603,9 +599,8 @@ __global__ void __launch_bounds__(1024) k_q_uvec(QuParams p) {
 //               accumulators, 2 x 128 x 128; CUDA-core path: the plain Gram matrix, directly into `gram`);
 //   [n_gram, +8): BatchNorm2-backward partial rows (sum dz, sum dz*yhat): 32 columns x 32 lanes each -> bnsum[256];
 //   [.., +4) (tensor-core path): per-channel max |dz2| from the kernel's partial maxima: 32 columns x 32 lanes -> pmx[128];
-//   last block: Gram = (hh + hl + hl^T) / 256 (tensor-core path); dgamma2, dbeta2, m1, m2; the 64 x 64 / 64-vector
-//               precompute of the fused layer-2/1 pass (K, cvec; l2bwd.cuh); and (tensor-core path) the per-channel scale of
-//               dz2 and the two A-operand images of that pass (tc_kb.cuh).
+//   last block: Gram = (hh + hl + hl^T) / 256 (tensor-core path); dgamma2, dbeta2, m1, m2.
+// (The 64 x 64 precompute of the fused layer-2/1 pass, which needs m1 / m2, runs as extra blocks of k_dw3: kb_prep_row.)
 struct TailKaParams {
     const float* gpart; int n_g; int gcols;       // [n_g][gcols] partial rows; gcols = 16384 (plain) or 32768 (hh, hl)
     float* g2;                                    // [gcols] reduced (scratch when sym)
@@ -613,19 +608,13 @@ struct TailKaParams {
     const float* bnpart; int n_bn; double count;  // [n_bn][2][128] partial (sum dz, sum dz*yhat)
     double* bnsum;                                // [256] scratch
     float* dgamma; float* dbeta; float* m1; float* m2;
-    const float* W2; BnState st2; float* Kmat; float* cvec;
     unsigned* counter;
-    // tensor-core path only
-    const float* pmax; int n_pm; float* pmx;      // [n_pm][2][128] partial maxima; pmx [128] scratch
-    float* esc; float* einv;
-    void* img1; void* img2; float* ginv; float act_scale;
+    float act_scale;
+    const float* pmax; int n_pm; float* pmx;      // tensor-core path: [n_pm][2][128] partial maxima of |dz2| -> pmx [128]
 };
 
 __global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
     __shared__ double sh[32][33];
-    __shared__ float s_w2[C2 * C1];               // 32 KB: conv2.weight staged for the last block
-    __shared__ double sd[C2], se[C2];
-    __shared__ float s_m1[C2], s_m2[C2], s_einv[C2];
     const int tid = (int)threadIdx.x;
     const int n_gram = p.gcols / 256;
     int blk = (int)blockIdx.x;
@@ -673,7 +662,6 @@ __global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
     }
     if (!last_block_done(p.counter, gridDim.x)) return;
     // ================================ last block ================================
-    for (int i = tid; i < C2 * C1; i += 1024) s_w2[i] = p.W2[i];
     if (p.sym) {
         const float sc = 1.0f / (p.act_scale * p.act_scale);
 #pragma unroll 4
@@ -684,85 +672,102 @@ __global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
     }
     if (tid < 2 * C2) {
         const double s = p.bnsum[tid];
-        if (tid < C2) { p.dbeta[tid] = (float)s; s_m1[tid] = (float)(s / p.count); p.m1[tid] = s_m1[tid]; }
-        else { p.dgamma[tid - C2] = (float)s; s_m2[tid - C2] = (float)(s / p.count); p.m2[tid - C2] = s_m2[tid - C2]; }
+        if (tid < C2) { p.dbeta[tid] = (float)s; p.m1[tid] = (float)(s / p.count); }
+        else { p.dgamma[tid - C2] = (float)s; p.m2[tid - C2] = (float)(s / p.count); }
     }
-    __syncthreads();
-    // ---- K[k][k'] = sum_c W2[c][k] s_c r_c m2_c W2[c][k'],  cvec[k] = sum_c W2[c][k] s_c (r_c m2_c mu_c - m1_c)
+}
+
+// Row r (0..127) of the precompute of the fused layer-2/1 backward pass, run as extra blocks of k_dw3 (512 threads):
+//   r < 64:  K[r][k'] = sum_c W2[c][r] s_c r_c m2_c W2[c][k'],  cvec[r] = sum_c W2[c][r] s_c (r_c m2_c mu_c - m1_c)   (l2bwd.cuh)
+//   tensor-core path: esc / einv (per-channel power-of-two scale of dz2, from the maxima pmx; written by row 0) and row r of the
+//   two A-operand images of tc_kb.cuh: A1op[r][c] = W2[c][r] s_c einv_c 2^g_r, A2op[r][k'] = -K[r][k'] 2^g_r / 16 (zero rows for
+//   r >= 64), ginv[r] = 2^-g_r.
+struct KbPrepParams {
+    const float* W2; BnState st2; const float* m1; const float* m2; float* Kmat; float* cvec;
+    const float* pmx; float* esc; float* einv; void* img1; void* img2; float* ginv; float act_scale;   // img1 == null: CUDA-core path
+};
+
+__device__ __forceinline__ void kb_prep_row(const KbPrepParams& p, int r) {
+    __shared__ double sd[C2], se[C2];
+    __shared__ float s_einv[C2];
+    __shared__ double s_part[8][C1];
+    __shared__ float s_k[C1];
+    __shared__ float s_red[C2 + C1];
+    const int tid = (int)threadIdx.x;
     if (tid < C2) {
-        const double sc = (double)p.st2.scale[tid], rm2 = (double)p.st2.rstd[tid] * (double)s_m2[tid];
+        const double sc = (double)p.st2.scale[tid], rm2 = (double)p.st2.rstd[tid] * (double)p.m2[tid];
         sd[tid] = sc * rm2;
-        se[tid] = sc * (rm2 * (double)p.st2.mean[tid] - (double)s_m1[tid]);
+        se[tid] = sc * (rm2 * (double)p.st2.mean[tid] - (double)p.m1[tid]);
+        float ev = 1.f;
+#ifndef PGPD_EMU
+        if (p.img1) {
+            const float mx = p.pmx[tid];
+            int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);          // max|dz2[.,c]| 2^e in [2^12, 2^13)
+            e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
+            ev = __uint_as_float((uint32_t)(127 - e) << 23);
+            if (r == 0) { p.esc[tid] = __uint_as_float((uint32_t)(127 + e) << 23); p.einv[tid] = ev; }
+        }
+#endif
+        s_einv[tid] = ev;
     }
     __syncthreads();
-    for (int o = tid; o < C1 * C1; o += 1024) {
-        const int k = o >> 6, kp = o & 63;
+    if (r < C1) {
+        const int kp = tid & 63, ln = tid >> 6;          // 8 lanes x 16 channels
         double a = 0.0;
 #pragma unroll 8
-        for (int c = 0; c < C2; ++c) a += (double)s_w2[c * C1 + k] * sd[c] * (double)s_w2[c * C1 + kp];
-        p.Kmat[o] = (float)a;
-    }
-    if (tid < C1) {
-        double cv = 0.0;
-#pragma unroll 8
-        for (int c = 0; c < C2; ++c) cv += (double)s_w2[c * C1 + tid] * se[c];
-        p.cvec[tid] = (float)cv;
+        for (int c = ln * 16; c < ln * 16 + 16; ++c) a += (double)p.W2[c * C1 + r] * sd[c] * (double)p.W2[c * C1 + kp];
+        s_part[ln][kp] = a;
+        __syncthreads();
+        if (tid < C1) {
+            double t = 0.0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) t += s_part[l][tid];
+            const float kv = (float)t;
+            p.Kmat[r * C1 + tid] = kv;
+            s_k[tid] = kv;
+        } else if (tid < C1 + 32) {
+            const int lane = tid - C1;
+            double cv = 0.0;
+#pragma unroll
+            for (int c = lane; c < C2; c += 32) cv += (double)p.W2[c * C1 + r] * se[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cv += __shfl_xor_sync(0xffffffffu, cv, o);
+            if (lane == 0) p.cvec[r] = (float)cv;
+        }
+        __syncthreads();
     }
 #ifndef PGPD_EMU
     if (!p.img1) return;
-    // ---- esc[c] = 2^e with max|dz2[.,c]| 2^e in [2^12, 2^13)
+    // row r of the two images: 128 + 64 values, common power-of-two scale
+    float v = 0.f;
+    if (tid < C2) v = (r < C1) ? p.W2[tid * C1 + r] * p.st2.scale[tid] * s_einv[tid] : 0.f;
+    else if (tid < C2 + C1) v = (r < C1) ? -s_k[tid - C2] * (1.0f / p.act_scale) : 0.f;
+    if (tid < C2 + C1) s_red[tid] = fabsf(v);
+    __syncthreads();
+    if (tid < C1) s_red[tid] = fmaxf(s_red[tid], s_red[tid + C2]);
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (tid < st) s_red[tid] = fmaxf(s_red[tid], s_red[tid + st]);
+        __syncthreads();
+    }
+    const float mx = s_red[0];
     if (tid < C2) {
-        const float mx = p.pmx[tid];
-        int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-        e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
-        const float ev = __uint_as_float((uint32_t)(127 - e) << 23);
-        p.esc[tid] = __uint_as_float((uint32_t)(127 + e) << 23);
-        p.einv[tid] = ev;
-        s_einv[tid] = ev;
-    }
-    __syncthreads();        // also: Kmat (global, written by this block) is visible to this block
-    // ---- A-operand images of the pass: row k < 64: A1op[k][c] = W2[c][k] s_c einv_c 2^g_k, A2op[k][k'] = -K[k][k'] 2^g_k / 16;
-    // rows 64..127 zero.  One warp per row (lane: 4 columns c of A1op, 2 columns k' of A2op).
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        __half* img1 = (__half*)p.img1;
+        const int e = tc::prepack_elem(v, mx, r, tid, (__half*)p.img1, 0);
+        if (tid == 0) p.ginv[r] = ldexpf(1.f, -e);
+    } else if (tid < C2 + C1) {
+        int ex = 0;
+        if (mx > 0.f) frexpf(mx, &ex);
+        const int e = (mx > 0.f && mx < INFINITY) ? 14 - ex : 0;
+        const int c = tid - C2;
+        const float ks = ldexpf(v, e);
+        const __half hi = __float2half_rn(ks);
+        const __half lo = __float2half_rn(ks - __half2float(hi));
+        const int chunk = c >> 3, within = c & 7;
+        const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
         __half* img2 = (__half*)p.img2;
-        for (int r = warp; r < 128; r += 32) {
-            float w[4], kk[2];
-            float mx = 0.f;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = lane + 32 * u;
-                w[u] = (r < C1) ? s_w2[c * C1 + r] * p.st2.scale[c] * s_einv[c] : 0.f;
-                mx = fmaxf(mx, fabsf(w[u]));
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int kp = lane + 32 * u;
-                kk[u] = (r < C1) ? -p.Kmat[r * C1 + kp] * (1.0f / p.act_scale) : 0.f;
-                mx = fmaxf(mx, fabsf(kk[u]));
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            int e = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) e = tc::prepack_elem(w[u], mx, r, lane + 32 * u, img1, 0);
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int c = lane + 32 * u;
-                const float ks = ldexpf(kk[u], e);
-                const __half hi = __float2half_rn(ks);
-                const __half lo = __float2half_rn(ks - __half2float(hi));
-                const int chunk = c >> 3, within = c & 7;
-                const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
-                img2[off] = hi;
-                img2[8192 + off] = lo;
-            }
-            if (lane == 0) p.ginv[r] = ldexpf(1.f, -e);
-        }
+        img2[off] = hi;
+        img2[8192 + off] = lo;
     }
-#else
-    (void)s_einv;
 #endif
 }
 
@@ -770,22 +775,19 @@ __global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
 //   blocks [0, 48): column slices (256 columns x 4 lanes) of the partial rows of C = sum dz2 a1^T (128 x 64) and
 //                   Gram1 = sum a1 a1^T (64 x 64);
 //   blocks [48, 52): BatchNorm1-backward partial rows (sum dz1, sum dz1 yhat1), 32 columns x 32 lanes each;
-//   last block: dgamma1, dbeta1, m1, m2;  dW2 = diag(s)[C - m1 S1a^T - diag(r m2)(W2 Gram1 - mu2 S1a^T)];  db2 = 0.
+//   last block: dgamma1, dbeta1, m1, m2.   (dW2, which needs C and Gram1 whole, runs as extra blocks of k_kb_l1: dw2_row.)
 struct TailKbParams {
     const float* Cpart; const float* G1part; int n_parts;     // [n_parts][8192], [n_parts][4096]
     float* Cm; float* G1;
     const float* bnpart; int n_bn; double count;              // [n_bn][2][64]
     double* bnsum;                                            // [128] scratch
     float* dgamma1; float* dbeta1; float* m1_1; float* m2_1;
-    const double* S1a; const float* W2; BnState st2; const float* m1_2; const float* m2_2;
-    float* dW2; float* db2;
     unsigned* counter;
 };
 constexpr int TKB_BLOCKS = 52;
 
 __global__ void __launch_bounds__(1024) k_tail_kb(TailKbParams p) {
     __shared__ double sh[32][33];
-    __shared__ float s_g1[C1 * C1];               // 16 KB
     const int tid = (int)threadIdx.x, blk = (int)blockIdx.x;
     if (blk < 48) {
         const int cl = tid & 255, ln = tid >> 8;
@@ -819,24 +821,39 @@ __global__ void __launch_bounds__(1024) k_tail_kb(TailKbParams p) {
         }
     }
     if (!last_block_done(p.counter, gridDim.x)) return;
-    for (int i = tid; i < C1 * C1; i += 1024) s_g1[i] = p.G1[i];
     if (tid < 2 * C1) {
         const double s = p.bnsum[tid];
         if (tid < C1) { p.dbeta1[tid] = (float)s; p.m1_1[tid] = (float)(s / p.count); }
         else { p.dgamma1[tid - C1] = (float)s; p.m2_1[tid - C1] = (float)(s / p.count); }
     }
-    __syncthreads();
-#pragma unroll 2
-    for (int o = tid; o < C2 * C1; o += 1024) {
-        const int c = o >> 6, k = o & 63;
+}
+
+// Row c (0..127) of dW2 = diag(s)[C - m1 S1a^T - diag(r m2)(W2 Gram1 - mu2 S1a^T)], run as extra blocks of k_kb_l1
+// (first 256 threads: 64 columns x 4 lanes over the 64 terms of W2 Gram1); db2 = 0.
+struct Dw2Params {
+    const float* Cm; const float* G1; const double* S1a; const float* W2; BnState st2; const float* m1_2; const float* m2_2;
+    float* dW2; float* db2;
+};
+
+__device__ __forceinline__ void dw2_row(const Dw2Params& p, int c) {
+    __shared__ double s_p[4][C1];
+    const int tid = (int)threadIdx.x;
+    if (tid < 256) {
+        const int k = tid & 63, ln = tid >> 6;
         double wg = 0.0;
 #pragma unroll 8
-        for (int kk = 0; kk < C1; ++kk) wg += (double)p.W2[c * C1 + kk] * (double)s_g1[kk * C1 + k];
-        const double sc = (double)p.st2.scale[c], rm2 = (double)p.st2.rstd[c] * (double)p.m2_2[c];
-        const double v = (double)p.Cm[o] - (double)p.m1_2[c] * p.S1a[k] - rm2 * (wg - (double)p.st2.mean[c] * p.S1a[k]);
-        p.dW2[o] = (float)(sc * v);
+        for (int kk = ln * 16; kk < ln * 16 + 16; ++kk) wg += (double)p.W2[c * C1 + kk] * (double)p.G1[kk * C1 + k];
+        s_p[ln][k] = wg;
     }
-    if (tid < C2 && p.db2) p.db2[tid] = 0.f;     // bias feeding a train-mode BatchNorm: gradient is identically zero
+    __syncthreads();
+    if (tid < C1) {
+        const int k = tid;
+        const double wg = ((s_p[0][k] + s_p[1][k]) + s_p[2][k]) + s_p[3][k];
+        const double sc = (double)p.st2.scale[c], rm2 = (double)p.st2.rstd[c] * (double)p.m2_2[c];
+        const double v = (double)p.Cm[c * C1 + k] - (double)p.m1_2[c] * p.S1a[k] - rm2 * (wg - (double)p.st2.mean[c] * p.S1a[k]);
+        p.dW2[c * C1 + k] = (float)(sc * v);
+        if (k == 0 && p.db2) p.db2[c] = 0.f;     // bias feeding a train-mode BatchNorm: gradient is identically zero
+    }
 }
 
 }  // namespace pgpd

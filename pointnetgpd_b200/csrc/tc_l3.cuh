@@ -657,7 +657,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 240);
     float* s_scale = reinterpret_cast<float*>(misc + 256);
     float* s_shift = s_scale + 128;
-    float* s_ma2 = s_shift + 128;                          // pilot mean of a2 (train mode)
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -675,7 +674,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     }
     if (tid < 128) {
         s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE;
-        s_ma2[tid] = p.s1_pilot ? (float)(p.s1_pilot[tid] * p.inv_n) : 0.f;
     }
     if (warp == 1) tmem_alloc_pair<512>(smem_u32(tmem_slot));
     tc_fence_before_sync();
@@ -802,20 +800,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;      // centred squares of my channel of block mt4 = 0..3, summed over my tiles
         float mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, mu3 = 0.f;      // their centres, in accumulator units
         if (stats) {
-            // centre[c] = W3[c] . mean(a2) (pilot): 4 channels per thread, 128 FMAs each, while the pipeline fills
+            // centre[c] = W3[c] . mean(a2) (pilot) for my 4 x 32 channels: the warp forms one dot product at a time (each lane
+            // 4 consecutive k: coalesced 512-byte row reads, fixed shuffle tree -> the same bits in every warp and pair), lane i
+            // keeps the result of row i.  Runs while the pipeline fills.
+            const float m0 = (float)(p.s1_pilot[4 * lane + 0] * p.inv_n), m1 = (float)(p.s1_pilot[4 * lane + 1] * p.inv_n);
+            const float m2 = (float)(p.s1_pilot[4 * lane + 2] * p.inv_n), m3 = (float)(p.s1_pilot[4 * lane + 3] * p.inv_n);
 #pragma unroll
             for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
-                const float4* wr = reinterpret_cast<const float4*>(p.W3f + (size_t)ch * C2);
-                float sacc = 0.f;
-#pragma unroll 8
-                for (int k4 = 0; k4 < C2 / 4; ++k4) {
-                    const float4 wv = wr[k4];
-                    sacc = fmaf(wv.x, s_ma2[4 * k4 + 0], sacc); sacc = fmaf(wv.y, s_ma2[4 * k4 + 1], sacc);
-                    sacc = fmaf(wv.z, s_ma2[4 * k4 + 2], sacc); sacc = fmaf(wv.w, s_ma2[4 * k4 + 3], sacc);
+                const int chb = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + q * 32;
+                float mine = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    const float4 wv = *reinterpret_cast<const float4*>(p.W3f + (size_t)(chb + i) * C2 + 4 * lane);
+                    float sacc = fmaf(wv.x, m0, fmaf(wv.y, m1, fmaf(wv.z, m2, wv.w * m3)));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (lane == i) mine = sacc;
                 }
-                if (half == 0) p.centre_out[ch] = sacc;          // every pair writes the same value
-                const float m = sacc / p.inv[ch];
+                const int ch = chb + lane;
+                if (half == 0) p.centre_out[ch] = mine;          // every pair writes the same value
+                const float m = mine / p.inv[ch];
                 if (mt4 == 0) mu0 = m; else if (mt4 == 1) mu1 = m; else if (mt4 == 2) mu2 = m; else mu3 = m;
             }
         }

@@ -19,8 +19,8 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include "l2bwd.cuh"
 #include "tails.cuh"
+#include "l2bwd.cuh"
 #ifndef PGPD_EMU
 #include "tc_l3.cuh"
 #include "tc_stream.cuh"
@@ -78,6 +78,7 @@ struct TowerScratch {
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
     float* pmax;      // [1024][2][128] per-epilogue-row maxima of |dz2|, |yhat2|
+    float* pmx;       // [128] per-channel max |dz2| (reduced from pmax)
     float* esc;       // [128] per-channel power-of-two scale of dy2 (tcgen05 dW2)
     float* einv;      // [128] its inverse
     // backward scratch
@@ -171,6 +172,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
     w.pmax = c.take<float>((size_t)1024 * 2 * C2);
+    w.pmx = c.take<float>(C2);
     w.esc = c.take<float>(C2);
     w.einv = c.take<float>(C2);
     if (backward) {
@@ -390,12 +392,16 @@ struct ProbGram {
 };
 
 // dW3[c][k] = sum_b coef[b][c] a2[argmax(b,c)][k]  -  d[c] * (W3 Gram)[c][k]  -  e[c] * S1[k]
-// grid = 1024 channels, block = 512 = 16 cloud lanes (warps) x 32 lanes of 4 consecutive k (one 16-byte load per lane and
+// grid = 1024 channels (+ extra blocks, see below), block = 512 = 16 cloud lanes (warps) x 32 lanes of 4 consecutive k (one 16-byte load per lane and
 // arg-max row, four rows in flight per warp); the 16 cloud lanes are summed in a fixed order.  The row c of W3 * Gram
 // (128 x 128, L2-resident) is formed here by warp 0 instead of by a separate 1024 x 128 x 128 GEMM launch.
+// Blocks [1024, gridDim.x) are a different job that merely shares the launch: rows of the precompute of the fused layer-2/1
+// backward pass (tails.cuh: kb_prep_row), which like dW3 only depends on the tail of pass A.
 __global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ Y2, BnState st2,
                       int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec, const float* __restrict__ W3,
-                      const float* __restrict__ gram, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3) {
+                      const float* __restrict__ gram, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3,
+                      KbPrepParams kp) {
+    if ((int)blockIdx.x >= C3) { kb_prep_row(kp, (int)blockIdx.x - C3); return; }
     __shared__ float4 sh[16][32];
     __shared__ float s_cf[512];
     __shared__ int s_ix[512];
@@ -744,9 +750,10 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
 
     // ---- pass A: d a2 -> dz2 (stored), BatchNorm2 backward sums, Gram matrix of a2 --------------------------------------------
     TailKaParams tk{};
-    tk.g2 = w.gram2; tk.gram = w.gram; tk.count = count; tk.bnsum = w.rtmp; tk.pmx = w.esc;   // esc doubles as the scratch of the maxima
-    tk.dgamma = g.bn[1].dgamma; tk.dbeta = g.bn[1].dbeta; tk.m1 = w.m1_2; tk.m2 = w.m2_2;
-    tk.W2 = t.conv[1].w; tk.st2 = w.bn[1]; tk.Kmat = w.Kmat; tk.cvec = w.cvec; tk.counter = w.counters + 3;
+    tk.g2 = w.gram2; tk.gram = w.gram; tk.count = count; tk.bnsum = w.rtmp; tk.pmx = w.pmx;
+    tk.dgamma = g.bn[1].dgamma; tk.dbeta = g.bn[1].dbeta; tk.m1 = w.m1_2; tk.m2 = w.m2_2; tk.counter = w.counters + 3;
+    KbPrepParams kp{};
+    kp.W2 = t.conv[1].w; kp.st2 = w.bn[1]; kp.m1 = w.m1_2; kp.m2 = w.m2_2; kp.Kmat = w.Kmat; kp.cvec = w.cvec;
     int g_b4 = 0;       // rows of pmax written by the tcgen05 pass-A kernel
 #ifndef PGPD_EMU
     if (tcp) {
@@ -757,8 +764,9 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         g_b4 = grid * tc::KA_EPI_ROWS;
         tk.gpart = w.fpart; tk.n_g = grid; tk.gcols = 2 * C2 * C2; tk.sym = 1;      // per-CTA hi.hi / hi.lo accumulators
         tk.bnpart = w.ka_part; tk.n_bn = g_b4;
-        tk.pmax = w.pmax; tk.n_pm = g_b4; tk.esc = w.esc; tk.einv = w.einv;
-        tk.img1 = w.wimg_kb; tk.img2 = (unsigned char*)w.wimg_kb + tc::KB_A1_BYTES; tk.ginv = w.inv_s; tk.act_scale = tc::ACT_SCALE;
+        tk.pmax = w.pmax; tk.n_pm = g_b4; tk.act_scale = tc::ACT_SCALE;
+        kp.pmx = w.pmx; kp.esc = w.esc; kp.einv = w.einv;
+        kp.img1 = w.wimg_kb; kp.img2 = (unsigned char*)w.wimg_kb + tc::KB_A1_BYTES; kp.ginv = w.inv_s; kp.act_scale = tc::ACT_SCALE;
     } else
 #endif
     {
@@ -774,8 +782,8 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     launch(k_tail_ka, dim3(tk.gcols / 256 + 8 + (tcp ? 4 : 0)), dim3(1024), 0, s, tk);
 
     // ---- dW3 ---------------------------------------------------------------------------------------------------------------
-    launch(k_dw3, dim3(C3), dim3(512), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
-           (const float*)w.dvec, (const float*)w.evec, t.conv[2].w, (const float*)w.gram, (const double*)w.S1, g.conv[2].dw, g.conv[2].db);
+    launch(k_dw3, dim3(C3 + (tcp ? C2 : C1)), dim3(512), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
+           (const float*)w.dvec, (const float*)w.evec, t.conv[2].w, (const float*)w.gram, (const double*)w.S1, g.conv[2].dw, g.conv[2].db, kp);
 
     // ---- layers 2 and 1: one fused pass over (dz2, a1) (l2bwd.cuh / tc_kb.cuh) -------------------------------------------------
     int nparts = 0, nrows = 0, rpc = 0;
@@ -800,13 +808,15 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     }
     {
         TailKbParams p{w.kb_Cpart, w.kb_G1part, nparts, w.kbC, w.kbG1, w.kb_bn, nrows, count, w.rtmp,
-                       g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1, w.S1a, t.conv[1].w, w.bn[1], w.m1_2, w.m2_2,
-                       g.conv[1].dw, g.conv[1].db, w.counters + 4};
+                       g.bn[0].dgamma, g.bn[0].dbeta, w.m1_1, w.m2_1, w.counters + 4};
         launch(k_tail_kb, dim3(TKB_BLOCKS), dim3(1024), 0, s, p);
     }
-    launch(k_kb_l1, dim3(a.B), dim3(768), 0, s, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
-           (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr, w.counters + 5,
-           g.conv[0].dw, g.conv[0].db);
+    {
+        Dw2Params d{w.kbC, w.kbG1, w.S1a, t.conv[1].w, w.bn[1], w.m1_2, w.m2_2, g.conv[1].dw, g.conv[1].db};
+        launch(k_kb_l1, dim3(a.B + C2), dim3(768), 0, s, a.B, (const float*)w.kb_H, rpc, (const double*)w.xmom, a.trans, t.conv[0].w, w.bn[0],
+               (const float*)w.m1_1, (const float*)w.m2_1, w.fpart, a.trans ? dtrans_out : (float*)nullptr, w.counters + 5,
+               g.conv[0].dw, g.conv[0].db, d);
+    }
 }
 
 }  // namespace pgpd
