@@ -53,6 +53,13 @@ extern "C" {
 #define PGPD_F_TRAIN   0x1        /* module.training: batch statistics + running-stat update   */
 #define PGPD_F_SAVE    0x2        /* keep what pgpd_backward needs in the workspace            */
 #define PGPD_F_SIMT    0x100      /* force the fp32 CUDA-core kernels (no tcgen05); debugging  */
+/* pgpd_backward in two calls, so that a data-parallel caller can start the gradient exchange of the first half while the
+ * second half is still being computed (main_1v.py:163-165 wraps the model in nn.DataParallel):
+ *   PGPD_F_BWD_HEAD : classifier head + trunk tower (+ the gradient reaching the T-Net output); needs dout
+ *   PGPD_F_BWD_STN  : T-Net head + T-Net tower; must follow a PGPD_F_BWD_HEAD call on the same workspace
+ * neither bit (or both): the whole backward in one call.  Only meaningful for PGPD_FEAT / PGPD_CLS. */
+#define PGPD_F_BWD_HEAD 0x10
+#define PGPD_F_BWD_STN  0x20
 
 /* nn.Conv1d(k=1) / nn.Linear (pointnet.py:12-18,127-129,182-184) */
 typedef struct pgpd_lin {

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libpgpd.so")
 
 PGPD_STN, PGPD_FEAT, PGPD_CLS = 1, 2, 3
 F_TRAIN, F_SAVE, F_SIMT = 0x1, 0x2, 0x100
+F_BWD_HEAD, F_BWD_STN = 0x10, 0x20
 E_ARG, E_WORKSPACE, E_BATCH1, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
 _fp = C.c_void_p  # device pointers travel as integers

@@ -17,7 +17,7 @@ namespace pgpd {
 
 constexpr size_t HEAD_PART_ELEMS = (size_t)4 << 20;   // 16 MB of fp32 split-K partials per buffer (two buffers)
 constexpr int HEAD_AMAX_BLOCKS = 64;                  // partial maxima per weight matrix (forward operand scales)
-constexpr int HEAD_AMAX_ELEMS = 2 * HEAD_AMAX_BLOCKS + 2 * 16;   // [fc1.weight | fc2.weight] x 64, [dU1 | dU2] x 16
+constexpr int HEAD_AMAX_ELEMS = 2 * HEAD_AMAX_BLOCKS + H1 / 8 + H2 / 8;   // [fc1.weight | fc2.weight] x 64, dU1 x 64, dU2 x 32 (one per BatchNorm-backward block)
 
 struct HeadWs {
     float* U1;        // [B][512]  bias-free pre-activation of fc1
@@ -124,26 +124,48 @@ inline int run_gemm_tc(tc::GemmOp A, tc::GemmOp Bo, int M, int N, int K, float* 
 // U[b][c] = sum_z part[z][b][c] (fixed order; written out, the backward needs it); train: batch statistics of U[:,c]
 // (two-pass, double) -> finalisation + running statistics; eval: folded running statistics; H = relu(scale*U + shift).
 // limit: an activation beyond it (the fp16 operand range of the tensor-core GEMM that consumes H) is replaced by NaN
-// instead of being clamped silently.  block = 32 channels x 32 row lanes (fixed-order reduction: deterministic).
+// instead of being clamped silently.
+// block = 1024 = BNH_CH channels x BNH_LANES row lanes (lane sums in row order, lanes added in order: deterministic); a thread
+// keeps its rows in registers across the three passes when the batch allows (B <= BNH_LANES * BNH_RMAX), else re-reads U.
+constexpr int BNH_CH = 8, BNH_LANES = 128, BNH_RMAX = 8;
+
 __global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ part, int nsl, int B, int C, int train,
                                                       const float* bias, pgpd_bn bn, BnState st, float limit,
                                                       float* __restrict__ U, float* __restrict__ Hout) {
-    __shared__ double sh[32][33];
-    __shared__ double smean[32];
-    __shared__ float s_sc[32], s_sf[32];
-    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
-    const int c = (int)blockIdx.x * 32 + cx;
+    __shared__ double sh[BNH_LANES][BNH_CH + 1];
+    __shared__ double smean[BNH_CH];
+    __shared__ float s_sc[BNH_CH], s_sf[BNH_CH];
+    const int tid = (int)threadIdx.x, cx = tid & (BNH_CH - 1), ry = tid >> 3;
+    const int c = (int)blockIdx.x * BNH_CH + cx;
     const size_t slice = (size_t)B * C;
+    const bool inreg = B <= BNH_LANES * BNH_RMAX;
+    float ur[BNH_RMAX];
     double s = 0.0;
     if (c < C) {
-#pragma unroll 2
-        for (int b = ry; b < B; b += 32) {
-            const size_t i = (size_t)b * C + c;
-            float u = part[i];
+        if (inreg) {
+#pragma unroll
+            for (int i = 0; i < BNH_RMAX; ++i) {
+                const int b = ry + BNH_LANES * i;
+                ur[i] = 0.f;
+                if (b < B) {
+                    const size_t e = (size_t)b * C + c;
+                    float u = part[e];
 #pragma unroll 8
-            for (int z = 1; z < nsl; ++z) u += part[(size_t)z * slice + i];      // loads are independent of the running sum
-            U[i] = u;
-            s += (double)u;
+                    for (int z = 1; z < nsl; ++z) u += part[(size_t)z * slice + e];      // loads are independent of the running sum
+                    U[e] = u;
+                    ur[i] = u;
+                    s += (double)u;
+                }
+            }
+        } else {
+            for (int b = ry; b < B; b += BNH_LANES) {
+                const size_t e = (size_t)b * C + c;
+                float u = part[e];
+#pragma unroll 8
+                for (int z = 1; z < nsl; ++z) u += part[(size_t)z * slice + e];
+                U[e] = u;
+                s += (double)u;
+            }
         }
     }
     if (train) {
@@ -151,19 +173,28 @@ __global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ 
         __syncthreads();
         if (ry == 0) {
             double t = 0.0;
-            for (int q = 0; q < 32; ++q) t += sh[q][cx];
+#pragma unroll 8
+            for (int q = 0; q < BNH_LANES; ++q) t += sh[q][cx];
             smean[cx] = t / B;
         }
         __syncthreads();
         const double mean = smean[cx];
         double v = 0.0;
-        if (c < C)
-            for (int b = ry; b < B; b += 32) { const double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
+        if (c < C) {
+            if (inreg) {
+#pragma unroll
+                for (int i = 0; i < BNH_RMAX; ++i)
+                    if (ry + BNH_LANES * i < B) { const double d = (double)ur[i] - mean; v += d * d; }
+            } else {
+                for (int b = ry; b < B; b += BNH_LANES) { const double d = (double)U[(size_t)b * C + c] - mean; v += d * d; }
+            }
+        }
         sh[ry][cx] = v;
         __syncthreads();
         if (ry == 0 && c < C) {
             double t = 0.0;
-            for (int q = 0; q < 32; ++q) t += sh[q][cx];
+#pragma unroll 8
+            for (int q = 0; q < BNH_LANES; ++q) t += sh[q][cx];
             bn_finalize_train(c, mean, t / B, (double)B, bias, bn, st);
             s_sc[cx] = st.scale[c]; s_sf[cx] = st.shift[c];
         }
@@ -177,10 +208,22 @@ __global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ 
     if (c < C) {
         const float sc = s_sc[cx], sf = s_sf[cx];
         const float qnan = __uint_as_float(0x7FC00000u);
-        for (int b = ry; b < B; b += 32) {
-            float h = relu_nan(sc * U[(size_t)b * C + c] + sf);
-            if (!(h <= limit)) h = qnan;
-            Hout[(size_t)b * C + c] = h;
+        if (inreg) {
+#pragma unroll
+            for (int i = 0; i < BNH_RMAX; ++i) {
+                const int b = ry + BNH_LANES * i;
+                if (b < B) {
+                    float h = relu_nan(sc * ur[i] + sf);
+                    if (!(h <= limit)) h = qnan;
+                    Hout[(size_t)b * C + c] = h;
+                }
+            }
+        } else {
+            for (int b = ry; b < B; b += BNH_LANES) {
+                float h = relu_nan(sc * U[(size_t)b * C + c] + sf);
+                if (!(h <= limit)) h = qnan;
+                Hout[(size_t)b * C + c] = h;
+            }
         }
     }
 }
@@ -273,40 +316,63 @@ __global__ void __launch_bounds__(1024) k_fc3_bwd(const float* __restrict__ dO, 
 // dz[b][c] = sum_z part[z][b][c] masked by H[b][c] > 0 (part != null: the dZ GEMM's split-K partials) or DZ as given;
 // sums -> dgamma, dbeta; dU = s*(dz - m1 - yhat*m2) written to DZ; db (the Linear bias feeding this BatchNorm) = 0;
 // amax_part[block] = max |dU| of the block (operand scale of the tcgen05 GEMMs that consume dU).
-// block = 32 channels x 32 row lanes.
+// block = 1024 = BNH_CH channels x BNH_LANES row lanes; rows kept in registers between the two passes when B allows.
 __device__ __forceinline__ void bn_head_bwd_block(int blk, const float* __restrict__ part, int nsl, const float* __restrict__ Hmask,
                                                   float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db,
                                                   unsigned* __restrict__ amax_part) {
-    __shared__ double sh1[32][33], sh2[32][33];
-    __shared__ float sm1[32], sm2[32];
+    __shared__ double sh1[BNH_LANES][BNH_CH + 1], sh2[BNH_LANES][BNH_CH + 1];
+    __shared__ float sm1[BNH_CH], sm2[BNH_CH];
     __shared__ float smx[32];
-    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
-    const int c = blk * 32 + cx;
+    const int tid = (int)threadIdx.x, cx = tid & (BNH_CH - 1), ry = tid >> 3;
+    const int c = blk * BNH_CH + cx;
     const float mu = c < C ? st.mean[c] : 0.f, r = c < C ? st.rstd[c] : 0.f, sc = c < C ? st.scale[c] : 0.f;
     const size_t slice = (size_t)B * C;
+    const bool inreg = B <= BNH_LANES * BNH_RMAX;
+    float dzr[BNH_RMAX], yhr[BNH_RMAX];
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-        for (int b = ry; b < B; b += 32) {
-            const size_t i = (size_t)b * C + c;
-            float dzf;
-            if (part) {
-                dzf = part[i];
+        if (inreg) {
+#pragma unroll
+            for (int i = 0; i < BNH_RMAX; ++i) {
+                const int b = ry + BNH_LANES * i;
+                dzr[i] = 0.f; yhr[i] = 0.f;
+                if (b < B) {
+                    const size_t e = (size_t)b * C + c;
+                    float dzf;
+                    if (part) {
+                        dzf = part[e];
 #pragma unroll 8
-                for (int z = 1; z < nsl; ++z) dzf += part[(size_t)z * slice + i];
-                if (!(Hmask[i] > 0.f)) dzf = 0.f;
-                DZ[i] = dzf;
-            } else dzf = DZ[i];
-            const double dz = (double)dzf;
-            const double yhat = (double)((U[i] - mu) * r);
-            s1 += dz; s2 += dz * yhat;
+                        for (int z = 1; z < nsl; ++z) dzf += part[(size_t)z * slice + e];
+                        if (!(Hmask[e] > 0.f)) dzf = 0.f;
+                    } else dzf = DZ[e];
+                    const float yh = (U[e] - mu) * r;
+                    dzr[i] = dzf; yhr[i] = yh;
+                    s1 += (double)dzf; s2 += (double)dzf * (double)yh;
+                }
+            }
+        } else {
+            for (int b = ry; b < B; b += BNH_LANES) {
+                const size_t e = (size_t)b * C + c;
+                float dzf;
+                if (part) {
+                    dzf = part[e];
+#pragma unroll 8
+                    for (int z = 1; z < nsl; ++z) dzf += part[(size_t)z * slice + e];
+                    if (!(Hmask[e] > 0.f)) dzf = 0.f;
+                    DZ[e] = dzf;
+                } else dzf = DZ[e];
+                const double yhat = (double)((U[e] - mu) * r);
+                s1 += (double)dzf; s2 += (double)dzf * yhat;
+            }
         }
     }
     sh1[ry][cx] = s1; sh2[ry][cx] = s2;
     __syncthreads();
     if (ry == 0) {
         double t1 = 0.0, t2 = 0.0;
-        for (int q = 0; q < 32; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
+#pragma unroll 8
+        for (int q = 0; q < BNH_LANES; ++q) { t1 += sh1[q][cx]; t2 += sh2[q][cx]; }
         if (c < C) { dgamma[c] = (float)t2; dbeta[c] = (float)t1; if (db) db[c] = 0.f; }
         sm1[cx] = (float)(t1 / B); sm2[cx] = (float)(t2 / B);
     }
@@ -314,18 +380,30 @@ __device__ __forceinline__ void bn_head_bwd_block(int blk, const float* __restri
     float mx = 0.f;
     if (c < C) {
         const float m1 = sm1[cx], m2 = sm2[cx];
-        for (int b = ry; b < B; b += 32) {
-            const size_t i = (size_t)b * C + c;
-            const float yhat = (U[i] - mu) * r;
-            const float du = sc * (DZ[i] - m1 - yhat * m2);
-            DZ[i] = du;
-            mx = fmaxf(mx, fabsf(du));
+        if (inreg) {
+#pragma unroll
+            for (int i = 0; i < BNH_RMAX; ++i) {
+                const int b = ry + BNH_LANES * i;
+                if (b < B) {
+                    const float du = sc * (dzr[i] - m1 - yhr[i] * m2);
+                    DZ[(size_t)b * C + c] = du;
+                    mx = fmaxf(mx, fabsf(du));
+                }
+            }
+        } else {
+            for (int b = ry; b < B; b += BNH_LANES) {
+                const size_t e = (size_t)b * C + c;
+                const float yhat = (U[e] - mu) * r;
+                const float du = sc * (DZ[e] - m1 - yhat * m2);
+                DZ[e] = du;
+                mx = fmaxf(mx, fabsf(du));
+            }
         }
     }
     if (amax_part) {     // max |dU| of this block (max is order-independent: deterministic)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (cx == 0) smx[ry] = mx;
+        if ((tid & 31) == 0) smx[tid >> 5] = mx;
         __syncthreads();
         if (tid == 0) {
             float m = smx[0];
@@ -413,7 +491,7 @@ inline void head_forward(const HeadArgs& a, HeadWs& w, float* user_out, float* l
     } else
 #endif
     nsl = run_plain(ProbPlain<true, false>{a.X, h.fc[0].w, w.partA, B, H1, C3, (size_t)C3, 1, 1, (size_t)C3, 0}, s, 8);
-    launch(k_bn_head_fwd, grid1d(H1, 32), dim3(1024), 0, s, (const float*)w.partA, nsl, B, H1, a.train ? 1 : 0, h.fc[0].b, h.bn[0], w.bn[0],
+    launch(k_bn_head_fwd, grid1d(H1, BNH_CH), dim3(1024), 0, s, (const float*)w.partA, nsl, B, H1, a.train ? 1 : 0, h.fc[0].b, h.bn[0], w.bn[0],
            limit, w.U1, w.Hm1);
     // fc2
 #ifndef PGPD_EMU
@@ -423,7 +501,7 @@ inline void head_forward(const HeadArgs& a, HeadWs& w, float* user_out, float* l
     else
 #endif
     nsl = run_plain(ProbPlain<true, false>{w.Hm1, h.fc[1].w, w.partB, B, H2, H1, (size_t)H1, 1, 1, (size_t)H1, 0}, s, 4);
-    launch(k_bn_head_fwd, grid1d(H2, 32), dim3(1024), 0, s, (const float*)w.partB, nsl, B, H2, a.train ? 1 : 0, h.fc[1].b, h.bn[1], w.bn[1],
+    launch(k_bn_head_fwd, grid1d(H2, BNH_CH), dim3(1024), 0, s, (const float*)w.partB, nsl, B, H2, a.train ? 1 : 0, h.fc[1].b, h.bn[1], w.bn[1],
            INFINITY, w.U2, w.Hm2);
     // fc3 (+ bias, + identity for the T-Net, + log_softmax for the classifier)
     launch(k_fc3_out, grid1d(B, 8), dim3(256), 0, s, (const float*)w.Hm2, h.fc[2].w, h.fc[2].b, B, a.out, a.is_stn ? 1 : 0, w.out,
@@ -439,20 +517,20 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
 #ifndef PGPD_EMU
     tcg = a.use_tc;
 #endif
-    unsigned* amax_du1 = w.amax + 2 * HEAD_AMAX_BLOCKS;        // [16] partial max |dU1| (512 channels / 32)
-    unsigned* amax_du2 = amax_du1 + 16;                        // [8 of 16]
+    unsigned* amax_du1 = w.amax + 2 * HEAD_AMAX_BLOCKS;        // [H1 / 8] partial max |dU1|
+    unsigned* amax_du2 = amax_du1 + H1 / BNH_CH;               // [H2 / 8]
     // ---- fc3: dW3, db3, dz2
     launch(k_fc3_bwd, dim3(J3 + idiv_up(B, 32)), dim3(1024), 0, s, (const float*)w.dO, (const float*)w.Hm2, h.fc[2].w, B, J3,
            g.fc[2].dw, g.fc[2].db, w.DZ2);
-    launch(k_bn_head_bwd, grid1d(H2, 32), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta,
+    launch(k_bn_head_bwd, grid1d(H2, BNH_CH), dim3(1024), 0, s, w.DZ2, (const float*)w.U2, B, H2, w.bn[1], g.bn[1].dgamma, g.bn[1].dbeta,
            g.fc[1].db, tcg ? amax_du2 : (unsigned*)nullptr);
     // ---- fc2 (w.DZ2 now holds dU2):  dW2 = dU2^T Hm1,  dz1 = (dU2 W2) masked by Hm1 > 0
     int nslW = 0, nslZ = 0;
 #ifndef PGPD_EMU
     if (tcg) {
-        nslW = run_gemm_tc(tc::GemmOp{w.DZ2, H2, 1, amax_du2, H2 / 32, 1.f}, tc::GemmOp{w.Hm1, H1, 1, nullptr, 0, tc::ACT_SCALE}, H2, H1, B,
+        nslW = run_gemm_tc(tc::GemmOp{w.DZ2, H2, 1, amax_du2, H2 / BNH_CH, 1.f}, tc::GemmOp{w.Hm1, H1, 1, nullptr, 0, tc::ACT_SCALE}, H2, H1, B,
                            w.partA, 0, s);
-        nslZ = run_gemm_tc(tc::GemmOp{w.DZ2, H2, 0, amax_du2, H2 / 32, 1.f},
+        nslZ = run_gemm_tc(tc::GemmOp{w.DZ2, H2, 0, amax_du2, H2 / BNH_CH, 1.f},
                            tc::GemmOp{h.fc[1].w, H1, 1, w.amax + HEAD_AMAX_BLOCKS, HEAD_AMAX_BLOCKS, 1.f}, B, H1, H2, w.partB, 0, s);
     } else
 #endif
@@ -461,7 +539,7 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
         nslZ = run_plain(ProbPlain<true, true>{w.DZ2, h.fc[1].w, w.partB, B, H1, H2, (size_t)H2, 1, (size_t)H1, 1, 0}, s, 0);
     }
     {
-        const int nbn = idiv_up(H1, 32);
+        const int nbn = idiv_up(H1, BNH_CH);
         const size_t nW = (size_t)H2 * H1;
         launch(k_head_mid, dim3(nbn + (unsigned)((nW + 1023) / 1024)), dim3(1024), 0, s, nbn, (const float*)w.partB, nslZ, (const float*)w.Hm1,
                w.DZ1, (const float*)w.U1, B, H1, w.bn[0], g.bn[0].dgamma, g.bn[0].dbeta, g.fc[0].db, tcg ? amax_du1 : (unsigned*)nullptr,
@@ -471,9 +549,9 @@ inline void head_backward(const HeadArgs& a, HeadWs& w, const pgpd_head_grad& g,
     int nsl1 = 0, nslX = 0;
 #ifndef PGPD_EMU
     if (tcg) {
-        nsl1 = run_gemm_tc(tc::GemmOp{w.DZ1, H1, 1, amax_du1, H1 / 32, 1.f}, tc::GemmOp{a.X, C3, 1, nullptr, 0, tc::ACT_SCALE}, H1, C3, B,
+        nsl1 = run_gemm_tc(tc::GemmOp{w.DZ1, H1, 1, amax_du1, H1 / BNH_CH, 1.f}, tc::GemmOp{a.X, C3, 1, nullptr, 0, tc::ACT_SCALE}, H1, C3, B,
                            w.partA, 0, s);
-        nslX = run_gemm_tc(tc::GemmOp{w.DZ1, H1, 0, amax_du1, H1 / 32, 1.f}, tc::GemmOp{h.fc[0].w, C3, 1, w.amax, HEAD_AMAX_BLOCKS, 1.f}, B, C3, H1,
+        nslX = run_gemm_tc(tc::GemmOp{w.DZ1, H1, 0, amax_du1, H1 / BNH_CH, 1.f}, tc::GemmOp{h.fc[0].w, C3, 1, w.amax, HEAD_AMAX_BLOCKS, 1.f}, B, C3, H1,
                            w.partB, 0, s);
     } else
 #endif

@@ -217,31 +217,36 @@ int pgpd_backward(int what, const pgpd_model* m, const pgpd_model_grad* g, const
     if (rc) return rc;
     if (!g) return fail(PGPD_E_ARG, "null gradient struct");
     if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
-    if (what != PGPD_STN && !dout) return fail(PGPD_E_ARG, "dout is null");
+    if (what != PGPD_STN && !dout && !((flags & PGPD_F_BWD_STN) && !(flags & PGPD_F_BWD_HEAD))) return fail(PGPD_E_ARG, "dout is null");
     if (what == PGPD_STN && !dtrans) return fail(PGPD_E_ARG, "dtrans is null");
     if (B == 1) return fail(PGPD_E_BATCH1, "batch of 1 in training mode");
     plan_model(workspace, what, B, N, k, flags, w);
     cudaStream_t s = (cudaStream_t)stream;
 
-    const float* dT_total = dtrans;   // gradient reaching the STN output
+    const bool split = what >= PGPD_FEAT && ((flags & PGPD_F_BWD_HEAD) != 0) != ((flags & PGPD_F_BWD_STN) != 0);
+    const bool do_head = !split || (flags & PGPD_F_BWD_HEAD), do_stn = !split || (flags & PGPD_F_BWD_STN);
     if (what >= PGPD_FEAT) {
-        const float* dG = dout;
-        if (what == PGPD_CLS) {
-            launch(k_log_softmax_bwd, grid1d(B, 128), dim3(128), 0, s, (const float*)w.logp, dout, B, k, w.cls_h.dO);
-            HeadArgs hb{&m->cls_head, w.G, B, k, true, false, s, head_tc(flags)};
-            head_backward(hb, w.cls_h, g->cls_head, w.dG);
-            dG = w.dG;
+        if (do_head) {
+            const float* dG = dout;
+            if (what == PGPD_CLS) {
+                launch(k_log_softmax_bwd, grid1d(B, 128), dim3(128), 0, s, (const float*)w.logp, dout, B, k, w.cls_h.dO);
+                HeadArgs hb{&m->cls_head, w.G, B, k, true, false, s, head_tc(flags)};
+                head_backward(hb, w.cls_h, g->cls_head, w.dG);
+                dG = w.dG;
+            }
+            TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, true, true, s, want_tc(flags)};
+            run_tower_bwd(tb, w.trunk_t, g->trunk, dG, w.dT, flags);
+            launch(k_add_opt, grid1d((size_t)B * 9, 128), dim3(128), 0, s, (const float*)w.dT, dtrans, w.stn_h.dO, (size_t)B * 9);
         }
-        TowerArgs tb{&m->trunk, x, w.stn_h.out, B, N, false, true, true, s, want_tc(flags)};
-        run_tower_bwd(tb, w.trunk_t, g->trunk, dG, w.dT, flags);
-        launch(k_add_opt, grid1d((size_t)B * 9, 128), dim3(128), 0, s, (const float*)w.dT, dtrans, w.stn_h.dO, (size_t)B * 9);
     } else {
-        cudaMemcpyAsync(w.stn_h.dO, dT_total, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(w.stn_h.dO, dtrans, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     }
-    HeadArgs ha{&m->stn_head, w.g_stn, B, 9, true, true, s, head_tc(flags)};
-    head_backward(ha, w.stn_h, g->stn_head, w.dg_stn);
-    TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, true, true, s, want_tc(flags)};
-    run_tower_bwd(ta, w.stn_t, g->stn_tower, w.dg_stn, nullptr, flags);
+    if (do_stn) {
+        HeadArgs ha{&m->stn_head, w.g_stn, B, 9, true, true, s, head_tc(flags)};
+        head_backward(ha, w.stn_h, g->stn_head, w.dg_stn);
+        TowerArgs ta{&m->stn_tower, x, nullptr, B, N, true, true, true, s, want_tc(flags)};
+        run_tower_bwd(ta, w.stn_t, g->stn_tower, w.dg_stn, nullptr, flags);
+    }
     return check_cuda("pgpd_backward");
 }
 

@@ -18,7 +18,7 @@ namespace pgpd {
 
 constexpr int PRE_THREADS = 256;
 constexpr int A1_CHUNK = 64;        // points per staging chunk of k_a1
-constexpr int A1_CPB = 16;          // chunks per block: one partial row of the a1 sums per 1024 points
+constexpr int A1_CPB = 8;           // chunks per block: one partial row of the a1 sums per 512 points
 
 // ================================================================================================
 // F1: k_tower_pre -- everything a tower forward needs before its first per-point kernel
@@ -204,15 +204,15 @@ __global__ void __launch_bounds__(PRE_THREADS) k_tower_pre(PreParams p) {
 
 // ================================================================================================
 // k_a1: a1 = relu(scale1 * (W1 T^T x) + shift1), stored [M][64]  (+ train: sum of a1 -> S1a, mean(u2) = W2 mean(a1))
-// grid = (ceil(N / 1024), clouds), block = 1024 threads = 64 channels x 16 point slots; chunks of 64 points are staged
-// (transformed) in shared memory.  Train mode: every block writes one partial row of the a1 sums; the LAST block sums the
-// rows (64 columns x 16 lanes, fixed order, double) and propagates the mean through conv2: mean(u2) = W2 mean(a1) -- the
+// grid = (ceil(N / 512), clouds), block = 512 threads = 64 channels x 8 point slots; the block's points are staged
+// (transformed) in shared memory once.  Train mode: every block writes one partial row of the a1 sums; the LAST block sums the
+// rows (64 columns x 8 lanes, fixed order, double) and propagates the mean through conv2: mean(u2) = W2 mean(a1) -- the
 // centre of layer 2's sum of squares.
 // `limit`: activations above it (or NaN) flag the cloud in bad[] (tensor-core path: the fp16 operand range).
 // Rule for every tail in this file: a serial loop over partial rows is a chain of L2 round trips (~0.4 us each), so rows are
 // spread over many lanes and the loops are unrolled 8-fold (8 loads in flight per thread).
 // ================================================================================================
-constexpr int A1_THREADS = 1024;
+constexpr int A1_THREADS = 512;
 struct A1Params {
     const float* x; const float* trans; int B, N;
     const float* W1; BnState st; float* A1;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
     __shared__ float xs[3][A1_CHUNK * A1_CPB];
     __shared__ double sh[A1_THREADS];
     __shared__ double vs[C1];
-    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;      // q = 0..15
+    const int tid = (int)threadIdx.x, k = tid & 63, q = tid >> 6;      // q = 0..7
     const int b = (int)blockIdx.y;
     const float w0 = p.W1[k * 3 + 0], w1 = p.W1[k * 3 + 1], w2 = p.W1[k * 3 + 2];
     const float sc = p.st.scale[k], sh_ = p.st.shift[k];
@@ -251,9 +251,9 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
     float acc = 0.f;
     bool flag = false;
     float* out = p.A1 + ((size_t)b * p.N + n0) * C1 + k;
-    // thread (k, q): points q, q+16, ... : a half warp writes one 128-byte segment per point
+    // thread (k, q): points q, q+8, ... : a warp writes one 128-byte segment of a point's row
 #pragma unroll 8
-    for (int pp = q; pp < nv; pp += 16) {
+    for (int pp = q; pp < nv; pp += 8) {
         const float u = w0 * xs[0][pp] + w1 * xs[1][pp] + w2 * xs[2][pp];
         const float a = relu_nan(sc * u + sh_);
         flag = flag || !(a <= p.limit);
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
     if (tid < 64) {
         double t = 0.0;
 #pragma unroll
-        for (int l = 0; l < 16; ++l) t += sh[l * 64 + tid];
+        for (int l = 0; l < A1_THREADS / 64; ++l) t += sh[l * 64 + tid];
         p.part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C1 + tid] = t;
     }
     if (!last_block_done(p.counter, nblk)) return;
@@ -276,13 +276,13 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
     {
         double s = 0.0;
 #pragma unroll 8
-        for (unsigned r = (unsigned)q; r < nblk; r += 16) s += p.part[(size_t)r * C1 + k];
+        for (unsigned r = (unsigned)q; r < nblk; r += A1_THREADS / 64) s += p.part[(size_t)r * C1 + k];
         sh[tid] = s;
         __syncthreads();
         if (tid < 64) {
             double t = 0.0;
 #pragma unroll
-            for (int l = 0; l < 16; ++l) t += sh[l * 64 + tid];
+            for (int l = 0; l < A1_THREADS / 64; ++l) t += sh[l * 64 + tid];
             vs[tid] = t;
             if (p.S1a) p.S1a[tid] = t;
         }
@@ -517,14 +517,15 @@ __global__ void __launch_bounds__(1024) k_tail_l3(TailL3Params p) {
 
 // B2: k_q_uvec -- after k_pool_bwd:  Q = W3^T diag(d) W3 (128 x 128),  uvec = W3^T e,  and (tensor-core path) the hi/lo
 // operand image of Q for the pass-A kernel.  grid = 32 blocks x 4 rows of Q, block = 1024 = 128 columns j x 8 lanes over the
-// 1024 channels (128 channels per lane, summed in order; the 8 lanes are added in lane order).
+// 1024 channels (128 channels per lane, summed in order; the 8 lanes are added in lane order).  The __global__ wrapper
+// k_q_uvec (tower.cuh) runs this in blocks [0, 32) and the per-cloud sort of the arg-max pairs in the remaining blocks.
 struct QuParams {
     const float* W3; const float* dvec; const float* evec;
     float* Q; float* uvec;
     void* qimg; float* inv_s; int act_shift;      // qimg == null: no image (CUDA-core path)
 };
 
-__global__ void __launch_bounds__(1024) k_q_uvec(QuParams p) {
+__device__ __forceinline__ void q_uvec_block(const QuParams& p) {
     __shared__ float s_q[8][4][128];
     __shared__ double s_u[4][32];              // [row][warp]: per-warp sums of the uvec products (fixed shuffle tree)
     __shared__ float s_mx[4][128];

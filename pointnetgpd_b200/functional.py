@@ -12,6 +12,31 @@ from . import _abi as A
 
 _KEY_CACHE = {}
 
+# Optional gradient-exchange hook of a data-parallel trainer (pointnetgpd_b200.ddp.FlatGradAllReduce.install):
+#   hook(stage, flat, lo, hi) is called from inside the backward with stage 0 as soon as flat[lo:hi] (the gradients of the
+#   classifier head + trunk tower) is final -- the T-Net half of the backward has not been launched yet, so an all-reduce issued
+#   on a side stream overlaps it -- and with stage 1 once the rest (flat[lo:hi] of the second call) is final.
+_GRAD_HOOK = None
+
+
+def set_grad_hook(fn):
+    """Install (or, with None, remove) the gradient-exchange hook; returns the previous one."""
+    global _GRAD_HOOK
+    old, _GRAD_HOOK = _GRAD_HOOK, fn
+    return old
+
+
+def _flat_layout(params, pkeys):
+    """Offsets (in floats, 16-byte aligned) of every gradient inside ONE flat buffer, in ABI key order, and the boundary
+    between the T-Net half (feat.stn.*: computed LAST by the backward) and the rest."""
+    offs, off, split = [], 0, None
+    for key, p in zip(pkeys, params):
+        if split is None and not key.startswith("feat.stn."):
+            split = off
+        offs.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    return offs, off, (off if split is None else split)
+
 
 class _DeviceCtx:
     """current-device guard + raw stream handle for a CUDA device.  (For host tensors -- only ever
@@ -136,7 +161,11 @@ class _Fused(torch.autograd.Function):
         table.update(zip(bkeys, bufs))
         model = A.build_model(lambda key: table[key].data_ptr(), what)
         with _DeviceCtx(dev) as stream:
-            grads = [torch.empty_like(p) for p in params]
+            # every gradient is a view into ONE flat buffer (ABI key order: T-Net tower, T-Net head | trunk, classifier head), so
+            # that a data-parallel trainer can all-reduce it in place, in two buckets, without packing copies
+            offs, total, split = _flat_layout(params, pkeys)
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            grads = [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
             gtable = dict(zip(pkeys, grads))
             g = A.build_grads(lambda key: gtable[key].data_ptr(), what)
             if what != A.PGPD_STN:
@@ -145,10 +174,22 @@ class _Fused(torch.autograd.Function):
                 dtrans = dtrans.contiguous().float()
             elif what == A.PGPD_STN:
                 dtrans = torch.zeros((B, 3, 3), dtype=torch.float32, device=dev)
-            rc = lib.pgpd_backward(what, C.byref(model), C.byref(g), x.data_ptr(), B, N, k, ctx.flags,
-                                   dout.data_ptr() if what != A.PGPD_STN else None,
-                                   dtrans.data_ptr() if dtrans is not None else None,
-                                   _aligned(ws), ws.numel() - 256, stream)
+            hook = _GRAD_HOOK if what != A.PGPD_STN else None
+
+            def call(extra):
+                return lib.pgpd_backward(what, C.byref(model), C.byref(g), x.data_ptr(), B, N, k, ctx.flags | extra,
+                                         dout.data_ptr() if what != A.PGPD_STN else None,
+                                         dtrans.data_ptr() if dtrans is not None else None,
+                                         _aligned(ws), ws.numel() - 256, stream)
+            if hook is None:
+                rc = call(0)
+            else:
+                rc = call(A.F_BWD_HEAD)
+                if rc == 0:
+                    hook(0, flat, split, total)
+                    rc = call(A.F_BWD_STN)
+                    if rc == 0:
+                        hook(1, flat, 0, split)
         A.check(lib, rc)
         return (None, None, None, None, None) + tuple(grads) + (None,) * len(bufs)
 

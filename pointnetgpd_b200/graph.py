@@ -11,18 +11,25 @@ import torch.nn.functional as F
 
 
 class GraphedTrainStep:
-    """Single GPU: one graph (zero_grad, forward, loss, backward, optimizer).
-    With a gradient all-reduce (`grad_sync`): two graphs -- (forward, loss, backward) and (optimizer) -- with the NCCL
-    all-reduce launched eagerly in between, so no collective is ever captured."""
+    """One graph: zero_grad, forward, loss, backward (with the gradient all-reduce issued from inside the backward on a side
+    stream when `grad_sync` is hooked in, ddp.FlatGradAllReduce.install), optimizer.  `capture_sync=False` keeps collectives
+    out of the graph: two graphs -- (forward, loss, backward) and (optimizer) -- with an eager all-reduce in between.
+
+    NOTE: construction runs `warmup` REAL training steps on the example batch before capturing (CUDA-graph capture needs warmed-up
+    allocator pools and library state).  To keep the caller's training trajectory untouched, parameters, BatchNorm buffers and the
+    optimizer state are snapshotted before and restored after the warm-up."""
 
     def __init__(self, model, optimizer, x_example, y_example, grad_sync=None, warmup=3, loss_fn=F.nll_loss,
-                 before_capture=None):
+                 before_capture=None, capture_sync=True):
         self.model, self.opt, self.sync, self.loss_fn = model, optimizer, grad_sync, loss_fn
         dev = x_example.device if x_example.is_cuda else next(model.parameters()).device
         self.sx = torch.empty_like(x_example, device=dev)
         self.sy = torch.empty_like(y_example, device=dev)
         self.sx.copy_(x_example)
         self.sy.copy_(y_example)
+        import copy
+        snap_model = copy.deepcopy(model.state_dict())
+        snap_opt = copy.deepcopy(optimizer.state_dict())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -33,15 +40,29 @@ class GraphedTrainStep:
                 self.opt.step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():                       # restore IN PLACE: the captured graph keeps the tensors' addresses
+            for k, v in model.state_dict().items():
+                v.copy_(snap_model[k])
+        cur_opt = optimizer.state_dict()
+        for idx, st in cur_opt["state"].items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    if idx in snap_opt["state"] and k in snap_opt["state"][idx]:
+                        v.copy_(snap_opt["state"][idx][k])
+                    else:
+                        v.zero_()                   # state created by the warm-up (Adam moments, step counter): back to its initial value
+        torch.cuda.synchronize(dev)
         if before_capture is not None:
             before_capture()
         self.g_main = torch.cuda.CUDAGraph()
         self.g_opt = None
         # gradients keep the tensors of the last warm-up step: capture re-creates them inside the graph's pool
         self.opt.zero_grad(set_to_none=True)
-        if self.sync is None:
+        if self.sync is None or capture_sync:
             with torch.cuda.graph(self.g_main):
                 self.loss = self._fwd_bwd()
+                if self.sync is not None:
+                    self.sync.all_reduce()          # no-op when the exchange already happened inside the backward
                 self.opt.step()
         else:
             with torch.cuda.graph(self.g_main):
