@@ -28,20 +28,22 @@ def _newest_src():
     return t
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_src():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: tuning builds of kernel variants (scripts/, never loaded by the package itself)."""
+    if out is None and not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_src():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", OUT, os.path.join(SRC, "pgpd_api.cu"),
-                                 "-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", os.path.join(ROOT, "include"), "-o", out or OUT,
+                                                               os.path.join(SRC, "pgpd_api.cu"), "-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libpgpd.so")
-    with open(os.path.join(HERE, "libpgpd.ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
-    return OUT
+    if out is None:
+        with open(os.path.join(HERE, "libpgpd.ptxas.log"), "w") as f:
+            f.write(res.stdout + res.stderr)
+    return out or OUT
 
 
 if __name__ == "__main__":

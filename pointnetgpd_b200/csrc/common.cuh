@@ -96,160 +96,6 @@ __device__ __forceinline__ void bn_finalize_train(int c, double mean_u, double v
     if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
 }
 
-// eval mode: y = gamma*(u + b - rm)/sqrt(rv+eps) + beta
-__global__ void k_bn_eval_affine(int C, const float* bias, pgpd_bn bn, BnState st) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    float rstd = 1.0f / sqrtf(bn.running_var[c] + BN_EPS);
-    float sc = bn.gamma[c] * rstd;
-    float b = bias ? bias[c] : 0.f;
-    st.mean[c] = bn.running_mean[c] - b;
-    st.rstd[c] = rstd;
-    st.scale[c] = sc;
-    st.shift[c] = bn.beta[c] + sc * (b - bn.running_mean[c]);
-}
-
-// ---- deterministic two-stage column reduction ------------------------------------------------------
-// stage 1: tmp[s][c] = sum over the rows of slice s of part[row][c]   (double accumulation, fixed order)
-// grid (ceil(C/32), S), block 256 = 32 columns x 8 row lanes
-constexpr int REDUCE_MAX_SLICES = 32;
-template <class T>
-__global__ void k_colreduce_stage1(const T* __restrict__ part, int nblk, int C, double* __restrict__ tmp) {
-    __shared__ double sh[8][33];
-    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
-    const int c = (int)blockIdx.x * 32 + cx;
-    const int S = (int)gridDim.y, sl = (int)blockIdx.y;
-    const int per = (nblk + S - 1) / S;
-    const int r0 = sl * per, r1 = (r0 + per < nblk) ? r0 + per : nblk;
-    double acc = 0.0;
-    if (c < C) {
-#pragma unroll 4
-        for (int i = r0 + ry; i < r1; i += 8) acc += (double)part[(size_t)i * C + c];
-    }
-    sh[ry][cx] = acc;
-    __syncthreads();
-    if (ry == 0 && c < C) {
-        double t = 0.0;
-        for (int q = 0; q < 8; ++q) t += sh[q][cx];
-        tmp[(size_t)sl * C + c] = t;
-    }
-}
-
-inline int reduce_slices(int nblk) {
-    int s = (nblk + 127) / 128;
-    return s < 1 ? 1 : (s > REDUCE_MAX_SLICES ? REDUCE_MAX_SLICES : s);
-}
-
-// runs stage 1 and returns the number of slices S; afterwards tmp holds [S][C] doubles
-template <class T>
-inline int colreduce(const T* part, int nblk, int C, double* tmp, cudaStream_t s) {
-    const int S = reduce_slices(nblk);
-    launch(k_colreduce_stage1<T>, dim3((unsigned)((C + 31) / 32), (unsigned)S), dim3(256), 0, s, part, nblk, C, tmp);
-    return S;
-}
-
-// one-kernel variant for at most 1024 partial rows: out[c] = (float) sum_rows part[row][c]; block = 32 columns x 32 row lanes
-// (each lane sums its rows in order, the 32 lane sums are added in lane order: deterministic)
-template <class T>
-__global__ void k_colreduce_direct(const T* __restrict__ part, int nblk, int C, float* __restrict__ out) {
-    __shared__ double sh[32][33];
-    const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
-    const int c = (int)blockIdx.x * 32 + cx;
-    double acc = 0.0;
-    if (c < C) {
-#pragma unroll 4
-        for (int i = ry; i < nblk; i += 32) acc += (double)part[(size_t)i * C + c];
-    }
-    sh[ry][cx] = acc;
-    __syncthreads();
-    if (ry == 0 && c < C) {
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) t += sh[q][cx];
-        out[c] = (float)t;
-    }
-}
-
-// slices of centred-square sums -> variance -> BatchNorm finalisation (train)
-// The squares were centred on `centre` (nullptr: on mean_u itself): sum (u-c)^2 = sum (u-mu)^2 + count (mu-c)^2.
-__global__ void k_bn_finalize_from_css(const double* tmp, int S, int C, const float* mean_u, double count,
-                                       const float* bias, pgpd_bn bn, BnState st, const float* centre) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    double s = 0.0;
-    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
-    const double mu = (double)mean_u[c];
-    double var = s / count;
-    if (centre) { const double d = mu - (double)centre[c]; var -= d * d; }
-    bn_finalize_train(c, mu, var, count, bias, bn, st);
-}
-
-// out[c] = (float) sum_i tmp[i][c]
-__global__ void k_reduce_f(const double* tmp, int S, int C, float* out) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    double s = 0.0;
-    for (int i = 0; i < S; ++i) s += tmp[(size_t)i * C + c];
-    out[c] = (float)s;
-}
-
-// vsum[k] = scale * sum_s tmp[s][k]  (the slices of a two-stage column reduction), then
-// mean_out[r] = (sum_k W[r][k] * vsum[k]) * inv   in double.  One warp per row (coalesced row reads, fixed shuffle tree);
-// block = 256 threads = 8 rows, grid = ceil(rows / 8); cols <= 128.  Block 0 also stores vsum (kept for the backward).
-__global__ void k_matvec_mean(const float* __restrict__ W, int rows, int cols, const double* __restrict__ tmp, int S, double scale,
-                              double inv, float* __restrict__ mean_out, double* __restrict__ vsum_out) {
-    __shared__ double vs[128];
-    const int tid = (int)threadIdx.x;
-    if (tid < cols) {
-        double t = 0.0;
-        for (int i = 0; i < S; ++i) t += tmp[(size_t)i * cols + tid];
-        t *= scale;
-        vs[tid] = t;
-        if (blockIdx.x == 0 && vsum_out) vsum_out[tid] = t;
-    }
-    __syncthreads();
-    const int r = (int)blockIdx.x * 8 + (tid >> 5), lane = tid & 31;
-    double s = 0.0;
-    if (r < rows)
-        for (int k = lane; k < cols; k += 32) s += (double)W[(size_t)r * cols + k] * vs[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (r < rows && lane == 0) mean_out[r] = (float)(s * inv);
-}
-
-// out[c] = (float) sum over the nblk partial rows; one kernel for up to 1024 rows, the two-stage reduction otherwise
-template <class T>
-inline void colreduce_to_float(const T* part, int nblk, int C, float* out, double* tmp, cudaStream_t s) {
-    if (nblk <= 1024) {
-        launch(k_colreduce_direct<T>, dim3((unsigned)((C + 31) / 32)), dim3(1024), 0, s, part, nblk, C, out);
-    } else {
-        const int S = colreduce<T>(part, nblk, C, tmp, s);
-        launch(k_reduce_f, dim3((unsigned)((C + 255) / 256)), dim3(256), 0, s, (const double*)tmp, S, C, out);
-    }
-}
-
-__global__ void k_fill(float* p, size_t n, float v) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
-// BatchNorm backward bookkeeping from slices [S][2][C] of (sum dz, sum dz*yhat):
-//   dgamma = sum dz*yhat ; dbeta = sum dz ; m1 = dbeta/count ; m2 = dgamma/count
-__global__ void k_bn_bwd_finalize(const double* tmp, int S, int C, double count,
-                                  float* dgamma, float* dbeta, float* m1, float* m2) {
-    int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < S; ++i) {
-        s1 += tmp[((size_t)i * 2 + 0) * C + c];
-        s2 += tmp[((size_t)i * 2 + 1) * C + c];
-    }
-    dgamma[c] = (float)s2;
-    dbeta[c] = (float)s1;
-    m1[c] = (float)(s1 / count);
-    m2[c] = (float)(s2 / count);
-}
-
 // ---- optional CUDA-event timing of the dominant kernel ---------------------------------------------
 struct Profiler {
     bool on = false;

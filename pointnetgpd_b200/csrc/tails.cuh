@@ -66,6 +66,7 @@ __device__ __forceinline__ int prepack_elem(float w, float mx, int r, int k, __h
 #endif
 
 __global__ void __launch_bounds__(PRE_THREADS) k_tower_pre(PreParams p) {
+    pdl_sync();
     __shared__ double sh[PRE_THREADS];
     __shared__ double raw[12];
     __shared__ float redf[PRE_THREADS];
@@ -222,6 +223,7 @@ struct A1Params {
 };
 
 __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
+    pdl_sync();
     __shared__ float xs[3][A1_CHUNK * A1_CPB];
     __shared__ double sh[A1_THREADS];
     __shared__ double vs[C1];
@@ -303,12 +305,14 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
 //   then the sum of a2 = relu(bn2(u2)): either from the caller's partial rows (CUDA-core path: k_a2_sum over all points,
 //                the exact mean) or, tensor-core path, a PILOT estimate from `nsample` points spread over the batch
 //                (each block sums its share; the layer-3 kernel accumulates the exact sum while it stages the tiles);
-//   the last block: S1 = the (pilot) sum of a2; CUDA-core path only (mean_u3 != null): mean(u3) = W3 S1 / nsample, the centre
-//                of layer 3's sum of squares (the tensor-core layer-3 kernel forms its centres itself from S1).
+//   tensor-core path (mu_s != null): every block forms the centres of 1024 / TL2_BLOCKS channels from ITS OWN share of the
+//                sample, centre[c] = W3[c] . (block sum / block samples): any value near the mean will do (the statistics are
+//                corrected exactly afterwards), so no cross-block step is needed; st3.mean = centre, mu_s = centre / inv;
+//   CUDA-core path: the last block adds the partial rows (exact sum of a2 -> S1) and forms mean(u3) = W3 S1 / nsample.
 // grid = TL2_BLOCKS, block = 1024 = 128 channels x 8 lanes.
 // ================================================================================================
 constexpr int TL2_BLOCKS = 32;
-constexpr int TL2_SAMPLE = 4096;              // points of the pilot estimate of mean(a2)
+constexpr int TL2_SAMPLE = 8192;              // points of the pilot estimate of mean(a2) (256 per block)
 struct TailL2Params {
     const float* css; int n_css;              // [n_css][128] partial sums of (u2 - mean)^2
     int bn_done;                              // 1: BatchNorm2 is already finalised (second call of the CUDA-core path): only read st2
@@ -317,11 +321,13 @@ struct TailL2Params {
     const double* a2part; int n_a2part;       // or: exact partial rows [n][128] (nsample = number of points they cover)
     double* part;                             // [TL2_BLOCKS][128] scratch
     unsigned* counter;
-    double* S1;                               // [128] sum of a2 over the nsample points
-    const float* W3; float* mean_u3;          // CUDA-core path: [1024] mean of u3; null on the tensor-core path
+    double* S1;                               // [128] sum of a2 over the nsample points (CUDA-core path)
+    const float* W3; float* mean_u3;          // [1024] (pilot) mean of u3
+    const float* inv3; float* mu_s;           // tensor-core path: accumulator scale / the centres in accumulator units
 };
 
 __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
+    pdl_sync();
     __shared__ double sh[1024];
     __shared__ float s_sc[C2], s_sf[C2];
     __shared__ double vs[C2];
@@ -372,12 +378,40 @@ __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
 #pragma unroll
         for (int l = 0; l < 8; ++l) t += sh[l * C2 + tid];
         p.part[(size_t)blockIdx.x * C2 + tid] = t;
+        vs[tid] = t;
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (p.mu_s) {
+        // tensor-core path: centres of my 32 channels from my own samples (one warp per row of W3: coalesced, fixed shuffle tree)
+        __syncthreads();
+        size_t mine = 0;                        // samples this block summed: i = blockIdx*8 + q + k * 8 * gridDim, i < nsample
+        {
+            const size_t first = (size_t)blockIdx.x * 8, stride = (size_t)gridDim.x * 8;
+            for (int qq = 0; qq < 8; ++qq)
+                if (first + qq < p.nsample) mine += (p.nsample - 1 - (first + qq)) / stride + 1;
+        }
+        const double inv_n = mine ? 1.0 / (double)mine : 0.0;
+        const int r = (int)blockIdx.x * (C3 / TL2_BLOCKS) + warp;
+        if (warp < C3 / TL2_BLOCKS) {
+            double s = 0.0;
+#pragma unroll
+            for (int kk = lane; kk < C2; kk += 32) s += (double)p.W3[(size_t)r * C2 + kk] * vs[kk];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                const float m = (float)(s * inv_n);
+                p.mean_u3[r] = m;
+                p.mu_s[r] = m / p.inv3[r];
+            }
+        }
+        return;
     }
     if (!last_block_done(p.counter, gridDim.x)) return;
-    // ---- last block: total
+    // ---- CUDA-core path, last block: total of the partial rows (exact sum of a2)
     {
         double s = 0.0;
         for (unsigned r = (unsigned)q; r < gridDim.x; r += 8) s += p.part[(size_t)r * C2 + c];
+        __syncthreads();
         sh[tid] = s;
         __syncthreads();
         if (tid < C2) {
@@ -389,9 +423,7 @@ __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
         }
         __syncthreads();
     }
-    if (!p.mean_u3) return;
-    // CUDA-core path: mean(u3) = W3 S / nsample  (one warp per row of W3: coalesced, fixed shuffle tree)
-    const int warp = tid >> 5, lane = tid & 31;
+    // mean(u3) = W3 S / nsample  (one warp per row of W3: coalesced, fixed shuffle tree)
     const double inv_n = 1.0 / (double)p.nsample;
     for (int r = warp; r < C3; r += 32) {
         double s = 0.0;
@@ -429,6 +461,7 @@ struct TailL3Params {
 };
 
 __global__ void __launch_bounds__(1024) k_tail_l3(TailL3Params p) {
+    pdl_sync();
     __shared__ double sh[TL3_LANES][TL3_CH + 1];
     __shared__ double vs[C2];
     __shared__ float s_sc[TL3_CH], s_sf[TL3_CH];
@@ -615,6 +648,7 @@ struct TailKaParams {
 };
 
 __global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
+    pdl_sync();
     __shared__ double sh[32][33];
     const int tid = (int)threadIdx.x;
     const int n_gram = p.gcols / 256;
@@ -788,6 +822,7 @@ struct TailKbParams {
 constexpr int TKB_BLOCKS = 52;
 
 __global__ void __launch_bounds__(1024) k_tail_kb(TailKbParams p) {
+    pdl_sync();
     __shared__ double sh[32][33];
     const int tid = (int)threadIdx.x, blk = (int)blockIdx.x;
     if (blk < 48) {

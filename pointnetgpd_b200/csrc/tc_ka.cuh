@@ -14,7 +14,6 @@
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
-#include "tc_accum.cuh"
 
 namespace pgpd { namespace tc {
 
@@ -31,7 +30,7 @@ constexpr int KA_SMEM_BYTES = KA_OFF_MISC + 256 + 1024;
 constexpr int KA_EPI_ROWS = 4;                              // partial rows per CTA (four 16-column groups)
 
 struct KaParams {
-    const __half* Qimg; const float* inv;                   // pre-packed Q (k_prepack_rows, extra shift ACT_SHIFT) and its row scales
+    const __half* Qimg; const float* inv;                   // pre-packed Q (tails.cuh: q_uvec_block, extra shift ACT_SHIFT) and its row scales
     const float* uvec; const float* scale2; const float* shift2; const float* gamma2; const float* beta2;
     const float* Y2; const float* da2s; const int* slot;
     int B, N, tiles_per_cloud, ntiles;
@@ -42,6 +41,7 @@ struct KaParams {
 };
 
 __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -299,14 +299,6 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 25) tmem_dealloc<512>(tmem);
-}
-
-// gram[m][n] = (hh[m][n] + hl[m][n] + hl[n][m]) / 256  from the reduced partial sums [2][128*128]
-__global__ void k_gram_sym(const float* __restrict__ hh_hl, float* __restrict__ gram) {
-    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (i >= C2 * C2) return;
-    const int m = i >> 7, n = i & 127;
-    gram[i] = (hh_hl[i] + hh_hl[C2 * C2 + i] + hh_hl[C2 * C2 + n * C2 + m]) * (1.0f / (ACT_SCALE * ACT_SCALE));
 }
 
 inline int launch_ka(const KaParams& p, int sms, cudaStream_t s) {

@@ -19,7 +19,6 @@
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
-#include "tc_accum.cuh"
 
 namespace pgpd { namespace tc {
 
@@ -38,67 +37,7 @@ constexpr int KB_OFF_MISC = KB_OFF_X + 2 * 3 * KB_NT * 4;
 constexpr int KB_SMEM_BYTES = KB_OFF_MISC + 256 + 1024;
 constexpr int KB_EPI_GROUPS = 4;                            // column groups of 16 points: partial rows per tile / per CTA
 
-// esc[c] = 2^e with max|dz2[.,c]| 2^e in [2^12, 2^13), from the per-row maxima written by the layer-2 backward pass 1.
-// block = 1024 = 128 channels x 8 row lanes
-__global__ void k_kb_scale(const float* __restrict__ pmax, int G, float* __restrict__ esc, float* __restrict__ einv) {
-    __shared__ float sh[8][C2];
-    const int c = (int)threadIdx.x & 127, ry = (int)threadIdx.x >> 7;
-    float mx = 0.f;
-    for (int g = ry; g < G; g += 8) mx = fmaxf(mx, pmax[(size_t)g * 2 * C2 + c]);
-    sh[ry][c] = mx;
-    __syncthreads();
-    if (ry == 0) {
-#pragma unroll
-        for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sh[q][c]);
-        int e = 139 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-        e = (mx > 0.f) ? (e > 100 ? 100 : (e < -100 ? -100 : e)) : 0;
-        esc[c] = __uint_as_float((uint32_t)(127 + e) << 23);
-        einv[c] = __uint_as_float((uint32_t)(127 - e) << 23);
-    }
-}
-
-// A-operand images of the pass.  Row k < 64:  A1op[k][c] = W2[c][k] s_c einv_c 2^g_k,  A2op[k][k'] = -K[k][k'] 2^g_k / 16,
-// with 2^g_k bringing the larger of the two row maxima into [2^13, 2^14); rows 64..127 are zero (the MMA M extent is 128).
-// ginv[k] = 2^-g_k.  grid = 128 rows, block = 128.
-__global__ void k_kb_prepack(const float* __restrict__ W2, const float* __restrict__ scale2, const float* __restrict__ einv,
-                             const float* __restrict__ Kmat, __half* __restrict__ img1, __half* __restrict__ img2,
-                             float* __restrict__ ginv) {
-    __shared__ float red[128];
-    const int r = (int)blockIdx.x, c = (int)threadIdx.x;
-    const float w = (r < C1) ? W2[c * C1 + r] * scale2[c] * einv[c] : 0.f;
-    const float kk = (r < C1 && c < C1) ? -Kmat[r * C1 + c] * (1.0f / ACT_SCALE) : 0.f;
-    red[c] = fmaxf(fabsf(w), fabsf(kk));
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if (c < s) red[c] = fmaxf(red[c], red[c + s]);
-        __syncthreads();
-    }
-    const float mx = red[0];
-    int ex = 0;
-    if (mx > 0.f) frexpf(mx, &ex);
-    const int e = (mx > 0.f) ? 14 - ex : 0;
-    {
-        const float ws = ldexpf(w, e);
-        const __half hi = __float2half_rn(ws);
-        const __half lo = __float2half_rn(ws - __half2float(hi));
-        const int kb = c >> 6, j = c & 63, chunk = j >> 3, within = j & 7;
-        const size_t base = (size_t)(kb * 2) * 8192;
-        const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
-        img1[base + off] = hi;
-        img1[base + 8192 + off] = lo;
-    }
-    if (c < C1) {
-        const float ks = ldexpf(kk, e);
-        const __half hi = __float2half_rn(ks);
-        const __half lo = __float2half_rn(ks - __half2float(hi));
-        const int chunk = c >> 3, within = c & 7;
-        const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
-        img2[off] = hi;
-        img2[8192 + off] = lo;
-    }
-    if (c == 0) ginv[r] = ldexpf(1.f, -e);
-}
-
+// The per-channel scale of dz2 (esc / einv) and the two A-operand images of this pass are produced by tails.cuh: kb_prep_row.
 struct KbParams {
     const __half* A1img; const __half* A2img; const float* ginv;
     const float* cvec; const float* gamma1; const float* beta1;
@@ -112,6 +51,7 @@ struct KbParams {
 };
 
 __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);

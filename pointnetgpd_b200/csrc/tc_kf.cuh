@@ -9,14 +9,13 @@
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
-#include "tc_stream.cuh"
 
 namespace pgpd { namespace tc {
 
 constexpr int KF_NT = 64;
 constexpr int KF_NBUF = 4;
 constexpr int KF_THREADS = 448;                             // 8 epilogue + 4 converter warps, loader, MMA issuer
-constexpr int KF_W_BYTES = 32768;                           // W2 image [part][128 rows][128 B]  (k_prepack_rows, KD = 64)
+constexpr int KF_W_BYTES = 32768;                           // W2 image [part][128 rows][128 B]  (tails.cuh: k_tower_pre)
 constexpr int KF_OP_BYTES = 16384;                          // a1 tile  [part][64 rows][128 B]    (raw: [64][64] fp32)
 constexpr int KF_OFF_BUF = KF_W_BYTES;
 constexpr int KF_OFF_MISC = KF_OFF_BUF + KF_NBUF * KF_OP_BYTES;
@@ -30,6 +29,7 @@ struct KfParams {
 };
 
 __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);

@@ -44,578 +44,23 @@ constexpr int L3A_THREADS = 320 + 32 * L3A_NP;   // v1 kernel: W producer, MMA i
 constexpr float L3_ACT_SCALE = 16.0f;             // 2^4
 constexpr size_t L3_WIMG_BYTES = (size_t)8 * 2 * L3_STAGE_BYTES;   // 512 KB
 
-// ---- weight pre-pack: W3 [1024][128] fp32 -> swizzled hi/lo fp16 image + per-channel inverse scale ----
-// image index: ((mt*2 + kb)*2 + part) * 16 KB + r*128 + ((chunk ^ (r&7)) << 4) + within*2
-// inv[c] = sign(gamma3[c]) * 2^-(e_c + 4): multiplying a TMEM accumulator value by inv[c] gives u3.
-__global__ void k_prepack_w3(const float* __restrict__ W3, const float* __restrict__ gamma3, const float* __restrict__ mean_u3,
-                             __half* __restrict__ img, float* __restrict__ inv, float* __restrict__ mu_s) {
-    __shared__ float red[128];
-    const int c = (int)blockIdx.x, k = (int)threadIdx.x;
-    const float w = W3[(size_t)c * 128 + k];
-    red[k] = fabsf(w);
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if (k < s) red[k] = fmaxf(red[k], red[k + s]);
-        __syncthreads();
-    }
-    const float mx = red[0];
-    int ex = 0;
-    if (mx > 0.f) frexpf(mx, &ex);             // mx in [2^(ex-1), 2^ex)
-    const int e = (mx > 0.f) ? 14 - ex : 0;    // mx * 2^e in [2^13, 2^14)
-    const float sg = gamma3[c] >= 0.f ? 1.f : -1.f;
-    const float ws = ldexpf(w, e) * sg;
-    const __half hi = __float2half_rn(ws);
-    const __half lo = __float2half_rn(ws - __half2float(hi));
-    const int mt = c >> 7, r = c & 127, kb = k >> 6, j = k & 63, chunk = j >> 3, within = j & 7;
-    const size_t base = ((size_t)(mt * 2 + kb) * 2) * 8192;     // in halves: 16 KB = 8192 halves
-    const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
-    img[base + off] = hi;
-    img[base + 8192 + off] = lo;
-    if (k == 0) {
-        const float iv = sg * ldexpf(1.f, -(e + 4));
-        inv[c] = iv;
-        if (mu_s) mu_s[c] = mean_u3 ? mean_u3[c] / iv : 0.f;
-    }
-}
-
+// The weight image (W3 [1024][128] fp32 -> swizzled hi/lo fp16, rows scaled by 2^e_c, sign(gamma3) folded in; index
+// ((mt*2 + kb)*2 + part) * 16 KB + r*128 + ((chunk ^ (r&7)) << 4) + within*2) and inv[c] = sign(gamma3[c]) * 2^-(e_c + 4) are
+// produced by tails.cuh: k_tower_pre.
 struct L3Params {
     const float* Y2;          // [M][128] layer-2 pre-activation
     const float* scale2;      // [128]
     const float* shift2;      // [128]
     const __half* Wimg;       // pre-packed W3 image
     const float* inv;         // [1024]
-    const float* mu_s;        // versions 1/2: [1024] mean of u3 in accumulator units, or nullptr (no statistics)
+    const float* mu_s;        // [1024] centre of the sums of squares (a pilot estimate of mean(u3)) in accumulator units, or nullptr (no statistics)
     unsigned long long* keys; // [B][1024] (ordered max value, ~arg-max)
     float* css_part;          // [ntiles][1024]
     int B, N, tiles_per_cloud, ntiles;
     long long* dbg;           // optional [gridDim.x][8] cycle counters (see PGPD_L3_DEBUG), or nullptr
     float* s1_part;           // optional partial sums over the points of a2 * 2^4: v1 [gridDim.x][128], v3 [gridDim.x * 8][128]
     unsigned* bad;            // [B] set to 1 for a cloud with a NaN / out-of-fp16-range activation (version 3)
-    // version 3, train mode: the kernel forms the centres of its sums of squares itself: centre[c] = W3[c] . (s1_pilot * inv_n)
-    // (a pilot estimate of mean(u3), tails.cuh: k_tail_l2) and publishes them in centre_out; null: no statistics
-    const double* s1_pilot; double inv_n; const float* W3f; float* centre_out;
 };
-
-// cycle accounting of the pipeline roles, for tuning (enabled by a non-null L3Params::dbg):
-//  0 mma: wait a2_full   1 mma: wait tmem_empty   2 mma: wait w_full   3 mma: total loop
-//  4 producer: wait a2_empty   5 producer: stage a tile   6 epilogue: wait tmem_full   7 epilogue: work
-#define L3_T0() const long long _t0 = p.dbg ? clock64() : 0
-#define L3_ACC(slot) do { if (p.dbg) dbg_acc[slot] += clock64() - _t0; } while (0)
-
-__global__ void __launch_bounds__(L3A_THREADS, 1) k_l3_fwd_tc(L3Params p) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // SWIZZLE_128B operand tiles need a 1024-byte aligned base: align by hand, do not rely on the attribute
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const uint32_t sbase = smem_u32(smem);
-    unsigned char* misc = smem + L3_SMEM_MISC;
-    // barriers (8 bytes each)
-    const uint32_t bar0 = sbase + L3_SMEM_MISC;
-    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // 0..2 w_full, 3..5 w_empty, 6 a2_full, 7 a2_empty, 8..9 tmem_full, 10..11 tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-    float* s_scale = reinterpret_cast<float*>(misc + 256);     // [128] (pre-multiplied by 2^4)
-    float* s_shift = s_scale + 128;
-
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long gt0 = 0, ck0 = 0;
-    if (p.dbg && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
-
-    if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-        mbar_init(BAR(6), 32 * L3A_NP); mbar_init(BAR(7), 1);
-        mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
-        mbar_init(BAR(10), 256); mbar_init(BAR(11), 256);
-        mbar_fence_init();
-    }
-    if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
-    if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    // contiguous range of tiles for this CTA
-    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
-
-    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (warp == 0) {
-        // ===================== W3 producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            // every CTA walks the eight 128-channel blocks in a different rotation, so that the 148 SMs do not all pull
-            // the same lines of the (L2-resident) weight image at the same moment
-            const int rot = cta & 7;
-            for (int t = t_begin; t < t_end; ++t)
-                for (int blk = 0; blk < 16; ++blk) {       // (mt, kb) in issue order
-                    const int sblk = ((((blk >> 1) + rot) & 7) << 1) | (blk & 1);
-                    mbar_wait(BAR(3 + stage), phase ^ 1);
-                    mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)sblk * L3_STAGE_BYTES;
-                    const uint32_t dst = sbase + L3_SMEM_W + stage * L3_STAGE_BYTES;
-                    bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(stage));                                   // hi part
-                    bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(stage));   // lo part
-                    if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
-                }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t IDESC = idesc_f16(128, L3_NT);
-            int stage = 0; uint32_t wphase = 0;
-            int acc = 0; uint32_t aphase = 0;
-            uint32_t a2phase = 0;
-            const long long tl0 = p.dbg ? clock64() : 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                { L3_T0(); mbar_wait(BAR(6), a2phase); L3_ACC(0); }   // a2 tile staged
-                tc_fence_after_sync();
-                for (int mt = 0; mt < 8; ++mt) {
-                    { L3_T0(); mbar_wait(BAR(10 + acc), aphase ^ 1); L3_ACC(1); }   // accumulator drained by the epilogue
-                    tc_fence_after_sync();
-                    const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
-                    for (int kb = 0; kb < 2; ++kb) {
-                        { L3_T0(); mbar_wait(BAR(stage), wphase); L3_ACC(2); }      // weights landed
-                        tc_fence_after_sync();
-                        const uint32_t w_hi = sbase + L3_SMEM_W + stage * L3_STAGE_BYTES, w_lo = w_hi + 16384;
-                        const uint32_t b_hi = sbase + (0 * 2 + kb) * L3_A2_PART, b_lo = sbase + (1 * 2 + kb) * L3_A2_PART;
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t wa = (pass == 1) ? w_lo : w_hi;
-                            const uint32_t bb = (pass == 2) ? b_lo : b_hi;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(bb + k * 32), IDESC,
-                                        (kb | pass | k) ? 1u : 0u);
-                        }
-                        mma_commit(BAR(3 + stage));         // stage free once these MMAs have read it
-                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1; }
-                    }
-                    mma_commit(BAR(8 + acc));               // accumulator complete
-                    if (++acc == 2) { acc = 0; aphase ^= 1; }
-                }
-                mma_commit(BAR(7));                         // a2 tile no longer needed
-                a2phase ^= 1;
-            }
-            if (p.dbg) {
-                dbg_acc[3] = clock64() - tl0;
-                for (int i = 0; i < 4; ++i) p.dbg[(size_t)cta * 8 + i] = dbg_acc[i];
-            }
-        }
-    } else if (warp < 10) {
-        // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 128 columns each =====================
-        const int q = warp & 3;                             // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;                   // which half of the 256 columns
-        const int row = q * 32 + lane;
-        const bool stats = p.mu_s != nullptr;
-        int acc = 0; uint32_t aphase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-            const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
-            const int n0 = tt * L3_NT;
-            const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
-            for (int mt = 0; mt < 8; ++mt) {
-                const int ch = ((mt + (cta & 7)) & 7) * 128 + row;      // same rotation as the weight producer
-                const float mu = stats ? p.mu_s[ch] : 0.f;
-                const uint64_t nmu2 = f2_pack(-mu, -mu);
-                { L3_T0(); mbar_wait(BAR(8 + acc), aphase); L3_ACC(6); }
-                tc_fence_after_sync();
-                const long long te0 = p.dbg ? clock64() : 0;
-                float best = -INFINITY; int bidx = 0; float css = 0.f;
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
-                for (int c0 = half * (L3_NT / 2); c0 < (half + 1) * (L3_NT / 2); c0 += 32) {
-                    if (c0 >= nvalid) break;                // warp-uniform
-                    float v[32];
-                    tmem_ld32(tbase + (uint32_t)c0, v);
-                    if (c0 + 32 <= nvalid) {
-                        // four independent chains each for the max and the centred squares (ILP)
-                        float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
-#pragma unroll
-                        for (int j = 4; j < 32; j += 4) {
-                            m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
-                        }
-                        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                        if (stats) {
-                            // centred squares with packed fp32 pairs (FADD2 / FFMA2): one issue slot per element instead of two
-                            uint64_t q0 = 0ull, q1 = 0ull;              // (+0.f, +0.f)
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const uint64_t d0 = f2_add(f2_pack(v[j], v[j + 1]), nmu2), d1 = f2_add(f2_pack(v[j + 2], v[j + 3]), nmu2);
-                                q0 = f2_fma(d0, d0, q0); q1 = f2_fma(d1, d1, q1);
-                            }
-                            float c0s, c1s, c2s, c3s;
-                            f2_unpack(q0, c0s, c1s); f2_unpack(q1, c2s, c3s);
-                            css += (c0s + c1s) + (c2s + c3s);
-                        }
-                        if (m > best) {
-                            best = m;
-                            int jj = 31;
-#pragma unroll
-                            for (int j = 30; j >= 0; --j) if (v[j] == m) jj = j;
-                            bidx = n0 + c0 + jj;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (c0 + j < nvalid) {
-                                if (stats) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
-                                if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
-                            }
-                        }
-                    }
-                }
-                tc_fence_before_sync();
-                mbar_arrive(BAR(10 + acc));                 // accumulator may be overwritten
-                if (p.dbg) dbg_acc[7] += clock64() - te0;
-                if (++acc == 2) { acc = 0; aphase ^= 1; }
-                const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
-                                               (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
-                atomicMax(&p.keys[(size_t)b * C3 + ch], key);
-                if (stats) {
-                    const float iv = p.inv[ch];
-                    p.css_part[((size_t)t * 2 + half) * C3 + ch] = css * iv * iv;     // two partial rows per tile
-                }
-            }
-        }
-        if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
-    } else {
-        // ===================== a2 producer =====================
-        const int wp = warp - 10;                           // 0..L3A_NP-1
-        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
-        const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
-        const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
-        uint32_t ephase = 0;
-        float sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f;   // sums of this thread's a2 values (x 2^4)
-        for (int t = t_begin; t < t_end; ++t) {
-            const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
-            const int n0 = tt * L3_NT;
-            const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
-            const float* src = p.Y2 + ((size_t)b * p.N + n0) * C2 + 4 * lane;
-            if (wp == 0 && lane == 0 && t + 1 < t_end) {
-                // pull the NEXT tile's rows into L2 while this tile is being staged / multiplied
-                const int b1 = (t + 1) / p.tiles_per_cloud, tt1 = (t + 1) % p.tiles_per_cloud;
-                const int nv1 = (p.N - tt1 * L3_NT < L3_NT) ? p.N - tt1 * L3_NT : L3_NT;
-                l2_prefetch(p.Y2 + ((size_t)b1 * p.N + (size_t)tt1 * L3_NT) * C2, (uint32_t)nv1 * C2 * 4u);
-            }
-            { L3_T0(); mbar_wait(BAR(7), ephase ^ 1); L3_ACC(4); }   // previous tile's MMAs are done with a2
-            ephase ^= 1;
-            const long long tp0 = p.dbg ? clock64() : 0;
-            constexpr int U = 8;
-            for (int i0 = 0; i0 < L3_NT / L3A_NP; i0 += U) {
-                float4 y[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {               // all loads of U rows first (memory-level parallelism)
-                    const int r = wp + L3A_NP * (i0 + u);
-                    y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int r = wp + L3A_NP * (i0 + u);
-                    const bool ok = r < nvalid;
-                    float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
-                    float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
-                    float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
-                    float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
-                    sa0 += a0; sa1 += a1; sa2 += a2; sa3 += a3;
-                    __half2 h01, l01, h23, l23;
-                    split2(a0, a1, h01, l01);
-                    split2(a2, a3, h23, l23);
-                    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
-                    uint2 hv, lv;
-                    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-                    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-                    *reinterpret_cast<uint2*>(smem + (0 * 2 + kb) * L3_A2_PART + off) = hv;
-                    *reinterpret_cast<uint2*>(smem + (1 * 2 + kb) * L3_A2_PART + off) = lv;
-                }
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(BAR(6));
-            if (p.dbg) dbg_acc[5] += clock64() - tp0;
-        }
-        if (p.dbg && wp == 0 && lane == 0) { p.dbg[(size_t)cta * 8 + 4] = dbg_acc[4]; p.dbg[(size_t)cta * 8 + 5] = dbg_acc[5]; }
-        if (p.s1_part) {
-            // per-CTA sum of a2 (for the exact mean of u3 = W3 mean(a2) and for dW3): the 8 producer warps' partial
-            // sums are added in a fixed order through the (now idle) operand tile
-            mbar_wait(BAR(7), ephase ^ 1);                  // the last tile's MMAs are done with the buffer
-            float* red = reinterpret_cast<float*>(smem);    // [L3A_NP][128]
-            red[wp * C2 + 4 * lane + 0] = sa0; red[wp * C2 + 4 * lane + 1] = sa1;
-            red[wp * C2 + 4 * lane + 2] = sa2; red[wp * C2 + 4 * lane + 3] = sa3;
-            named_bar_sync(1, 32 * L3A_NP);
-            if (wp == 0) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int ch = 4 * lane + e;
-                    float t = 0.f;
-#pragma unroll
-                    for (int w8 = 0; w8 < L3A_NP; ++w8) t += red[w8 * C2 + ch];
-                    p.s1_part[(size_t)cta * C2 + ch] = t;
-                }
-            }
-        }
-    }
-
-    tc_fence_before_sync();
-    __syncthreads();
-    if (p.dbg && tid == 0) {            // wall time (ns) and SM cycles of this CTA: effective clock under this load
-        long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
-        p.dbg[(size_t)(200 + (blockIdx.x & 31)) * 8 + 0] = gt1 - gt0;
-        p.dbg[(size_t)(200 + (blockIdx.x & 31)) * 8 + 1] = clock64() - ck0;
-    }
-    if (warp == 1) tmem_dealloc<512>(tmem);
-}
-
-// ====================================================================================================================
-// Version 2: CTA PAIRS (thread-block cluster of 2) share the W3 stream.
-//   * every 32 KB weight stage is fetched from L2 only ONCE per pair: each CTA bulk-copies one 16 KB half with
-//     .multicast::cluster into both CTAs' shared memory -> half the L2 traffic per SM, which is what allows
-//   * 128-point tiles with a DOUBLE-BUFFERED a2 operand (2 x 64 KB): staging the next tile overlaps the MMAs of the
-//     current one (in version 1 the 256-point tile is single-buffered and the tensor pipe idles while it is staged),
-//   * four 128-column TMEM accumulators (512 columns) decouple the MMA issuer from the epilogue.
-// The two CTAs of a pair walk disjoint tiles but consume the weight ring in lock step (a stage is refilled only when
-// BOTH have released it: the MMA issuer's tcgen05.commit is multicast to both CTAs' "empty" barriers).
-// ====================================================================================================================
-constexpr int L3B_NT = 128;
-constexpr int L3B_A2_PART = L3B_NT * 128;          // 16 KB: one (part, k-block) sub-tile
-constexpr int L3B_A2_BUF = 4 * L3B_A2_PART;        // 64 KB: hi/lo x 2 k-blocks
-constexpr int L3B_SMEM_W = 2 * L3B_A2_BUF;         // 128 KB
-constexpr int L3B_SMEM_MISC = L3B_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
-constexpr int L3B_SMEM_BYTES = L3B_SMEM_MISC + 2048 + 1024;
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3_THREADS, 1) k_l3_fwd_tc2(L3Params p) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const uint32_t sbase = smem_u32(smem);
-    unsigned char* misc = smem + L3B_SMEM_MISC;
-    const uint32_t bar0 = sbase + L3B_SMEM_MISC;
-    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // 0..2 w_full, 3..5 w_empty, 6..7 a2_full, 8..9 a2_empty, 10..13 tmem_full, 14..17 tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 192);
-    float* s_scale = reinterpret_cast<float*>(misc + 256);
-    float* s_shift = s_scale + 128;
-
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-
-    if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 2); }
-        mbar_init(BAR(6), 256); mbar_init(BAR(7), 256);
-        mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(BAR(10 + i), 1); mbar_init(BAR(14 + i), 128); }
-        mbar_fence_init();
-    }
-    if (tid < 128) { s_scale[tid] = p.scale2[tid] * L3_ACT_SCALE; s_shift[tid] = p.shift2[tid] * L3_ACT_SCALE; }
-    if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
-    tc_fence_before_sync();
-    __syncthreads();
-    cluster_sync_all();                 // the peer's barriers exist before anything is multicast to them
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    // tiles of this PAIR, interleaved between its two CTAs; both run the same number of iterations
-    const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
-    const int T0 = (int)(((long long)p.ntiles * pair) / npairs), T1 = (int)(((long long)p.ntiles * (pair + 1)) / npairs);
-    const int niter = (T1 - T0 + 1) >> 1;
-    const int cta = (int)blockIdx.x;
-    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-    if (warp == 0) {
-        // ===================== W3 producer: my 16 KB half of every stage, multicast to both CTAs =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < niter; ++it)
-                for (int blk = 0; blk < 16; ++blk) {
-                    mbar_wait(BAR(3 + stage), phase ^ 1);                       // released by BOTH CTAs
-                    mbar_arrive_expect_tx(BAR(stage), L3_STAGE_BYTES);          // 16 KB from me + 16 KB from the peer
-                    bulk_g2s_multicast(sbase + L3B_SMEM_W + stage * L3_STAGE_BYTES + rank * 16384,
-                                       reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES + rank * 16384,
-                                       16384, BAR(stage), (uint16_t)0x3);
-                    if (++stage == L3_STAGES) { stage = 0; phase ^= 1; }
-                }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t IDESC = idesc_f16(128, L3B_NT);
-            int stage = 0; uint32_t wphase = 0;
-            int acc = 0; uint32_t aphase = 0;
-            int buf = 0; uint32_t bphase = 0;
-            const long long tl0 = p.dbg ? clock64() : 0;
-            for (int it = 0; it < niter; ++it) {
-                { L3_T0(); mbar_wait(BAR(6 + buf), bphase); L3_ACC(0); }
-                tc_fence_after_sync();
-                const uint32_t a2b = sbase + buf * L3B_A2_BUF;
-                for (int mt = 0; mt < 8; ++mt) {
-                    { L3_T0(); mbar_wait(BAR(14 + acc), aphase ^ 1); L3_ACC(1); }
-                    tc_fence_after_sync();
-                    const uint32_t d = tmem + (uint32_t)(acc * L3B_NT);
-                    for (int kb = 0; kb < 2; ++kb) {
-                        { L3_T0(); mbar_wait(BAR(stage), wphase); L3_ACC(2); }
-                        tc_fence_after_sync();
-                        const uint32_t w_hi = sbase + L3B_SMEM_W + stage * L3_STAGE_BYTES, w_lo = w_hi + 16384;
-                        const uint32_t b_hi = a2b + (0 * 2 + kb) * L3B_A2_PART, b_lo = a2b + (1 * 2 + kb) * L3B_A2_PART;
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t wa = (pass == 1) ? w_lo : w_hi;
-                            const uint32_t bb = (pass == 2) ? b_lo : b_hi;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(bb + k * 32), IDESC,
-                                        (kb | pass | k) ? 1u : 0u);
-                        }
-                        mma_commit_multicast(BAR(3 + stage), (uint16_t)0x3);    // stage released in BOTH CTAs' books
-                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1; }
-                    }
-                    mma_commit(BAR(10 + acc));
-                    if (++acc == 4) { acc = 0; aphase ^= 1; }
-                }
-                mma_commit(BAR(8 + buf));                                        // a2 buffer free
-                if (++buf == 2) { buf = 0; bphase ^= 1; }
-            }
-            if (p.dbg) {
-                dbg_acc[3] = clock64() - tl0;
-                for (int i = 0; i < 4; ++i) p.dbg[(size_t)cta * 8 + i] = dbg_acc[i];
-            }
-        }
-    } else if (warp < 6) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const bool stats = p.mu_s != nullptr;
-        int acc = 0; uint32_t aphase = 0;
-        for (int it = 0; it < niter; ++it) {
-            const int t = T0 + 2 * it + (int)rank;
-            const bool live = t < T1;
-            const int b = live ? t / p.tiles_per_cloud : 0, tt = live ? t % p.tiles_per_cloud : 0;
-            const int n0 = tt * L3B_NT;
-            const int nvalid = live ? ((p.N - n0 < L3B_NT) ? p.N - n0 : L3B_NT) : 0;
-            for (int mt = 0; mt < 8; ++mt) {
-                const int ch = mt * 128 + row;
-                const float mu = stats ? p.mu_s[ch] : 0.f;
-                { L3_T0(); mbar_wait(BAR(10 + acc), aphase); L3_ACC(6); }
-                tc_fence_after_sync();
-                const long long te0 = p.dbg ? clock64() : 0;
-                float best = -INFINITY; int bidx = 0; float css = 0.f;
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3B_NT);
-                for (int c0 = 0; c0 < L3B_NT; c0 += 32) {
-                    if (c0 >= nvalid) break;
-                    float v[32];
-                    tmem_ld32(tbase + (uint32_t)c0, v);
-                    if (c0 + 32 <= nvalid) {
-                        float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
-#pragma unroll
-                        for (int j = 4; j < 32; j += 4) {
-                            m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
-                        }
-                        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                        if (stats) {
-                            float c0s = 0.f, c1s = 0.f, c2s = 0.f, c3s = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float d0 = v[j] - mu, d1 = v[j + 1] - mu, d2 = v[j + 2] - mu, d3 = v[j + 3] - mu;
-                                c0s = fmaf(d0, d0, c0s); c1s = fmaf(d1, d1, c1s); c2s = fmaf(d2, d2, c2s); c3s = fmaf(d3, d3, c3s);
-                            }
-                            css += (c0s + c1s) + (c2s + c3s);
-                        }
-                        if (m > best) {
-                            best = m;
-                            int jj = 31;
-#pragma unroll
-                            for (int j = 30; j >= 0; --j) if (v[j] == m) jj = j;
-                            bidx = n0 + c0 + jj;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (c0 + j < nvalid) {
-                                if (stats) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
-                                if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
-                            }
-                        }
-                    }
-                }
-                tc_fence_before_sync();
-                mbar_arrive(BAR(14 + acc));
-                if (p.dbg) dbg_acc[7] += clock64() - te0;
-                if (++acc == 4) { acc = 0; aphase ^= 1; }
-                if (live) {
-                    const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
-                                                   (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
-                    atomicMax(&p.keys[(size_t)b * C3 + ch], key);
-                    if (stats) {
-                        const float iv = p.inv[ch];
-                        p.css_part[(size_t)t * C3 + ch] = css * iv * iv;
-                    }
-                }
-            }
-        }
-        if (p.dbg && warp == 2 && lane == 0) { p.dbg[(size_t)cta * 8 + 6] = dbg_acc[6]; p.dbg[(size_t)cta * 8 + 7] = dbg_acc[7]; }
-    } else {
-        // ===================== a2 producer (8 warps, double-buffered 128-point tiles) =====================
-        const int wp = warp - 6;
-        const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
-        const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
-        const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
-        int buf = 0; uint32_t bphase = 0;
-        for (int it = 0; it < niter; ++it) {
-            const int t = T0 + 2 * it + (int)rank;
-            const bool live = t < T1;
-            const int b = live ? t / p.tiles_per_cloud : 0, tt = live ? t % p.tiles_per_cloud : 0;
-            const int n0 = tt * L3B_NT;
-            const int nvalid = live ? ((p.N - n0 < L3B_NT) ? p.N - n0 : L3B_NT) : 0;
-            const float* src = p.Y2 + ((size_t)b * p.N + n0) * C2 + 4 * lane;
-            if (wp == 0 && lane == 0) {
-                const int t2 = t + 4;                           // two iterations ahead
-                if (t2 < T1) {
-                    const int b2 = t2 / p.tiles_per_cloud, tt2 = t2 % p.tiles_per_cloud;
-                    const int nv2 = (p.N - tt2 * L3B_NT < L3B_NT) ? p.N - tt2 * L3B_NT : L3B_NT;
-                    l2_prefetch(p.Y2 + ((size_t)b2 * p.N + (size_t)tt2 * L3B_NT) * C2, (uint32_t)nv2 * C2 * 4u);
-                }
-            }
-            { L3_T0(); mbar_wait(BAR(8 + buf), bphase ^ 1); L3_ACC(4); }
-            const long long tp0 = p.dbg ? clock64() : 0;
-            unsigned char* a2b = smem + buf * L3B_A2_BUF;
-            if (live) {
-                constexpr int U = 8;
-                for (int i0 = 0; i0 < L3B_NT / 8; i0 += U) {
-                    float4 y[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int r = wp + 8 * (i0 + u);
-                        y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int r = wp + 8 * (i0 + u);
-                        const bool ok = r < nvalid;
-                        float a0 = ok ? fminf(fmaxf(fmaf(sc0, y[u].x, sh0), 0.f), 60000.f) : 0.f;
-                        float a1 = ok ? fminf(fmaxf(fmaf(sc1, y[u].y, sh1), 0.f), 60000.f) : 0.f;
-                        float a2 = ok ? fminf(fmaxf(fmaf(sc2, y[u].z, sh2), 0.f), 60000.f) : 0.f;
-                        float a3 = ok ? fminf(fmaxf(fmaf(sc3, y[u].w, sh3), 0.f), 60000.f) : 0.f;
-                        __half2 h01, l01, h23, l23;
-                        split2(a0, a1, h01, l01);
-                        split2(a2, a3, h23, l23);
-                        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
-                        uint2 hv, lv;
-                        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-                        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-                        *reinterpret_cast<uint2*>(a2b + (0 * 2 + kb) * L3B_A2_PART + off) = hv;
-                        *reinterpret_cast<uint2*>(a2b + (1 * 2 + kb) * L3B_A2_PART + off) = lv;
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(BAR(6 + buf));
-            if (p.dbg) dbg_acc[5] += clock64() - tp0;
-            if (++buf == 2) { buf = 0; bphase ^= 1; }
-        }
-        if (p.dbg && wp == 0 && lane == 0) { p.dbg[(size_t)cta * 8 + 4] = dbg_acc[4]; p.dbg[(size_t)cta * 8 + 5] = dbg_acc[5]; }
-    }
-
-    tc_fence_before_sync();
-    __syncthreads();
-    cluster_sync_all();                 // nobody exits while the peer may still multicast into / arrive on this CTA
-    if (warp == 1) tmem_dealloc<512>(tmem);
-}
 
 // ====================================================================================================================
 // Version 3: CTA PAIRS with cta_group::2 MMAs (M = 256 channels x N = 256 points per instruction).
@@ -642,6 +87,7 @@ constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred sq
 // starts ~0.5 k cycles earlier -- the 3-stage ring otherwise runs dry (profiles/README.md).
 template <bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p) {
+    pdl_sync();
     constexpr int NSUB = SPLIT ? 6 : 3;                    // ring slots
     constexpr int SUB_BYTES = SPLIT ? L3_STAGE_BYTES / 2 : L3_STAGE_BYTES;
     constexpr int W_FULL = 0, W_FULLP = 6, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 24;
@@ -795,41 +241,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;                   // 0..3: which quarter of the 256 columns
         const int row = q * 32 + lane;
-        const bool stats = p.centre_out != nullptr;
+        const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;      // centred squares of my channel of block mt4 = 0..3, summed over my tiles
-        float mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, mu3 = 0.f;      // their centres, in accumulator units
-        if (stats) {
-            // centre[c] = W3[c] . mean(a2) (pilot) for my 4 x 32 channels: the warp forms one dot product at a time (each lane
-            // 4 consecutive k: coalesced 512-byte row reads, fixed shuffle tree -> the same bits in every warp and pair), lane i
-            // keeps the result of row i.  Runs while the pipeline fills.
-            const float m0 = (float)(p.s1_pilot[4 * lane + 0] * p.inv_n), m1 = (float)(p.s1_pilot[4 * lane + 1] * p.inv_n);
-            const float m2 = (float)(p.s1_pilot[4 * lane + 2] * p.inv_n), m3 = (float)(p.s1_pilot[4 * lane + 3] * p.inv_n);
-#pragma unroll
-            for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int chb = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + q * 32;
-                float mine = 0.f;
-#pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const float4 wv = *reinterpret_cast<const float4*>(p.W3f + (size_t)(chb + i) * C2 + 4 * lane);
-                    float sacc = fmaf(wv.x, m0, fmaf(wv.y, m1, fmaf(wv.z, m2, wv.w * m3)));
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                    if (lane == i) mine = sacc;
-                }
-                const int ch = chb + lane;
-                if (half == 0) p.centre_out[ch] = mine;          // every pair writes the same value
-                const float m = mine / p.inv[ch];
-                if (mt4 == 0) mu0 = m; else if (mt4 == 1) mu1 = m; else if (mt4 == 2) mu2 = m; else mu3 = m;
-            }
-        }
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt4 = 0; mt4 < 4; ++mt4) {
                 const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
-                const float mu = mt4 == 0 ? mu0 : (mt4 == 1 ? mu1 : (mt4 == 2 ? mu2 : mu3));
+                const float mu = stats ? p.mu_s[ch] : 0.f;
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
                 mbar_wait(BAR(TM_FULL + acc), aphase);
                 tc_fence_after_sync();
@@ -1009,10 +430,7 @@ inline DevInfo& dev_info() {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         if (d.sms <= 0) d.sms = 148;
         if (d.sms > 256) d.sms = 256;      // per-CTA partial buffers are sized for <= 256 CTAs (plan_tower_scratch)
-        cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, L3B_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_l3_fwd_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
         d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
         if (e != cudaSuccess) cudaGetLastError();
     }

@@ -131,10 +131,21 @@ __device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
+// MN-major SWIZZLE_128B descriptor: atoms of 64 M/N-elements (128 B) x 8 K-rows; atom pitch `lbo` bytes
+__device__ __forceinline__ uint64_t desc_sw128_mnmajor(uint32_t saddr, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // instruction descriptor for kind::f16, fp16 A/B (K-major), fp32 accumulate, M x N tile
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t idesc_f16_mn(int M, int N) { return idesc_f16(M, N) | (1u << 15) | (1u << 16); }   // both operands MN-major
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -215,6 +226,17 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+
+// O(1) activations are multiplied by 2^4 before the fp16 hi/lo split (keeps the lo parts in fp16's normal range)
+constexpr float ACT_SCALE = 16.0f;
+constexpr int ACT_SHIFT = 4;
+
+// tuning aid (builds with -DPGPD_DEBUG only): when non-null, the streaming kernels add their pipeline cycle counters here
+#ifdef PGPD_DEBUG
+__device__ long long* g_stream_dbg = nullptr;
+#else
+constexpr long long* g_stream_dbg = nullptr;
+#endif
 
 // fp32 -> (hi, lo) fp16 pair with hi + lo == x to ~22 bits (x must be pre-scaled into fp16's normal range)
 __device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {

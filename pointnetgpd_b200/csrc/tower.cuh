@@ -23,26 +23,12 @@
 #include "l2bwd.cuh"
 #ifndef PGPD_EMU
 #include "tc_l3.cuh"
-#include "tc_stream.cuh"
-#include "tc_accum.cuh"
 #include "tc_kb.cuh"
 #include "tc_ka.cuh"
 #include "tc_kf.cuh"
 #endif
 
 namespace pgpd {
-
-// which tcgen05 kernels may run (debugging aid): PGPD_TC_MASK bit0 layer-3 fwd, bit1 layer-2 fwd,
-// bit2 Gram (only with PGPD_KA=0), bit3 layer-2 bwd pass 1, bit4 fused layer-2/1 backward pass, bit5 unused, bit6 FC-head GEMMs.
-// Default: all.
-inline unsigned tc_mask() {
-    static int m = -1;
-    if (m < 0) {
-        const char* e = getenv("PGPD_TC_MASK");
-        m = e ? (int)strtol(e, nullptr, 0) : 0x7F;
-    }
-    return (unsigned)m;
-}
 
 // ================================================================================================
 // workspace
@@ -139,7 +125,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.nb_l2 = (int)((M + 127) / 128);
     w.nb_gram = (int)((M + GRAM_CHUNK - 1) / GRAM_CHUNK);
     w.moments = c.take<double>((size_t)B * 12);
-    w.rtmp = c.take<double>((size_t)REDUCE_MAX_SLICES * C2 * C2);
+    w.rtmp = c.take<double>((size_t)TL2_BLOCKS * C2 + 256);      // scratch rows of the fused tails (k_tail_l2 partials, BatchNorm-backward sums)
     w.dpart = c.take<double>((size_t)std::max(w.nb_a1 * C1, w.nb_a2 * C2));
     w.dsum = c.take<double>(C2);
     // persistent tcgen05 kernels write one partial row per CTA (<= TC_MAX_CTAS rows)
@@ -213,6 +199,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
 // per-block sums over points of a2 = relu(scale2*u2 + shift2); block = 128 channels x 2 slots.
 // pstride > 1: only every pstride-th point (Ms = ceil(M / pstride) samples) -- the pilot estimate of mean(a2).
 __global__ void k_a2_sum(const float* __restrict__ Y2, size_t Ms, size_t pstride, BnState st, double* __restrict__ part) {
+    pdl_sync();
     __shared__ double sh[256];
     const int tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
     const float sc = st.scale[k], sf = st.shift[k];
@@ -335,6 +322,7 @@ __global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict
                            double count, const float* __restrict__ gamma, BnState st,
                            float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
                            float* __restrict__ dvec, float* __restrict__ evec) {
+    pdl_sync();
     __shared__ double sh1[32][33], sh2[32][33];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
@@ -405,6 +393,7 @@ __global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, con
                       int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec, const float* __restrict__ W3,
                       const float* __restrict__ gram, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3,
                       KbPrepParams kp) {
+    pdl_sync();
     if ((int)blockIdx.x >= C3) { kb_prep_row(kp, (int)blockIdx.x - C3); return; }
     __shared__ float4 sh[16][32];
     __shared__ float s_cf[512];
@@ -523,6 +512,7 @@ __device__ __forceinline__ void da2_sort_cloud(const Da2SortParams& p, int b) {
 
 // one launch, two jobs that both depend on k_pool_bwd only: blocks [0, 32): Q / uvec (tails.cuh), blocks [32, 32 + B): the sort
 __global__ void __launch_bounds__(1024) k_q_uvec(QuParams p, Da2SortParams sp) {
+    pdl_sync();
     if ((int)blockIdx.x >= C2 / 4) { da2_sort_cloud(sp, (int)blockIdx.x - C2 / 4); return; }
     q_uvec_block(p);
 }
@@ -537,16 +527,22 @@ struct Da2AccumParams {
 // grid = multiple of 4 blocks (block j: column slice j % 4, clouds j / 4, j / 4 + gridDim.x / 4, ...), block = 1024 threads
 // = 32 warps (one row at a time each) x 32 lanes (columns); dynamic shared memory: the W3 slice [1024][32].
 __global__ void __launch_bounds__(1024) k_da2_accum(Da2AccumParams p) {
+    pdl_sync();
     float* w3s = dyn_smem<float>();
     __shared__ float s_cf[C3];
     __shared__ unsigned s_key[C3];
     __shared__ int s_rp[DA2_ROWPOS_LD];
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kq = (int)blockIdx.x & 3, cstep = (int)gridDim.x >> 2;
-    for (int i = tid; i < C3 * DA2_SLICE; i += 1024) {
-        const int c = i >> 5, j = i & 31;
-        w3s[i] = p.W3[(size_t)c * C2 + kq * DA2_SLICE + j];
+    {
+        // the slice: float4 per thread and row group, 8 loads in flight
+        const int j4 = tid & 7, c0 = tid >> 3;              // 128 rows per pass
+#pragma unroll 8
+        for (int c = c0; c < C3; c += 128)
+            *reinterpret_cast<float4*>(w3s + c * DA2_SLICE + 4 * j4) =
+                *reinterpret_cast<const float4*>(p.W3 + (size_t)c * C2 + kq * DA2_SLICE + 4 * j4);
     }
+    const int sub = lane >> 3, l8 = lane & 7;               // 4 rows per warp at a time, 8 lanes x 4 columns each
     for (int b = (int)blockIdx.x >> 2; b < p.B; b += cstep) {
         __syncthreads();
         s_cf[tid] = p.coef[(size_t)b * C3 + tid];
@@ -554,14 +550,16 @@ __global__ void __launch_bounds__(1024) k_da2_accum(Da2AccumParams p) {
         for (int i = tid; i < DA2_ROWPOS_LD; i += 1024) s_rp[i] = p.rowpos[(size_t)b * DA2_ROWPOS_LD + i];
         __syncthreads();
         const int nrows = s_rp[C3 + 3];
-        for (int r = warp; r < nrows; r += 32) {
+        for (int r = warp * 4 + sub; r < nrows; r += 128) {
             const int e0 = s_rp[r], e1 = s_rp[r + 1];
-            float acc = 0.f;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int e = e0; e < e1; ++e) {
                 const int c = (int)(s_key[e] & 1023u);
-                acc = fmaf(s_cf[c], w3s[c * DA2_SLICE + lane], acc);
+                const float cf = s_cf[c];
+                const float4 wv = *reinterpret_cast<const float4*>(w3s + c * DA2_SLICE + 4 * l8);
+                acc.x = fmaf(cf, wv.x, acc.x); acc.y = fmaf(cf, wv.y, acc.y); acc.z = fmaf(cf, wv.z, acc.z); acc.w = fmaf(cf, wv.w, acc.w);
             }
-            p.da2s[((size_t)b * C3 + r) * C2 + kq * DA2_SLICE + lane] = acc;
+            *reinterpret_cast<float4*>(p.da2s + ((size_t)b * C3 + r) * C2 + kq * DA2_SLICE + 4 * l8) = acc;
         }
     }
 }
@@ -688,15 +686,13 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     // centre of the layer-3 kernel's sum of squares); that kernel's operand producers accumulate the exact sum of a2 on the
     // way and k_tail_l3 corrects the statistics (var = sum (u-c)^2 / M - (mean - c)^2, an identity).
     bool l3_pilot = false;
-    size_t tl2_nsample = 1;
     if (a.train) {
         TailL2Params p{};
         p.css = w.fpart; p.n_css = n_css2; p.mean_u2 = w.bn[1].mean; p.count = count; p.bias2 = t.conv[1].b; p.bn2 = t.bn[1]; p.st2 = w.bn[1];
         p.Y2 = w.Y2; p.part = w.rtmp; p.counter = w.counters + 2;
-        p.W3 = t.conv[2].w; p.mean_u3 = tcp ? (float*)nullptr : w.bn[2].mean; p.S1 = w.S1;
+        p.W3 = t.conv[2].w; p.mean_u3 = w.bn[2].mean; p.S1 = w.S1; p.inv3 = w.sgn; p.mu_s = tcp ? w.mu_s : nullptr;
         const size_t pstride = M >= 4 * (size_t)TL2_SAMPLE ? M / TL2_SAMPLE : 1;
         p.pstride = pstride; p.nsample = (M + pstride - 1) / pstride;
-        tl2_nsample = p.nsample;
         launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(1024), 0, s, p);
         if (tcp) {
             l3_pilot = pstride > 1;
@@ -715,10 +711,9 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
 #ifndef PGPD_EMU
     if (tcp) {
         const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
-        tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, nullptr,
+        tc::L3Params p{w.Y2, w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, a.train ? w.mu_s : nullptr,
                        w.keys, w.fpart, a.B, a.N, tpc, ntiles, tc::l3_debug_buffer_if_enabled(),
-                       l3_pilot ? w.s1part : (float*)nullptr, w.bad,
-                       a.train ? w.S1 : (const double*)nullptr, 1.0 / (double)tl2_nsample, t.conv[2].w, a.train ? w.bn[2].mean : (float*)nullptr};
+                       l3_pilot ? w.s1part : (float*)nullptr, w.bad};
         const int sms = tc::dev_info().sms;
         const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
         profiler().begin(s);
