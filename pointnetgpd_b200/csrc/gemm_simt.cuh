@@ -91,7 +91,6 @@ __device__ __forceinline__ unsigned long long block_row_max_u64(const unsigned l
 //   __device__ void  epilogue(const Blk&, const float* scratch, float (&acc)[TM][TN], int ty, int tx, void* red) const;
 template <class Cfg, class P>
 __global__ void __launch_bounds__(Cfg::NT) gemm_kernel(P p) {
-    pdl_sync();
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN, NT = Cfg::NT;
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];

@@ -132,7 +132,6 @@ constexpr int BNH_CH = 8, BNH_LANES = 128, BNH_RMAX = 8;
 __global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ part, int nsl, int B, int C, int train,
                                                       const float* bias, pgpd_bn bn, BnState st, float limit,
                                                       float* __restrict__ U, float* __restrict__ Hout) {
-    pdl_sync();
     __shared__ double sh[BNH_LANES][BNH_CH + 1];
     __shared__ double smean[BNH_CH];
     __shared__ float s_sc[BNH_CH], s_sf[BNH_CH];
@@ -236,7 +235,6 @@ __global__ void __launch_bounds__(1024) k_bn_head_fwd(const float* __restrict__ 
 __global__ void __launch_bounds__(256) k_fc3_out(const float* __restrict__ Hm2, const float* __restrict__ W, const float* __restrict__ bias,
                                                  int B, int J, int add_identity, float* __restrict__ out, float* __restrict__ user1,
                                                  float* __restrict__ logp, float* __restrict__ user2) {
-    pdl_sync();
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
     const int b = (int)blockIdx.x * 8 + warp;
     if (b >= B) return;
@@ -271,7 +269,6 @@ __global__ void __launch_bounds__(256) k_fc3_out(const float* __restrict__ Hm2, 
 // dlogits = dlogp - softmax * sum_j dlogp
 __global__ void k_log_softmax_bwd(const float* __restrict__ logp, const float* __restrict__ dlogp, int B, int K,
                                   float* __restrict__ dlogits) {
-    pdl_sync();
     int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (b >= B) return;
     float s = 0.f;
@@ -284,7 +281,6 @@ __global__ void k_log_softmax_bwd(const float* __restrict__ logp, const float* _
 // lanes are added in order) + db3[j];  blocks [J, J + ceil(B/32)): dz2 of 32 clouds (8 per lane).
 __global__ void __launch_bounds__(1024) k_fc3_bwd(const float* __restrict__ dO, const float* __restrict__ Hm2, const float* __restrict__ W3,
                                                   int B, int J, float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ DZ2) {
-    pdl_sync();
     __shared__ float s_a[4][H2];
     __shared__ double s_b[4];
     const int i = (int)threadIdx.x & 255, ln = (int)threadIdx.x >> 8;
@@ -420,7 +416,6 @@ __device__ __forceinline__ void bn_head_bwd_block(int blk, const float* __restri
 __global__ void __launch_bounds__(1024) k_bn_head_bwd(float* __restrict__ DZ, const float* __restrict__ U, int B, int C, BnState st,
                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db,
                                                       unsigned* __restrict__ amax_part) {
-    pdl_sync();
     bn_head_bwd_block((int)blockIdx.x, nullptr, 0, nullptr, DZ, U, B, C, st, dgamma, dbeta, db, amax_part);
 }
 
@@ -431,7 +426,6 @@ __global__ void __launch_bounds__(1024) k_head_mid(int nbn, const float* __restr
                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db,
                                                    unsigned* __restrict__ amax_part,
                                                    const float* __restrict__ partW, int nslW, size_t nW, float* __restrict__ dW) {
-    pdl_sync();
     if ((int)blockIdx.x < nbn) {
         bn_head_bwd_block((int)blockIdx.x, partZ, nslZ, Hmask, DZ, U, B, C, st, dgamma, dbeta, db, amax_part);
         return;
@@ -447,7 +441,6 @@ __global__ void __launch_bounds__(1024) k_head_mid(int nbn, const float* __restr
 // out1[i] = sum_z part1[z][i] (i < n1);  out2[i] = sum_z part2[z][i] (i < n2)
 __global__ void __launch_bounds__(1024) k_finish2(const float* __restrict__ part1, int nsl1, size_t n1, float* __restrict__ out1,
                                                   const float* __restrict__ part2, int nsl2, size_t n2, float* __restrict__ out2) {
-    pdl_sync();
     size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
     const size_t n1r = ((n1 + 1023) / 1024) * 1024;
     if (i < n1r) {

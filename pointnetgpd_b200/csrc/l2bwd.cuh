@@ -44,7 +44,6 @@ struct KbRefParams {
 
 // block = 256 threads, persistent over a contiguous range of 32-point tiles (tiles never straddle clouds)
 __global__ void __launch_bounds__(256) k_kb_ref(KbRefParams p) {
-    pdl_sync();
     __shared__ float sdz[KB_REF_NT][C2];
     __shared__ float sa1[KB_REF_NT][C1];
     __shared__ float sx[3][KB_REF_NT];
@@ -143,7 +142,6 @@ __global__ void __launch_bounds__(768) k_kb_l1(int B, const float* __restrict__ 
                         const float* __restrict__ trans, const float* __restrict__ W1, BnState st1, const float* __restrict__ m1,
                         const float* __restrict__ m2, float* __restrict__ dW1part, float* __restrict__ dtrans, unsigned* counter,
                         float* __restrict__ dW1, float* __restrict__ db1, Dw2Params d2) {
-    pdl_sync();
     if ((int)blockIdx.x >= B) { dw2_row(d2, (int)blockIdx.x - B); return; }
     __shared__ float G[C1 * 3];
     __shared__ float hs[4][C1 * 3];

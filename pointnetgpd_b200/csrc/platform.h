@@ -26,8 +26,6 @@ inline std::atomic<unsigned long long>& launch_counter() { static std::atomic<un
 #ifdef PGPD_EMU
 template <class T> __device__ __forceinline__ T* dyn_smem() { return reinterpret_cast<T*>(emu::dyn_smem()); }
 
-__device__ __forceinline__ void pdl_sync() {}
-
 template <class... KArgs, class... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args... args) {
     ++launch_counter();
@@ -39,35 +37,10 @@ template <class T> __device__ __forceinline__ T* dyn_smem() {
     return reinterpret_cast<T*>(pgpd_dyn_smem_);
 }
 
-// Programmatic dependent launch (sm_90+): every kernel of this library starts with pdl_sync(), which first waits until the
-// grid it depends on has completed and flushed its memory (griddepcontrol.wait) and then allows the NEXT grid of the stream
-// to be launched early (griddepcontrol.launch_dependents): that grid's blocks are scheduled as SMs free up and park at their
-// own wait, so launch latency and block start-up overlap the tail of the previous kernel instead of following it.  Launches
-// carry the matching attribute; with ~60 short dependent kernels per training step this is worth ~5 % of the step.
-#ifndef PGPD_NO_PDL
-#define PGPD_PDL 1
-#endif
-__device__ __forceinline__ void pdl_sync() {
-#ifdef PGPD_PDL
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-
 template <class... KArgs, class... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     ++launch_counter();
-#ifdef PGPD_PDL
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-#else
     kernel<<<grid, block, smem, stream>>>(args...);
-#endif
 }
 #endif
 

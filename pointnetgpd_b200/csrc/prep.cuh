@@ -17,7 +17,6 @@ constexpr int FRAME_DOUBLES = 15;
 __global__ void k_crop_box(const float* __restrict__ pc, int P, const double* __restrict__ frames,
                            const int* __restrict__ offsets, int* __restrict__ counts,
                            float* __restrict__ out_pts, int* __restrict__ out_idx) {
-    pdl_sync();
     __shared__ int warp_cnt[8];
     __shared__ int base_s;
     const int g = (int)blockIdx.x, tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -73,7 +72,6 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 // grid = (candidates, repeat), block = 256.  Output x is channel-major [C*repeat][3][N] (the model's input layout).
 __global__ void k_resample(const float* __restrict__ pts, const int* __restrict__ offsets, int N, unsigned long long seed,
                            float* __restrict__ out_x, int* __restrict__ out_idx) {
-    pdl_sync();
     __shared__ int red[256];
     __shared__ int warp_cnt[8];
     __shared__ int base_s;

@@ -66,7 +66,6 @@ __device__ __forceinline__ int prepack_elem(float w, float mx, int r, int k, __h
 #endif
 
 __global__ void __launch_bounds__(PRE_THREADS) k_tower_pre(PreParams p) {
-    pdl_sync();
     __shared__ double sh[PRE_THREADS];
     __shared__ double raw[12];
     __shared__ float redf[PRE_THREADS];
@@ -223,7 +222,6 @@ struct A1Params {
 };
 
 __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
-    pdl_sync();
     __shared__ float xs[3][A1_CHUNK * A1_CPB];
     __shared__ double sh[A1_THREADS];
     __shared__ double vs[C1];
@@ -327,7 +325,6 @@ struct TailL2Params {
 };
 
 __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
-    pdl_sync();
     __shared__ double sh[1024];
     __shared__ float s_sc[C2], s_sf[C2];
     __shared__ double vs[C2];
@@ -461,7 +458,6 @@ struct TailL3Params {
 };
 
 __global__ void __launch_bounds__(1024) k_tail_l3(TailL3Params p) {
-    pdl_sync();
     __shared__ double sh[TL3_LANES][TL3_CH + 1];
     __shared__ double vs[C2];
     __shared__ float s_sc[TL3_CH], s_sf[TL3_CH];
@@ -648,7 +644,6 @@ struct TailKaParams {
 };
 
 __global__ void __launch_bounds__(1024) k_tail_ka(TailKaParams p) {
-    pdl_sync();
     __shared__ double sh[32][33];
     const int tid = (int)threadIdx.x;
     const int n_gram = p.gcols / 256;
@@ -822,7 +817,6 @@ struct TailKbParams {
 constexpr int TKB_BLOCKS = 52;
 
 __global__ void __launch_bounds__(1024) k_tail_kb(TailKbParams p) {
-    pdl_sync();
     __shared__ double sh[32][33];
     const int tid = (int)threadIdx.x, blk = (int)blockIdx.x;
     if (blk < 48) {

@@ -45,7 +45,6 @@ struct GemmParams {
 // consumer takes the max over the gridDim.x values, see gemm_op_scale).
 // grid = (blocks, 2), block = 256; array lengths must be multiples of 4 and the pointers 16-byte aligned.
 __global__ void k_absmax2(const float* __restrict__ a, size_t na, const float* __restrict__ b, size_t nb, unsigned* __restrict__ out) {
-    pdl_sync();
     __shared__ float sh[8];
     const int tid = (int)threadIdx.x, which = (int)blockIdx.y;
     const float4* p = reinterpret_cast<const float4*>(which ? b : a);
@@ -158,7 +157,6 @@ __device__ __forceinline__ void gemm_stage(const GemmOp& o, float scale, int mn0
 }
 
 __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_tc(GemmParams p) {
-    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);

@@ -51,7 +51,6 @@ struct KbParams {
 };
 
 __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
-    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);

@@ -29,7 +29,6 @@ struct KfParams {
 };
 
 __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
-    pdl_sync();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);

@@ -87,7 +87,6 @@ constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred sq
 // starts ~0.5 k cycles earlier -- the 3-stage ring otherwise runs dry (profiles/README.md).
 template <bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p) {
-    pdl_sync();
     constexpr int NSUB = SPLIT ? 6 : 3;                    // ring slots
     constexpr int SUB_BYTES = SPLIT ? L3_STAGE_BYTES / 2 : L3_STAGE_BYTES;
     constexpr int W_FULL = 0, W_FULLP = 6, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 24;

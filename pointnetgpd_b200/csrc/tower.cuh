@@ -79,8 +79,6 @@ struct TowerScratch {
     float* uvec;      // [128]
     float* da2s;      // [B*1024][128] compact rows of the sparse part of d a2
     int* slot;        // [M]  row in da2s or -1
-    unsigned* skeys;  // [B][1024] sorted (arg-max point, channel) keys of every cloud
-    int* rowpos;      // [B][DA2_ROWPOS_LD] row boundaries in skeys
     float* DZ2;       // [M][128]
     float* m1_2; float* m2_2;   // [128]
     float* m1_1; float* m2_1;   // [64]
@@ -175,8 +173,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
         w.uvec = c.take<float>(C2);
         w.da2s = c.take<float>((size_t)B * C3 * C2);
         w.slot = c.take<int>(M);
-        w.skeys = c.take<unsigned>((size_t)B * C3);
-        w.rowpos = c.take<int>((size_t)B * (C3 + 4));
         w.DZ2 = c.take<float>(M * C2);
         w.m1_2 = c.take<float>(C2); w.m2_2 = c.take<float>(C2);
         w.m1_1 = c.take<float>(C1); w.m2_1 = c.take<float>(C1);
@@ -199,7 +195,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
 // per-block sums over points of a2 = relu(scale2*u2 + shift2); block = 128 channels x 2 slots.
 // pstride > 1: only every pstride-th point (Ms = ceil(M / pstride) samples) -- the pilot estimate of mean(a2).
 __global__ void k_a2_sum(const float* __restrict__ Y2, size_t Ms, size_t pstride, BnState st, double* __restrict__ part) {
-    pdl_sync();
     __shared__ double sh[256];
     const int tid = (int)threadIdx.x, k = tid & 127, q = tid >> 7;
     const float sc = st.scale[k], sf = st.shift[k];
@@ -322,7 +317,6 @@ __global__ void k_pool_bwd(const float* __restrict__ dG, const float* __restrict
                            double count, const float* __restrict__ gamma, BnState st,
                            float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
                            float* __restrict__ dvec, float* __restrict__ evec) {
-    pdl_sync();
     __shared__ double sh1[32][33], sh2[32][33];
     const int tid = (int)threadIdx.x, cx = tid & 31, ry = tid >> 5;
     const int c = (int)blockIdx.x * 32 + cx;
@@ -393,7 +387,6 @@ __global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, con
                       int B, int N, const float* __restrict__ dvec, const float* __restrict__ evec, const float* __restrict__ W3,
                       const float* __restrict__ gram, const double* __restrict__ S1, float* __restrict__ dW3, float* __restrict__ db3,
                       KbPrepParams kp) {
-    pdl_sync();
     if ((int)blockIdx.x >= C3) { kb_prep_row(kp, (int)blockIdx.x - C3); return; }
     __shared__ float4 sh[16][32];
     __shared__ float s_cf[512];
@@ -446,28 +439,18 @@ __global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, con
     }
 }
 
-// ---- sparse part of d a2: rows  sum_{c : argmax(b,c)=p} coef[b][c] W3[c][:]  for the arg-max points of every cloud -----------
-// Two steps.  (1) da2_sort_cloud (one 1024-thread block per cloud; runs as extra blocks of k_q_uvec): sort the cloud's
-// (arg-max point, channel) pairs, find the row starts, publish the sorted keys + row boundaries, and slot[point] = row.
-// (2) k_da2_accum (persistent): every block keeps a 32-column slice of W3 (128 KB) in shared memory and forms its columns of the
-// rows of the clouds it owns -- round 1 pulled the W3 rows from L2 for every (cloud, channel) pair (268 MB per launch for a 512 KB
-// matrix; profiles/README.md).  Entries of a row are summed in ascending channel order: reproducible.
-constexpr int DA2_ROWPOS_LD = C3 + 4;           // row starts of a cloud + end sentinel (+ nrows in the last slot)
-
-struct Da2SortParams {
-    const float* coef; const int* idx; int N;
-    unsigned* skeys;        // [B][1024] sorted (point << 10 | channel), 0xFFFFFFFF = unused
-    int* rowpos;            // [B][DA2_ROWPOS_LD]: row r covers sorted entries [rowpos[r], rowpos[r+1]); rowpos[C3 + 3] = nrows
-    int* slot;              // [M] row in da2s (b * 1024 + r) or -1
-};
-
-__device__ __forceinline__ void da2_sort_cloud(const Da2SortParams& p, int b) {
+// sparse part of d a2: rows  sum_{c : argmax(b,c)=p} coef[b][c] W3[c][:]  for the arg-max points of one cloud.
+// block = 1024 threads (one per channel) = one cloud.
+__global__ void k_da2_sparse(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ W3, int N,
+                             float* __restrict__ da2s, int* __restrict__ slot) {
     __shared__ unsigned sk[C3];
     __shared__ int scan[2][C3];
-    const int tid = (int)threadIdx.x;
+    __shared__ int rowpos[C3 + 1];
+    __shared__ int nrows_s;
+    const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
     {
-        const float cf = p.coef[(size_t)b * C3 + tid];
-        sk[tid] = (cf != 0.f) ? (((unsigned)p.idx[(size_t)b * C3 + tid] << 10) | (unsigned)tid) : 0xFFFFFFFFu;
+        const float cf = coef[(size_t)b * C3 + tid];
+        sk[tid] = (cf != 0.f) ? (((unsigned)idx[(size_t)b * C3 + tid] << 10) | (unsigned)tid) : 0xFFFFFFFFu;
     }
     __syncthreads();
     // bitonic sort of 1024 keys
@@ -497,72 +480,49 @@ __device__ __forceinline__ void da2_sort_cloud(const Da2SortParams& p, int b) {
         __syncthreads();
     }
     const int rowid = scan[cur][tid] - 1;   // for valid entries
-    int* rp = p.rowpos + (size_t)b * DA2_ROWPOS_LD;
-    p.skeys[(size_t)b * C3 + tid] = key;
-    if (start) {
-        rp[rowid] = tid;
-        p.slot[(size_t)b * p.N + (key >> 10)] = b * C3 + rowid;
+    if (start) rowpos[rowid] = tid;
+    if (tid == C3 - 1) nrows_s = scan[cur][tid];
+    __syncthreads();
+    const int nrows = nrows_s;
+    if (tid == 0) {
+        // end sentinel: first invalid entry (or 1024)
+        int nvalid = 0;
+        // binary search for the first invalid key (keys are sorted, invalid = max)
+        int lo = 0, hi = C3;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (sk[mid] != 0xFFFFFFFFu) lo = mid + 1; else hi = mid; }
+        nvalid = lo;
+        rowpos[nrows] = nvalid;
     }
-    // end sentinel: position of the first invalid key (keys are sorted, invalid = max); number of rows
-    const bool first_invalid = !valid && (tid == 0 || sk[tid - 1] != 0xFFFFFFFFu);
-    const int nrows = scan[cur][C3 - 1];
-    if (first_invalid) rp[nrows] = tid;
-    if (tid == C3 - 1) { if (valid) rp[nrows] = C3; rp[C3 + 3] = nrows; }
-}
-
-// one launch, two jobs that both depend on k_pool_bwd only: blocks [0, 32): Q / uvec (tails.cuh), blocks [32, 32 + B): the sort
-__global__ void __launch_bounds__(1024) k_q_uvec(QuParams p, Da2SortParams sp) {
-    pdl_sync();
-    if ((int)blockIdx.x >= C2 / 4) { da2_sort_cloud(sp, (int)blockIdx.x - C2 / 4); return; }
-    q_uvec_block(p);
-}
-
-constexpr int DA2_SLICE = 32;                    // columns of W3 per block
-constexpr int DA2_SMEM_BYTES = C3 * DA2_SLICE * 4;
-struct Da2AccumParams {
-    const float* coef; const float* W3; const unsigned* skeys; const int* rowpos; int B;
-    float* da2s;            // [B*1024][128]
-};
-
-// grid = multiple of 4 blocks (block j: column slice j % 4, clouds j / 4, j / 4 + gridDim.x / 4, ...), block = 1024 threads
-// = 32 warps (one row at a time each) x 32 lanes (columns); dynamic shared memory: the W3 slice [1024][32].
-__global__ void __launch_bounds__(1024) k_da2_accum(Da2AccumParams p) {
-    pdl_sync();
-    float* w3s = dyn_smem<float>();
-    __shared__ float s_cf[C3];
-    __shared__ unsigned s_key[C3];
-    __shared__ int s_rp[DA2_ROWPOS_LD];
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kq = (int)blockIdx.x & 3, cstep = (int)gridDim.x >> 2;
-    {
-        // the slice: float4 per thread and row group, 8 loads in flight
-        const int j4 = tid & 7, c0 = tid >> 3;              // 128 rows per pass
-#pragma unroll 8
-        for (int c = c0; c < C3; c += 128)
-            *reinterpret_cast<float4*>(w3s + c * DA2_SLICE + 4 * j4) =
-                *reinterpret_cast<const float4*>(p.W3 + (size_t)c * C2 + kq * DA2_SLICE + 4 * j4);
-    }
-    const int sub = lane >> 3, l8 = lane & 7;               // 4 rows per warp at a time, 8 lanes x 4 columns each
-    for (int b = (int)blockIdx.x >> 2; b < p.B; b += cstep) {
-        __syncthreads();
-        s_cf[tid] = p.coef[(size_t)b * C3 + tid];
-        s_key[tid] = p.skeys[(size_t)b * C3 + tid];
-        for (int i = tid; i < DA2_ROWPOS_LD; i += 1024) s_rp[i] = p.rowpos[(size_t)b * DA2_ROWPOS_LD + i];
-        __syncthreads();
-        const int nrows = s_rp[C3 + 3];
-        for (int r = warp * 4 + sub; r < nrows; r += 128) {
-            const int e0 = s_rp[r], e1 = s_rp[r + 1];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int e = e0; e < e1; ++e) {
-                const int c = (int)(s_key[e] & 1023u);
-                const float cf = s_cf[c];
-                const float4 wv = *reinterpret_cast<const float4*>(w3s + c * DA2_SLICE + 4 * l8);
-                acc.x = fmaf(cf, wv.x, acc.x); acc.y = fmaf(cf, wv.y, acc.y); acc.z = fmaf(cf, wv.z, acc.z); acc.w = fmaf(cf, wv.w, acc.w);
-            }
-            *reinterpret_cast<float4*>(p.da2s + ((size_t)b * C3 + r) * C2 + kq * DA2_SLICE + 4 * l8) = acc;
+    __syncthreads();
+    // one WARP per output row (lane = 4 consecutive channels, float4): 32 independent rows in flight per block.
+    // The entries of a row are summed in ascending channel order (the sort order), so the result is reproducible.
+    const int wrp = tid >> 5, lane = tid & 31;
+    const float4* W3v = reinterpret_cast<const float4*>(W3);
+    for (int r = wrp; r < nrows; r += 32) {
+        const int e0 = rowpos[r], e1 = rowpos[r + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = e0;
+        for (; e + 1 < e1; e += 2) {            // two entries per iteration: their loads are independent
+            const int c0 = (int)(sk[e] & 1023u), c1 = (int)(sk[e + 1] & 1023u);
+            const float f0 = coef[(size_t)b * C3 + c0], f1 = coef[(size_t)b * C3 + c1];
+            const float4 w0 = W3v[(size_t)c0 * (C2 / 4) + lane], w1 = W3v[(size_t)c1 * (C2 / 4) + lane];
+            acc.x = fmaf(f0, w0.x, acc.x); acc.y = fmaf(f0, w0.y, acc.y); acc.z = fmaf(f0, w0.z, acc.z); acc.w = fmaf(f0, w0.w, acc.w);
+            acc.x = fmaf(f1, w1.x, acc.x); acc.y = fmaf(f1, w1.y, acc.y); acc.z = fmaf(f1, w1.z, acc.z); acc.w = fmaf(f1, w1.w, acc.w);
         }
+        if (e < e1) {
+            const int c0 = (int)(sk[e] & 1023u);
+            const float f0 = coef[(size_t)b * C3 + c0];
+            const float4 w0 = W3v[(size_t)c0 * (C2 / 4) + lane];
+            acc.x = fmaf(f0, w0.x, acc.x); acc.y = fmaf(f0, w0.y, acc.y); acc.z = fmaf(f0, w0.z, acc.z); acc.w = fmaf(f0, w0.w, acc.w);
+        }
+        const size_t row = (size_t)b * C3 + r;
+        reinterpret_cast<float4*>(da2s)[row * (C2 / 4) + lane] = acc;
+        if (lane == 0) slot[(size_t)b * N + (sk[e0] >> 10)] = (int)row;
     }
 }
+
+// Q = W3^T diag(d) W3, uvec = W3^T e (+ the operand image of Q): tails.cuh: q_uvec_block
+__global__ void __launch_bounds__(1024) k_q_uvec(QuParams p) { q_uvec_block(p); }
 
 // ---- layer 2 backward, pass 1: d a2 -> dz2 (stored) + BN2 backward sums ---------------------------
 struct ProbL2BwdA {
@@ -767,27 +727,12 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
 #ifndef PGPD_EMU
         p.act_shift = tc::ACT_SHIFT;
 #endif
-        // the same launch sorts every cloud's (arg-max point, channel) pairs (blocks [32, 32 + B)): both jobs depend on
-        // k_pool_bwd only
-        cudaMemsetAsync(w.slot, 0xFF, M * sizeof(int), s);
-        Da2SortParams sp{w.coef, w.idx, a.N, w.skeys, w.rowpos, w.slot};
-        launch(k_q_uvec, dim3(C2 / 4 + a.B), dim3(1024), 0, s, p, sp);
+        launch(k_q_uvec, dim3(C2 / 4), dim3(1024), 0, s, p);
     }
 
     // ---- sparse part of d a2 -----------------------------------------------------------------------
-    {
-        int grid = 8;
-#ifndef PGPD_EMU
-        if (tcp) grid = (tc::dev_info().sms / 4) * 4;
-        else { static int sms_cached = 0; if (!sms_cached) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev); } grid = (sms_cached / 4) * 4; }
-        static int attr_done[64] = {0};
-        { int dev = 0; cudaGetDevice(&dev); if (!attr_done[dev & 63]) { cudaFuncSetAttribute(k_da2_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, DA2_SMEM_BYTES); attr_done[dev & 63] = 1; } }
-#endif
-        if (grid > 4 * a.B) grid = 4 * a.B;
-        if (grid < 4) grid = 4;
-        Da2AccumParams ap{w.coef, t.conv[2].w, w.skeys, w.rowpos, a.B, w.da2s};
-        launch(k_da2_accum, dim3(grid), dim3(1024), (size_t)DA2_SMEM_BYTES, s, ap);
-    }
+    cudaMemsetAsync(w.slot, 0xFF, M * sizeof(int), s);
+    launch(k_da2_sparse, dim3(a.B), dim3(C3), 0, s, (const float*)w.coef, (const int*)w.idx, t.conv[2].w, a.N, w.da2s, w.slot);
 
     // ---- pass A: d a2 -> dz2 (stored), BatchNorm2 backward sums, Gram matrix of a2 --------------------------------------------
     TailKaParams tk{};
