@@ -310,12 +310,13 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
 // grid = TL2_BLOCKS, block = 1024 = 128 channels x 8 lanes.
 // ================================================================================================
 constexpr int TL2_BLOCKS = 32;
-constexpr int TL2_SAMPLE = 8192;              // points of the pilot estimate of mean(a2) (256 per block)
+constexpr int TL2_SPB = 256;                  // sample points per block of the pilot estimate of mean(a2)
 struct TailL2Params {
     const float* css; int n_css;              // [n_css][128] partial sums of (u2 - mean)^2
     int bn_done;                              // 1: BatchNorm2 is already finalised (second call of the CUDA-core path): only read st2
     const float* mean_u2; double count; const float* bias2; pgpd_bn bn2; BnState st2;
-    const float* Y2; size_t nsample, pstride;  // pilot: points P = i * pstride, i < nsample   (a2part == null)
+    const float* Y2; size_t npoints, pstride;  // pilot (a2part == null): block b samples points ((b * TL2_SPB + j) * pstride) mod npoints
+    size_t nsample;                           // CUDA-core path: number of points the partial rows cover
     const double* a2part; int n_a2part;       // or: exact partial rows [n][128] (nsample = number of points they cover)
     double* part;                             // [TL2_BLOCKS][128] scratch
     unsigned* counter;
@@ -360,12 +361,14 @@ __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
 #pragma unroll 4
         for (int r = (int)blockIdx.x * 8 + q; r < p.n_a2part; r += 8 * (int)gridDim.x) acc += p.a2part[(size_t)r * C2 + c];
     } else {
+        // pilot: this block's own TL2_SPB sample points, spread over the batch (indices wrap around when the batch is small)
         const float sc = s_sc[c], sf = s_sf[c];
         float f = 0.f;
-        const size_t stride = (size_t)gridDim.x * 8;
-        const size_t rs = p.pstride * C2;
 #pragma unroll 8
-        for (size_t i = (size_t)blockIdx.x * 8 + q; i < p.nsample; i += stride) f += relu_nan(sc * p.Y2[i * rs + c] + sf);
+        for (int j = q; j < TL2_SPB; j += 8) {
+            const size_t P = (((size_t)blockIdx.x * TL2_SPB + j) * p.pstride) % p.npoints;
+            f += relu_nan(sc * p.Y2[P * C2 + c] + sf);
+        }
         acc = (double)f;
     }
     sh[tid] = acc;
@@ -381,13 +384,7 @@ __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
     if (p.mu_s) {
         // tensor-core path: centres of my 32 channels from my own samples (one warp per row of W3: coalesced, fixed shuffle tree)
         __syncthreads();
-        size_t mine = 0;                        // samples this block summed: i = blockIdx*8 + q + k * 8 * gridDim, i < nsample
-        {
-            const size_t first = (size_t)blockIdx.x * 8, stride = (size_t)gridDim.x * 8;
-            for (int qq = 0; qq < 8; ++qq)
-                if (first + qq < p.nsample) mine += (p.nsample - 1 - (first + qq)) / stride + 1;
-        }
-        const double inv_n = mine ? 1.0 / (double)mine : 0.0;
+        const double inv_n = 1.0 / (double)TL2_SPB;
         const int r = (int)blockIdx.x * (C3 / TL2_BLOCKS) + warp;
         if (warp < C3 / TL2_BLOCKS) {
             double s = 0.0;

@@ -651,11 +651,11 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         p.css = w.fpart; p.n_css = n_css2; p.mean_u2 = w.bn[1].mean; p.count = count; p.bias2 = t.conv[1].b; p.bn2 = t.bn[1]; p.st2 = w.bn[1];
         p.Y2 = w.Y2; p.part = w.rtmp; p.counter = w.counters + 2;
         p.W3 = t.conv[2].w; p.mean_u3 = w.bn[2].mean; p.S1 = w.S1; p.inv3 = w.sgn; p.mu_s = tcp ? w.mu_s : nullptr;
-        const size_t pstride = M >= 4 * (size_t)TL2_SAMPLE ? M / TL2_SAMPLE : 1;
-        p.pstride = pstride; p.nsample = (M + pstride - 1) / pstride;
+        const size_t total_samples = (size_t)TL2_BLOCKS * TL2_SPB;
+        p.npoints = M; p.pstride = M > total_samples ? M / total_samples : 1; p.nsample = M;
         launch(k_tail_l2, dim3(TL2_BLOCKS), dim3(1024), 0, s, p);
         if (tcp) {
-            l3_pilot = pstride > 1;
+            l3_pilot = true;        // the centres are estimates: the layer-3 kernel accumulates the exact sum of a2, k_tail_l3 corrects
         } else {
             // CUDA-core path: its layer-3 kernel centres the squares on the exact mean, so the sum of a2 over ALL points is
             // taken now (BatchNorm2 is final) and the tail runs once more for the mean propagation only
