@@ -303,7 +303,7 @@ def main():
     if args.config == "train":
         model.train()
         opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True, capturable=True)
-        sync = FlatGradAllReduce(list(model.parameters()), world).install()   # buckets all-reduced from inside the backward, overlapped
+        sync = FlatGradAllReduce(list(model.parameters()), world, overlap=os.environ.get("PGPD_DDP_OVERLAP", "1") != "0").install()   # all-reduce issued from inside the backward
         flags_extra = A.F_SIMT if args.simt else 0
         if flags_extra:
             from pointnetgpd_b200.functional import run_module
@@ -472,7 +472,8 @@ def main():
     if rank == 0:
         peaks, peak_src = load_peaks()
         M = B * N
-        k3_flops = 2.0 * 128 * 1024 * M                       # layer-3 GEMM of one tower forward, algorithmic
+        fused = args.config != "train" and not args.simt    # eval forward: ONE kernel per tower (layers 1-3 + max-pool, tc_fused.cuh)
+        k3_flops = 2.0 * (3 * 64 + 64 * 128 + 128 * 1024) * M if fused else 2.0 * 128 * 1024 * M     # algorithmic flops per launch
         k3_ms = (tot.value / nl.value) if nl.value else None
         # a 20-step timed region lasts ~50 ms: the like-for-like denominator is the burst figure (a kernel timed inside a
         # seconds-long step would use bf16_tflops_sustained)
@@ -486,7 +487,8 @@ def main():
                 traffic_src = "profiles/" + name
                 break
         ach = (k3_flops / (k3_ms * 1e-3) / 1e12) if k3_ms else None
-        roofline = {"bound": "tensor", "kernel": "tower layer-3 GEMM (128->1024) + max-pool epilogue, one launch per tower forward",
+        roofline = {"bound": "tensor", "kernel": ("fused tower 3->64->128->1024 + max-pool (eval), one launch per tower forward" if fused else
+                                                  "tower layer-3 GEMM (128->1024) + max-pool epilogue, one launch per tower forward"),
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                     "peak_source": peak_src + " bf16_tflops (burst: the timed region is tens of ms)",
                     "frac_vs_sustained_peak": (ach / float(peaks["bf16_tflops_sustained"])) if ach and "bf16_tflops_sustained" in peaks else None,

@@ -26,6 +26,7 @@
 #include "tc_kb.cuh"
 #include "tc_ka.cuh"
 #include "tc_kf.cuh"
+#include "tc_fused.cuh"
 #endif
 
 namespace pgpd {
@@ -617,6 +618,27 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         const int n_sign = tcp ? 0 : C3 / PRE_THREADS;
         launch(k_tower_pre, dim3(p.n_mom + p.n_w2 + p.n_w3 + n_sign), dim3(PRE_THREADS), 0, s, p);
     }
+
+#ifndef PGPD_EMU
+    // ---- eval mode on the tensor-core path: the whole tower in ONE kernel (tc_fused.cuh); a1 / u2 / a2 never leave the SM --------
+    if (tcp && !a.train && tc::fused_configure()) {
+        const int tpc = idiv_up(a.N, tc::L3_NT), ntiles = a.B * tpc;
+        tc::FusedParams p{a.x, a.trans, t.conv[0].w, w.bn[0].scale, w.bn[0].shift, (const __half*)w.wimg_s, w.inv_s,
+                          w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, w.keys, a.B, a.N, tpc, ntiles, w.bad};
+        const int sms = tc::dev_info().sms;
+        const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
+        profiler().begin(s);
+        launch(tc::k_tower_fused_eval, dim3(2 * pairs), dim3(tc::FZ_THREADS), (size_t)tc::FZ_SMEM_BYTES, s, p);
+        profiler().end(s);
+        TailL3Params q{};
+        q.B = a.B; q.relu_last = a.relu_last ? 1 : 0; q.train = 0;
+        q.keys = w.keys; q.sgn = w.sgn; q.st3 = w.bn[2];
+        q.pooled = pooled; q.uext = nullptr; q.idx = nullptr;
+        q.bad = w.bad; q.limit = act_limit;
+        launch(k_tail_l3, dim3(C3 / TL3_CH), dim3(1024), 0, s, q);
+        return;
+    }
+#endif
 
     // ---- layer 1 (+ train: sum of a1, mean of the layer-2 pre-activation) ---------------------------------------------------
     {

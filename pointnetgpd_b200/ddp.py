@@ -21,7 +21,8 @@ class FlatGradAllReduce:
     a model wrapped differently): packs into a persistent flat buffer, one all-reduce, writes the averages back in
     place.  install(): the overlapped, copy-free path described in the module docstring."""
 
-    def __init__(self, params, world_size=None, group=None):
+    def __init__(self, params, world_size=None, group=None, overlap=True):
+        self.overlap = overlap
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         if world_size is None:
@@ -57,6 +58,13 @@ class FlatGradAllReduce:
         cur = torch.cuda.current_stream(flat.device)
         if self.side is None:
             self.side = torch.cuda.Stream(device=flat.device)
+        if not self.overlap:
+            # one all-reduce of the whole flat buffer on the compute stream once the backward is complete
+            if stage == 1:
+                self._avg(flat)
+                self._in_hook_step = True
+                self.hooked_steps += 1
+            return
         if stage == 0:
             self.side.wait_stream(cur)                 # bucket 0 is final on the compute stream
             with torch.cuda.stream(self.side):
