@@ -106,8 +106,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                         mbar_wait(BAR(W_EMPTY + stage), phase ^ 1);
                         mbar_arrive_expect_tx(BAR(W_FULL + stage), L3_STAGE_BYTES);
                         const uint32_t dst = sbase + FZ_W + stage * L3_STAGE_BYTES;
-                        bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(W_FULL + stage));
-                        bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(W_FULL + stage));
+#pragma unroll
+                        for (int cpy = 0; cpy < L3_WCOPIES; ++cpy)
+                            bulk_g2s(dst + cpy * (L3_STAGE_BYTES / L3_WCOPIES), src + cpy * (L3_STAGE_BYTES / L3_WCOPIES),
+                                     L3_STAGE_BYTES / L3_WCOPIES, BAR(W_FULL + stage));
                         if (++stage == 3) { stage = 0; phase ^= 1; }
                     }
         }

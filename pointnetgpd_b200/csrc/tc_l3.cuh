@@ -29,6 +29,10 @@ namespace pgpd { namespace tc {
 
 constexpr int L3_NT = 256;                        // points per tile (MMA N)
 constexpr int L3_STAGES = 3;
+#ifndef PGPD_L3_WCOPIES
+#define PGPD_L3_WCOPIES 2
+#endif
+constexpr int L3_WCOPIES = PGPD_L3_WCOPIES;      // bulk copies per 32 KB weight stage
 constexpr int L3_STAGE_BYTES = 2 * 128 * 128;     // hi + lo, 128 rows x 128 B
 constexpr int L3_A2_PART = L3_NT * 128;           // one (part,kblock) sub-tile: 256 rows x 128 B = 32 KB
 constexpr int L3_A2_BYTES = 4 * L3_A2_PART;       // hi/lo x 2 k-blocks = 128 KB
@@ -147,8 +151,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                             if (SPLIT) {
                                 bulk_g2s(dst, src + part * SUB_BYTES, SUB_BYTES, BAR(W_FULL + stage));
                             } else {
-                                bulk_g2s(dst, src, L3_STAGE_BYTES / 2, BAR(W_FULL + stage));
-                                bulk_g2s(dst + L3_STAGE_BYTES / 2, src + L3_STAGE_BYTES / 2, L3_STAGE_BYTES / 2, BAR(W_FULL + stage));
+#pragma unroll
+                                for (int cpy = 0; cpy < L3_WCOPIES; ++cpy)
+                                    bulk_g2s(dst + cpy * (L3_STAGE_BYTES / L3_WCOPIES), src + cpy * (L3_STAGE_BYTES / L3_WCOPIES),
+                                             L3_STAGE_BYTES / L3_WCOPIES, BAR(W_FULL + stage));
                             }
                             if (++stage == NSUB) { stage = 0; phase ^= 1; }
                         }

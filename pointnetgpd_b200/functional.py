@@ -220,10 +220,17 @@ def _prepare_input(x, num_points, input_chann):
     return x if x.is_contiguous() else x.contiguous()
 
 
+def _input_channels(module, what):
+    """Input channels the module's first convolutions were built for (also correct for un-pickled reference checkpoints)."""
+    convs = {A.PGPD_CLS: ("feat.conv1", "feat.stn.conv1"), A.PGPD_FEAT: ("conv1", "stn.conv1"), A.PGPD_STN: ("conv1",)}[what]
+    chans = {int(_resolve(module, c).weight.shape[1]) for c in convs}
+    return chans.pop() if len(chans) == 1 else -1
+
+
 def run_module(module, what, x, k=1, flags_extra=0):
     """Evaluate STN3d / PointNetfeat / PointNetCls `module` on x through libpgpd."""
     num_points = module.num_points
-    x = _prepare_input(x, num_points, getattr(module, "_pgpd_input_chann", 3))
+    x = _prepare_input(x, num_points, _input_channels(module, what))
     params, bufs = gather_tensors(module, what)
     out, trans = _Fused.apply(what, bool(module.training), int(k), int(flags_extra), x, *params, *bufs)
     return out, trans

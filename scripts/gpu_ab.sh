@@ -3,6 +3,6 @@
 mkdir -p gpurun_out
 for rep in 1 2; do
   for v in "$@"; do
-    PGPD_LIB=build/variants/libpgpd_$v.so TOP=14 timeout 120 python scripts/kprof.py 2>&1 | grep -E "eager fwd|k_l3_fwd|k_da2|k_ka_tc|k_kb_tc|k_a1|k_tail_l3|sum of" | sed "s/^/[$v $rep] /" | tee -a gpurun_out/r2_ab.log
+    PGPD_LIB=build/variants/libpgpd_$v.so TOP=14 timeout 120 python scripts/kprof.py 2>&1 | grep -E "eager fwd|k_l3_fwd" | sed "s/^/[$v $rep] /" | tee -a gpurun_out/r2_ab2.log
   done
 done
