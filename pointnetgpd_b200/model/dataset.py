@@ -21,6 +21,21 @@ __all__ = ["BaseGraspDataset", "PointGraspDataset", "PointGraspMultiClassDataset
            "PointGraspOneViewMultiClassDataset"]
 
 
+_MMAPS = {}
+
+
+def _mmap(path):
+    """Read-only memory map of a .npy file, cached per process (falls back to np.load for files numpy cannot map)."""
+    m = _MMAPS.get(path)
+    if m is None:
+        try:
+            m = np.load(path, mmap_mode="r")
+        except ValueError:
+            m = np.load(path)
+        _MMAPS[path] = m
+    return m
+
+
 def grasp_frame(grasp, transform):
     """(center, rows=(approach, binormal, minor_normal), width) of a 12-float grasp row in the cloud frame."""
     c = np.asarray(grasp[0:3], dtype=np.float64)
@@ -98,12 +113,14 @@ class _GraspDataset(BaseGraspDataset):
         name = self.object[obj_ind]
         cloud_name, transform = self.transform[name][0], self.transform[name][1]
         files = self.d_pc[cloud_name]
-        grasp = np.load(self.d_grasp[name])[grasp_ind]
+        # memory-mapped reads: the reference re-reads and parses the whole 6500 x 12 grasp file and the view
+        # clouds for every item; a read-only map touches only the row / pages it uses and is shared by the DataLoader workers
+        grasp = np.array(_mmap(self.d_grasp[name])[grasp_ind])
         if self.ONE_VIEW:
-            pc = np.load(files[np.random.randint(len(files))])                      # one random view
+            pc = _mmap(files[np.random.randint(len(files))])                        # one random view
         else:
             picks = np.random.choice(len(files), size=self.pc_file_used_num)        # stack views, thin to obj_points_num
-            pc = np.vstack([np.load(files[i]) for i in picks])
+            pc = np.vstack([_mmap(files[i]) for i in picks])
             pc = pc[np.random.choice(len(pc), size=self.obj_points_num)]
         pts = self.collect_pc(grasp, pc, transform)
         if pts is None:

@@ -48,7 +48,7 @@ class Guarded:
         assert (self.raw[self.off + self.nbytes:] == self.snapshot_hi).all(), "write past the workspace"
 
 
-def run_model(state, x, what=A.PGPD_CLS, train=True, dout=None, dtrans=None, backward=False, flags_extra=0):
+def run_model(state, x, what=A.PGPD_CLS, train=True, dout=None, dtrans=None, backward=False, flags_extra=0, split_backward=False):
     """state: dict of numpy arrays (float32 / int64), modified in place for running stats.
     Returns dict(out, trans, grads)."""
     lib = emu_lib()
@@ -75,10 +75,11 @@ def run_model(state, x, what=A.PGPD_CLS, train=True, dout=None, dtrans=None, bac
         g = A.build_grads(lambda key: _addr(grads[key]), what)
         dout_a = None if dout is None else np.ascontiguousarray(dout, dtype=np.float32)
         dtr_a = None if dtrans is None else np.ascontiguousarray(dtrans, dtype=np.float32)
-        rc = lib.pgpd_backward(what, C.byref(model), C.byref(g), _addr(x), B, N, k, flags,
-                               None if dout_a is None else _addr(dout_a),
-                               None if dtr_a is None else _addr(dtr_a), ws.addr, nbytes, None)
-        A.check(lib, rc)
+        for extra in ((A.F_BWD_HEAD, A.F_BWD_STN) if split_backward else (0,)):     # two calls: the halves a data-parallel trainer overlaps
+            rc = lib.pgpd_backward(what, C.byref(model), C.byref(g), _addr(x), B, N, k, flags | extra,
+                                   None if dout_a is None else _addr(dout_a),
+                                   None if dtr_a is None else _addr(dtr_a), ws.addr, nbytes, None)
+            A.check(lib, rc)
         ws.check()
         res["grads"] = grads
     return res

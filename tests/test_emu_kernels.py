@@ -204,3 +204,16 @@ def test_permutation_and_duplicate_invariance_eval():
     xd = np.concatenate([x, x[:, :, :17]], axis=2)
     r2 = E.run_model(_copy(st), xd, train=False)
     assert np.array_equal(r0["out"], r2["out"])
+
+
+def test_two_phase_backward_equals_one_call():
+    """pgpd_backward(PGPD_F_BWD_HEAD) followed by pgpd_backward(PGPD_F_BWD_STN) -- the split a data-parallel trainer uses to
+    overlap the gradient exchange of the first half -- writes exactly the gradients of the single call."""
+    c = load_case(SMALL_CASES[0])
+    B, k = c["B"], c["k"]
+    dlogp = np.zeros((B, k), np.float32)
+    dlogp[np.arange(B), c["y"]] = -1.0 / B
+    one = E.run_model(_copy(c["state"]), c["x"], train=True, backward=True, dout=dlogp, dtrans=c["wt"])
+    two = E.run_model(_copy(c["state"]), c["x"], train=True, backward=True, dout=dlogp, dtrans=c["wt"], split_backward=True)
+    for n in one["grads"]:
+        assert np.array_equal(one["grads"][n], two["grads"][n]), n
