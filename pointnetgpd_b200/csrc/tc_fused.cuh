@@ -14,12 +14,12 @@
 //     pair's a1 tiles, B = the W2 image, half of its rows resident in each CTA) into whichever accumulator is free;
 //   * the producer warps drain that accumulator (tcgen05.ld: lane = point, columns = channels), apply BatchNorm2 + ReLU, split
 //     to hi/lo fp16 and write the a2 operand tile in place -- the tile layer 3 then consumes exactly as in tc_l3.cuh.
-// Accumulator uses per tile: blk0, blk1, blk2, L2 of the NEXT tile, blk3 (5: the two TMEM slots keep alternating); a slot is
-// released by whoever drained it (producers after an L2 use, epilogue warps after a layer-3 block).  The a2 tile is
-// single-buffered (shared memory: 64 KB a2 + 32 KB a1 + 16 KB W2 half + 96 KB W3 ring) but managed per k-block (channels 0-63 /
-// 64-127): block 3 releases each half as soon as its MMAs over that half are done, the producer warps of that half then drain the
-// (already finished) layer-2 accumulator of the next tile into it, and block 0 of the next tile starts on the first half while
-// the second is still being written -- so the tensor pipe does not wait for the on-chip hand-over.
+// Accumulator uses per tile: L2, blk0, blk1, blk2, blk3 (5: the two TMEM slots keep alternating); a slot is released by
+// whoever drained it (producers after an L2 use, epilogue warps after a layer-3 block).  The a2 tile is single-buffered
+// (shared memory: 64 KB a2 + 32 KB a1 + 16 KB W2 half + 96 KB W3 ring), so the tensor pipe idles while the L2 result of the
+// next tile is drained (~3 k of ~21 k cycles per tile) -- the price for not writing 768 B per point to HBM and reading it back.
+// (Tried: layer 2 of the next tile ahead of block 3 with the a2 tile handed over per k-block.  With two accumulator slots block 3
+// then lands in the slot block 2 has just filled and waits for its drain; measured 5 % slower, profiles/r2/README.md.)
 // Numerics as everywhere: fp32-grade 3-pass hi/lo fp16 split, power-of-two operand scales.
 #pragma once
 #include "common.cuh"
@@ -48,7 +48,7 @@ struct FusedParams {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tower_fused_eval(FusedParams p) {
-    constexpr int W_FULL = 0, W_FULLP = 3, W_EMPTY = 6, A1_FULL = 9, TM2_FULL = 11, TM2_EMPTY = 12, TM_FULL = 14, TM_EMPTY = 16, A2_FULL = 18, A2K_EMPTY = 20;
+    constexpr int W_FULL = 0, W_FULLP = 3, W_EMPTY = 6, A1_FULL = 9, A2_FULL = 10, TM2_FULL = 11, TM2_EMPTY = 12, TM_FULL = 14, TM_EMPTY = 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -68,9 +68,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_FULLP + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
-        mbar_init(BAR(A1_FULL), 16);
-        mbar_init(BAR(A2_FULL), 8); mbar_init(BAR(A2_FULL + 1), 8);          // per k-block: 4 producer warps x 2 CTAs (leader side)
-        mbar_init(BAR(A2K_EMPTY), 1); mbar_init(BAR(A2K_EMPTY + 1), 1);      // commit: block 3 is done with this k-block of the a2 tile
+        mbar_init(BAR(A1_FULL), 16); mbar_init(BAR(A2_FULL), 16);
         mbar_init(BAR(TM2_FULL), 1);
         mbar_init(BAR(TM2_EMPTY), 16); mbar_init(BAR(TM2_EMPTY + 1), 16);
         mbar_init(BAR(TM_FULL), 1); mbar_init(BAR(TM_FULL + 1), 1);
@@ -134,49 +132,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                 constexpr uint32_t IDESC2 = idesc_f16(256, 128);
                 int stage = 0; uint32_t wphase = 0;
                 uint32_t ph_e[2] = {0u, 0u}, ph_p[2] = {0u, 0u};       // next completion parity of TM_EMPTY[s] / TM2_EMPTY[s]
-                uint32_t ph_a1 = 0u, ph_a2[2] = {0u, 0u};
+                uint32_t ph_a1 = 0u, ph_a2 = 0u;
                 long long use = 0;                                     // accumulator uses so far: slot = use & 1
-                bool slot_l2[2] = {false, false};                      // was the slot's previous use a layer-2 use (drained by the producers)?
                 auto wait_slot = [&]() {
                     if (use < 2) return;
                     const int s = (int)(use & 1);
-                    if (slot_l2[s]) { mbar_wait_cluster(BAR(TM2_EMPTY + s), ph_p[s]); ph_p[s] ^= 1u; }
-                    else { mbar_wait_cluster(BAR(TM_EMPTY + s), ph_e[s]); ph_e[s] ^= 1u; }
+                    if ((use - 2) % 5 == 0) { mbar_wait_cluster(BAR(TM2_EMPTY + s), ph_p[s]); ph_p[s] ^= 1u; }   // drained by the producers
+                    else { mbar_wait_cluster(BAR(TM_EMPTY + s), ph_e[s]); ph_e[s] ^= 1u; }                      // drained by the epilogue
                     tc_fence_after_sync();
                 };
                 const uint32_t a1s = sbase + FZ_A1, w2s = sbase + FZ_W2, a2b = sbase;
-                auto layer2 = [&]() {
-                    // D[256 points][128 channels] = a1 (hi, lo) x W2 (hi, lo), K = 64, of the tile whose a1 operand is staged
+                for (int t = T0; t < T1; ++t) {
+                    // ---- layer 2 of this tile: D[256 points][128 channels] = a1 (hi, lo) x W2 (hi, lo), K = 64
                     mbar_wait_cluster(BAR(A1_FULL), ph_a1); ph_a1 ^= 1u;
                     tc_fence_after_sync();
                     wait_slot();
-                    const int s = (int)(use & 1);
-                    const uint32_t d2 = tmem + (uint32_t)(s * L3_NT);
-                    const uint64_t da = desc_sw128_kmajor(a1s), db = desc_sw128_kmajor(w2s);
+                    {
+                        const uint32_t d2 = tmem + (uint32_t)((use & 1) * L3_NT);
+                        const uint64_t da = desc_sw128_kmajor(a1s), db = desc_sw128_kmajor(w2s);
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t oa = (pass == 1) ? 16384u : 0u;      // a1 lo
-                        const uint32_t ob = (pass == 2) ? 8192u : 0u;       // W2 lo
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t oa = (pass == 1) ? 16384u : 0u;      // a1 lo
+                            const uint32_t ob = (pass == 2) ? 8192u : 0u;       // W2 lo
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_f16_pair(d2, da + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC2, (pass | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)
+                                mma_f16_pair(d2, da + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC2, (pass | k) ? 1u : 0u);
+                        }
+                        mma_commit_pair(BAR(TM2_FULL), (uint16_t)0x3);
+                        ++use;
                     }
-                    mma_commit_pair(BAR(TM2_FULL), (uint16_t)0x3);
-                    slot_l2[s] = true;
-                    ++use;
-                };
-                if (T0 < T1) layer2();                                 // layer 2 of the first tile
-                for (int t = T0; t < T1; ++t) {
+                    // ---- layer 3: four 256-channel blocks
+                    mbar_wait_cluster(BAR(A2_FULL), ph_a2); ph_a2 ^= 1u;
+                    tc_fence_after_sync();
                     for (int mt4 = 0; mt4 < 4; ++mt4) {
-                        if (mt4 == 3 && t + 1 < T1) layer2();          // layer 2 of the NEXT tile runs ahead of this tile's last block
                         wait_slot();
                         const int s = (int)(use & 1);
                         const uint32_t d = tmem + (uint32_t)(s * L3_NT);
                         for (int kb = 0; kb < 2; ++kb) {
-                            if (mt4 == 0) {                            // k-block kb of this tile's a2 operand is staged
-                                mbar_wait_cluster(BAR(A2_FULL + kb), ph_a2[kb]); ph_a2[kb] ^= 1u;
-                                tc_fence_after_sync();
-                            }
                             const uint64_t dbk = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
                             constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);
                             mbar_wait(BAR(W_FULL + stage), wphase);
@@ -193,10 +185,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                             }
                             mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);
                             if (++stage == 3) { stage = 0; wphase ^= 1u; }
-                            if (mt4 == 3) mma_commit_pair(BAR(A2K_EMPTY + kb), (uint16_t)0x3);   // this half of the a2 tile may be overwritten
                         }
                         mma_commit_pair(BAR(TM_FULL + s), (uint16_t)0x3);
-                        slot_l2[s] = false;
                         ++use;
                     }
                 }
@@ -208,13 +198,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
         const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         uint32_t fe[2] = {0u, 0u};
-        long long use = (T0 < T1) ? 1 : 0;                           // the layer-2 use of the first tile is not mine
+        long long use = 0;
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
+            ++use;                                                   // the layer-2 use of this tile is not mine
             for (int mt4 = 0; mt4 < 4; ++mt4, ++use) {
-                if (mt4 == 3 && t + 1 < T1) ++use;                   // nor is the layer-2 use of the next tile (issued before block 3)
                 const int s = (int)(use & 1);
                 const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
                 mbar_wait(BAR(TM_FULL + s), fe[s]); fe[s] ^= 1u;
@@ -311,15 +301,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                 if (leader) mbar_arrive(BAR(A1_FULL)); else mbar_arrive_cluster(BAR(A1_FULL), 0u);
             }
         };
-        uint32_t ph2 = 0u, phk = 0u;
-        // layer-2 accumulator of tile t (TMEM slot s) -> BatchNorm2 + ReLU -> my 64 channels (k-block hh) of the a2 operand tile
-        auto drain = [&](int t, int s) {
+        if (T0 < T1) stage_a1(T0);
+        uint32_t ph2 = 0u;
+        long long use = 0;
+        for (int t = T0; t < T1; ++t, use += 5) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT + (int)rank * L3C_NH;
             const bool valid = n0 + r2 < p.N;
-            mbar_wait(BAR(TM2_FULL), ph2); ph2 ^= 1u;               // layer 2 of tile t is complete (the a1 tile is free again)
-            mbar_wait(BAR(A2K_EMPTY + hh), phk ^ 1u); phk ^= 1u;    // block 3 of the previous tile is done with my half of the a2 tile
-            tc_fence_after_sync();
+            const int s = (int)(use & 1);
+            mbar_wait(BAR(TM2_FULL), ph2); ph2 ^= 1u;       // layer 2 of this tile is complete (and with it every earlier MMA:
+            tc_fence_after_sync();                          // the a2 tile and the a1 tile are free to be overwritten)
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * L3_NT + hh * 64);
             bool oor = false;
 #pragma unroll 1
@@ -362,25 +353,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                if (leader) mbar_arrive(BAR(A2_FULL + hh)); else mbar_arrive_cluster(BAR(A2_FULL + hh), 0u);
+                if (leader) mbar_arrive(BAR(A2_FULL)); else mbar_arrive_cluster(BAR(A2_FULL), 0u);
             }
-        };
-        if (T0 < T1) {
-            stage_a1(T0);
-            long long use = 0;
-            drain(T0, 0);                                   // the first tile's layer 2 is accumulator use 0
-            if (T0 + 1 < T1) stage_a1(T0 + 1);
-            use = 1;
-            for (int t = T0; t < T1; ++t) {
-                use += 3;                                   // blocks 0..2 of tile t
-                if (t + 1 < T1) {
-                    const int s = (int)(use & 1);           // layer 2 of tile t+1
-                    ++use;
-                    drain(t + 1, s);
-                    if (t + 2 < T1) stage_a1(t + 2);
-                }
-                ++use;                                      // block 3
-            }
+            if (t + 1 < T1) stage_a1(t + 1);
         }
     }
 
