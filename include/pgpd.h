@@ -168,6 +168,19 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
                         const float* dpooled, float* dtrans_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- GPDClassifier, the paper's baseline CNN (PointNetGPD/model/gpd.py:5-31) ---------------------
+ *   x [B][C][60][60] -> conv1(C->20,5x5) -> maxpool2 -> conv2(20->50,5x5) -> maxpool2 -> fc1(7200->500)+ReLU -> fc2(500->2)
+ *   -> log_softmax.  Weights in the reference layouts: Conv2d [out][in][5][5], Linear [out][in] (fc1.w 16-byte aligned).
+ *   The optional Dropout2d of the reference (if_dropout=True, training) draws from torch's RNG stream and is not provided.
+ *   pgpd_gpd_forward(..., PGPD_F_SAVE) keeps what pgpd_gpd_backward needs in the workspace. */
+typedef struct pgpd_gpd { pgpd_lin conv1, conv2, fc1, fc2; } pgpd_gpd;
+typedef struct pgpd_gpd_grad { pgpd_lin_grad conv1, conv2, fc1, fc2; } pgpd_gpd_grad;
+size_t pgpd_gpd_workspace_bytes(int B, int C, int flags);
+int pgpd_gpd_forward(const pgpd_gpd* m, const float* x, int B, int C, int flags, float* logp,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int pgpd_gpd_backward(const pgpd_gpd* m, const pgpd_gpd_grad* g, const float* x, int B, int C, int flags,
+                      const float* dlogp, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- data preparation in front of the model ------------------------------------
  * Gripper-box crop of one cloud for G grasps (BaseGraspDataset.collect_pc, PointNetGPD/model/dataset.py:51-76;
  * kinect2grasp.py:178-235).

@@ -59,7 +59,17 @@ class ModelGrad(C.Structure):
     _fields_ = [("stn_tower", TowerGrad), ("stn_head", HeadGrad), ("trunk", TowerGrad), ("cls_head", HeadGrad)]
 
 
-EXPORTS = ("pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_launch_count",
+class Gpd(C.Structure):
+    _fields_ = [("conv1", Lin), ("conv2", Lin), ("fc1", Lin), ("fc2", Lin)]
+
+
+class GpdGrad(C.Structure):
+    _fields_ = [("conv1", LinGrad), ("conv2", LinGrad), ("fc1", LinGrad), ("fc2", LinGrad)]
+
+
+GPD_LAYERS = ("conv1", "conv2", "fc1", "fc2")
+
+EXPORTS = ("pgpd_gpd_workspace_bytes", "pgpd_gpd_forward", "pgpd_gpd_backward", "pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_launch_count",
            "pgpd_profile_enable", "pgpd_profile_read", "pgpd_workspace_bytes",
            "pgpd_forward", "pgpd_backward", "pgpd_tower_workspace_bytes", "pgpd_tower_forward",
            "pgpd_tower_backward", "pgpd_crop_box", "pgpd_resample")
@@ -94,6 +104,12 @@ def bind(lib):
     lib.pgpd_tower_backward.restype = C.c_int
     lib.pgpd_tower_backward.argtypes = [C.POINTER(Tower), C.POINTER(TowerGrad), _fp, _fp, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]
+    lib.pgpd_gpd_workspace_bytes.restype = C.c_size_t
+    lib.pgpd_gpd_workspace_bytes.argtypes = [C.c_int] * 3
+    lib.pgpd_gpd_forward.restype = C.c_int
+    lib.pgpd_gpd_forward.argtypes = [C.POINTER(Gpd), _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]
+    lib.pgpd_gpd_backward.restype = C.c_int
+    lib.pgpd_gpd_backward.argtypes = [C.POINTER(Gpd), C.POINTER(GpdGrad), _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]
     lib.pgpd_crop_box.restype = C.c_int
     lib.pgpd_crop_box.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp]
     lib.pgpd_resample.restype = C.c_int

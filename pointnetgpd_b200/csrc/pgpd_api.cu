@@ -5,6 +5,7 @@
 #include "tower.cuh"
 #include "head.cuh"
 #include "prep.cuh"
+#include "gpd.cuh"
 
 #include <string>
 
@@ -303,6 +304,52 @@ int pgpd_tower_backward(const pgpd_tower* t, const pgpd_tower_grad* g, const flo
     TowerArgs a{t, x, trans, B, N, relu_last != 0, true, true, (cudaStream_t)stream, want_tc(flags)};
     run_tower_bwd(a, w, *g, dpooled, dtrans_out, flags);
     return check_cuda("pgpd_tower_backward");
+}
+
+// ---- GPDClassifier ---------------------------------------------------------------------
+size_t pgpd_gpd_workspace_bytes(int B, int C, int flags) {
+    if (B < 1 || C < 1) return 0;
+    GpdWs w;
+    plan_gpd(nullptr, B, (flags & PGPD_F_SAVE) != 0, w);
+    return w.bytes;
+}
+
+static int gpd_check(const pgpd_gpd* m, const float* x, int B, int C, const void* ws, size_t ws_bytes, size_t need) {
+    if (!m || !x) return fail(PGPD_E_ARG, "null model or input pointer");
+    if (B < 1 || C < 1 || C > 64) return fail(PGPD_E_ARG, "B must be >= 1 and C in [1,64]");
+    if ((long long)B * GPD_FLAT > 0x7fffffffLL) return fail(PGPD_E_ARG, "B too large");
+    if (!m->conv1.w || !m->conv2.w || !m->fc1.w || !m->fc2.w || !m->conv1.b || !m->conv2.b || !m->fc1.b || !m->fc2.b)
+        return fail(PGPD_E_ARG, "null weight pointer");
+    if ((uintptr_t)m->fc1.w & 15) return fail(PGPD_E_ARG, "fc1 weight pointer must be 16-byte aligned");
+    if (!ws || ((uintptr_t)ws & 255)) return fail(PGPD_E_WORKSPACE, "workspace is null or not 256-byte aligned");
+    if (ws_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small (see pgpd_gpd_workspace_bytes)");
+    return PGPD_OK;
+}
+
+int pgpd_gpd_forward(const pgpd_gpd* m, const float* x, int B, int C, int flags, float* logp,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    GpdWs w;
+    plan_gpd(nullptr, B < 1 ? 1 : B, (flags & PGPD_F_SAVE) != 0, w);
+    int rc = gpd_check(m, x, B, C, workspace, workspace_bytes, w.bytes);
+    if (rc) return rc;
+    if (!logp) return fail(PGPD_E_ARG, "logp output pointer is null");
+    plan_gpd(workspace, B, (flags & PGPD_F_SAVE) != 0, w);
+    GpdArgs a{m, x, B, C, (cudaStream_t)stream, want_tc(flags)};
+    gpd_forward(a, w, logp);
+    return check_cuda("pgpd_gpd_forward");
+}
+
+int pgpd_gpd_backward(const pgpd_gpd* m, const pgpd_gpd_grad* g, const float* x, int B, int C, int flags,
+                      const float* dlogp, void* workspace, size_t workspace_bytes, void* stream) {
+    GpdWs w;
+    plan_gpd(nullptr, B < 1 ? 1 : B, true, w);
+    int rc = gpd_check(m, x, B, C, workspace, workspace_bytes, w.bytes);
+    if (rc) return rc;
+    if (!g || !dlogp) return fail(PGPD_E_ARG, "null gradient struct or dlogp");
+    plan_gpd(workspace, B, true, w);
+    GpdArgs a{m, x, B, C, (cudaStream_t)stream, want_tc(flags)};
+    gpd_backward(a, w, *g, dlogp);
+    return check_cuda("pgpd_gpd_backward");
 }
 
 // ---- data preparation in front of the model ---------------------------------------
