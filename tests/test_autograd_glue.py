@@ -130,8 +130,11 @@ def test_product_surface_rejects_what_it_does_not_cover():
     with pytest.raises(NotImplementedError):
         DualPointNetCls()
     from pointnetgpd_b200.model.gpd import GPDClassifier
-    with pytest.raises(NotImplementedError):
-        GPDClassifier(3)
+    g = GPDClassifier(3)                                     # constructible (same sub-modules as the reference); CUDA-only forward
+    assert list(g.state_dict().keys()) == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "fc1.weight", "fc1.bias",
+                                           "fc2.weight", "fc2.bias"]
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        g(torch.zeros(2, 3, 60, 60))
 
 
 def test_state_dict_keys_and_pickle_roundtrip():

@@ -100,19 +100,26 @@ def test_gpd_module_gpu(B, Cc):
 def test_gpd_training_loop_and_pickle(tmp_path):
     """main_1v_gpd.py:123-133 shape of use: Adam on model.parameters(); torch.save(model) / torch.load round trip."""
     from pointnetgpd_b200.model.gpd import GPDClassifier
-    torch.manual_seed(0)
-    m = GPDClassifier(3).cuda().train()
+    sd = G.make_gpd_state(41, 3)
+    m = GPDClassifier(3)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
     x = torch.tensor(_inputs(31, 32, 3)[0]).cuda()
     y = torch.tensor(_inputs(31, 32, 3)[1]).cuda()
-    opt = torch.optim.Adam(m.parameters(), lr=0.005)
-    losses = []
-    for _ in range(15):
+    opt = torch.optim.Adam(m.parameters(), lr=0.0005)
+    # the same loop through the oracle's port, executed by eager PyTorch on the GPU: the loss trajectories must agree
+    rs = {k: v.cuda().clone().requires_grad_(True) for k, v in sd.items()}
+    ropt = torch.optim.Adam(list(rs.values()), lr=0.0005)
+    for _ in range(8):
         opt.zero_grad()
         loss = torch.nn.functional.nll_loss(m(x), y)
         loss.backward()
         opt.step()
-        losses.append(float(loss.detach()))
-    assert losses[-1] < 0.5 * losses[0]
+        ropt.zero_grad()
+        rloss = torch.nn.functional.nll_loss(G.gpd_forward(rs, x), y)
+        rloss.backward()
+        ropt.step()
+        assert abs(float(loss.detach()) - float(rloss.detach())) < 2e-3 * max(1.0, abs(float(rloss.detach())))
     path = str(tmp_path / "gpd.model")
     torch.save(m, path)
     m2 = torch.load(path, weights_only=False)
