@@ -51,7 +51,15 @@ __device__ __forceinline__ float ord_decode(unsigned k) {
 }
 
 // relu that keeps NaN (fmaxf(NaN, 0) is 0; torch.relu(NaN) is NaN)
-__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }
+__device__ __forceinline__ float relu_nan(float v) {
+#if defined(PGPD_EMU)
+    return v < 0.f ? 0.f : v;
+#else
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));      // one instruction; NaN if v is NaN
+    return r;
+#endif
+}
 
 // fp16 operand range of the tensor-core path: activations are pre-scaled by 2^4 before the hi/lo split, so anything
 // above 60000/16 would saturate.  Producers of activations flag such values (and NaN) per cloud instead of clamping

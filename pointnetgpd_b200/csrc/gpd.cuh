@@ -244,23 +244,21 @@ __global__ void __launch_bounds__(256) k_gpd_conv_dgrad(const float* __restrict_
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int x = (int)(i % HIN), y = (int)((i / HIN) % HIN), ic = (int)((i / ((size_t)HIN * HIN)) % CIN), b = (int)(i / ((size_t)HIN * HIN * CIN));
-    const int HC = 2 * HP;                              // conv output size
+    // conv positions (cy, cx) with y - 4 <= cy <= y lie in the pooling windows py in [ceil((y-5)/2), y/2]: at most 3 x 3 windows,
+    // each with ONE kept position
+    const int py0 = (y - 4) > 0 ? ((y - 4) >> 1) : 0, py1 = (y >> 1) < HP ? (y >> 1) : HP - 1;
+    const int px0 = (x - 4) > 0 ? ((x - 4) >> 1) : 0, px1 = (x >> 1) < HP ? (x >> 1) : HP - 1;
     float acc = 0.f;
     for (int oc = 0; oc < COUT; ++oc) {
         const float* wp = W + ((size_t)oc * CIN + ic) * 25;
         const size_t ob = ((size_t)b * COUT + oc) * HP * HP;
-#pragma unroll
-        for (int ky = 0; ky < 5; ++ky) {
-            const int cy = y - ky;
-            if (cy < 0 || cy >= HC) continue;
-#pragma unroll
-            for (int kx = 0; kx < 5; ++kx) {
-                const int cx = x - kx;
-                if (cx < 0 || cx >= HC) continue;
-                const size_t o = ob + (size_t)(cy >> 1) * HP + (cx >> 1);
-                if (pos[o] == (unsigned char)(((cy & 1) << 1) | (cx & 1))) acc = fmaf(dP[o], wp[ky * 5 + kx], acc);
+        for (int py = py0; py <= py1; ++py)
+            for (int px = px0; px <= px1; ++px) {
+                const size_t o = ob + (size_t)py * HP + px;
+                const int p = pos[o];
+                const int ky = y - (2 * py + (p >> 1)), kx = x - (2 * px + (p & 1));
+                if (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) acc = fmaf(dP[o], wp[ky * 5 + kx], acc);
             }
-        }
     }
     dIn[i] = acc;
 }

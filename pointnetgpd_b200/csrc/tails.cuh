@@ -17,6 +17,8 @@
 namespace pgpd {
 
 constexpr int PRE_THREADS = 256;
+constexpr int PRE_SAMPLE = 256;      // points of the pilot estimate of mean(a1): one per thread of the finalising block
+static_assert(PRE_SAMPLE == PRE_THREADS, "k_tower_pre: one sample point per thread");
 constexpr int A1_CHUNK = 64;        // points per staging chunk of k_a1
 constexpr int A1_CPB = 8;           // chunks per block: one partial row of the a1 sums per 512 points
 
@@ -42,6 +44,8 @@ struct PreParams {
     void* wimg2; float* inv2;                 // W2 image (32 KB) + per-row inverse scale [128]
     void* wimg3; float* sgn;                  // W3 image (512 KB) + inv / sign [1024]
     int act_shift;
+    float* centre2;                           // tensor-core train path: [128] pilot estimate of mean(u2) = W2 mean(a1) over a sample of
+                                              // points (the layer-2 kernel centres its squares on it and also sums u2 exactly); or null
 };
 
 #ifndef PGPD_EMU
@@ -150,6 +154,57 @@ __global__ void __launch_bounds__(PRE_THREADS) k_tower_pre(PreParams p) {
                 for (int i = 0; i < 3; ++i)
                     for (int i2 = 0; i2 < 3; ++i2) var += w[i] * (raw[3 + i * 3 + i2] - raw[i] * raw[i2]) * w[i2];
                 bn_finalize_train(c, mean_u, var, p.count, p.conv[0].b, p.bn[0], p.st[0]);
+            }
+            if (p.centre2) {
+                // pilot mean of a1 over PRE_SAMPLE points spread over the batch, then W2 . mean.  All global loads (the sample
+                // points, this thread's half row of W2) are issued up front: one latency epoch, not a chain.
+                const int c2 = tid & 127, hk = tid >> 7;            // matvec: channel x half of k
+                float4 wv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) wv[e] = *reinterpret_cast<const float4*>(p.conv[1].w + (size_t)c2 * C1 + hk * 32 + e * 4);
+                const size_t M = (size_t)p.B * p.N;
+                const size_t step = M > PRE_SAMPLE ? M / PRE_SAMPLE : 1;
+                const int ns = (int)(M < PRE_SAMPLE ? M : PRE_SAMPLE);
+                __shared__ float s_pt[3][PRE_SAMPLE];
+                __shared__ float s_m[C1];
+                {
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                    if (tid < ns) {
+                        const size_t P = (size_t)tid * step;
+                        const int b = (int)(P / p.N), n = (int)(P % p.N);
+                        const float* xb = p.x + (size_t)b * 3 * p.N + n;
+                        const float p0 = xb[0], p1 = xb[p.N], p2 = xb[2 * (size_t)p.N];
+                        t0 = p0; t1 = p1; t2 = p2;
+                        if (p.trans) {
+                            const float* T = p.trans + (size_t)b * 9;
+                            t0 = T[0] * p0 + T[3] * p1 + T[6] * p2;
+                            t1 = T[1] * p0 + T[4] * p1 + T[7] * p2;
+                            t2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+                        }
+                    }
+                    s_pt[0][tid] = t0; s_pt[1][tid] = t1; s_pt[2][tid] = t2;
+                }
+                __syncthreads();                                     // also: BatchNorm1 scale / shift written above are visible
+                const int k = tid & 63, ln = tid >> 6;               // thread = channel x 4 point lanes
+                const float w0 = p.conv[0].w[k * 3 + 0], w1 = p.conv[0].w[k * 3 + 1], w2 = p.conv[0].w[k * 3 + 2];
+                const float sc = p.st[0].scale[k], sf = p.st[0].shift[k];
+                float acc = 0.f;
+#pragma unroll 8
+                for (int i = ln; i < ns; i += 4)
+                    acc += relu_nan(sc * (w0 * s_pt[0][i] + w1 * s_pt[1][i] + w2 * s_pt[2][i]) + sf);
+                redf[tid] = acc;
+                __syncthreads();
+                if (tid < C1) s_m[tid] = (((redf[tid] + redf[tid + 64]) + redf[tid + 128]) + redf[tid + 192]) / (float)ns;
+                __syncthreads();
+                float s2 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float* mm = s_m + hk * 32 + e * 4;
+                    s2 += wv[e].x * mm[0] + wv[e].y * mm[1] + wv[e].z * mm[2] + wv[e].w * mm[3];
+                }
+                redf[tid] = s2;
+                __syncthreads();
+                if (tid < C2) p.centre2[tid] = redf[tid] + redf[tid + 128];
             }
         }
         return;
@@ -312,7 +367,9 @@ __global__ void __launch_bounds__(A1_THREADS) k_a1(A1Params p) {
 constexpr int TL2_BLOCKS = 32;
 constexpr int TL2_SPB = 256;                  // sample points per block of the pilot estimate of mean(a2)
 struct TailL2Params {
-    const float* css; int n_css;              // [n_css][128] partial sums of (u2 - mean)^2
+    const float* css; int n_css;              // partial rows [n_css][128]: sum (u2 - c)^2, c = mean_u2
+    const float* s1a_part; int n_s1a; double* S1a;     // tensor-core path (c is a pilot): partial rows [n_s1a][64] of sum a1 * 2^4 -> S1a; else null
+    double s1a_scale; const float* W2;        //   ... their scale (2^-4), conv2.weight [128][64]
     int bn_done;                              // 1: BatchNorm2 is already finalised (second call of the CUDA-core path): only read st2
     const float* mean_u2; double count; const float* bias2; pgpd_bn bn2; BnState st2;
     const float* Y2; size_t npoints, pstride;  // pilot (a2part == null): block b samples points ((b * TL2_SPB + j) * pstride) mod npoints
@@ -335,23 +392,62 @@ __global__ void __launch_bounds__(1024) k_tail_l2(TailL2Params p) {
         if (tid < C2) { s_sc[tid] = p.st2.scale[tid]; s_sf[tid] = p.st2.shift[tid]; }
         __syncthreads();
     } else {
+        // Tensor-core path: the layer-2 kernel centred its squares on a pilot c and summed a1 exactly; the exact mean of u2 is
+        // W2 (sum a1) / M and var = sum (u-c)^2 / M - (mean - c)^2 (an identity).  CUDA-core path: c is the exact mean already.
+        const bool pilot = p.s1a_part != nullptr;
+        __shared__ double s_a[C1];
+        __shared__ double s_dm[C2];
+        // every global load of this section is issued before the first barrier (one latency epoch): the css rows, and on the
+        // tensor-core path the a1-sum rows and this thread's eight weights of W2
         double s = 0.0;
 #pragma unroll 8
         for (int r = q; r < p.n_css; r += 8) s += (double)p.css[(size_t)r * C2 + c];
+        if (pilot) {
+            const int k = tid & 63, ln = tid >> 6;          // 64 columns x 16 lanes, lanes added in order
+            float4 wa = *reinterpret_cast<const float4*>(p.W2 + (size_t)c * C1 + q * 8);
+            float4 wb = *reinterpret_cast<const float4*>(p.W2 + (size_t)c * C1 + q * 8 + 4);
+            double t = 0.0;
+#pragma unroll 8
+            for (int r = ln; r < p.n_s1a; r += 16) t += (double)p.s1a_part[(size_t)r * C1 + k];
+            sh[tid] = t;
+            __syncthreads();
+            if (tid < C1) {
+                double tt = 0.0;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) tt += sh[l * C1 + tid];
+                tt *= p.s1a_scale;
+                s_a[tid] = tt;
+                if (blockIdx.x == 0) p.S1a[tid] = tt;       // the backward's dW2 needs it
+            }
+            __syncthreads();
+            const double* sa = s_a + q * 8;
+            const double m = (double)wa.x * sa[0] + (double)wa.y * sa[1] + (double)wa.z * sa[2] + (double)wa.w * sa[3]
+                           + (double)wb.x * sa[4] + (double)wb.y * sa[5] + (double)wb.z * sa[6] + (double)wb.w * sa[7];
+            sh[tid] = m;
+            __syncthreads();
+            if (tid < C2) {
+                double mm = 0.0;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) mm += sh[l * C2 + tid];
+                s_dm[tid] = mm / p.count - (double)p.mean_u2[tid];
+            }
+            __syncthreads();
+        }
         sh[tid] = s;
         __syncthreads();
         if (tid < C2) {
-            double t = 0.0;
+            double tsq = 0.0;
 #pragma unroll
-            for (int l = 0; l < 8; ++l) t += sh[l * C2 + tid];
-            const double var0 = t / p.count;
+            for (int l = 0; l < 8; ++l) tsq += sh[l * C2 + tid];
+            const double dm = pilot ? s_dm[tid] : 0.0;
+            const double mean = (double)p.mean_u2[tid] + dm;
+            const double var0 = tsq / p.count - dm * dm;
             const double var = var0 < 0.0 ? 0.0 : var0;
             const float rstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
             const float sc = p.bn2.gamma[tid] * rstd;
-            const float mu = p.mean_u2[tid];
             s_sc[tid] = sc;
-            s_sf[tid] = p.bn2.beta[tid] - sc * mu;
-            if (blockIdx.x == 0) bn_finalize_train(tid, (double)mu, var0, p.count, p.bias2, p.bn2, p.st2);
+            s_sf[tid] = p.bn2.beta[tid] - sc * (float)mean;
+            if (blockIdx.x == 0) bn_finalize_train(tid, mean, var0, p.count, p.bias2, p.bn2, p.st2);
         }
         __syncthreads();
     }

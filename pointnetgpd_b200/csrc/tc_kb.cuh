@@ -42,7 +42,8 @@ struct KbParams {
     const __half* A1img; const __half* A2img; const float* ginv;
     const float* cvec; const float* gamma1; const float* beta1;
     const float* esc; const float* einv;
-    const float* DZ2; const float* A1; const float* x;
+    const float* DZ2; const float* x; const float* trans;           // a1 is recomputed from the coordinates (tc_kf.cuh)
+    const float* W1; const float* sc1; const float* sh1;
     int B, N, tiles_per_cloud, ntiles;
     float* Cpart;     // [gridDim.x][128*64]
     float* G1part;    // [gridDim.x][64*64]
@@ -105,7 +106,6 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                         const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
                         const size_t P0 = (size_t)cb * p.N + n0;
                         l2_prefetch(p.DZ2 + P0 * C2, (uint32_t)nv * C2 * 4u);
-                        l2_prefetch(p.A1 + P0 * C1, (uint32_t)nv * C1 * 4u);
                     }
                 }
                 const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
@@ -113,10 +113,9 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 const size_t P0 = (size_t)cb * p.N + n0;
                 KB_T(0, mbar_wait(BAR(7 + b), ph ^ 1));
                 if (dbg) s_clk[b] = clock64();
-                mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)nv * (C2 + C1) * 4u);
+                mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)nv * C2 * 4u);
                 const uint32_t dst = sbase + KB_OFF_BUF + b * KB_BUF_BYTES;
                 bulk_g2s(dst, p.DZ2 + P0 * C2, (uint32_t)nv * C2 * 4u, BAR(1 + b));
-                bulk_g2s(dst + KB_DZ_BYTES, p.A1 + P0 * C1, (uint32_t)nv * C1 * 4u, BAR(1 + b));
             }
             if (dbg) dbg[cta * 8 + 0] = dacc[0];
         }
@@ -250,6 +249,15 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
         const int cw = warp < 16 ? (warp >> 2) * 2 + (warp & 1) : warp - 8;        // 0..15
         const int ctid = cw * 32 + lane;
         const float4 e4 = *reinterpret_cast<const float4*>(p.esc + 4 * lane);
+        // a1 is recomputed from the coordinates: my four channels 4 cg .. 4 cg + 3 (cg = lane & 15)
+        float w1[4][3], sf1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * (lane & 15) + j;
+            const float s16 = p.sc1[c] * ACT_SCALE;         // folded exactly as in tc_kf.cuh: the same a1 bit for bit
+            w1[j][0] = s16 * p.W1[c * 3 + 0]; w1[j][1] = s16 * p.W1[c * 3 + 1]; w1[j][2] = s16 * p.W1[c * 3 + 2];
+            sf1[j] = p.sh1[c] * ACT_SCALE;
+        }
         int i = 0;
         for (int t = t_begin; t < t_end; ++t, ++i) {
             const int b = i & 1;
@@ -266,13 +274,16 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             if (dbg) dacc[1] += tc0 - s_clk[b];
             unsigned char* dzb = smem + KB_OFF_BUF + b * KB_BUF_BYTES;
             unsigned char* a1b = dzb + KB_DZ_BYTES;
-            float4 rdz[4], ra[2];
+            float4 rdz[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) rdz[u] = *reinterpret_cast<const float4*>(dzb + (cw * 4 + u) * 512 + lane * 16);
+            if (ctid < 3 * KB_NT) sx[b * (3 * KB_NT) + ctid] = xv;      // raw coordinates (the epilogue needs them too)
+            named_bar_sync(1, KB_CONV_THREADS);             // every converter thread has read its raw rows; the coordinates are staged
+            float T[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+            if (p.trans) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) ra[u] = *reinterpret_cast<const float4*>(a1b + (cw * 4 + u * 2 + (lane >> 4)) * 256 + (lane & 15) * 16);
-            named_bar_sync(1, KB_CONV_THREADS);             // every converter thread has read its raw rows
-            if (ctid < 3 * KB_NT) sx[b * (3 * KB_NT) + ctid] = xv;
+                for (int e = 0; e < 9; ++e) T[e] = __ldg(p.trans + (size_t)cb * 9 + e);
+            }
             {
                 const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
 #pragma unroll
@@ -300,13 +311,19 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 for (int u = 0; u < 2; ++u) {
                     const int r = cw * 4 + u * 2 + (lane >> 4);
                     const bool ok = r < nv;
-                    const float a0 = ok ? fminf(ra[u].x * ACT_SCALE, 60000.f) : 0.f;
-                    const float a1v = ok ? fminf(ra[u].y * ACT_SCALE, 60000.f) : 0.f;
-                    const float a2 = ok ? fminf(ra[u].z * ACT_SCALE, 60000.f) : 0.f;
-                    const float a3 = ok ? fminf(ra[u].w * ACT_SCALE, 60000.f) : 0.f;
+                    // a1 * 2^4 = relu(w' . (T^T x) + shift'), exactly as the forward computed it (tc_kf.cuh)
+                    const float* xb = sx + b * (3 * KB_NT);
+                    const float p0 = xb[r], p1 = xb[KB_NT + r], p2 = xb[2 * KB_NT + r];
+                    const float q0 = T[0] * p0 + T[3] * p1 + T[6] * p2, q1 = T[1] * p0 + T[4] * p1 + T[7] * p2,
+                                q2 = T[2] * p0 + T[5] * p1 + T[8] * p2;
+                    float av4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        av4[j] = ok ? fminf(relu_nan(fmaf(w1[j][0], q0, fmaf(w1[j][1], q1, fmaf(w1[j][2], q2, sf1[j])))), 60000.f) : 0.f;
+                    }
                     __half2 h01, l01, h23, l23;
-                    split2(a0, a1v, h01, l01);
-                    split2(a2, a3, h23, l23);
+                    split2(av4[0], av4[1], h01, l01);
+                    split2(av4[2], av4[3], h23, l23);
                     const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + half8 * 8);
                     uint2 hv, lv;
                     hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);

@@ -50,7 +50,6 @@ struct TowerKeep {
 struct TowerScratch {
     double* moments;  // [B][9]
     double* dpart;    // double partials, max(nb_a1*64, nb_a2*128)
-    double* dsum;     // [128]
     double* rtmp;     // [REDUCE_MAX_SLICES][16384] stage-1 output of the two-stage reductions
     float* fpart;     // float partials: max over users (see plan_tower_scratch)
     unsigned long long* keys;  // [B][1024]   -- keys, bad and counters are contiguous: ONE memset of zero_bytes per forward
@@ -59,7 +58,7 @@ struct TowerScratch {
     size_t zero_bytes;
     void* wimg;       // 512 KB: pre-swizzled hi/lo fp16 image of W3 for the tcgen05 kernel
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
-    float* mu_x;      // [1024] exact mean of u3 when the kernel centred its squares on a pilot estimate
+    float* centre2;   // [128] pilot estimate of mean(u2) the tcgen05 layer-2 kernel centres its squares on (train)
     float* s1part;    // [256 * 8][128] partial sums of a2 * 2^4 written by the tcgen05 layer-3 kernel
     void* wimg_kb;    // 96 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
@@ -126,7 +125,6 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.moments = c.take<double>((size_t)B * 12);
     w.rtmp = c.take<double>((size_t)TL2_BLOCKS * C2 + 256);      // scratch rows of the fused tails (k_tail_l2 partials, BatchNorm-backward sums)
     w.dpart = c.take<double>((size_t)std::max(w.nb_a1 * C1, w.nb_a2 * C2));
-    w.dsum = c.take<double>(C2);
     // persistent tcgen05 kernels write one partial row per CTA (<= TC_MAX_CTAS rows)
     constexpr size_t TC_MAX_CTAS = 256;
     size_t fp = (size_t)w.nb_l2 * C2;                                        // css2 partials
@@ -153,7 +151,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     }
     w.wimg = c.take<unsigned char>((size_t)512 * 1024);
     w.mu_s = c.take<float>(C3);
-    w.mu_x = c.take<float>(C3);
+    w.centre2 = c.take<float>(C2);
     w.s1part = c.take<float>((size_t)256 * 8 * C2);
     w.wimg_kb = c.take<unsigned char>((size_t)96 * 1024);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
@@ -614,6 +612,7 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
         p.wimg2 = w.wimg_s; p.inv2 = w.inv_s; p.wimg3 = w.wimg; p.sgn = w.sgn;
 #ifndef PGPD_EMU
         p.act_shift = tc::ACT_SHIFT;
+        p.centre2 = (tcp && a.train) ? w.centre2 : nullptr;
 #endif
         const int n_sign = tcp ? 0 : C3 / PRE_THREADS;
         launch(k_tower_pre, dim3(p.n_mom + p.n_w2 + p.n_w3 + n_sign), dim3(PRE_THREADS), 0, s, p);
@@ -640,24 +639,25 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     }
 #endif
 
-    // ---- layer 1 (+ train: sum of a1, mean of the layer-2 pre-activation) ---------------------------------------------------
-    {
-        A1Params p{a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1, a.train ? w.dpart : (double*)nullptr,
-                   w.counters + 1, t.conv[1].w, count, w.bn[1].mean, w.S1a, w.bad, act_limit};
-        launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK * A1_CPB), a.B), dim3(A1_THREADS), 0, s, p);
-    }
-
-    // ---- layer 2 ---------------------------------------------------------------------------------------------------------
-    int n_css2 = 0;
+    // ---- layers 1 + 2 ---------------------------------------------------------------------------------------------------------
+    // Tensor-core path: ONE kernel; a1 is formed from the coordinates inside the layer-2 kernel's operand producers and never
+    // written (the backward recomputes it the same way, tc_kb.cuh).  CUDA-core path: k_a1 writes a1, a tiled GEMM reads it.
+    int n_css2 = 0, n_s1a = 0;
 #ifndef PGPD_EMU
     if (tcp) {
         const int tpc = idiv_up(a.N, tc::KF_NT), ntiles = a.B * tpc;
-        tc::KfParams p{(const __half*)w.wimg_s, w.inv_s, a.train ? (const float*)w.bn[1].mean : (const float*)nullptr,
-                       w.A1, w.Y2, w.fpart, a.B, a.N, tpc, ntiles};
-        n_css2 = tc::KF_EPI_ROWS * tc::launch_kf(p, tc::dev_info().sms, s);
+        tc::KfParams p{(const __half*)w.wimg_s, w.inv_s, a.train ? (const float*)w.centre2 : (const float*)nullptr,
+                       a.x, a.trans, t.conv[0].w, w.bn[0].scale, w.bn[0].shift, w.Y2, w.fpart,
+                       a.train ? w.pmax : (float*)nullptr, w.bad, a.B, a.N, tpc, ntiles};
+        const int grid = tc::launch_kf(p, tc::dev_info().sms, s);
+        n_css2 = tc::KF_EPI_ROWS * grid;
+        n_s1a = grid;
     } else
 #endif
     {
+        A1Params q{a.x, a.trans, a.B, a.N, t.conv[0].w, w.bn[0], w.A1, a.train ? w.dpart : (double*)nullptr,
+                   w.counters + 1, t.conv[1].w, count, w.bn[1].mean, w.S1a, w.bad, act_limit};
+        launch(k_a1, dim3(idiv_up(a.N, A1_CHUNK * A1_CPB), a.B), dim3(A1_THREADS), 0, s, q);
         ProbL2Fwd p{w.A1, t.conv[1].w, w.Y2, a.train ? w.bn[1].mean : nullptr, w.fpart, M};
         launch_gemm<ProbL2Fwd::Cfg>(p, dim3(w.nb_l2), s);
         n_css2 = w.nb_l2;
@@ -670,7 +670,9 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
     bool l3_pilot = false;
     if (a.train) {
         TailL2Params p{};
-        p.css = w.fpart; p.n_css = n_css2; p.mean_u2 = w.bn[1].mean; p.count = count; p.bias2 = t.conv[1].b; p.bn2 = t.bn[1]; p.st2 = w.bn[1];
+        p.css = w.fpart; p.n_css = n_css2;
+        p.s1a_part = tcp ? w.pmax : nullptr; p.n_s1a = n_s1a; p.S1a = w.S1a; p.s1a_scale = 1.0 / 16.0; p.W2 = t.conv[1].w;
+        p.mean_u2 = tcp ? w.centre2 : w.bn[1].mean; p.count = count; p.bias2 = t.conv[1].b; p.bn2 = t.bn[1]; p.st2 = w.bn[1];
         p.Y2 = w.Y2; p.part = w.rtmp; p.counter = w.counters + 2;
         p.W3 = t.conv[2].w; p.mean_u3 = w.bn[2].mean; p.S1 = w.S1; p.inv3 = w.sgn; p.mu_s = tcp ? w.mu_s : nullptr;
         const size_t total_samples = (size_t)TL2_BLOCKS * TL2_SPB;
@@ -800,8 +802,8 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
         __half* img1 = (__half*)w.wimg_kb;
         __half* img2 = img1 + tc::KB_A1_BYTES / 2;
         const int tpc = idiv_up(a.N, tc::KB_NT), ntiles = a.B * tpc;
-        tc::KbParams p{img1, img2, w.inv_s, w.cvec, t.bn[0].gamma, t.bn[0].beta, w.esc, w.einv, w.DZ2, w.A1, a.x,
-                       a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
+        tc::KbParams p{img1, img2, w.inv_s, w.cvec, t.bn[0].gamma, t.bn[0].beta, w.esc, w.einv, w.DZ2, a.x, a.trans,
+                       t.conv[0].w, w.bn[0].scale, w.bn[0].shift, a.B, a.N, tpc, ntiles, w.kb_Cpart, w.kb_G1part, w.kb_bn, w.kb_H};
         nparts = tc::launch_kb(p, tc::dev_info().sms, s);
         nrows = nparts * tc::KB_EPI_GROUPS; rpc = tpc * tc::KB_EPI_GROUPS;
     } else
