@@ -151,7 +151,7 @@ int pgpd_debug_l3_counters(long long* host_out) {
     (void)host_out; return PGPD_E_UNSUPPORTED;
 #else
     cudaDeviceSynchronize();
-    return cudaMemcpy(host_out, tc::l3_debug_buffer(), 256 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : PGPD_E_CUDA;
+    return cudaMemcpy(host_out, tc::l3_debug_buffer(), 512 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : PGPD_E_CUDA;
 #endif
 }
 
@@ -162,7 +162,7 @@ int pgpd_debug_stream_counters(int on) {
 #else
     long long* ptr = on ? tc::l3_debug_buffer() : nullptr;
     cudaDeviceSynchronize();
-    if (on) cudaMemset(ptr, 0, 256 * 8 * sizeof(long long));
+    if (on) cudaMemset(ptr, 0, 512 * 8 * sizeof(long long));
     return cudaMemcpyToSymbol(tc::g_stream_dbg, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : PGPD_E_CUDA;
 #endif
 }

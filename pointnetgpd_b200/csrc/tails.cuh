@@ -52,7 +52,8 @@ struct PreParams {
 namespace tc {
 // one row of a K-major hi/lo operand image: row r of [kb][part][128 rows][64 halves], 128-byte swizzle.
 // w: this thread's element k of the row (already sign-adjusted), mx: the row's max |w|.  Returns the exponent e used.
-__device__ __forceinline__ int prepack_elem(float w, float mx, int r, int k, __half* img, size_t img_base_halves) {
+__device__ __forceinline__ int prepack_elem(float w, float mx, int r, int k, __half* img, size_t img_base_halves,
+                                            size_t block_halves = 8192) {     // 8192: 128-row blocks; 4096: 64-row blocks
     int ex = 0;
     if (mx > 0.f) frexpf(mx, &ex);               // mx in [2^(ex-1), 2^ex)
     const int e = (mx > 0.f && mx < INFINITY) ? 14 - ex : 0;     // mx * 2^e in [2^13, 2^14)
@@ -60,10 +61,10 @@ __device__ __forceinline__ int prepack_elem(float w, float mx, int r, int k, __h
     const __half hi = __float2half_rn(ws);
     const __half lo = __float2half_rn(ws - __half2float(hi));
     const int kb = k >> 6, j = k & 63, chunk = j >> 3, within = j & 7;
-    const size_t base = img_base_halves + (size_t)(kb * 2) * 8192;
+    const size_t base = img_base_halves + (size_t)(kb * 2) * block_halves;
     const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
     img[base + off] = hi;
-    img[base + 8192 + off] = lo;
+    img[base + block_halves + off] = lo;
     return e;
 }
 }  // namespace tc
@@ -861,10 +862,11 @@ __device__ __forceinline__ void kb_prep_row(const KbPrepParams& p, int r) {
     }
 #ifndef PGPD_EMU
     if (!p.img1) return;
-    // row r of the two images: 128 + 64 values, common power-of-two scale
+    // row r (< 64: the images hold only their real rows, tc_kb.cuh) of the two images: 128 + 64 values, common power-of-two scale
+    if (r >= C1) return;
     float v = 0.f;
-    if (tid < C2) v = (r < C1) ? p.W2[tid * C1 + r] * p.st2.scale[tid] * s_einv[tid] : 0.f;
-    else if (tid < C2 + C1) v = (r < C1) ? -s_k[tid - C2] * (1.0f / p.act_scale) : 0.f;
+    if (tid < C2) v = p.W2[tid * C1 + r] * p.st2.scale[tid] * s_einv[tid];
+    else if (tid < C2 + C1) v = -s_k[tid - C2] * (1.0f / p.act_scale);
     if (tid < C2 + C1) s_red[tid] = fabsf(v);
     __syncthreads();
     if (tid < C1) s_red[tid] = fmaxf(s_red[tid], s_red[tid + C2]);
@@ -875,7 +877,7 @@ __device__ __forceinline__ void kb_prep_row(const KbPrepParams& p, int r) {
     }
     const float mx = s_red[0];
     if (tid < C2) {
-        const int e = tc::prepack_elem(v, mx, r, tid, (__half*)p.img1, 0);
+        const int e = tc::prepack_elem(v, mx, r, tid, (__half*)p.img1, 0, 4096);
         if (tid == 0) p.ginv[r] = ldexpf(1.f, -e);
     } else if (tid < C2 + C1) {
         int ex = 0;
@@ -889,7 +891,7 @@ __device__ __forceinline__ void kb_prep_row(const KbPrepParams& p, int r) {
         const size_t off = (size_t)r * 64 + (size_t)((chunk ^ (r & 7)) << 3) + within;
         __half* img2 = (__half*)p.img2;
         img2[off] = hi;
-        img2[8192 + off] = lo;
+        img2[4096 + off] = lo;
     }
 #endif
 }

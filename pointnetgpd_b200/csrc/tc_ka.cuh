@@ -5,12 +5,14 @@
 //   Gram = sum_P a2 a2^T   as  hi.hi  and  hi.lo  accumulators (Gram = hh + hl + hl^T: the third pass is the transpose
 //   of the second)
 //
-// Same structure as tc_kb.cuh: one persistent CTA per SM, 64-point tiles that never straddle a cloud; per tile the
-// loader warp bulk-copies the raw u2 rows (32 KB) into the operand buffer and the <= 64 sparse rows of d a2 that the
-// tile's points own into a staging buffer (it reads the tile's slot indices itself, one tile ahead); 8 converter
-// warps turn u2 into the a2 = relu(bn2(u2)) hi/lo fp16 operand tile IN PLACE; the epilogue (16 warps, channel = TMEM
-// lane) reads a2 back from the operand tile (mask, and yhat2 = (a2 - beta2)/gamma2 where a2 > 0) and the sparse
-// rows from shared memory, so it issues no global loads at all; its only global traffic are the dz2 stores.
+// One persistent CTA per SM, 64-point tiles that never straddle a cloud, a FOUR-deep ring of 32 KB operand buffers: the loader
+// bulk-copies the raw u2 rows of a tile into a buffer, 8 converter warps turn them into the a2 = relu(bn2(u2)) hi/lo fp16
+// operand tile IN PLACE, one thread issues the tile's MMAs, and the buffer is free again as soon as those complete.  The
+// epilogue (16 warps, channel = TMEM lane) does NOT touch the operand buffers: it re-reads its u2 values (L2 hits: the bulk copy
+// just fetched them) and the sparse rows of d a2 straight from global memory, issued BEFORE it waits for the accumulator, so
+// the loads hide behind the MMAs.  (Round 1 / early round 2 staged the sparse rows in shared memory and read a2 back from the
+// operand tile: the buffer then lived through copy + conversion + MMAs + epilogue, only two fitted, and the kernel ran at the
+// sum of its stages -- 5.3 k cycles per tile against an HBM floor of 2.6 k.)
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -18,14 +20,12 @@
 namespace pgpd { namespace tc {
 
 constexpr int KA_NT = 64;
+constexpr int KA_NBUF = 4;
 constexpr int KA_THREADS = 832;                             // 16 epilogue + 8 converter warps, loader warp, MMA issuer
 constexpr int KA_Q_BYTES = 65536;                           // Q image [kb][part][128 rows][128 B]
 constexpr int KA_OP_BYTES = 32768;                          // a2 tile [part][kb][64 rows][128 B]   (raw: [64][128] fp32)
-constexpr int KA_SP_BYTES = 32768;                          // sparse rows of the tile [64][128] fp32 (only owned rows are filled)
-constexpr int KA_BUF_BYTES = KA_OP_BYTES + KA_SP_BYTES;
 constexpr int KA_OFF_BUF = KA_Q_BYTES;
-constexpr int KA_OFF_SLOT = KA_OFF_BUF + 2 * KA_BUF_BYTES;  // [2][64] int
-constexpr int KA_OFF_MISC = KA_OFF_SLOT + 2 * KA_NT * 4;
+constexpr int KA_OFF_MISC = KA_OFF_BUF + KA_NBUF * KA_OP_BYTES;
 constexpr int KA_SMEM_BYTES = KA_OFF_MISC + 256 + 1024;
 constexpr int KA_EPI_ROWS = 4;                              // partial rows per CTA (four 16-column groups)
 
@@ -47,18 +47,17 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
     unsigned char* misc = smem + KA_OFF_MISC;
     const uint32_t bar0 = sbase + KA_OFF_MISC;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // 0 q_full | 1,2 full | 3,4 op_ready | 5,6 acc_full | 7,8 buf_empty | 9 final
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-    int* s_slot = reinterpret_cast<int*>(smem + KA_OFF_SLOT);        // [2][64]
+    // 0 q_full | 1..4 full (bulk copy landed) | 5..8 op_ready (converted) | 9..12 buf_empty (the tile's MMAs complete)
+    // 13,14 acc_full (d a2 accumulator complete) | 15,16 acc_empty (epilogue has it in registers) | 17 final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 160);
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(BAR(0), 1);
-        mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-        mbar_init(BAR(3), 256); mbar_init(BAR(4), 256);
-        mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-        mbar_init(BAR(7), 513); mbar_init(BAR(8), 513);
-        mbar_init(BAR(9), 1);
+        for (int b = 0; b < KA_NBUF; ++b) { mbar_init(BAR(1 + b), 1); mbar_init(BAR(5 + b), 256); mbar_init(BAR(9 + b), 1); }
+        mbar_init(BAR(13), 1); mbar_init(BAR(14), 1);
+        mbar_init(BAR(15), 512); mbar_init(BAR(16), 512);
+        mbar_init(BAR(17), 1);
         mbar_fence_init();
     }
     if (warp == 25) tmem_alloc<512>(smem_u32(tmem_slot));
@@ -69,66 +68,31 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
-    // tuning aid (pgpd_debug_stream_counters): 0 loader wait buf_empty | 1 load latency (issue -> landed, seen by a converter)
-    // 2 converter work | 3 mma wait op_ready | 4 mma issue | 5 epilogue wait acc_full | 6 epilogue work | 7 total
+    // tuning aid (pgpd_debug_stream_counters): 0 loader wait buf_empty | 2 converter work | 3 mma wait op_ready | 4 mma issue
+    // 5 epilogue wait acc_full | 6 epilogue work | 7 total
     long long* const dbg = g_stream_dbg;
     long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    volatile long long* s_clk = reinterpret_cast<volatile long long*>(misc + 160);
     const long long tk0 = dbg ? clock64() : 0;
 #define KA_T(slot, call) do { const long long _t0 = dbg ? clock64() : 0; call; if (dbg) dacc[slot] += clock64() - _t0; } while (0)
 
     if (warp == 24) {
-        // ===================== loader (whole warp: lane l owns points 2l, 2l+1 of the tile) =====================
+        // ===================== loader =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(BAR(0), KA_Q_BYTES);
             bulk_g2s(sbase, p.Qimg, KA_Q_BYTES, BAR(0));
-        }
-        auto tile_slots = [&](int t, int& s0, int& s1) {
-            s0 = -1; s1 = -1;
-            if (t < t_end) {
+            int i = 0;
+            for (int t = t_begin; t < t_end; ++t, ++i) {
+                const int b = i % KA_NBUF;
+                const uint32_t ph = (uint32_t)(i / KA_NBUF) & 1u;
                 const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
                 const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
                 const size_t P0 = (size_t)cb * p.N + n0;
-                if (2 * lane < nv) s0 = __ldg(p.slot + P0 + 2 * lane);
-                if (2 * lane + 1 < nv) s1 = __ldg(p.slot + P0 + 2 * lane + 1);
+                KA_T(0, mbar_wait(BAR(9 + b), ph ^ 1));
+                mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)nv * C2 * 4u);
+                bulk_g2s(sbase + KA_OFF_BUF + b * KA_OP_BYTES, p.Y2 + P0 * C2, (uint32_t)nv * C2 * 4u, BAR(1 + b));
             }
-        };
-        int s0, s1;
-        tile_slots(t_begin, s0, s1);
-        int i = 0;
-        for (int t = t_begin; t < t_end; ++t, ++i) {
-            const int b = i & 1;
-            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            int n0s, n1s;
-            tile_slots(t + 1, n0s, n1s);                    // next tile's slot indices: in flight while this tile is issued
-            if (lane == 0) {
-                const int tp = t + 3;                       // tile t+3 -> L2
-                if (tp < t_end) {
-                    const int cb = tp / p.tiles_per_cloud, tt = tp % p.tiles_per_cloud, n0 = tt * KA_NT;
-                    const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
-                    l2_prefetch(p.Y2 + ((size_t)cb * p.N + n0) * C2, (uint32_t)nv * C2 * 4u);
-                }
-            }
-            const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
-            const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
-            const size_t P0 = (size_t)cb * p.N + n0;
-            KA_T(0, mbar_wait(BAR(7 + b), ph ^ 1));
-            if (dbg && lane == 0) s_clk[b] = clock64();
-            s_slot[b * KA_NT + 2 * lane] = s0;
-            s_slot[b * KA_NT + 2 * lane + 1] = s1;
-            const int cnt = __popc(__ballot_sync(0xffffffffu, s0 >= 0)) + __popc(__ballot_sync(0xffffffffu, s1 >= 0));
-            __syncwarp();
-            const uint32_t dst = sbase + KA_OFF_BUF + b * KA_BUF_BYTES;
-            if (lane == 0) {
-                mbar_arrive_expect_tx(BAR(1 + b), (uint32_t)(nv + cnt) * C2 * 4u);
-                bulk_g2s(dst, p.Y2 + P0 * C2, (uint32_t)nv * C2 * 4u, BAR(1 + b));
-            }
-            __syncwarp();
-            if (s0 >= 0) bulk_g2s(dst + KA_OP_BYTES + (uint32_t)(2 * lane) * 512u, p.da2s + (size_t)s0 * C2, 512u, BAR(1 + b));
-            if (s1 >= 0) bulk_g2s(dst + KA_OP_BYTES + (uint32_t)(2 * lane + 1) * 512u, p.da2s + (size_t)s1 * C2, 512u, BAR(1 + b));
-            s0 = n0s; s1 = n1s;
+            if (dbg) dbg[cta * 8 + 0] = dacc[0];
         }
-        if (dbg && lane == 0) dbg[cta * 8 + 0] = dacc[0];
     } else if (warp == 25) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -140,13 +104,14 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             const uint64_t dQ = desc_sw128_kmajor(sbase);
             int i = 0;
             for (int t = t_begin; t < t_end; ++t, ++i) {
-                const int b = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                KA_T(3, mbar_wait(BAR(3 + b), ph));
+                const int b = i % KA_NBUF, acc = i & 1;
+                const uint32_t ph = (uint32_t)(i / KA_NBUF) & 1u, aph = (uint32_t)(i >> 1) & 1u;
+                KA_T(3, mbar_wait(BAR(5 + b), ph));
+                mbar_wait(BAR(15 + acc), aph ^ 1);
                 tc_fence_after_sync();
                 const long long ti0 = dbg ? clock64() : 0;
-                const uint32_t op = sbase + KA_OFF_BUF + b * KA_BUF_BYTES;
-                const uint32_t d1 = tmem + (uint32_t)(b * KA_NT);
+                const uint32_t op = sbase + KA_OFF_BUF + b * KA_OP_BYTES;
+                const uint32_t d1 = tmem + (uint32_t)(acc * KA_NT);
                 const uint64_t kop = desc_sw128_kmajor(op), mop = desc_sw128_mnmajor(op, 8192);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
@@ -159,7 +124,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
                             mma_f16(d1, dQ + ((oa + k * 32) >> 4), kop + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
                     }
                 }
-                mma_commit(BAR(5 + b));
+                mma_commit(BAR(13 + acc));
                 // Gram: hh += a2_hi^T a2_hi,  hl += a2_hi^T a2_lo   (K = the tile's 64 points; both operands MN-major,
                 // the two 64-channel atoms of a part are 8 KB apart)
 #pragma unroll
@@ -171,61 +136,87 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
                         mma_f16(dg, mop + ((k * 2048) >> 4), mop + ((ob + k * 2048) >> 4), IDESC_MN, (first && k == 0) ? 0u : 1u);
                 }
                 first = 0;
-                mma_commit(BAR(7 + b));
+                mma_commit(BAR(9 + b));
                 if (dbg) dacc[4] += clock64() - ti0;
             }
-            mma_commit(BAR(9));
+            mma_commit(BAR(17));
             if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
     } else if (warp < 16) {
         // ===================== epilogue: channel c = TMEM lane, 16 of the tile's 64 points per warp =====================
+        // The kernel is bound by instruction issue (16 epilogue warps x 16 points per tile), so this loop is written for few
+        // instructions per point: constant-offset loads / stores from one base pointer on full tiles, sparse rows loaded
+        // unconditionally (row 0 for a point that owns none) and discarded after the wait -- a select on the loaded value before
+        // the wait would make the thread wait for the load at once --, folded constants.
         const int q = warp & 3, cgp = warp >> 2;
         const int c = q * 32 + lane;
-        const float inv = p.inv[c], u = p.uvec[c], be = p.beta2[c];
-        const float gm = p.gamma2[c], g2inv = gm != 0.f ? 1.0f / gm : 0.f;
-        const uint32_t coff = (uint32_t)((c & 7) * 2), cchunk = (uint32_t)((c & 63) >> 3), ckb = (uint32_t)(c >> 6);
+        const float ninv = -p.inv[c], u = p.uvec[c];
+        const float gm = p.gamma2[c], g2inv = gm != 0.f ? 1.0f / gm : 0.f, nbg = -p.beta2[c] * g2inv;   // yhat2 = a2 g2inv + nbg
+        const float sc2 = p.scale2[c], sh2 = p.shift2[c];
+        const float* sp_c = p.da2s + c;
         float s1 = 0.f, s2 = 0.f, mxdz = 0.f;
+        int cb = t_begin / p.tiles_per_cloud, tt = t_begin % p.tiles_per_cloud;      // advanced incrementally (no divisions per tile)
+        // slot index (row of the sparse part of d a2, or -1) of this warp's 16 points: lane j < 16 holds point cgp*16 + j;
+        // fetched one tile ahead
+        auto tile_slot = [&](int cbx, int ttx) -> int {
+            if (cbx >= p.B || lane >= 16) return -1;
+            const int n = ttx * KA_NT + cgp * 16 + lane;
+            return n < p.N ? __ldg(p.slot + (size_t)cbx * p.N + n) : -1;
+        };
+        int myslot = (t_begin < t_end) ? tile_slot(cb, tt) : -1;
         int i = 0;
         for (int t = t_begin; t < t_end; ++t, ++i) {
-            const int b = i & 1;
-            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
+            const int acc = i & 1;
+            const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+            const int n0 = tt * KA_NT;
             const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
-            const size_t P0 = (size_t)cb * p.N + n0;
-            KA_T(5, mbar_wait(BAR(5 + b), ph));
+            const size_t Pw = (size_t)cb * p.N + n0 + cgp * 16;          // this warp's first point
+            // u2 and the sparse rows of this tile: loads issued before the wait for the accumulator
+            const float* yin = p.Y2 + Pw * C2 + c;
+            float yv[16], sv[16];
+            if (nv == KA_NT) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yv[j] = __ldg(yin + j * C2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int pp = cgp * 16 + j;
+                    yv[j] = __ldg(yin + (ptrdiff_t)((pp < nv ? pp : nv - 1) - cgp * 16) * C2);
+                }
+            }
+            const unsigned own = __ballot_sync(0xffffffffu, myslot >= 0);      // bit j: point j of this warp owns a sparse row
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int sl = __shfl_sync(0xffffffffu, myslot, j);
+                sv[j] = __ldg(sp_c + (size_t)(unsigned)(sl < 0 ? 0 : sl) * C2);   // always a valid row; discarded below if not owned
+            }
+            int cbn = cb, ttn = tt + 1;
+            if (ttn == p.tiles_per_cloud) { ttn = 0; ++cbn; }
+            myslot = (t + 1 < t_end) ? tile_slot(cbn, ttn) : -1;
+            KA_T(5, mbar_wait(BAR(13 + acc), aph));
             tc_fence_after_sync();
             const long long te0 = dbg ? clock64() : 0;
             float v[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KA_NT + cgp * 16), v);
-            const unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES + ckb * 8192;
-            const float* sp = reinterpret_cast<const float*>(smem + KA_OFF_BUF + b * KA_BUF_BYTES + KA_OP_BYTES);
-            const int* sl = s_slot + b * KA_NT;
-            float* dzo = p.DZ2 + P0 * C2 + c;
-            float av[16], sv[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {                  // a2 read back from the operand tile, sparse rows from the staging buffer
-                const int pp = cgp * 16 + j;
-                const uint32_t off = (uint32_t)pp * 128u + ((cchunk ^ (uint32_t)(pp & 7)) << 4) + coff;
-                av[j] = (__half2float(*reinterpret_cast<const __half*>(opb + off)) +
-                         __half2float(*reinterpret_cast<const __half*>(opb + 16384 + off))) * (1.0f / ACT_SCALE);
-                sv[j] = (sl[pp] >= 0) ? sp[pp * C2 + c] : 0.f;
-            }
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * KA_NT + cgp * 16), v);
+            tc_fence_before_sync();
+            mbar_arrive(BAR(15 + acc));                     // the accumulator is in registers
+            float* dzo = p.DZ2 + Pw * C2 + c;
+            const int nj = nv - cgp * 16;                   // valid points of this warp's 16 (>= 16 on full tiles)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int pp = cgp * 16 + j;
-                if (pp < nv) {
-                    const float a = av[j];
-                    const float da2 = -v[j] * inv - u + sv[j];
+                if (nv == KA_NT || j < nj) {
+                    const float a = fmaxf(fmaf(sc2, yv[j], sh2), 0.f);      // a2 (same sign decision as the operand tile's)
+                    const float da2 = fmaf(v[j], ninv, ((own >> j) & 1u ? sv[j] : 0.f) - u);
                     const float dz = a > 0.f ? da2 : 0.f;
-                    dzo[(size_t)pp * C2] = dz;
-                    const float yh = (a - be) * g2inv;      // only used where dz != 0
+#ifndef PGPD_DIAG_NOSTORE
+                    dzo[j * C2] = dz;
+#endif
                     s1 += dz;
-                    s2 = fmaf(dz, yh, s2);
+                    s2 = fmaf(dz, fmaf(a, g2inv, nbg), s2);                 // yhat2 only matters where dz != 0
                     mxdz = fmaxf(mxdz, fabsf(dz));
                 }
             }
-            tc_fence_before_sync();
-            mbar_arrive(BAR(7 + b));
+            cb = cbn; tt = ttn;
             if (dbg) dacc[6] += clock64() - te0;
         }
         if (dbg && warp == 0 && lane == 0) { dbg[cta * 8 + 5] = dacc[5]; dbg[cta * 8 + 6] = dacc[6]; dbg[cta * 8 + 7] = clock64() - tk0; }
@@ -242,14 +233,13 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
         const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
         int i = 0;
         for (int t = t_begin; t < t_end; ++t, ++i) {
-            const int b = i & 1;
-            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int b = i % KA_NBUF;
+            const uint32_t ph = (uint32_t)(i / KA_NBUF) & 1u;
             const int tt = t % p.tiles_per_cloud, n0 = tt * KA_NT;
             const int nv = (p.N - n0 < KA_NT) ? p.N - n0 : KA_NT;
             mbar_wait(BAR(1 + b), ph);
             const long long tc0 = dbg ? clock64() : 0;
-            if (dbg) dacc[1] += tc0 - s_clk[b];
-            unsigned char* opb = smem + KA_OFF_BUF + b * KA_BUF_BYTES;
+            unsigned char* opb = smem + KA_OFF_BUF + b * KA_OP_BYTES;
             float4 ry[8];
 #pragma unroll
             for (int uu = 0; uu < 8; ++uu) ry[uu] = *reinterpret_cast<const float4*>(opb + (cw * 8 + uu) * 512 + lane * 16);
@@ -273,17 +263,17 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
                 *reinterpret_cast<uint2*>(opb + (1 * 2 + kb) * 8192 + off) = lv;
             }
             fence_proxy_async_smem();
-            mbar_arrive(BAR(3 + b));
+            mbar_arrive(BAR(5 + b));
             if (dbg) dacc[2] += clock64() - tc0;
         }
-        if (dbg && cw == 0 && lane == 0) { dbg[cta * 8 + 1] = dacc[1]; dbg[cta * 8 + 2] = dacc[2]; }
+        if (dbg && cw == 0 && lane == 0) dbg[cta * 8 + 2] = dacc[2];
     }
 #undef KA_T
 
     // ===================== read-out of the Gram accumulators (warps 0..15) =====================
     if (warp < 16) {
         const int q = warp & 3, cg = warp >> 2, row = q * 32 + lane;
-        mbar_wait(BAR(9), 0);
+        mbar_wait(BAR(17), 0);
         tc_fence_after_sync();
 #pragma unroll 1
         for (int part = 0; part < 2; ++part) {

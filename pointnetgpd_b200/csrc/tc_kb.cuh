@@ -25,15 +25,20 @@ namespace pgpd { namespace tc {
 constexpr int KB_NT = 64;                                   // points per tile
 constexpr int KB_THREADS = 832;                             // 26 warps: 8 epilogue + 16 converter, loader, MMA issuer
 constexpr int KB_CONV_THREADS = 512;
-constexpr int KB_A1_BYTES = 65536;                          // W2^T image  [kb][part][128 rows][128 B]
-constexpr int KB_A2_BYTES = 32768;                          // -K image        [part][128 rows][128 B]
+constexpr int KB_NBUF = 3;                                  // operand buffers in flight
+// The two A-operand images hold only their 64 real rows (features): the M = 128 MMAs read rows 64..127 from whatever follows
+// in shared memory (the next 8 KB block), which only fills TMEM lanes 64..127 of the d a1 accumulator -- lanes nobody reads.
+// Zero-padding the images to 128 rows (round 1) cost 48 KB, i.e. the third operand buffer.
+constexpr int KB_A1_BYTES = 32768;                          // W2^T image  [kb][part][64 rows][128 B]
+constexpr int KB_A2_BYTES = 16384;                          // -K image        [part][64 rows][128 B]
+constexpr int KB_IMG_BLOCK = 8192;                          // bytes per (kb, part) block of an image
 constexpr int KB_DZ_BYTES = 32768;                          // dz2 tile    [part][kb][64 rows][128 B]  (raw: [64][128] fp32)
 constexpr int KB_A1T_BYTES = 16384;                         // a1 tile         [part][64 rows][128 B]  (raw: [64][64] fp32)
 constexpr int KB_BUF_BYTES = KB_DZ_BYTES + KB_A1T_BYTES;
 constexpr int KB_OFF_A2 = KB_A1_BYTES;
 constexpr int KB_OFF_BUF = KB_A1_BYTES + KB_A2_BYTES;
-constexpr int KB_OFF_X = KB_OFF_BUF + 2 * KB_BUF_BYTES;     // [2][3][64] floats
-constexpr int KB_OFF_MISC = KB_OFF_X + 2 * 3 * KB_NT * 4;
+constexpr int KB_OFF_X = KB_OFF_BUF + KB_NBUF * KB_BUF_BYTES;   // [KB_NBUF][3][64] floats
+constexpr int KB_OFF_MISC = KB_OFF_X + KB_NBUF * 3 * KB_NT * 4;
 constexpr int KB_SMEM_BYTES = KB_OFF_MISC + 256 + 1024;
 constexpr int KB_EPI_GROUPS = 4;                            // column groups of 16 points: partial rows per tile / per CTA
 
@@ -58,19 +63,18 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     unsigned char* misc = smem + KB_OFF_MISC;
     const uint32_t bar0 = sbase + KB_OFF_MISC;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // 0 a_full | 1,2 full (bulk copies landed) | 3,4 op_ready (converted) | 5,6 acc_full (D1 complete)
-    // 7,8 buf_empty (all MMAs reading the buffer complete + epilogue done with it) | 9 final (every MMA complete)
+    // 0 a_full | 1..3 full (bulk copies landed) | 4..6 op_ready (converted) | 7..9 buf_empty (all MMAs reading the buffer complete +
+    // epilogue done with it) | 10,11 acc_full (D1 complete) | 12,13 acc_empty (epilogue has D1 in registers) | 14 final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-    float* sx = reinterpret_cast<float*>(smem + KB_OFF_X);           // [2][3][64]
+    float* sx = reinterpret_cast<float*>(smem + KB_OFF_X);           // [KB_NBUF][3][64]
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(BAR(0), 1);
-        mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-        mbar_init(BAR(3), KB_CONV_THREADS); mbar_init(BAR(4), KB_CONV_THREADS);
-        mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-        mbar_init(BAR(7), 257); mbar_init(BAR(8), 257);
-        mbar_init(BAR(9), 1);
+        for (int b = 0; b < KB_NBUF; ++b) { mbar_init(BAR(1 + b), 1); mbar_init(BAR(4 + b), KB_CONV_THREADS); mbar_init(BAR(7 + b), 257); }
+        mbar_init(BAR(10), 1); mbar_init(BAR(11), 1);
+        mbar_init(BAR(12), 256); mbar_init(BAR(13), 256);
+        mbar_init(BAR(14), 1);
         mbar_fence_init();
     }
     if (warp == 25) tmem_alloc<256>(smem_u32(tmem_slot));
@@ -83,9 +87,9 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
     // tuning aid (pgpd_debug_stream_counters): 0 loader wait buf_empty | 1 load latency (issue -> landed, seen by a converter)
     // 2 converter work | 3 mma wait op_ready | 4 mma issue | 5 epilogue wait acc_full | 6 epilogue work | 7 total
-    long long* const dbg = g_stream_dbg;
+    long long* const dbg = g_stream_dbg ? g_stream_dbg + 256 * 8 : nullptr;      // rows 256.. of the debug buffer
     long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    volatile long long* s_clk = reinterpret_cast<volatile long long*>(misc + 160);      // [2] issue time of the buffer's loads
+    volatile long long* s_clk = reinterpret_cast<volatile long long*>(misc + 160);      // [KB_NBUF] issue time of the buffer's loads
     const long long tk0 = dbg ? clock64() : 0;
 #define KB_T(slot, call) do { const long long _t0 = dbg ? clock64() : 0; call; if (dbg) dacc[slot] += clock64() - _t0; } while (0)
 
@@ -97,10 +101,10 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             bulk_g2s(sbase + KB_OFF_A2, p.A2img, KB_A2_BYTES, BAR(0));
             int i = 0;
             for (int t = t_begin; t < t_end; ++t, ++i) {
-                const int b = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                {   // tile t+3 -> L2
-                    const int tp = t + 3;
+                const int b = i % KB_NBUF;
+                const uint32_t ph = (uint32_t)(i / KB_NBUF) & 1u;
+                {   // tile t+4 -> L2
+                    const int tp = t + 4;
                     if (tp < t_end) {
                         const int cb = tp / p.tiles_per_cloud, tt = tp % p.tiles_per_cloud, n0 = tt * KB_NT;
                         const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
@@ -130,13 +134,14 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
             const uint64_t dA1 = desc_sw128_kmajor(sbase), dA2 = desc_sw128_kmajor(sbase + KB_OFF_A2);
             int i = 0;
             for (int t = t_begin; t < t_end; ++t, ++i) {
-                const int b = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                KB_T(3, mbar_wait(BAR(3 + b), ph));
+                const int b = i % KB_NBUF, acc = i & 1;
+                const uint32_t ph = (uint32_t)(i / KB_NBUF) & 1u, aph = (uint32_t)(i >> 1) & 1u;
+                KB_T(3, mbar_wait(BAR(4 + b), ph));
+                mbar_wait(BAR(12 + acc), aph ^ 1);
                 tc_fence_after_sync();
                 const long long ti0 = dbg ? clock64() : 0;
                 const uint32_t dz = sbase + KB_OFF_BUF + b * KB_BUF_BYTES, a1 = dz + KB_DZ_BYTES;
-                const uint32_t d1 = tmem + (uint32_t)(b * KB_NT);
+                const uint32_t d1 = tmem + (uint32_t)(acc * KB_NT);
                 // descriptors: one base per operand, every other one is base + (byte offset >> 4) in the address field
                 const uint64_t kA1 = dA1, kA2 = dA2;
                 const uint64_t kdz = desc_sw128_kmajor(dz), ka1 = desc_sw128_kmajor(a1);
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t oa = (uint32_t)((kb * 2 + (pass == 1 ? 1 : 0)) * 16384);
+                        const uint32_t oa = (uint32_t)((kb * 2 + (pass == 1 ? 1 : 0)) * KB_IMG_BLOCK);
                         const uint32_t ob = (uint32_t)(((pass == 2 ? 1 : 0) * 2 + kb) * 8192);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -156,12 +161,12 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 // ---- D1 += A2op x a1 (K = 64 channels)
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t oa = (pass == 1) ? 16384u : 0u, ob = (pass == 2) ? 8192u : 0u;
+                    const uint32_t oa = (pass == 1) ? (uint32_t)KB_IMG_BLOCK : 0u, ob = (pass == 2) ? 8192u : 0u;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         mma_f16(d1, kA2 + ((oa + k * 32) >> 4), ka1 + ((ob + k * 32) >> 4), IDESC_K, 1u);
                 }
-                mma_commit(BAR(5 + b));                     // d a1 of this tile complete -> epilogue
+                mma_commit(BAR(10 + acc));                  // d a1 of this tile complete -> epilogue
                 // ---- D2 += dz^T a1 (K = 64 points, MN-major operands; A atoms = the two 64-channel blocks, 8 KB apart)
                 {
                     const uint32_t d2 = tmem + 128u;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 mma_commit(BAR(7 + b));                     // the tensor core is done reading this buffer
                 if (dbg) dacc[4] += clock64() - ti0;
             }
-            mma_commit(BAR(9));
+            mma_commit(BAR(14));
             if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
     } else if (warp < 16 && (warp & 3) < 2) {
@@ -203,15 +208,17 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
         float s1 = 0.f, s2 = 0.f;
         int i = 0;
         for (int t = t_begin; t < t_end; ++t, ++i) {
-            const int b = i & 1;
-            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int b = i % KB_NBUF, acc = i & 1;
+            const uint32_t aph = (uint32_t)(i >> 1) & 1u;
             const int tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
             const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
-            KB_T(5, mbar_wait(BAR(5 + b), ph));
+            KB_T(5, mbar_wait(BAR(10 + acc), aph));
             tc_fence_after_sync();
             const long long te0 = dbg ? clock64() : 0;
             float v[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * KB_NT + cgp * 16), v);
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * KB_NT + cgp * 16), v);
+            tc_fence_before_sync();
+            mbar_arrive(BAR(12 + acc));                     // the accumulator is in registers
             const unsigned char* a1b = smem + KB_OFF_BUF + b * KB_BUF_BYTES + KB_DZ_BYTES;
             const float* xb = sx + b * (3 * KB_NT);
             float h0 = 0.f, h1 = 0.f, h2 = 0.f;
@@ -260,8 +267,8 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
         }
         int i = 0;
         for (int t = t_begin; t < t_end; ++t, ++i) {
-            const int b = i & 1;
-            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int b = i % KB_NBUF;
+            const uint32_t ph = (uint32_t)(i / KB_NBUF) & 1u;
             const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KB_NT;
             const int nv = (p.N - n0 < KB_NT) ? p.N - n0 : KB_NT;
             float xv = 0.f;
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(BAR(3 + b));
+            mbar_arrive(BAR(4 + b));
             if (dbg) dacc[2] += clock64() - tc0;
         }
         if (dbg && cw == 0 && lane == 0) { dbg[cta * 8 + 1] = dacc[1]; dbg[cta * 8 + 2] = dacc[2]; }
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     // ===================== read-out of the persistent accumulators (warps 0..15: all four TMEM lane quadrants) ==========
     if (warp < 16) {
         const int q = warp & 3, cg = warp >> 2, row = q * 32 + lane;
-        mbar_wait(BAR(9), 0);
+        mbar_wait(BAR(14), 0);
         tc_fence_after_sync();
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(cg * 16), v);

@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float u = v[j] * inv;
+#ifndef PGPD_DIAG_NOSTORE
                     yo[(size_t)(half * 32 + j) * C2] = u;
+#endif
                     const float d = u - mu;
                     css = fmaf(d, d, css);
                 }
@@ -165,33 +167,33 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
             sf[j] = p.sh1[c] * ACT_SCALE;
         }
         float sa[4] = {0.f, 0.f, 0.f, 0.f};
-        // the tile's points, transformed (x' = T^T x): threads 0..63, one point each; the loads of tile t + 1 are issued before
-        // tile t is converted (their latency would otherwise sit on every tile's critical path)
-        auto load_point = [&](int t, float& t0, float& t1, float& t2) {
-            t0 = 0.f; t1 = 0.f; t2 = 0.f;
+        // the tile's points (threads 0..63, one point each) and the cloud's transform: the RAW loads of tile t + 1 are issued
+        // while tile t is converted and first touched one iteration later (any arithmetic on them here would wait for them here)
+        float rp[3], rT[9];
+        auto load_raw = [&](int t) {
+            rp[0] = rp[1] = rp[2] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) rT[e] = (e % 4 == 0) ? 1.f : 0.f;
             if (t >= t_end || ctid >= KF_NT) return;
             const int cb = t / p.tiles_per_cloud, n = (t % p.tiles_per_cloud) * KF_NT + ctid;
-            if (n >= p.N) return;
-            const float* xb = p.x + (size_t)cb * 3 * p.N + n;
-            const float p0 = __ldg(xb), p1 = __ldg(xb + p.N), p2 = __ldg(xb + 2 * (size_t)p.N);
-            t0 = p0; t1 = p1; t2 = p2;
+            const float* xb = p.x + (size_t)cb * 3 * p.N + (n < p.N ? n : p.N - 1);
+            rp[0] = __ldg(xb); rp[1] = __ldg(xb + p.N); rp[2] = __ldg(xb + 2 * (size_t)p.N);
             if (p.trans) {
-                const float* T = p.trans + (size_t)cb * 9;
-                t0 = __ldg(T + 0) * p0 + __ldg(T + 3) * p1 + __ldg(T + 6) * p2;
-                t1 = __ldg(T + 1) * p0 + __ldg(T + 4) * p1 + __ldg(T + 7) * p2;
-                t2 = __ldg(T + 2) * p0 + __ldg(T + 5) * p1 + __ldg(T + 8) * p2;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) rT[e] = __ldg(p.trans + (size_t)cb * 9 + e);
             }
         };
-        float nx0, nx1, nx2;
-        load_point(t_begin, nx0, nx1, nx2);
+        load_raw(t_begin);
         int i = 0;
         for (int t = t_begin; t < t_end; ++t, ++i) {
             const int b = i % KF_NBUF;
             const uint32_t ph = (uint32_t)(i / KF_NBUF) & 1u;
             const int cb = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud, n0 = tt * KF_NT;
             const int nv = (p.N - n0 < KF_NT) ? p.N - n0 : KF_NT;
-            const float t0 = nx0, t1 = nx1, t2 = nx2;
-            load_point(t + 1, nx0, nx1, nx2);
+            const float t0 = rT[0] * rp[0] + rT[3] * rp[1] + rT[6] * rp[2];
+            const float t1 = rT[1] * rp[0] + rT[4] * rp[1] + rT[7] * rp[2];
+            const float t2 = rT[2] * rp[0] + rT[5] * rp[1] + rT[8] * rp[2];
+            load_raw(t + 1);
             mbar_wait(BAR(9 + b), ph ^ 1);                  // the MMAs that read this buffer four tiles ago are done
             float* sxb = sx + b * (3 * KF_NT);
             if (ctid < KF_NT) { sxb[ctid] = t0; sxb[KF_NT + ctid] = t1; sxb[2 * KF_NT + ctid] = t2; }

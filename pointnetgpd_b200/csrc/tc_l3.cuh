@@ -444,11 +444,11 @@ inline DevInfo& dev_info() {
 inline bool available() { return dev_info().state == 1; }
 
 // tuning aid, only in builds with -DPGPD_DEBUG (never in the product library: the ABI promises no allocation, no global
-// state): a lazily cudaMalloc'ed [256][8] int64 buffer of pipeline cycle counters, used when PGPD_L3_DEBUG is set
+// state): a lazily cudaMalloc'ed [512][8] int64 buffer (rows 256.. : the layer-2/1 backward kernel) of pipeline cycle counters, used when PGPD_L3_DEBUG is set
 #ifdef PGPD_DEBUG
 inline long long* l3_debug_buffer() {
     static long long* buf = nullptr;
-    if (!buf) { cudaMalloc(&buf, 256 * 8 * sizeof(long long)); cudaMemset(buf, 0, 256 * 8 * sizeof(long long)); }
+    if (!buf) { cudaMalloc(&buf, 512 * 8 * sizeof(long long)); cudaMemset(buf, 0, 512 * 8 * sizeof(long long)); }
     return buf;
 }
 inline long long* l3_debug_buffer_if_enabled() {

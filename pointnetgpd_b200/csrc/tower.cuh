@@ -60,7 +60,7 @@ struct TowerScratch {
     float* mu_s;      // [1024] mean of u3 in accumulator units (tcgen05 kernel)
     float* centre2;   // [128] pilot estimate of mean(u2) the tcgen05 layer-2 kernel centres its squares on (train)
     float* s1part;    // [256 * 8][128] partial sums of a2 * 2^4 written by the tcgen05 layer-3 kernel
-    void* wimg_kb;    // 96 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
+    void* wimg_kb;    // 48 KB: the two A-operand images of the fused layer-2/1 backward pass (tc_kb.cuh)
     void* wimg_s;     // 64 KB: image of the resident weight matrix of a streaming tcgen05 GEMM
     float* inv_s;     // [128] its per-row inverse scales
     float* pmax;      // [1024][2][128] per-epilogue-row maxima of |dz2|, |yhat2|
@@ -153,7 +153,7 @@ inline void plan_tower_scratch(Carver& c, TowerScratch& w, int B, int N, bool ba
     w.mu_s = c.take<float>(C3);
     w.centre2 = c.take<float>(C2);
     w.s1part = c.take<float>((size_t)256 * 8 * C2);
-    w.wimg_kb = c.take<unsigned char>((size_t)96 * 1024);
+    w.wimg_kb = c.take<unsigned char>((size_t)48 * 1024);
     w.wimg_s = c.take<unsigned char>((size_t)64 * 1024);
     w.inv_s = c.take<float>(C2);
     w.pmax = c.take<float>((size_t)1024 * 2 * C2);
@@ -792,7 +792,7 @@ inline void tower_backward(const TowerArgs& a, TowerWs& w, const pgpd_tower_grad
     launch(k_tail_ka, dim3(tk.gcols / 256 + 8 + (tcp ? 4 : 0)), dim3(1024), 0, s, tk);
 
     // ---- dW3 ---------------------------------------------------------------------------------------------------------------
-    launch(k_dw3, dim3(C3 + (tcp ? C2 : C1)), dim3(512), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
+    launch(k_dw3, dim3(C3 + C1), dim3(512), 0, s, (const float*)w.coef, (const int*)w.idx, (const float*)w.Y2, w.bn[1], a.B, a.N,
            (const float*)w.dvec, (const float*)w.evec, t.conv[2].w, (const float*)w.gram, (const double*)w.S1, g.conv[2].dw, g.conv[2].db, kp);
 
     // ---- layers 2 and 1: one fused pass over (dz2, a1) (l2bwd.cuh / tc_kb.cuh) -------------------------------------------------

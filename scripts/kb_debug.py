@@ -21,11 +21,11 @@ torch.cuda.synchronize()
 lib.pgpd_debug_stream_counters(1)
 step()
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * (256 * 8))()
+buf = (ctypes.c_longlong * (512 * 8))()
 lib.pgpd_debug_l3_counters.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
 lib.pgpd_debug_l3_counters(buf)
 lib.pgpd_debug_stream_counters(0)
-a = np.array(buf[:], dtype=np.int64).reshape(256, 8)[:148]
+a = np.array(buf[:], dtype=np.int64).reshape(512, 8)[256:256 + 148]
 names = ["loader wait buf_empty", "load latency (issue->landed)", "converter work", "mma wait op_ready", "mma issue", "epi wait acc_full", "epi work", "total"]
 tiles = (B * (N // 64)) / 148
 print("kernel:", os.environ.get("WHICH", "kb"), "(ka: run with PGPD_TC_MASK=0x2F so that k_kb_tc does not overwrite the counters)")

@@ -14,10 +14,10 @@ for _ in range(3):
         m(x)
 torch.cuda.synchronize()
 lib = A.load()
-buf = (ctypes.c_longlong * (256 * 8))()
+buf = (ctypes.c_longlong * (512 * 8))()
 lib.pgpd_debug_l3_counters.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
 lib.pgpd_debug_l3_counters(buf)
-full = np.array(buf[:], dtype=np.int64).reshape(256, 8)
+full = np.array(buf[:], dtype=np.int64).reshape(512, 8)
 a = full[:148]
 ver = os.environ.get("PGPD_L3_VERSION", "1")
 if ver == "3":
