@@ -181,6 +181,38 @@ int pgpd_gpd_forward(const pgpd_gpd* m, const float* x, int B, int C, int flags,
 int pgpd_gpd_backward(const pgpd_gpd* m, const pgpd_gpd_grad* g, const float* x, int B, int C, int flags,
                       const float* dlogp, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the dual-cloud network (PointNetGPD/model/pointnet.py:48-120,157-174) ---------------------------
+ *   PGPD_DUAL_STN  : SimpleSTN3d        x [B,3,N] -> trans [B,3,3]          tower 3->64->128->256, head 256->128->64->9 (+ I)
+ *   PGPD_DUAL_FEAT : DualPointNetfeat   x [B,6,N] -> (G [B,1024], trans1 + trans2): one SimpleSTN3d per 3-channel half, each half
+ *                                       transformed by its own T-Net, trunk 6->64->128->1024 (no ReLU before the pool)
+ *   PGPD_DUAL_CLS  : DualPointNetCls    x [B,6,N] -> (logp [B,k], trans1 + trans2)
+ * The tower / head structs are the ones above with this network's widths (stn*_tower.conv[2].w is [256][128], stn*_head.fc[0].w
+ * [128][256], trunk.conv[0].w [64][6], ...).  PGPD_DUAL_STN reads stn1_* only.  fp32 CUDA-core kernels (csrc/dual.cuh); flags as for
+ * pgpd_forward (PGPD_F_TRAIN, PGPD_F_SAVE).  No reference script constructs these classes. */
+#define PGPD_DUAL_STN  11
+#define PGPD_DUAL_FEAT 12
+#define PGPD_DUAL_CLS  13
+typedef struct pgpd_dual {
+    pgpd_tower stn1_tower; pgpd_head stn1_head;       /* feat.stn1.*                                   */
+    pgpd_tower stn2_tower; pgpd_head stn2_head;       /* feat.stn2.*                                   */
+    pgpd_tower trunk;                                 /* feat.conv1-3 / feat.bn1-3                     */
+    pgpd_head  cls_head;                              /* fc1-3 / bn1-2                                 */
+} pgpd_dual;
+typedef struct pgpd_dual_grad {
+    pgpd_tower_grad stn1_tower; pgpd_head_grad stn1_head;
+    pgpd_tower_grad stn2_tower; pgpd_head_grad stn2_head;
+    pgpd_tower_grad trunk;
+    pgpd_head_grad  cls_head;
+} pgpd_dual_grad;
+size_t pgpd_dual_workspace_bytes(int what, int B, int N, int k, int flags);
+/*   out : PGPD_DUAL_CLS -> logp [B,k]; PGPD_DUAL_FEAT -> G [B,1024]; PGPD_DUAL_STN -> ignored;   trans: [B,3,3], always written */
+int pgpd_dual_forward(int what, const pgpd_dual* m, const float* x, int B, int N, int k, int flags,
+                      float* out, float* trans, void* workspace, size_t workspace_bytes, void* stream);
+/*   after pgpd_dual_forward(..., PGPD_F_TRAIN | PGPD_F_SAVE, ...) on the same workspace; dout: gradient w.r.t. out (PGPD_DUAL_STN:
+ *   NULL), dtrans: gradient w.r.t. trans or NULL for zero (PGPD_DUAL_STN: required).  Writes every gradient the module owns. */
+int pgpd_dual_backward(int what, const pgpd_dual* m, const pgpd_dual_grad* g, const float* x, int B, int N, int k, int flags,
+                       const float* dout, const float* dtrans, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- data preparation in front of the model ------------------------------------
  * Gripper-box crop of one cloud for G grasps (BaseGraspDataset.collect_pc, PointNetGPD/model/dataset.py:51-76;
  * kinect2grasp.py:178-235).

@@ -188,10 +188,49 @@ def run_collect_pc():
     print("wrote collect_pc golden:", [len(out[f"in_ind_{g}"]) for g in range(G)])
 
 
+def run_dual(only=False):
+    """DualPointNetCls(input_chann=6) (model/pointnet.py:157-174) on two seeded clouds per grasp: eval forward, and a training
+    forward + backward of sum(logp * wl) + sum(trans * wt)."""
+    from model.pointnet import DualPointNetCls
+    B, N, k, seed = 6, 72, 2, 41
+    st = W.make_state(seed, k=k, style="wild", dual=True)
+    x = np.concatenate([W.make_clouds(seed + 1000, B, N, "box"), W.make_clouds(seed + 1000 + 77, B, N, "box")], axis=1)
+    out = {"meta": np.array([B, N, k, seed], dtype=np.int64)}
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        m = DualPointNetCls(num_points=N, input_chann=6, k=k)
+        load_state(m, st)
+        m = m.to(dtype)
+        xt = torch.tensor(x).to(dtype)
+        m.eval()
+        with torch.no_grad():
+            logp_e, trans_e = m(xt)
+        out[f"eval_logp_{tag}"] = logp_e.numpy()
+        out[f"eval_trans_{tag}"] = trans_e.numpy()
+        m.train()
+        m.zero_grad()
+        logp, trans = m(xt)
+        wl = torch.tensor(W.normal(seed + 3000, (B, k))).to(dtype)
+        wt = torch.tensor(W.normal(seed + 4000, (B, 3, 3))).to(dtype)
+        ((logp * wl).sum() + (trans * wt).sum()).backward()
+        out[f"train_logp_{tag}"] = logp.detach().numpy()
+        out[f"train_trans_{tag}"] = trans.detach().numpy()
+        for pname, p in m.named_parameters():
+            g = p.grad.detach().numpy().reshape(-1)
+            out[f"gnorm_{tag}/{pname}"] = np.array(np.linalg.norm(g.astype(np.float64)))
+            out[f"gsub_{tag}/{pname}"] = g[sub_idx(g.size)]
+        for bname, b in m.named_buffers():
+            out[f"buf_{tag}/{bname}"] = b.detach().numpy()
+    np.savez_compressed(os.path.join(GOLD, "dual_b6_n72_k2.npz"), **out)
+    print("wrote dual_b6_n72_k2; eval logp[0] =", out["eval_logp_f32"][0])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     PointNetCls = _import_reference()
+    run_dual()
+    if "--dual-only" in sys.argv:
+        return
     for case in CASES:
         run_case(PointNetCls, *case)
     run_shipped(PointNetCls)

@@ -69,7 +69,20 @@ class GpdGrad(C.Structure):
 
 GPD_LAYERS = ("conv1", "conv2", "fc1", "fc2")
 
-EXPORTS = ("pgpd_gpd_workspace_bytes", "pgpd_gpd_forward", "pgpd_gpd_backward", "pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_launch_count",
+# the dual-cloud network (SimpleSTN3d / DualPointNetfeat / DualPointNetCls, pointnet.py:48-120,157-174)
+PGPD_DUAL_STN, PGPD_DUAL_FEAT, PGPD_DUAL_CLS = 11, 12, 13
+
+
+class Dual(C.Structure):
+    _fields_ = [("stn1_tower", Tower), ("stn1_head", Head), ("stn2_tower", Tower), ("stn2_head", Head), ("trunk", Tower), ("cls_head", Head)]
+
+
+class DualGrad(C.Structure):
+    _fields_ = [("stn1_tower", TowerGrad), ("stn1_head", HeadGrad), ("stn2_tower", TowerGrad), ("stn2_head", HeadGrad),
+                ("trunk", TowerGrad), ("cls_head", HeadGrad)]
+
+
+EXPORTS = ("pgpd_dual_workspace_bytes", "pgpd_dual_forward", "pgpd_dual_backward", "pgpd_gpd_workspace_bytes", "pgpd_gpd_forward", "pgpd_gpd_backward", "pgpd_version", "pgpd_last_error", "pgpd_has_tensor_core_path", "pgpd_launch_count",
            "pgpd_profile_enable", "pgpd_profile_read", "pgpd_workspace_bytes",
            "pgpd_forward", "pgpd_backward", "pgpd_tower_workspace_bytes", "pgpd_tower_forward",
            "pgpd_tower_backward", "pgpd_crop_box", "pgpd_resample")
@@ -110,6 +123,13 @@ def bind(lib):
     lib.pgpd_gpd_forward.argtypes = [C.POINTER(Gpd), _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]
     lib.pgpd_gpd_backward.restype = C.c_int
     lib.pgpd_gpd_backward.argtypes = [C.POINTER(Gpd), C.POINTER(GpdGrad), _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]
+    lib.pgpd_dual_workspace_bytes.restype = C.c_size_t
+    lib.pgpd_dual_workspace_bytes.argtypes = [C.c_int] * 5
+    lib.pgpd_dual_forward.restype = C.c_int
+    lib.pgpd_dual_forward.argtypes = [C.c_int, C.POINTER(Dual), _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]
+    lib.pgpd_dual_backward.restype = C.c_int
+    lib.pgpd_dual_backward.argtypes = [C.c_int, C.POINTER(Dual), C.POINTER(DualGrad), _fp, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]
     lib.pgpd_crop_box.restype = C.c_int
     lib.pgpd_crop_box.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp]
     lib.pgpd_resample.restype = C.c_int
@@ -251,4 +271,59 @@ def buffer_keys(what=PGPD_CLS):
     if what == PGPD_CLS:
         for b in HEAD_CLS[1]:
             bn(HEAD_CLS[0] + b)
+    return keys
+
+
+# ---- the dual-cloud network: module-relative key prefixes per sub-struct ------------------------------------------------------------
+#   PGPD_DUAL_CLS keys are DualPointNetCls-relative ("feat.stn1.conv1.weight", ..., "fc3.bias"); stand-alone DualPointNetfeat /
+#   SimpleSTN3d modules strip "feat." / use no prefix at all (see functional.run_dual).
+_DUAL_STN_HEAD_BNS = ("bn4", "bn5")
+
+
+def _dual_parts(what):
+    """[(struct field, kind, key prefix, head BatchNorm names)] of the sub-structs a module owns, in ABI order."""
+    if what == PGPD_DUAL_STN:
+        return [("stn1_tower", "tower", "", None), ("stn1_head", "head", "", _DUAL_STN_HEAD_BNS)]
+    pre = "feat." if what == PGPD_DUAL_CLS else ""
+    parts = []
+    for i in (1, 2):
+        parts += [("stn%d_tower" % i, "tower", pre + "stn%d." % i, None), ("stn%d_head" % i, "head", pre + "stn%d." % i, _DUAL_STN_HEAD_BNS)]
+    parts.append(("trunk", "tower", pre, None))
+    if what == PGPD_DUAL_CLS:
+        parts.append(("cls_head", "head", "", ("bn1", "bn2")))
+    return parts
+
+
+def build_dual(ptr, what, grad=False):
+    """ptr(key) -> device address of the tensor (grad: of its gradient) stored under the module-relative state-dict key."""
+    m = DualGrad() if grad else Dual()
+    for field, kind, prefix, bns in _dual_parts(what):
+        sub = getattr(m, field)
+        if kind == "tower":
+            (fill_tower_grad if grad else fill_tower)(sub, prefix, ptr)
+        else:
+            (fill_head_grad if grad else fill_head)(sub, (prefix, bns), ptr)
+    return m
+
+
+def dual_param_keys(what):
+    keys = []
+    for _f, kind, prefix, bns in _dual_parts(what):
+        if kind == "tower":
+            for conv, bn in _tower_keys(prefix):
+                keys.extend([conv + ".weight", conv + ".bias", bn + ".weight", bn + ".bias"])
+        else:
+            for i in range(3):
+                keys.extend([prefix + "fc%d.weight" % (i + 1), prefix + "fc%d.bias" % (i + 1)])
+            for bn in bns:
+                keys.extend([prefix + bn + ".weight", prefix + bn + ".bias"])
+    return keys
+
+
+def dual_buffer_keys(what):
+    keys = []
+    for _f, kind, prefix, bns in _dual_parts(what):
+        names = [b for _c, b in _tower_keys(prefix)] if kind == "tower" else [prefix + b for b in bns]
+        for name in names:
+            keys.extend([name + ".running_mean", name + ".running_var", name + ".num_batches_tracked"])
     return keys

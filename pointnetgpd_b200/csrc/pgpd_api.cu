@@ -6,6 +6,7 @@
 #include "head.cuh"
 #include "prep.cuh"
 #include "gpd.cuh"
+#include "dual.cuh"
 
 #include <string>
 
@@ -350,6 +351,59 @@ int pgpd_gpd_backward(const pgpd_gpd* m, const pgpd_gpd_grad* g, const float* x,
     GpdArgs a{m, x, B, C, (cudaStream_t)stream, want_tc(flags)};
     gpd_backward(a, w, *g, dlogp);
     return check_cuda("pgpd_gpd_backward");
+}
+
+// ---- the dual-cloud network (csrc/dual.cuh) ----------------------------------------------------------
+static int dual_check(int what, const pgpd_dual* m, const float* x, int B, int N, int k, const void* ws, size_t ws_bytes, size_t need) {
+    if (what != PGPD_DUAL_STN && what != PGPD_DUAL_FEAT && what != PGPD_DUAL_CLS)
+        return fail(PGPD_E_ARG, "what must be PGPD_DUAL_STN, PGPD_DUAL_FEAT or PGPD_DUAL_CLS");
+    if (!m || !x) return fail(PGPD_E_ARG, "null model or input pointer");
+    if (B < 1 || N < 1) return fail(PGPD_E_ARG, "B and N must be >= 1");
+    if (what == PGPD_DUAL_CLS && (k < 1 || k > 1024)) return fail(PGPD_E_ARG, "k must be in [1,1024]");
+    if ((long long)B * N > 0x7fffffffLL / 1024) return fail(PGPD_E_ARG, "B*N too large for this build (B*N*1024 must fit in int32)");
+    if (!ws || ((uintptr_t)ws & 255)) return fail(PGPD_E_WORKSPACE, "workspace is null or not 256-byte aligned");
+    if (ws_bytes < need) return fail(PGPD_E_WORKSPACE, "workspace too small (see pgpd_dual_workspace_bytes)");
+    return PGPD_OK;
+}
+
+size_t pgpd_dual_workspace_bytes(int what, int B, int N, int k, int flags) {
+    if (B < 1 || N < 1) return 0;
+    dual::DualWs w;
+    dual::plan_dual(nullptr, what, B, N, k < 1 ? 1 : k, (flags & PGPD_F_SAVE) != 0, w);
+    return w.bytes;
+}
+
+int pgpd_dual_forward(int what, const pgpd_dual* m, const float* x, int B, int N, int k, int flags,
+                      float* out, float* trans, void* workspace, size_t workspace_bytes, void* stream) {
+    dual::DualWs w;
+    const bool save = (flags & PGPD_F_SAVE) != 0;
+    dual::plan_dual(nullptr, what, B < 1 ? 1 : B, N < 1 ? 1 : N, k < 1 ? 1 : k, save, w);
+    int rc = dual_check(what, m, x, B, N, k, workspace, workspace_bytes, w.bytes);
+    if (rc) return rc;
+    if (!trans) return fail(PGPD_E_ARG, "trans output pointer is null");
+    if (what != PGPD_DUAL_STN && !out) return fail(PGPD_E_ARG, "out pointer is null");
+    const bool train = (flags & PGPD_F_TRAIN) != 0;
+    if (train && B == 1)
+        return fail(PGPD_E_BATCH1, "Expected more than 1 value per channel when training (BatchNorm over a batch of 1)");
+    dual::plan_dual(workspace, what, B, N, k, save, w);
+    dual::dual_forward(what, *m, x, B, N, k, train, out, trans, w, (cudaStream_t)stream);
+    return check_cuda("pgpd_dual_forward");
+}
+
+int pgpd_dual_backward(int what, const pgpd_dual* m, const pgpd_dual_grad* g, const float* x, int B, int N, int k, int flags,
+                       const float* dout, const float* dtrans, void* workspace, size_t workspace_bytes, void* stream) {
+    dual::DualWs w;
+    dual::plan_dual(nullptr, what, B < 1 ? 1 : B, N < 1 ? 1 : N, k < 1 ? 1 : k, true, w);
+    int rc = dual_check(what, m, x, B, N, k, workspace, workspace_bytes, w.bytes);
+    if (rc) return rc;
+    if (!g) return fail(PGPD_E_ARG, "null gradient struct");
+    if (!(flags & PGPD_F_TRAIN)) return fail(PGPD_E_UNSUPPORTED, "backward through eval-mode BatchNorm is not implemented");
+    if (what != PGPD_DUAL_STN && !dout) return fail(PGPD_E_ARG, "dout is null");
+    if (what == PGPD_DUAL_STN && !dtrans) return fail(PGPD_E_ARG, "dtrans is null");
+    if (B == 1) return fail(PGPD_E_BATCH1, "batch of 1 in training mode");
+    dual::plan_dual(workspace, what, B, N, k, true, w);
+    dual::dual_backward(what, *m, *g, x, B, N, k, dout, dtrans, w, (cudaStream_t)stream);
+    return check_cuda("pgpd_dual_backward");
 }
 
 // ---- data preparation in front of the model ---------------------------------------

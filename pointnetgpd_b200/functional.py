@@ -234,3 +234,111 @@ def run_module(module, what, x, k=1, flags_extra=0):
     params, bufs = gather_tensors(module, what)
     out, trans = _Fused.apply(what, bool(module.training), int(k), int(flags_extra), x, *params, *bufs)
     return out, trans
+
+
+# ---- the dual-cloud network: SimpleSTN3d / DualPointNetfeat / DualPointNetCls (pointnet.py:48-120,157-174) -> pgpd_dual_* ----------
+_DUAL_KEYS = {}
+
+
+def _dual_keys(what):
+    if what not in _DUAL_KEYS:
+        _DUAL_KEYS[what] = (tuple(A.dual_param_keys(what)), tuple(A.dual_buffer_keys(what)))
+    return _DUAL_KEYS[what]
+
+
+class _DualFn(torch.autograd.Function):
+    """forward(what, training, k, x, *params, *buffers) -> (out, trans)"""
+
+    @staticmethod
+    def forward(ctx, what, training, k, x, *tensors):
+        lib = A.load()
+        pkeys, bkeys = _dual_keys(what)
+        n_p = len(pkeys)
+        dev = x.device
+        params = [_check_tensor(t, pkeys[i], dev) for i, t in enumerate(tensors[:n_p])]
+        bufs = list(tensors[n_p:])
+        for i, b in enumerate(bufs):
+            if b is None or b.device != dev or not b.is_contiguous():
+                raise RuntimeError("pgpd: buffer %s must be a contiguous tensor on %s" % (bkeys[i], dev))
+        B, _, N = x.shape
+        need_grad = any(ctx.needs_input_grad[4:4 + n_p])
+        if ctx.needs_input_grad[3]:
+            raise NotImplementedError("pgpd: gradient w.r.t. the input points is not provided")
+        save = bool(need_grad and training)
+        flags = (A.F_TRAIN if training else 0) | (A.F_SAVE if save else 0)
+        table = dict(zip(pkeys, params))
+        table.update(zip(bkeys, bufs))
+        model = A.build_dual(lambda key: table[key].data_ptr(), what)
+        width = {A.PGPD_DUAL_CLS: k, A.PGPD_DUAL_FEAT: 1024, A.PGPD_DUAL_STN: 1}[what]
+        with _DeviceCtx(dev) as stream:
+            nbytes = lib.pgpd_dual_workspace_bytes(what, B, N, k, flags)
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            out = torch.empty((B, width), dtype=torch.float32, device=dev)
+            trans = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+            rc = lib.pgpd_dual_forward(what, C.byref(model), x.data_ptr(), B, N, k, flags, out.data_ptr(), trans.data_ptr(),
+                                       _aligned(ws), nbytes, stream)
+        A.check(lib, rc)
+        ctx.what, ctx.k, ctx.flags, ctx.saved = what, k, flags, save
+        if need_grad:
+            ctx.save_for_backward(x, ws if save else None, *params, *bufs)
+        if what == A.PGPD_DUAL_STN:
+            ctx.mark_non_differentiable(out)
+        return out, trans
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout, dtrans):
+        if not ctx.saved:
+            raise NotImplementedError("pgpd: backward through eval-mode BatchNorm is not implemented (call model.train() first)")
+        lib = A.load()
+        what, k = ctx.what, ctx.k
+        pkeys, bkeys = _dual_keys(what)
+        n_p = len(pkeys)
+        x, ws = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        params = ctx.saved_tensors[2:2 + n_p]
+        bufs = ctx.saved_tensors[2 + n_p:]
+        dev = x.device
+        B, _, N = x.shape
+        table = dict(zip(pkeys, params))
+        table.update(zip(bkeys, bufs))
+        model = A.build_dual(lambda key: table[key].data_ptr(), what)
+        grads = [torch.empty_like(p) for p in params]
+        gtable = dict(zip(pkeys, grads))
+        g = A.build_dual(lambda key: gtable[key].data_ptr(), what, grad=True)
+        with _DeviceCtx(dev) as stream:
+            if what != A.PGPD_DUAL_STN:
+                dout = torch.zeros((B, k if what == A.PGPD_DUAL_CLS else 1024), dtype=torch.float32, device=dev) if dout is None \
+                    else dout.contiguous().float()
+            if dtrans is not None:
+                dtrans = dtrans.contiguous().float()
+            elif what == A.PGPD_DUAL_STN:
+                dtrans = torch.zeros((B, 3, 3), dtype=torch.float32, device=dev)
+            rc = lib.pgpd_dual_backward(what, C.byref(model), C.byref(g), x.data_ptr(), B, N, k, ctx.flags,
+                                        dout.data_ptr() if what != A.PGPD_DUAL_STN else None,
+                                        dtrans.data_ptr() if dtrans is not None else None, _aligned(ws), ws.numel() - 256, stream)
+        A.check(lib, rc)
+        return (None, None, None, None) + tuple(grads) + (None,) * len(bufs)
+
+
+def run_dual(module, what, x, k=1):
+    """Evaluate SimpleSTN3d / DualPointNetfeat / DualPointNetCls `module` on x ([B,3,N] / [B,6,N]) through libpgpd."""
+    chans = 3 if what == A.PGPD_DUAL_STN else 6
+    if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != chans:
+        raise ValueError("expected a [B, %d, N] tensor" % chans)
+    if not x.is_cuda:
+        raise RuntimeError("pointnetgpd_b200: the dual-cloud path is CUDA-only (input is on %s); there is no CPU implementation in "
+                           "this package" % x.device)
+    if x.shape[2] != module.num_points:
+        raise ValueError("pointnetgpd_b200: got %d points per cloud but the model was built with num_points=%d "
+                         "(MaxPool1d(num_points), pointnet.py:54,99)" % (x.shape[2], module.num_points))
+    if x.dtype != torch.float32:
+        raise TypeError("pointnetgpd_b200: input must be float32")
+    x = x if x.is_contiguous() else x.contiguous()
+    pkeys, bkeys = _dual_keys(what)
+    params = [_resolve(module, key) for key in pkeys]
+    bufs = [_resolve(module, key) for key in bkeys]
+    first = {A.PGPD_DUAL_STN: ("conv1", 3), A.PGPD_DUAL_FEAT: ("conv1", 6), A.PGPD_DUAL_CLS: ("feat.conv1", 6)}[what]
+    if int(_resolve(module, first[0]).weight.shape[1]) != first[1]:
+        raise ValueError("pointnetgpd_b200: the dual-cloud network needs input_chann=6 (3 per T-Net): torch.bmm with the 3x3 transforms "
+                         "(pointnet.py:108) only works for two 3-channel halves in the reference as well")
+    return _DualFn.apply(what, bool(module.training), int(k), x, *params, *bufs)

@@ -8,15 +8,15 @@ computation to libpgpd through `pointnetgpd_b200.functional` (one C call forward
 The sub-modules (`conv1`, `bn1`, `fc1`, `mp1`, `relu`, ...) exist only as parameter containers
 with the reference's names; their own `forward` is never called.
 
-Classes that no reference script constructs (SimpleSTN3d, DualPointNetfeat, DualPointNetCls,
-PointNetDenseCls) are outside this package's scope: the names resolve so that
-`from model.pointnet import PointNetCls, DualPointNetCls` (main_1v.py:16) works, but constructing
-them raises.
+SimpleSTN3d (:48-85), DualPointNetfeat (:88-120) and DualPointNetCls (:157-174) -- imported by main_1v.py:16 but
+constructed by no reference script -- run through libpgpd's `pgpd_dual_*` entry points (fp32 CUDA-core kernels,
+csrc/dual.cuh).  PointNetDenseCls (:197-221, per-point segmentation; no script, no caller) resolves as a name and
+raises on construction.
 """
 import torch.nn as nn
 
 from .. import _abi as A
-from ..functional import run_module
+from ..functional import run_dual, run_module
 
 
 def _shared_mlp(owner, input_chann, num_points):
@@ -90,6 +90,76 @@ class PointNetCls(nn.Module):
         return run_module(self, A.PGPD_CLS, x, k=self.fc3.out_features)
 
 
+class SimpleSTN3d(nn.Module):
+    """The dual network's T-Net: [B,3,N] -> [B,3,3], tower 3->64->128->256, head 256->128->64->9  (pointnet.py:48-85)."""
+
+    def __init__(self, num_points=2500, input_chann=3):
+        super().__init__()
+        self.num_points = num_points
+        self.conv1 = nn.Conv1d(input_chann, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, 256, 1)
+        self.mp1 = nn.MaxPool1d(num_points)
+        self.fc1 = nn.Linear(256, 128)
+        self.fc2 = nn.Linear(128, 64)
+        self.fc3 = nn.Linear(64, 9)
+        self.relu = nn.ReLU()
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(256)
+        self.bn4 = nn.BatchNorm1d(128)
+        self.bn5 = nn.BatchNorm1d(64)
+
+    def forward(self, x):
+        _, trans = run_dual(self, A.PGPD_DUAL_STN, x)
+        return trans
+
+
+class DualPointNetfeat(nn.Module):
+    """Two clouds per grasp: [B,6,N] -> ([B,1024], trans1 + trans2); one SimpleSTN3d per 3-channel half, 6-channel trunk
+    (pointnet.py:88-120)."""
+
+    def __init__(self, num_points=2500, input_chann=6, global_feat=True):
+        super().__init__()
+        self.stn1 = SimpleSTN3d(num_points=num_points, input_chann=input_chann // 2)
+        self.stn2 = SimpleSTN3d(num_points=num_points, input_chann=input_chann // 2)
+        self.conv1 = nn.Conv1d(input_chann, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, 1024, 1)
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(1024)
+        self.mp1 = nn.MaxPool1d(num_points)
+        self.num_points = num_points
+        self.global_feat = global_feat
+
+    def forward(self, x):
+        if not self.global_feat:
+            raise NotImplementedError("DualPointNetfeat(global_feat=False) is used by no reference script "
+                                      "(pointnet.py:118-120) and is outside this package's scope")
+        return run_dual(self, A.PGPD_DUAL_FEAT, x)
+
+
+class DualPointNetCls(nn.Module):
+    """[B,6,N] -> (log_probs [B,k], trans1 + trans2 [B,3,3])  (pointnet.py:157-174).  Like the reference's, the default
+    input_chann=3 constructs a model whose forward cannot run (1-channel T-Nets against 3-channel slices, pointnet.py:105): pass
+    input_chann=6."""
+
+    def __init__(self, num_points=2500, input_chann=3, k=2):
+        super().__init__()
+        self.num_points = num_points
+        self.feat = DualPointNetfeat(num_points, input_chann=input_chann, global_feat=True)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, k)
+        self.bn1 = nn.BatchNorm1d(512)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        return run_dual(self, A.PGPD_DUAL_CLS, x, k=self.fc3.out_features)
+
+
 def _out_of_scope(name, where):
     def __init__(self, *args, **kwargs):
         raise NotImplementedError(
@@ -98,9 +168,6 @@ def _out_of_scope(name, where):
     return type(name, (nn.Module,), {"__init__": __init__, "__module__": __name__})
 
 
-SimpleSTN3d = _out_of_scope("SimpleSTN3d", "pointnet.py:48-85")
-DualPointNetfeat = _out_of_scope("DualPointNetfeat", "pointnet.py:88-120")
-DualPointNetCls = _out_of_scope("DualPointNetCls", "pointnet.py:157-174")
 PointNetDenseCls = _out_of_scope("PointNetDenseCls", "pointnet.py:197-221")
 
 # BASELINE.json names a 3-class variant "PointNetClsMC"; in the reference it is PointNetCls(k=3)

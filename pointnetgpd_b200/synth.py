@@ -74,13 +74,27 @@ def _layout(k):
     ]
 
 
-def state_keys(k=2):
-    """The 74 state_dict keys of the reference PointNetCls, in registration order
+def _dual_layout(k):
+    """DualPointNetCls(input_chann=6) (pointnet.py:157-174): feat.stn1 / feat.stn2 (SimpleSTN3d, :48-85), the 6-channel trunk
+    (DualPointNetfeat, :88-120) and the classifier head."""
+    def stn(p):
+        return (p, [("conv1", 64, 3, True), ("conv2", 128, 64, True), ("conv3", 256, 128, True),
+                    ("fc1", 128, 256, False), ("fc2", 64, 128, False), ("fc3", 9, 64, False)],
+                [("bn1", 64), ("bn2", 128), ("bn3", 256), ("bn4", 128), ("bn5", 64)])
+    return [stn("feat.stn1."), stn("feat.stn2."),
+            ("feat.", [("conv1", 64, 6, True), ("conv2", 128, 64, True), ("conv3", 1024, 128, True)],
+             [("bn1", 64), ("bn2", 128), ("bn3", 1024)]),
+            ("", [("fc1", 512, 1024, False), ("fc2", 256, 512, False), ("fc3", k, 256, False)],
+             [("bn1", 512), ("bn2", 256)])]
+
+
+def state_keys(k=2, dual=False):
+    """The 74 state_dict keys of the reference PointNetCls (dual: the 111 of DualPointNetCls), in registration order
     (conv/fc first, then bn, per module -- pointnet.py:11-25,126-132,181-186)."""
     keys = []
     # registration order inside each reference __init__: convs, (mp1), fcs, relu, bns
     # but nested: PointNetCls registers feat (PointNetfeat: stn (STN3d), conv*, bn*), fc*, bn*
-    for prefix, lins, bns in _layout(k):
+    for prefix, lins, bns in (_dual_layout(k) if dual else _layout(k)):
         # feat.stn.* comes before feat.conv* because stn is the first attribute set
         for name, _o, _i, _c in lins:
             keys += [prefix + name + ".weight", prefix + name + ".bias"]
@@ -90,8 +104,8 @@ def state_keys(k=2):
     return keys
 
 
-def make_state(seed, k=2, style="default", dtype=np.float32):
-    """Build a full PointNetCls state dict as numpy arrays.
+def make_state(seed, k=2, style="default", dtype=np.float32, dual=False):
+    """Build a full PointNetCls (dual: DualPointNetCls(input_chann=6)) state dict as numpy arrays.
 
     style="default": torch default-init distributions (Conv1d/Linear U(+-1/sqrt(fan_in)),
         BN gamma=1 beta=0 rm=0 rv=1)  -- pointnet.py:178-187 default constructors.
@@ -99,7 +113,7 @@ def make_state(seed, k=2, style="default", dtype=np.float32):
         (the shipped checkpoint has 143/1024 negative gammas in feat.bn3 -- SURVEY App. B).
     """
     sd = {}
-    for prefix, lins, bns in _layout(k):
+    for prefix, lins, bns in (_dual_layout(k) if dual else _layout(k)):
         for name, o, i, is_conv in lins:
             bound = 1.0 / np.sqrt(i)
             w = uniform(seed ^ _stable_hash(prefix + name + ".weight"), (o, i), -bound, bound)

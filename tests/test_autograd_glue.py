@@ -127,8 +127,14 @@ def test_product_surface_rejects_what_it_does_not_cover():
     m = PointNetCls(num_points=32, k=2)
     with pytest.raises(RuntimeError, match="CUDA-only"):
         m(torch.zeros(2, 3, 32))
+    d = DualPointNetCls(32, 6, 2)                            # constructible; same 111 state_dict keys as the reference class
+    from pointnetgpd_b200 import synth
+    assert list(d.state_dict().keys()) == synth.state_keys(2, dual=True)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        d(torch.zeros(2, 6, 32))
+    from pointnetgpd_b200.model.pointnet import PointNetDenseCls
     with pytest.raises(NotImplementedError):
-        DualPointNetCls()
+        PointNetDenseCls()
     from pointnetgpd_b200.model.gpd import GPDClassifier
     g = GPDClassifier(3)                                     # constructible (same sub-modules as the reference); CUDA-only forward
     assert list(g.state_dict().keys()) == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "fc1.weight", "fc1.bias",
