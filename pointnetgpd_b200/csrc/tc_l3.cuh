@@ -28,6 +28,11 @@
 namespace pgpd { namespace tc {
 
 constexpr int L3_NT = 256;                        // points per tile (MMA N)
+#ifdef PGPD_L3_NOROT
+#define L3_ROT(pair) 0
+#else
+#define L3_ROT(pair) (pair)
+#endif
 constexpr int L3_STAGES = 3;
 #ifndef PGPD_L3_WCOPIES
 #define PGPD_L3_WCOPIES 2
@@ -106,6 +111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 240);
     float* s_scale = reinterpret_cast<float*>(misc + 256);
     float* s_shift = s_scale + 128;
+    volatile long long* wclk = reinterpret_cast<volatile long long*>(misc + 1536);   // debug builds: issue time of the copy into each ring slot
 
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -142,11 +148,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             for (int t = T0; t < T1; ++t)
                 for (int mt4 = 0; mt4 < 4; ++mt4)
                     for (int kb = 0; kb < 2; ++kb) {
-                        const int blk = ((((mt4 + pair) & 3) * 2 + (int)rank) * 2 + kb);      // pairs walk the channel blocks in different rotations
+#if defined(PGPD_L3_SAMEBLK)      /* timing diagnostic only (wrong results): every CTA streams the same 64 KB */
+                        const int blk = (int)rank * 2 + kb;
+#else
+                        const int blk = ((((mt4 + L3_ROT(pair)) & 3) * 2 + (int)rank) * 2 + kb);      // pairs walk the channel blocks in different rotations
+#endif
                         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES;
                         for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
                             mbar_wait(BAR(W_EMPTY + stage), phase ^ 1);
                             mbar_arrive_expect_tx(BAR(W_FULL + stage), SUB_BYTES);
+                            if (p.dbg) wclk[stage] = clock64();
                             const uint32_t dst = sbase + L3C_SMEM_W + stage * SUB_BYTES;
                             if (SPLIT) {
                                 bulk_g2s(dst, src + part * SUB_BYTES, SUB_BYTES, BAR(W_FULL + stage));
@@ -177,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 int stage = 0; uint32_t wphase = 0;
                 int acc = 0; uint32_t aphase = 0;
                 int buf = 0; uint32_t bphase = 0;
-                long long w_a2 = 0, w_acc = 0, w_w = 0;
+                long long w_a2 = 0, w_acc = 0, w_w = 0, w_peer = 0, lat_sum = 0, nstall = 0, lat_max = 0;
                 const long long tl0 = p.dbg ? clock64() : 0;
                 for (int t = T0; t < T1; ++t) {
                     { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(A2_FULL + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
@@ -192,9 +203,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                             constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);      // the a2 lo part
                             auto wait_w = [&]() {
                                 const long long _t = p.dbg ? clock64() : 0;
+                                const bool stalled = p.dbg && !mbar_try_wait(BAR(W_FULL + stage), wphase);
                                 mbar_wait(BAR(W_FULL + stage), wphase);                 // my half of the weight slot
+                                const long long _t1 = p.dbg ? clock64() : 0;
                                 mbar_wait_cluster(BAR(W_FULLP + stage), wphase);        // the peer's half
-                                if (p.dbg) w_w += clock64() - _t;
+                                if (p.dbg) {
+                                    const long long _t2 = clock64();
+                                    w_w += _t1 - _t; w_peer += _t2 - _t1;
+                                    if (stalled) { const long long lat = _t1 - wclk[stage]; lat_sum += lat; ++nstall; lat_max = lat > lat_max ? lat : lat_max; }
+                                }
                                 tc_fence_after_sync();
                             };
                             auto release_w = [&]() {
@@ -236,7 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 }
                 if (p.dbg) {
                     long long* o = p.dbg + (size_t)blockIdx.x * 8;
-                    o[0] = w_a2; o[1] = w_acc; o[2] = w_w; o[3] = clock64() - tl0;
+                    o[0] = w_a2; o[1] = w_acc; o[2] = w_w; o[3] = clock64() - tl0; o[4] = w_peer; o[5] = lat_sum; o[6] = nstall; o[7] = lat_max;
                 }
             }
         }
@@ -254,7 +271,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
+                const int ch = (((mt4 + L3_ROT(pair)) & 3) * 2 + (int)rank) * 128 + row;
                 const float mu = stats ? p.mu_s[ch] : 0.f;
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
                 mbar_wait(BAR(TM_FULL + acc), aphase);
@@ -316,7 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             // four partial rows per PAIR (one per 64-column quarter); each CTA of the pair fills its 512 channels of them
 #pragma unroll
             for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
+                const int ch = (((mt4 + L3_ROT(pair)) & 3) * 2 + (int)rank) * 128 + row;
                 const float iv = p.inv[ch];
                 const float cs = mt4 == 0 ? cs0 : (mt4 == 1 ? cs1 : (mt4 == 2 ? cs2 : cs3));
                 p.css_part[((size_t)pair * L3C_EPI_ROWS + half) * C3 + ch] = cs * iv * iv;
