@@ -47,8 +47,8 @@ struct FusedParams {
     unsigned* bad;                            // [B] flags: NaN / out-of-fp16-range activation in this cloud
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tower_fused_eval(FusedParams p) {
-    constexpr int W_FULL = 0, W_FULLP = 3, W_EMPTY = 6, A1_FULL = 9, A2_FULL = 10, TM2_FULL = 11, TM2_EMPTY = 12, TM_FULL = 14, TM_EMPTY = 16;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tower_fused_eval(FusedParams p, const __grid_constant__ CUtensorMap wmap) {
+    constexpr int W_FULL = 0, W_EMPTY = 6, A1_FULL = 9, A2_FULL = 10, TM2_FULL = 11, TM2_EMPTY = 12, TM_FULL = 14, TM_EMPTY = 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -62,12 +62,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
     float* s_s2 = s_sh1 + 64;                                      // scale2 * 16 * inv2: accumulator of layer 2 -> a2 * 16
     float* s_h2 = s_s2 + 128;
 
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const int warp = (int)warp_uniform((uint32_t)tid >> 5);     // provably warp-uniform (tc_ptx.cuh: elect_one)
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_FULLP + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
         mbar_init(BAR(A1_FULL), 16); mbar_init(BAR(A2_FULL), 16);
         mbar_init(BAR(TM2_FULL), 1);
         mbar_init(BAR(TM2_EMPTY), 16); mbar_init(BAR(TM2_EMPTY + 1), 16);
@@ -91,7 +92,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
     __syncthreads();
     cluster_sync_all();                 // both CTAs' barriers and W2 halves exist before anything is signalled across
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = warp_uniform(*tmem_slot);
 
     const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
     const int T0 = (int)(((long long)p.ntiles * pair) / npairs), T1 = (int)(((long long)p.ntiles * (pair + 1)) / npairs);
@@ -104,52 +105,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                 for (int mt4 = 0; mt4 < 4; ++mt4)
                     for (int kb = 0; kb < 2; ++kb) {
                         const int blk = ((((mt4 + pair) & 3) * 2 + (int)rank) * 2 + kb);
-                        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.W3img) + (size_t)blk * L3_STAGE_BYTES;
                         mbar_wait(BAR(W_EMPTY + stage), phase ^ 1);
-                        mbar_arrive_expect_tx(BAR(W_FULL + stage), L3_STAGE_BYTES);
-                        const uint32_t dst = sbase + FZ_W + stage * L3_STAGE_BYTES;
-#pragma unroll
-                        for (int cpy = 0; cpy < L3_WCOPIES; ++cpy)
-                            bulk_g2s(dst + cpy * (L3_STAGE_BYTES / L3_WCOPIES), src + cpy * (L3_STAGE_BYTES / L3_WCOPIES),
-                                     L3_STAGE_BYTES / L3_WCOPIES, BAR(W_FULL + stage));
+                        // as in tc_l3.cuh: both CTAs' tensor-map copies complete on the LEADER's barrier
+                        if (leader) mbar_arrive_expect_tx(BAR(W_FULL + stage), 2 * L3_STAGE_BYTES);
+                        tma2d_g2s_pair_leaderbar(sbase + FZ_W + stage * L3_STAGE_BYTES, &wmap, 0, blk * 256, BAR(W_FULL + stage));
                         if (++stage == 3) { stage = 0; phase ^= 1; }
                     }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            if (!leader) {
-                // ===================== peer: relay "my weight stage has landed" to the leader =====================
-                int stage = 0; uint32_t phase = 0;
-                for (int t = T0; t < T1; ++t)
-                    for (int blk = 0; blk < 8; ++blk) {
-                        mbar_wait(BAR(W_FULL + stage), phase);
-                        mbar_arrive_cluster(BAR(W_FULLP + stage), 0u);
-                        if (++stage == 3) { stage = 0; phase ^= 1; }
-                    }
-            } else {
-                // ===================== leader: MMA issuer for the pair =====================
-                constexpr uint32_t IDESC3 = idesc_f16(256, L3_NT);
-                constexpr uint32_t IDESC2 = idesc_f16(256, 128);
-                int stage = 0; uint32_t wphase = 0;
-                uint32_t ph_e[2] = {0u, 0u}, ph_p[2] = {0u, 0u};       // next completion parity of TM_EMPTY[s] / TM2_EMPTY[s]
-                uint32_t ph_a1 = 0u, ph_a2 = 0u;
-                long long use = 0;                                     // accumulator uses so far: slot = use & 1
-                auto wait_slot = [&]() {
-                    if (use < 2) return;
-                    const int s = (int)(use & 1);
-                    if ((use - 2) % 5 == 0) { mbar_wait_cluster(BAR(TM2_EMPTY + s), ph_p[s]); ph_p[s] ^= 1u; }   // drained by the producers
-                    else { mbar_wait_cluster(BAR(TM_EMPTY + s), ph_e[s]); ph_e[s] ^= 1u; }                      // drained by the epilogue
-                    tc_fence_after_sync();
-                };
-                const uint32_t a1s = sbase + FZ_A1, w2s = sbase + FZ_W2, a2b = sbase;
-                for (int t = T0; t < T1; ++t) {
-                    // ---- layer 2 of this tile: D[256 points][128 channels] = a1 (hi, lo) x W2 (hi, lo), K = 64
-                    mbar_wait_cluster(BAR(A1_FULL), ph_a1); ph_a1 ^= 1u;
-                    tc_fence_after_sync();
-                    wait_slot();
-                    {
-                        const uint32_t d2 = tmem + (uint32_t)((use & 1) * L3_NT);
-                        const uint64_t da = desc_sw128_kmajor(a1s), db = desc_sw128_kmajor(w2s);
+        if (leader) {
+            // ===================== leader: MMA issuer for the pair (whole warp, one elected lane issues: tc_ptx.cuh) =====================
+            constexpr uint32_t IDESC3 = idesc_f16(256, L3_NT);
+            constexpr uint32_t IDESC2 = idesc_f16(256, 128);
+            constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);
+            int stage = 0; uint32_t wphase = 0;
+            uint32_t ph_e[2] = {0u, 0u}, ph_p[2] = {0u, 0u};       // next completion parity of TM_EMPTY[s] / TM2_EMPTY[s]
+            uint32_t ph_a1 = 0u, ph_a2 = 0u;
+            long long use = 0;                                     // accumulator uses so far: slot = use & 1
+            auto wait_slot = [&]() {
+                if (use < 2) return;
+                const int s = (int)(use & 1);
+                if ((use - 2) % 5 == 0) { mbar_wait_cluster(BAR(TM2_EMPTY + s), ph_p[s]); ph_p[s] ^= 1u; }   // drained by the producers
+                else { mbar_wait_cluster(BAR(TM_EMPTY + s), ph_e[s]); ph_e[s] ^= 1u; }                      // drained by the epilogue
+                tc_fence_after_sync();
+            };
+            const uint32_t a1s = sbase + FZ_A1, w2s = sbase + FZ_W2, a2b = sbase;
+            for (int t = T0; t < T1; ++t) {
+                // ---- layer 2 of this tile: D[256 points][128 channels] = a1 (hi, lo) x W2 (hi, lo), K = 64
+                mbar_wait_cluster(BAR(A1_FULL), ph_a1); ph_a1 ^= 1u;
+                tc_fence_after_sync();
+                wait_slot();
+                {
+                    const uint32_t d2 = tmem + (uint32_t)((use & 1) * L3_NT);
+                    const uint64_t da = desc_sw128_kmajor(a1s), db = desc_sw128_kmajor(w2s);
+                    if (elect_one()) {
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
                             const uint32_t oa = (pass == 1) ? 16384u : 0u;      // a1 lo
@@ -159,22 +148,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                                 mma_f16_pair(d2, da + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC2, (pass | k) ? 1u : 0u);
                         }
                         mma_commit_pair(BAR(TM2_FULL), (uint16_t)0x3);
-                        ++use;
                     }
-                    // ---- layer 3: four 256-channel blocks
-                    mbar_wait_cluster(BAR(A2_FULL), ph_a2); ph_a2 ^= 1u;
-                    tc_fence_after_sync();
-                    for (int mt4 = 0; mt4 < 4; ++mt4) {
-                        wait_slot();
-                        const int s = (int)(use & 1);
-                        const uint32_t d = tmem + (uint32_t)(s * L3_NT);
-                        for (int kb = 0; kb < 2; ++kb) {
-                            const uint64_t dbk = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
-                            constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);
-                            mbar_wait(BAR(W_FULL + stage), wphase);
-                            mbar_wait_cluster(BAR(W_FULLP + stage), wphase);
-                            tc_fence_after_sync();
-                            const uint64_t dw = desc_sw128_kmajor(sbase + FZ_W + stage * L3_STAGE_BYTES);
+                    __syncwarp();
+                    ++use;
+                }
+                // ---- layer 3: four 256-channel blocks
+                mbar_wait_cluster(BAR(A2_FULL), ph_a2); ph_a2 ^= 1u;
+                tc_fence_after_sync();
+                for (int mt4 = 0; mt4 < 4; ++mt4) {
+                    wait_slot();
+                    const int s = (int)(use & 1);
+                    const uint32_t d = tmem + (uint32_t)(s * L3_NT);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t dbk = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
+                        mbar_wait(BAR(W_FULL + stage), wphase);
+                        tc_fence_after_sync();
+                        const uint64_t dw = desc_sw128_kmajor(sbase + FZ_W + stage * L3_STAGE_BYTES);
+                        if (elect_one()) {
 #pragma unroll
                             for (int pass = 0; pass < 3; ++pass) {
                                 const uint32_t oa = (pass == 1) ? 16384u : 0u;
@@ -184,11 +174,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                                     mma_f16_pair(d, dw + ((oa + k * 32) >> 4), dbk + ((ob + k * 32) >> 4), IDESC3, (kb | pass | k) ? 1u : 0u);
                             }
                             mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);
-                            if (++stage == 3) { stage = 0; wphase ^= 1u; }
+                            if (kb == 1) mma_commit_pair(BAR(TM_FULL + s), (uint16_t)0x3);
                         }
-                        mma_commit_pair(BAR(TM_FULL + s), (uint16_t)0x3);
-                        ++use;
+                        __syncwarp();
+                        if (++stage == 3) { stage = 0; wphase ^= 1u; }
                     }
+                    ++use;
                 }
             }
         }
@@ -210,11 +201,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                 mbar_wait(BAR(TM_FULL + s), fe[s]); fe[s] ^= 1u;
                 tc_fence_after_sync();
                 float best = -INFINITY; int bidx = 0;
+                bool released = false;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * L3_NT);
                 for (int c0 = half * (L3_NT / 4); c0 < (half + 1) * (L3_NT / 4); c0 += 32) {
                     if (c0 >= nvalid) break;                // warp-uniform
                     float v[32];
                     tmem_ld32(tbase + (uint32_t)c0, v);
+                    if (c0 + 32 >= (half + 1) * (L3_NT / 4) || c0 + 32 >= nvalid) {
+                        // my last chunk is in registers: hand the accumulator back before the arithmetic on it (tc_l3.cuh)
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) { if (leader) mbar_arrive(BAR(TM_EMPTY + s)); else mbar_arrive_cluster(BAR(TM_EMPTY + s), 0u); }
+                        released = true;
+                    }
                     if (c0 + 32 <= nvalid) {
                         float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
@@ -235,10 +234,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1) k_tow
                             if (c0 + j < nvalid && v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
                     }
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) {                            // one arrival per warp on the LEADER's barrier
-                    if (leader) mbar_arrive(BAR(TM_EMPTY + s)); else mbar_arrive_cluster(BAR(TM_EMPTY + s), 0u);
+                if (!released) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) {                        // one arrival per warp on the LEADER's barrier
+                        if (leader) mbar_arrive(BAR(TM_EMPTY + s)); else mbar_arrive_cluster(BAR(TM_EMPTY + s), 0u);
+                    }
                 }
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_tc(GemmParams p) {
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     // 0,1 full (256 loader threads) | 2,3 empty (MMA commit) | 4 done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const int warp = (int)warp_uniform((uint32_t)tid >> 5);     // provably warp-uniform (tc_ptx.cuh: elect_one)
     if (tid == 0) {
         mbar_init(BAR(0), 256); mbar_init(BAR(1), 256);
         mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_tc(GemmParams p) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = warp_uniform(*tmem_slot);
 
     const int n0 = (int)blockIdx.x * GM_T, m0 = (int)blockIdx.y * GM_T;
     const int k_begin = (int)blockIdx.z * p.kslice;
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_tc(GemmParams p) {
         }
     } else if (warp == 12) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {   // the whole warp runs the loop (uniform operands), one elected lane issues: tc_ptx.cuh: elect_one
+            const bool el = elect_one();
             const uint32_t idesc = idesc_f16(GM_T, GM_T) | ((uint32_t)(p.A.mode ? 1u : 0u) << 15) | ((uint32_t)(p.B.mode ? 1u : 0u) << 16);
             const uint32_t stepA = p.A.mode ? 2048u : 32u, stepB = p.B.mode ? 2048u : 32u;
             for (int i = 0; i < nchunks; ++i) {
@@ -216,11 +218,11 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_tc(GemmParams p) {
                     const uint32_t oa = (pass == 1) ? 16384u : 0u, ob = (pass == 2) ? 16384u : 0u;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        mma_f16(tmem, da + ((oa + k * stepA) >> 4), db + ((ob + k * stepB) >> 4), idesc, (i | pass | k) ? 1u : 0u);
+                        if (el) mma_f16(tmem, da + ((oa + k * stepA) >> 4), db + ((ob + k * stepB) >> 4), idesc, (i | pass | k) ? 1u : 0u);
                 }
-                mma_commit(BAR(2 + b));
+                if (el) mma_commit(BAR(2 + b));
             }
-            mma_commit(BAR(4));
+            if (el) mma_commit(BAR(4));
         }
     } else if (warp < 4) {
         // ===================== epilogue: row m = TMEM lane =====================

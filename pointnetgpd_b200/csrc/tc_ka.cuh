@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
     // 13,14 acc_full (d a2 accumulator complete) | 15,16 acc_empty (epilogue has it in registers) | 17 final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 160);
 
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const int warp = (int)warp_uniform((uint32_t)tid >> 5);     // provably warp-uniform (tc_ptx.cuh: elect_one)
     if (tid == 0) {
         mbar_init(BAR(0), 1);
         for (int b = 0; b < KA_NBUF; ++b) { mbar_init(BAR(1 + b), 1); mbar_init(BAR(5 + b), 256); mbar_init(BAR(9 + b), 1); }
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = warp_uniform(*tmem_slot);
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             if (dbg) dbg[cta * 8 + 0] = dacc[0];
         }
     } else if (warp == 25) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (tc_ptx.cuh: elect_one) =====================
+        {
             constexpr uint32_t IDESC_K = idesc_f16(128, KA_NT);
             constexpr uint32_t IDESC_MN = idesc_f16_mn(128, 128);
             mbar_wait(BAR(0), 0);
@@ -113,34 +114,38 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
                 const uint32_t op = sbase + KA_OFF_BUF + b * KA_OP_BYTES;
                 const uint32_t d1 = tmem + (uint32_t)(acc * KA_NT);
                 const uint64_t kop = desc_sw128_kmajor(op), mop = desc_sw128_mnmajor(op, 8192);
+                if (elect_one()) {
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
+                    for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t oa = (uint32_t)((kb * 2 + (pass == 1 ? 1 : 0)) * 16384);
-                        const uint32_t ob = (uint32_t)(((pass == 2 ? 1 : 0) * 2 + kb) * 8192);
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t oa = (uint32_t)((kb * 2 + (pass == 1 ? 1 : 0)) * 16384);
+                            const uint32_t ob = (uint32_t)(((pass == 2 ? 1 : 0) * 2 + kb) * 8192);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_f16(d1, dQ + ((oa + k * 32) >> 4), kop + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)
+                                mma_f16(d1, dQ + ((oa + k * 32) >> 4), kop + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
+                        }
                     }
-                }
-                mma_commit(BAR(13 + acc));
-                // Gram: hh += a2_hi^T a2_hi,  hl += a2_hi^T a2_lo   (K = the tile's 64 points; both operands MN-major,
-                // the two 64-channel atoms of a part are 8 KB apart)
+                    mma_commit(BAR(13 + acc));
+                    // Gram: hh += a2_hi^T a2_hi,  hl += a2_hi^T a2_lo   (K = the tile's 64 points; both operands MN-major,
+                    // the two 64-channel atoms of a part are 8 KB apart)
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const uint32_t dg = tmem + 128u + (uint32_t)(pass * 128);
-                    const uint32_t ob = pass ? 16384u : 0u;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const uint32_t dg = tmem + 128u + (uint32_t)(pass * 128);
+                        const uint32_t ob = pass ? 16384u : 0u;
 #pragma unroll
-                    for (int k = 0; k < KA_NT / 16; ++k)
-                        mma_f16(dg, mop + ((k * 2048) >> 4), mop + ((ob + k * 2048) >> 4), IDESC_MN, (first && k == 0) ? 0u : 1u);
+                        for (int k = 0; k < KA_NT / 16; ++k)
+                            mma_f16(dg, mop + ((k * 2048) >> 4), mop + ((ob + k * 2048) >> 4), IDESC_MN, (first && k == 0) ? 0u : 1u);
+                    }
+                    mma_commit(BAR(9 + b));
                 }
+                __syncwarp();
                 first = 0;
-                mma_commit(BAR(9 + b));
                 if (dbg) dacc[4] += clock64() - ti0;
             }
-            mma_commit(BAR(17));
-            if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
+            if (elect_one()) mma_commit(BAR(17));
+            __syncwarp();
+            if (dbg && lane == 0) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
     } else if (warp < 16) {
         // ===================== epilogue: channel c = TMEM lane, 16 of the tile's 64 points per warp =====================

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
     float* sx = reinterpret_cast<float*>(smem + KB_OFF_X);           // [KB_NBUF][3][64]
 
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const int warp = (int)warp_uniform((uint32_t)tid >> 5);     // provably warp-uniform (tc_ptx.cuh: elect_one)
     if (tid == 0) {
         mbar_init(BAR(0), 1);
         for (int b = 0; b < KB_NBUF; ++b) { mbar_init(BAR(1 + b), 1); mbar_init(BAR(4 + b), KB_CONV_THREADS); mbar_init(BAR(7 + b), 257); }
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = warp_uniform(*tmem_slot);
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
         }
     } else if (warp == 25) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {   // the whole warp runs the loop (uniform operands), one elected lane issues: tc_ptx.cuh: elect_one
+            const bool el = elect_one();
             constexpr uint32_t IDESC_K = idesc_f16(128, KB_NT);
             constexpr uint32_t IDESC_MN = idesc_f16_mn(128, KB_NT);
             mbar_wait(BAR(0), 0);
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                         const uint32_t ob = (uint32_t)(((pass == 2 ? 1 : 0) * 2 + kb) * 8192);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_f16(d1, kA1 + ((oa + k * 32) >> 4), kdz + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
+                            if (el) mma_f16(d1, kA1 + ((oa + k * 32) >> 4), kdz + ((ob + k * 32) >> 4), IDESC_K, (kb | pass | k) ? 1u : 0u);
                     }
                 }
                 // ---- D1 += A2op x a1 (K = 64 channels)
@@ -164,9 +166,9 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                     const uint32_t oa = (pass == 1) ? (uint32_t)KB_IMG_BLOCK : 0u, ob = (pass == 2) ? 8192u : 0u;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        mma_f16(d1, kA2 + ((oa + k * 32) >> 4), ka1 + ((ob + k * 32) >> 4), IDESC_K, 1u);
+                        if (el) mma_f16(d1, kA2 + ((oa + k * 32) >> 4), ka1 + ((ob + k * 32) >> 4), IDESC_K, 1u);
                 }
-                mma_commit(BAR(10 + acc));                  // d a1 of this tile complete -> epilogue
+                if (el) mma_commit(BAR(10 + acc));                  // d a1 of this tile complete -> epilogue
                 // ---- D2 += dz^T a1 (K = 64 points, MN-major operands; A atoms = the two 64-channel blocks, 8 KB apart)
                 {
                     const uint32_t d2 = tmem + 128u;
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                         const uint32_t oa = (pass == 1) ? 16384u : 0u, ob = (pass == 2) ? 8192u : 0u;
 #pragma unroll
                         for (int k = 0; k < KB_NT / 16; ++k)
-                            mma_f16(d2, mdz + ((oa + k * 2048) >> 4), ma1 + ((ob + k * 2048) >> 4), IDESC_MN,
+                            if (el) mma_f16(d2, mdz + ((oa + k * 2048) >> 4), ma1 + ((ob + k * 2048) >> 4), IDESC_MN,
                                     (first && pass == 0 && k == 0) ? 0u : 1u);
                     }
                 }
@@ -187,15 +189,15 @@ __global__ void __launch_bounds__(KB_THREADS, 1) k_kb_tc(KbParams p) {
                         const uint32_t ob = pass ? 8192u : 0u;
 #pragma unroll
                         for (int k = 0; k < KB_NT / 16; ++k)
-                            mma_f16(d3, ma1 + ((k * 2048) >> 4), ma1 + ((ob + k * 2048) >> 4), IDESC_MN,
+                            if (el) mma_f16(d3, ma1 + ((k * 2048) >> 4), ma1 + ((ob + k * 2048) >> 4), IDESC_MN,
                                     (first && pass == 0 && k == 0) ? 0u : 1u);
                     }
                 }
                 first = 0;
-                mma_commit(BAR(7 + b));                     // the tensor core is done reading this buffer
+                if (el) mma_commit(BAR(7 + b));                     // the tensor core is done reading this buffer
                 if (dbg) dacc[4] += clock64() - ti0;
             }
-            mma_commit(BAR(14));
+            if (el) mma_commit(BAR(14));
             if (dbg) { dbg[cta * 8 + 3] = dacc[3]; dbg[cta * 8 + 4] = dacc[4]; }
         }
     } else if (warp < 16 && (warp & 3) < 2) {

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
     // 0 w_full | 1..4 full | 5..8 op_ready | 9..12 buf_empty (MMAs done reading) | 13,14 acc_full | 15,16 acc_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 256);
 
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const int warp = (int)warp_uniform((uint32_t)tid >> 5);     // provably warp-uniform (tc_ptx.cuh: elect_one)
     if (tid == 0) {
         mbar_init(BAR(0), 1);
         for (int b = 0; b < KF_NBUF; ++b) { mbar_init(BAR(1 + b), 1); mbar_init(BAR(5 + b), KF_CONV_THREADS); mbar_init(BAR(9 + b), 1); }
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = warp_uniform(*tmem_slot);
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int t_begin = (int)(((long long)p.ntiles * cta) / G), t_end = (int)(((long long)p.ntiles * (cta + 1)) / G);
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
         }
     } else if (warp == KF_WARP_MMA) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {   // the whole warp runs the loop (uniform operands), one elected lane issues: tc_ptx.cuh: elect_one
+            const bool el = elect_one();
             constexpr uint32_t IDESC = idesc_f16(128, KF_NT);
             mbar_wait(BAR(0), 0);
             tc_fence_after_sync();
@@ -97,10 +99,10 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k_kf_tc(KfParams p) {
                     const uint32_t wb = (pass == 2) ? op + 8192 : op;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC, (pass | k) ? 1u : 0u);
+                        if (el) mma_f16(d, desc_sw128_kmajor(wa + k * 32), desc_sw128_kmajor(wb + k * 32), IDESC, (pass | k) ? 1u : 0u);
                 }
-                mma_commit(BAR(9 + b));
-                mma_commit(BAR(13 + acc));
+                if (el) mma_commit(BAR(9 + b));
+                if (el) mma_commit(BAR(13 + acc));
             }
         }
     } else if (warp < 8) {

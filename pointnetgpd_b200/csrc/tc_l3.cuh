@@ -14,30 +14,50 @@
 // Orientation: channels on the MMA M axis (TMEM lanes), points on N (columns): the max / sum over
 // points is then a per-thread serial reduction over the columns each epilogue thread loads.
 //
-// CTA = 10 warps, persistent over tiles of 256 points:
-//   warp 0    W3 producer: bulk-copies 32 KB stages (one 128-channel x 64-k block, hi+lo) of the
-//             pre-swizzled weight image from L2 into a 3-deep ring;
-//   warp 1    MMA issuer (one thread): per 128-channel block, 2 k-blocks x 3 passes x 4 MMAs of
-//             128 x 256 x 16 into one of two 256-column TMEM accumulators;
-//   warps 2-5 epilogue: tcgen05.ld the accumulator, max / arg-max / centred squares per channel;
-//   warps 6-9 a2 producer: u2 tile -> BN2+ReLU -> hi/lo fp16 -> swizzled shared memory.
+// CTA PAIRS (cta_group::2), 26 warps per CTA, persistent over tiles of 256 points (128 per CTA):
+//   warp 0      W3 producer: tensor-map (TMA) copies of 32 KB stages (this CTA's 128 channels x 64 k, hi+lo) of the pre-swizzled
+//               weight image from L2 into a 3-deep ring; both CTAs' copies complete on the leader's barrier;
+//   warp 1      MMA issuer of the leader CTA (whole warp runs the loop, one elected lane issues: tc_ptx.cuh): per 256-channel
+//               block 2 k-blocks x 3 passes x 4 MMAs of 256 x 256 x 16 into one of two 256-column TMEM accumulators;
+//   warps 2-17  epilogue: tcgen05.ld the accumulator, max / arg-max / centred squares per channel;
+//   warps 18-25 a2 producers: u2 tile -> BN2+ReLU -> hi/lo fp16 -> swizzled shared memory (double-buffered).
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace pgpd { namespace tc {
 
+// Tensor map over a pre-swizzled operand image seen as rows of 128 bytes: box = 256 rows = one 32 KB weight stage (hi + lo of a
+// 128-channel x 64-k block).  Encoding is a host-side computation (no allocation, no synchronisation); the driver entry point is
+// looked up once through the runtime, so the library has no link-time dependency on libcuda.
+inline PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+        else cudaGetLastError();
+    }
+    return enc;
+}
+inline bool make_image_map(CUtensorMap* m, const void* img, size_t bytes) {
+    const PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 128)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {128, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(img), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 constexpr int L3_NT = 256;                        // points per tile (MMA N)
-#ifdef PGPD_L3_NOROT
-#define L3_ROT(pair) 0
-#else
-#define L3_ROT(pair) (pair)
-#endif
 constexpr int L3_STAGES = 3;
-#ifndef PGPD_L3_WCOPIES
-#define PGPD_L3_WCOPIES 2
-#endif
-constexpr int L3_WCOPIES = PGPD_L3_WCOPIES;      // bulk copies per 32 KB weight stage
 constexpr int L3_STAGE_BYTES = 2 * 128 * 128;     // hi + lo, 128 rows x 128 B
 constexpr int L3_A2_PART = L3_NT * 128;           // one (part,kblock) sub-tile: 256 rows x 128 B = 32 KB
 constexpr int L3_A2_BYTES = 4 * L3_A2_PART;       // hi/lo x 2 k-blocks = 128 KB
@@ -72,15 +92,20 @@ struct L3Params {
 };
 
 // ====================================================================================================================
-// Version 3: CTA PAIRS with cta_group::2 MMAs (M = 256 channels x N = 256 points per instruction).
+// CTA PAIRS with cta_group::2 MMAs (M = 256 channels x N = 256 points per instruction).
 //   * each CTA of a pair holds HALF of the W3 block of a stage (its 128 of the 256 channels: 32 KB) and HALF of the a2
-//     operand tile (its 128 of the pair's 256 points: 64 KB): the W3 stream per SM is halved (the layer's L2->SM traffic
-//     per point drops from 2.5 KB to 1.25 KB) and the a2 operand fits twice, so staging the next tile overlaps the MMAs of
-//     the current one (version 1 is single-buffered: ~9 k of its ~38 k cycles per tile are exposed staging);
+//     operand tile (its 128 of the pair's 256 points: 64 KB): the W3 stream per SM is halved and the a2 operand fits twice,
+//     so staging the next tile overlaps the MMAs of the current one;
 //   * the leader CTA (cluster rank 0) issues every MMA; tcgen05.commit arrives on BOTH CTAs' barriers (multicast);
-//     barriers the leader waits on that depend on the peer (operand tile staged, weight stage landed, accumulator
-//     drained) receive the peer's arrivals through DSMEM (mapa + mbarrier.arrive.release.cluster);
-//   * each CTA's epilogue drains its own 128 channels x 256 points from its own TMEM; everything else as in version 1.
+//     barriers the leader waits on that depend on the peer (operand tile staged, accumulator drained) receive the peer's
+//     arrivals through DSMEM (mapa + mbarrier.arrive.release.cluster); the weight stages need no relay: the peer's TMA copy
+//     signals the leader's barrier directly (.cta_group::2);
+//   * each CTA's epilogue drains its own 128 channels x 256 points from its own TMEM and hands the accumulator back as soon
+//     as its last tcgen05.ld has landed, before the arithmetic.
+// What round 2's measurements say about this kernel (profiles/r2/README.md, "layer-3 kernel: what bounds it"): the weight ring
+// never runs dry (the issuing thread's "wait" cycles were MMA-queue back-pressure); knocking out the accumulator drain saves 21 %,
+// the operand staging 5 %, the weight stream 0 %; and issuing the MMAs under `if (lane == 0)` made every tcgen05.mma cost ~130
+// cycles of issue (per-instruction R2UR waterfall) -- as long as its own 128.6 cycles of execution.
 // ====================================================================================================================
 constexpr int L3C_NH = 128;                        // points staged per CTA (half of the pair's tile)
 constexpr int L3C_A2_PART = L3C_NH * 128;          // 16 KB: one (part, k-block) sub-tile
@@ -88,43 +113,47 @@ constexpr int L3C_A2_BUF = 4 * L3C_A2_PART;        // 64 KB
 constexpr int L3C_SMEM_W = 2 * L3C_A2_BUF;         // 128 KB
 constexpr int L3C_SMEM_MISC = L3C_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3C_SMEM_BYTES = L3C_SMEM_MISC + 2048 + 1024;
-constexpr int L3C_THREADS = 832;                   // W producer, MMA issuer / relay, 16 epilogue, 8 a2 producer warps
+constexpr int L3C_THREADS = 832;                   // W producer, MMA issuer, 16 epilogue, 8 a2 producer warps
 constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred squares per tile (one per 64-column quarter)
 
-// SPLIT: the weight ring is managed in 16 KB sub-stages (the hi and the lo half of a stage separately) and the passes
-// run in the order hi.hi, hi.lo, lo.hi, so that the hi half is released after 8 of a stage's 12 MMAs and its refill
-// starts ~0.5 k cycles earlier -- the 3-stage ring otherwise runs dry (profiles/README.md).
-template <bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p) {
-    constexpr int NSUB = SPLIT ? 6 : 3;                    // ring slots
-    constexpr int SUB_BYTES = SPLIT ? L3_STAGE_BYTES / 2 : L3_STAGE_BYTES;
-    constexpr int W_FULL = 0, W_FULLP = 6, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 24;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p, const __grid_constant__ CUtensorMap wmap) {
+    constexpr int NSUB = L3_STAGES;                        // ring slots
+    constexpr int SUB_BYTES = L3_STAGE_BYTES;
+#ifdef PGPD_L3_ACC4
+    constexpr int W_FULL = 0, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 26;   // four accumulators
+#else
+    constexpr int W_FULL = 0, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 24;
+#endif
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     unsigned char* misc = smem + L3C_SMEM_MISC;
     const uint32_t bar0 = sbase + L3C_SMEM_MISC;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // W_FULL.. w_full (local bulk copies) | W_FULLP.. (leader: the peer's slot landed) | W_EMPTY.. (commit, both CTAs)
+    // W_FULL.. (leader: both CTAs' tensor-map copies of a weight stage have landed) | W_EMPTY.. (commit, both CTAs)
     // A2_FULL (leader: 16 producer warps of both CTAs) | A2_EMPTY (commit, both) | TM_FULL (commit, both)
     // TM_EMPTY (leader: 2 x 16 epilogue warps of both CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 240);
     float* s_scale = reinterpret_cast<float*>(misc + 256);
     float* s_shift = s_scale + 128;
-    volatile long long* wclk = reinterpret_cast<volatile long long*>(misc + 1536);   // debug builds: issue time of the copy into each ring slot
 
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const int warp = (int)warp_uniform((uint32_t)tid >> 5);     // provably warp-uniform: role dispatch without divergence
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     long long gt0 = 0, ck0 = 0;
     if (p.dbg && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
 
     if (tid == 0) {
-        for (int i = 0; i < NSUB; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_FULLP + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
+        for (int i = 0; i < NSUB; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
         mbar_init(BAR(A2_FULL), 16); mbar_init(BAR(A2_FULL + 1), 16);
         mbar_init(BAR(A2_EMPTY), 1); mbar_init(BAR(A2_EMPTY + 1), 1);
+#ifdef PGPD_L3_ACC4
+        for (int i = 0; i < 4; ++i) { mbar_init(BAR(TM_FULL + i), 1); mbar_init(BAR(TM_EMPTY + i), 32); }
+#else
         mbar_init(BAR(TM_FULL), 1); mbar_init(BAR(TM_FULL + 1), 1);
         mbar_init(BAR(TM_EMPTY), 32); mbar_init(BAR(TM_EMPTY + 1), 32);
+#endif
         mbar_fence_init();
     }
     if (tid < 128) {
@@ -135,7 +164,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
     __syncthreads();
     cluster_sync_all();                 // both CTAs' barriers exist before anything is signalled across
     tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = warp_uniform(*tmem_slot);
 
     // tiles of this PAIR (256 points each); both CTAs walk the same tiles
     const int npairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
@@ -148,113 +177,110 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             for (int t = T0; t < T1; ++t)
                 for (int mt4 = 0; mt4 < 4; ++mt4)
                     for (int kb = 0; kb < 2; ++kb) {
-#if defined(PGPD_L3_SAMEBLK)      /* timing diagnostic only (wrong results): every CTA streams the same 64 KB */
-                        const int blk = (int)rank * 2 + kb;
-#else
-                        const int blk = ((((mt4 + L3_ROT(pair)) & 3) * 2 + (int)rank) * 2 + kb);      // pairs walk the channel blocks in different rotations
-#endif
-                        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Wimg) + (size_t)blk * L3_STAGE_BYTES;
-                        for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
-                            mbar_wait(BAR(W_EMPTY + stage), phase ^ 1);
-                            mbar_arrive_expect_tx(BAR(W_FULL + stage), SUB_BYTES);
-                            if (p.dbg) wclk[stage] = clock64();
-                            const uint32_t dst = sbase + L3C_SMEM_W + stage * SUB_BYTES;
-                            if (SPLIT) {
-                                bulk_g2s(dst, src + part * SUB_BYTES, SUB_BYTES, BAR(W_FULL + stage));
-                            } else {
-#pragma unroll
-                                for (int cpy = 0; cpy < L3_WCOPIES; ++cpy)
-                                    bulk_g2s(dst + cpy * (L3_STAGE_BYTES / L3_WCOPIES), src + cpy * (L3_STAGE_BYTES / L3_WCOPIES),
-                                             L3_STAGE_BYTES / L3_WCOPIES, BAR(W_FULL + stage));
-                            }
-                            if (++stage == NSUB) { stage = 0; phase ^= 1; }
-                        }
+                        const int blk = ((((mt4 + pair) & 3) * 2 + (int)rank) * 2 + kb);      // pairs walk the channel blocks in different rotations
+                        mbar_wait(BAR(W_EMPTY + stage), phase ^ 1);
+                        // tensor-map copy of my 32 KB half of the stage; BOTH CTAs' copies complete on the LEADER's barrier, which
+                        // expects the whole 64 KB: the MMA issuer waits on one local barrier, nothing is relayed through the peer
+                        // (round 1 / early round 2: plain bulk copies + a relay thread in the peer: +4 % kernel time)
+                        if (leader) mbar_arrive_expect_tx(BAR(W_FULL + stage), 2 * SUB_BYTES);
+                        tma2d_g2s_pair_leaderbar(sbase + L3C_SMEM_W + stage * SUB_BYTES, &wmap, 0, blk * 256, BAR(W_FULL + stage));
+                        if (++stage == NSUB) { stage = 0; phase ^= 1; }
                     }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            if (!leader) {
-                // ===================== peer: relay "my weight stage has landed" to the leader =====================
-                int stage = 0; uint32_t phase = 0;
-                for (int t = T0; t < T1; ++t)
-                    for (int blk = 0; blk < (SPLIT ? 16 : 8); ++blk) {
-                        mbar_wait(BAR(W_FULL + stage), phase);
-                        mbar_arrive_cluster(BAR(W_FULLP + stage), 0u);
-                        if (++stage == NSUB) { stage = 0; phase ^= 1; }
-                    }
-            } else {
-                // ===================== leader: MMA issuer for the pair =====================
-                constexpr uint32_t IDESC = idesc_f16(256, L3_NT);
-                int stage = 0; uint32_t wphase = 0;
-                int acc = 0; uint32_t aphase = 0;
-                int buf = 0; uint32_t bphase = 0;
-                long long w_a2 = 0, w_acc = 0, w_w = 0, w_peer = 0, lat_sum = 0, nstall = 0, lat_max = 0;
-                const long long tl0 = p.dbg ? clock64() : 0;
-                for (int t = T0; t < T1; ++t) {
-                    { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(A2_FULL + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
-                    tc_fence_after_sync();
-                    const uint32_t a2b = sbase + buf * L3C_A2_BUF;
-                    for (int mt4 = 0; mt4 < 4; ++mt4) {
-                        { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(TM_EMPTY + acc), aphase ^ 1); if (p.dbg) w_acc += clock64() - _t; }   // drained
+        if (leader) {
+            // ===================== leader: MMA issuer for the pair (WHOLE WARP, one elected lane issues; tc_ptx.cuh: elect_one) =====
+            // (Measured and dropped, profiles/r2/README.md: testing the next stage's barriers one unit ahead, a 16 KB sub-stage ring,
+            // four 128-column accumulators -- twice the MMA instructions.)
+            constexpr uint32_t IDESC = idesc_f16(256, L3_NT);
+            constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);      // the a2 lo part
+            int stage = 0; uint32_t wphase = 0;
+            int acc = 0; uint32_t aphase = 0;
+            int buf = 0; uint32_t bphase = 0;
+            long long w_a2 = 0, w_acc = 0, w_w = 0;
+            const long long tl0 = p.dbg ? clock64() : 0;
+#ifdef PGPD_L3_ACC4
+            // FOUR accumulators of 128 columns: block b of a tile accumulates its two point halves h = 0, 1 into accumulators
+            // 2*(b&1) + h with MMAs of 256 channels x 128 points; per weight stage the two halves are issued back to back (the weight
+            // ring behaves as with 256-column MMAs), but an accumulator is needed again 1.25 block times after it completes instead
+            // of one block time minus the drain.
+            constexpr uint32_t IDESC4 = idesc_f16(256, 128);
+            int nb = 0;
+            for (int t = T0; t < T1; ++t) {
+                mbar_wait_cluster(BAR(A2_FULL + buf), bphase);
+                tc_fence_after_sync();
+                const uint32_t a2b = sbase + buf * L3C_A2_BUF;
+                for (int mt4 = 0; mt4 < 4; ++mt4, ++nb) {
+                    const int accb = (nb & 1) * 2;
+                    const uint32_t aph4 = (uint32_t)(nb >> 1) & 1u;
+                    for (int kb = 0; kb < 2; ++kb) {
+                        mbar_wait(BAR(W_FULL + stage), wphase);
+                        if (kb == 0) { mbar_wait_cluster(BAR(TM_EMPTY + accb), aph4 ^ 1u); mbar_wait_cluster(BAR(TM_EMPTY + accb + 1), aph4 ^ 1u); }
                         tc_fence_after_sync();
-                        const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
-                        for (int kb = 0; kb < 2; ++kb) {
-                            const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
-                            constexpr uint32_t OB_LO = (uint32_t)(2 * L3C_A2_PART);      // the a2 lo part
-                            auto wait_w = [&]() {
-                                const long long _t = p.dbg ? clock64() : 0;
-                                const bool stalled = p.dbg && !mbar_try_wait(BAR(W_FULL + stage), wphase);
-                                mbar_wait(BAR(W_FULL + stage), wphase);                 // my half of the weight slot
-                                const long long _t1 = p.dbg ? clock64() : 0;
-                                mbar_wait_cluster(BAR(W_FULLP + stage), wphase);        // the peer's half
-                                if (p.dbg) {
-                                    const long long _t2 = clock64();
-                                    w_w += _t1 - _t; w_peer += _t2 - _t1;
-                                    if (stalled) { const long long lat = _t1 - wclk[stage]; lat_sum += lat; ++nstall; lat_max = lat > lat_max ? lat : lat_max; }
-                                }
-                                tc_fence_after_sync();
-                            };
-                            auto release_w = [&]() {
-                                mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);   // slot free in both CTAs
-                                if (++stage == NSUB) { stage = 0; wphase ^= 1; }
-                            };
-                            if (SPLIT) {
-                                wait_w();                                               // W hi
-                                const uint64_t dwh = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * SUB_BYTES);
+                        const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES);
+                        if (elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) mma_f16_pair(d, dwh + ((k * 32) >> 4), db + ((k * 32) >> 4), IDESC, (kb | k) ? 1u : 0u);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) mma_f16_pair(d, dwh + ((k * 32) >> 4), db + ((OB_LO + k * 32) >> 4), IDESC, 1u);
-                                release_w();
-                                wait_w();                                               // W lo
-                                const uint64_t dwl = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * SUB_BYTES);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) mma_f16_pair(d, dwl + ((k * 32) >> 4), db + ((k * 32) >> 4), IDESC, 1u);
-                                release_w();
-                            } else {
-                                wait_w();
-                                const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * SUB_BYTES);
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t d = tmem + (uint32_t)((accb + h) * 128);
+                                const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART + h * 8192);   // my 64 rows of this half
 #pragma unroll
                                 for (int pass = 0; pass < 3; ++pass) {
                                     const uint32_t oa = (pass == 1) ? 16384u : 0u;
                                     const uint32_t ob = (pass == 2) ? OB_LO : 0u;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC, (kb | pass | k) ? 1u : 0u);
+                                        mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC4, (kb | pass | k) ? 1u : 0u);
                                 }
-                                release_w();
+                                if (kb == 1) mma_commit_pair(BAR(TM_FULL + accb + h), (uint16_t)0x3);   // this half is complete in both CTAs
                             }
+                            mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);
+                            if (kb == 1 && mt4 == 3) mma_commit_pair(BAR(A2_EMPTY + buf), (uint16_t)0x3);
                         }
-                        mma_commit_pair(BAR(TM_FULL + acc), (uint16_t)0x3);        // accumulator complete in both CTAs
-                        if (++acc == 2) { acc = 0; aphase ^= 1; }
+                        __syncwarp();
+                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1u; }
                     }
-                    mma_commit_pair(BAR(A2_EMPTY + buf), (uint16_t)0x3);        // operand buffer free in both CTAs
-                    if (++buf == 2) { buf = 0; bphase ^= 1; }
                 }
-                if (p.dbg) {
-                    long long* o = p.dbg + (size_t)blockIdx.x * 8;
-                    o[0] = w_a2; o[1] = w_acc; o[2] = w_w; o[3] = clock64() - tl0; o[4] = w_peer; o[5] = lat_sum; o[6] = nstall; o[7] = lat_max;
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+            (void)acc; (void)aphase; (void)IDESC; (void)w_a2; (void)w_acc; (void)w_w;
+#else
+            for (int t = T0; t < T1; ++t) {
+                { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(A2_FULL + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
+                tc_fence_after_sync();
+                const uint32_t a2b = sbase + buf * L3C_A2_BUF;
+                for (int mt4 = 0; mt4 < 4; ++mt4) {
+                    { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(TM_EMPTY + acc), aphase ^ 1); if (p.dbg) w_acc += clock64() - _t; }   // drained
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem + (uint32_t)(acc * L3_NT);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART);
+                        { const long long _t = p.dbg ? clock64() : 0; mbar_wait(BAR(W_FULL + stage), wphase); if (p.dbg) w_w += clock64() - _t; }   // weight slot (both halves)
+                        tc_fence_after_sync();
+                        const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int pass = 0; pass < 3; ++pass) {
+                                const uint32_t oa = (pass == 1) ? 16384u : 0u;
+                                const uint32_t ob = (pass == 2) ? OB_LO : 0u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC, (kb | pass | k) ? 1u : 0u);
+                            }
+                            mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);      // slot free in both CTAs
+                            if (kb == 1) mma_commit_pair(BAR(TM_FULL + acc), (uint16_t)0x3);                 // accumulator complete in both CTAs
+                            if (kb == 1 && mt4 == 3) mma_commit_pair(BAR(A2_EMPTY + buf), (uint16_t)0x3);   // operand buffer free in both CTAs
+                        }
+                        __syncwarp();
+                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1u; }
+                    }
+                    if (++acc == 2) { acc = 0; aphase ^= 1; }
                 }
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+#endif
+            if (p.dbg && lane == 0) {
+                long long* o = p.dbg + (size_t)blockIdx.x * 8;
+                o[0] = w_a2; o[1] = w_acc; o[2] = w_w; o[3] = clock64() - tl0; o[4] = 0; o[5] = 0; o[6] = 0; o[7] = 0;
             }
         }
     } else if (warp < 18) {
@@ -265,24 +291,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         const int row = q * 32 + lane;
         const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
+        int nb = 0;                                         // blocks so far (PGPD_L3_ACC4)
+        (void)acc; (void)aphase; (void)nb;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;      // centred squares of my channel of block mt4 = 0..3, summed over my tiles
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
             const int n0 = tt * L3_NT;
             const int nvalid = (p.N - n0 < L3_NT) ? p.N - n0 : L3_NT;
             for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int ch = (((mt4 + L3_ROT(pair)) & 3) * 2 + (int)rank) * 128 + row;
+                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
                 const float mu = stats ? p.mu_s[ch] : 0.f;
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
-                mbar_wait(BAR(TM_FULL + acc), aphase);
-                tc_fence_after_sync();
                 float best = -INFINITY; int bidx = 0; float css = 0.f;
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT);
-                for (int c0 = half * (L3_NT / 4); c0 < (half + 1) * (L3_NT / 4); c0 += 32) {
-                    if (c0 >= nvalid) break;                // warp-uniform
+                // my two chunks of 32 columns (points half*64 + u*32 of the tile) of this block's accumulator
+                bool released = false;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+#ifdef PGPD_L3_ACC4
+                    // one chunk in each of the block's two accumulators (u = point half); accumulator columns 0-63 are the leader
+                    // CTA's 64 points of the half, 64-127 the peer's
+                    const int a = ((nb & 1) << 1) + u;
+                    const uint32_t aph = (uint32_t)(nb >> 1) & 1u;
+                    const bool first = true, last = true;
+                    const uint32_t col = (uint32_t)(a * 128 + half * 32);
+                    const int pb = (half >> 1) * 128 + u * 64 + (half & 1) * 32;
+                    released = false;
+#else
+                    const int a = acc;
+                    const uint32_t aph = aphase;
+                    const bool first = u == 0, last = u == 1;
+                    const uint32_t col = (uint32_t)(acc * L3_NT + half * 64 + u * 32);
+                    const int pb = half * 64 + u * 32;
+#endif
+                    if (first) { mbar_wait(BAR(TM_FULL + a), aph); tc_fence_after_sync(); }
+                    const bool any = pb < nvalid;           // warp-uniform
                     float v[32];
-                    tmem_ld32(tbase + (uint32_t)c0, v);
-                    if (c0 + 32 <= nvalid) {
+                    if (any) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + col, v);
+                    if (!released && (last || pb + 32 >= nvalid)) {
+                        // everything I need of this accumulator is in registers: hand it back BEFORE the arithmetic (drain time and MMA
+                        // time per block are nearly equal: every cycle between the last tcgen05.ld and this arrival is on the critical path)
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) { if (leader) mbar_arrive(BAR(TM_EMPTY + a)); else mbar_arrive_cluster(BAR(TM_EMPTY + a), 0u); }
+                        released = true;
+                    }
+                    if (!any) continue;
+                    if (pb + 32 <= nvalid) {
                         float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
                         for (int j = 4; j < 32; j += 4) {
@@ -305,24 +359,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                             int jj = 31;
 #pragma unroll
                             for (int j = 30; j >= 0; --j) if (v[j] == m) jj = j;
-                            bidx = n0 + c0 + jj;
+                            bidx = n0 + pb + jj;
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            if (c0 + j < nvalid) {
+                            if (pb + j < nvalid) {
                                 if (stats) { const float dlt = v[j] - mu; css = fmaf(dlt, dlt, css); }
-                                if (v[j] > best) { best = v[j]; bidx = n0 + c0 + j; }
+                                if (v[j] > best) { best = v[j]; bidx = n0 + pb + j; }
                             }
                         }
                     }
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) {                            // one arrival per warp on the LEADER's barrier
-                    if (leader) mbar_arrive(BAR(TM_EMPTY + acc)); else mbar_arrive_cluster(BAR(TM_EMPTY + acc), 0u);
-                }
+#ifdef PGPD_L3_ACC4
+                ++nb;
+#else
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
+#endif
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
                 atomicMax(&p.keys[(size_t)b * C3 + ch], key);
@@ -333,7 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             // four partial rows per PAIR (one per 64-column quarter); each CTA of the pair fills its 512 channels of them
 #pragma unroll
             for (int mt4 = 0; mt4 < 4; ++mt4) {
-                const int ch = (((mt4 + L3_ROT(pair)) & 3) * 2 + (int)rank) * 128 + row;
+                const int ch = (((mt4 + pair) & 3) * 2 + (int)rank) * 128 + row;
                 const float iv = p.inv[ch];
                 const float cs = mt4 == 0 ? cs0 : (mt4 == 1 ? cs1 : (mt4 == 2 ? cs2 : cs3));
                 p.css_part[((size_t)pair * L3C_EPI_ROWS + half) * C3 + ch] = cs * iv * iv;
@@ -452,8 +505,8 @@ inline DevInfo& dev_info() {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         if (d.sms <= 0) d.sms = 148;
         if (d.sms > 256) d.sms = 256;      // per-CTA partial buffers are sized for <= 256 CTAs (plan_tower_scratch)
-        cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
-        d.state = (major == 10 && e == cudaSuccess) ? 1 : -1;
+        cudaError_t e = cudaFuncSetAttribute(k_l3_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, L3C_SMEM_BYTES);
+        d.state = (major == 10 && e == cudaSuccess && tensor_map_encoder() != nullptr) ? 1 : -1;   // the weight stream needs the driver's tensor-map encoder
         if (e != cudaSuccess) cudaGetLastError();
     }
     return d;

@@ -103,6 +103,30 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     __trap();
 }
 
+// ---- warp-uniform single-thread issue --------------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / TMA take their operands from UNIFORM registers.  Issued under `if (lane == 0)` the operands live in
+// per-thread registers and the compiler wraps EVERY instruction in an elect / R2UR.BROADCAST x5 / branch "waterfall" (~130 cycles per
+// MMA, measured: the issuing thread, not the tensor pipe, then paces the kernel).  Issued from warp-uniform code -- the whole warp
+// runs the loop, operands are computed by all lanes from provably uniform values, one elected lane executes the instruction -- they
+// are formed directly in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// a value every lane holds, made provably uniform for the compiler (warp index, a TMEM base address read from shared memory)
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// ---- tensor-map (TMA) copy for CTA pairs ------------------------------------------------------------------------------------
+// 2-D box of a tensor map -> THIS CTA's shared memory; the complete_tx goes to the mbarrier at local offset `bar` of the pair's
+// LEADER CTA (rank 0), whichever CTA issues the copy (.cta_group::2 allows the barrier to live in the peer CTA): the MMA issuer
+// then waits on ONE barrier for both halves of a weight stage, with no relay through the peer.
+__device__ __forceinline__ void tma2d_g2s_pair_leaderbar(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("{\n\t.reg .b32 rb;\n\tmapa.shared::cluster.u32 rb, %4, 0;\n\t"
+                 "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [rb];\n\t}"
+                 :: "r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
 // pull [src, src+bytes) into L2 ahead of use (bytes multiple of 16, src 16-byte aligned); no completion tracking
 __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");

@@ -626,8 +626,10 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
                           w.bn[1].scale, w.bn[1].shift, (const __half*)w.wimg, w.sgn, w.keys, a.B, a.N, tpc, ntiles, w.bad};
         const int sms = tc::dev_info().sms;
         const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
+        CUtensorMap wmap;
+        tc::make_image_map(&wmap, w.wimg, tc::L3_WIMG_BYTES);      // host-side encoding of the weight image's tensor map (no driver call that allocates or synchronises)
         profiler().begin(s);
-        launch(tc::k_tower_fused_eval, dim3(2 * pairs), dim3(tc::FZ_THREADS), (size_t)tc::FZ_SMEM_BYTES, s, p);
+        launch(tc::k_tower_fused_eval, dim3(2 * pairs), dim3(tc::FZ_THREADS), (size_t)tc::FZ_SMEM_BYTES, s, p, wmap);
         profiler().end(s);
         TailL3Params q{};
         q.B = a.B; q.relu_last = a.relu_last ? 1 : 0; q.train = 0;
@@ -700,8 +702,10 @@ inline void tower_forward(const TowerArgs& a, TowerWs& w, float* pooled) {
                        l3_pilot ? w.s1part : (float*)nullptr, w.bad};
         const int sms = tc::dev_info().sms;
         const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
+        CUtensorMap wmap;
+        tc::make_image_map(&wmap, w.wimg, tc::L3_WIMG_BYTES);      // host-side encoding of the weight image's tensor map (no driver call that allocates or synchronises)
         profiler().begin(s);
-        launch(tc::k_l3_fwd_tc3<false>, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p);
+        launch(tc::k_l3_fwd_tc3, dim3(2 * pairs), dim3(tc::L3C_THREADS), (size_t)tc::L3C_SMEM_BYTES, s, p, wmap);
         profiler().end(s);
         n_css = pairs * tc::L3C_EPI_ROWS;             // partial rows of centred squares: four per CTA pair
         n_s1 = 2 * pairs;                             // partial rows of the sum of a2: one per CTA

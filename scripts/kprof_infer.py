@@ -3,13 +3,17 @@ import collections, os, re, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pointnetgpd_b200 import synth as W
+from pointnetgpd_b200 import _abi as A
+if os.environ.get("PGPD_LIB"):
+    A.LIB_PATH = os.path.abspath(os.environ["PGPD_LIB"])
 from pointnetgpd_b200.model.pointnet import PointNetCls
 B, N, k = int(os.environ.get("B", 4096)), int(os.environ.get("N", 750)), 2
 m = PointNetCls(N, 3, k); m.load_state_dict({kk: torch.tensor(v) for kk, v in W.make_state(0, k=k, style="wild").items()}); m = m.cuda().eval()
 x = torch.tensor(W.make_clouds(5, B, N, "dup")).cuda()
 with torch.no_grad():
-    for _ in range(3): m(x)
+    for _ in range(3): out = m(x)
     torch.cuda.synchronize()
+    print("lib", A.LIB_PATH, "checksum %.6f %.6f" % (float(out[0].double().sum()), float(out[1].double().abs().sum())))
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(3): m(x)

@@ -242,8 +242,8 @@ def test_dual_modules_gpu(what, B, N, k):
     for key in A.dual_param_keys(what):
         g = Fn_resolve(mod, key).grad.cpu().numpy()
         r = rg[key]
-        if np.linalg.norm(r) < 1e-5:       # biases feeding a train-mode BatchNorm: identically zero here
-            assert np.abs(g).max() < 1e-5, key
+        if np.linalg.norm(r) < 1e-5:       # analytically zero (biases in front of a train-mode BatchNorm, a T-Net's bn3.bias): fp32 noise
+            assert np.abs(g).max() < max(1e-4, 20 * float(np.abs(rg32[key]).max())), key
             continue
         assert rel(g, r) < max(2e-3, 20 * rel(rg32[key], r)), key
     for key in A.dual_buffer_keys(what):
