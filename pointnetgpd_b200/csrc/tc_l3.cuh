@@ -119,11 +119,7 @@ constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred sq
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p, const __grid_constant__ CUtensorMap wmap) {
     constexpr int NSUB = L3_STAGES;                        // ring slots
     constexpr int SUB_BYTES = L3_STAGE_BYTES;
-#ifdef PGPD_L3_ACC4
-    constexpr int W_FULL = 0, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 26;   // four accumulators
-#else
     constexpr int W_FULL = 0, W_EMPTY = 12, A2_FULL = 18, A2_EMPTY = 20, TM_FULL = 22, TM_EMPTY = 24;
-#endif
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -148,12 +144,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         for (int i = 0; i < NSUB; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
         mbar_init(BAR(A2_FULL), 16); mbar_init(BAR(A2_FULL + 1), 16);
         mbar_init(BAR(A2_EMPTY), 1); mbar_init(BAR(A2_EMPTY + 1), 1);
-#ifdef PGPD_L3_ACC4
-        for (int i = 0; i < 4; ++i) { mbar_init(BAR(TM_FULL + i), 1); mbar_init(BAR(TM_EMPTY + i), 32); }
-#else
         mbar_init(BAR(TM_FULL), 1); mbar_init(BAR(TM_FULL + 1), 1);
         mbar_init(BAR(TM_EMPTY), 32); mbar_init(BAR(TM_EMPTY + 1), 32);
-#endif
         mbar_fence_init();
     }
     if (tid < 128) {
@@ -199,51 +191,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             int buf = 0; uint32_t bphase = 0;
             long long w_a2 = 0, w_acc = 0, w_w = 0;
             const long long tl0 = p.dbg ? clock64() : 0;
-#ifdef PGPD_L3_ACC4
-            // FOUR accumulators of 128 columns: block b of a tile accumulates its two point halves h = 0, 1 into accumulators
-            // 2*(b&1) + h with MMAs of 256 channels x 128 points; per weight stage the two halves are issued back to back (the weight
-            // ring behaves as with 256-column MMAs), but an accumulator is needed again 1.25 block times after it completes instead
-            // of one block time minus the drain.
-            constexpr uint32_t IDESC4 = idesc_f16(256, 128);
-            int nb = 0;
-            for (int t = T0; t < T1; ++t) {
-                mbar_wait_cluster(BAR(A2_FULL + buf), bphase);
-                tc_fence_after_sync();
-                const uint32_t a2b = sbase + buf * L3C_A2_BUF;
-                for (int mt4 = 0; mt4 < 4; ++mt4, ++nb) {
-                    const int accb = (nb & 1) * 2;
-                    const uint32_t aph4 = (uint32_t)(nb >> 1) & 1u;
-                    for (int kb = 0; kb < 2; ++kb) {
-                        mbar_wait(BAR(W_FULL + stage), wphase);
-                        if (kb == 0) { mbar_wait_cluster(BAR(TM_EMPTY + accb), aph4 ^ 1u); mbar_wait_cluster(BAR(TM_EMPTY + accb + 1), aph4 ^ 1u); }
-                        tc_fence_after_sync();
-                        const uint64_t dw = desc_sw128_kmajor(sbase + L3C_SMEM_W + stage * L3_STAGE_BYTES);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const uint32_t d = tmem + (uint32_t)((accb + h) * 128);
-                                const uint64_t db = desc_sw128_kmajor(a2b + kb * L3C_A2_PART + h * 8192);   // my 64 rows of this half
-#pragma unroll
-                                for (int pass = 0; pass < 3; ++pass) {
-                                    const uint32_t oa = (pass == 1) ? 16384u : 0u;
-                                    const uint32_t ob = (pass == 2) ? OB_LO : 0u;
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        mma_f16_pair(d, dw + ((oa + k * 32) >> 4), db + ((ob + k * 32) >> 4), IDESC4, (kb | pass | k) ? 1u : 0u);
-                                }
-                                if (kb == 1) mma_commit_pair(BAR(TM_FULL + accb + h), (uint16_t)0x3);   // this half is complete in both CTAs
-                            }
-                            mma_commit_pair(BAR(W_EMPTY + stage), (uint16_t)0x3);
-                            if (kb == 1 && mt4 == 3) mma_commit_pair(BAR(A2_EMPTY + buf), (uint16_t)0x3);
-                        }
-                        __syncwarp();
-                        if (++stage == L3_STAGES) { stage = 0; wphase ^= 1u; }
-                    }
-                }
-                if (++buf == 2) { buf = 0; bphase ^= 1; }
-            }
-            (void)acc; (void)aphase; (void)IDESC; (void)w_a2; (void)w_acc; (void)w_w;
-#else
             for (int t = T0; t < T1; ++t) {
                 { const long long _t = p.dbg ? clock64() : 0; mbar_wait_cluster(BAR(A2_FULL + buf), bphase); if (p.dbg) w_a2 += clock64() - _t; }   // both halves staged
                 tc_fence_after_sync();
@@ -277,7 +224,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 }
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
             }
-#endif
             if (p.dbg && lane == 0) {
                 long long* o = p.dbg + (size_t)blockIdx.x * 8;
                 o[0] = w_a2; o[1] = w_acc; o[2] = w_w; o[3] = clock64() - tl0; o[4] = 0; o[5] = 0; o[6] = 0; o[7] = 0;
@@ -291,8 +237,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         const int row = q * 32 + lane;
         const bool stats = p.mu_s != nullptr;
         int acc = 0; uint32_t aphase = 0;
-        int nb = 0;                                         // blocks so far (PGPD_L3_ACC4)
-        (void)acc; (void)aphase; (void)nb;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;      // centred squares of my channel of block mt4 = 0..3, summed over my tiles
         for (int t = T0; t < T1; ++t) {
             const int b = t / p.tiles_per_cloud, tt = t % p.tiles_per_cloud;
@@ -307,22 +251,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 bool released = false;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-#ifdef PGPD_L3_ACC4
-                    // one chunk in each of the block's two accumulators (u = point half); accumulator columns 0-63 are the leader
-                    // CTA's 64 points of the half, 64-127 the peer's
-                    const int a = ((nb & 1) << 1) + u;
-                    const uint32_t aph = (uint32_t)(nb >> 1) & 1u;
-                    const bool first = true, last = true;
-                    const uint32_t col = (uint32_t)(a * 128 + half * 32);
-                    const int pb = (half >> 1) * 128 + u * 64 + (half & 1) * 32;
-                    released = false;
-#else
                     const int a = acc;
                     const uint32_t aph = aphase;
                     const bool first = u == 0, last = u == 1;
                     const uint32_t col = (uint32_t)(acc * L3_NT + half * 64 + u * 32);
                     const int pb = half * 64 + u * 32;
-#endif
                     if (first) { mbar_wait(BAR(TM_FULL + a), aph); tc_fence_after_sync(); }
                     const bool any = pb < nvalid;           // warp-uniform
                     float v[32];
@@ -371,11 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                         }
                     }
                 }
-#ifdef PGPD_L3_ACC4
-                ++nb;
-#else
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
-#endif
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)bidx);
                 atomicMax(&p.keys[(size_t)b * C3 + ch], key);
