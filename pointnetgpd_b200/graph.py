@@ -78,10 +78,26 @@ class GraphedTrainStep:
         loss.backward()
         return loss.detach()
 
+    def staged_input(self):
+        """A `staging.StagedInput` over this step's static inputs: `prefetch((x_host, y_host))` the next batch while a step runs,
+        then `step_staged()`."""
+        from .staging import StagedInput
+        if getattr(self, "_staged", None) is None:
+            self._staged = StagedInput([self.sx, self.sy])
+        return self._staged
+
+    def step_staged(self):
+        """Replay on the batch last handed to `staged_input().prefetch`.  Returns the (static) loss tensor."""
+        self._staged.commit()
+        return self._replay()
+
     def step(self, x, y):
         """x, y: device tensors or pinned host tensors of the captured shapes.  Returns the (static) loss tensor."""
         self.sx.copy_(x, non_blocking=True)
         self.sy.copy_(y, non_blocking=True)
+        return self._replay()
+
+    def _replay(self):
         self.g_main.replay()
         if self.g_opt is not None:
             self.sync.all_reduce()          # eager NCCL all-reduce, in place on the graph's static gradient tensors

@@ -43,3 +43,31 @@ def test_graphed_step_matches_eager_steps():
     for p0, p1 in zip(m0.parameters(), m1.parameters()):
         assert torch.equal(p0, p1)
     assert int(m1.bn1.num_batches_tracked) == int(m0.bn1.num_batches_tracked) == 4
+
+
+def test_staged_input_steps_match_plain_steps():
+    """The prefetching input path (staging.StagedInput: next batch's H2D copy on a side stream while a step runs) feeds the
+    captured step the same batches as the plain path."""
+    B, N, k = 16, 200, 2
+    xs = [torch.tensor(W.make_clouds(991 + i, B, N, "box")).pin_memory() for i in range(5)]
+    ys = [torch.tensor(W.make_labels(995 + i, B, k)).pin_memory() for i in range(5)]
+    losses = []
+    for staged in (False, True):
+        m = _make(N, k)
+        o = torch.optim.Adam(m.parameters(), lr=0.005, fused=True, capturable=True)
+        g = GraphedTrainStep(m, o, xs[0].cuda(), ys[0].cuda(), warmup=3)
+        out = []
+        if staged:
+            st = g.staged_input()
+            st.prefetch((xs[0], ys[0]))
+            for i in range(5):
+                loss = g.step_staged()
+                if i + 1 < 5:
+                    st.prefetch((xs[i + 1], ys[i + 1]))
+                out.append(float(loss.item()))
+        else:
+            for x, y in zip(xs, ys):
+                out.append(float(g.step(x, y).item()))
+        losses.append(out)
+    assert losses[0] == losses[1]
+    assert len(set(losses[0])) > 1
