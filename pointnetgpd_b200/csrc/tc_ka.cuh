@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int sl = __shfl_sync(0xffffffffu, myslot, j);
-                sv[j] = __ldg(sp_c + (size_t)(unsigned)(sl < 0 ? 0 : sl) * C2);   // always a valid row; discarded below if not owned
+                // `own` is the same in every lane: a uniform predicate on the LOAD (not a select on its result, which would make the
+                // thread wait for it here); points without a sparse row -- two out of three -- cost no L2 traffic
+                sv[j] = ((own >> j) & 1u) ? __ldg(sp_c + (size_t)(unsigned)sl * C2) : 0.f;
             }
             int cbn = cb, ttn = tt + 1;
             if (ttn == p.tiles_per_cloud) { ttn = 0; ++cbn; }
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) k_ka_tc(KaParams p) {
             for (int j = 0; j < 16; ++j) {
                 if (nv == KA_NT || j < nj) {
                     const float a = fmaxf(fmaf(sc2, yv[j], sh2), 0.f);      // a2 (same sign decision as the operand tile's)
-                    const float da2 = fmaf(v[j], ninv, ((own >> j) & 1u ? sv[j] : 0.f) - u);
+                    const float da2 = fmaf(v[j], ninv, sv[j] - u);
                     const float dz = a > 0.f ? da2 : 0.f;
 #ifndef PGPD_DIAG_NOSTORE
                     dzo[j * C2] = dz;

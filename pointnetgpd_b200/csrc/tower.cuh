@@ -413,110 +413,158 @@ __global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, con
         }
         __syncthreads();
     }
+    // (W3 Gram)[c][4*lane .. 4*lane+3]: every warp takes 8 of the 128 terms (all loads in flight at once; one warp doing all 128 in
+    // sequence was a 7 us serial tail per block: ncu, profiles/r2) and folds -d * its partial into its gather sum
+    {
+        float4 wg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int jj = 0; jj < C2 / 16; ++jj) {
+            const int j = q * (C2 / 16) + jj;
+            const float wj = s_w[j];
+            const float4 gr = *reinterpret_cast<const float4*>(gram + (size_t)j * C2 + 4 * lane);
+            wg.x = fmaf(wj, gr.x, wg.x); wg.y = fmaf(wj, gr.y, wg.y); wg.z = fmaf(wj, gr.z, wg.z); wg.w = fmaf(wj, gr.w, wg.w);
+        }
+        const float d = dvec[c];
+        acc.x = fmaf(-d, wg.x, acc.x); acc.y = fmaf(-d, wg.y, acc.y); acc.z = fmaf(-d, wg.z, acc.z); acc.w = fmaf(-d, wg.w, acc.w);
+    }
     sh[q][lane] = acc;
     __syncthreads();
     if (q == 0) {
         float4 t = sh[0][lane];
 #pragma unroll
         for (int w = 1; w < 16; ++w) { const float4 u = sh[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
-        // (W3 Gram)[c][4*lane .. 4*lane+3]
-        float4 wg = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int j = 0; j < C2; ++j) {
-            const float wj = s_w[j];
-            const float4 gr = *reinterpret_cast<const float4*>(gram + (size_t)j * C2 + 4 * lane);
-            wg.x = fmaf(wj, gr.x, wg.x); wg.y = fmaf(wj, gr.y, wg.y); wg.z = fmaf(wj, gr.z, wg.z); wg.w = fmaf(wj, gr.w, wg.w);
-        }
-        const float d = dvec[c], e = evec[c];
+        const float e = evec[c];
         float4 o;
-        o.x = t.x - d * wg.x - e * (float)S1[4 * lane + 0];
-        o.y = t.y - d * wg.y - e * (float)S1[4 * lane + 1];
-        o.z = t.z - d * wg.z - e * (float)S1[4 * lane + 2];
-        o.w = t.w - d * wg.w - e * (float)S1[4 * lane + 3];
+        o.x = t.x - e * (float)S1[4 * lane + 0];
+        o.y = t.y - e * (float)S1[4 * lane + 1];
+        o.z = t.z - e * (float)S1[4 * lane + 2];
+        o.w = t.w - e * (float)S1[4 * lane + 3];
         *reinterpret_cast<float4*>(dW3 + (size_t)c * C2 + 4 * lane) = o;
         if (lane == 0 && db3) db3[c] = 0.f;   // bias feeding a train-mode BatchNorm: gradient is identically zero
     }
 }
 
 // sparse part of d a2: rows  sum_{c : argmax(b,c)=p} coef[b][c] W3[c][:]  for the arg-max points of one cloud.
-// block = 1024 threads (one per channel) = one cloud.
-__global__ void k_da2_sparse(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ W3, int N,
+// block = 1024 threads (one per channel) = one cloud.  The (point, channel) pairs are sorted, then the 1024 entries are processed
+// ENTRY-parallel: warp w takes the sorted entries 32w .. 32w+31 (lane = 4 consecutive output channels), loads the W3 rows and
+// coefficients of eight entries at a time (all in flight together) and accumulates runs of equal points in sorted order.  A row that
+// starts in warp w and continues into later warps is finished by warp w, which adds the later warps' "head" partials from shared
+// memory in warp order -- every row is a fixed-order sum, the result is reproducible.  (Round 1 walked the ROWS, one warp per row,
+// one dependent L2 round trip per two entries: 79 us per launch with `long scoreboard` as the top stall; ncu, profiles/r2.)
+__global__ void __launch_bounds__(1024, 1) k_da2_sparse(const float* __restrict__ coef, const int* __restrict__ idx, const float* __restrict__ W3, int N,
                              float* __restrict__ da2s, int* __restrict__ slot) {
     __shared__ unsigned sk[C3];
     __shared__ int scan[2][C3];
     __shared__ int rowpos[C3 + 1];
-    __shared__ int nrows_s;
+    __shared__ float4 headp[32][32];
+    __shared__ int nvalid_s;
     const int b = (int)blockIdx.x, tid = (int)threadIdx.x;
+    // bitonic sort of 1024 keys, one per thread IN A REGISTER: partners less than 32 apart are exchanged by warp shuffle, only the
+    // 15 steps with stride >= 32 go through shared memory (two alternating buffers: one barrier per step instead of the 55 barriers
+    // of the all-shared-memory version)
+    unsigned key;
     {
         const float cf = coef[(size_t)b * C3 + tid];
-        sk[tid] = (cf != 0.f) ? (((unsigned)idx[(size_t)b * C3 + tid] << 10) | (unsigned)tid) : 0xFFFFFFFFu;
+        key = (cf != 0.f) ? (((unsigned)idx[(size_t)b * C3 + tid] << 10) | (unsigned)tid) : 0xFFFFFFFFu;
     }
-    __syncthreads();
-    // bitonic sort of 1024 keys
-    for (int size = 2; size <= C3; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            int partner = tid ^ stride;
-            if (partner > tid) {
-                bool up = ((tid & size) == 0);
-                unsigned a = sk[tid], c = sk[partner];
-                if ((a > c) == up) { sk[tid] = c; sk[partner] = a; }
+    {
+        unsigned* xbuf[2] = {sk, reinterpret_cast<unsigned*>(scan[0])};
+        int xb = 0;
+        for (int size = 2; size <= C3; size <<= 1) {
+            const bool up = ((tid & size) == 0);
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                unsigned other;
+                if (stride >= 32) {
+                    xbuf[xb][tid] = key;
+                    __syncthreads();
+                    other = xbuf[xb][tid ^ stride];
+                    xb ^= 1;
+                } else {
+                    other = __shfl_xor_sync(0xffffffffu, key, stride);
+                }
+                const bool lower = (tid & stride) == 0;         // I hold the lower index of the pair
+                const unsigned mn = key < other ? key : other, mx = key < other ? other : key;
+                key = (lower == up) ? mn : mx;
             }
-            __syncthreads();
         }
+        __syncthreads();                                        // the last readers of the exchange buffers are done
+        sk[tid] = key;
+        __syncthreads();
     }
-    // row starts + inclusive scan
-    const unsigned key = sk[tid];
+    // row starts + inclusive scan: entry e belongs to row incl[e] - 1
     const bool valid = key != 0xFFFFFFFFu;
     const bool start = valid && (tid == 0 || (sk[tid - 1] >> 10) != (key >> 10));
     scan[0][tid] = start ? 1 : 0;
     __syncthreads();
-    int cur = 0;
+    int cb = 0;
     for (int off = 1; off < C3; off <<= 1) {
-        int v = scan[cur][tid];
-        if (tid >= off) v += scan[cur][tid - off];
-        scan[cur ^ 1][tid] = v;
-        cur ^= 1;
+        int v = scan[cb][tid];
+        if (tid >= off) v += scan[cb][tid - off];
+        scan[cb ^ 1][tid] = v;
+        cb ^= 1;
         __syncthreads();
     }
-    const int rowid = scan[cur][tid] - 1;   // for valid entries
-    if (start) rowpos[rowid] = tid;
-    if (tid == C3 - 1) nrows_s = scan[cur][tid];
-    __syncthreads();
-    const int nrows = nrows_s;
+    const int* incl = scan[cb];
+    if (start) rowpos[incl[tid] - 1] = tid;
     if (tid == 0) {
-        // end sentinel: first invalid entry (or 1024)
-        int nvalid = 0;
-        // binary search for the first invalid key (keys are sorted, invalid = max)
-        int lo = 0, hi = C3;
+        int lo = 0, hi = C3;                        // first invalid key (keys are sorted, invalid = max)
         while (lo < hi) { int mid = (lo + hi) >> 1; if (sk[mid] != 0xFFFFFFFFu) lo = mid + 1; else hi = mid; }
-        nvalid = lo;
-        rowpos[nrows] = nvalid;
+        nvalid_s = lo;
     }
     __syncthreads();
-    // one WARP per output row (lane = 4 consecutive channels, float4): 32 independent rows in flight per block.
-    // The entries of a row are summed in ascending channel order (the sort order), so the result is reproducible.
+    const int nvalid = nvalid_s;
     const int wrp = tid >> 5, lane = tid & 31;
+    const int wbeg = wrp * 32, wend = (wbeg + 32 < nvalid) ? wbeg + 32 : nvalid;
     const float4* W3v = reinterpret_cast<const float4*>(W3);
-    for (int r = wrp; r < nrows; r += 32) {
-        const int e0 = rowpos[r], e1 = rowpos[r + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int e = e0;
-        for (; e + 1 < e1; e += 2) {            // two entries per iteration: their loads are independent
-            const int c0 = (int)(sk[e] & 1023u), c1 = (int)(sk[e + 1] & 1023u);
-            const float f0 = coef[(size_t)b * C3 + c0], f1 = coef[(size_t)b * C3 + c1];
-            const float4 w0 = W3v[(size_t)c0 * (C2 / 4) + lane], w1 = W3v[(size_t)c1 * (C2 / 4) + lane];
-            acc.x = fmaf(f0, w0.x, acc.x); acc.y = fmaf(f0, w0.y, acc.y); acc.z = fmaf(f0, w0.z, acc.z); acc.w = fmaf(f0, w0.w, acc.w);
-            acc.x = fmaf(f1, w1.x, acc.x); acc.y = fmaf(f1, w1.y, acc.y); acc.z = fmaf(f1, w1.z, acc.z); acc.w = fmaf(f1, w1.w, acc.w);
-        }
-        if (e < e1) {
-            const int c0 = (int)(sk[e] & 1023u);
-            const float f0 = coef[(size_t)b * C3 + c0];
-            const float4 w0 = W3v[(size_t)c0 * (C2 / 4) + lane];
-            acc.x = fmaf(f0, w0.x, acc.x); acc.y = fmaf(f0, w0.y, acc.y); acc.z = fmaf(f0, w0.z, acc.z); acc.w = fmaf(f0, w0.w, acc.w);
-        }
+    float4* out = reinterpret_cast<float4*>(da2s);
+    auto store_row = [&](int r, const float4& a) {
         const size_t row = (size_t)b * C3 + r;
-        reinterpret_cast<float4*>(da2s)[row * (C2 / 4) + lane] = acc;
-        if (lane == 0) slot[(size_t)b * N + (sk[e0] >> 10)] = (int)row;
+        out[row * (C2 / 4) + lane] = a;
+        if (lane == 0) slot[(size_t)b * N + (sk[rowpos[r]] >> 10)] = (int)row;
+    };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = -1;
+    bool own = false;
+    if (wbeg < wend) {
+        cur = incl[wbeg] - 1;
+        const bool head_open = rowpos[cur] < wbeg;          // my first row began in an earlier warp: its part here is a head partial
+        bool first_row = true;
+        constexpr int U = 8;
+        for (int e0 = wbeg; e0 < wend; e0 += U) {
+            float4 wv[U]; float cf[U]; int rw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u;
+                if (e < wend) {
+                    const int c = (int)(sk[e] & 1023u);
+                    cf[u] = coef[(size_t)b * C3 + c];
+                    wv[u] = W3v[(size_t)c * (C2 / 4) + lane];
+                    rw[u] = incl[e] - 1;
+                } else { cf[u] = 0.f; wv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rw[u] = -1; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (rw[u] < 0) continue;
+                if (rw[u] != cur) {                             // the run of `cur` ends inside my segment
+                    if (first_row && head_open) headp[wrp][lane] = acc; else store_row(cur, acc);
+                    first_row = false;
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cur = rw[u];
+                }
+                acc.x = fmaf(cf[u], wv[u].x, acc.x); acc.y = fmaf(cf[u], wv[u].y, acc.y);
+                acc.z = fmaf(cf[u], wv[u].z, acc.z); acc.w = fmaf(cf[u], wv[u].w, acc.w);
+            }
+        }
+        if (first_row && head_open) headp[wrp][lane] = acc;     // my whole segment lies inside a row that began earlier
+        else own = true;                                        // my last row began in my segment: I finish it
+    }
+    __syncthreads();
+    if (own) {
+        for (int w2 = wrp + 1; w2 < 32 && w2 * 32 < nvalid && incl[w2 * 32] - 1 == cur; ++w2) {
+            const float4 h = headp[w2][lane];
+            acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+        }
+        store_row(cur, acc);
     }
 }
 

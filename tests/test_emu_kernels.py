@@ -129,10 +129,13 @@ def test_odd_shapes_eval(B, N):
     assert np.abs(r["trans"] - trans).max() < LOGP_TOL
 
 
-def test_train_tail_tile_and_duplicates():
-    B, N, k = 4, 150, 2
+@pytest.mark.parametrize("B,N,kind", [(4, 150, "dup"), (3, 2, "box"), (8, 4, "box")])
+def test_train_tail_tile_and_duplicates(B, N, kind):
+    """Tile tails, duplicated points and -- N = 2, 4 -- clouds whose few points each own hundreds of arg-max channels: the rows of
+    the sparse part of d a2 then span many warps of k_da2_sparse (head partials, whole-warp segments inside one row)."""
+    k = 2
     st = W.make_state(41, k=k, style="wild")
-    x = W.make_clouds(42, B, N, "dup")
+    x = W.make_clouds(42, B, N, kind)
     sd64 = PN.cast_state(st, np.float64)
     logp, trans, cache, _ = PN.forward(sd64, x.astype(np.float64), training=True)
     wl = W.normal(43, (B, k))
