@@ -34,7 +34,7 @@ constexpr int FZ_W = FZ_W2 + 16384;                        // W3 ring
 constexpr int FZ_CONST = FZ_W + L3_STAGES * L3_STAGE_BYTES;    // W1 (192), scale1 (64), shift1 (64), s2' (128), h2' (128) floats
 constexpr int FZ_MISC = FZ_CONST + 3072;
 constexpr int FZ_SMEM_BYTES = FZ_MISC + 1024 + 1024;       // + slack to align the base to 1024 B
-constexpr int FZ_THREADS = L3C_THREADS;
+constexpr int FZ_THREADS = 832;                               // W producer, MMA issuer, 16 epilogue, 8 producer warps
 
 struct FusedParams {
     const float* x; const float* trans;       // [B][3][N]; [B][9] or null (identity)

@@ -113,7 +113,11 @@ constexpr int L3C_A2_BUF = 4 * L3C_A2_PART;        // 64 KB
 constexpr int L3C_SMEM_W = 2 * L3C_A2_BUF;         // 128 KB
 constexpr int L3C_SMEM_MISC = L3C_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3C_SMEM_BYTES = L3C_SMEM_MISC + 2048 + 1024;
-constexpr int L3C_THREADS = 832;                   // W producer, MMA issuer, 16 epilogue, 8 a2 producer warps
+#ifndef PGPD_L3_NPROD
+#define PGPD_L3_NPROD 8
+#endif
+constexpr int L3C_NPROD = PGPD_L3_NPROD;           // a2 producer warps (4: 704 threads, 88 registers per thread -- room for both tcgen05.ld of an epilogue warp in flight)
+constexpr int L3C_THREADS = (2 + 16 + L3C_NPROD) * 32;   // W producer, MMA issuer, 16 epilogue, L3C_NPROD a2 producer warps
 constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred squares per tile (one per 64-column quarter)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3_fwd_tc3(L3Params p, const __grid_constant__ CUtensorMap wmap) {
@@ -142,7 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
 
     if (tid == 0) {
         for (int i = 0; i < NSUB; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
-        mbar_init(BAR(A2_FULL), 16); mbar_init(BAR(A2_FULL + 1), 16);
+        mbar_init(BAR(A2_FULL), 2 * L3C_NPROD); mbar_init(BAR(A2_FULL + 1), 2 * L3C_NPROD);
         mbar_init(BAR(A2_EMPTY), 1); mbar_init(BAR(A2_EMPTY + 1), 1);
         mbar_init(BAR(TM_FULL), 1); mbar_init(BAR(TM_FULL + 1), 1);
         mbar_init(BAR(TM_EMPTY), 32); mbar_init(BAR(TM_EMPTY + 1), 32);
@@ -248,27 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 const uint64_t nmu2 = f2_pack(-mu, -mu);
                 float best = -INFINITY; int bidx = 0; float css = 0.f;
                 // my two chunks of 32 columns (points half*64 + u*32 of the tile) of this block's accumulator
-                bool released = false;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int a = acc;
-                    const uint32_t aph = aphase;
-                    const bool first = u == 0, last = u == 1;
-                    const uint32_t col = (uint32_t)(acc * L3_NT + half * 64 + u * 32);
-                    const int pb = half * 64 + u * 32;
-                    if (first) { mbar_wait(BAR(TM_FULL + a), aph); tc_fence_after_sync(); }
-                    const bool any = pb < nvalid;           // warp-uniform
-                    float v[32];
-                    if (any) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + col, v);
-                    if (!released && (last || pb + 32 >= nvalid)) {
-                        // everything I need of this accumulator is in registers: hand it back BEFORE the arithmetic (drain time and MMA
-                        // time per block are nearly equal: every cycle between the last tcgen05.ld and this arrival is on the critical path)
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) { if (leader) mbar_arrive(BAR(TM_EMPTY + a)); else mbar_arrive_cluster(BAR(TM_EMPTY + a), 0u); }
-                        released = true;
-                    }
-                    if (!any) continue;
+                auto chunk = [&](const float (&v)[32], int pb) {
                     if (pb + 32 <= nvalid) {
                         float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
@@ -303,6 +287,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                             }
                         }
                     }
+                };
+                auto release = [&]() {
+                    // everything I need of this accumulator is in registers: hand it back BEFORE the arithmetic (drain time and MMA
+                    // time per block are nearly equal: every cycle between the last tcgen05.ld and this arrival is on the critical path)
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) { if (leader) mbar_arrive(BAR(TM_EMPTY + acc)); else mbar_arrive_cluster(BAR(TM_EMPTY + acc), 0u); }
+                };
+                const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L3_NT + half * 64);
+                const int pb0 = half * 64;
+                mbar_wait(BAR(TM_FULL + acc), aphase);
+                tc_fence_after_sync();
+#if PGPD_L3_NPROD <= 4
+                // 88 registers per thread: BOTH loads in flight, then the hand-back, then the arithmetic on both chunks
+                if (pb0 + 32 < nvalid) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32_issue(tcol, r0);
+                    tmem_ld32_issue(tcol + 32u, r1);
+                    tmem_ld32_wait(r0);
+                    tmem_ld32_wait(r1);
+                    release();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+                    chunk(v, pb0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+                    chunk(v, pb0 + 32);
+                } else
+#endif
+                {
+                    float v[32];
+                    if (pb0 < nvalid) tmem_ld32(tcol, v);
+                    const bool more = pb0 + 32 < nvalid;            // warp-uniform
+                    if (!more) release();
+                    if (pb0 < nvalid) chunk(v, pb0);
+                    if (more) {
+                        tmem_ld32(tcol + 32u, v);
+                        release();
+                        chunk(v, pb0 + 32);
+                    }
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
                 const unsigned long long key = ((unsigned long long)ord_encode(best) << 32) |
@@ -323,7 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
         }
     } else {
         // ===================== a2 producer: my 128 of the tile's 256 points, double-buffered =====================
-        const int wp = warp - 18;                           // 0..7
+        const int wp = warp - 18;                           // 0 .. L3C_NPROD-1
         const int kb = lane >> 4, chunk = (lane & 15) >> 1, half8 = lane & 1;
         const float sc0 = s_scale[4 * lane + 0], sc1 = s_scale[4 * lane + 1], sc2 = s_scale[4 * lane + 2], sc3 = s_scale[4 * lane + 3];
         const float sh0 = s_shift[4 * lane + 0], sh1 = s_shift[4 * lane + 1], sh2 = s_shift[4 * lane + 2], sh3 = s_shift[4 * lane + 3];
@@ -347,17 +372,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             mbar_wait(BAR(A2_EMPTY + buf), bphase ^ 1);     // the MMAs that read this buffer two tiles ago are done
             unsigned char* a2b = smem + buf * L3C_A2_BUF;
             constexpr int U = 8;
-            for (int i0 = 0; i0 < L3C_NH / 8; i0 += U) {
+            for (int i0 = 0; i0 < L3C_NH / L3C_NPROD; i0 += U) {
                 float4 y[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = wp + 8 * (i0 + u);
+                    const int r = wp + L3C_NPROD * (i0 + u);
                     y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < nvalid) y[u] = *reinterpret_cast<const float4*>(src + (size_t)r * C2);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = wp + 8 * (i0 + u);
+                    const int r = wp + L3C_NPROD * (i0 + u);
                     const bool ok = r < nvalid;
                     // relu that keeps NaN; values beyond the fp16 operand range (or NaN) flag the cloud (its pooled feature
                     // becomes NaN in k_tail_l3) instead of being clamped silently
@@ -397,13 +422,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
             float* red = reinterpret_cast<float*>(smem);
             float* o = red + wp * C2 + 4 * lane;
             o[0] = sa0; o[1] = sa1; o[2] = sa2; o[3] = sa3;
-            named_bar_sync(3, 256);
+            named_bar_sync(3, L3C_NPROD * 32);
             if (wp == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float t = red[4 * lane + i];
 #pragma unroll
-                    for (int w2 = 1; w2 < 8; ++w2) t += red[w2 * C2 + 4 * lane + i];
+                    for (int w2 = 1; w2 < L3C_NPROD; ++w2) t += red[w2 * C2 + 4 * lane + i];
                     p.s1_part[(size_t)blockIdx.x * C2 + 4 * lane + i] = t;
                 }
             }
