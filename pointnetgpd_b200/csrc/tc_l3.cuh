@@ -113,10 +113,8 @@ constexpr int L3C_A2_BUF = 4 * L3C_A2_PART;        // 64 KB
 constexpr int L3C_SMEM_W = 2 * L3C_A2_BUF;         // 128 KB
 constexpr int L3C_SMEM_MISC = L3C_SMEM_W + L3_STAGES * L3_STAGE_BYTES;
 constexpr int L3C_SMEM_BYTES = L3C_SMEM_MISC + 2048 + 1024;
-#ifndef PGPD_L3_NPROD
-#define PGPD_L3_NPROD 8
-#endif
-constexpr int L3C_NPROD = PGPD_L3_NPROD;           // a2 producer warps (4: 704 threads, 88 registers per thread -- room for both tcgen05.ld of an epilogue warp in flight)
+constexpr int L3C_NPROD = 8;                       // a2 producer warps (measured with 4 / 2 and both tcgen05.ld of an epilogue warp in flight: the
+                                                   // register allocator still spills at 80 / 96 registers, 2.6-2.9x slower; profiles/r2)
 constexpr int L3C_THREADS = (2 + 16 + L3C_NPROD) * 32;   // W producer, MMA issuer, 16 epilogue, L3C_NPROD a2 producer warps
 constexpr int L3C_EPI_ROWS = 4;                    // partial rows of centred squares per tile (one per 64-column quarter)
 
@@ -299,24 +297,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L3C_THREADS, 1) k_l3
                 const int pb0 = half * 64;
                 mbar_wait(BAR(TM_FULL + acc), aphase);
                 tc_fence_after_sync();
-#if PGPD_L3_NPROD <= 4
-                // 88 registers per thread: BOTH loads in flight, then the hand-back, then the arithmetic on both chunks
-                if (pb0 + 32 < nvalid) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32_issue(tcol, r0);
-                    tmem_ld32_issue(tcol + 32u, r1);
-                    tmem_ld32_wait(r0);
-                    tmem_ld32_wait(r1);
-                    release();
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-                    chunk(v, pb0);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
-                    chunk(v, pb0 + 32);
-                } else
-#endif
                 {
                     float v[32];
                     if (pb0 < nvalid) tmem_ld32(tcol, v);
