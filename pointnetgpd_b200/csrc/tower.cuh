@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(512) k_dw3(const float* __restrict__ coef, con
         // stage this channel's coefficients / arg-max indices first, so the row loads below are independent
         if (tid < nb) { s_cf[tid] = coef[(size_t)(b0 + tid) * C3 + c]; s_ix[tid] = idx[(size_t)(b0 + tid) * C3 + c]; }
         __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
         for (int bb = q; bb < nb; bb += 16) {
             const float cf = s_cf[bb];
             const size_t P = (size_t)(b0 + bb) * N + s_ix[bb];
